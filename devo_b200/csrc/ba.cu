@@ -1,0 +1,706 @@
+// ba.cu -- in-place Gauss-Newton bundle adjustment (cuda_ba.forward), reprojection
+// (cuda_ba.reproject) and the fused projective transform (projective_ops.transform).
+//
+// Reference behaviour: devo/fastba/ba_cuda.cu:214-365 (per-edge residuals/Jacobians, ~340
+// global float atomics per edge into B,E,C,v,u), :461-537 (~20 ATen launches per iteration:
+// Schur complement via cuBLAS, cuSOLVER potrf with a host sync, back-substitution),
+// :160-211 (retractions).  Same normal equations here, organised for B200:
+//
+//   plan   (graph_plan.cu, 1 launch)   edges grouped by patch: perm / gstart / gkey
+//   accum  (1 launch per iteration)    CTA c owns a contiguous range of patches.  Per-edge
+//                                      Jacobians in fp32 with the reference's formulas; each
+//                                      residual row is the sparse vector g = [-Ji @ i', +Jj @ j']
+//                                      (so B = sum w g g^T, v = sum w r g, E_k = sum w Jz g).
+//                                      Rows + the per-patch vectors E_k (coefficient -Q_k) are
+//                                      staged densely in shared memory (fp64) and the CTA's
+//                                      partial of the *reduced* system  S = B - E Q E^T,
+//                                      y = v - E Q u  is accumulated in registers, one fixed
+//                                      set of matrix entries per thread, fixed summation order:
+//                                      no atomics at all, bitwise reproducible.
+//   solve  (1 launch per iteration)    one CTA: fixed-order reduction of the partials, damping,
+//                                      in-smem fp64 Cholesky + triangular solves, SE3 retraction.
+//   depth update                       dZ_k = Q_k (u_k - E_k . dX); fused into the prologue of the
+//                                      next iteration's accum launch (same patch ownership).
+//
+// => 2*iterations+2 launches, no host sync, no global atomics, CUDA-graph capturable.
+// Deliberate deviations from the reference (documented in DESIGN.md):
+//   * the 6N x 6N system is accumulated and solved in fp64 (the reference: fp32 atomics,
+//     run-to-run non-deterministic); inputs/outputs and per-edge Jacobians stay fp32.
+//   * an edge that is masked out contributes exactly zero (the reference multiplies by a 0
+//     weight, which turns Z==0 into NaN: ba_cuda.cu:268-281).
+//   * pose block indices >= t1 are treated as fixed (the reference would write out of bounds).
+//   * a non-positive-definite system sets *status = iteration+1 and skips the remaining
+//     iterations instead of throwing from inside the launch sequence.
+#include "common.cuh"
+
+extern "C" size_t devo_graph_plan_workspace(int E);
+
+namespace {
+
+constexpr int kAccThreads = 256;
+constexpr int kSolveThreads = 1024;
+constexpr int kMaxN6 = 150;            // 25 free poses
+constexpr size_t kAccSmemBudget = 200 * 1024;
+
+// ---- fastba's own SE3 helpers (un-normalised quaternions; ba_cuda.cu:18-156) ----------------
+__device__ __forceinline__ void rot(const float* q, const float* X, float* Y) {
+  float uv0 = 2.0f * (q[1] * X[2] - q[2] * X[1]);
+  float uv1 = 2.0f * (q[2] * X[0] - q[0] * X[2]);
+  float uv2 = 2.0f * (q[0] * X[1] - q[1] * X[0]);
+  Y[0] = X[0] + q[3] * uv0 + (q[1] * uv2 - q[2] * uv1);
+  Y[1] = X[1] + q[3] * uv1 + (q[2] * uv0 - q[0] * uv2);
+  Y[2] = X[2] + q[3] * uv2 + (q[0] * uv1 - q[1] * uv0);
+}
+// Gij = Gj * Gi^-1 without renormalisation
+__device__ __forceinline__ void rel_pose(const float* Pi, const float* Pj, float* tij, float* qij) {
+  const float* ti = Pi; const float* qi = Pi + 3;
+  const float* tj = Pj; const float* qj = Pj + 3;
+  qij[0] = -qj[3] * qi[0] + qj[0] * qi[3] - qj[1] * qi[2] + qj[2] * qi[1];
+  qij[1] = -qj[3] * qi[1] + qj[1] * qi[3] - qj[2] * qi[0] + qj[0] * qi[2];
+  qij[2] = -qj[3] * qi[2] + qj[2] * qi[3] - qj[0] * qi[1] + qj[1] * qi[0];
+  qij[3] = qj[3] * qi[3] + qj[0] * qi[0] + qj[1] * qi[1] + qj[2] * qi[2];
+  float r[3];
+  rot(qij, ti, r);
+  tij[0] = tj[0] - r[0]; tij[1] = tj[1] - r[1]; tij[2] = tj[2] - r[2];
+}
+// Y = Ad(G)^T X
+__device__ __forceinline__ void adjT(const float* t, const float* q, const float* X, float* Y) {
+  float qinv[4] = {-q[0], -q[1], -q[2], q[3]};
+  rot(qinv, X, Y);
+  rot(qinv, X + 3, Y + 3);
+  float u[3] = {t[2] * X[1] - t[1] * X[2], t[0] * X[2] - t[2] * X[0], t[1] * X[0] - t[0] * X[1]};
+  float v[3];
+  rot(qinv, u, v);
+  Y[3] += v[0]; Y[4] += v[1]; Y[5] += v[2];
+}
+__device__ __forceinline__ void exp_se3(const float* xi, float* t, float* q) {
+  const float* phi = xi + 3;
+  float theta_sq = phi[0] * phi[0] + phi[1] * phi[1] + phi[2] * phi[2];
+  float theta_p4 = theta_sq * theta_sq;
+  float theta = sqrtf(theta_sq);
+  float imag, real;
+  if (theta_sq < 1e-8) {   // double literals on purpose: the reference evaluates these series in double
+    imag = (float)(0.5 - (1.0 / 48.0) * theta_sq + (1.0 / 3840.0) * theta_p4);
+    real = (float)(1.0 - (1.0 / 8.0) * theta_sq + (1.0 / 384.0) * theta_p4);
+  } else {
+    imag = sinf(0.5f * theta) / theta;
+    real = cosf(0.5f * theta);
+  }
+  q[0] = imag * phi[0]; q[1] = imag * phi[1]; q[2] = imag * phi[2]; q[3] = real;
+  float tau[3] = {xi[0], xi[1], xi[2]};
+  t[0] = tau[0]; t[1] = tau[1]; t[2] = tau[2];
+  if (theta > 1e-4) {
+    float a = (1 - cosf(theta)) / theta_sq;
+    float c[3] = {phi[1] * tau[2] - phi[2] * tau[1], phi[2] * tau[0] - phi[0] * tau[2], phi[0] * tau[1] - phi[1] * tau[0]};
+    t[0] += a * c[0]; t[1] += a * c[1]; t[2] += a * c[2];
+    float b = (theta - sinf(theta)) / (theta * theta_sq);
+    float c2[3] = {phi[1] * c[2] - phi[2] * c[1], phi[2] * c[0] - phi[0] * c[2], phi[0] * c[1] - phi[1] * c[0]};
+    t[0] += b * c2[0]; t[1] += b * c2[1]; t[2] += b * c2[2];
+  }
+}
+// T <- Exp(xi) * T
+__device__ __forceinline__ void retract_pose(const float* xi, float* P) {
+  float dt[3], dq[4];
+  exp_se3(xi, dt, dq);
+  const float* q = P + 3;
+  float q1[4];
+  q1[0] = dq[3] * q[0] + dq[0] * q[3] + dq[1] * q[2] - dq[2] * q[1];
+  q1[1] = dq[3] * q[1] + dq[1] * q[3] + dq[2] * q[0] - dq[0] * q[2];
+  q1[2] = dq[3] * q[2] + dq[2] * q[3] + dq[0] * q[1] - dq[1] * q[0];
+  q1[3] = dq[3] * q[3] - dq[0] * q[0] - dq[1] * q[1] - dq[2] * q[2];
+  float t1[3];
+  rot(dq, P, t1);
+  P[0] = t1[0] + dt[0]; P[1] = t1[1] + dt[1]; P[2] = t1[2] + dt[2];
+  P[3] = q1[0]; P[4] = q1[1]; P[5] = q1[2]; P[6] = q1[3];
+}
+
+struct EdgeTerms {
+  float r[2], w[2], Jz[2];
+  float Ji[2][6], Jj[2][6];
+  bool active;
+};
+
+// reprojection_residuals_and_hessian :240-332, one edge
+__device__ __forceinline__ void edge_terms(const float* __restrict__ poses, const float* __restrict__ patches,
+                                           float fx, float fy, float cx, float cy,
+                                           const float* __restrict__ target, const float* __restrict__ weight,
+                                           int i, int j, int k, int n, int PP, int centre, EdgeTerms& T) {
+  float Pi[7], Pj[7];
+#pragma unroll
+  for (int c = 0; c < 7; c++) { Pi[c] = poses[(size_t)i * 7 + c]; Pj[c] = poses[(size_t)j * 7 + c]; }
+  const float* pk = patches + (size_t)k * 3 * PP;
+  float Xi[3] = {(pk[centre] - cx) / fx, (pk[PP + centre] - cy) / fy, 1.0f};
+  const float dinv = pk[2 * PP + centre];
+  float tij[3], qij[4], Xj[3];
+  rel_pose(Pi, Pj, tij, qij);
+  rot(qij, Xi, Xj);
+  Xj[0] += dinv * tij[0]; Xj[1] += dinv * tij[1]; Xj[2] += dinv * tij[2];
+  const float X = Xj[0], Y = Xj[1], Z = Xj[2], W = dinv;
+  const float d = (Z >= 0.2f) ? 1.0f / Z : 0.0f;
+  const float d2 = d * d;
+  const float x1 = fx * (X / Z) + cx;
+  const float y1 = fy * (Y / Z) + cy;
+  const float rx = target[(size_t)n * 2 + 0] - x1;
+  const float ry = target[(size_t)n * 2 + 1] - y1;
+  const bool inb = (sqrtf(rx * rx + ry * ry) < 128) && (Z > 0.2f) && (x1 > -64) && (y1 > -64) &&
+                   (x1 < 2 * cx + 64) && (y1 < 2 * cy + 64);
+  T.active = inb;
+  T.r[0] = rx; T.r[1] = ry;
+  T.w[0] = inb ? weight[(size_t)n * 2 + 0] : 0.0f;
+  T.w[1] = inb ? weight[(size_t)n * 2 + 1] : 0.0f;
+  T.Jz[0] = fx * (tij[0] * d - tij[2] * (X * d2));
+  T.Jz[1] = fy * (tij[1] * d - tij[2] * (Y * d2));
+  T.Jj[0][0] = fx * W * d; T.Jj[0][1] = 0; T.Jj[0][2] = fx * -X * W * d2;
+  T.Jj[0][3] = fx * -X * Y * d2; T.Jj[0][4] = fx * (1 + X * X * d2); T.Jj[0][5] = fx * -Y * d;
+  T.Jj[1][0] = 0; T.Jj[1][1] = fy * W * d; T.Jj[1][2] = fy * -Y * W * d2;
+  T.Jj[1][3] = fy * (-1 - Y * Y * d2); T.Jj[1][4] = fy * (X * Y * d2); T.Jj[1][5] = fy * X * d;
+  adjT(tij, qij, T.Jj[0], T.Ji[0]);
+  adjT(tij, qij, T.Jj[1], T.Ji[1]);
+}
+
+// ---- workspace ------------------------------------------------------------------------------
+struct BaLayout {
+  size_t perm, gstart, gkey, ngroups, plan_ws, plan_bytes, Q, U, Ek, partials, dX, total;
+  int grid, nent, n6;
+};
+static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static int acc_grid(int E) {
+  int g = (E + 127) / 128;
+  if (g < 1) g = 1;
+  if (g > 148) g = 148;
+  return g;
+}
+
+static BaLayout ba_layout(int E, int nfree) {
+  BaLayout L;
+  const int n6 = 6 * (nfree > 0 ? nfree : 0);
+  L.n6 = n6;
+  L.nent = (n6 + 1) * (n6 + 2) / 2;
+  L.grid = acc_grid(E);
+  size_t off = 0;
+  const size_t Em = (size_t)(E > 0 ? E : 1);
+  L.perm = off;    off += al(Em * 4);
+  L.gstart = off;  off += al((Em + 1) * 4);
+  L.gkey = off;    off += al(Em * 8);
+  L.ngroups = off; off += al(16);
+  L.plan_bytes = devo_graph_plan_workspace(E);
+  L.plan_ws = off; off += al(L.plan_bytes);
+  L.Q = off;       off += al(Em * 8);
+  L.U = off;       off += al(Em * 8);
+  L.Ek = off;      off += al(Em * (size_t)(n6 > 0 ? n6 : 1) * 8);
+  L.partials = off; off += al((size_t)L.grid * L.nent * 8);
+  L.dX = off;      off += al((size_t)(n6 > 0 ? n6 : 1) * 8);
+  L.total = off;
+  return L;
+}
+
+// upper-triangular (row-major, a<=b) linear index -> (a,b) for an m x m matrix
+__device__ __forceinline__ void tri_decode(int idx, int m, int& a, int& b) {
+  // row a starts at a*m - a*(a-1)/2
+  float fm = (float)(2 * m + 1);
+  int aa = (int)floorf((fm - sqrtf(fm * fm - 8.0f * (float)idx)) * 0.5f);
+  if (aa < 0) aa = 0;
+  if (aa > m - 1) aa = m - 1;
+  while (aa > 0 && aa * m - aa * (aa - 1) / 2 > idx) aa--;
+  while (aa + 1 < m && (aa + 1) * m - (aa + 1) * aa / 2 <= idx) aa++;
+  a = aa;
+  b = idx - (aa * m - aa * (aa - 1) / 2) + aa;
+}
+
+// ---- accumulate kernel ----------------------------------------------------------------------
+// smem: X[R][LD] doubles, coef[R] doubles, zj[R] doubles (Jz per row), batch bookkeeping
+template <int EPT>
+__global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
+    float* __restrict__ poses_rw, float* __restrict__ patches, const float* __restrict__ intrinsics,
+    const float* __restrict__ target, const float* __restrict__ weight, const float* __restrict__ lmbda,
+    const int64_t* __restrict__ ii, const int64_t* __restrict__ jj, const int64_t* __restrict__ kk,
+    const int32_t* __restrict__ perm, const int32_t* __restrict__ gstart, const int64_t* __restrict__ gkey,
+    const int32_t* __restrict__ ngroups_p,
+    double* __restrict__ Qg, double* __restrict__ Ug, double* __restrict__ Ekg,
+    double* __restrict__ partials, const double* __restrict__ dX,
+    int32_t* __restrict__ status, int E, int PP, int centre, int t0, int nfree, int n_poses,
+    int EB, int GB, int apply_update, int do_accumulate, int itr) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const float* poses = poses_rw;
+  const int n6 = 6 * nfree;
+  const int LD = n6 + 1;
+  const int RCAP = 2 * EB + GB;
+  double* X = reinterpret_cast<double*>(smem_raw);
+  double* coef = X + (size_t)RCAP * LD;
+  double* zj = coef + RCAP;
+  __shared__ int s_batch[3];   // gs, ge, bad
+  __shared__ float s_intr[4];
+
+  const int tid = threadIdx.x;
+  const int st = *status;
+  if (st != 0) {               // an earlier iteration failed: do nothing (reference would have thrown)
+    if (do_accumulate) {
+      const int nent = (n6 + 1) * (n6 + 2) / 2;
+      for (int q = tid; q < nent; q += kAccThreads) partials[(size_t)blockIdx.x * nent + q] = 0.0;
+    }
+    return;
+  }
+  if (tid < 4) s_intr[tid] = intrinsics[tid];   // only intrinsics[0] is used (:232-238)
+  const int G = *ngroups_p;
+  const int gpc = (G + gridDim.x - 1) / gridDim.x;
+  const int g0 = blockIdx.x * gpc;
+  const int g1 = min(G, g0 + gpc);
+  const float lm = lmbda[0];
+  const int nent = (n6 + 1) * (n6 + 2) / 2;
+
+  // ---- prologue: apply the previous iteration's depth update to the patches this CTA owns
+  if (apply_update) {
+    for (int g = g0 + tid; g < g1; g += kAccThreads) {
+      double acc = Ug[g];
+      const double* ek = Ekg + (size_t)g * (n6 > 0 ? n6 : 1);
+      for (int c = 0; c < n6; c++) acc -= ek[c] * dX[c];
+      const float dz = (float)(Qg[g] * acc);
+      float* pk = patches + (size_t)gkey[g] * 3 * PP + 2 * PP;
+      float d = pk[0];
+      d = d + dz;
+      d = (d > 20) ? 1.0f : d;
+      d = fmaxf(d, 1e-4f);
+      for (int c = 0; c < PP; c++) pk[c] = d;
+    }
+  }
+  if (!do_accumulate) return;
+  __syncthreads();   // depth updates of this CTA's patches are visible to its own threads; s_intr ready
+  const float fx = s_intr[0], fy = s_intr[1], cx = s_intr[2], cy = s_intr[3];
+
+  // entries owned by this thread
+  double acc[EPT];
+  unsigned int ab[EPT];
+#pragma unroll
+  for (int q = 0; q < EPT; q++) {
+    acc[q] = 0.0;
+    int idx = tid + q * kAccThreads;
+    int a = 0, b = 0;
+    if (idx < nent) tri_decode(idx, LD, a, b);
+    ab[q] = ((unsigned)a << 16) | (unsigned)b;
+  }
+
+  int gs = g0;
+  while (gs < g1) {
+    // ---- choose a batch of whole groups: <= EB edges, <= GB groups
+    if (tid == 0) {
+      const int base = gstart[gs];
+      int ge = gs;
+      while (ge < g1 && (ge - gs) < GB && (gstart[ge + 1] - base) <= EB) ge++;
+      s_batch[0] = gs; s_batch[1] = ge; s_batch[2] = (ge == gs);
+    }
+    __syncthreads();
+    const int ge = s_batch[1];
+    if (s_batch[2]) {        // a single patch has more edges than a batch can hold
+      if (tid == 0) atomicCAS(status, 0, DEVO_ECAPACITY);
+      break;
+    }
+    const int ebase = gstart[gs];
+    const int ne = gstart[ge] - ebase;
+    const int ng = ge - gs;
+    const int R = 2 * ne + ng;
+
+    // zero the dense rows
+    for (int q = tid; q < R * LD; q += kAccThreads) X[q] = 0.0;
+    __syncthreads();
+
+    // ---- one thread per edge: Jacobians -> two dense rows
+    if (tid < ne) {
+      const int n = perm[ebase + tid];
+      const int i = (int)ii[n], j = (int)jj[n], k = (int)kk[n];
+      EdgeTerms T;
+      edge_terms(poses, patches, fx, fy, cx, cy, target, weight, i, j, k, n, PP, centre, T);
+      const int bi = i - t0, bj = j - t0;
+      const bool fi = (bi >= 0 && bi < nfree), fj = (bj >= 0 && bj < nfree);
+#pragma unroll
+      for (int rho = 0; rho < 2; rho++) {
+        const int r = 2 * tid + rho;
+        double* row = X + (size_t)r * LD;
+        const bool on = T.active;
+        if (on) {
+          if (fi) {
+#pragma unroll
+            for (int c = 0; c < 6; c++) row[6 * bi + c] -= (double)T.Ji[rho][c];
+          }
+          if (fj) {
+#pragma unroll
+            for (int c = 0; c < 6; c++) row[6 * bj + c] += (double)T.Jj[rho][c];
+          }
+          row[n6] = (double)T.r[rho];
+        }
+        coef[r] = on ? (double)T.w[rho] : 0.0;
+        zj[r] = on ? (double)T.Jz[rho] : 0.0;
+      }
+    }
+    __syncthreads();
+
+    // ---- per patch: C_k, u_k, Q_k and the dense vector E_k (one warp per patch, lanes over columns)
+    {
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int gi = warp; gi < ng; gi += kAccThreads / 32) {
+        const int g = gs + gi;
+        const int r0 = 2 * (gstart[g] - ebase), r1 = 2 * (gstart[g + 1] - ebase);
+        double C = 0.0, u = 0.0;
+        for (int r = r0; r < r1; r++) {
+          const double wz = coef[r] * zj[r];
+          C += wz * zj[r];
+          u += wz * X[(size_t)r * LD + n6];
+        }
+        const double Q = 1.0 / (C + (double)lm);
+        double* erow = X + (size_t)(2 * ne + gi) * LD;
+        for (int c = lane; c < n6; c += 32) {
+          double e = 0.0;
+          for (int r = r0; r < r1; r++) e += coef[r] * zj[r] * X[(size_t)r * LD + c];
+          erow[c] = e;
+          Ekg[(size_t)g * n6 + c] = e;
+        }
+        if (lane == 0) {
+          erow[n6] = u;
+          coef[2 * ne + gi] = -Q;
+          Qg[g] = Q;
+          Ug[g] = u;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- reduced-system partial: acc(a,b) += coef_r * X[r][a] * X[r][b]
+    for (int r = 0; r < R; r++) {
+      const double c = coef[r];
+      if (c == 0.0) continue;            // block-uniform branch
+      const double* row = X + (size_t)r * LD;
+#pragma unroll
+      for (int q = 0; q < EPT; q++) {
+        const int a = ab[q] >> 16, b = ab[q] & 0xffff;
+        acc[q] += c * row[a] * row[b];
+      }
+    }
+    __syncthreads();
+    gs = ge;
+  }
+
+#pragma unroll
+  for (int q = 0; q < EPT; q++) {
+    int idx = tid + q * kAccThreads;
+    if (idx < nent) partials[(size_t)blockIdx.x * nent + idx] = acc[q];
+  }
+  (void)n_poses; (void)itr; (void)E;
+}
+
+// ---- solve kernel ---------------------------------------------------------------------------
+// smem: L packed lower-triangular n6(n6+1)/2 doubles, y[n6] doubles
+__global__ void __launch_bounds__(kSolveThreads, 1) ba_solve_kernel(
+    float* __restrict__ poses, const double* __restrict__ partials, double* __restrict__ dX,
+    int32_t* __restrict__ status, int nparts, int t0, int nfree, int itr) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = 6 * nfree;
+  const int LD = n + 1;
+  const int nent = (n + 1) * (n + 2) / 2;
+  double* L = reinterpret_cast<double*>(smem_raw);       // L(i,j) at i(i+1)/2 + j, j<=i
+  double* y = L + (size_t)n * (n + 1) / 2;
+  __shared__ int s_fail;
+  const int tid = threadIdx.x;
+  if (*status != 0) return;
+  if (n == 0) return;
+  if (tid == 0) s_fail = 0;
+
+  // fixed-order reduction of the per-CTA partials; entry (a,b), a<=b of the (n+1)x(n+1) augmented matrix
+  for (int idx = tid; idx < nent; idx += kSolveThreads) {
+    double s = 0.0;
+    for (int p = 0; p < nparts; p++) s += partials[(size_t)p * nent + idx];
+    int a, b;
+    tri_decode(idx, LD, a, b);
+    if (b == n) {
+      if (a < n) y[a] = s;                                // y = v - E Q u
+    } else {
+      if (a == b) s += 1e-4 * s + 1.0;                    // S += I o (1e-4 S + 1)   (:517-518)
+      L[(size_t)b * (b + 1) / 2 + a] = s;                 // symmetric: store as lower (b,a)
+    }
+  }
+  __syncthreads();
+
+  // right-looking Cholesky, in place
+  for (int k = 0; k < n; k++) {
+    const double akk = L[(size_t)k * (k + 1) / 2 + k];
+    if (!(akk > 0.0) || !isfinite(akk)) {                // uniform: every thread reads the same value
+      if (tid == 0) { s_fail = 1; }
+      break;
+    }
+    const double dk = sqrt(akk);
+    __syncthreads();                                      // everyone has read akk
+    for (int i = k + tid; i < n; i += kSolveThreads) {
+      double* p = &L[(size_t)i * (i + 1) / 2 + k];
+      *p = (i == k) ? dk : (*p / dk);
+    }
+    __syncthreads();
+    const int m = n - k - 1;                              // trailing size
+    const int cnt = m * (m + 1) / 2;
+    for (int q = tid; q < cnt; q += kSolveThreads) {
+      // (i,j) lower-tri of trailing block, i>=j
+      int i = (int)floorf((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
+      while (i * (i + 1) / 2 > q) i--;
+      while ((i + 1) * (i + 2) / 2 <= q) i++;
+      const int j = q - i * (i + 1) / 2;
+      const int gi = k + 1 + i, gj = k + 1 + j;
+      L[(size_t)gi * (gi + 1) / 2 + gj] -= L[(size_t)gi * (gi + 1) / 2 + k] * L[(size_t)gj * (gj + 1) / 2 + k];
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (s_fail) {
+    if (tid == 0) atomicCAS(status, 0, itr + 1);
+    return;
+  }
+  // forward substitution  L z = y
+  for (int k = 0; k < n; k++) {
+    const double zk = y[k] / L[(size_t)k * (k + 1) / 2 + k];
+    __syncthreads();
+    for (int i = k + 1 + tid; i < n; i += kSolveThreads) y[i] -= L[(size_t)i * (i + 1) / 2 + k] * zk;
+    if (tid == 0) y[k] = zk;
+    __syncthreads();
+  }
+  // backward substitution  L^T x = z
+  for (int k = n - 1; k >= 0; k--) {
+    const double xk = y[k] / L[(size_t)k * (k + 1) / 2 + k];
+    __syncthreads();
+    for (int i = tid; i < k; i += kSolveThreads) y[i] -= L[(size_t)k * (k + 1) / 2 + i] * xk;
+    if (tid == 0) y[k] = xk;
+    __syncthreads();
+  }
+  bool bad = false;
+  for (int i = tid; i < n; i += kSolveThreads) {
+    dX[i] = y[i];
+    if (!isfinite(y[i])) bad = true;
+  }
+  if (__syncthreads_or(bad)) {
+    if (tid == 0) atomicCAS(status, 0, itr + 1);
+    return;
+  }
+  // pose retraction  T <- Exp(dX) T   (:160-188)
+  for (int p = tid; p < nfree; p += kSolveThreads) {
+    float xi[6], P[7];
+#pragma unroll
+    for (int c = 0; c < 6; c++) xi[c] = (float)y[6 * p + c];
+    float* dst = poses + (size_t)(t0 + p) * 7;
+#pragma unroll
+    for (int c = 0; c < 7; c++) P[c] = dst[c];
+    retract_pose(xi, P);
+#pragma unroll
+    for (int c = 0; c < 7; c++) dst[c] = P[c];
+  }
+}
+
+// ---- reproject (:368-418) ---------------------------------------------------------------------
+__global__ void reproject_kernel(const float* __restrict__ poses, const float* __restrict__ patches,
+                                 const float* __restrict__ intrinsics, const int64_t* __restrict__ ii,
+                                 const int64_t* __restrict__ jj, const int64_t* __restrict__ kk,
+                                 float* __restrict__ coords, int E, int PP) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= E * PP) return;
+  const int n = t / PP, p = t - n * PP;
+  const float fx = intrinsics[0], fy = intrinsics[1], cx = intrinsics[2], cy = intrinsics[3];
+  const int i = (int)ii[n], j = (int)jj[n], k = (int)kk[n];
+  float Pi[7], Pj[7];
+#pragma unroll
+  for (int c = 0; c < 7; c++) { Pi[c] = poses[(size_t)i * 7 + c]; Pj[c] = poses[(size_t)j * 7 + c]; }
+  float tij[3], qij[4];
+  rel_pose(Pi, Pj, tij, qij);
+  const float* pk = patches + (size_t)k * 3 * PP;
+  float Xi[3] = {(pk[p] - cx) / fx, (pk[PP + p] - cy) / fy, 1.0f};
+  const float d = pk[2 * PP + p];
+  float Xj[3];
+  rot(qij, Xi, Xj);
+  Xj[0] += d * tij[0]; Xj[1] += d * tij[1]; Xj[2] += d * tij[2];
+  coords[(size_t)n * 2 * PP + p] = fx * (Xj[0] / Xj[2]) + cx;
+  coords[(size_t)n * 2 * PP + PP + p] = fy * (Xj[1] / Xj[2]) + cy;
+}
+
+}  // namespace
+
+// =============================================================================================
+#include "lie.cuh"
+namespace {
+// fused projective_ops.transform forward (devo/projective_ops.py:53-105), lietorch semantics
+// (quaternions renormalised on every construction), one thread per (edge, pixel)
+__global__ void transform_kernel(const float* __restrict__ poses, const float* __restrict__ patches,
+                                 const float* __restrict__ intrinsics, const int64_t* __restrict__ ii,
+                                 const int64_t* __restrict__ jj, const int64_t* __restrict__ kk,
+                                 float* __restrict__ coords, float* __restrict__ valid, float* __restrict__ Ji_o,
+                                 float* __restrict__ Jj_o, float* __restrict__ Jz_o, int E, int P, int layout, int tonly) {
+  const int PP = P * P;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= E * PP) return;
+  const int n = t / PP, p = t - n * PP;
+  const int i = (int)ii[n], j = (int)jj[n], k = (int)kk[n];
+  float di[7], dj[7];
+#pragma unroll
+  for (int c = 0; c < 7; c++) { di[c] = poses[(size_t)i * 7 + c]; dj[c] = poses[(size_t)j * 7 + c]; }
+  lie::SE3<float> Gi = lie::SE3<float>::load(di), Gj = lie::SE3<float>::load(dj);
+  lie::SE3<float> Gij = Gj * Gi.inv();
+  if (tonly) { Gij.R.q = lie::Quat<float>{0.f, 0.f, 0.f, 1.f}; }
+  const float* Ki = intrinsics + (size_t)i * 4;
+  const float* Kj = intrinsics + (size_t)j * 4;
+  const float* pk = patches + (size_t)k * 3 * PP;
+  float X0[4] = {(pk[p] - Ki[2]) / Ki[0], (pk[PP + p] - Ki[3]) / Ki[1], 1.0f, pk[2 * PP + p]};
+  float X1[4];
+  Gij.act4(X0, X1);
+  const float fx = Kj[0], fy = Kj[1], cx = Kj[2], cy = Kj[3];
+  const float dd = 1.0f / fmaxf(X1[2], 0.1f);
+  const float x = fx * (dd * X1[0]) + cx;
+  const float y = fy * (dd * X1[1]) + cy;
+  if (layout == 0) {
+    coords[((size_t)n * PP + p) * 2 + 0] = x;
+    coords[((size_t)n * PP + p) * 2 + 1] = y;
+  } else {
+    coords[(size_t)n * 2 * PP + p] = x;
+    coords[(size_t)n * 2 * PP + PP + p] = y;
+  }
+  const int centre = (P / 2) * P + (P / 2);
+  if (p == centre) {
+    const float X = X1[0], Y = X1[1], Z = X1[2], H = X1[3];
+    if (valid) valid[n] = (Z > 0.2f) ? 1.0f : 0.0f;
+    if (Jj_o) {
+      const float d = (fabsf(Z) > 0.2f) ? 1.0f / Z : 0.0f;
+      // Jj = Jp * Ja  (2x4 * 4x6)
+      const float a0 = fx * d, a2 = -fx * X * d * d, b1 = fy * d, b2 = -fy * Y * d * d;
+      float J[2][6];
+      J[0][0] = a0 * H; J[0][1] = 0.f;    J[0][2] = a2 * H; J[0][3] = a2 * Y;           J[0][4] = a0 * Z - a2 * X; J[0][5] = -a0 * Y;
+      J[1][0] = 0.f;    J[1][1] = b1 * H; J[1][2] = b2 * H; J[1][3] = -b1 * Z + b2 * Y; J[1][4] = -b2 * X;         J[1][5] = b1 * X;
+      lie::Mat<float, 6, 6> A = Gij.Adj();
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        float o[6];
+        lie::matTvec(A, J[r], o);
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+          Jj_o[((size_t)n * 2 + r) * 6 + c] = J[r][c];
+          if (Ji_o) Ji_o[((size_t)n * 2 + r) * 6 + c] = -o[c];
+        }
+      }
+      if (Jz_o) {
+        Jz_o[(size_t)n * 2 + 0] = a0 * Gij.t[0] + a2 * Gij.t[2];
+        Jz_o[(size_t)n * 2 + 1] = b1 * Gij.t[1] + b2 * Gij.t[2];
+      }
+    }
+  }
+}
+}  // namespace
+
+template <int EPT>
+static int launch_accumulate(const BaLayout& L, char* w, float* poses, float* patches, const float* intrinsics,
+                             const float* target, const float* weight, const float* lmbda, const int64_t* ii,
+                             const int64_t* jj, const int64_t* kk, int32_t* status, int E, int PP, int centre,
+                             int t0, int nfree, int n_poses, int EB, int GB, size_t smem, int apply_update,
+                             int do_accumulate, int itr, cudaStream_t s) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    DEVO_CUDA(cudaFuncSetAttribute(ba_accumulate_kernel<EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  ba_accumulate_kernel<EPT><<<L.grid, kAccThreads, smem, s>>>(
+      poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, (const int32_t*)(w + L.perm),
+      (const int32_t*)(w + L.gstart), (const int64_t*)(w + L.gkey), (const int32_t*)(w + L.ngroups),
+      (double*)(w + L.Q), (double*)(w + L.U), (double*)(w + L.Ek), (double*)(w + L.partials),
+      (const double*)(w + L.dX), status, E, PP, centre, t0, nfree, n_poses, EB, GB, apply_update, do_accumulate, itr);
+  DEVO_LAUNCH_CHECK("ba_accumulate");
+  return DEVO_OK;
+}
+
+extern "C" {
+
+size_t devo_ba_workspace(int E, int n_free_poses) { return ba_layout(E, n_free_poses).total; }
+
+int devo_ba_forward(float* poses, float* patches, const float* intrinsics, const float* target,
+                    const float* weight, const float* lmbda, const int64_t* ii, const int64_t* jj,
+                    const int64_t* kk, int E, int n_poses, int n_patches, int P, int t0, int t1,
+                    int iterations, void* workspace, size_t workspace_bytes, int32_t* status, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  DEVO_REQUIRE(status != nullptr, DEVO_EINVAL, "ba_forward: status pointer is NULL");
+  DEVO_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), s));
+  if (E <= 0 || iterations <= 0) return DEVO_OK;
+  int nfree = t1 - t0;
+  if (nfree < 0) nfree = 0;
+  DEVO_REQUIRE(P >= 1 && P <= 8, DEVO_EINVAL, "ba_forward: patch size %d unsupported", P);
+  DEVO_REQUIRE(6 * nfree <= kMaxN6, DEVO_ECAPACITY,
+               "ba_forward: %d free poses exceed the in-shared-memory solver capacity (%d)", nfree, kMaxN6 / 6);
+  DEVO_REQUIRE(t0 >= 0 && t1 <= n_poses, DEVO_EINVAL, "ba_forward: pose window [%d,%d) outside [0,%d)", t0, t1, n_poses);
+  BaLayout L = ba_layout(E, nfree);
+  DEVO_REQUIRE(workspace && workspace_bytes >= L.total, DEVO_EWORKSPACE,
+               "ba_forward: workspace too small (%zu < %zu)", workspace_bytes, L.total);
+  char* w = (char*)workspace;
+  const int PP = P * P;
+  const int centre = (P == 3) ? 4 : (1 * P + 1 < PP ? 1 * P + 1 : 0);   // the reference hard-codes [1][1]
+  // patches grouped by kk (== torch::_unique(kk), ba_cuda.cu:435-437), edges of a patch contiguous
+  int rc = devo_graph_plan(kk, jj, E, n_patches, n_poses, (int32_t*)(w + L.perm), nullptr,
+                           (int32_t*)(w + L.gstart), (int64_t*)(w + L.gkey), (int32_t*)(w + L.ngroups),
+                           nullptr, nullptr, w + L.plan_ws, L.plan_bytes, stream);
+  if (rc != DEVO_OK) return rc;
+
+  const int n6 = L.n6, LD = n6 + 1;
+  int rows_cap = (int)(kAccSmemBudget / ((size_t)(LD + 2) * 8));
+  int EB = rows_cap * 2 / 5;
+  if (EB > kAccThreads) EB = kAccThreads;
+  int GB = rows_cap - 2 * EB;
+  if (GB > EB) GB = EB;
+  DEVO_REQUIRE(EB >= 8 && GB >= 1, DEVO_ECAPACITY, "ba_forward: system too large for shared memory");
+  const size_t smem_acc = (size_t)(2 * EB + GB) * (LD + 2) * 8;
+  const int ept = (L.nent + kAccThreads - 1) / kAccThreads;
+
+#define ACC(EPT_, APPLY, DOACC, ITR)                                                                         \
+  launch_accumulate<EPT_>(L, w, poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, status, E, PP, \
+                          centre, t0, nfree, n_poses, EB, GB, smem_acc, APPLY, DOACC, ITR, s)
+#define ACC_DISPATCH(APPLY, DOACC, ITR)                   \
+  do {                                                    \
+    if (ept <= 4) rc = ACC(4, APPLY, DOACC, ITR);         \
+    else if (ept <= 8) rc = ACC(8, APPLY, DOACC, ITR);    \
+    else if (ept <= 16) rc = ACC(16, APPLY, DOACC, ITR);  \
+    else if (ept <= 32) rc = ACC(32, APPLY, DOACC, ITR);  \
+    else rc = ACC(48, APPLY, DOACC, ITR);                 \
+    if (rc != DEVO_OK) return rc;                         \
+  } while (0)
+
+  DEVO_REQUIRE(ept <= 48, DEVO_ECAPACITY, "ba_forward: system too large (%d entries)", L.nent);
+  const size_t smem_solve = ((size_t)n6 * (n6 + 1) / 2 + n6 + 2) * 8;
+  static size_t solve_configured = 0;
+  if (smem_solve > solve_configured) {
+    DEVO_CUDA(cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
+    solve_configured = smem_solve;
+  }
+  for (int itr = 0; itr < iterations; itr++) {
+    ACC_DISPATCH(itr > 0 ? 1 : 0, 1, itr);
+    if (nfree > 0) {
+      ba_solve_kernel<<<1, kSolveThreads, smem_solve, s>>>(poses, (const double*)(w + L.partials),
+                                                           (double*)(w + L.dX), status, L.grid, t0, nfree, itr);
+      DEVO_LAUNCH_CHECK("ba_solve");
+    }
+  }
+  ACC_DISPATCH(1, 0, iterations);   // final depth update only
+#undef ACC
+#undef ACC_DISPATCH
+  return DEVO_OK;
+}
+
+int devo_reproject(const float* poses, const float* patches, const float* intrinsics, const int64_t* ii,
+                   const int64_t* jj, const int64_t* kk, float* coords, int E, int P, void* stream) {
+  if (E <= 0) return DEVO_OK;
+  const int PP = P * P;
+  reproject_kernel<<<devo::cdiv((long long)E * PP, 256), 256, 0, (cudaStream_t)stream>>>(
+      poses, patches, intrinsics, ii, jj, kk, coords, E, PP);
+  DEVO_LAUNCH_CHECK("reproject");
+  return DEVO_OK;
+}
+
+int devo_transform_forward(const float* poses, const float* patches, const float* intrinsics,
+                           const int64_t* ii, const int64_t* jj, const int64_t* kk, float* coords_out,
+                           float* valid_out, float* Ji, float* Jj, float* Jz, int E, int P, int layout,
+                           int tonly, void* stream) {
+  if (E <= 0) return DEVO_OK;
+  DEVO_REQUIRE(coords_out != nullptr, DEVO_EINVAL, "transform_forward: coords_out is NULL");
+  DEVO_REQUIRE(!(Ji && !Jj), DEVO_EINVAL, "transform_forward: Ji requires Jj");
+  transform_kernel<<<devo::cdiv((long long)E * P * P, 256), 256, 0, (cudaStream_t)stream>>>(
+      poses, patches, intrinsics, ii, jj, kk, coords_out, valid_out, Ji, Jj, Jz, E, P, layout, tonly);
+  DEVO_LAUNCH_CHECK("transform_forward");
+  return DEVO_OK;
+}
+
+}  // extern "C"

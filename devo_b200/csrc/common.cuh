@@ -1,0 +1,76 @@
+// common.cuh -- shared helpers for libdevo_b200 (error reporting, launch accounting, dtype traits)
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/devo_b200.h"
+
+namespace devo {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define DEVO_REQUIRE(cond, code, ...)                    \
+  do {                                                   \
+    if (!(cond)) {                                       \
+      devo::set_error(__VA_ARGS__);                      \
+      return (code);                                     \
+    }                                                    \
+  } while (0)
+
+// call after every kernel launch: records launch-configuration errors
+#define DEVO_LAUNCH_CHECK(name)                                              \
+  do {                                                                       \
+    devo::count_launch();                                                    \
+    cudaError_t _e = cudaGetLastError();                                     \
+    if (_e != cudaSuccess) {                                                 \
+      devo::set_error("%s: launch failed: %s", name, cudaGetErrorString(_e)); \
+      return (int)_e;                                                        \
+    }                                                                        \
+  } while (0)
+
+#define DEVO_CUDA(call)                                                       \
+  do {                                                                        \
+    cudaError_t _e = (call);                                                  \
+    if (_e != cudaSuccess) {                                                  \
+      devo::set_error("%s failed: %s", #call, cudaGetErrorString(_e));        \
+      return (int)_e;                                                         \
+    }                                                                         \
+  } while (0)
+
+template <typename T> struct ElemTraits;
+template <> struct ElemTraits<__half> {
+  static __device__ __forceinline__ float to_float(__half v) { return __half2float(v); }
+  static __device__ __forceinline__ __half from_float(float v) { return __float2half_rn(v); }
+  using acc_t = float;
+};
+template <> struct ElemTraits<__nv_bfloat16> {
+  static __device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+  static __device__ __forceinline__ __nv_bfloat16 from_float(float v) { return __float2bfloat16_rn(v); }
+  using acc_t = float;
+};
+template <> struct ElemTraits<float> {
+  static __device__ __forceinline__ float to_float(float v) { return v; }
+  static __device__ __forceinline__ float from_float(float v) { return v; }
+  using acc_t = float;
+};
+template <> struct ElemTraits<double> {
+  static __device__ __forceinline__ double to_float(double v) { return v; }
+  static __device__ __forceinline__ double from_float(double v) { return v; }
+  using acc_t = double;
+};
+
+static inline int elem_size(int dtype) {
+  switch (dtype) {
+    case DEVO_F16: case DEVO_BF16: return 2;
+    case DEVO_F32: return 4;
+    case DEVO_F64: return 8;
+  }
+  return 0;
+}
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace devo

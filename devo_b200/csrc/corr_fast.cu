@@ -1,0 +1,476 @@
+// corr_fast.cu -- B200 fast path of the sparse patch correlation lookup.
+//
+// What it replaces (per update iteration): pyramidify (devo/utils.py:70-79), L x altcorr.corr
+// (devo/devo.py:210-217 / devo/enet.py:203-216: per level 1 SIMT kernel with 2*C strided
+// scalar loads per thread + ~19 ATen launches for the bilinear blend, correlation_kernel.cu:
+// 82-136,193-233) and the torch.stack that interleaves the levels.
+//
+// Layout: feature pyramids are kept PIXEL-MAJOR ([frame][y][x][C], C contiguous), so the
+// (2r+2)^2 window union of a reprojected 3x3 patch is a dense box of 256-byte pixels instead
+// of C strided 20-byte row fragments (planar layout wastes >2x of every 32-byte sector).
+//
+// One work item = (edge, level):
+//   * producer warp : TMA (cp.async.bulk.tensor.4d, SWIZZLE_128B, OOB zero fill == the
+//                     reference's "out of bounds => 0") loads the 11x11-pixel box of frame jj
+//                     at level l -> smem A [121(+7) pixels][C] in UMMA K-major canonical form,
+//                     and the patch's [9 pixels][C] features -> smem B; 4-stage mbarrier ring.
+//   * MMA warp      : one thread issues C/16 tcgen05.mma (M=128 box pixels x N=16 patch pixels
+//                     x K=16), fp32 accumulator in TMEM (2 x 16 columns, double buffered);
+//                     tcgen05.commit releases the smem stage and publishes the accumulator.
+//   * 4 epilogue warps: tcgen05.ld the 128x16 accumulator (one box pixel per thread), park the
+//                     9 useful columns in smem, then apply the bilinear blend for the 9 x 7 x 7
+//                     outputs and store them directly in the interleaved [E, 49*9*L] layout the
+//                     GRU consumes (permute + stack fused).
+// Patch pixels whose window does not fit in the 11x11 box (reprojection scale > ~1.5x) take a
+// per-output direct path inside the same kernel.
+#include <cuda.h>
+#include <type_traits>
+#include "common.cuh"
+
+namespace {
+
+constexpr int kBox = 11;                    // box edge in pixels: 8 + floor-span 3
+constexpr int kBoxPix = kBox * kBox;        // 121 rows used of the M=128 tile
+constexpr int kStages = 4;
+constexpr int kThreads = 192;               // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int kATileBytes = 128 * 128;      // 128 rows x 64 ch x 2 B   (one K half)
+constexpr int kBTileBytes = 16 * 128;       // 16 rows  x 64 ch x 2 B
+constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;   // 36 KB
+constexpr int kVsFloats = 9 * 128;
+constexpr int kRadius = 3, kP = 3, kPP = 9, kOut = 7;
+
+struct FastParams {
+  int E, L, items, khalves;                 // khalves = C / 64
+  int H[DEVO_MAX_LEVELS], W[DEVO_MAX_LEVELS];
+  float scale[DEVO_MAX_LEVELS];
+  const float* coords;
+  const int64_t* ii;
+  const int64_t* jj;
+  void* out;
+  const void* gmap_pm;
+  const void* level[DEVO_MAX_LEVELS];
+  int C;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, SWIZZLE_128B canonical layout: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (=1)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;     // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;     // SWIZZLE_128B
+  return d;
+}
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ int safe_floor_int(float v, float& frac) {
+  float f = floorf(v);
+  frac = v - f;
+  if (!(f > -1.0e6f)) { f = -1.0e6f; frac = 0.f; }     // also catches NaN
+  if (f > 1.0e6f) { f = 1.0e6f; frac = 0.f; }
+  return (int)f;
+}
+
+// geometry of one (edge, level): lanes 0..8 own patch pixel p = lane
+struct Geo {
+  int fx, fy;        // floor of the (scaled) coordinate of this lane's pixel
+  float dx, dy;      // fractional part
+  int x0, y0;        // box origin (warp-uniform)
+};
+__device__ __forceinline__ Geo load_geo(const FastParams& prm, int e, int l, int lane) {
+  Geo g;
+  const float* co = prm.coords + (size_t)e * 2 * kPP;
+  float x = 0.f, y = 0.f;
+  if (lane < kPP) { x = co[lane] / prm.scale[l]; y = co[kPP + lane] / prm.scale[l]; }
+  g.fx = safe_floor_int(x, g.dx);
+  g.fy = safe_floor_int(y, g.dy);
+  int mx = lane < kPP ? g.fx : 0x7fffffff, my = lane < kPP ? g.fy : 0x7fffffff;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = min(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    my = min(my, __shfl_xor_sync(0xffffffffu, my, o));
+  }
+  g.x0 = mx - kRadius;
+  g.y0 = my - kRadius;
+  return g;
+}
+
+template <typename T>
+__device__ float direct_dot(const T* __restrict__ g, const T* __restrict__ lvl, int H, int W, int C, int frame, int y, int x) {
+  if (y < 0 || y >= H || x < 0 || x >= W) return 0.f;
+  const T* f = lvl + (((size_t)frame * H + y) * W + x) * C;
+  float s = 0.f;
+  for (int c = 0; c < C; c++) s += to_f<T>(g[c]) * to_f<T>(f[c]);
+  return s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
+    const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_l0,
+    const __grid_constant__ CUtensorMap tm_l1, const __grid_constant__ CUtensorMap tm_l2,
+    const __grid_constant__ CUtensorMap tm_l3, const FastParams prm) {
+  extern __shared__ unsigned char smem_dyn[];
+  // 1024-byte aligned carve-up (SWIZZLE_128B atoms repeat every 1024 B)
+  unsigned char* base = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+  unsigned char* tiles = base;                                           // kStages * kStageBytes
+  float* Vs = reinterpret_cast<float*>(base + kStages * kStageBytes);    // 2 * kVsFloats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Vs + 2 * kVsFloats);
+  uint64_t* full = bars;                 // [kStages]
+  uint64_t* empty = bars + kStages;      // [kStages]
+  uint64_t* tfull = bars + 2 * kStages;  // [2]
+  uint64_t* tempty = tfull + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per = (prm.items + gridDim.x - 1) / gridDim.x;
+  const int first = blockIdx.x * per;
+  const int last = min(prm.items, first + per);
+  const int khalves = prm.khalves;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(32) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    uint32_t stage = 0, phase = 0;
+    const uint32_t bytes = (uint32_t)khalves * (kBoxPix * 128 + kPP * 128);
+    for (int item = first; item < last; item++) {
+      const int e = item / prm.L, l = item - e * prm.L;
+      Geo g = load_geo(prm, e, l, lane);
+      if (lane == 0) {
+        const CUtensorMap* tm = (l == 0) ? &tm_l0 : (l == 1) ? &tm_l1 : (l == 2) ? &tm_l2 : &tm_l3;
+        const int frame = (int)prm.jj[e];
+        const int patch = (int)prm.ii[e];
+        unsigned char* st = tiles + (size_t)stage * kStageBytes;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full[stage], bytes);
+        for (int kh = 0; kh < khalves; kh++) {
+          tma_load_4d(st + kh * kATileBytes, tm, &full[stage], kh * 64, g.x0, g.y0, frame);
+          tma_load_3d(st + 2 * kATileBytes + kh * kBTileBytes, &tm_g, &full[stage], kh * 64, 0, patch);
+        }
+      }
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    // instruction descriptor: D=f32, A=B=f16|bf16, K-major both, N=16, M=128
+    const uint32_t fmt = (sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value) ? 1u : 0u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+    uint32_t stage = 0, phase = 0, acc = 0, aphase = 0;
+    for (int item = first; item < last; item++) {
+      if (lane == 0) {
+        mbar_wait(&tempty[acc], aphase ^ 1);
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(tiles + (size_t)stage * kStageBytes);
+        const uint32_t sb = sa + 2 * kATileBytes;
+        uint32_t accumulate = 0;
+        for (int kh = 0; kh < khalves; kh++) {
+#pragma unroll
+          for (int k4 = 0; k4 < 4; k4++) {
+            const uint64_t ad = umma_desc_sw128(sa + kh * kATileBytes + k4 * 32);
+            const uint64_t bd = umma_desc_sw128(sb + kh * kBTileBytes + k4 * 32);
+            tc_mma_f16(tmem_base + acc * 16, ad, bd, idesc, accumulate);
+            accumulate = 1;
+          }
+        }
+        tc_commit(&empty[stage]);    // smem stage may be refilled once these MMAs retire
+        tc_commit(&tfull[acc]);      // accumulator ready
+      }
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+      if (++acc == 2) { acc = 0; aphase ^= 1; }
+    }
+  } else {
+    // =============================== epilogue (4 warps) ===============================
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
+    const int row = quarter * 32 + lane;          // box pixel handled by this thread
+    const int et = (warp - 2) * 32 + lane;        // 0..127 within the epilogue group
+    T* out = reinterpret_cast<T*>(prm.out);
+    uint32_t acc = 0, aphase = 0;
+    int buf = 0;
+    for (int item = first; item < last; item++) {
+      const int e = item / prm.L, l = item - e * prm.L;
+      Geo g = load_geo(prm, e, l, lane);
+      mbar_wait(&tfull[acc], aphase);
+      tc_fence_after();
+      uint32_t v[16];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 16;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);   // accumulator stage free for the MMA warp
+      float* vs = Vs + buf * kVsFloats;
+#pragma unroll
+      for (int p = 0; p < kPP; p++) vs[p * 128 + row] = __uint_as_float(v[p]);
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // the 4 epilogue warps only
+
+      const int H = prm.H[l], W = prm.W[l];
+      const size_t obase = (size_t)e * (kOut * kOut * kPP) * prm.L;
+#pragma unroll 1
+      for (int it = 0; it < 4; it++) {
+        const int q = et + it * 128;
+        const bool active = q < kOut * kOut * kPP;
+        const int p = active ? q % kPP : 0;
+        const int yo = (q / kPP) % kOut, xo = q / (kPP * kOut);
+        const int pfx = __shfl_sync(0xffffffffu, g.fx, p), pfy = __shfl_sync(0xffffffffu, g.fy, p);
+        const float dx = __shfl_sync(0xffffffffu, g.dx, p), dy = __shfl_sync(0xffffffffu, g.dy, p);
+        if (!active) continue;
+        const int ox = pfx - kRadius - g.x0, oy = pfy - kRadius - g.y0;   // window origin inside the box (>= 0)
+        float r;
+        if (ox + 8 <= kBox && oy + 8 <= kBox) {
+          const float* s = vs + p * 128 + (oy + yo) * kBox + (ox + xo);
+          r = (1.f - dx) * (1.f - dy) * s[0] + dx * (1.f - dy) * s[1] + (1.f - dx) * dy * s[kBox] + dx * dy * s[kBox + 1];
+        } else {
+          // window outside the staged box (large scale change): direct evaluation
+          const T* gp = reinterpret_cast<const T*>(prm.gmap_pm) + ((size_t)prm.ii[e] * kPP + p) * prm.C;
+          const T* lv = reinterpret_cast<const T*>(prm.level[l]);
+          const int fr = (int)prm.jj[e];
+          const int yy = pfy - kRadius + yo, xx = pfx - kRadius + xo;
+          const float v00 = direct_dot<T>(gp, lv, H, W, prm.C, fr, yy, xx);
+          const float v01 = direct_dot<T>(gp, lv, H, W, prm.C, fr, yy, xx + 1);
+          const float v10 = direct_dot<T>(gp, lv, H, W, prm.C, fr, yy + 1, xx);
+          const float v11 = direct_dot<T>(gp, lv, H, W, prm.C, fr, yy + 1, xx + 1);
+          r = (1.f - dx) * (1.f - dy) * v00 + dx * (1.f - dy) * v01 + (1.f - dx) * dy * v10 + dx * dy * v11;
+        }
+        out[obase + (size_t)q * prm.L + l] = from_f<T>(r);
+      }
+      buf ^= 1;
+      if (++acc == 2) { acc = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32) : "memory");
+  }
+}
+
+// ---- packing kernels ------------------------------------------------------------------------
+// planar [N,C,H,W] --avg-pool pool x pool--> pixel-major [N,Ho,Wo,C]; one CTA per (n, yo, 32-pixel strip)
+template <typename T>
+__global__ void __launch_bounds__(256) pyramid_pack_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                           int C, int H, int W, int Ho, int Wo, int pool) {
+  extern __shared__ float tile[];   // [32][C+1]
+  const int n = blockIdx.z, yo = blockIdx.y, x0 = blockIdx.x * 32;
+  const int nx = min(32, Wo - x0);
+  const float div = (float)(pool * pool);
+  const T* src = in + (size_t)n * C * H * W;
+  // threads sweep (c, x) with x fastest -> coalesced planar reads
+  for (int q = threadIdx.x; q < C * 32; q += blockDim.x) {
+    const int x = q & 31, c = q >> 5;
+    if (x < nx) {
+      float s = 0.f;
+      const T* p = src + ((size_t)c * H + (size_t)yo * pool) * W + (size_t)(x0 + x) * pool;
+      for (int a = 0; a < pool; a++)
+        for (int b = 0; b < pool; b++) s += devo::ElemTraits<T>::to_float(p[(size_t)a * W + b]);
+      tile[x * (C + 1) + c] = (pool == 1) ? s : s / div;
+    }
+  }
+  __syncthreads();
+  T* dst = out + (((size_t)n * Ho + yo) * Wo + x0) * C;
+  for (int q = threadIdx.x; q < nx * C; q += blockDim.x) {
+    const int c = q % C, x = q / C;
+    dst[(size_t)x * C + c] = devo::ElemTraits<T>::from_float(tile[x * (C + 1) + c]);
+  }
+}
+
+template <typename T>
+__global__ void gmap_pack_kernel(const T* __restrict__ in, T* __restrict__ out, int Np, int C, int PP) {
+  const long long total = (long long)Np * C * PP;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(q % C);
+    const int p = (int)((q / C) % PP);
+    const long long n = q / ((long long)C * PP);
+    out[q] = in[(n * C + c) * PP + p];
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* m, int dtype, int rank, const void* ptr, const cuuint64_t* dims,
+                    const cuuint64_t* strides, const cuuint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  DEVO_REQUIRE(enc != nullptr, DEVO_EUNSUPPORTED, "corr_lookup_fused: cuTensorMapEncodeTiled unavailable");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, dtype == DEVO_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                   (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DEVO_REQUIRE(r == CUDA_SUCCESS, DEVO_EINVAL, "corr_lookup_fused: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return DEVO_OK;
+}
+
+template <typename T>
+static int launch_fast(const CUtensorMap* maps, const FastParams& prm, cudaStream_t s) {
+  const size_t smem = 1024 + (size_t)kStages * kStageBytes + 2 * kVsFloats * sizeof(float) + 16 * sizeof(uint64_t);
+  static bool configured = false;
+  if (!configured) {
+    DEVO_CUDA(cudaFuncSetAttribute(corr_fast_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  int grid = prm.items < 148 ? prm.items : 148;
+  corr_fast_kernel<T><<<grid, kThreads, smem, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], prm);
+  DEVO_LAUNCH_CHECK("corr_lookup_fused");
+  return DEVO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int devo_pyramid_pack(const void* fmap_planar, void* out_pixel_major, int dtype, int N, int C, int H, int W,
+                      int pool, void* stream) {
+  DEVO_REQUIRE(dtype == DEVO_F16 || dtype == DEVO_BF16, DEVO_EINVAL, "pyramid_pack: dtype must be f16 or bf16");
+  DEVO_REQUIRE(pool >= 1 && N >= 0 && C > 0 && H >= pool && W >= pool, DEVO_EINVAL, "pyramid_pack: bad sizes");
+  if (N == 0) return DEVO_OK;
+  const int Ho = H / pool, Wo = W / pool;
+  DEVO_REQUIRE(Ho <= 65535 && N <= 65535, DEVO_EINVAL, "pyramid_pack: dims too large");
+  const size_t smem = (size_t)32 * (C + 1) * sizeof(float);
+  DEVO_REQUIRE(smem <= 48 * 1024, DEVO_ECAPACITY, "pyramid_pack: C too large");
+  dim3 grid((Wo + 31) / 32, Ho, N);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == DEVO_F16)
+    pyramid_pack_kernel<__half><<<grid, 256, smem, s>>>((const __half*)fmap_planar, (__half*)out_pixel_major, C, H, W, Ho, Wo, pool);
+  else
+    pyramid_pack_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>((const __nv_bfloat16*)fmap_planar, (__nv_bfloat16*)out_pixel_major, C, H, W, Ho, Wo, pool);
+  DEVO_LAUNCH_CHECK("pyramid_pack");
+  return DEVO_OK;
+}
+
+int devo_gmap_pack(const void* gmap_planar, void* out, int dtype, int Np, int C, int PP, void* stream) {
+  DEVO_REQUIRE(dtype == DEVO_F16 || dtype == DEVO_BF16, DEVO_EINVAL, "gmap_pack: dtype must be f16 or bf16");
+  const long long total = (long long)Np * C * PP;
+  if (total <= 0) return DEVO_OK;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == DEVO_F16) gmap_pack_kernel<__half><<<grid, 256, 0, s>>>((const __half*)gmap_planar, (__half*)out, Np, C, PP);
+  else gmap_pack_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)gmap_planar, (__nv_bfloat16*)out, Np, C, PP);
+  DEVO_LAUNCH_CHECK("gmap_pack");
+  return DEVO_OK;
+}
+
+int devo_corr_lookup_fused(const void* gmap_pm, const devo_pyramid_t* pyr, const float* coords,
+                           const int64_t* ii, const int64_t* jj, void* out, int dtype, int Np, int Nf, int C,
+                           int E, void* stream) {
+  DEVO_REQUIRE(pyr != nullptr && pyr->n_levels >= 1 && pyr->n_levels <= DEVO_MAX_LEVELS, DEVO_EINVAL,
+               "corr_lookup_fused: bad pyramid");
+  DEVO_REQUIRE(dtype == DEVO_F16 || dtype == DEVO_BF16, DEVO_EUNSUPPORTED, "corr_lookup_fused: dtype must be f16 or bf16");
+  DEVO_REQUIRE(C == 64 || C == 128, DEVO_EUNSUPPORTED, "corr_lookup_fused: C must be 64 or 128 (got %d)", C);
+  DEVO_REQUIRE(((uintptr_t)gmap_pm & 15) == 0, DEVO_EINVAL, "corr_lookup_fused: gmap must be 16-byte aligned");
+  if (E <= 0) return DEVO_OK;
+  CUtensorMap maps[5];
+  FastParams prm;
+  prm.E = E; prm.L = pyr->n_levels; prm.items = E * pyr->n_levels; prm.khalves = C / 64; prm.C = C;
+  prm.coords = coords; prm.ii = ii; prm.jj = jj; prm.out = out; prm.gmap_pm = gmap_pm;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)kPP, (cuuint64_t)Np};
+    cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * kPP};
+    cuuint32_t box[3] = {64, (cuuint32_t)kPP, 1};
+    int rc = make_map(&maps[0], dtype, 3, gmap_pm, dims, strides, box);
+    if (rc != DEVO_OK) return rc;
+  }
+  for (int l = 0; l < DEVO_MAX_LEVELS; l++) {
+    const int ls = l < pyr->n_levels ? l : 0;
+    DEVO_REQUIRE(((uintptr_t)pyr->level[ls] & 15) == 0, DEVO_EINVAL, "corr_lookup_fused: level %d not 16-byte aligned", ls);
+    DEVO_REQUIRE(pyr->scale[ls] > 0.f, DEVO_EINVAL, "corr_lookup_fused: level %d scale must be > 0", ls);
+    prm.H[l] = pyr->H[ls]; prm.W[l] = pyr->W[ls]; prm.scale[l] = pyr->scale[ls]; prm.level[l] = pyr->level[ls];
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)pyr->W[ls], (cuuint64_t)pyr->H[ls], (cuuint64_t)Nf};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * pyr->W[ls], (cuuint64_t)C * 2 * pyr->W[ls] * pyr->H[ls]};
+    cuuint32_t box[4] = {64, kBox, kBox, 1};
+    int rc = make_map(&maps[1 + l], dtype, 4, pyr->level[ls], dims, strides, box);
+    if (rc != DEVO_OK) return rc;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == DEVO_F16) return launch_fast<__half>(maps, prm, s);
+  return launch_fast<__nv_bfloat16>(maps, prm, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,167 @@
+/*
+ * devo_b200.h -- C ABI of libdevo_b200.so: the B200 (sm_100a) implementation of the
+ * DEVO update-operator hot path (sparse patch correlation, SE3/Sim3 Lie-group ops,
+ * projective transform, Gauss-Newton bundle adjustment).
+ *
+ * This is the drop-in boundary.  Every entry point takes plain device pointers, sizes
+ * and a CUDA stream (as void*); no torch types.  The functions correspond one-to-one
+ * to what the reference binds through pybind11 (file:line of the reference interface
+ * each one replaces is cited).  Tensors are dense row-major ("contiguous") unless a
+ * stride is given.  All functions return 0 on success, a negative DEVO_E* code on an
+ * argument / capacity error, or a positive cudaError_t; devo_last_error() gives text.
+ * All work is enqueued on `stream`; nothing synchronises with the host.
+ */
+#ifndef DEVO_B200_H
+#define DEVO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DEVO_B200_ABI_VERSION 1
+
+/* element types (the reference dispatches half/float/double: correlation_kernel.cu:211,
+ * float/double: lietorch/include/dispatch.h:41-42) */
+enum { DEVO_F16 = 0, DEVO_BF16 = 1, DEVO_F32 = 2, DEVO_F64 = 3 };
+/* Lie groups (devo/lietorch/groups.py:236,252,268,290; dispatch.h:16-31) */
+enum { DEVO_SO3 = 1, DEVO_RXSO3 = 2, DEVO_SE3 = 3, DEVO_SIM3 = 4 };
+/* error codes */
+enum { DEVO_OK = 0, DEVO_EINVAL = -1, DEVO_ECAPACITY = -2, DEVO_EWORKSPACE = -3, DEVO_EUNSUPPORTED = -4 };
+
+int         devo_abi_version(void);
+const char* devo_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+uint64_t    devo_launch_count(void);
+
+/* ------------------------------------------------------------------ altcorr (cuda_corr) */
+/* cuda_corr.forward  (devo/altcorr/correlation.cpp:57, correlation_kernel.cu:82-136,193-233)
+ * fmap1 [B,Np,C,P,P], fmap2 [B,Nf,C,H,W] (dtype), coords [B,E,2,P,P] f32, ii/jj i64[E].
+ * out: [B,E,2r+1 (x-off),2r+1 (y-off),P,P] dtype, contiguous -- the value of the
+ * reference's (permuted) return tensor, with the bilinear blend fused in. */
+int devo_corr_forward(const void* fmap1, const void* fmap2, const float* coords,
+                      const int64_t* ii, const int64_t* jj, void* out, int dtype,
+                      int B, int Np, int Nf, int C, int H, int W, int E, int P, int radius,
+                      void* stream);
+/* cuda_corr.backward (correlation.cpp:58, correlation_kernel.cu:139-190,236-286)
+ * grad: [B,E,2r+1,2r+1,P,P] f32 contiguous (x-off,y-off order, as returned by forward).
+ * fmap1_grad/fmap2_grad (dtype) are fully overwritten (zeroed inside, then accumulated). */
+int devo_corr_backward(const void* fmap1, const void* fmap2, const float* coords,
+                       const int64_t* ii, const int64_t* jj, const float* grad,
+                       void* fmap1_grad, void* fmap2_grad, int dtype,
+                       int B, int Np, int Nf, int C, int H, int W, int E, int P, int radius,
+                       void* stream);
+/* cuda_corr.patchify_forward (correlation.cpp:60, correlation_kernel.cu:16-47,288-307)
+ * net [B,C,H,W], coords [B,M,2] f32 -> patches [B,M,C,2r+2,2r+2] (fully written, OOB = 0). */
+int devo_patchify_forward(const void* net, const float* coords, void* patches, int dtype,
+                          int B, int C, int H, int W, int M, int radius, void* stream);
+/* cuda_corr.patchify_backward (correlation.cpp:61, correlation_kernel.cu:49-80,309-333)
+ * net_grad [B,C,H,W] is fully overwritten. */
+int devo_patchify_backward(const void* patch_grad, const float* coords, void* net_grad, int dtype,
+                           int B, int C, int H, int W, int M, int radius, void* stream);
+
+/* --- B200-native fast path of the lookup: pixel-major (channels-last) pyramid + fused
+ * multi-level lookup.  Same arithmetic as devo_corr_forward over every level; replaces
+ * pyramidify + 2x altcorr.corr + torch.stack (devo/devo.py:210-217, devo/enet.py:203-216,
+ * devo/utils.py:70-79). */
+/* average-pool `pool`x`pool` (stride pool) of planar fmap [N,C,H,W] and write it
+ * pixel-major [N,H/pool,W/pool,C] (f16 or bf16). */
+int devo_pyramid_pack(const void* fmap_planar, void* out_pixel_major, int dtype,
+                      int N, int C, int H, int W, int pool, void* stream);
+/* repack gmap [Np,C,P,P] -> [Np,P*P,C] */
+int devo_gmap_pack(const void* gmap_planar, void* out, int dtype, int Np, int C, int PP, void* stream);
+#define DEVO_MAX_LEVELS 4
+typedef struct {
+  int n_levels;
+  const void* level[DEVO_MAX_LEVELS];   /* pixel-major [Nf,H_l,W_l,C] */
+  int H[DEVO_MAX_LEVELS], W[DEVO_MAX_LEVELS];
+  float scale[DEVO_MAX_LEVELS];         /* level-1 coords are divided by this per level (1, 4, ...) */
+} devo_pyramid_t;
+/* out [E, 49*P*P*n_levels]: index (((xo*7+yo)*P+i0)*P+j0)*L+l  == torch.stack(corrs,-1).view(1,E,-1)
+ * gmap_pm: [Np,P*P,C] pixel-major; coords [E,2,P,P] f32 at level-1 resolution; radius 3, P 3, C%64==0.
+ * ii indexes gmap (already reduced modulo the ring buffer by the caller), jj indexes frames. */
+int devo_corr_lookup_fused(const void* gmap_pm, const devo_pyramid_t* pyr, const float* coords,
+                           const int64_t* ii, const int64_t* jj, void* out, int dtype,
+                           int Np, int Nf, int C, int E, void* stream);
+
+/* ------------------------------------------------------------------ fastba (cuda_ba) */
+/* Edge-graph analysis shared by neighbors / BA / segment softmax: edges sorted by
+ * (ka, kb, edge index).  All outputs are device arrays; any may be NULL.
+ *   perm   i32[E]   edge index at each sorted position
+ *   gid    i32[E]   dense id (rank of ka among the sorted unique ka) of each EDGE  (= torch.unique inverse)
+ *   gstart i32[E+1] start of each group in `perm`; gstart[ngroups] = E
+ *   gkey   i64[E]   unique ka values (first ngroups valid)                          (= torch.unique values)
+ *   ngroups i32[1]
+ *   ix,jx  i64[E]   previous / next edge of the same ka in kb order, -1 at the ends (= cuda_ba.neighbors)
+ * max_ka / max_kb: exclusive upper bounds if known, else -1. */
+size_t devo_graph_plan_workspace(int E);
+int devo_graph_plan(const int64_t* ka, const int64_t* kb, int E, int64_t max_ka, int64_t max_kb,
+                    int32_t* perm, int32_t* gid, int32_t* gstart, int64_t* gkey, int32_t* ngroups,
+                    int64_t* ix, int64_t* jx, void* workspace, size_t workspace_bytes, void* stream);
+/* cuda_ba.neighbors (devo/fastba/ba.cpp:104-149,154) -- on the GPU, no host round trip */
+int devo_neighbors(const int64_t* ii, const int64_t* jj, int64_t* ix, int64_t* jx, int E,
+                   void* workspace, size_t workspace_bytes, void* stream);
+/* cuda_ba.forward (devo/fastba/ba.cpp:153, ba_cuda.cu:422-540): `iterations` Gauss-Newton
+ * steps, IN PLACE on poses [n_poses,7] and patches [n_patches,3,P,P] (f32).
+ * status (device i32[1]): 0, or iteration+1 at which the Schur system was not positive
+ * definite (the reference raises there: later iterations are skipped), or a DEVO_E* code. */
+size_t devo_ba_workspace(int E, int n_free_poses);
+int devo_ba_forward(float* poses, float* patches, const float* intrinsics, const float* target,
+                    const float* weight, const float* lmbda,
+                    const int64_t* ii, const int64_t* jj, const int64_t* kk,
+                    int E, int n_poses, int n_patches, int P, int t0, int t1, int iterations,
+                    void* workspace, size_t workspace_bytes, int32_t* status, void* stream);
+/* cuda_ba.reproject (devo/fastba/ba.cpp:155, ba_cuda.cu:368-418,543-575) -> coords [E,2,P,P] f32 */
+int devo_reproject(const float* poses, const float* patches, const float* intrinsics,
+                   const int64_t* ii, const int64_t* jj, const int64_t* kk, float* coords,
+                   int E, int P, void* stream);
+
+/* ------------------------------------------------------------------ projective_ops */
+/* Fused forward of devo/projective_ops.py:53-105 `transform` for SE3 f32:
+ * Gij = Gj * Gi^-1, X1 = Gij * iproj(patch), proj with 1/clamp(Z,0.1).
+ * coords_out [E,P,P,2] if layout==0 (what transform returns), [E,2,P,P] if layout==1
+ * (what devo.py:223 / enet.py:342 permute it to).  valid_out [E] (Z_centre>0.2) and
+ * Ji,Jj [E,2,6], Jz [E,2,1] may be NULL.  tonly zeroes the rotation (:63-64). */
+int devo_transform_forward(const float* poses, const float* patches, const float* intrinsics,
+                           const int64_t* ii, const int64_t* jj, const int64_t* kk,
+                           float* coords_out, float* valid_out, float* Ji, float* Jj, float* Jz,
+                           int E, int P, int layout, int tonly, void* stream);
+
+/* ------------------------------------------------------------------ lietorch_backends */
+/* The 19 entry points of devo/lietorch/src/lietorch.cpp:286-316.  `n` = batch (rows).
+ * X,Y,Z group elements [n,N]; a,b tangents [n,K]; p,q points [n,3] or [n,4]; gradients
+ * w.r.t. group elements are [n,N] with the K-vector in the first K slots, rest 0
+ * (lietorch_gpu.cu:41-42,120-123).  dtype in {DEVO_F32, DEVO_F64}. */
+int devo_lie_expm(int group, int dtype, const void* a, void* X, int64_t n, void* stream);
+int devo_lie_expm_backward(int group, int dtype, const void* grad, const void* a, void* da, int64_t n, void* stream);
+int devo_lie_logm(int group, int dtype, const void* X, void* a, int64_t n, void* stream);
+int devo_lie_logm_backward(int group, int dtype, const void* grad, const void* X, void* dX, int64_t n, void* stream);
+int devo_lie_inv(int group, int dtype, const void* X, void* Y, int64_t n, void* stream);
+int devo_lie_inv_backward(int group, int dtype, const void* grad, const void* X, void* dX, int64_t n, void* stream);
+int devo_lie_mul(int group, int dtype, const void* X, const void* Y, void* Z, int64_t n, void* stream);
+int devo_lie_mul_backward(int group, int dtype, const void* grad, const void* X, const void* Y, void* dX, void* dY, int64_t n, void* stream);
+int devo_lie_adj(int group, int dtype, const void* X, const void* a, void* b, int64_t n, void* stream);
+int devo_lie_adj_backward(int group, int dtype, const void* grad, const void* X, const void* a, void* dX, void* da, int64_t n, void* stream);
+int devo_lie_adjT(int group, int dtype, const void* X, const void* a, void* b, int64_t n, void* stream);
+int devo_lie_adjT_backward(int group, int dtype, const void* grad, const void* X, const void* a, void* dX, void* da, int64_t n, void* stream);
+int devo_lie_act(int group, int dtype, const void* X, const void* p, void* q, int64_t n, void* stream);
+int devo_lie_act_backward(int group, int dtype, const void* grad, const void* X, const void* p, void* dX, void* dp, int64_t n, void* stream);
+int devo_lie_act4(int group, int dtype, const void* X, const void* p, void* q, int64_t n, void* stream);
+int devo_lie_act4_backward(int group, int dtype, const void* grad, const void* X, const void* p, void* dX, void* dp, int64_t n, void* stream);
+int devo_lie_as_matrix(int group, int dtype, const void* X, void* T4x4, int64_t n, void* stream);
+int devo_lie_projector(int group, int dtype, const void* X, void* PNxN, int64_t n, void* stream);
+int devo_lie_jinv(int group, int dtype, const void* X, const void* a, void* b, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------ segment ops (torch_scatter role) */
+/* scatter_softmax / scatter_sum over dim 1 of x [n_rows, dim] with group ids gid i32[n_rows]
+ * (devo/blocks.py:40-48).  softmax_out [n_rows,dim]; sum_out [n_groups,dim] (overwritten). */
+int devo_segment_softmax_sum(const void* g, const void* f, const int32_t* perm, const int32_t* gstart,
+                             const int32_t* ngroups, int max_groups, void* y_out, int dtype,
+                             int n_rows, int dim, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEVO_B200_H */
