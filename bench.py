@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py -- update-operator iterations/s on the BASELINE.json workload "S8"
+(96 patches x 8 frames, 640x480x5 voxels => 160x120 features, C=128, 6144 edges).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One step = one DEVO update iteration (devo/devo.py:308-338): reproject -> correlation lookup
+(levels [1,4]) -> context gather -> Update (GRU, fp16 autocast, cuBLAS) -> fastba.BA(2 iterations),
+preceded by the ingest of one new frame into the pixel-major pyramid ring (what DEVO.__call__ does
+before update(), devo.py:523-527).  The whole step is one CUDA-graph replay.
+
+  value     device-timed (CUDA events on the launching stream, summed per step), inputs resident in
+            HBM, L2 flushed between timed steps; whole job = N replicas (one sequence per GPU, no
+            data-path collective: "weak" scaling); max over ranks.
+  e2e       same step through the public API with HOST (pinned) inputs: H2D of every input of the
+            step, frame ingest of all frames, the iteration, D2H of the updated poses/depths.
+  roofline  the dominant kernel of ours (corr_fast_kernel): algorithmic bytes / measured duration
+            vs the measured HBM peak (MEASURED_PEAKS.json).
+  cpu_baseline / --impl reference
+            the reference's CPU path restated by the oracle (oracle/: corr + torch-CPU GRU +
+            ba.py Gauss-Newton), timed on the host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "update-op iters/sec (96 patches x 8 frames, 640x480x5 voxels)"
+UNIT = "iterations/s"
+WORKLOAD = dict(workload="S8: 8 frames x 96 patches, 6144 edges, 160x120x128 fp16 features, pyramid levels [1,4], "
+                         "r=3, P=3, GRU dim 384, fastba t0=1 t1=8 2 GN iterations", seed=1234)
+
+
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic_bytes():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture"""
+    p = os.path.join(ROOT, "profiles", "corr_fast_traffic.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
+# ----------------------------------------------------------------------------------------------
+def build_engine(device, wl=None):
+    from devo_b200 import synthetic
+    from devo_b200.engine import UpdateOperator
+    wl = wl or synthetic.make_workload(seed=WORKLOAD["seed"])
+    up = synthetic.make_update_module(seed=WORKLOAD["seed"]).to(device).eval()
+    op = UpdateOperator(up, wl["n_frames"], wl["patches_per_frame"], wl["E"], wl["H4"], wl["W4"], C=wl["C"],
+                        dim=wl["dim"], levels=(1, 4), device=device, t0=1)
+    return op, up, wl
+
+
+def load_state(op, wl, dev):
+    M = wl["patches_per_frame"]
+    op.poses.copy_(wl["poses0"].to(dev)[None])
+    op.patches.copy_(wl["patches0"].to(dev)[None])
+    op.intrinsics.copy_(wl["intrinsics"].to(dev)[None])
+    op.set_graph(wl["ii"].to(dev), wl["jj"].to(dev), wl["kk"].to(dev))
+    fmap, gmap, imap = wl["fmap"].to(dev), wl["gmap"].to(dev), wl["imap"].to(dev)
+    for f in range(wl["n_frames"]):
+        op.ingest_frame(f, fmap[f], gmap[f * M:(f + 1) * M], imap[f * M:(f + 1) * M])
+    op.net.copy_(wl["net"].to(dev)[None])
+    op.snapshot_geometry()
+    return fmap, gmap, imap
+
+
+def run_ours(args, rank, world, local_rank):
+    from devo_b200 import _lib, cuda_corr, synthetic
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    _lib.lib()                                   # fail loudly if the CUDA library is missing
+    op, up, wl = build_engine(dev)
+    fmap, gmap, imap = load_state(op, wl, dev)
+    M, Nf = wl["patches_per_frame"], wl["n_frames"]
+    new_frame = Nf - 1                           # the frame that "arrives" before each update
+
+    def step_body():
+        # steady-state DEVO: one new frame enters the ring, then one update iteration
+        op.ingest_frame(new_frame, fmap[new_frame], gmap[new_frame * M:(new_frame + 1) * M], imap[new_frame * M:(new_frame + 1) * M])
+        op._iteration(reset_geometry=True)
+
+    # eager warm-up (also counts our kernel launches per step), then capture the step in a CUDA graph
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side), torch.no_grad():
+        step_body()
+        torch.cuda.synchronize(dev)
+        l0 = _lib.launch_count()
+        step_body()
+        launches_per_step = _lib.launch_count() - l0
+        step_body()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize(dev)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph), torch.no_grad():
+        step_body()
+    stream = torch.cuda.current_stream(dev)
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        graph.replay()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.zero_()                            # L2 flush, outside the timed bracket of the step
+        ev[k][0].record(stream)
+        graph.replay()
+        ev[k][1].record(stream)
+    barrier()
+    clocks = sampler.stop()
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    status = int(op.status_sticky.item())
+
+    # L2-warm variant (informational): back-to-back replays, one event pair
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    a.record(stream)
+    for _ in range(args.steps):
+        graph.replay()
+    b.record(stream)
+    torch.cuda.synchronize(dev)
+    warm_ms = a.elapsed_time(b)
+
+    if world > 1:
+        t = torch.tensor([total_ms, warm_ms], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        total_ms, warm_ms = t.tolist()
+        s = torch.tensor([status], device=dev)
+        torch.distributed.all_reduce(s, op=torch.distributed.ReduceOp.MAX)
+        status = int(s.item())
+    if rank != 0:
+        return None
+
+    # ---- roofline of the dominant kernel (the fused correlation lookup), timed alone with L2 flushes
+    with torch.no_grad():
+        coords = op.coords[0].clone()
+        kt = []
+        for _ in range(30):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            cuda_corr.lookup_fused(op.gmap_pm, op.levels_pm, op.levels, coords, op.kk, op.jj)
+            e1.record(stream)
+            kt.append((e0, e1))
+        torch.cuda.synchronize(dev)
+        kms = sorted(x.elapsed_time(y) for x, y in kt[5:])
+        k_ms = sum(kms) / len(kms)
+    alg = synthetic.corr_algorithmic_bytes(Nf, M, wl["E"], wl["C"], wl["H4"], wl["W4"], (1, 4), 2)
+    peak, peak_src = measured_peak_gbs()
+    achieved = alg / (k_ms * 1e-3) / 1e9
+    roofline = dict(bound="hbm", kernel="corr_fast_kernel (devo_corr_lookup_fused)", achieved=round(achieved, 1),
+                    peak=peak, unit="GB/s", frac=round(achieved / peak, 4), traffic=ncu_traffic_bytes(),
+                    algorithmic_bytes=alg, kernel_ms=round(k_ms, 5), peak_source=peak_src,
+                    note="window gathers overlap ~6x: L2->SM bytes, not HBM bytes, bound this kernel (DESIGN.md)")
+
+    # ---- end to end through the public API with host (pinned) inputs
+    e2e = run_e2e(op, wl, dev, max(5, min(args.steps, 50)))
+    if world > 1:
+        e2e["note"] = "measured on rank 0 only; x%d replicas" % world
+        e2e["value"] = round(e2e["value"] * world, 2)
+
+    value = world * args.steps / (total_ms * 1e-3)
+    line = dict(metric=METRIC, value=round(value, 2), unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                ms_per_step=round(total_ms / args.steps, 5), higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f16", data="synthetic",
+                config=dict(WORKLOAD, l2="flushed (256 MiB memset) between timed steps; per-step CUDA events summed",
+                            parallelism="replicas: one sequence per GPU, no data-path collective",
+                            step="ingest of 1 frame + 1 update iteration, one CUDA-graph replay",
+                            ba_status=status, value_l2_warm=round(world * args.steps / (warm_ms * 1e-3), 2)),
+                roofline=roofline, e2e=e2e, gpu_launches=int(launches_per_step * args.steps), clocks=clocks)
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_once()
+    return line
+
+
+def run_e2e(op, wl, dev, steps):
+    """host buffers -> H2D -> ingest all frames + iteration -> D2H of the result, every step"""
+    M, Nf = wl["patches_per_frame"], wl["n_frames"]
+    host = {k: wl[k].contiguous().pin_memory() for k in ("fmap", "gmap", "imap", "net", "poses0", "patches0", "intrinsics",
+                                                         "targets", "ii", "jj", "kk")}
+    dbuf = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+    out_p = torch.empty(Nf, 7, dtype=torch.float32).pin_memory()
+    out_d = torch.empty(Nf * M, dtype=torch.float32).pin_memory()
+    h2d = sum(v.numel() * v.element_size() for k, v in host.items() if k != "targets")
+    d2h = out_p.numel() * 4 + out_d.numel() * 4
+
+    def one():
+        for k, v in host.items():
+            if k != "targets":
+                dbuf[k].copy_(v, non_blocking=True)
+        op.poses.copy_(dbuf["poses0"][None])
+        op.patches.copy_(dbuf["patches0"][None])
+        op.intrinsics.copy_(dbuf["intrinsics"][None])
+        op.set_graph(dbuf["ii"], dbuf["jj"], dbuf["kk"])
+        op.net.copy_(dbuf["net"][None])
+        for f in range(Nf):
+            op.ingest_frame(f, dbuf["fmap"][f], dbuf["gmap"][f * M:(f + 1) * M], dbuf["imap"][f * M:(f + 1) * M])
+        op._iteration(reset_geometry=False)
+        out_p.copy_(op.poses[0], non_blocking=True)
+        out_d.copy_(op.patches[0, :, 2, 1, 1], non_blocking=True)
+        torch.cuda.synchronize(dev)
+
+    with torch.no_grad():
+        for _ in range(3):
+            one()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one()
+        dt = time.perf_counter() - t0
+    return dict(value=round(steps / dt, 2), unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                steps=steps, note="host pinned inputs incl. the full 8-frame feature pyramid each step; wall clock with a "
+                                  "device sync per step")
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_iteration(wl, up_cpu, edge_stride):
+    """one update iteration of the reference algorithm on the CPU (oracle port), on every
+    `edge_stride`-th edge of the S8 graph.  Returns seconds (and a per-stage breakdown)."""
+    from oracle import ba as oba
+    from oracle import corr as ocorr
+    from oracle import neighbors as onb  # noqa: F401
+    from oracle import pops as opops
+    sel = torch.arange(0, wl["E"], edge_stride)
+    ii, jj, kk = wl["ii"][sel], wl["jj"][sel], wl["kk"][sel]
+    f32 = torch.float32
+    poses = wl["poses0"][None].to(f32)
+    patches = wl["patches0"][None].to(f32)
+    intr = wl["intrinsics"][None].to(f32)
+    M, Nf = wl["patches_per_frame"], wl["n_frames"]
+    fmap = wl["fmap"].float()
+    pyr = [fmap[None], torch.nn.functional.avg_pool2d(fmap, 4, 4)[None]]
+    gmap = wl["gmap"].float()[None]
+    t = {}
+    t0 = time.perf_counter()
+    coords = opops.transform(poses, patches, intr, ii, jj, kk).permute(0, 1, 4, 2, 3).contiguous()
+    t["reproject"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    cs = [ocorr.corr_forward(gmap, pyr[l], coords / s, kk, jj, 3, compute_dtype=f32) for l, s in enumerate((1, 4))]
+    corr = torch.stack(cs, -1).reshape(1, ii.numel(), -1)
+    t["corr"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        net = wl["net"].float()[None][:, sel]
+        ctx = wl["imap"].float()[None][:, kk]
+        x = up_cpu.norm(net + ctx + up_cpu.corr(corr))
+        ix, jx = onb.neighbors(kk, jj)
+        x = x + up_cpu.c1((ix >= 0).float().reshape(1, -1, 1) * x[:, ix])
+        x = x + up_cpu.c2((jx >= 0).float().reshape(1, -1, 1) * x[:, jx])
+        x = x + up_cpu.agg_kk(x, kk)
+        x = x + up_cpu.agg_ij(x, ii * 12345 + jj)
+        x, (delta, weight, _) = up_cpu._heads(x)
+    t["gru"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    target = coords[..., 1, 1] + delta
+    bounds = [-64, -64, wl["W4"] + 64, wl["H4"] + 64]
+    for _ in range(2):   # the reference CPU path: devo/ba.py Gauss-Newton (enet.py:353-356)
+        poses, patches = oba.ba_step(poses, patches, intr, target, weight, 1e-4, ii, jj, kk, bounds, ep=10.0, fixedp=1)
+    t["ba"] = time.perf_counter() - t0
+    return sum(t.values()), t
+
+
+def cpu_baseline_once(edge_stride=8):
+    from devo_b200 import synthetic
+    torch.set_num_threads(os.cpu_count() or 1)
+    wl = synthetic.make_workload(seed=WORKLOAD["seed"])
+    up = synthetic.make_update_module(seed=WORKLOAD["seed"]).eval()
+    cpu_iteration(wl, up, 64)                     # warm-up
+    secs, parts = cpu_iteration(wl, up, edge_stride)
+    full, parts_full = (secs, parts) if edge_stride == 1 else (None, None)
+    its = 1.0 / (secs * edge_stride)
+    return dict(value=round(its, 4), unit=UNIT, cores=torch.get_num_threads(), kind="port",
+                sample="one S8 update iteration on every %dth edge (%d of 6144 edges) on the host cores, scaled by %d; "
+                       "oracle port: reproject %.2fs corr %.2fs gru(torch-cpu) %.2fs ba.py x2 %.2fs"
+                       % (edge_stride, 6144 // edge_stride, edge_stride, parts["reproject"], parts["corr"], parts["gru"], parts["ba"]))
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return None
+    from devo_b200 import synthetic
+    torch.set_num_threads(os.cpu_count() or 1)
+    wl = synthetic.make_workload(seed=WORKLOAD["seed"])
+    up = synthetic.make_update_module(seed=WORKLOAD["seed"]).eval()
+    stride = 8
+    for _ in range(min(args.warmup, 2)):
+        cpu_iteration(wl, up, 64)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_iteration(wl, up, stride)
+    dt = time.perf_counter() - t0
+    value = args.steps / (dt * stride)
+    cb = dict(value=round(value, 4), unit=UNIT, cores=torch.get_num_threads(), kind="port",
+              sample="each step = one S8 update iteration restricted to every %dth edge (768 of 6144), scaled by %d; "
+                     "oracle port of corr + torch-CPU GRU + devo/ba.py Gauss-Newton x2 (the reference's CPU path); the "
+                     "reference's altcorr/fastba have no CPU implementation and lietorch's needs Eigen (absent)" % (stride, stride))
+    return dict(metric=METRIC, value=round(value, 4), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=round(1e3 * dt * stride / args.steps, 3), higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic", impl="reference", config=dict(WORKLOAD), cpu_baseline=cb,
+                e2e=dict(value=round(value, 4), unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        line = run_reference(args, rank, world)
+        if line is not None:
+            print(json.dumps(line), flush=True)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback; use --impl reference for the CPU arm)")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        line = run_ours(args, rank, world, local_rank)
+        if line is not None:
+            print(json.dumps(line), flush=True)
+    finally:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

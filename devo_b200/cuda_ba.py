@@ -1,0 +1,148 @@
+"""`cuda_ba` -- drop-in for the reference's pybind module (devo/fastba/ba.cpp:152-155):
+forward (in-place Gauss-Newton BA), neighbors, reproject.
+
+`forward` mutates `poses` and `patches` in place and returns [] like the reference.
+Error behaviour: the reference raises from torch::linalg::cholesky when the Schur
+system is not positive definite (the caller, devo/devo.py:336-340, catches it).  With
+STRICT (default) this module reads the device status word after the launch sequence
+and raises RuntimeError likewise; the fused engine uses the non-blocking form.
+"""
+import torch
+
+from . import _lib
+
+STRICT = True
+
+
+def _f32c(t, name, inplace=False):
+    _lib.require_cuda(t)
+    _lib.require_dtype(t, torch.float32, name)
+    if not t.is_contiguous():
+        if inplace:
+            raise RuntimeError("cuda_ba: %s is updated in place and must be contiguous" % name)
+        t = t.contiguous()
+    return t
+
+
+def _idx(t, name):
+    _lib.require_cuda(t)
+    _lib.require_dtype(t, torch.int64, name)
+    return t.contiguous()
+
+
+def forward_async(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, t0, t1, iterations, status=None):
+    """enqueue the BA; returns the device status tensor (int32[1]) without synchronising"""
+    poses = _f32c(poses, "poses", True)
+    patches = _f32c(patches, "patches", True)
+    intrinsics = _f32c(intrinsics, "intrinsics")
+    target = _f32c(target, "target")
+    weight = _f32c(weight, "weight")
+    lmbda = _f32c(lmbda.reshape(-1), "lmbda")
+    ii, jj, kk = _idx(ii, "ii"), _idx(jj, "jj"), _idx(kk, "kk")
+    E = ii.numel()
+    if target.numel() != 2 * E or weight.numel() != 2 * E or jj.numel() != E or kk.numel() != E:
+        raise RuntimeError("cuda_ba.forward: target/weight/ii/jj/kk sizes disagree")
+    P = patches.shape[-1]
+    n_poses = poses.numel() // 7
+    n_patches = patches.numel() // (3 * P * P)
+    dev = poses.device
+    if status is None:
+        status = torch.empty(1, dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    nbytes = L.devo_ba_workspace(E, max(int(t1) - int(t0), 0))
+    ws = _lib.workspace(nbytes, dev, "ba")
+    _lib.check(L.devo_ba_forward(poses.data_ptr(), patches.data_ptr(), intrinsics.data_ptr(), target.data_ptr(),
+                                 weight.data_ptr(), lmbda.data_ptr(), ii.data_ptr(), jj.data_ptr(), kk.data_ptr(),
+                                 E, n_poses, n_patches, P, int(t0), int(t1), int(iterations), ws.data_ptr(),
+                                 ws.numel(), status.data_ptr(), _lib.stream_ptr(dev)), "ba_forward")
+    return status
+
+
+def forward(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, t0, t1, iterations):
+    status = forward_async(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, t0, t1, iterations)
+    if STRICT:
+        code = int(status.item())
+        if code > 0:
+            raise RuntimeError("cuda_ba.forward: Schur complement not positive definite at iteration %d "
+                               "(linalg.cholesky would have raised)" % (code - 1))
+        if code < 0:
+            raise RuntimeError("cuda_ba.forward: capacity error %d (a patch has more edges than one batch holds)" % code)
+    return []
+
+
+def neighbors(ii, jj):
+    """-> [ix, jx] int64 CUDA tensors (previous / next edge of the same ii in jj order, -1 at the ends)"""
+    ii, jj = _idx(ii, "ii"), _idx(jj, "jj")
+    E = ii.numel()
+    if jj.numel() != E:
+        raise RuntimeError("cuda_ba.neighbors: ii and jj must have the same length")
+    ix = torch.empty(E, dtype=torch.int64, device=ii.device)
+    jx = torch.empty(E, dtype=torch.int64, device=ii.device)
+    if E == 0:
+        return [ix, jx]
+    L = _lib.lib()
+    ws = _lib.workspace(L.devo_graph_plan_workspace(E), ii.device, "plan")
+    _lib.check(L.devo_neighbors(ii.data_ptr(), jj.data_ptr(), ix.data_ptr(), jx.data_ptr(), E, ws.data_ptr(),
+                                ws.numel(), _lib.stream_ptr(ii.device)), "neighbors")
+    return [ix, jx]
+
+
+def reproject(poses, patches, intrinsics, ii, jj, kk):
+    """-> coords [1,E,2,P,P] float32"""
+    poses = _f32c(poses, "poses")
+    patches = _f32c(patches, "patches")
+    intrinsics = _f32c(intrinsics, "intrinsics")
+    ii, jj, kk = _idx(ii, "ii"), _idx(jj, "jj"), _idx(kk, "kk")
+    E = ii.numel()
+    P = patches.shape[-1]
+    coords = torch.empty(1, E, 2, P, P, dtype=torch.float32, device=poses.device)
+    _lib.check(_lib.lib().devo_reproject(poses.data_ptr(), patches.data_ptr(), intrinsics.data_ptr(), ii.data_ptr(),
+                                         jj.data_ptr(), kk.data_ptr(), coords.data_ptr(), E, P,
+                                         _lib.stream_ptr(poses.device)), "reproject")
+    return coords
+
+
+class GraphPlan:
+    """device-side analysis of an edge list grouped by `ka` and ordered by `kb`
+    (replaces torch.unique / fastba.neighbors host round trips; see include/devo_b200.h)"""
+
+    def __init__(self, ka, kb, max_ka=-1, max_kb=-1, want_neighbors=True):
+        ka, kb = _idx(ka, "ka"), _idx(kb, "kb")
+        E = ka.numel()
+        dev = ka.device
+        self.E = E
+        self.perm = torch.empty(E, dtype=torch.int32, device=dev)
+        self.gid = torch.empty(E, dtype=torch.int32, device=dev)
+        self.gstart = torch.empty(E + 1, dtype=torch.int32, device=dev)
+        self.gkey = torch.empty(E, dtype=torch.int64, device=dev)
+        self.ngroups = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.ix = torch.empty(E, dtype=torch.int64, device=dev) if want_neighbors else None
+        self.jx = torch.empty(E, dtype=torch.int64, device=dev) if want_neighbors else None
+        self._ka, self._kb, self._max = ka, kb, (int(max_ka), int(max_kb))
+        L = _lib.lib()
+        self._ws = torch.empty(max(L.devo_graph_plan_workspace(E), 256), dtype=torch.uint8, device=dev)
+        self.update()
+
+    def update(self):
+        """recompute in place (same buffers: CUDA-graph friendly)"""
+        _lib.check(_lib.lib().devo_graph_plan(self._ka.data_ptr(), self._kb.data_ptr(), self.E, self._max[0],
+                                              self._max[1], self.perm.data_ptr(), self.gid.data_ptr(),
+                                              self.gstart.data_ptr(), self.gkey.data_ptr(), self.ngroups.data_ptr(),
+                                              _lib.ptr(self.ix), _lib.ptr(self.jx), self._ws.data_ptr(),
+                                              self._ws.numel(), _lib.stream_ptr(self._ka.device)), "graph_plan")
+        return self
+
+
+def segment_softmax_sum(g, f, plan, max_groups):
+    """y[grp] = sum_r f[r] * softmax_over_group(g)[r]  for x of shape [1,E,dim] -> [1,max_groups,dim]"""
+    _lib.require_cuda(g, f)
+    g = g.contiguous()
+    f = f.contiguous()
+    dim = g.shape[-1]
+    n_rows = g.numel() // dim
+    y = torch.empty(1, max_groups, dim, dtype=g.dtype, device=g.device)
+    _lib.check(_lib.lib().devo_segment_softmax_sum(g.data_ptr(), f.data_ptr(), plan.perm.data_ptr(),
+                                                   plan.gstart.data_ptr(), plan.ngroups.data_ptr(), max_groups,
+                                                   y.data_ptr(), _lib.dtype_code(g), n_rows, dim,
+                                                   _lib.stream_ptr(g.device)), "segment_softmax_sum")
+    return y

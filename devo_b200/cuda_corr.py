@@ -1,0 +1,173 @@
+"""`cuda_corr` -- drop-in for the reference's pybind module of the same name
+(devo/altcorr/correlation.cpp:57-62): forward, backward, patchify_forward,
+patchify_backward, same argument order and meaning, list-of-tensors results.
+
+Host side only: validation, output allocation and the call into the C ABI
+(include/devo_b200.h) on the current CUDA stream.
+"""
+import os
+
+import torch
+
+from . import _lib
+
+_pack_cache = {}
+_USE_CACHE = os.environ.get("DEVO_B200_CORR_CACHE", "1") != "0"
+_FORCE_GENERIC = os.environ.get("DEVO_B200_CORR_IMPL", "") == "generic"
+
+
+def _check_common(fmap1, fmap2, coords, ii, jj):
+    _lib.require_cuda(fmap1, fmap2, coords, ii, jj)
+    if fmap1.dim() != 5 or fmap2.dim() != 5 or coords.dim() != 5:
+        raise RuntimeError("cuda_corr: fmap1 [B,Np,C,P,P], fmap2 [B,Nf,C,H,W], coords [B,E,2,P,P] expected")
+    if fmap1.dtype != fmap2.dtype:
+        raise RuntimeError("cuda_corr: fmap1/fmap2 dtype mismatch (%s vs %s)" % (fmap1.dtype, fmap2.dtype))
+    if fmap1.shape[2] != fmap2.shape[2]:
+        raise RuntimeError("cuda_corr: channel mismatch")
+    _lib.require_dtype(coords, torch.float32, "coords")
+    _lib.require_dtype(ii, torch.int64, "ii")
+    _lib.require_dtype(jj, torch.int64, "jj")
+    if ii.numel() != coords.shape[1] or jj.numel() != coords.shape[1]:
+        raise RuntimeError("cuda_corr: ii/jj length must equal coords.shape[1]")
+
+
+def pack_pixel_major(fmap, pool=1):
+    """planar [N,C,H,W] -> pixel-major [N,H//pool,W//pool,C] (average pooled); f16/bf16"""
+    _lib.require_cuda(fmap)
+    fmap = fmap.contiguous()
+    N, C, H, W = fmap.shape
+    out = torch.empty(N, H // pool, W // pool, C, dtype=fmap.dtype, device=fmap.device)
+    _lib.check(_lib.lib().devo_pyramid_pack(fmap.data_ptr(), out.data_ptr(), _lib.dtype_code(fmap),
+                                            N, C, H, W, pool, _lib.stream_ptr(fmap.device)), "pyramid_pack")
+    return out
+
+
+def pack_gmap(gmap):
+    """planar [Np,C,P,P] -> [Np,P*P,C]"""
+    _lib.require_cuda(gmap)
+    gmap = gmap.contiguous()
+    Np, C = gmap.shape[0], gmap.shape[1]
+    PP = gmap.shape[2] * gmap.shape[3]
+    out = torch.empty(Np, PP, C, dtype=gmap.dtype, device=gmap.device)
+    _lib.check(_lib.lib().devo_gmap_pack(gmap.data_ptr(), out.data_ptr(), _lib.dtype_code(gmap), Np, C, PP,
+                                         _lib.stream_ptr(gmap.device)), "gmap_pack")
+    return out
+
+
+def _cached(t, fn):
+    if not _USE_CACHE:
+        return fn(t)
+    key = (t.data_ptr(), tuple(t.shape), t.dtype, t.device)
+    hit = _pack_cache.get(key)
+    if hit is not None and hit[0] == t._version:
+        return hit[1]
+    out = fn(t)
+    if len(_pack_cache) > 16:
+        _pack_cache.clear()
+    _pack_cache[key] = (t._version, out)
+    return out
+
+
+def lookup_fused(gmap_pm, levels_pm, scales, coords, ii, jj):
+    """fused multi-level lookup on pixel-major buffers.
+    gmap_pm [Np,9,C]; levels_pm: list of [Nf,H_l,W_l,C]; coords [E,2,3,3] f32 (level-1 resolution).
+    returns [E, 49*9*L] (dtype of the features), levels interleaved on the last axis exactly like
+    torch.stack(corrs, -1).view(1, E, -1) in devo/devo.py:217."""
+    L = len(levels_pm)
+    E = coords.shape[0]
+    Np, _, C = gmap_pm.shape
+    out = torch.empty(E, 49 * 9 * L, dtype=gmap_pm.dtype, device=gmap_pm.device)
+    pyr = _lib.PyramidStruct()
+    pyr.n_levels = L
+    for l, lv in enumerate(levels_pm):
+        pyr.level[l] = lv.data_ptr()
+        pyr.H[l] = lv.shape[1]
+        pyr.W[l] = lv.shape[2]
+        pyr.scale[l] = float(scales[l])
+    import ctypes
+    _lib.check(_lib.lib().devo_corr_lookup_fused(gmap_pm.data_ptr(), ctypes.addressof(pyr), coords.data_ptr(),
+                                                 ii.data_ptr(), jj.data_ptr(), out.data_ptr(),
+                                                 _lib.dtype_code(gmap_pm), Np, levels_pm[0].shape[0], C, E,
+                                                 _lib.stream_ptr(gmap_pm.device)), "corr_lookup_fused")
+    return out
+
+
+def _fast_eligible(fmap1, fmap2, coords, radius):
+    return (not _FORCE_GENERIC and fmap1.dtype in (torch.float16, torch.bfloat16) and fmap1.shape[0] == 1
+            and fmap1.shape[2] in (64, 128) and fmap1.shape[3] == 3 and fmap1.shape[4] == 3 and radius == 3)
+
+
+def forward(fmap1, fmap2, coords, ii, jj, radius):
+    """cuda_corr.forward -> [corr [B,E,2r+1,2r+1,P,P]]  (dims 2,3 = x-offset, y-offset)"""
+    _check_common(fmap1, fmap2, coords, ii, jj)
+    fmap1 = fmap1.contiguous()
+    fmap2 = fmap2.contiguous()
+    coords = coords.contiguous()
+    ii = ii.contiguous()
+    jj = jj.contiguous()
+    B, Np, C, P, _ = fmap1.shape
+    _, Nf, _, H, W = fmap2.shape
+    E = coords.shape[1]
+    D1 = 2 * radius + 1
+    if E > 0 and _fast_eligible(fmap1, fmap2, coords, radius):
+        lv = _cached(fmap2, lambda t: pack_pixel_major(t[0], 1))
+        g = _cached(fmap1, lambda t: pack_gmap(t[0]))
+        out = lookup_fused(g, [lv], [1.0], coords[0], ii, jj)
+        return [out.view(1, E, D1, D1, P, P)]
+    out = torch.empty(B, E, D1, D1, P, P, dtype=fmap1.dtype, device=fmap1.device)
+    _lib.check(_lib.lib().devo_corr_forward(fmap1.data_ptr(), fmap2.data_ptr(), coords.data_ptr(), ii.data_ptr(),
+                                            jj.data_ptr(), out.data_ptr(), _lib.dtype_code(fmap1), B, Np, Nf, C, H, W,
+                                            E, P, radius, _lib.stream_ptr(fmap1.device)), "corr_forward")
+    return [out]
+
+
+def backward(fmap1, fmap2, coords, ii, jj, corr_grad, radius):
+    """cuda_corr.backward -> [fmap1_grad, fmap2_grad]"""
+    _check_common(fmap1, fmap2, coords, ii, jj)
+    _lib.require_cuda(corr_grad)
+    fmap1 = fmap1.contiguous()
+    fmap2 = fmap2.contiguous()
+    coords = coords.contiguous()
+    grad = corr_grad.to(torch.float32).contiguous()
+    B, Np, C, P, _ = fmap1.shape
+    _, Nf, _, H, W = fmap2.shape
+    E = coords.shape[1]
+    g1 = torch.empty_like(fmap1)
+    g2 = torch.empty_like(fmap2)
+    _lib.check(_lib.lib().devo_corr_backward(fmap1.data_ptr(), fmap2.data_ptr(), coords.data_ptr(),
+                                             ii.contiguous().data_ptr(), jj.contiguous().data_ptr(), grad.data_ptr(),
+                                             g1.data_ptr(), g2.data_ptr(), _lib.dtype_code(fmap1), B, Np, Nf, C, H, W,
+                                             E, P, radius, _lib.stream_ptr(fmap1.device)), "corr_backward")
+    return [g1, g2]
+
+
+def patchify_forward(net, coords, radius):
+    """cuda_corr.patchify_forward -> [patches [B,M,C,2r+2,2r+2]]"""
+    _lib.require_cuda(net, coords)
+    if net.dim() != 4 or coords.dim() != 3 or coords.shape[-1] != 2:
+        raise RuntimeError("cuda_corr.patchify_forward: net [B,C,H,W], coords [B,M,2] expected")
+    _lib.require_dtype(coords, torch.float32, "coords")
+    net = net.contiguous()
+    coords = coords.contiguous()
+    B, C, H, W = net.shape
+    M = coords.shape[1]
+    D = 2 * radius + 2
+    out = torch.empty(B, M, C, D, D, dtype=net.dtype, device=net.device)
+    _lib.check(_lib.lib().devo_patchify_forward(net.data_ptr(), coords.data_ptr(), out.data_ptr(), _lib.dtype_code(net),
+                                                B, C, H, W, M, radius, _lib.stream_ptr(net.device)), "patchify_forward")
+    return [out]
+
+
+def patchify_backward(net, coords, gradient, radius):
+    """cuda_corr.patchify_backward -> [net_grad [B,C,H,W]]"""
+    _lib.require_cuda(net, coords, gradient)
+    _lib.require_dtype(coords, torch.float32, "coords")
+    coords = coords.contiguous()
+    gradient = gradient.to(net.dtype).contiguous()
+    B, C, H, W = net.shape
+    M = coords.shape[1]
+    out = torch.empty(B, C, H, W, dtype=net.dtype, device=net.device)
+    _lib.check(_lib.lib().devo_patchify_backward(gradient.data_ptr(), coords.data_ptr(), out.data_ptr(),
+                                                 _lib.dtype_code(net), B, C, H, W, M, radius,
+                                                 _lib.stream_ptr(net.device)), "patchify_backward")
+    return [out]

@@ -1,0 +1,133 @@
+"""UpdateOperator -- the B200-native form of one DEVO update iteration
+(the body of DEVO.update, devo/devo.py:308-338):
+
+    reproject -> correlation lookup (all pyramid levels) -> context gather -> Update (GRU)
+    -> target/weight -> fastba.BA(iterations)
+
+All state lives in fixed device buffers (HBM layout below), every op is enqueued on one
+stream with no host synchronisation, so the whole iteration is captured once in a CUDA graph
+and replayed.  Feature pyramids and patch features are held PIXEL-MAJOR (channels last) --
+the layout the TMA-staged lookup kernel wants; `ingest_frame` converts a planar frame once,
+when it enters the ring buffer (replaces devo/devo.py:523-527 + pyramidify, utils.py:70-79).
+
+  poses      f32 [1, n_frames, 7]        patches  f32 [1, n_patches, 3, 3, 3]
+  intrinsics f32 [1, n_frames, 4]        net      f16 [1, E, 384]
+  imap       f16 [1, n_patches, 384]     gmap_pm  f16 [n_patches, 9, C]
+  levels_pm  f16 [n_frames, H/s, W/s, C] for s in levels
+  ii, jj, kk i64 [E]
+"""
+import torch
+
+from . import cuda_ba, cuda_corr, projective_ops as pops
+
+
+class UpdateOperator:
+    def __init__(self, update, n_frames, patches_per_frame, n_edges, H, W, C=128, dim=384, levels=(1, 4),
+                 device="cuda", feat_dtype=torch.float16, ba_iterations=2, t0=1, t1=None):
+        self.update = update
+        self.Nf, self.M, self.E = n_frames, patches_per_frame, n_edges
+        self.Np = n_frames * patches_per_frame
+        self.H, self.W, self.C, self.dim = H, W, C, dim
+        self.levels = tuple(levels)
+        self.device = torch.device(device)
+        self.feat_dtype = feat_dtype
+        self.ba_iterations = ba_iterations
+        self.t0 = t0
+        self.t1 = n_frames if t1 is None else t1
+        dev, f32, i64 = self.device, torch.float32, torch.int64
+        self.poses = torch.zeros(1, self.Nf, 7, dtype=f32, device=dev)
+        self.poses[..., 6] = 1.0
+        self.patches = torch.zeros(1, self.Np, 3, 3, 3, dtype=f32, device=dev)
+        self.intrinsics = torch.zeros(1, self.Nf, 4, dtype=f32, device=dev)
+        self.ii = torch.zeros(self.E, dtype=i64, device=dev)
+        self.jj = torch.zeros(self.E, dtype=i64, device=dev)
+        self.kk = torch.zeros(self.E, dtype=i64, device=dev)
+        self.pair_key = torch.zeros(self.E, dtype=i64, device=dev)
+        self.net = torch.zeros(1, self.E, dim, dtype=feat_dtype, device=dev)
+        self.imap = torch.zeros(1, self.Np, dim, dtype=feat_dtype, device=dev)
+        self.gmap_pm = torch.zeros(self.Np, 9, C, dtype=feat_dtype, device=dev)
+        self.levels_pm = [torch.zeros(self.Nf, H // s, W // s, C, dtype=feat_dtype, device=dev) for s in self.levels]
+        self.lmbda = torch.as_tensor([1e-4], dtype=f32, device=dev)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.status_sticky = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.plan_kk = None
+        self.plan_ij = None
+        self._graph = None
+        self._pristine = None
+        self.delta = None
+        self.weight = None
+        self.coords = None
+
+    # ---- state -------------------------------------------------------------------------------
+    def set_graph(self, ii, jj, kk):
+        """install the edge list (patch kk observed from frame ii in frame jj)"""
+        self.ii.copy_(ii)
+        self.jj.copy_(jj)
+        self.kk.copy_(kk)
+        torch.add(self.ii * 12345, self.jj, out=self.pair_key)
+        if self.plan_kk is None:
+            self.plan_kk = cuda_ba.GraphPlan(self.kk, self.jj, self.Np, self.Nf)
+            self.plan_ij = cuda_ba.GraphPlan(self.pair_key, self.kk, -1, -1, want_neighbors=False)
+
+    def ingest_frame(self, idx, fmap, gmap_patches=None, imap_patches=None):
+        """fmap [C,H,W] planar features of frame `idx` -> all pixel-major pyramid levels;
+        gmap_patches [M,C,3,3], imap_patches [M,dim] -> patch feature buffers"""
+        f = fmap.reshape(1, self.C, self.H, self.W).to(self.feat_dtype)
+        for l, s in enumerate(self.levels):
+            self.levels_pm[l][idx:idx + 1].copy_(cuda_corr.pack_pixel_major(f, s))
+        if gmap_patches is not None:
+            self.gmap_pm[idx * self.M:(idx + 1) * self.M].copy_(cuda_corr.pack_gmap(gmap_patches.to(self.feat_dtype)))
+        if imap_patches is not None:
+            self.imap[0, idx * self.M:(idx + 1) * self.M].copy_(imap_patches.to(self.feat_dtype))
+
+    def snapshot_geometry(self):
+        self._pristine = (self.poses.clone(), self.patches.clone())
+
+    # ---- one iteration -----------------------------------------------------------------------
+    def _iteration(self, reset_geometry=False):
+        if reset_geometry and self._pristine is not None:
+            self.poses.copy_(self._pristine[0])
+            self.patches.copy_(self._pristine[1])
+        # (1) reproject: [1,E,2,3,3]
+        coords = pops.transform_fused(self.poses, self.patches, self.intrinsics, self.ii, self.jj, self.kk, layout=1)
+        # (2) correlation lookup over all levels, output already in the GRU's [E, 882] layout
+        corr = cuda_corr.lookup_fused(self.gmap_pm, self.levels_pm, self.levels, coords[0], self.kk, self.jj)
+        # (3) graph analysis on the device (neighbours, patch groups, frame-pair groups)
+        self.plan_kk.update()
+        self.plan_ij.update()
+        # (4) GRU
+        with torch.autocast("cuda", dtype=self.feat_dtype):
+            ctx = self.imap[:, self.kk]
+            net, (delta, weight, _) = self.update.forward_planned(
+                self.net, ctx, corr.view(1, self.E, -1), self.plan_kk, self.plan_ij, self.Np, self.Nf * self.Nf)
+        self.net.copy_(net)
+        # (5) BA targets and in-place Gauss-Newton
+        target = coords[:, :, :, 1, 1] + delta.float()
+        weight = weight.float()
+        cuda_ba.forward_async(self.poses, self.patches, self.intrinsics, target, weight, self.lmbda,
+                              self.ii, self.jj, self.kk, self.t0, self.t1, self.ba_iterations, status=self.status)
+        torch.maximum(self.status_sticky, self.status.abs(), out=self.status_sticky)
+        self.coords, self.delta, self.weight = coords, delta, weight
+
+    @torch.no_grad()
+    def step(self, reset_geometry=False):
+        self._iteration(reset_geometry)
+
+    @torch.no_grad()
+    def capture(self, reset_geometry=False, warmup=3):
+        """capture one iteration into a CUDA graph (after `warmup` eager iterations)"""
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._iteration(reset_geometry)
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._iteration(reset_geometry)
+        self._graph = g
+        return g
+
+    def replay(self):
+        self._graph.replay()

@@ -1,0 +1,213 @@
+"""GPU parity: fastba.BA / neighbors / reproject / graph plan / projective transform /
+differentiable ba.BA (all through the C ABI) vs the CPU oracle.
+Tolerances: index outputs bit-exact; BA pose / inverse-depth updates <= 1e-5 absolute on
+well-conditioned synthetic graphs (BASELINE.json north_star); transform <= 1e-4 px."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ba as oba
+from oracle import fastba as ofba
+from oracle import neighbors as onb
+from oracle import pops as opops
+from problems import ba_problem, fully_connected_graph
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_ba(P, t0, t1, iters, poses=None, patches=None):
+    from devo_b200 import fastba
+    poses = (P["poses0"] if poses is None else poses).float().cuda().contiguous()
+    patches = (P["patches0"] if patches is None else patches).float().cuda().contiguous()
+    fastba.BA(poses, patches, P["intrinsics"].float().cuda(), P["targets"].float().cuda(), P["weights"].float().cuda(),
+              torch.tensor([1e-4], device="cuda"), P["ii"].cuda(), P["jj"].cuda(), P["kk"].cuda(), t0, t1, iters)
+    return poses, patches
+
+
+def _oracle_ba(P, t0, t1, iters):
+    # same fp32-rounded inputs as the GPU sees, arithmetic in fp64
+    f = lambda t: t.float().double()
+    return ofba.ba(f(P["poses0"]), f(P["patches0"][0]), f(P["intrinsics"]), f(P["targets"]), f(P["weights"]),
+                   torch.tensor([1e-4]).float().double(), P["ii"], P["jj"], P["kk"], t0, t1, iters)
+
+
+@pytest.mark.parametrize("nf,m,t0,iters", [(2, 32, 1, 2), (4, 24, 1, 2), (8, 96, 1, 2), (8, 96, 1, 10), (6, 16, 3, 3)])
+def test_ba_vs_oracle(nf, m, t0, iters):
+    P = ba_problem(n_frames=nf, patches_per_frame=m, seed=1234 + nf, init="perturbed", noise=0.3)
+    poses, patches = _run_ba(P, t0, nf, iters)
+    po, xo, st = _oracle_ba(P, t0, nf, iters)
+    assert st == 0
+    dp = (poses[0].double().cpu() - po).abs().max().item()
+    dd = (patches[0, :, 2].double().cpu() - xo[:, 2]).abs().max().item()
+    assert dp <= 1e-5, dp
+    assert dd <= 1e-5, dd
+    # poses outside [t0,t1) and the x/y channels are untouched, depth is constant over a patch
+    assert torch.equal(poses[0, :t0].cpu(), P["poses0"][0, :t0].float())
+    assert torch.equal(patches[0, :, :2].cpu(), P["patches0"][0, :, :2].float())
+    assert torch.equal(patches[0, :, 2], patches[0, :, 2, :1, :1].expand(-1, 3, 3))
+
+
+def test_ba_from_identity_converges_like_oracle():
+    """config 3 of BASELINE.json (8 keyframes x 96 patches, 10 GN iterations from identity poses)"""
+    P = ba_problem(n_frames=8, patches_per_frame=96, seed=1234)
+    poses, patches = _run_ba(P, 1, 8, 10)
+    po, xo, st = _oracle_ba(P, 1, 8, 10)
+    assert st == 0
+    # after 10 iterations from a poor start, fp32 Jacobians vs fp64 differ a little more
+    assert (poses[0].double().cpu() - po).abs().max().item() <= 2e-4
+    c = opops.transform(poses.double().cpu(), patches.double().cpu(), P["intrinsics"], P["ii"], P["jj"], P["kk"])
+    assert (c[..., 1, 1, :] - P["targets"]).norm(dim=-1).median() < 1.0
+
+
+def test_ba_structure_only_zero_iterations_and_buffer_views():
+    from devo_b200 import fastba
+    P = ba_problem(n_frames=4, patches_per_frame=16, seed=3, init="perturbed")
+    poses, patches = _run_ba(P, 4, 4, 1)            # t1 - t0 == 0 => structure only (ba_cuda.cu:494-506)
+    po, xo, _ = _oracle_ba(P, 4, 4, 1)
+    assert torch.equal(poses.cpu(), P["poses0"].float())
+    assert (patches[0, :, 2].double().cpu() - xo[:, 2]).abs().max().item() <= 1e-5
+    poses, patches = _run_ba(P, 1, 4, 0)
+    assert torch.equal(poses.cpu(), P["poses0"].float()) and torch.equal(patches.cpu(), P["patches0"].float())
+    # DEVO passes views of big ring buffers (devo.py:151-177): poses [1,4096,7], patches [1,4096*M,3,3,3]
+    big_p = torch.zeros(1, 64, 7, device="cuda")
+    big_p[..., 6] = 1
+    big_x = torch.zeros(1, 64 * 16, 3, 3, 3, device="cuda")
+    big_p[0, :4] = P["poses0"][0].float().cuda()
+    big_x[0, :64] = P["patches0"][0].float().cuda()
+    intr = torch.zeros(1, 64, 4, device="cuda")
+    intr[0, :] = P["intrinsics"][0, 0].float().cuda()
+    fastba.BA(big_p, big_x, intr, P["targets"].float().cuda(), P["weights"].float().cuda(),
+              torch.tensor([1e-4], device="cuda"), P["ii"].cuda(), P["jj"].cuda(), P["kk"].cuda(), 1, 4, 2)
+    p2, x2 = _run_ba(P, 1, 4, 2)
+    assert torch.equal(big_p[0, :4], p2[0]) and torch.equal(big_x[0, :64], x2[0])      # deterministic, layout independent
+    assert torch.equal(big_p[0, 4:, :6], torch.zeros(60, 6, device="cuda"))
+
+
+def test_ba_masked_edges_and_failure_status():
+    from devo_b200 import cuda_ba
+    P = ba_problem(n_frames=3, patches_per_frame=8, seed=9, init="perturbed")
+    # targets far away (> 128 px) mask every edge: nothing may move except the depth regulariser (dZ = 0)
+    far = dict(P)
+    far["targets"] = P["targets"] + 1000.0
+    poses, patches = _run_ba(far, 1, 3, 2)
+    assert torch.allclose(poses.cpu(), P["poses0"].float(), atol=1e-6)
+    # NaN pose => non-finite system => status = iteration+1, and STRICT raises like linalg.cholesky
+    bad = P["poses0"].clone()
+    bad[0, 1, 0] = float("nan")
+    st = cuda_ba.forward_async(bad.float().cuda(), P["patches0"].float().cuda(), P["intrinsics"].float().cuda(),
+                               P["targets"].float().cuda(), P["weights"].float().cuda(), torch.tensor([1e-4], device="cuda"),
+                               P["ii"].cuda(), P["jj"].cuda(), P["kk"].cuda(), 1, 3, 2)
+    assert int(st.item()) == 1
+    with pytest.raises(RuntimeError):
+        _run_ba(P, 1, 3, 2, poses=bad)
+
+
+@pytest.mark.parametrize("E,nk,nj", [(1, 1, 1), (7, 2, 3), (300, 20, 6), (5000, 300, 8), (12000, 500, 12), (40000, 2000, 22)])
+def test_neighbors_bit_exact(E, nk, nj):
+    from devo_b200 import fastba
+    rng = np.random.RandomState(E)
+    kk = torch.from_numpy(rng.randint(0, nk, E))
+    jj = torch.from_numpy(rng.randint(0, nj, E))
+    ix, jx = fastba.neighbors(kk.cuda(), jj.cuda())
+    rx, ry = onb.neighbors(kk, jj)
+    assert ix.dtype == torch.int64 and ix.is_cuda
+    assert torch.equal(ix.cpu(), rx) and torch.equal(jx.cpu(), ry)
+
+
+def test_graph_plan_equals_torch_unique():
+    from devo_b200 import cuda_ba
+    for E, nk in [(50, 7), (6144, 768), (20000, 1500)]:
+        rng = np.random.RandomState(E)
+        ka = torch.from_numpy(rng.randint(0, nk, E) * 3 + 5)
+        kb = torch.from_numpy(rng.randint(0, 9, E))
+        pl = cuda_ba.GraphPlan(ka.cuda(), kb.cuda())
+        uq, inv = torch.unique(ka, sorted=True, return_inverse=True)
+        G = int(pl.ngroups.item())
+        assert G == uq.numel()
+        assert torch.equal(pl.gkey[:G].cpu(), uq) and torch.equal(pl.gid.cpu().long(), inv)
+        order = np.lexsort((np.arange(E), kb.numpy(), ka.numpy()))
+        assert torch.equal(pl.perm.cpu().long(), torch.from_numpy(order))
+        counts = torch.bincount(inv, minlength=G)
+        assert torch.equal(pl.gstart[:G + 1].cpu().long(), torch.cat([torch.zeros(1, dtype=torch.long), counts.cumsum(0)]))
+    ii, jj, kk = fully_connected_graph(8, 96)
+    ix, jx = cuda_ba.neighbors(kk.cuda(), jj.cuda())
+    e = torch.arange(6144)
+    assert torch.equal(ix.cpu(), torch.where(e % 8 == 0, -1, e - 1)) and torch.equal(jx.cpu(), torch.where(e % 8 == 7, -1, e + 1))
+
+
+def test_reproject_and_transform_vs_oracle():
+    from devo_b200 import fastba, projective_ops as pops, lietorch as lt
+    P = ba_problem(n_frames=5, patches_per_frame=20, seed=21, init="perturbed")
+    f32 = lambda t: t.float().cuda()
+    ii, jj, kk = P["ii"].cuda(), P["jj"].cuda(), P["kk"].cuda()
+    rp = fastba.reproject(f32(P["poses0"]), f32(P["patches0"]), f32(P["intrinsics"]), ii, jj, kk)
+    ro = ofba.reproject(P["poses0"].float(), P["patches0"][0].float(), P["intrinsics"].float(), P["ii"], P["jj"], P["kk"])
+    assert rp.shape == (1, ii.numel(), 2, 3, 3)
+    assert (rp.double().cpu() - ro).abs().max().item() <= 1e-3 * 1.0      # pixels, fp32 vs fp64 on O(100) px values
+    G = lt.SE3(f32(P["poses0"]))
+    a = (f32(P["patches0"]), f32(P["intrinsics"]), ii, jj, kk)
+    od = lambda t: t.float().double()
+    oa = (od(P["poses0"]), od(P["patches0"]), od(P["intrinsics"]), P["ii"], P["jj"], P["kk"])
+    c, v, (Ji, Jj, Jz) = pops.transform(G, *a, jacobian=True)          # fused kernel (no grad)
+    co, vo, (Jio, Jjo, Jzo) = opops.transform(*oa, jacobian=True)
+    assert c.shape == co.shape and (c.double().cpu() - co).abs().max().item() <= 1e-3
+    assert torch.equal(v.cpu().double(), vo)
+    for x, y in ((Ji, Jio), (Jj, Jjo), (Jz, Jzo)):
+        assert x.shape == y.shape
+        assert ((x.double().cpu() - y).abs().max() / y.abs().max()).item() <= 1e-5
+    ct = pops.transform(G, *a, tonly=True)
+    assert (ct.double().cpu() - opops.transform(*oa, tonly=True)).abs().max().item() <= 1e-3
+    # composed (autograd) path gives the same numbers as the fused kernel
+    pr = a[0].clone().requires_grad_(True)
+    c2, v2, (Ji2, Jj2, Jz2) = pops.transform(G, pr, *a[1:], jacobian=True)
+    assert (c2 - c).abs().max().item() <= 2e-3 and torch.equal(v2, v)
+    assert ((Ji2 - Ji).abs().max() / Ji.abs().max()).item() <= 1e-4 and ((Jz2 - Jz).abs().max() / Jz.abs().max()).item() <= 1e-4
+    fm = pops.flow_mag(G, *a, beta=0.5)
+    assert (fm.double().cpu() - opops.flow_mag(*oa, beta=0.5)).abs().max().item() <= 2e-3
+
+
+def test_differentiable_ba_vs_oracle_and_golden():
+    """devo_b200.ba.BA (training path, fp64 on CUDA) == reference ba.py golden vectors (config 1)"""
+    import os
+    from devo_b200 import ba as pba, lietorch as lt
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "ba_config1.pt"))
+    P = g["problem"]
+    Gs, X = lt.SE3(P["poses0"].cuda()), P["patches0"].cuda()
+    cu = lambda t: t.cuda()
+    for it, (pg, dg) in enumerate(g["traj"][:4]):
+        Gs, X = pba.BA(Gs, X, cu(P["intrinsics"]), cu(P["targets"]), cu(P["weights"]), 1e-4, cu(P["ii"]), cu(P["jj"]),
+                       cu(P["kk"]), P["bounds"], ep=10.0, fixedp=1)
+        assert torch.allclose(Gs.data.cpu(), pg, atol=1e-8), (it, (Gs.data.cpu() - pg).abs().max())
+        assert torch.allclose(X[:, :, 2, 1, 1].cpu(), dg, atol=1e-8)
+    g2 = torch.load(os.path.join(os.path.dirname(__file__), "golden", "ba_4x12.pt"))
+    P = g2["problem"]
+    a = (cu(P["intrinsics"]), cu(P["targets"]), cu(P["weights"]), 1e-4, cu(P["ii"]), cu(P["jj"]), cu(P["kk"]))
+    G1, X1 = pba.BA(lt.SE3(cu(P["poses0"])), cu(P["patches0"]), *a, [20, 20, 140, 100], ep=10.0, fixedp=1)
+    assert torch.allclose(G1.data.cpu(), g2["poses_a"], atol=1e-8) and torch.allclose(X1[:, :, 2, 1, 1].cpu(), g2["depth_a"], atol=1e-8)
+    G2, X2 = pba.BA(lt.SE3(cu(P["poses0"])), cu(P["patches0"]), *a, P["bounds"], ep=100.0, fixedp=2, structure_only=True)
+    assert torch.allclose(G2.data.cpu(), g2["poses_b"], atol=1e-10) and torch.allclose(X2[:, :, 2, 1, 1].cpu(), g2["depth_b"], atol=1e-8)
+    # gradients flow to weights/targets/patches (training uses them)
+    w = cu(P["weights"]).clone().requires_grad_(True)
+    G3, X3 = pba.BA(lt.SE3(cu(P["poses0"])), cu(P["patches0"]), a[0], a[1], w, *a[3:], P["bounds"], ep=10.0, fixedp=1)
+    (G3.data.sum() + X3.sum()).backward()
+    assert torch.isfinite(w.grad).all() and w.grad.abs().sum() > 0
+
+
+def test_segment_softmax_sum_and_update_planned_equals_reference_semantics():
+    from devo_b200 import cuda_ba
+    from devo_b200.update import Update
+    torch.manual_seed(0)
+    ii, jj, kk = [t.cuda() for t in fully_connected_graph(4, 12)]
+    E = ii.numel()
+    perm = torch.randperm(E, device="cuda")          # unsorted edge order
+    ii, jj, kk = ii[perm], jj[perm], kk[perm]
+    up = Update(3).cuda().eval()
+    net = torch.randn(1, E, 384, device="cuda")
+    inp = torch.randn(1, E, 384, device="cuda")
+    corr = torch.randn(1, E, 882, device="cuda")
+    with torch.no_grad():
+        n1, (d1, w1, _) = up(net, inp, corr, None, ii, jj, kk)
+        pk = cuda_ba.GraphPlan(kk, jj, 48, 4)
+        pij = cuda_ba.GraphPlan(ii * 12345 + jj, kk, -1, -1, want_neighbors=False)
+        n2, (d2, w2, _) = up.forward_planned(net, inp, corr, pk, pij, 48, 16)
+    assert torch.allclose(n1, n2, atol=2e-4, rtol=1e-4) and torch.allclose(d1, d2, atol=2e-4) and torch.allclose(w1, w2, atol=2e-4)

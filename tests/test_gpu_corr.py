@@ -1,0 +1,166 @@
+"""GPU parity: correlation lookup / patch gather (through the C ABI) vs the CPU oracle.
+Tolerances (BASELINE.json north_star): correlation <= 1e-4 relative for fp32 inputs;
+patchify / index scatter bit-exact; half inputs: error vs the fp64 oracle is bounded by
+half output rounding (our accumulation is fp32, the reference's is half)."""
+import pytest
+import torch
+
+from oracle import corr as ocorr
+from problems import corr_problem
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def _rand_problem(B, Np, Nf, C, H, W, E, P, seed, dtype, spread=4.0):
+    g = torch.Generator().manual_seed(seed)
+    f1 = (torch.randn(B, Np, C, P, P, generator=g) / 4).to(dtype)
+    f2 = (torch.randn(B, Nf, C, H, W, generator=g) / 4).to(dtype)
+    cx = torch.rand(B, E, 1, 1, 1, generator=g) * (W + 8) - 4
+    cy = torch.rand(B, E, 1, 1, 1, generator=g) * (H + 8) - 4
+    coords = torch.cat([cx + torch.rand(B, E, 1, P, P, generator=g) * spread, cy + torch.rand(B, E, 1, P, P, generator=g) * spread], 2)
+    ii = torch.randint(0, Np, (E,), generator=g)
+    jj = torch.randint(0, Nf, (E,), generator=g)
+    return f1, f2, coords.float(), ii, jj
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.float64, 1e-12), (torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)])
+@pytest.mark.parametrize("R,P,C", [(3, 3, 128), (1, 3, 24), (2, 2, 8)])
+def test_generic_forward_vs_oracle(dtype, tol, R, P, C):
+    from devo_b200 import _lib
+    f1, f2, coords, ii, jj = _rand_problem(2, 20, 3, C, 30, 40, 150, P, 7, dtype)
+    ref = ocorr.corr_forward(f1, f2, coords, ii, jj, R)
+    D1 = 2 * R + 1
+    out = torch.empty(2, 150, D1, D1, P, P, dtype=dtype, device="cuda")
+    a = [t.cuda().contiguous() for t in (f1, f2, coords, ii, jj)]
+    _lib.check(_lib.lib().devo_corr_forward(a[0].data_ptr(), a[1].data_ptr(), a[2].data_ptr(), a[3].data_ptr(),
+                                            a[4].data_ptr(), out.data_ptr(), _lib.dtype_code(a[0]), 2, 20, 3, C, 30, 40,
+                                            150, P, R, _lib.stream_ptr()), "corr_forward")
+    assert _rel(out, ref) <= tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("C", [128, 64])
+def test_fast_path_vs_oracle_and_generic(dtype, C):
+    """cuda_corr.forward takes the TMA + tcgen05 path for (half, C in {64,128}, P=3, r=3, B=1)"""
+    from devo_b200 import cuda_corr
+    f1, f2, coords, ii, jj = _rand_problem(1, 40, 5, C, 30, 40, 700, 3, 11, dtype, spread=2.5)
+    coords[0, :50] += 1000.0           # windows entirely out of bounds -> zeros
+    coords[0, 50:80, :, 2, 2] += 7.0   # one patch pixel far away -> per-output direct path
+    ref = ocorr.corr_forward(f1, f2, coords, ii, jj, 3)
+    a = [t.cuda() for t in (f1, f2, coords, ii, jj)]
+    assert cuda_corr._fast_eligible(a[0], a[1], a[2], 3)
+    (out,) = cuda_corr.forward(*a, 3)
+    assert out.shape == ref.shape and out.dtype == dtype
+    tol = 2e-3 if dtype == torch.float16 else 1.6e-2
+    assert _rel(out, ref) <= tol, _rel(out, ref)
+    assert out[0, :50].abs().max().item() == 0.0
+    # generic path on the same inputs agrees to output rounding
+    from devo_b200 import _lib
+    gen = torch.empty_like(out)
+    _lib.check(_lib.lib().devo_corr_forward(a[0].data_ptr(), a[1].data_ptr(), a[2].data_ptr(), a[3].data_ptr(),
+                                            a[4].data_ptr(), gen.data_ptr(), _lib.dtype_code(a[0]), 1, 40, 5, C, 30, 40,
+                                            700, 3, 3, _lib.stream_ptr()), "corr_forward")
+    assert _rel(out, gen) <= tol
+
+
+def test_fused_multilevel_layout_matches_stack():
+    """lookup_fused over levels [1,4] == torch.stack([corr(l) for l], -1).view(1,E,-1) (devo.py:210-217)"""
+    from devo_b200 import cuda_corr
+    Pm = corr_problem(n_frames=3, patches_per_frame=20, C=128, H4=60, W4=80, seed=3)
+    gm = cuda_corr.pack_gmap(Pm["gmap"][0].cuda())
+    lv = [cuda_corr.pack_pixel_major(Pm["fmap"][0].cuda(), s) for s in (1, 4)]
+    # the packer's pooled level equals avg_pool2d of the planar map (bit exact in half)
+    for l, s in enumerate((1, 4)):
+        assert torch.equal(lv[l].permute(0, 3, 1, 2).cpu(), Pm["pyramid"][l][0])
+    coords = Pm["coords"].cuda()
+    ii, jj = Pm["kk"].cuda(), Pm["jj"].cuda()
+    out = cuda_corr.lookup_fused(gm, lv, (1, 4), coords[0], ii, jj)
+    refs = [ocorr.corr_forward(Pm["gmap"], Pm["pyramid"][l], Pm["coords"] / s, Pm["kk"], Pm["jj"], 3) for l, s in enumerate((1, 4))]
+    ref = torch.stack(refs, -1).reshape(1, Pm["kk"].numel(), -1)
+    assert out.shape == (Pm["kk"].numel(), 882)
+    assert _rel(out, ref[0]) <= 2e-3
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.float64, 1e-11)])
+def test_backward_vs_oracle(dtype, tol):
+    from devo_b200 import cuda_corr
+    f1, f2, coords, ii, jj = _rand_problem(1, 12, 3, 16, 20, 24, 60, 3, 5, dtype)
+    g = torch.randn(1, 60, 7, 7, 3, 3)
+    r1, r2 = ocorr.corr_backward(f1, f2, coords, ii, jj, g, 3)
+    g1, g2 = cuda_corr.backward(f1.cuda(), f2.cuda(), coords.cuda(), ii.cuda(), jj.cuda(), g.cuda(), 3)
+    assert _rel(g1, r1) <= tol and _rel(g2, r2) <= tol
+
+
+def test_autograd_wrappers():
+    from devo_b200 import altcorr
+    f1, f2, coords, ii, jj = _rand_problem(1, 6, 2, 8, 12, 14, 20, 3, 9, torch.float32)
+    a = f1.cuda().requires_grad_(True)
+    b = f2.cuda().requires_grad_(True)
+    out = altcorr.corr(a, b, coords.cuda(), ii.cuda(), jj.cuda(), 3, 1)
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    r1, r2 = ocorr.corr_backward(f1, f2, coords, ii, jj, w.cpu(), 3)
+    assert _rel(a.grad, r1) <= 2e-5 and _rel(b.grad, r2) <= 2e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.float64, torch.bfloat16])
+@pytest.mark.parametrize("R", [0, 1, 3])
+def test_patchify_bit_exact(dtype, R):
+    from devo_b200 import cuda_corr, altcorr
+    g = torch.Generator().manual_seed(R)
+    net = torch.randn(2, 7, 13, 17, generator=g).to(dtype)
+    coords = torch.cat([torch.rand(2, 30, 1, generator=g) * 21 - 2, torch.rand(2, 30, 1, generator=g) * 17 - 2], -1)
+    coords[:, :10] = coords[:, :10].floor()
+    ref = ocorr.patchify_forward(net, coords, R)
+    (out,) = cuda_corr.patchify_forward(net.cuda(), coords.cuda(), R)
+    assert torch.equal(out.cpu(), ref)                     # pure copy => bit exact
+    if dtype in (torch.float32, torch.float64):
+        gr = torch.randn_like(ref)
+        (gb,) = cuda_corr.patchify_backward(net.cuda(), coords.cuda(), gr.cuda(), R)
+        assert _rel(gb, ocorr.patchify_backward(net, coords, gr, R)) <= 1e-5
+        pb = altcorr.patchify(net.cuda(), coords.cuda(), R)
+        assert _rel(pb, ocorr.patchify(net, coords, R)) <= 1e-5
+
+
+def test_empty_and_errors():
+    from devo_b200 import cuda_corr
+    f1 = torch.zeros(1, 4, 8, 3, 3, device="cuda")
+    f2 = torch.zeros(1, 2, 8, 5, 5, device="cuda")
+    e = torch.zeros(0, dtype=torch.long, device="cuda")
+    (o,) = cuda_corr.forward(f1, f2, torch.zeros(1, 0, 2, 3, 3, device="cuda"), e, e, 3)
+    assert o.shape == (1, 0, 7, 7, 3, 3)
+    with pytest.raises(RuntimeError):
+        cuda_corr.forward(f1.cpu(), f2.cpu(), torch.zeros(1, 0, 2, 3, 3), e.cpu(), e.cpu(), 3)   # no CPU fallback
+    with pytest.raises(RuntimeError):
+        cuda_corr.forward(f1, f2.half(), torch.zeros(1, 0, 2, 3, 3, device="cuda"), e, e, 3)
+
+
+def test_full_size_properties_s8():
+    """BASELINE.json config 2 at full size (E=6144, 160x120, C=128): size-independent properties --
+    linearity in fmap1, zero for out-of-bounds windows, level interleave, determinism."""
+    from devo_b200 import cuda_corr
+    Pm = corr_problem(seed=1234)
+    gm = cuda_corr.pack_gmap(Pm["gmap"][0].cuda())
+    lv = [cuda_corr.pack_pixel_major(Pm["fmap"][0].cuda(), s) for s in (1, 4)]
+    coords, ii, jj = Pm["coords"].cuda()[0], Pm["kk"].cuda(), Pm["jj"].cuda()
+    out = cuda_corr.lookup_fused(gm, lv, (1, 4), coords, ii, jj)
+    out2 = cuda_corr.lookup_fused(gm, lv, (1, 4), coords, ii, jj)
+    assert torch.equal(out, out2) and torch.isfinite(out).all()
+    outn = cuda_corr.lookup_fused(-gm, lv, (1, 4), coords, ii, jj)
+    assert torch.equal(outn, -out)                                     # exact: sign flip commutes with rounding
+    l0 = cuda_corr.lookup_fused(gm, lv[:1], (1,), coords, ii, jj)
+    assert torch.equal(out.view(-1, 441, 2)[..., 0], l0)
+    far = cuda_corr.lookup_fused(gm, lv, (1, 4), coords + 5000.0, ii, jj)
+    assert far.abs().max().item() == 0.0
+    # spot-check 64 random edges against the fp64 oracle
+    sel = torch.randperm(ii.numel(), generator=torch.Generator().manual_seed(0))[:64]
+    refs = [ocorr.corr_forward(Pm["gmap"], Pm["pyramid"][l], Pm["coords"][:, sel] / s, Pm["kk"][sel], Pm["jj"][sel], 3)
+            for l, s in enumerate((1, 4))]
+    ref = torch.stack(refs, -1).reshape(64, -1)
+    assert _rel(out[sel.cuda()], ref) <= 2e-3

@@ -1,0 +1,173 @@
+"""GPU parity: devo_b200.lietorch_backends (CUDA, through the C ABI) vs the CPU oracle on
+identical inputs, for the 19 ops x 4 groups x {fp32, fp64}; plus the reference's own
+test-suite properties (devo/lietorch/run_tests.py) on the CUDA backend.
+Tolerance: fp64 1e-10 abs/rel, fp32 2e-5 (floating point; identical formulas, different
+summation/contraction order)."""
+import os
+
+import pytest
+import torch
+
+from oracle import lie as olie
+from lie_harness import make_group, analytic_jacobian, numeric_jacobian
+
+pytestmark = pytest.mark.gpu
+GIDS = [1, 2, 3, 4]
+DIMS = {1: (3, 4), 2: (4, 5), 3: (6, 7), 4: (7, 8)}
+
+
+def _be():
+    from devo_b200 import lietorch_backends
+    return lietorch_backends
+
+
+def _close(a, b, dtype):
+    tol = 1e-10 if dtype == torch.float64 else 2e-5
+    a = a.detach().cpu().double()
+    b = b.detach().cpu().double()
+    assert a.shape == b.shape
+    err = (a - b).abs() / (1.0 + b.abs())
+    assert err.max().item() <= tol, err.max().item()
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("gid", GIDS)
+def test_all_19_ops_match_oracle(gid, dtype):
+    be = _be()
+    K, N = DIMS[gid]
+    torch.manual_seed(100 + gid)
+    n = 1000
+    a = (0.5 * torch.randn(n, K, dtype=torch.float64))
+    a[0] = 0                       # identity / small-angle branch
+    a[1] = 1e-7
+    a[2, :] = 0
+    a[2, K - 1 if gid in (2, 4) else 0] = 0.3   # pure scale / pure translation
+    b = torch.randn(n, K, dtype=torch.float64)
+    X = olie.expm(gid, a)
+    Y = olie.expm(gid, 0.7 * torch.randn(n, K, dtype=torch.float64))
+    X = X * (1.0 + 0.01 * torch.randn(n, 1, dtype=torch.float64)) if gid in (1, 3) else X   # un-normalised quaternions are renormalised
+    p3 = torch.randn(n, 3, dtype=torch.float64)
+    p4 = torch.randn(n, 4, dtype=torch.float64)
+    gK = torch.randn(n, K, dtype=torch.float64)
+    gN = torch.randn(n, N, dtype=torch.float64)
+    g3 = torch.randn(n, 3, dtype=torch.float64)
+    g4 = torch.randn(n, 4, dtype=torch.float64)
+
+    def c(t):
+        return t.to(dtype).cuda().contiguous()
+
+    def o(t):
+        return t.to(dtype)
+
+    cases = [
+        ("expm", (a,)), ("logm", (X,)), ("inv", (X,)), ("mul", (X, Y)), ("adj", (X, b)), ("adjT", (X, b)),
+        ("act", (X, p3)), ("act4", (X, p4)), ("as_matrix", (X,)), ("projector", (X,)), ("Jinv", (X, b)),
+        ("expm_backward", (gN, a)), ("logm_backward", (gK, X)), ("inv_backward", (gN, X)),
+        ("mul_backward", (gN, X, Y)), ("adj_backward", (gK, X, b)), ("adjT_backward", (gK, X, b)),
+        ("act_backward", (g3, X, p3)), ("act4_backward", (g4, X, p4)),
+    ]
+    assert len(cases) == 19
+    for name, args in cases:
+        got = getattr(be, name)(gid, *[c(t) for t in args])
+        ref = getattr(olie, name)(gid, *[o(t) for t in args])
+        if isinstance(ref, (list, tuple)):
+            assert len(got) == len(ref), name
+            for x, y in zip(got, ref):
+                _close(x, y, dtype)
+        else:
+            _close(got, ref, dtype)
+
+
+@pytest.mark.parametrize("gid", GIDS)
+def test_reference_properties_on_cuda(gid):
+    """run_tests.py:16-52 forward identities in fp64 on the CUDA backend"""
+    G = make_group(_be(), gid)
+    torch.manual_seed(gid)
+    dt = torch.float64
+    a = 0.2 * torch.randn(2 * 3 * 4 * 5, G.manifold_dim, dtype=dt, device="cuda")
+    assert torch.allclose(a, G.exp(a).log(), atol=1e-8)
+    X = G.exp(0.1 * torch.randn(120, G.manifold_dim, dtype=dt, device="cuda"))
+    z = (X * X.inv()).log()
+    assert torch.allclose(z, torch.zeros_like(z), atol=1e-8)
+    X = G.exp(torch.randn(120, G.manifold_dim, dtype=dt, device="cuda"))
+    b = torch.randn(120, G.manifold_dim, dtype=dt, device="cuda")
+    z = ((X * G.exp(b)) * (G.exp(X.adj(b)) * X).inv()).log()
+    assert torch.allclose(z, torch.zeros_like(z), atol=1e-8)
+    p = torch.randn(120, 3, dtype=dt, device="cuda")
+    ph = torch.cat([p, torch.ones_like(p[:, :1])], -1)
+    assert torch.allclose(X.act(p), torch.matmul(X.matrix(), ph[..., None])[..., 0][:, :3], atol=1e-8)
+
+
+@pytest.mark.parametrize("gid", GIDS)
+def test_reference_gradchecks_on_cuda(gid):
+    """run_tests.py:56-164 backward checks (finite differences, fp64)"""
+    G = make_group(_be(), gid)
+    torch.manual_seed(40 + gid)
+    dt = torch.float64
+    K = G.manifold_dim
+    tol = 1e-3 if gid == 4 else 1e-6
+    a0 = torch.zeros(1, K, dtype=dt, device="cuda")
+    J = analytic_jacobian(lambda x: G.exp(x).log(), 0.2 * torch.randn(1, K, dtype=dt, device="cuda"))
+    assert torch.allclose(J, torch.eye(K, dtype=dt, device="cuda"), atol=1e-3 if gid == 4 else 1e-8)
+    X = G.exp(0.5 * torch.randn(1, K, dtype=dt, device="cuda"))
+    b0 = torch.randn(1, K, dtype=dt, device="cuda")
+    p0 = torch.randn(1, 3, dtype=dt, device="cuda")
+    for fn, xs in [(lambda a: (G.exp(a) * X).inv().log(), [a0]),
+                   (lambda a, b: (G.exp(a) * X).adj(b), [a0, b0]),
+                   (lambda a, b: (G.exp(a) * X).adjT(b), [a0, b0]),
+                   (lambda a, p: (X * G.exp(a)).act(p), [a0, p0]),
+                   (lambda a: (G.exp(a) * X).matrix(), [a0])]:
+        for k in range(len(xs)):
+            def f(x, k=k):
+                args = list(xs)
+                args[k] = x
+                return fn(*args)
+            Ja, Jn = analytic_jacobian(f, xs[k]), numeric_jacobian(f, xs[k], eps=1e-6)
+            assert torch.allclose(Ja, Jn, atol=tol), (Ja - Jn).abs().max()
+
+
+def test_golden_autograd_through_product_wrappers():
+    """the product's lietorch classes reproduce the gradients the reference's python wrappers
+    produce (fixture: tests/golden/lie_autograd.pt)"""
+    from devo_b200 import lietorch as lt
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "lie_autograd.pt"))
+    dt = torch.float64
+    for Grp in (lt.SO3, lt.RxSO3, lt.SE3, lt.Sim3):
+        r = gold[Grp.group_name]
+        K = Grp.manifold_dim
+        a = r["a"].cuda().requires_grad_(True)
+        b = r["b"].cuda().requires_grad_(True)
+        p = r["p"].cuda().requires_grad_(True)
+        Y = Grp.exp(a) * Grp(r["X0"].cuda())
+        w = torch.arange(1, K + 1, dtype=dt, device="cuda")
+        f = (Y.inv().log() * w).sum() + (Y.adjT(b) ** 2).sum() + (Y.adj(b) * 0.3).sum() + (Y.act(p) ** 2).sum() \
+            + Y.matrix().sum() + (Y.vec() ** 2).sum()
+        ga, gb, gp = torch.autograd.grad(f, [a, b, p])
+        assert torch.allclose(Y.data.cpu(), r["Y"], atol=1e-10)
+        assert torch.allclose(f.cpu(), r["f"], atol=1e-9)
+        assert torch.allclose(ga.cpu(), r["ga"], atol=1e-8), (Grp.group_name, (ga.cpu() - r["ga"]).abs().max())
+        assert torch.allclose(gb.cpu(), r["gb"], atol=1e-8) and torch.allclose(gp.cpu(), r["gp"], atol=1e-8)
+
+
+def test_class_api_surface_and_errors():
+    from devo_b200 import lietorch as lt, lietorch_backends as be
+    I = lt.SE3.Identity(2, 3, device="cuda")
+    assert I.shape == (2, 3) and I.data.shape == (2, 3, 7)
+    R = lt.SE3.Random(4, device="cuda")
+    assert torch.allclose((R * R.inv()).log(), torch.zeros(4, 6, device="cuda"), atol=1e-5)
+    assert lt.cat([R, R], 0).shape == (8,) and lt.stack([R, R], 0).shape == (2, 4)
+    assert R[1:3].shape == (2,) and R.view((2, 2)).shape == (2, 2)
+    s = torch.rand(4, device="cuda")
+    assert torch.allclose(R.scale(s).data[:, :3], R.data[:, :3] * s[:, None])
+    assert lt.Sim3(R).data.shape == (4, 8) and lt.SO3(R).data.shape == (4, 4)
+    assert torch.allclose(R.translation()[:, :3], R.data[:, :3], atol=1e-6)
+    # broadcasting of a [n,1] group against [n,m,4] points, like transform does
+    pts = torch.randn(4, 5, 4, device="cuda")
+    out = R[:, None] * pts
+    assert out.shape == (4, 5, 4)
+    with pytest.raises(RuntimeError):
+        be.expm(3, torch.zeros(6, 4, device="cuda").t())          # CHECK_CONTIGUOUS (lietorch.cpp:7)
+    with pytest.raises(RuntimeError):
+        be.expm(3, torch.zeros(4, 6))                              # no CPU backend in this build
+    with pytest.raises(RuntimeError):
+        be.expm(9, torch.zeros(4, 6, device="cuda"))

@@ -1,0 +1,134 @@
+"""GPU parity against the REFERENCE's own CUDA extensions, compiled from /root/reference into
+oracle/_ref/ by oracle/build_ref.py (they travel to the GPU box as prebuilt .so files).
+This pins corr / patchify / neighbors / fastba / reproject -- for which the reference has no
+tests or fixtures -- on identical seeded inputs.
+
+  * patchify forward, neighbors: bit-exact.
+  * corr forward fp32: <= 1e-4 relative.  fp16: the reference accumulates in half, ours in fp32:
+    require our error vs the fp64 oracle <= the reference's (+ half rounding).
+  * corr backward fp32: <= 1e-4 relative (both use float atomics).
+  * fastba: the reference is run-to-run non-deterministic (float atomics); require
+    |ours - ref| <= 1e-5 + 4 x the reference's own self-difference, and that ours is at least as
+    close to the fp64 oracle as the reference is.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import corr as ocorr
+from oracle import fastba as ofba
+from oracle.build_ref import load_ref
+from problems import ba_problem, corr_problem
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(name):
+    m = load_ref(name)
+    if m is None:
+        pytest.skip("oracle/_ref/%s.so not built" % name)
+    return m
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def test_corr_forward_fp32_vs_reference():
+    ref = _ref("cuda_corr_ref")
+    from devo_b200 import cuda_corr
+    Pm = corr_problem(n_frames=4, patches_per_frame=48, seed=2, dtype=torch.float32)
+    for lvl, s in enumerate((1, 4)):
+        for coords in (Pm["coords"], corr_problem(n_frames=4, patches_per_frame=48, seed=2, dtype=torch.float32, oob_stress=True)["coords"]):
+            a = (Pm["gmap"].cuda(), Pm["pyramid"][lvl].cuda(), (coords / s).cuda(), Pm["kk"].cuda(), Pm["jj"].cuda())
+            (r,) = ref.forward(*a, 3)
+            (o,) = cuda_corr.forward(*a, 3)
+            assert o.shape == r.shape
+            assert _rel(o, r) <= 1e-4, _rel(o, r)
+
+
+def test_corr_forward_fp16_not_worse_than_reference():
+    ref = _ref("cuda_corr_ref")
+    from devo_b200 import cuda_corr
+    Pm = corr_problem(n_frames=3, patches_per_frame=32, seed=4, dtype=torch.float16)
+    a = (Pm["gmap"].cuda(), Pm["pyramid"][0].cuda(), Pm["coords"].cuda(), Pm["kk"].cuda(), Pm["jj"].cuda())
+    (r,) = ref.forward(*a, 3)
+    (o,) = cuda_corr.forward(*a, 3)           # TMA + tcgen05 path
+    exact = ocorr.corr_forward(Pm["gmap"], Pm["pyramid"][0], Pm["coords"], Pm["kk"], Pm["jj"], 3)
+    e_ref, e_ours = _rel(r, exact), _rel(o, exact)
+    assert e_ours <= max(e_ref, 1e-3), (e_ours, e_ref)
+    assert _rel(o, r) <= 4 * max(e_ref, 1e-3)
+
+
+def test_corr_backward_fp32_vs_reference():
+    ref = _ref("cuda_corr_ref")
+    from devo_b200 import cuda_corr
+    Pm = corr_problem(n_frames=3, patches_per_frame=16, C=32, H4=40, W4=48, seed=6, dtype=torch.float32)
+    a = (Pm["gmap"].cuda(), Pm["pyramid"][0].cuda(), Pm["coords"].cuda(), Pm["kk"].cuda(), Pm["jj"].cuda())
+    g = torch.randn(1, Pm["kk"].numel(), 7, 7, 3, 3, device="cuda")
+    r1, r2 = ref.backward(*a, g, 3)
+    o1, o2 = cuda_corr.backward(*a, g, 3)
+    assert _rel(o1, r1) <= 1e-4 and _rel(o2, r2) <= 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_patchify_bit_exact_vs_reference(dtype):
+    ref = _ref("cuda_corr_ref")
+    from devo_b200 import cuda_corr
+    g = torch.Generator().manual_seed(1)
+    net = torch.randn(2, 128, 30, 40, generator=g).to(dtype).cuda()
+    coords = torch.cat([torch.randint(-2, 42, (2, 96, 1), generator=g), torch.randint(-2, 32, (2, 96, 1), generator=g)], -1).float().cuda()
+    for R in (0, 1):
+        (r,) = ref.patchify_forward(net, coords, R)
+        (o,) = cuda_corr.patchify_forward(net, coords, R)
+        assert torch.equal(o, r)
+
+
+def test_neighbors_bit_exact_vs_reference():
+    ref = _ref("cuda_ba_ref")
+    from devo_b200 import cuda_ba
+    rng = np.random.RandomState(3)
+    for E, nk, nj in [(6144, 768, 8), (3000, 200, 12), (33, 4, 3)]:
+        kk = torch.from_numpy(rng.randint(0, nk, E)).cuda()
+        jj = torch.from_numpy(rng.randint(0, nj, E)).cuda()
+        rx, ry = ref.neighbors(kk, jj)
+        ox, oy = cuda_ba.neighbors(kk, jj)
+        assert torch.equal(ox, rx) and torch.equal(oy, ry)
+
+
+def test_reproject_vs_reference():
+    ref = _ref("cuda_ba_ref")
+    from devo_b200 import cuda_ba
+    P = ba_problem(n_frames=5, patches_per_frame=20, seed=21, init="perturbed")
+    a = (P["poses0"].float().cuda(), P["patches0"].float().cuda(), P["intrinsics"].float().cuda(),
+         P["ii"].cuda(), P["jj"].cuda(), P["kk"].cuda())
+    assert (cuda_ba.reproject(*a) - ref.reproject(*a)).abs().max().item() <= 1e-4
+
+
+@pytest.mark.parametrize("nf,m,iters", [(4, 24, 2), (8, 96, 2), (8, 96, 10)])
+def test_fastba_vs_reference(nf, m, iters):
+    ref = _ref("cuda_ba_ref")
+    from devo_b200 import cuda_ba
+    P = ba_problem(n_frames=nf, patches_per_frame=m, seed=77 + nf, init="perturbed", noise=0.3)
+
+    def run(fn):
+        poses, patches = P["poses0"].float().cuda().contiguous(), P["patches0"].float().cuda().contiguous()
+        fn(poses, patches, P["intrinsics"].float().cuda(), P["targets"].float().cuda(), P["weights"].float().cuda(),
+           torch.tensor([1e-4], device="cuda"), P["ii"].cuda(), P["jj"].cuda(), P["kk"].cuda(), 1, nf, iters)
+        return poses[0].double().cpu(), patches[0, :, 2, 1, 1].double().cpu()
+
+    r1, r2, ours = run(ref.forward), run(ref.forward), run(cuda_ba.forward)
+    self_p = (r1[0] - r2[0]).abs().max().item()
+    self_d = (r1[1] - r2[1]).abs().max().item()
+    f = lambda t: t.float().double()
+    po, xo, st = ofba.ba(f(P["poses0"]), f(P["patches0"][0]), f(P["intrinsics"]), f(P["targets"]), f(P["weights"]),
+                         torch.tensor([1e-4]).float().double(), P["ii"], P["jj"], P["kk"], 1, nf, iters)
+    assert st == 0
+    ep_ref, ep_ours = (r1[0] - po).abs().max().item(), (ours[0] - po).abs().max().item()
+    ed_ref, ed_ours = (r1[1] - xo[:, 2, 1, 1]).abs().max().item(), (ours[1] - xo[:, 2, 1, 1]).abs().max().item()
+    print("fastba nf=%d iters=%d: ref self-diff pose %.2e depth %.2e | err vs fp64 oracle: ref %.2e/%.2e ours %.2e/%.2e"
+          % (nf, iters, self_p, self_d, ep_ref, ed_ref, ep_ours, ed_ours))
+    assert (ours[0] - r1[0]).abs().max().item() <= 1e-5 + 4 * self_p + 2 * ep_ref
+    assert (ours[1] - r1[1]).abs().max().item() <= 1e-5 + 4 * self_d + 2 * ed_ref
+    assert ep_ours <= max(ep_ref, 1e-5) * 1.5 and ed_ours <= max(ed_ref, 1e-5) * 1.5
