@@ -204,6 +204,8 @@ def run_ours(args, rank, world, local_rank):
         status = int(s.item())
     if rank != 0:
         return None
+    if args.profile:
+        return dict(metric=METRIC, profile_run=True, ms_per_step=round(total_ms / args.steps, 5), gpu_launches=int(launches_per_step * args.steps))
 
     # ---- roofline of the dominant kernel (the fused correlation lookup), timed alone with L2 flushes
     with torch.no_grad():
@@ -380,6 +382,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="under ncu: timed steps only (no e2e / roofline / cpu legs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -34,6 +34,7 @@ SIGNATURES = {
     "devo_neighbors": (_i, [_vp] * 4 + [_i, _vp, _sz, _vp]),
     "devo_ba_workspace": (_sz, [_i, _i]),
     "devo_ba_forward": (_i, [_vp] * 9 + [_i] * 7 + [_vp, _sz, _vp, _vp]),
+    "devo_ba_forward_planned": (_i, [_vp] * 9 + [_i] * 7 + [_vp] * 4 + [_vp, _sz, _vp, _vp]),
     "devo_reproject": (_i, [_vp] * 7 + [_i, _i, _vp]),
     "devo_transform_forward": (_i, [_vp] * 11 + [_i] * 4 + [_vp]),
     "devo_segment_softmax_sum": (_i, [_vp] * 5 + [_i, _vp, _i, _i, _i, _vp]),

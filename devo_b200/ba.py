@@ -4,7 +4,8 @@ semantics of devo/ba.py:86-182 (one damped Gauss-Newton step on the poses after 
 `(poses, patches)`; autograd flows through everything).
 
 Formulation (the same one the CUDA fastba kernels use, see csrc/ba.cu): every residual row
-is the sparse vector  g = [-Ji at block i', +Jj at block j']  so that
+is the sparse vector  g = [Ji at block i', Jj at block j']  (projective_ops.transform already returns
+Ji = -Ad(Gij)^T Jj, sign included)  so that
 
     B = G^T W G,   v = G^T W r,   E_k = sum_{rows of patch k} w Jz g,   C_k, u_k likewise
     S = B - E^T Q E,  y = v - E^T Q u,  Q = 1/(C + lambda)
@@ -82,7 +83,7 @@ def BA(poses, patches, intrinsics, targets, weights, lmbda, ii, jj, kk, bounds, 
     if structure_only or nfree == 0:
         dZ = Q * u
     else:
-        G = (_block_rows(Ji, ii - fixedp, nfree, -1.0) + _block_rows(Jj, jj - fixedp, nfree, 1.0)).reshape(1, 2 * E, n6)
+        G = (_block_rows(Ji, ii - fixedp, nfree, 1.0) + _block_rows(Jj, jj - fixedp, nfree, 1.0)).reshape(1, 2 * E, n6)
         wG = w * G
         B = torch.matmul(G.transpose(1, 2), wG)
         v = torch.matmul(G.transpose(1, 2), w * r)

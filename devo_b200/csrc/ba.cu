@@ -18,7 +18,8 @@
 //                                      set of matrix entries per thread, fixed summation order:
 //                                      no atomics at all, bitwise reproducible.
 //   solve  (1 launch per iteration)    one CTA: fixed-order reduction of the partials, damping,
-//                                      in-smem fp64 Cholesky + triangular solves, SE3 retraction.
+//                                      in-smem fp64 LDL^T elimination of [S|y] (one barrier per pivot),
+//                                      warp-shuffle back-substitution, SE3 retraction.
 //   depth update                       dZ_k = Q_k (u_k - E_k . dX); fused into the prologue of the
 //                                      next iteration's accum launch (same patch ownership).
 //
@@ -388,7 +389,12 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
 }
 
 // ---- solve kernel ---------------------------------------------------------------------------
-// smem: L packed lower-triangular n6(n6+1)/2 doubles, y[n6] doubles
+// smem: A packed lower-triangular n(n+1)/2 doubles (A(i,j) at i(i+1)/2 + j, j<=i), y[n] doubles.
+// Square-root-free elimination of the augmented system [S | y] with ONE barrier per pivot:
+//   step k:  r = 1/A_kk ;  A_ij -= A_ik A_jk r  (i>=j>k) ;  y_i -= A_ik y_k r  (i>k)
+// reads touch column k only, writes touch columns > k only, so no second barrier is needed.
+// Afterwards A_ik (i>k) = L_ik d_k and y = L^-1 y; warp 0 finishes x = L^-T D^-1 y with shuffles.
+// S positive definite  <=>  every pivot d_k = A_kk > 0 (same acceptance test as Cholesky).
 __global__ void __launch_bounds__(kSolveThreads, 1) ba_solve_kernel(
     float* __restrict__ poses, const double* __restrict__ partials, double* __restrict__ dX,
     int32_t* __restrict__ status, int nparts, int t0, int nfree, int itr) {
@@ -396,8 +402,8 @@ __global__ void __launch_bounds__(kSolveThreads, 1) ba_solve_kernel(
   const int n = 6 * nfree;
   const int LD = n + 1;
   const int nent = (n + 1) * (n + 2) / 2;
-  double* L = reinterpret_cast<double*>(smem_raw);       // L(i,j) at i(i+1)/2 + j, j<=i
-  double* y = L + (size_t)n * (n + 1) / 2;
+  double* A = reinterpret_cast<double*>(smem_raw);
+  double* y = A + (size_t)n * (n + 1) / 2;
   __shared__ int s_fail;
   const int tid = threadIdx.x;
   if (*status != 0) return;
@@ -406,43 +412,48 @@ __global__ void __launch_bounds__(kSolveThreads, 1) ba_solve_kernel(
 
   // fixed-order reduction of the per-CTA partials; entry (a,b), a<=b of the (n+1)x(n+1) augmented matrix
   for (int idx = tid; idx < nent; idx += kSolveThreads) {
-    double s = 0.0;
-    for (int p = 0; p < nparts; p++) s += partials[(size_t)p * nent + idx];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int p = 0;
+    for (; p + 4 <= nparts; p += 4) {
+      s0 += partials[(size_t)(p + 0) * nent + idx];
+      s1 += partials[(size_t)(p + 1) * nent + idx];
+      s2 += partials[(size_t)(p + 2) * nent + idx];
+      s3 += partials[(size_t)(p + 3) * nent + idx];
+    }
+    for (; p < nparts; p++) s0 += partials[(size_t)p * nent + idx];
+    double s = (s0 + s1) + (s2 + s3);
     int a, b;
     tri_decode(idx, LD, a, b);
     if (b == n) {
       if (a < n) y[a] = s;                                // y = v - E Q u
     } else {
       if (a == b) s += 1e-4 * s + 1.0;                    // S += I o (1e-4 S + 1)   (:517-518)
-      L[(size_t)b * (b + 1) / 2 + a] = s;                 // symmetric: store as lower (b,a)
+      A[(size_t)b * (b + 1) / 2 + a] = s;                 // symmetric: store as lower (b,a)
     }
   }
   __syncthreads();
 
-  // right-looking Cholesky, in place
   for (int k = 0; k < n; k++) {
-    const double akk = L[(size_t)k * (k + 1) / 2 + k];
+    const double akk = A[(size_t)k * (k + 1) / 2 + k];
     if (!(akk > 0.0) || !isfinite(akk)) {                // uniform: every thread reads the same value
-      if (tid == 0) { s_fail = 1; }
+      if (tid == 0) s_fail = 1;
       break;
     }
-    const double dk = sqrt(akk);
-    __syncthreads();                                      // everyone has read akk
-    for (int i = k + tid; i < n; i += kSolveThreads) {
-      double* p = &L[(size_t)i * (i + 1) / 2 + k];
-      *p = (i == k) ? dk : (*p / dk);
-    }
-    __syncthreads();
+    const double r = 1.0 / akk;
     const int m = n - k - 1;                              // trailing size
     const int cnt = m * (m + 1) / 2;
-    for (int q = tid; q < cnt; q += kSolveThreads) {
-      // (i,j) lower-tri of trailing block, i>=j
-      int i = (int)floorf((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
-      while (i * (i + 1) / 2 > q) i--;
-      while ((i + 1) * (i + 2) / 2 <= q) i++;
-      const int j = q - i * (i + 1) / 2;
-      const int gi = k + 1 + i, gj = k + 1 + j;
-      L[(size_t)gi * (gi + 1) / 2 + gj] -= L[(size_t)gi * (gi + 1) / 2 + k] * L[(size_t)gj * (gj + 1) / 2 + k];
+    for (int q = tid; q < cnt + m; q += kSolveThreads) {
+      if (q < cnt) {
+        int i = (int)floorf((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
+        while (i * (i + 1) / 2 > q) i--;
+        while ((i + 1) * (i + 2) / 2 <= q) i++;
+        const int j = q - i * (i + 1) / 2;
+        const int gi = k + 1 + i, gj = k + 1 + j;
+        A[(size_t)gi * (gi + 1) / 2 + gj] -= A[(size_t)gi * (gi + 1) / 2 + k] * A[(size_t)gj * (gj + 1) / 2 + k] * r;
+      } else {
+        const int gi = k + 1 + (q - cnt);
+        y[gi] -= A[(size_t)gi * (gi + 1) / 2 + k] * y[k] * r;
+      }
     }
     __syncthreads();
   }
@@ -451,22 +462,35 @@ __global__ void __launch_bounds__(kSolveThreads, 1) ba_solve_kernel(
     if (tid == 0) atomicCAS(status, 0, itr + 1);
     return;
   }
-  // forward substitution  L z = y
-  for (int k = 0; k < n; k++) {
-    const double zk = y[k] / L[(size_t)k * (k + 1) / 2 + k];
-    __syncthreads();
-    for (int i = k + 1 + tid; i < n; i += kSolveThreads) y[i] -= L[(size_t)i * (i + 1) / 2 + k] * zk;
-    if (tid == 0) y[k] = zk;
-    __syncthreads();
+  // back substitution by warp 0: x_k = y_k/d_k - sum_{i>k} (A_ik/d_k) x_i ; lane l owns x[l + 32 m]
+  if (tid < 32) {
+    constexpr int kMaxPerLane = (kMaxN6 + 31) / 32;
+    double x[kMaxPerLane], invd[kMaxPerLane];
+#pragma unroll
+    for (int mm = 0; mm < kMaxPerLane; mm++) {
+      const int i = tid + 32 * mm;
+      invd[mm] = (i < n) ? 1.0 / A[(size_t)i * (i + 1) / 2 + i] : 0.0;
+      x[mm] = (i < n) ? y[i] * invd[mm] : 0.0;                           // D^-1 y
+    }
+    for (int k = n - 1; k >= 0; k--) {
+      // x_k is final; broadcast it and eliminate it from all rows i < k
+      double xk = 0.0;
+#pragma unroll
+      for (int mm = 0; mm < kMaxPerLane; mm++)
+        if ((k >> 5) == mm) xk = __shfl_sync(0xffffffffu, x[mm], k & 31);
+#pragma unroll
+      for (int mm = 0; mm < kMaxPerLane; mm++) {
+        const int i = tid + 32 * mm;
+        if (i < k) x[mm] -= A[(size_t)k * (k + 1) / 2 + i] * invd[mm] * xk;
+      }
+    }
+#pragma unroll
+    for (int mm = 0; mm < kMaxPerLane; mm++) {
+      const int i = tid + 32 * mm;
+      if (i < n) y[i] = x[mm];
+    }
   }
-  // backward substitution  L^T x = z
-  for (int k = n - 1; k >= 0; k--) {
-    const double xk = y[k] / L[(size_t)k * (k + 1) / 2 + k];
-    __syncthreads();
-    for (int i = tid; i < k; i += kSolveThreads) y[i] -= L[(size_t)k * (k + 1) / 2 + i] * xk;
-    if (tid == 0) y[k] = xk;
-    __syncthreads();
-  }
+  __syncthreads();
   bool bad = false;
   for (int i = tid; i < n; i += kSolveThreads) {
     dX[i] = y[i];
@@ -591,15 +615,15 @@ static int launch_accumulate(const BaLayout& L, char* w, float* poses, float* pa
                              const float* target, const float* weight, const float* lmbda, const int64_t* ii,
                              const int64_t* jj, const int64_t* kk, int32_t* status, int E, int PP, int centre,
                              int t0, int nfree, int n_poses, int EB, int GB, size_t smem, int apply_update,
-                             int do_accumulate, int itr, cudaStream_t s) {
+                             int do_accumulate, int itr, cudaStream_t s, const int32_t* perm_p, const int32_t* gstart_p,
+                             const int64_t* gkey_p, const int32_t* ngroups_p) {
   static size_t configured = 0;
   if (smem > configured) {
     DEVO_CUDA(cudaFuncSetAttribute(ba_accumulate_kernel<EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   ba_accumulate_kernel<EPT><<<L.grid, kAccThreads, smem, s>>>(
-      poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, (const int32_t*)(w + L.perm),
-      (const int32_t*)(w + L.gstart), (const int64_t*)(w + L.gkey), (const int32_t*)(w + L.ngroups),
+      poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, perm_p, gstart_p, gkey_p, ngroups_p,
       (double*)(w + L.Q), (double*)(w + L.U), (double*)(w + L.Ek), (double*)(w + L.partials),
       (const double*)(w + L.dX), status, E, PP, centre, t0, nfree, n_poses, EB, GB, apply_update, do_accumulate, itr);
   DEVO_LAUNCH_CHECK("ba_accumulate");
@@ -610,10 +634,12 @@ extern "C" {
 
 size_t devo_ba_workspace(int E, int n_free_poses) { return ba_layout(E, n_free_poses).total; }
 
-int devo_ba_forward(float* poses, float* patches, const float* intrinsics, const float* target,
-                    const float* weight, const float* lmbda, const int64_t* ii, const int64_t* jj,
-                    const int64_t* kk, int E, int n_poses, int n_patches, int P, int t0, int t1,
-                    int iterations, void* workspace, size_t workspace_bytes, int32_t* status, void* stream) {
+static int ba_forward_impl(float* poses, float* patches, const float* intrinsics, const float* target,
+                           const float* weight, const float* lmbda, const int64_t* ii, const int64_t* jj,
+                           const int64_t* kk, int E, int n_poses, int n_patches, int P, int t0, int t1,
+                           int iterations, void* workspace, size_t workspace_bytes, int32_t* status, void* stream,
+                           const int32_t* ext_perm, const int32_t* ext_gstart, const int64_t* ext_gkey,
+                           const int32_t* ext_ngroups) {
   cudaStream_t s = (cudaStream_t)stream;
   DEVO_REQUIRE(status != nullptr, DEVO_EINVAL, "ba_forward: status pointer is NULL");
   DEVO_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), s));
@@ -631,10 +657,19 @@ int devo_ba_forward(float* poses, float* patches, const float* intrinsics, const
   const int PP = P * P;
   const int centre = (P == 3) ? 4 : (1 * P + 1 < PP ? 1 * P + 1 : 0);   // the reference hard-codes [1][1]
   // patches grouped by kk (== torch::_unique(kk), ba_cuda.cu:435-437), edges of a patch contiguous
-  int rc = devo_graph_plan(kk, jj, E, n_patches, n_poses, (int32_t*)(w + L.perm), nullptr,
-                           (int32_t*)(w + L.gstart), (int64_t*)(w + L.gkey), (int32_t*)(w + L.ngroups),
-                           nullptr, nullptr, w + L.plan_ws, L.plan_bytes, stream);
-  if (rc != DEVO_OK) return rc;
+  int rc = DEVO_OK;
+  const int32_t* perm_p = (const int32_t*)(w + L.perm);
+  const int32_t* gstart_p = (const int32_t*)(w + L.gstart);
+  const int64_t* gkey_p = (const int64_t*)(w + L.gkey);
+  const int32_t* ngroups_p = (const int32_t*)(w + L.ngroups);
+  if (ext_perm) {   // the caller already analysed this edge list (devo_graph_plan on (kk, jj))
+    perm_p = ext_perm; gstart_p = ext_gstart; gkey_p = ext_gkey; ngroups_p = ext_ngroups;
+  } else {
+    rc = devo_graph_plan(kk, jj, E, n_patches, n_poses, (int32_t*)(w + L.perm), nullptr,
+                         (int32_t*)(w + L.gstart), (int64_t*)(w + L.gkey), (int32_t*)(w + L.ngroups),
+                         nullptr, nullptr, w + L.plan_ws, L.plan_bytes, stream);
+    if (rc != DEVO_OK) return rc;
+  }
 
   const int n6 = L.n6, LD = n6 + 1;
   int rows_cap = (int)(kAccSmemBudget / ((size_t)(LD + 2) * 8));
@@ -648,7 +683,7 @@ int devo_ba_forward(float* poses, float* patches, const float* intrinsics, const
 
 #define ACC(EPT_, APPLY, DOACC, ITR)                                                                         \
   launch_accumulate<EPT_>(L, w, poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, status, E, PP, \
-                          centre, t0, nfree, n_poses, EB, GB, smem_acc, APPLY, DOACC, ITR, s)
+                          centre, t0, nfree, n_poses, EB, GB, smem_acc, APPLY, DOACC, ITR, s, perm_p, gstart_p, gkey_p, ngroups_p)
 #define ACC_DISPATCH(APPLY, DOACC, ITR)                   \
   do {                                                    \
     if (ept <= 4) rc = ACC(4, APPLY, DOACC, ITR);         \
@@ -678,6 +713,25 @@ int devo_ba_forward(float* poses, float* patches, const float* intrinsics, const
 #undef ACC
 #undef ACC_DISPATCH
   return DEVO_OK;
+}
+
+int devo_ba_forward(float* poses, float* patches, const float* intrinsics, const float* target,
+                    const float* weight, const float* lmbda, const int64_t* ii, const int64_t* jj,
+                    const int64_t* kk, int E, int n_poses, int n_patches, int P, int t0, int t1,
+                    int iterations, void* workspace, size_t workspace_bytes, int32_t* status, void* stream) {
+  return ba_forward_impl(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, E, n_poses, n_patches, P, t0, t1,
+                         iterations, workspace, workspace_bytes, status, stream, nullptr, nullptr, nullptr, nullptr);
+}
+
+int devo_ba_forward_planned(float* poses, float* patches, const float* intrinsics, const float* target,
+                            const float* weight, const float* lmbda, const int64_t* ii, const int64_t* jj,
+                            const int64_t* kk, int E, int n_poses, int n_patches, int P, int t0, int t1,
+                            int iterations, const int32_t* perm, const int32_t* gstart, const int64_t* gkey,
+                            const int32_t* ngroups, void* workspace, size_t workspace_bytes, int32_t* status,
+                            void* stream) {
+  DEVO_REQUIRE(perm && gstart && gkey && ngroups, DEVO_EINVAL, "ba_forward_planned: plan pointers must not be NULL");
+  return ba_forward_impl(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, E, n_poses, n_patches, P, t0, t1,
+                         iterations, workspace, workspace_bytes, status, stream, perm, gstart, gkey, ngroups);
 }
 
 int devo_reproject(const float* poses, const float* patches, const float* intrinsics, const int64_t* ii,

@@ -17,10 +17,12 @@
 //   * MMA warp      : one thread issues C/16 tcgen05.mma (M=128 box pixels x N=16 patch pixels
 //                     x K=16), fp32 accumulator in TMEM (2 x 16 columns, double buffered);
 //                     tcgen05.commit releases the smem stage and publishes the accumulator.
-//   * 4 epilogue warps: tcgen05.ld the 128x16 accumulator (one box pixel per thread), park the
-//                     9 useful columns in smem, then apply the bilinear blend for the 9 x 7 x 7
-//                     outputs and store them directly in the interleaved [E, 49*9*L] layout the
-//                     GRU consumes (permute + stack fused).
+//   * 2 x 4 epilogue warps (one group per TMEM accumulator stage): tcgen05.ld the 128x16
+//                     accumulator (one box pixel per thread), park the 9 useful columns in smem,
+//                     then apply the bilinear blend for the 9 x 7 x 7 outputs and store them directly
+//                     in the interleaved [E, 49*9*L] layout the GRU consumes (permute + stack fused).
+//   * patch coordinates are staged by the TMA unit too (cp.async.bulk, 8 edges = 576 B per batch,
+//     4-batch ring), so no role ever waits on a dependent global load inside its item loop.
 // Patch pixels whose window does not fit in the 11x11 box (reprojection scale > ~1.5x) take a
 // per-output direct path inside the same kernel.
 #include <cuda.h>
@@ -32,12 +34,16 @@ namespace {
 constexpr int kBox = 11;                    // box edge in pixels: 8 + floor-span 3
 constexpr int kBoxPix = kBox * kBox;        // 121 rows used of the M=128 tile
 constexpr int kStages = 4;
-constexpr int kThreads = 192;               // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int kEpiGroups = 2;               // one epilogue group (4 warps) per TMEM accumulator stage
+constexpr int kThreads = 32 * (2 + 4 * kEpiGroups);   // warp0 TMA, warp1 MMA, 2 x 4 epilogue warps
 constexpr int kATileBytes = 128 * 128;      // 128 rows x 64 ch x 2 B   (one K half)
 constexpr int kBTileBytes = 16 * 128;       // 16 rows  x 64 ch x 2 B
 constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;   // 36 KB
 constexpr int kVsFloats = 9 * 128;
-constexpr int kRadius = 3, kP = 3, kPP = 9, kOut = 7;
+constexpr int kRadius = 3, kPP = 9, kOut = 7;
+constexpr int kCoordBatch = 8;              // edges per coordinate batch (8 x 72 B = 576 B, 16-byte multiple)
+constexpr int kCoordRing = 4;               // batches in flight in shared memory
+constexpr int kCoordFloats = kCoordBatch * 2 * kPP;
 
 struct FastParams {
   int E, L, items, khalves;                 // khalves = C / 64
@@ -85,6 +91,14 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// 1-D bulk copy global -> shared (TMA unit, no tensor map); bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -130,21 +144,21 @@ struct Geo {
   float dx, dy;      // fractional part
   int x0, y0;        // box origin (warp-uniform)
 };
-__device__ __forceinline__ Geo load_geo(const FastParams& prm, int e, int l, int lane) {
+// cs: the edge's 18 staged coordinates in shared memory ([2][9])
+__device__ __forceinline__ Geo make_geo(const float* cs, float scale, int lane) {
   Geo g;
-  const float* co = prm.coords + (size_t)e * 2 * kPP;
   float x = 0.f, y = 0.f;
-  if (lane < kPP) { x = co[lane] / prm.scale[l]; y = co[kPP + lane] / prm.scale[l]; }
+  if (lane < kPP) { x = cs[lane] / scale; y = cs[kPP + lane] / scale; }
   g.fx = safe_floor_int(x, g.dx);
   g.fy = safe_floor_int(y, g.dy);
   int mx = lane < kPP ? g.fx : 0x7fffffff, my = lane < kPP ? g.fy : 0x7fffffff;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
+  for (int o = 8; o > 0; o >>= 1) {       // pixels live in lanes 0..15
     mx = min(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     my = min(my, __shfl_xor_sync(0xffffffffu, my, o));
   }
-  g.x0 = mx - kRadius;
-  g.y0 = my - kRadius;
+  g.x0 = __shfl_sync(0xffffffffu, mx, 0) - kRadius;
+  g.y0 = __shfl_sync(0xffffffffu, my, 0) - kRadius;
   return g;
 }
 
@@ -157,6 +171,21 @@ __device__ float direct_dot(const T* __restrict__ g, const T* __restrict__ lvl, 
   return s;
 }
 
+// per-role view of the coordinate ring: batch b holds edges [eb0 + 8b, eb0 + 8b + 8)
+struct CoordView {
+  const float* ring;
+  uint64_t* cfull;
+  int eb0, cur;
+  __device__ __forceinline__ const float* edge(int e) {
+    const int b = (e - eb0) >> 3;
+    if (b != cur) {                        // first use of this batch by this warp: wait until it has landed
+      cur = b;
+      mbar_wait(&cfull[b & (kCoordRing - 1)], (uint32_t)(b / kCoordRing) & 1u);
+    }
+    return ring + (b & (kCoordRing - 1)) * kCoordFloats + (e - eb0 - 8 * b) * 2 * kPP;
+  }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
     const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_l0,
@@ -166,23 +195,28 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
   // 1024-byte aligned carve-up (SWIZZLE_128B atoms repeat every 1024 B)
   unsigned char* base = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
   unsigned char* tiles = base;                                           // kStages * kStageBytes
-  float* Vs = reinterpret_cast<float*>(base + kStages * kStageBytes);    // 2 * kVsFloats
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Vs + 2 * kVsFloats);
+  float* Vs = reinterpret_cast<float*>(base + kStages * kStageBytes);    // kEpiGroups * 2 * kVsFloats
+  float* cring = Vs + kEpiGroups * 2 * kVsFloats;                        // kCoordRing * kCoordFloats (16 B aligned)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cring + kCoordRing * kCoordFloats);
   uint64_t* full = bars;                 // [kStages]
   uint64_t* empty = bars + kStages;      // [kStages]
   uint64_t* tfull = bars + 2 * kStages;  // [2]
   uint64_t* tempty = tfull + 2;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* cfull = tempty + 2;          // [kCoordRing]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cfull + kCoordRing);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per = (prm.items + gridDim.x - 1) / gridDim.x;
   const int first = blockIdx.x * per;
   const int last = min(prm.items, first + per);
   const int khalves = prm.khalves;
+  const int L = prm.L;
+  const int eb0 = (first / L) & ~1;      // even edge => 16-byte aligned source for the bulk copies
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    for (int c = 0; c < kCoordRing; c++) mbar_init(&cfull[c], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -193,14 +227,44 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  CoordView cv{cring, cfull, eb0, -1};
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
+    if (lane == 0) {
+      prefetch_tensormap(&tm_g); prefetch_tensormap(&tm_l0);
+      if (L > 1) prefetch_tensormap(&tm_l1);
+    }
+    const int nb = (first < last) ? (((last - 1) / L - eb0) >> 3) + 1 : 0;
+    // stage the coordinates of batch b: TMA bulk copy for a full batch, plain loads for the ragged tail
+    auto issue_coords = [&](int b) {
+      const int eb = eb0 + kCoordBatch * b;
+      const int n = min(kCoordBatch, prm.E - eb);
+      float* dst = cring + (b & (kCoordRing - 1)) * kCoordFloats;
+      const float* src = prm.coords + (size_t)eb * 2 * kPP;
+      uint64_t* bar = &cfull[b & (kCoordRing - 1)];
+      if (n == kCoordBatch && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+        if (lane == 0) {
+          mbar_arrive_expect_tx(bar, kCoordFloats * 4);
+          bulk_load_1d(dst, src, kCoordFloats * 4, bar);
+        }
+      } else {
+        for (int q = lane; q < n * 2 * kPP; q += 32) dst[q] = src[q];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar);
+      }
+      __syncwarp();
+    };
+    if (nb > 0) issue_coords(0);
+    if (nb > 1) issue_coords(1);
+    int issued = 2;
     uint32_t stage = 0, phase = 0;
     const uint32_t bytes = (uint32_t)khalves * (kBoxPix * 128 + kPP * 128);
     for (int item = first; item < last; item++) {
-      const int e = item / prm.L, l = item - e * prm.L;
-      Geo g = load_geo(prm, e, l, lane);
+      const int e = item / L, l = item - e * L;
+      const int b = (e - eb0) >> 3;
+      if (b + 2 > issued && issued < nb) { issue_coords(issued); issued++; }   // keep one batch ahead
+      Geo g = make_geo(cv.edge(e), prm.scale[l], lane);
       if (lane == 0) {
         const CUtensorMap* tm = (l == 0) ? &tm_l0 : (l == 1) ? &tm_l1 : (l == 2) ? &tm_l2 : &tm_l3;
         const int frame = (int)prm.jj[e];
@@ -219,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
     // instruction descriptor: D=f32, A=B=f16|bf16, K-major both, N=16, M=128
-    const uint32_t fmt = (sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value) ? 1u : 0u;
+    const uint32_t fmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
     uint32_t stage = 0, phase = 0, acc = 0, aphase = 0;
     for (int item = first; item < last; item++) {
@@ -247,20 +311,25 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
       if (++acc == 2) { acc = 0; aphase ^= 1; }
     }
   } else {
-    // =============================== epilogue (4 warps) ===============================
+    // =============================== epilogue: group g owns TMEM accumulator stage g ===============
+    const int grp = (warp - 2) >> 2;              // 0 or 1
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
     const int row = quarter * 32 + lane;          // box pixel handled by this thread
-    const int et = (warp - 2) * 32 + lane;        // 0..127 within the epilogue group
+    const int et = ((warp - 2) & 3) * 32 + lane;  // 0..127 within the group
     T* out = reinterpret_cast<T*>(prm.out);
-    uint32_t acc = 0, aphase = 0;
+    float* vbase = Vs + grp * 2 * kVsFloats;
+    uint32_t aphase = 0;
     int buf = 0;
-    for (int item = first; item < last; item++) {
-      const int e = item / prm.L, l = item - e * prm.L;
-      Geo g = load_geo(prm, e, l, lane);
-      mbar_wait(&tfull[acc], aphase);
+    for (int item = first + grp; item < last; item += kEpiGroups) {
+      const int e = item / L, l = item - e * L;
+      Geo g = make_geo(cv.edge(e), prm.scale[l], lane);
+      // per-pixel blend record, owned by lane p: offset of the window origin inside the box (or -1), fractions
+      const int ox = g.fx - kRadius - g.x0, oy = g.fy - kRadius - g.y0;
+      const int woff = (ox + 8 <= kBox && oy + 8 <= kBox) ? oy * kBox + ox : -1;
+      mbar_wait(&tfull[grp], aphase);
       tc_fence_after();
       uint32_t v[16];
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 16;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + grp * 16;
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
           : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
@@ -269,33 +338,34 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);   // accumulator stage free for the MMA warp
-      float* vs = Vs + buf * kVsFloats;
+      if (lane == 0) mbar_arrive(&tempty[grp]);   // accumulator stage free for the MMA warp
+      float* vs = vbase + buf * kVsFloats;
 #pragma unroll
       for (int p = 0; p < kPP; p++) vs[p * 128 + row] = __uint_as_float(v[p]);
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // the 4 epilogue warps only
+      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // the 4 warps of this group only
+      else          asm volatile("bar.sync 2, 128;" ::: "memory");
 
-      const int H = prm.H[l], W = prm.W[l];
-      const size_t obase = (size_t)e * (kOut * kOut * kPP) * prm.L;
+      const size_t obase = (size_t)e * (kOut * kOut * kPP) * L + l;
 #pragma unroll 1
       for (int it = 0; it < 4; it++) {
         const int q = et + it * 128;
         const bool active = q < kOut * kOut * kPP;
         const int p = active ? q % kPP : 0;
-        const int yo = (q / kPP) % kOut, xo = q / (kPP * kOut);
-        const int pfx = __shfl_sync(0xffffffffu, g.fx, p), pfy = __shfl_sync(0xffffffffu, g.fy, p);
+        const int pw = __shfl_sync(0xffffffffu, woff, p);
         const float dx = __shfl_sync(0xffffffffu, g.dx, p), dy = __shfl_sync(0xffffffffu, g.dy, p);
+        const int pfx = __shfl_sync(0xffffffffu, g.fx, p), pfy = __shfl_sync(0xffffffffu, g.fy, p);
         if (!active) continue;
-        const int ox = pfx - kRadius - g.x0, oy = pfy - kRadius - g.y0;   // window origin inside the box (>= 0)
+        const int yo = (q / kPP) % kOut, xo = q / (kPP * kOut);
         float r;
-        if (ox + 8 <= kBox && oy + 8 <= kBox) {
-          const float* s = vs + p * 128 + (oy + yo) * kBox + (ox + xo);
+        if (pw >= 0) {
+          const float* s = vs + p * 128 + pw + yo * kBox + xo;
           r = (1.f - dx) * (1.f - dy) * s[0] + dx * (1.f - dy) * s[1] + (1.f - dx) * dy * s[kBox] + dx * dy * s[kBox + 1];
         } else {
           // window outside the staged box (large scale change): direct evaluation
           const T* gp = reinterpret_cast<const T*>(prm.gmap_pm) + ((size_t)prm.ii[e] * kPP + p) * prm.C;
           const T* lv = reinterpret_cast<const T*>(prm.level[l]);
           const int fr = (int)prm.jj[e];
+          const int H = prm.H[l], W = prm.W[l];
           const int yy = pfy - kRadius + yo, xx = pfx - kRadius + xo;
           const float v00 = direct_dot<T>(gp, lv, H, W, prm.C, fr, yy, xx);
           const float v01 = direct_dot<T>(gp, lv, H, W, prm.C, fr, yy, xx + 1);
@@ -303,10 +373,10 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
           const float v11 = direct_dot<T>(gp, lv, H, W, prm.C, fr, yy + 1, xx + 1);
           r = (1.f - dx) * (1.f - dy) * v00 + dx * (1.f - dy) * v01 + (1.f - dx) * dy * v10 + dx * dy * v11;
         }
-        out[obase + (size_t)q * prm.L + l] = from_f<T>(r);
+        out[obase + (size_t)q * L] = from_f<T>(r);
       }
       buf ^= 1;
-      if (++acc == 2) { acc = 0; aphase ^= 1; }
+      aphase ^= 1;
     }
   }
 
@@ -344,6 +414,52 @@ __global__ void __launch_bounds__(256) pyramid_pack_kernel(const T* __restrict__
   for (int q = threadIdx.x; q < nx * C; q += blockDim.x) {
     const int c = q % C, x = q / C;
     dst[(size_t)x * C + c] = devo::ElemTraits<T>::from_float(tile[x * (C + 1) + c]);
+  }
+}
+
+// vectorised variant: 16-byte loads along x (8 input pixels of one channel), 16-byte stores along C
+// (8 channels of one output pixel); requires W % 8 == 0, C % 8 == 0, POOL in {1,2,4,8}
+template <typename T, int POOL>
+__global__ void __launch_bounds__(256) pyramid_pack_vec_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                               int C, int H, int W, int Ho, int Wo) {
+  extern __shared__ float tile[];   // [32][C+1]
+  const int n = blockIdx.z, yo = blockIdx.y, x0 = blockIdx.x * 32;
+  const int nx = min(32, Wo - x0);
+  constexpr int OPC = 8 / POOL;                     // output pixels per 16-byte chunk
+  constexpr int CHUNKS = 32 / OPC;                  // chunks per (channel, input row) of this tile
+  const T* src = in + (size_t)n * C * H * W;
+  for (int q = threadIdx.x; q < C * CHUNKS; q += blockDim.x) {
+    const int ch = q % CHUNKS, c = q / CHUNKS;
+    const int xin = (x0 * POOL) + ch * 8;           // first input column of the chunk
+    if (xin >= W || ch * OPC >= nx) continue;
+    float acc[OPC];
+#pragma unroll
+    for (int o = 0; o < OPC; o++) acc[o] = 0.f;
+#pragma unroll
+    for (int a = 0; a < POOL; a++) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(src + ((size_t)c * H + (size_t)yo * POOL + a) * W + xin);
+      const T* v = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+      for (int o = 0; o < OPC; o++)
+#pragma unroll
+        for (int b = 0; b < POOL; b++) acc[o] += devo::ElemTraits<T>::to_float(v[o * POOL + b]);
+    }
+#pragma unroll
+    for (int o = 0; o < OPC; o++) {
+      const int x = ch * OPC + o;
+      if (x < nx) tile[x * (C + 1) + c] = (POOL == 1) ? acc[o] : acc[o] / (float)(POOL * POOL);
+    }
+  }
+  __syncthreads();
+  T* dst = out + (((size_t)n * Ho + yo) * Wo + x0) * C;
+  const int cv = C / 8;
+  for (int q = threadIdx.x; q < nx * cv; q += blockDim.x) {
+    const int c8 = q % cv, x = q / cv;
+    uint4 pk;
+    T* v = reinterpret_cast<T*>(&pk);
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = devo::ElemTraits<T>::from_float(tile[x * (C + 1) + c8 * 8 + k]);
+    *reinterpret_cast<uint4*>(dst + (size_t)x * C + c8 * 8) = pk;
   }
 }
 
@@ -389,7 +505,8 @@ static int make_map(CUtensorMap* m, int dtype, int rank, const void* ptr, const 
 
 template <typename T>
 static int launch_fast(const CUtensorMap* maps, const FastParams& prm, cudaStream_t s) {
-  const size_t smem = 1024 + (size_t)kStages * kStageBytes + 2 * kVsFloats * sizeof(float) + 16 * sizeof(uint64_t);
+  const size_t smem = 1024 + (size_t)kStages * kStageBytes + (size_t)kEpiGroups * 2 * kVsFloats * sizeof(float) +
+                      (size_t)kCoordRing * kCoordFloats * sizeof(float) + 32 * sizeof(uint64_t);
   static bool configured = false;
   if (!configured) {
     DEVO_CUDA(cudaFuncSetAttribute(corr_fast_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -416,10 +533,15 @@ int devo_pyramid_pack(const void* fmap_planar, void* out_pixel_major, int dtype,
   DEVO_REQUIRE(smem <= 48 * 1024, DEVO_ECAPACITY, "pyramid_pack: C too large");
   dim3 grid((Wo + 31) / 32, Ho, N);
   cudaStream_t s = (cudaStream_t)stream;
-  if (dtype == DEVO_F16)
-    pyramid_pack_kernel<__half><<<grid, 256, smem, s>>>((const __half*)fmap_planar, (__half*)out_pixel_major, C, H, W, Ho, Wo, pool);
-  else
-    pyramid_pack_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>((const __nv_bfloat16*)fmap_planar, (__nv_bfloat16*)out_pixel_major, C, H, W, Ho, Wo, pool);
+  const bool vec_ok = (W % 8 == 0) && (C % 8 == 0) && (pool == 1 || pool == 2 || pool == 4 || pool == 8) &&
+                      (((uintptr_t)fmap_planar & 15) == 0) && (((uintptr_t)out_pixel_major & 15) == 0);
+#define PACK_VEC(T, POOL) pyramid_pack_vec_kernel<T, POOL><<<grid, 256, smem, s>>>((const T*)fmap_planar, (T*)out_pixel_major, C, H, W, Ho, Wo)
+#define PACK_ANY(T) do { if (!vec_ok) pyramid_pack_kernel<T><<<grid, 256, smem, s>>>((const T*)fmap_planar, (T*)out_pixel_major, C, H, W, Ho, Wo, pool); \
+    else if (pool == 1) PACK_VEC(T, 1); else if (pool == 2) PACK_VEC(T, 2); else if (pool == 4) PACK_VEC(T, 4); else PACK_VEC(T, 8); } while (0)
+  if (dtype == DEVO_F16) PACK_ANY(__half);
+  else PACK_ANY(__nv_bfloat16);
+#undef PACK_ANY
+#undef PACK_VEC
   DEVO_LAUNCH_CHECK("pyramid_pack");
   return DEVO_OK;
 }

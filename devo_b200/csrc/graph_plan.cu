@@ -23,10 +23,12 @@ __device__ __forceinline__ int bits_needed(unsigned long long v) {   // v = max 
 template <int NT, int IPT>
 struct PlanSmall {
   using Sort = cub::BlockRadixSort<unsigned long long, NT, IPT, int>;
+  using Sort32 = cub::BlockRadixSort<unsigned int, NT, IPT, int, 5>;   // keys that fit 32 bits: half the exchange traffic
   using Reduce = cub::BlockReduce<unsigned long long, NT>;
   using Scan = cub::BlockScan<int, NT>;
   union Temp {
     typename Sort::TempStorage sort;
+    typename Sort32::TempStorage sort32;
     typename Reduce::TempStorage reduce;
     typename Scan::TempStorage scan;
   };
@@ -78,7 +80,16 @@ __global__ void __launch_bounds__(NT) plan_small_kernel(
     vals[k] = idx;
     keys[k] = (idx < E) ? ((a[k] << bits_b) | b[k]) : (1ull << bits);   // padding sorts last
   }
-  typename P::Sort(temp.sort).Sort(keys, vals, 0, bits + 1);
+  if (bits + 1 <= 32) {     // block-uniform
+    unsigned int k32[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; k++) k32[k] = (unsigned int)keys[k];
+    typename P::Sort32(temp.sort32).Sort(k32, vals, 0, bits + 1);
+#pragma unroll
+    for (int k = 0; k < IPT; k++) keys[k] = k32[k];
+  } else {
+    typename P::Sort(temp.sort).Sort(keys, vals, 0, bits + 1);
+  }
   __syncthreads();
 
   int32_t* pm = perm ? perm : perm_ws;

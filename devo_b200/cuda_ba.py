@@ -30,8 +30,10 @@ def _idx(t, name):
     return t.contiguous()
 
 
-def forward_async(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, t0, t1, iterations, status=None):
-    """enqueue the BA; returns the device status tensor (int32[1]) without synchronising"""
+def forward_async(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, t0, t1, iterations, status=None,
+                  plan=None, workspace=None):
+    """enqueue the BA; returns the device status tensor (int32[1]) without synchronising.
+    plan: a GraphPlan(kk, jj) of the same edge list to reuse (skips the internal sort)."""
     poses = _f32c(poses, "poses", True)
     patches = _f32c(patches, "patches", True)
     intrinsics = _f32c(intrinsics, "intrinsics")
@@ -50,7 +52,17 @@ def forward_async(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk,
         status = torch.empty(1, dtype=torch.int32, device=dev)
     L = _lib.lib()
     nbytes = L.devo_ba_workspace(E, max(int(t1) - int(t0), 0))
-    ws = _lib.workspace(nbytes, dev, "ba")
+    ws = workspace if workspace is not None else _lib.workspace(nbytes, dev, "ba")
+    if ws.numel() < nbytes:
+        raise RuntimeError("cuda_ba.forward: workspace too small")
+    if plan is not None:
+        _lib.check(L.devo_ba_forward_planned(poses.data_ptr(), patches.data_ptr(), intrinsics.data_ptr(), target.data_ptr(),
+                                             weight.data_ptr(), lmbda.data_ptr(), ii.data_ptr(), jj.data_ptr(), kk.data_ptr(),
+                                             E, n_poses, n_patches, P, int(t0), int(t1), int(iterations),
+                                             plan.perm.data_ptr(), plan.gstart.data_ptr(), plan.gkey.data_ptr(),
+                                             plan.ngroups.data_ptr(), ws.data_ptr(), ws.numel(), status.data_ptr(),
+                                             _lib.stream_ptr(dev)), "ba_forward_planned")
+        return status
     _lib.check(L.devo_ba_forward(poses.data_ptr(), patches.data_ptr(), intrinsics.data_ptr(), target.data_ptr(),
                                  weight.data_ptr(), lmbda.data_ptr(), ii.data_ptr(), jj.data_ptr(), kk.data_ptr(),
                                  E, n_poses, n_patches, P, int(t0), int(t1), int(iterations), ws.data_ptr(),

@@ -18,7 +18,8 @@ when it enters the ring buffer (replaces devo/devo.py:523-527 + pyramidify, util
 """
 import torch
 
-from . import cuda_ba, cuda_corr, projective_ops as pops
+from . import _lib, cuda_ba, cuda_corr, projective_ops as pops
+from .update import FrozenCast
 
 
 class UpdateOperator:
@@ -52,6 +53,10 @@ class UpdateOperator:
         self.status_sticky = torch.zeros(1, dtype=torch.int32, device=dev)
         self.plan_kk = None
         self.plan_ij = None
+        self.zeros_e = torch.zeros(self.E, dtype=i64, device=dev)
+        self.fc = FrozenCast(feat_dtype)
+        self._side = torch.cuda.Stream(device=dev)
+        self._ba_ws = torch.empty(_lib.lib().devo_ba_workspace(self.E, max(self.t1 - self.t0, 0)), dtype=torch.uint8, device=dev)
         self._graph = None
         self._pristine = None
         self.delta = None
@@ -67,7 +72,7 @@ class UpdateOperator:
         torch.add(self.ii * 12345, self.jj, out=self.pair_key)
         if self.plan_kk is None:
             self.plan_kk = cuda_ba.GraphPlan(self.kk, self.jj, self.Np, self.Nf)
-            self.plan_ij = cuda_ba.GraphPlan(self.pair_key, self.kk, -1, -1, want_neighbors=False)
+            self.plan_ij = cuda_ba.GraphPlan(self.pair_key, self.zeros_e, -1, 1, want_neighbors=False)
 
     def ingest_frame(self, idx, fmap, gmap_patches=None, imap_patches=None):
         """fmap [C,H,W] planar features of frame `idx` -> all pixel-major pyramid levels;
@@ -88,24 +93,30 @@ class UpdateOperator:
         if reset_geometry and self._pristine is not None:
             self.poses.copy_(self._pristine[0])
             self.patches.copy_(self._pristine[1])
+        # (0) graph analysis on the device (neighbours, patch groups, frame-pair groups) on a side stream:
+        #     it only depends on ii/jj/kk, so it overlaps the reprojection and the correlation lookup
+        cur = torch.cuda.current_stream(self.device)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            self.plan_kk.update()
+            self.plan_ij.update()
         # (1) reproject: [1,E,2,3,3]
         coords = pops.transform_fused(self.poses, self.patches, self.intrinsics, self.ii, self.jj, self.kk, layout=1)
         # (2) correlation lookup over all levels, output already in the GRU's [E, 882] layout
         corr = cuda_corr.lookup_fused(self.gmap_pm, self.levels_pm, self.levels, coords[0], self.kk, self.jj)
-        # (3) graph analysis on the device (neighbours, patch groups, frame-pair groups)
-        self.plan_kk.update()
-        self.plan_ij.update()
-        # (4) GRU
-        with torch.autocast("cuda", dtype=self.feat_dtype):
-            ctx = self.imap[:, self.kk]
-            net, (delta, weight, _) = self.update.forward_planned(
-                self.net, ctx, corr.view(1, self.E, -1), self.plan_kk, self.plan_ij, self.Np, self.Nf * self.Nf)
+        cur.wait_stream(self._side)
+        # (3) GRU: cached fp16 weights, autocast-identical dtype flow, no host sync
+        ctx = self.imap[:, self.kk]
+        net, (delta, weight, _) = self.update.forward_planned(
+            self.net, ctx, corr.view(1, self.E, -1), self.plan_kk, self.plan_ij, self.Np, self.Nf * self.Nf, self.fc)
         self.net.copy_(net)
-        # (5) BA targets and in-place Gauss-Newton
+        # (4) BA targets and in-place Gauss-Newton (reuses the kk/jj plan: one sort serves neighbours,
+        #     SoftAgg and the Schur grouping)
         target = coords[:, :, :, 1, 1] + delta.float()
         weight = weight.float()
         cuda_ba.forward_async(self.poses, self.patches, self.intrinsics, target, weight, self.lmbda,
-                              self.ii, self.jj, self.kk, self.t0, self.t1, self.ba_iterations, status=self.status)
+                              self.ii, self.jj, self.kk, self.t0, self.t1, self.ba_iterations, status=self.status,
+                              plan=self.plan_kk, workspace=self._ba_ws)
         torch.maximum(self.status_sticky, self.status.abs(), out=self.status_sticky)
         self.coords, self.delta, self.weight = coords, delta, weight
 

@@ -25,10 +25,16 @@ def _prep(*ts):
 
 
 def _call(name, gid, ref, ptrs, n):
-    if gid not in _DIMS:
-        raise RuntimeError("lietorch_backends: unknown group id %r" % (gid,))
+    _dims(gid)
     fn = getattr(_lib.lib(), "devo_lie_" + name)
     _lib.check(fn(int(gid), _lib.dtype_code(ref), *ptrs, int(n), _lib.stream_ptr(ref.device)), "lie_" + name)
+
+
+def _dims(gid):
+    try:
+        return _DIMS[gid]
+    except KeyError:
+        raise RuntimeError("lietorch_backends: unknown group id %r (SO3=1, RxSO3=2, SE3=3, Sim3=4)" % (gid,))
 
 
 def _new(ref, *shape):
@@ -37,7 +43,7 @@ def _new(ref, *shape):
 
 def expm(gid, a):
     _prep(a)
-    X = _new(a, a.shape[0], _DIMS[gid][1])
+    X = _new(a, a.shape[0], _dims(gid)[1])
     _call("expm", gid, a, [a.data_ptr(), X.data_ptr()], a.shape[0])
     return X
 
@@ -51,7 +57,7 @@ def expm_backward(gid, grad, a):
 
 def logm(gid, X):
     _prep(X)
-    a = _new(X, X.shape[0], _DIMS[gid][0])
+    a = _new(X, X.shape[0], _dims(gid)[0])
     _call("logm", gid, X, [X.data_ptr(), a.data_ptr()], X.shape[0])
     return a
 
@@ -146,7 +152,7 @@ def as_matrix(gid, X):
 
 def projector(gid, X):
     _prep(X)
-    N = _DIMS[gid][1]
+    N = _dims(gid)[1]
     P = _new(X, X.shape[0], N, N)
     _call("projector", gid, X, [X.data_ptr(), P.data_ptr()], X.shape[0])
     return P

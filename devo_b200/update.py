@@ -11,11 +11,58 @@ PyTorch / cuBLAS (only the index ops around them are on the hot pat
 """
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import cuda_ba, fastba
 from .scatter import scatter_softmax, scatter_sum
 
 DIM = 384
+
+
+class FrozenCast:
+    """Low-precision copies of a module's Linear parameters, made once and refreshed only when a
+    parameter changes.  torch.autocast re-casts every fp32 weight on every forward (about 40 cast
+    kernels and 18 MB of traffic per update iteration here); running the layers by hand on the cached
+    copies gives bit-identical results (same rounding of the weights, same dtype flow: Linear -> half,
+    LayerNorm -> float32, element-wise ops by type promotion) without that cost."""
+
+    def __init__(self, dtype=torch.float16):
+        self.dtype = dtype
+        self._cache = {}
+
+    def get(self, p):
+        hit = self._cache.get(id(p))
+        if hit is None or hit[0] != p._version or hit[1].device != p.device:
+            hit = (p._version, p.detach().to(self.dtype))
+            self._cache[id(p)] = hit
+        return hit[1]
+
+    def linear(self, layer, x):
+        return F.linear(x.to(self.dtype), self.get(layer.weight), self.get(layer.bias))
+
+    @staticmethod
+    def layer_norm(layer, x):
+        return F.layer_norm(x.float(), layer.normalized_shape, layer.weight, layer.bias, layer.eps)
+
+    def run(self, module, x):
+        """evaluate an nn.Sequential / layer of the update operator with autocast semantics"""
+        if isinstance(module, nn.Sequential):
+            for m in module:
+                x = self.run(m, x)
+            return x
+        if isinstance(module, nn.Linear):
+            return self.linear(module, x)
+        if isinstance(module, nn.LayerNorm):
+            return self.layer_norm(module, x)
+        if isinstance(module, nn.ReLU):
+            return torch.relu(x)
+        if isinstance(module, nn.Sigmoid):
+            return torch.sigmoid(x)
+        if isinstance(module, GradientClip):
+            return x
+        if isinstance(module, GatedResidual):
+            return x + self.run(module.gate, x) * self.run(module.res, x)
+        return module(x)
 
 
 class _ClipGrad(torch.autograd.Function):
@@ -61,9 +108,10 @@ class SoftAgg(nn.Module):
         y = scatter_sum(self.f(x) * w, jx, dim=1)
         return self.h(y)[:, jx] if self.expand else self.h(y)
 
-    def forward_planned(self, x, plan, max_groups):
-        y = cuda_ba.segment_softmax_sum(self.g(x), self.f(x), plan, max_groups)
-        return self.h(y)[:, plan.gid] if self.expand else self.h(y)
+    def forward_planned(self, x, plan, max_groups, fc=None):
+        lin = (lambda layer, t: layer(t)) if fc is None else fc.linear
+        y = cuda_ba.segment_softmax_sum(lin(self.g, x), lin(self.f, x), plan, max_groups)
+        return lin(self.h, y)[:, plan.gid] if self.expand else lin(self.h, y)
 
 
 class Update(nn.Module):
@@ -95,12 +143,16 @@ class Update(nn.Module):
         net = net + self.agg_ij(net, ii * 12345 + jj)
         return self._heads(net)
 
-    def forward_planned(self, net, inp, corr, plan_kk, plan_ij, max_patches, max_pairs):
-        """same computation; plan_kk = GraphPlan(kk, jj), plan_ij = GraphPlan(ii*12345+jj, ...)"""
-        net = self.norm(net + inp + self.corr(corr))
+    def forward_planned(self, net, inp, corr, plan_kk, plan_ij, max_patches, max_pairs, fc=None):
+        """same computation; plan_kk = GraphPlan(kk, jj), plan_ij = GraphPlan(ii*12345+jj, ...).
+        With `fc` (a FrozenCast) the layers run on cached low-precision weights with autocast's exact
+        dtype flow and no autocast context is needed; without it, call under torch.autocast."""
+        run = (lambda m, t: m(t)) if fc is None else fc.run
+        net = run(self.norm, net + inp + run(self.corr, corr))
         ix, jx = plan_kk.ix, plan_kk.jx
-        net = net + self.c1((ix >= 0).to(net.dtype).reshape(1, -1, 1) * net[:, ix])
-        net = net + self.c2((jx >= 0).to(net.dtype).reshape(1, -1, 1) * net[:, jx])
-        net = net + self.agg_kk.forward_planned(net, plan_kk, max_patches)
-        net = net + self.agg_ij.forward_planned(net, plan_ij, max_pairs)
-        return self._heads(net)
+        net = net + run(self.c1, (ix >= 0).to(net.dtype).reshape(1, -1, 1) * net[:, ix])
+        net = net + run(self.c2, (jx >= 0).to(net.dtype).reshape(1, -1, 1) * net[:, jx])
+        net = net + self.agg_kk.forward_planned(net, plan_kk, max_patches, fc)
+        net = net + self.agg_ij.forward_planned(net, plan_ij, max_pairs, fc)
+        net = run(self.gru, net)
+        return net, (run(self.d, net), run(self.w, net), None)

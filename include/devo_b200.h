@@ -113,6 +113,14 @@ int devo_ba_forward(float* poses, float* patches, const float* intrinsics, const
                     const int64_t* ii, const int64_t* jj, const int64_t* kk,
                     int E, int n_poses, int n_patches, int P, int t0, int t1, int iterations,
                     void* workspace, size_t workspace_bytes, int32_t* status, void* stream);
+/* same, reusing a devo_graph_plan(kk, jj) the caller already holds (perm/gstart/gkey/ngroups): the update
+ * operator needs that plan anyway for neighbors and the patch-wise SoftAgg, so one sort serves all three. */
+int devo_ba_forward_planned(float* poses, float* patches, const float* intrinsics, const float* target,
+                            const float* weight, const float* lmbda,
+                            const int64_t* ii, const int64_t* jj, const int64_t* kk,
+                            int E, int n_poses, int n_patches, int P, int t0, int t1, int iterations,
+                            const int32_t* perm, const int32_t* gstart, const int64_t* gkey, const int32_t* ngroups,
+                            void* workspace, size_t workspace_bytes, int32_t* status, void* stream);
 /* cuda_ba.reproject (devo/fastba/ba.cpp:155, ba_cuda.cu:368-418,543-575) -> coords [E,2,P,P] f32 */
 int devo_reproject(const float* poses, const float* patches, const float* intrinsics,
                    const int64_t* ii, const int64_t* jj, const int64_t* kk, float* coords,

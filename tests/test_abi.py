@@ -1,0 +1,39 @@
+"""CPU: the C-ABI shared library loads and exports every symbol include/devo_b200.h declares
+(no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from devo_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        from devo_b200 import build
+        build.build()
+    hdr = open(os.path.join(ROOT, "include", "devo_b200.h")).read()
+    declared = set(re.findall(r"\b(devo_[a-z0-9_A-Z]+)\s*\(", hdr))
+    assert len(declared) >= 37
+    h = ctypes.CDLL(_lib.LIB_PATH)
+    for sym in declared:
+        assert hasattr(h, sym), sym
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    L = _lib.lib()
+    assert L.devo_abi_version() == 1
+    assert L.devo_graph_plan_workspace(6144) > 0 and L.devo_ba_workspace(6144, 7) > L.devo_graph_plan_workspace(6144)
+    assert L.devo_launch_count() == 0 or L.devo_launch_count() > 0
+
+
+def test_sm100a_cubin_with_blackwell_instructions():
+    """the built library carries an sm_100a cubin whose SASS shows TMA and tcgen05 (B200_PROFILING.md)"""
+    import shutil
+    import subprocess
+    from devo_b200 import _lib
+    cu = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cu):
+        return
+    out = subprocess.run([cu, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in out, mnemonic

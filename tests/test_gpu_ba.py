@@ -91,15 +91,25 @@ def test_ba_masked_edges_and_failure_status():
     far["targets"] = P["targets"] + 1000.0
     poses, patches = _run_ba(far, 1, 3, 2)
     assert torch.allclose(poses.cpu(), P["poses0"].float(), atol=1e-6)
-    # NaN pose => non-finite system => status = iteration+1, and STRICT raises like linalg.cholesky
-    bad = P["poses0"].clone()
-    bad[0, 1, 0] = float("nan")
-    st = cuda_ba.forward_async(bad.float().cuda(), P["patches0"].float().cuda(), P["intrinsics"].float().cuda(),
-                               P["targets"].float().cuda(), P["weights"].float().cuda(), torch.tensor([1e-4], device="cuda"),
-                               P["ii"].cuda(), P["jj"].cuda(), P["kk"].cuda(), 1, 3, 2)
+    # a NaN weight makes the Schur system non-finite => status = iteration+1 (no update applied), and
+    # STRICT raises like torch::linalg::cholesky does in the reference (caught by devo.py:336-340)
+    badw = P["weights"].clone()
+    badw[0, 3, 0] = float("nan")
+    p0, x0 = P["poses0"].float().cuda(), P["patches0"].float().cuda()
+    st = cuda_ba.forward_async(p0, x0, P["intrinsics"].float().cuda(), P["targets"].float().cuda(), badw.float().cuda(),
+                               torch.tensor([1e-4], device="cuda"), P["ii"].cuda(), P["jj"].cuda(), P["kk"].cuda(), 1, 3, 2)
     assert int(st.item()) == 1
+    assert torch.equal(p0.cpu(), P["poses0"].float()) and torch.equal(x0.cpu(), P["patches0"].float())
+    bad = dict(P)
+    bad["weights"] = badw
     with pytest.raises(RuntimeError):
-        _run_ba(P, 1, 3, 2, poses=bad)
+        _run_ba(bad, 1, 3, 2)
+    # a NaN *pose* only masks its edges here (mask comparisons are false), where the reference turns
+    # 0*NaN into a failed factorisation: documented deviation
+    badp = P["poses0"].clone()
+    badp[0, 2, 0] = float("nan")
+    poses, patches = _run_ba(P, 1, 3, 1, poses=badp)
+    assert torch.isfinite(poses[0, :2]).all()
 
 
 @pytest.mark.parametrize("E,nk,nj", [(1, 1, 1), (7, 2, 3), (300, 20, 6), (5000, 300, 8), (12000, 500, 12), (40000, 2000, 22)])
@@ -211,3 +221,39 @@ def test_segment_softmax_sum_and_update_planned_equals_reference_semantics():
         pij = cuda_ba.GraphPlan(ii * 12345 + jj, kk, -1, -1, want_neighbors=False)
         n2, (d2, w2, _) = up.forward_planned(net, inp, corr, pk, pij, 48, 16)
     assert torch.allclose(n1, n2, atol=2e-4, rtol=1e-4) and torch.allclose(d1, d2, atol=2e-4) and torch.allclose(w1, w2, atol=2e-4)
+
+
+def test_frozen_cast_equals_autocast():
+    """the engine's cached-weight GRU path reproduces torch.autocast numerics"""
+    from devo_b200 import cuda_ba
+    from devo_b200.update import Update, FrozenCast
+    torch.manual_seed(1)
+    ii, jj, kk = [t.cuda() for t in fully_connected_graph(4, 12)]
+    E = ii.numel()
+    up = Update(3).cuda().eval()
+    net = torch.randn(1, E, 384, device="cuda").half()
+    inp = torch.randn(1, E, 384, device="cuda").half()
+    corr = torch.randn(1, E, 882, device="cuda").half()
+    pk = cuda_ba.GraphPlan(kk, jj, 48, 4)
+    pij = cuda_ba.GraphPlan(ii * 12345 + jj, torch.zeros_like(kk), -1, 1, want_neighbors=False)
+    with torch.no_grad():
+        with torch.autocast("cuda", dtype=torch.float16):
+            n1, (d1, w1, _) = up.forward_planned(net, inp, corr, pk, pij, 48, 16)
+        n2, (d2, w2, _) = up.forward_planned(net, inp, corr, pk, pij, 48, 16, FrozenCast(torch.float16))
+    assert n1.dtype == n2.dtype and d1.dtype == d2.dtype and w1.dtype == w2.dtype
+    assert torch.allclose(n1, n2, atol=1e-3, rtol=1e-3) and torch.allclose(d1.float(), d2.float(), atol=1e-3)
+    assert torch.allclose(w1.float(), w2.float(), atol=1e-3)
+
+
+def test_ba_with_shared_plan_is_bitwise_identical():
+    from devo_b200 import cuda_ba
+    P = ba_problem(n_frames=5, patches_per_frame=20, seed=4, init="perturbed")
+    a = lambda: (P["poses0"].float().cuda().contiguous(), P["patches0"].float().cuda().contiguous())
+    rest = (P["intrinsics"].float().cuda(), P["targets"].float().cuda(), P["weights"].float().cuda(),
+            torch.tensor([1e-4], device="cuda"), P["ii"].cuda(), P["jj"].cuda(), P["kk"].cuda(), 1, 5, 2)
+    p1, x1 = a()
+    cuda_ba.forward_async(p1, x1, *rest)
+    p2, x2 = a()
+    plan = cuda_ba.GraphPlan(P["kk"].cuda(), P["jj"].cuda(), 100, 5)
+    st = cuda_ba.forward_async(p2, x2, *rest, plan=plan)
+    assert int(st.item()) == 0 and torch.equal(p1, p2) and torch.equal(x1, x2)
