@@ -38,8 +38,8 @@ extern "C" size_t devo_graph_plan_workspace(int E);
 
 namespace {
 
-constexpr int kAccThreads = 256;
-constexpr int kSolveThreads = 1024;
+constexpr int kAccThreads = 512;
+constexpr int kSolveThreads = 512;
 constexpr int kMaxN6 = 150;            // 25 free poses
 constexpr size_t kAccSmemBudget = 200 * 1024;
 
@@ -167,7 +167,7 @@ struct BaLayout {
 static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static int acc_grid(int E) {
-  int g = (E + 127) / 128;
+  int g = (E + 63) / 64;
   if (g < 1) g = 1;
   if (g > 148) g = 148;
   return g;
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
 }
 
 // ---- solve kernel ---------------------------------------------------------------------------
-// smem: A packed lower-triangular n(n+1)/2 doubles (A(i,j) at i(i+1)/2 + j, j<=i), y[n] doubles.
+// smem: A packed lower-triangular n(n+1)/2 doubles (A(i,j) at i(i+1)/2 + j, j<=i), y[n+1], rinv[n] doubles.
 // Square-root-free elimination of the augmented system [S | y] with ONE barrier per pivot:
 //   step k:  r = 1/A_kk ;  A_ij -= A_ik A_jk r  (i>=j>k) ;  y_i -= A_ik y_k r  (i>k)
 // reads touch column k only, writes touch columns > k only, so no second barrier is needed.
@@ -433,26 +433,51 @@ __global__ void __launch_bounds__(kSolveThreads, 1) ba_solve_kernel(
   }
   __syncthreads();
 
-  for (int k = 0; k < n; k++) {
-    const double akk = A[(size_t)k * (k + 1) / 2 + k];
-    if (!(akk > 0.0) || !isfinite(akk)) {                // uniform: every thread reads the same value
-      if (tid == 0) s_fail = 1;
-      break;
+  // Fixed ownership: thread t owns lower-triangular entries e = t, t+1024, ... of the augmented matrix
+  // (row gi, column gj <= gi; the extra last row gi == n is y^T).  Entry (gi,gj) takes part in pivot step
+  // k while gj > k.  The reciprocal of the next pivot is produced by the one thread that finalises it, so the
+  // 1/d division (a long fp64 sequence) is executed once per step instead of by every warp.
+  constexpr int kEnt = ((kMaxN6 + 1) * (kMaxN6 + 2) / 2 + kSolveThreads - 1) / kSolveThreads;
+  int ent[kEnt];                                          // (gi << 16) | gj, or -1
+  const int naug = (n + 1) * (n + 2) / 2 - 1;            // lower triangle of the (n+1)x(n+1) matrix without (n,n)
+#pragma unroll
+  for (int q = 0; q < kEnt; q++) {
+    const int e = tid + q * kSolveThreads;
+    int gi = 0, gj = 0;
+    if (e < naug) {
+      gi = (int)floorf((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+      while (gi * (gi + 1) / 2 > e) gi--;
+      while ((gi + 1) * (gi + 2) / 2 <= e) gi++;
+      gj = e - gi * (gi + 1) / 2;
     }
-    const double r = 1.0 / akk;
-    const int m = n - k - 1;                              // trailing size
-    const int cnt = m * (m + 1) / 2;
-    for (int q = tid; q < cnt + m; q += kSolveThreads) {
-      if (q < cnt) {
-        int i = (int)floorf((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
-        while (i * (i + 1) / 2 > q) i--;
-        while ((i + 1) * (i + 2) / 2 <= q) i++;
-        const int j = q - i * (i + 1) / 2;
-        const int gi = k + 1 + i, gj = k + 1 + j;
-        A[(size_t)gi * (gi + 1) / 2 + gj] -= A[(size_t)gi * (gi + 1) / 2 + k] * A[(size_t)gj * (gj + 1) / 2 + k] * r;
+    ent[q] = (e < naug) ? ((gi << 16) | gj) : -1;
+  }
+  double* rinv = y + n + 1;                               // [n] reciprocals of the pivots
+  if (tid == 0) {
+    const double a00 = A[0];
+    if (!(a00 > 0.0) || !isfinite(a00)) s_fail = 1;
+    rinv[0] = 1.0 / a00;
+  }
+  __syncthreads();
+  for (int k = 0; k < n; k++) {
+    if (s_fail) break;                                    // uniform (written before the last barrier)
+    const double r = rinv[k];
+    const double yk = y[k];
+#pragma unroll
+    for (int q = 0; q < kEnt; q++) {
+      if (ent[q] < 0) continue;
+      const int gi = ent[q] >> 16, gj = ent[q] & 0xffff;
+      if (gj <= k) continue;
+      if (gi < n) {
+        const size_t at = (size_t)gi * (gi + 1) / 2;
+        const double v = A[at + gj] - A[at + k] * A[(size_t)gj * (gj + 1) / 2 + k] * r;
+        A[at + gj] = v;
+        if (gi == k + 1 && gj == k + 1) {                 // the next pivot is final now
+          if (!(v > 0.0) || !isfinite(v)) s_fail = 1;
+          rinv[k + 1] = 1.0 / v;
+        }
       } else {
-        const int gi = k + 1 + (q - cnt);
-        y[gi] -= A[(size_t)gi * (gi + 1) / 2 + k] * y[k] * r;
+        y[gj] -= A[(size_t)gj * (gj + 1) / 2 + k] * yk * r;   // last row of the augmented matrix: y
       }
     }
     __syncthreads();
@@ -686,16 +711,16 @@ static int ba_forward_impl(float* poses, float* patches, const float* intrinsics
                           centre, t0, nfree, n_poses, EB, GB, smem_acc, APPLY, DOACC, ITR, s, perm_p, gstart_p, gkey_p, ngroups_p)
 #define ACC_DISPATCH(APPLY, DOACC, ITR)                   \
   do {                                                    \
-    if (ept <= 4) rc = ACC(4, APPLY, DOACC, ITR);         \
+    if (ept <= 2) rc = ACC(2, APPLY, DOACC, ITR);         \
+    else if (ept <= 4) rc = ACC(4, APPLY, DOACC, ITR);    \
     else if (ept <= 8) rc = ACC(8, APPLY, DOACC, ITR);    \
     else if (ept <= 16) rc = ACC(16, APPLY, DOACC, ITR);  \
-    else if (ept <= 32) rc = ACC(32, APPLY, DOACC, ITR);  \
-    else rc = ACC(48, APPLY, DOACC, ITR);                 \
+    else rc = ACC(24, APPLY, DOACC, ITR);                 \
     if (rc != DEVO_OK) return rc;                         \
   } while (0)
 
-  DEVO_REQUIRE(ept <= 48, DEVO_ECAPACITY, "ba_forward: system too large (%d entries)", L.nent);
-  const size_t smem_solve = ((size_t)n6 * (n6 + 1) / 2 + n6 + 2) * 8;
+  DEVO_REQUIRE(ept <= 24, DEVO_ECAPACITY, "ba_forward: system too large (%d entries)", L.nent);
+  const size_t smem_solve = ((size_t)n6 * (n6 + 1) / 2 + 2 * n6 + 4) * 8;
   static size_t solve_configured = 0;
   if (smem_solve > solve_configured) {
     DEVO_CUDA(cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));

@@ -49,6 +49,7 @@ struct FastParams {
   int E, L, items, khalves;                 // khalves = C / 64
   int H[DEVO_MAX_LEVELS], W[DEVO_MAX_LEVELS];
   float scale[DEVO_MAX_LEVELS];
+  float inv_scale[DEVO_MAX_LEVELS];         // 1/scale when that is exact (power of two), else 0 => divide
   const float* coords;
   const int64_t* ii;
   const int64_t* jj;
@@ -145,10 +146,14 @@ struct Geo {
   int x0, y0;        // box origin (warp-uniform)
 };
 // cs: the edge's 18 staged coordinates in shared memory ([2][9])
-__device__ __forceinline__ Geo make_geo(const float* cs, float scale, int lane) {
+__device__ __forceinline__ Geo make_geo(const float* cs, float scale, float inv_scale, int lane) {
   Geo g;
   float x = 0.f, y = 0.f;
-  if (lane < kPP) { x = cs[lane] / scale; y = cs[kPP + lane] / scale; }
+  if (lane < kPP) {
+    x = cs[lane]; y = cs[kPP + lane];
+    if (inv_scale != 0.f) { x *= inv_scale; y *= inv_scale; }   // exact for powers of two (== coords / scale)
+    else { x /= scale; y /= scale; }
+  }
   g.fx = safe_floor_int(x, g.dx);
   g.fy = safe_floor_int(y, g.dy);
   int mx = lane < kPP ? g.fx : 0x7fffffff, my = lane < kPP ? g.fy : 0x7fffffff;
@@ -264,7 +269,7 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
       const int e = item / L, l = item - e * L;
       const int b = (e - eb0) >> 3;
       if (b + 2 > issued && issued < nb) { issue_coords(issued); issued++; }   // keep one batch ahead
-      Geo g = make_geo(cv.edge(e), prm.scale[l], lane);
+      Geo g = make_geo(cv.edge(e), prm.scale[l], prm.inv_scale[l], lane);
       if (lane == 0) {
         const CUtensorMap* tm = (l == 0) ? &tm_l0 : (l == 1) ? &tm_l1 : (l == 2) ? &tm_l2 : &tm_l3;
         const int frame = (int)prm.jj[e];
@@ -318,14 +323,35 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
     const int et = ((warp - 2) & 3) * 32 + lane;  // 0..127 within the group
     T* out = reinterpret_cast<T*>(prm.out);
     float* vbase = Vs + grp * 2 * kVsFloats;
+    // output ownership, fixed for the whole kernel: thread -> patch pixel p and window offsets
+    // o = s, s+14, s+28, s+42 (< 49).  Consecutive threads own consecutive p, so for a fixed offset nine
+    // neighbouring threads write nine neighbouring outputs.
+    const bool owner = et < 14 * kPP;
+    const int p = owner ? et % kPP : 0;
+    const int s14 = et / kPP;
+    int soff[4], ooff[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int o = s14 + 14 * k;
+      const int yo = o / kOut, xo = o - yo * kOut;
+      soff[k] = (owner && o < kOut * kOut) ? yo * kBox + xo : -1;
+      ooff[k] = ((xo * kOut + yo) * kPP + p) * L;
+    }
     uint32_t aphase = 0;
     int buf = 0;
     for (int item = first + grp; item < last; item += kEpiGroups) {
       const int e = item / L, l = item - e * L;
-      Geo g = make_geo(cv.edge(e), prm.scale[l], lane);
+      Geo g = make_geo(cv.edge(e), prm.scale[l], prm.inv_scale[l], lane);
       // per-pixel blend record, owned by lane p: offset of the window origin inside the box (or -1), fractions
       const int ox = g.fx - kRadius - g.x0, oy = g.fy - kRadius - g.y0;
       const int woff = (ox + 8 <= kBox && oy + 8 <= kBox) ? oy * kBox + ox : -1;
+      const int pw = __shfl_sync(0xffffffffu, woff, p);
+      const float dx = __shfl_sync(0xffffffffu, g.dx, p), dy = __shfl_sync(0xffffffffu, g.dy, p);
+      const bool any_unfit = __any_sync(0xffffffffu, lane < kPP && woff < 0);
+      int pfx = 0, pfy = 0;
+      if (any_unfit) { pfx = __shfl_sync(0xffffffffu, g.fx, p); pfy = __shfl_sync(0xffffffffu, g.fy, p); }
+      const float w00 = (1.f - dx) * (1.f - dy), w01 = dx * (1.f - dy), w10 = (1.f - dx) * dy, w11 = dx * dy;
+
       mbar_wait(&tfull[grp], aphase);
       tc_fence_after();
       uint32_t v[16];
@@ -341,39 +367,39 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
       if (lane == 0) mbar_arrive(&tempty[grp]);   // accumulator stage free for the MMA warp
       float* vs = vbase + buf * kVsFloats;
 #pragma unroll
-      for (int p = 0; p < kPP; p++) vs[p * 128 + row] = __uint_as_float(v[p]);
+      for (int q = 0; q < kPP; q++) vs[q * 128 + row] = __uint_as_float(v[q]);
       if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // the 4 warps of this group only
       else          asm volatile("bar.sync 2, 128;" ::: "memory");
 
-      const size_t obase = (size_t)e * (kOut * kOut * kPP) * L + l;
+      T* orow = out + (size_t)e * (kOut * kOut * kPP) * L + l;
+      if (pw >= 0) {
+        const float* sp = vs + p * 128 + pw;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if (soff[k] >= 0) {
+            const float* s4 = sp + soff[k];
+            const float r = w00 * s4[0] + w01 * s4[1] + w10 * s4[kBox] + w11 * s4[kBox + 1];
+            orow[ooff[k]] = from_f<T>(r);
+          }
+        }
+      } else if (owner) {
+        // this pixel's window lies outside the staged box (large scale change): direct evaluation
+        const T* gp = reinterpret_cast<const T*>(prm.gmap_pm) + ((size_t)prm.ii[e] * kPP + p) * prm.C;
+        const T* lv = reinterpret_cast<const T*>(prm.level[l]);
+        const int fr = (int)prm.jj[e];
+        const int H = prm.H[l], W = prm.W[l];
 #pragma unroll 1
-      for (int it = 0; it < 4; it++) {
-        const int q = et + it * 128;
-        const bool active = q < kOut * kOut * kPP;
-        const int p = active ? q % kPP : 0;
-        const int pw = __shfl_sync(0xffffffffu, woff, p);
-        const float dx = __shfl_sync(0xffffffffu, g.dx, p), dy = __shfl_sync(0xffffffffu, g.dy, p);
-        const int pfx = __shfl_sync(0xffffffffu, g.fx, p), pfy = __shfl_sync(0xffffffffu, g.fy, p);
-        if (!active) continue;
-        const int yo = (q / kPP) % kOut, xo = q / (kPP * kOut);
-        float r;
-        if (pw >= 0) {
-          const float* s = vs + p * 128 + pw + yo * kBox + xo;
-          r = (1.f - dx) * (1.f - dy) * s[0] + dx * (1.f - dy) * s[1] + (1.f - dx) * dy * s[kBox] + dx * dy * s[kBox + 1];
-        } else {
-          // window outside the staged box (large scale change): direct evaluation
-          const T* gp = reinterpret_cast<const T*>(prm.gmap_pm) + ((size_t)prm.ii[e] * kPP + p) * prm.C;
-          const T* lv = reinterpret_cast<const T*>(prm.level[l]);
-          const int fr = (int)prm.jj[e];
-          const int H = prm.H[l], W = prm.W[l];
+        for (int k = 0; k < 4; k++) {
+          const int o = s14 + 14 * k;
+          if (o >= kOut * kOut) continue;
+          const int yo = o / kOut, xo = o - yo * kOut;
           const int yy = pfy - kRadius + yo, xx = pfx - kRadius + xo;
           const float v00 = direct_dot<T>(gp, lv, H, W, prm.C, fr, yy, xx);
           const float v01 = direct_dot<T>(gp, lv, H, W, prm.C, fr, yy, xx + 1);
           const float v10 = direct_dot<T>(gp, lv, H, W, prm.C, fr, yy + 1, xx);
           const float v11 = direct_dot<T>(gp, lv, H, W, prm.C, fr, yy + 1, xx + 1);
-          r = (1.f - dx) * (1.f - dy) * v00 + dx * (1.f - dy) * v01 + (1.f - dx) * dy * v10 + dx * dy * v11;
+          orow[((xo * kOut + yo) * kPP + p) * L] = from_f<T>(w00 * v00 + w01 * v01 + w10 * v10 + w11 * v11);
         }
-        out[obase + (size_t)q * L] = from_f<T>(r);
       }
       buf ^= 1;
       aphase ^= 1;
@@ -584,6 +610,11 @@ int devo_corr_lookup_fused(const void* gmap_pm, const devo_pyramid_t* pyr, const
     DEVO_REQUIRE(((uintptr_t)pyr->level[ls] & 15) == 0, DEVO_EINVAL, "corr_lookup_fused: level %d not 16-byte aligned", ls);
     DEVO_REQUIRE(pyr->scale[ls] > 0.f, DEVO_EINVAL, "corr_lookup_fused: level %d scale must be > 0", ls);
     prm.H[l] = pyr->H[ls]; prm.W[l] = pyr->W[ls]; prm.scale[l] = pyr->scale[ls]; prm.level[l] = pyr->level[ls];
+    {
+      int ex = 0;
+      const float m = frexpf(pyr->scale[ls], &ex);
+      prm.inv_scale[l] = (m == 0.5f) ? 1.0f / pyr->scale[ls] : 0.0f;   // power of two => multiplication is exact
+    }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)pyr->W[ls], (cuuint64_t)pyr->H[ls], (cuuint64_t)Nf};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * pyr->W[ls], (cuuint64_t)C * 2 * pyr->W[ls] * pyr->H[ls]};
     cuuint32_t box[4] = {64, kBox, kBox, 1};

@@ -3,8 +3,7 @@
 // the role torch_scatter 2.0.9 plays in the reference.  Groups come from the graph plan
 // (graph_plan.cu): rows of a group are perm[gstart[g] .. gstart[g+1]).
 //
-// One CTA per group; threads cover the channels (coalesced along the channel axis) times up to 4
-// row-parts, single pass with an online (running max) softmax: every g/f element is read exactly
+// grid = (groups, channel chunks of 128); threads = 128 channels (coalesced) x up to 8 row-parts, single pass with an online (running max) softmax: every g/f element is read exactly
 // once; nothing but the [n_groups, dim] result is written.  fp32 arithmetic regardless of storage type.
 #include "common.cuh"
 
@@ -17,18 +16,18 @@ template <typename T>
 __global__ void segment_softmax_sum_kernel(const T* __restrict__ g, const T* __restrict__ f,
                                            const int32_t* __restrict__ perm, const int32_t* __restrict__ gstart,
                                            const int32_t* __restrict__ ngroups, T* __restrict__ y, int dim) {
-  extern __shared__ float red[];   // [parts][3][dim]
+  extern __shared__ float red[];   // [parts][3][blockDim.x]
   const int grp = blockIdx.x;
   const int G = *ngroups;
   const int parts = blockDim.y, part = threadIdx.y;
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;    // one channel per thread, channel chunks across blockIdx.y
   T* yo = y + (size_t)grp * dim;
   if (grp >= G) {   // padding rows of the fixed-size output
-    if (part == 0)
-      for (int c = threadIdx.x; c < dim; c += blockDim.x) yo[c] = ElemTraits<T>::from_float(0.f);
+    if (part == 0 && c < dim) yo[c] = ElemTraits<T>::from_float(0.f);
     return;
   }
   const int s0 = gstart[grp], s1 = gstart[grp + 1];
-  for (int c = threadIdx.x; c < dim; c += blockDim.x) {
+  if (c < dim) {
     float m = -INFINITY, den = 0.f, num = 0.f;
     for (int s = s0 + part; s < s1; s += 4 * parts) {
       float gv[4], fv[4];
@@ -56,24 +55,22 @@ __global__ void segment_softmax_sum_kernel(const T* __restrict__ g, const T* __r
         }
       }
     }
-    red[(part * 3 + 0) * dim + c] = m;
-    red[(part * 3 + 1) * dim + c] = den;
-    red[(part * 3 + 2) * dim + c] = num;
+    red[(part * 3 + 0) * blockDim.x + threadIdx.x] = m;
+    red[(part * 3 + 1) * blockDim.x + threadIdx.x] = den;
+    red[(part * 3 + 2) * blockDim.x + threadIdx.x] = num;
   }
   __syncthreads();
-  if (part == 0) {
-    for (int c = threadIdx.x; c < dim; c += blockDim.x) {
-      float m = -INFINITY;
-      for (int p = 0; p < parts; p++) m = fmaxf(m, red[(p * 3 + 0) * dim + c]);
-      float den = 0.f, num = 0.f;
-      for (int p = 0; p < parts; p++) {
-        const float mp = red[(p * 3 + 0) * dim + c];
-        const float sc = (mp > -INFINITY) ? __expf(mp - m) : 0.f;
-        den += sc * red[(p * 3 + 1) * dim + c];
-        num += sc * red[(p * 3 + 2) * dim + c];
-      }
-      yo[c] = ElemTraits<T>::from_float(den > 0.f ? num / den : 0.f);
+  if (part == 0 && c < dim) {
+    float m = -INFINITY;
+    for (int p = 0; p < parts; p++) m = fmaxf(m, red[(p * 3 + 0) * blockDim.x + threadIdx.x]);
+    float den = 0.f, num = 0.f;
+    for (int p = 0; p < parts; p++) {
+      const float mp = red[(p * 3 + 0) * blockDim.x + threadIdx.x];
+      const float sc = (mp > -INFINITY) ? __expf(mp - m) : 0.f;
+      den += sc * red[(p * 3 + 1) * blockDim.x + threadIdx.x];
+      num += sc * red[(p * 3 + 2) * blockDim.x + threadIdx.x];
     }
+    yo[c] = ElemTraits<T>::from_float(den > 0.f ? num / den : 0.f);
   }
 }
 }  // namespace
@@ -83,14 +80,14 @@ extern "C" int devo_segment_softmax_sum(const void* g, const void* f, const int3
                                         int dim, void* stream) {
   if (max_groups <= 0 || dim <= 0) return DEVO_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  int tx = dim >= 256 ? 256 : ((dim + 31) / 32) * 32;
-  int parts = 1024 / tx;
-  if (parts > 4) parts = 4;
-  if (n_rows > 0 && max_groups > 0 && n_rows / max_groups < 2 * parts) parts = 1;   // tiny groups: no split
+  const int tx = 128;                                        // channels per CTA
+  int parts = 8;                                             // row-parts per channel
+  const int avg_rows = (n_rows > 0 && max_groups > 0) ? n_rows / max_groups : 1;
+  while (parts > 1 && avg_rows < 2 * parts) parts >>= 1;     // small groups: fewer parts
   dim3 block(tx, parts);
-  const size_t smem = (size_t)parts * 3 * dim * sizeof(float);
-  DEVO_REQUIRE(smem <= 48 * 1024, DEVO_ECAPACITY, "segment_softmax_sum: dim too large");
-#define SEG(T) segment_softmax_sum_kernel<T><<<max_groups, block, smem, s>>>((const T*)g, (const T*)f, perm, gstart, ngroups, (T*)y_out, dim)
+  dim3 grid(max_groups, (dim + tx - 1) / tx);
+  const size_t smem = (size_t)parts * 3 * tx * sizeof(float);
+#define SEG(T) segment_softmax_sum_kernel<T><<<grid, block, smem, s>>>((const T*)g, (const T*)f, perm, gstart, ngroups, (T*)y_out, dim)
   switch (dtype) {
     case DEVO_F16: SEG(__half); break;
     case DEVO_BF16: SEG(__nv_bfloat16); break;
