@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdevo_b200.so")
+LIB_PATH = os.environ.get("DEVO_B200_LIB") or os.path.join(_HERE, "lib", "libdevo_b200.so")
 
 F16, BF16, F32, F64 = 0, 1, 2, 3
 _DTYPES = {torch.float16: F16, torch.bfloat16: BF16, torch.float32: F32, torch.float64: F64}

@@ -17,13 +17,15 @@
 //                                      y = v - E Q u  is accumulated in registers, one fixed
 //                                      set of matrix entries per thread, fixed summation order:
 //                                      no atomics at all, bitwise reproducible.
-//   solve  (1 launch per iteration)    one CTA: fixed-order reduction of the partials, damping,
-//                                      in-smem fp64 LDL^T elimination of [S|y] (one barrier per pivot),
-//                                      warp-shuffle back-substitution, SE3 retraction.
+//   solve  (same launch)               the last accumulate CTA to finish (atomic ticket): fixed-order
+//                                      reduction of the partials, damping, in-smem fp64 LDL^T elimination
+//                                      of [S|y] (one barrier per pivot), warp-shuffle back-substitution,
+//                                      SE3 retraction.
 //   depth update                       dZ_k = Q_k (u_k - E_k . dX); fused into the prologue of the
 //                                      next iteration's accum launch (same patch ownership).
 //
-// => 2*iterations+2 launches, no host sync, no global atomics, CUDA-graph capturable.
+// => iterations+1 launches (+1 for the plan unless shared), no host sync, no floating-point atomics,
+//    CUDA-graph capturable.
 // Deliberate deviations from the reference (documented in DESIGN.md):
 //   * the 6N x 6N system is accumulated and solved in fp64 (the reference: fp32 atomics,
 //     run-to-run non-deterministic); inputs/outputs and per-edge Jacobians stay fp32.
@@ -39,7 +41,7 @@ extern "C" size_t devo_graph_plan_workspace(int E);
 namespace {
 
 constexpr int kAccThreads = 512;
-constexpr int kSolveThreads = 512;
+constexpr int kSolveThreads = kAccThreads;   // the solve runs inside the last accumulate CTA
 constexpr int kMaxN6 = 150;            // 25 free poses
 constexpr size_t kAccSmemBudget = 200 * 1024;
 
@@ -161,7 +163,7 @@ __device__ __forceinline__ void edge_terms(const float* __restrict__ poses, cons
 
 // ---- workspace ------------------------------------------------------------------------------
 struct BaLayout {
-  size_t perm, gstart, gkey, ngroups, plan_ws, plan_bytes, Q, U, Ek, partials, dX, total;
+  size_t perm, gstart, gkey, ngroups, plan_ws, plan_bytes, Q, U, Ek, partials, dX, ticket, total;
   int grid, nent, n6;
 };
 static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -192,6 +194,7 @@ static BaLayout ba_layout(int E, int nfree) {
   L.Ek = off;      off += al(Em * (size_t)(n6 > 0 ? n6 : 1) * 8);
   L.partials = off; off += al((size_t)L.grid * L.nent * 8);
   L.dX = off;      off += al((size_t)(n6 > 0 ? n6 : 1) * 8);
+  L.ticket = off;  off += al(16);
   L.total = off;
   return L;
 }
@@ -209,6 +212,156 @@ __device__ __forceinline__ void tri_decode(int idx, int m, int& a, int& b) {
   b = idx - (aa * m - aa * (aa - 1) / 2) + aa;
 }
 
+// ---- solve (executed by the last accumulate CTA to finish) -----------------------------------
+// smem: A packed lower-triangular n(n+1)/2 doubles (A(i,j) at i(i+1)/2 + j, j<=i), y[n+1], rinv[n] doubles.
+// Square-root-free elimination of the augmented system [S | y] with ONE barrier per pivot:
+//   step k:  r = 1/A_kk ;  A_ij -= A_ik A_jk r  (i>=j>k) ;  y_i -= A_ik y_k r  (i>k)
+// reads touch column k only, writes touch columns > k only, so no second barrier is needed.
+// Afterwards A_ik (i>k) = L_ik d_k and y = L^-1 y; warp 0 finishes x = L^-T D^-1 y with shuffles.
+// S positive definite  <=>  every pivot d_k = A_kk > 0 (same acceptance test as Cholesky).
+__device__ void ba_solve_device(unsigned char* smem_raw, float* poses, const double* partials, double* dX,
+                                int32_t* status, int nparts, int t0, int nfree, int itr) {
+  const int n = 6 * nfree;
+  const int LD = n + 1;
+  const int nent = (n + 1) * (n + 2) / 2;
+  double* A = reinterpret_cast<double*>(smem_raw);
+  double* y = A + (size_t)n * (n + 1) / 2;
+  __shared__ int s_fail;
+  const int tid = threadIdx.x;
+  if (*status != 0) return;
+  if (n == 0) return;
+  if (tid == 0) s_fail = 0;
+
+  // fixed-order reduction of the per-CTA partials; entry (a,b), a<=b of the (n+1)x(n+1) augmented matrix
+  for (int idx = tid; idx < nent; idx += kSolveThreads) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int p = 0;
+    for (; p + 4 <= nparts; p += 4) {
+      s0 += __ldcg(&partials[(size_t)(p + 0) * nent + idx]);
+      s1 += __ldcg(&partials[(size_t)(p + 1) * nent + idx]);
+      s2 += __ldcg(&partials[(size_t)(p + 2) * nent + idx]);
+      s3 += __ldcg(&partials[(size_t)(p + 3) * nent + idx]);
+    }
+    for (; p < nparts; p++) s0 += __ldcg(&partials[(size_t)p * nent + idx]);
+    double s = (s0 + s1) + (s2 + s3);
+    int a, b;
+    tri_decode(idx, LD, a, b);
+    if (b == n) {
+      if (a < n) y[a] = s;                                // y = v - E Q u
+    } else {
+      if (a == b) s += 1e-4 * s + 1.0;                    // S += I o (1e-4 S + 1)   (:517-518)
+      A[(size_t)b * (b + 1) / 2 + a] = s;                 // symmetric: store as lower (b,a)
+    }
+  }
+  __syncthreads();
+
+  // Fixed ownership: thread t owns lower-triangular entries e = t, t+1024, ... of the augmented matrix
+  // (row gi, column gj <= gi; the extra last row gi == n is y^T).  Entry (gi,gj) takes part in pivot step
+  // k while gj > k.  The reciprocal of the next pivot is produced by the one thread that finalises it, so the
+  // 1/d division (a long fp64 sequence) is executed once per step instead of by every warp.
+  constexpr int kEnt = ((kMaxN6 + 1) * (kMaxN6 + 2) / 2 + kSolveThreads - 1) / kSolveThreads;
+  int ent[kEnt];                                          // (gi << 16) | gj, or -1
+  const int naug = (n + 1) * (n + 2) / 2 - 1;            // lower triangle of the (n+1)x(n+1) matrix without (n,n)
+#pragma unroll
+  for (int q = 0; q < kEnt; q++) {
+    const int e = tid + q * kSolveThreads;
+    int gi = 0, gj = 0;
+    if (e < naug) {
+      gi = (int)floorf((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+      while (gi * (gi + 1) / 2 > e) gi--;
+      while ((gi + 1) * (gi + 2) / 2 <= e) gi++;
+      gj = e - gi * (gi + 1) / 2;
+    }
+    ent[q] = (e < naug) ? ((gi << 16) | gj) : -1;
+  }
+  double* rinv = y + n + 1;                               // [n] reciprocals of the pivots
+  if (tid == 0) {
+    const double a00 = A[0];
+    if (!(a00 > 0.0) || !isfinite(a00)) s_fail = 1;
+    rinv[0] = 1.0 / a00;
+  }
+  __syncthreads();
+  for (int k = 0; k < n; k++) {
+    if (s_fail) break;                                    // uniform (written before the last barrier)
+    const double r = rinv[k];
+    const double yk = y[k];
+#pragma unroll
+    for (int q = 0; q < kEnt; q++) {
+      if (ent[q] < 0) continue;
+      const int gi = ent[q] >> 16, gj = ent[q] & 0xffff;
+      if (gj <= k) continue;
+      if (gi < n) {
+        const size_t at = (size_t)gi * (gi + 1) / 2;
+        const double v = A[at + gj] - A[at + k] * A[(size_t)gj * (gj + 1) / 2 + k] * r;
+        A[at + gj] = v;
+        if (gi == k + 1 && gj == k + 1) {                 // the next pivot is final now
+          if (!(v > 0.0) || !isfinite(v)) s_fail = 1;
+          rinv[k + 1] = 1.0 / v;
+        }
+      } else {
+        y[gj] -= A[(size_t)gj * (gj + 1) / 2 + k] * yk * r;   // last row of the augmented matrix: y
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (s_fail) {
+    if (tid == 0) atomicCAS(status, 0, itr + 1);
+    return;
+  }
+  // back substitution by warp 0: x_k = y_k/d_k - sum_{i>k} (A_ik/d_k) x_i ; lane l owns x[l + 32 m]
+  if (tid < 32) {
+    constexpr int kMaxPerLane = (kMaxN6 + 31) / 32;
+    const int nper = (n + 31) >> 5;                      // slots actually used
+    double x[kMaxPerLane], invd[kMaxPerLane];
+#pragma unroll
+    for (int mm = 0; mm < kMaxPerLane; mm++) {
+      const int i = tid + 32 * mm;
+      invd[mm] = (i < n) ? 1.0 / A[(size_t)i * (i + 1) / 2 + i] : 0.0;
+      x[mm] = (i < n) ? y[i] * invd[mm] : 0.0;                           // D^-1 y
+    }
+    for (int k = n - 1; k >= 0; k--) {
+      // x_k is final; broadcast it and eliminate it from all rows i < k
+      double xk = 0.0;
+#pragma unroll
+      for (int mm = 0; mm < kMaxPerLane; mm++)
+        if ((k >> 5) == mm) xk = __shfl_sync(0xffffffffu, x[mm], k & 31);
+#pragma unroll
+      for (int mm = 0; mm < kMaxPerLane; mm++) {
+        const int i = tid + 32 * mm;
+        if (mm < nper && i < k) x[mm] -= A[(size_t)k * (k + 1) / 2 + i] * invd[mm] * xk;
+      }
+    }
+#pragma unroll
+    for (int mm = 0; mm < kMaxPerLane; mm++) {
+      const int i = tid + 32 * mm;
+      if (i < n) y[i] = x[mm];
+    }
+  }
+  __syncthreads();
+  bool bad = false;
+  for (int i = tid; i < n; i += kSolveThreads) {
+    dX[i] = y[i];
+    if (!isfinite(y[i])) bad = true;
+  }
+  if (__syncthreads_or(bad)) {
+    if (tid == 0) atomicCAS(status, 0, itr + 1);
+    return;
+  }
+  // pose retraction  T <- Exp(dX) T   (:160-188)
+  for (int p = tid; p < nfree; p += kSolveThreads) {
+    float xi[6], P[7];
+#pragma unroll
+    for (int c = 0; c < 6; c++) xi[c] = (float)y[6 * p + c];
+    float* dst = poses + (size_t)(t0 + p) * 7;
+#pragma unroll
+    for (int c = 0; c < 7; c++) P[c] = dst[c];
+    retract_pose(xi, P);
+#pragma unroll
+    for (int c = 0; c < 7; c++) dst[c] = P[c];
+  }
+}
+
 // ---- accumulate kernel ----------------------------------------------------------------------
 // smem: X[R][LD] doubles, coef[R] doubles, zj[R] doubles (Jz per row), batch bookkeeping
 template <int EPT>
@@ -219,7 +372,7 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
     const int32_t* __restrict__ perm, const int32_t* __restrict__ gstart, const int64_t* __restrict__ gkey,
     const int32_t* __restrict__ ngroups_p,
     double* __restrict__ Qg, double* __restrict__ Ug, double* __restrict__ Ekg,
-    double* __restrict__ partials, const double* __restrict__ dX,
+    double* __restrict__ partials, double* dX, int32_t* __restrict__ ticket,
     int32_t* __restrict__ status, int E, int PP, int centre, int t0, int nfree, int n_poses,
     int EB, int GB, int apply_update, int do_accumulate, int itr) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -385,157 +538,19 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
     int idx = tid + q * kAccThreads;
     if (idx < nent) partials[(size_t)blockIdx.x * nent + idx] = acc[q];
   }
-  (void)n_poses; (void)itr; (void)E;
-}
-
-// ---- solve kernel ---------------------------------------------------------------------------
-// smem: A packed lower-triangular n(n+1)/2 doubles (A(i,j) at i(i+1)/2 + j, j<=i), y[n+1], rinv[n] doubles.
-// Square-root-free elimination of the augmented system [S | y] with ONE barrier per pivot:
-//   step k:  r = 1/A_kk ;  A_ij -= A_ik A_jk r  (i>=j>k) ;  y_i -= A_ik y_k r  (i>k)
-// reads touch column k only, writes touch columns > k only, so no second barrier is needed.
-// Afterwards A_ik (i>k) = L_ik d_k and y = L^-1 y; warp 0 finishes x = L^-T D^-1 y with shuffles.
-// S positive definite  <=>  every pivot d_k = A_kk > 0 (same acceptance test as Cholesky).
-__global__ void __launch_bounds__(kSolveThreads, 1) ba_solve_kernel(
-    float* __restrict__ poses, const double* __restrict__ partials, double* __restrict__ dX,
-    int32_t* __restrict__ status, int nparts, int t0, int nfree, int itr) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int n = 6 * nfree;
-  const int LD = n + 1;
-  const int nent = (n + 1) * (n + 2) / 2;
-  double* A = reinterpret_cast<double*>(smem_raw);
-  double* y = A + (size_t)n * (n + 1) / 2;
-  __shared__ int s_fail;
-  const int tid = threadIdx.x;
-  if (*status != 0) return;
-  if (n == 0) return;
-  if (tid == 0) s_fail = 0;
-
-  // fixed-order reduction of the per-CTA partials; entry (a,b), a<=b of the (n+1)x(n+1) augmented matrix
-  for (int idx = tid; idx < nent; idx += kSolveThreads) {
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int p = 0;
-    for (; p + 4 <= nparts; p += 4) {
-      s0 += partials[(size_t)(p + 0) * nent + idx];
-      s1 += partials[(size_t)(p + 1) * nent + idx];
-      s2 += partials[(size_t)(p + 2) * nent + idx];
-      s3 += partials[(size_t)(p + 3) * nent + idx];
-    }
-    for (; p < nparts; p++) s0 += partials[(size_t)p * nent + idx];
-    double s = (s0 + s1) + (s2 + s3);
-    int a, b;
-    tri_decode(idx, LD, a, b);
-    if (b == n) {
-      if (a < n) y[a] = s;                                // y = v - E Q u
-    } else {
-      if (a == b) s += 1e-4 * s + 1.0;                    // S += I o (1e-4 S + 1)   (:517-518)
-      A[(size_t)b * (b + 1) / 2 + a] = s;                 // symmetric: store as lower (b,a)
-    }
-  }
-  __syncthreads();
-
-  // Fixed ownership: thread t owns lower-triangular entries e = t, t+1024, ... of the augmented matrix
-  // (row gi, column gj <= gi; the extra last row gi == n is y^T).  Entry (gi,gj) takes part in pivot step
-  // k while gj > k.  The reciprocal of the next pivot is produced by the one thread that finalises it, so the
-  // 1/d division (a long fp64 sequence) is executed once per step instead of by every warp.
-  constexpr int kEnt = ((kMaxN6 + 1) * (kMaxN6 + 2) / 2 + kSolveThreads - 1) / kSolveThreads;
-  int ent[kEnt];                                          // (gi << 16) | gj, or -1
-  const int naug = (n + 1) * (n + 2) / 2 - 1;            // lower triangle of the (n+1)x(n+1) matrix without (n,n)
-#pragma unroll
-  for (int q = 0; q < kEnt; q++) {
-    const int e = tid + q * kSolveThreads;
-    int gi = 0, gj = 0;
-    if (e < naug) {
-      gi = (int)floorf((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-      while (gi * (gi + 1) / 2 > e) gi--;
-      while ((gi + 1) * (gi + 2) / 2 <= e) gi++;
-      gj = e - gi * (gi + 1) / 2;
-    }
-    ent[q] = (e < naug) ? ((gi << 16) | gj) : -1;
-  }
-  double* rinv = y + n + 1;                               // [n] reciprocals of the pivots
-  if (tid == 0) {
-    const double a00 = A[0];
-    if (!(a00 > 0.0) || !isfinite(a00)) s_fail = 1;
-    rinv[0] = 1.0 / a00;
-  }
-  __syncthreads();
-  for (int k = 0; k < n; k++) {
-    if (s_fail) break;                                    // uniform (written before the last barrier)
-    const double r = rinv[k];
-    const double yk = y[k];
-#pragma unroll
-    for (int q = 0; q < kEnt; q++) {
-      if (ent[q] < 0) continue;
-      const int gi = ent[q] >> 16, gj = ent[q] & 0xffff;
-      if (gj <= k) continue;
-      if (gi < n) {
-        const size_t at = (size_t)gi * (gi + 1) / 2;
-        const double v = A[at + gj] - A[at + k] * A[(size_t)gj * (gj + 1) / 2 + k] * r;
-        A[at + gj] = v;
-        if (gi == k + 1 && gj == k + 1) {                 // the next pivot is final now
-          if (!(v > 0.0) || !isfinite(v)) s_fail = 1;
-          rinv[k + 1] = 1.0 / v;
-        }
-      } else {
-        y[gj] -= A[(size_t)gj * (gj + 1) / 2 + k] * yk * r;   // last row of the augmented matrix: y
-      }
-    }
+  (void)n_poses; (void)E;
+  // ---- the last CTA to finish reduces the partials (fixed order => deterministic), solves the reduced
+  //      system and retracts the poses: one launch per Gauss-Newton iteration
+  if (nfree > 0) {
+    __threadfence();
     __syncthreads();
-  }
-  __syncthreads();
-  if (s_fail) {
-    if (tid == 0) atomicCAS(status, 0, itr + 1);
-    return;
-  }
-  // back substitution by warp 0: x_k = y_k/d_k - sum_{i>k} (A_ik/d_k) x_i ; lane l owns x[l + 32 m]
-  if (tid < 32) {
-    constexpr int kMaxPerLane = (kMaxN6 + 31) / 32;
-    double x[kMaxPerLane], invd[kMaxPerLane];
-#pragma unroll
-    for (int mm = 0; mm < kMaxPerLane; mm++) {
-      const int i = tid + 32 * mm;
-      invd[mm] = (i < n) ? 1.0 / A[(size_t)i * (i + 1) / 2 + i] : 0.0;
-      x[mm] = (i < n) ? y[i] * invd[mm] : 0.0;                           // D^-1 y
+    if (tid == 0) s_batch[0] = atomicAdd(ticket, 1);
+    __syncthreads();
+    if (s_batch[0] == (int)gridDim.x - 1) {
+      if (tid == 0) *ticket = 0;                 // armed for the next launch
+      __threadfence();
+      ba_solve_device(smem_raw, poses_rw, partials, dX, status, (int)gridDim.x, t0, nfree, itr);
     }
-    for (int k = n - 1; k >= 0; k--) {
-      // x_k is final; broadcast it and eliminate it from all rows i < k
-      double xk = 0.0;
-#pragma unroll
-      for (int mm = 0; mm < kMaxPerLane; mm++)
-        if ((k >> 5) == mm) xk = __shfl_sync(0xffffffffu, x[mm], k & 31);
-#pragma unroll
-      for (int mm = 0; mm < kMaxPerLane; mm++) {
-        const int i = tid + 32 * mm;
-        if (i < k) x[mm] -= A[(size_t)k * (k + 1) / 2 + i] * invd[mm] * xk;
-      }
-    }
-#pragma unroll
-    for (int mm = 0; mm < kMaxPerLane; mm++) {
-      const int i = tid + 32 * mm;
-      if (i < n) y[i] = x[mm];
-    }
-  }
-  __syncthreads();
-  bool bad = false;
-  for (int i = tid; i < n; i += kSolveThreads) {
-    dX[i] = y[i];
-    if (!isfinite(y[i])) bad = true;
-  }
-  if (__syncthreads_or(bad)) {
-    if (tid == 0) atomicCAS(status, 0, itr + 1);
-    return;
-  }
-  // pose retraction  T <- Exp(dX) T   (:160-188)
-  for (int p = tid; p < nfree; p += kSolveThreads) {
-    float xi[6], P[7];
-#pragma unroll
-    for (int c = 0; c < 6; c++) xi[c] = (float)y[6 * p + c];
-    float* dst = poses + (size_t)(t0 + p) * 7;
-#pragma unroll
-    for (int c = 0; c < 7; c++) P[c] = dst[c];
-    retract_pose(xi, P);
-#pragma unroll
-    for (int c = 0; c < 7; c++) dst[c] = P[c];
   }
 }
 
@@ -650,7 +665,7 @@ static int launch_accumulate(const BaLayout& L, char* w, float* poses, float* pa
   ba_accumulate_kernel<EPT><<<L.grid, kAccThreads, smem, s>>>(
       poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, perm_p, gstart_p, gkey_p, ngroups_p,
       (double*)(w + L.Q), (double*)(w + L.U), (double*)(w + L.Ek), (double*)(w + L.partials),
-      (const double*)(w + L.dX), status, E, PP, centre, t0, nfree, n_poses, EB, GB, apply_update, do_accumulate, itr);
+      (double*)(w + L.dX), (int32_t*)(w + L.ticket), status, E, PP, centre, t0, nfree, n_poses, EB, GB, apply_update, do_accumulate, itr);
   DEVO_LAUNCH_CHECK("ba_accumulate");
   return DEVO_OK;
 }
@@ -703,7 +718,7 @@ static int ba_forward_impl(float* poses, float* patches, const float* intrinsics
   int GB = rows_cap - 2 * EB;
   if (GB > EB) GB = EB;
   DEVO_REQUIRE(EB >= 8 && GB >= 1, DEVO_ECAPACITY, "ba_forward: system too large for shared memory");
-  const size_t smem_acc = (size_t)(2 * EB + GB) * (LD + 2) * 8;
+  size_t smem_acc = (size_t)(2 * EB + GB) * (LD + 2) * 8;
   const int ept = (L.nent + kAccThreads - 1) / kAccThreads;
 
 #define ACC(EPT_, APPLY, DOACC, ITR)                                                                         \
@@ -721,18 +736,10 @@ static int ba_forward_impl(float* poses, float* patches, const float* intrinsics
 
   DEVO_REQUIRE(ept <= 24, DEVO_ECAPACITY, "ba_forward: system too large (%d entries)", L.nent);
   const size_t smem_solve = ((size_t)n6 * (n6 + 1) / 2 + 2 * n6 + 4) * 8;
-  static size_t solve_configured = 0;
-  if (smem_solve > solve_configured) {
-    DEVO_CUDA(cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
-    solve_configured = smem_solve;
-  }
+  DEVO_REQUIRE(smem_solve <= smem_acc, DEVO_ECAPACITY, "ba_forward: solver does not fit the accumulate CTA's shared memory");
+  DEVO_CUDA(cudaMemsetAsync(w + L.ticket, 0, 16, s));
   for (int itr = 0; itr < iterations; itr++) {
-    ACC_DISPATCH(itr > 0 ? 1 : 0, 1, itr);
-    if (nfree > 0) {
-      ba_solve_kernel<<<1, kSolveThreads, smem_solve, s>>>(poses, (const double*)(w + L.partials),
-                                                           (double*)(w + L.dX), status, L.grid, t0, nfree, itr);
-      DEVO_LAUNCH_CHECK("ba_solve");
-    }
+    ACC_DISPATCH(itr > 0 ? 1 : 0, 1, itr);   // accumulate + (last CTA) solve + retraction
   }
   ACC_DISPATCH(1, 0, iterations);   // final depth update only
 #undef ACC

@@ -31,11 +31,35 @@
 
 namespace {
 
-constexpr int kBox = 11;                    // box edge in pixels: 8 + floor-span 3
+#ifndef DEVO_CORR_BOX
+#define DEVO_CORR_BOX 11
+#endif
+#ifndef DEVO_CORR_STAGES
+#define DEVO_CORR_STAGES 4
+#endif
+constexpr int kBox = DEVO_CORR_BOX;          // box edge in pixels: 8 + floor-span 3
 constexpr int kBoxPix = kBox * kBox;        // 121 rows used of the M=128 tile
-constexpr int kStages = 4;
-constexpr int kEpiGroups = 2;               // one epilogue group (4 warps) per TMEM accumulator stage
-constexpr int kThreads = 32 * (2 + 4 * kEpiGroups);   // warp0 TMA, warp1 MMA, 2 x 4 epilogue warps
+constexpr int kStages = DEVO_CORR_STAGES;
+#ifndef DEVO_CORR_PRODUCERS
+#define DEVO_CORR_PRODUCERS 3
+#endif
+#ifndef DEVO_CORR_EPI_GROUPS
+#define DEVO_CORR_EPI_GROUPS 3
+#endif
+constexpr int kProducers = DEVO_CORR_PRODUCERS;   // TMA producer warps (warps 0..kProducers-1), kProducers <= 3
+#ifndef DEVO_CORR_MMA_WARPS
+#define DEVO_CORR_MMA_WARPS 1
+#endif
+#ifndef DEVO_CORR_MMA_INTERLEAVE
+#define DEVO_CORR_MMA_INTERLEAVE 2
+#endif
+constexpr int kMmaWarps = DEVO_CORR_MMA_WARPS;     // MMA-issuing warps (items alternate between them)
+constexpr int kMmaInterleave = DEVO_CORR_MMA_INTERLEAVE;   // items (accumulators) one MMA warp issues round-robin
+constexpr int kMmaWarp = kProducers;               // first MMA warp (owns the TMEM allocation)
+constexpr int kFirstEpiWarp = (kProducers + kMmaWarps <= 4) ? 4 : 8;   // (warp % 4) is the TMEM lane quarter
+constexpr int kEpiGroups = DEVO_CORR_EPI_GROUPS;   // one epilogue group (4 warps) per TMEM accumulator stage
+constexpr int kTmemCols = (kEpiGroups * 16 <= 32) ? 32 : 64;
+constexpr int kThreads = 32 * (kFirstEpiWarp + 4 * kEpiGroups);
 constexpr int kATileBytes = 128 * 128;      // 128 rows x 64 ch x 2 B   (one K half)
 constexpr int kBTileBytes = 16 * 128;       // 16 rows  x 64 ch x 2 B
 constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;   // 36 KB
@@ -44,6 +68,10 @@ constexpr int kRadius = 3, kPP = 9, kOut = 7;
 constexpr int kCoordBatch = 8;              // edges per coordinate batch (8 x 72 B = 576 B, 16-byte multiple)
 constexpr int kCoordRing = 4;               // batches in flight in shared memory
 constexpr int kCoordFloats = kCoordBatch * 2 * kPP;
+constexpr int kSlotBytes = kCoordFloats * 4 + 2 * kCoordBatch * 8;   // coords + ii + jj of one batch (704 B)
+constexpr int kRecRing = 16;                // per-item blend records (producer -> epilogue); must be >= kProducers + kStages + kEpiGroups
+constexpr int kRecWords = 48;               // 9 pixels x {woff, dx, dy, fx, fy} = 45 words, padded
+static_assert(kRecRing >= kProducers + kStages + kEpiGroups, "blend-record ring too small");
 
 struct FastParams {
   int E, L, items, khalves;                 // khalves = C / 64
@@ -102,6 +130,51 @@ __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// Variants for fully converged warps: every lane executes the call with identical operands and ONE elected
+// lane issues the instruction.  Keeping the warp converged lets the compiler feed the uniform datapath
+// (UTCHMMA / UTMALDG / UTCBAR take uniform registers) directly; issuing from inside an `if (lane == 0)` region
+// costs an ELECT + R2UR + BRA.U.ANY loop (~19 instructions) per instruction instead.
+__device__ __forceinline__ void tc_mma_f16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar_addr) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_elect(uint32_t bar_addr, uint32_t bytes) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+      "}" ::"r"(bar_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar_addr, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t"
+      "}" ::"r"(dst), "l"((uint64_t)map), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar_addr, int c0, int c1, int c2) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t"
+      "}" ::"r"(dst), "l"((uint64_t)map), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -156,14 +229,9 @@ __device__ __forceinline__ Geo make_geo(const float* cs, float scale, float inv_
   }
   g.fx = safe_floor_int(x, g.dx);
   g.fy = safe_floor_int(y, g.dy);
-  int mx = lane < kPP ? g.fx : 0x7fffffff, my = lane < kPP ? g.fy : 0x7fffffff;
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) {       // pixels live in lanes 0..15
-    mx = min(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    my = min(my, __shfl_xor_sync(0xffffffffu, my, o));
-  }
-  g.x0 = __shfl_sync(0xffffffffu, mx, 0) - kRadius;
-  g.y0 = __shfl_sync(0xffffffffu, my, 0) - kRadius;
+  const int mx = lane < kPP ? g.fx : 0x7fffffff, my = lane < kPP ? g.fy : 0x7fffffff;
+  g.x0 = __reduce_min_sync(0xffffffffu, mx) - kRadius;     // REDUX: one instruction per warp-wide minimum
+  g.y0 = __reduce_min_sync(0xffffffffu, my) - kRadius;
   return g;
 }
 
@@ -178,16 +246,39 @@ __device__ float direct_dot(const T* __restrict__ g, const T* __restrict__ lvl, 
 
 // per-role view of the coordinate ring: batch b holds edges [eb0 + 8b, eb0 + 8b + 8)
 struct CoordView {
-  const float* ring;
+  const unsigned char* ring;
   uint64_t* cfull;
   int eb0, cur;
+  const unsigned char* slot;
+  int off;
+  // select edge e: waits (once per warp and batch) until its batch has landed in shared memory
   __device__ __forceinline__ const float* edge(int e) {
     const int b = (e - eb0) >> 3;
-    if (b != cur) {                        // first use of this batch by this warp: wait until it has landed
+    if (b != cur) {
       cur = b;
       mbar_wait(&cfull[b & (kCoordRing - 1)], (uint32_t)(b / kCoordRing) & 1u);
     }
-    return ring + (b & (kCoordRing - 1)) * kCoordFloats + (e - eb0 - 8 * b) * 2 * kPP;
+    slot = ring + (b & (kCoordRing - 1)) * kSlotBytes;
+    off = e - eb0 - 8 * b;
+    return reinterpret_cast<const float*>(slot) + off * 2 * kPP;
+  }
+  __device__ __forceinline__ int patch() const { return (int)reinterpret_cast<const long long*>(slot + kCoordFloats * 4)[off]; }
+  __device__ __forceinline__ int frame() const { return (int)reinterpret_cast<const long long*>(slot + kCoordFloats * 4 + kCoordBatch * 8)[off]; }
+};
+
+// per-role item cursor: (e, l) advanced by `step` items without divisions
+struct ItemCursor {
+  int it, e, l;
+  __device__ __forceinline__ void init(int first, int L, int offset) {
+    it = offset;
+    const int item = first + offset;
+    e = item / L;
+    l = item - e * L;
+  }
+  __device__ __forceinline__ void advance(int step, int L) {
+    it += step;
+    l += step;
+    while (l >= L) { l -= L; e++; }
   }
 };
 
@@ -198,129 +289,204 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
     const __grid_constant__ CUtensorMap tm_l3, const FastParams prm) {
   extern __shared__ unsigned char smem_dyn[];
   // 1024-byte aligned carve-up (SWIZZLE_128B atoms repeat every 1024 B)
-  unsigned char* base = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+  // (offset arithmetic on the shared pointer itself: a round trip through an integer would turn every access
+  //  below into a generic LD/ST instead of LDS/STS)
+  unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* tiles = base;                                           // kStages * kStageBytes
   float* Vs = reinterpret_cast<float*>(base + kStages * kStageBytes);    // kEpiGroups * 2 * kVsFloats
-  float* cring = Vs + kEpiGroups * 2 * kVsFloats;                        // kCoordRing * kCoordFloats (16 B aligned)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(cring + kCoordRing * kCoordFloats);
-  uint64_t* full = bars;                 // [kStages]
-  uint64_t* empty = bars + kStages;      // [kStages]
-  uint64_t* tfull = bars + 2 * kStages;  // [2]
-  uint64_t* tempty = tfull + 2;          // [2]
-  uint64_t* cfull = tempty + 2;          // [kCoordRing]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cfull + kCoordRing);
+  unsigned char* cring = reinterpret_cast<unsigned char*>(Vs + kEpiGroups * 2 * kVsFloats);   // kCoordRing slots, 16 B aligned
+  uint32_t* recs = reinterpret_cast<uint32_t*>(cring + kCoordRing * kSlotBytes);          // kRecRing * kRecWords
+  uint64_t* bars = reinterpret_cast<uint64_t*>(recs + kRecRing * kRecWords);
+  uint64_t* full = bars;                          // [kStages]
+  uint64_t* empty = full + kStages;               // [kStages]
+  uint64_t* tfull = empty + kStages;              // [kEpiGroups]
+  uint64_t* tempty = tfull + kEpiGroups;          // [kEpiGroups]
+  uint64_t* cfull = tempty + kEpiGroups;          // [kCoordRing]
+  uint64_t* rfull = cfull + kCoordRing;           // [kRecRing]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + kRecRing);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
+  const int lane = threadIdx.x & 31;
   const int per = (prm.items + gridDim.x - 1) / gridDim.x;
   const int first = blockIdx.x * per;
   const int last = min(prm.items, first + per);
+  const int nitems = max(last - first, 0);
   const int khalves = prm.khalves;
   const int L = prm.L;
   const int eb0 = (first / L) & ~1;      // even edge => 16-byte aligned source for the bulk copies
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    for (int a = 0; a < kEpiGroups; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
     for (int c = 0; c < kCoordRing; c++) mbar_init(&cfull[c], 1);
+    for (int r = 0; r < kRecRing; r++) mbar_init(&rfull[r], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(32) : "memory");
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  CoordView cv{cring, cfull, eb0, -1};
+  CoordView cv{cring, cfull, eb0, -1, cring, 0};
 
-  if (warp == 0) {
-    // =============================== TMA producer ===============================
-    if (lane == 0) {
+  if (warp < kProducers) {
+    // =============================== TMA producers (items warp, warp+P, ...) ===============================
+    // A single warp needs ~1700 cycles of dependent instructions per item (measured), so the item stream is
+    // split over kProducers warps; stage and phase follow from the item index alone.
+    if (warp == 0 && lane == 0) {
       prefetch_tensormap(&tm_g); prefetch_tensormap(&tm_l0);
       if (L > 1) prefetch_tensormap(&tm_l1);
     }
-    const int nb = (first < last) ? (((last - 1) / L - eb0) >> 3) + 1 : 0;
-    // stage the coordinates of batch b: TMA bulk copy for a full batch, plain loads for the ragged tail
+    const int nb = (nitems > 0) ? (((last - 1) / L - eb0) >> 3) + 1 : 0;
+    // warp 0 stages the coordinate/index batches: TMA bulk copies for a full batch, plain loads for the ragged tail
     auto issue_coords = [&](int b) {
       const int eb = eb0 + kCoordBatch * b;
       const int n = min(kCoordBatch, prm.E - eb);
-      float* dst = cring + (b & (kCoordRing - 1)) * kCoordFloats;
+      unsigned char* dst = cring + (b & (kCoordRing - 1)) * kSlotBytes;
       const float* src = prm.coords + (size_t)eb * 2 * kPP;
       uint64_t* bar = &cfull[b & (kCoordRing - 1)];
-      if (n == kCoordBatch && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+      const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(prm.ii + eb) |
+                             reinterpret_cast<uintptr_t>(prm.jj + eb)) & 15) == 0;
+      if (n == kCoordBatch && aligned) {
         if (lane == 0) {
-          mbar_arrive_expect_tx(bar, kCoordFloats * 4);
+          mbar_arrive_expect_tx(bar, kSlotBytes);
           bulk_load_1d(dst, src, kCoordFloats * 4, bar);
+          bulk_load_1d(dst + kCoordFloats * 4, prm.ii + eb, kCoordBatch * 8, bar);
+          bulk_load_1d(dst + kCoordFloats * 4 + kCoordBatch * 8, prm.jj + eb, kCoordBatch * 8, bar);
         }
       } else {
-        for (int q = lane; q < n * 2 * kPP; q += 32) dst[q] = src[q];
+        float* dc = reinterpret_cast<float*>(dst);
+        long long* di = reinterpret_cast<long long*>(dst + kCoordFloats * 4);
+        for (int q = lane; q < n * 2 * kPP; q += 32) dc[q] = src[q];
+        if (lane < n) { di[lane] = prm.ii[eb + lane]; di[kCoordBatch + lane] = prm.jj[eb + lane]; }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar);
       }
       __syncwarp();
     };
-    if (nb > 0) issue_coords(0);
-    if (nb > 1) issue_coords(1);
-    int issued = 2;
-    uint32_t stage = 0, phase = 0;
+    int issued = 0;
+    if (warp == 0) {
+      for (; issued < min(nb, 2); issued++) issue_coords(issued);
+    }
     const uint32_t bytes = (uint32_t)khalves * (kBoxPix * 128 + kPP * 128);
-    for (int item = first; item < last; item++) {
-      const int e = item / L, l = item - e * L;
-      const int b = (e - eb0) >> 3;
-      if (b + 2 > issued && issued < nb) { issue_coords(issued); issued++; }   // keep one batch ahead
-      Geo g = make_geo(cv.edge(e), prm.scale[l], prm.inv_scale[l], lane);
-      if (lane == 0) {
-        const CUtensorMap* tm = (l == 0) ? &tm_l0 : (l == 1) ? &tm_l1 : (l == 2) ? &tm_l2 : &tm_l3;
-        const int frame = (int)prm.jj[e];
-        const int patch = (int)prm.ii[e];
-        unsigned char* st = tiles + (size_t)stage * kStageBytes;
+    ItemCursor c;
+    c.init(first, L, warp);
+    uint32_t stage = warp % kStages, phase = (warp / kStages) & 1;
+    for (; c.it < nitems; c.advance(kProducers, L)) {
+      if (warp == 0) {
+        const int b = (c.e - eb0) >> 3;
+        if (b + 2 > issued && issued < nb) { issue_coords(issued); issued++; }   // stay one batch ahead
+      }
+      Geo g = make_geo(cv.edge(c.e), prm.scale[c.l], prm.inv_scale[c.l], lane);
+      {
+        // blend record of this item for the epilogue: lane p owns pixel p.  Slot reuse needs no "empty" barrier:
+        // a producer writing item R has passed empty[] for item R-kProducers, so the MMA warp finished item
+        // R-kProducers-kStages and the epilogue has read every record up to R-kProducers-kStages-kEpiGroups.
+        uint32_t* rec = recs + (c.it & (kRecRing - 1)) * kRecWords;
+        if (lane < kPP) {
+          const int ox = g.fx - kRadius - g.x0, oy = g.fy - kRadius - g.y0;   // window origin inside the box (>= 0)
+          rec[lane] = (uint32_t)((ox + 8 <= kBox && oy + 8 <= kBox) ? oy * kBox + ox : -1);
+          rec[kPP + lane] = __float_as_uint(g.dx);
+          rec[2 * kPP + lane] = __float_as_uint(g.dy);
+          rec[3 * kPP + lane] = (uint32_t)g.fx;
+          rec[4 * kPP + lane] = (uint32_t)g.fy;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&rfull[c.it & (kRecRing - 1)]);
+        // whole warp converged, one elected lane issues (see tc_mma_f16_elect)
+        const CUtensorMap* tm = (c.l == 0) ? &tm_l0 : (c.l == 1) ? &tm_l1 : (c.l == 2) ? &tm_l2 : &tm_l3;
+        const int frame = __shfl_sync(0xffffffffu, cv.frame(), 0);
+        const int patch = __shfl_sync(0xffffffffu, cv.patch(), 0);
+        const uint32_t st = smem_u32(tiles) + stage * kStageBytes;
+        const uint32_t fb = smem_u32(&full[stage]);
         mbar_wait(&empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full[stage], bytes);
-        for (int kh = 0; kh < khalves; kh++) {
-          tma_load_4d(st + kh * kATileBytes, tm, &full[stage], kh * 64, g.x0, g.y0, frame);
-          tma_load_3d(st + 2 * kATileBytes + kh * kBTileBytes, &tm_g, &full[stage], kh * 64, 0, patch);
+        mbar_arrive_expect_tx_elect(fb, bytes);
+        tma_load_4d_elect(st, tm, fb, 0, g.x0, g.y0, frame);
+        tma_load_3d_elect(st + 2 * kATileBytes, &tm_g, fb, 0, 0, patch);
+        if (khalves == 2) {
+          tma_load_4d_elect(st + kATileBytes, tm, fb, 64, g.x0, g.y0, frame);
+          tma_load_3d_elect(st + 2 * kATileBytes + kBTileBytes, &tm_g, fb, 64, 0, patch);
         }
       }
-      __syncwarp();
-      if (++stage == kStages) { stage = 0; phase ^= 1; }
+      stage += kProducers;
+      while (stage >= kStages) { stage -= kStages; phase ^= 1; }
     }
-  } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
+  } else if (warp < kProducers + kMmaWarps) {
+    // =============================== MMA issuers (items alternate between the kMmaWarps warps) ===========
     // instruction descriptor: D=f32, A=B=f16|bf16, K-major both, N=16, M=128
     const uint32_t fmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
-    uint32_t stage = 0, phase = 0, acc = 0, aphase = 0;
-    for (int item = first; item < last; item++) {
-      if (lane == 0) {
-        mbar_wait(&tempty[acc], aphase ^ 1);
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(tiles + (size_t)stage * kStageBytes);
-        const uint32_t sb = sa + 2 * kATileBytes;
-        uint32_t accumulate = 0;
-        for (int kh = 0; kh < khalves; kh++) {
+    {
+      // smem matrix descriptors only differ in their 14-bit (address >> 4) field
+      const uint64_t ad0 = umma_desc_sw128(smem_u32(tiles));
+      const uint64_t bd0 = umma_desc_sw128(smem_u32(tiles) + 2 * kATileBytes);
+      const uint32_t bar_base = smem_u32(full);
+      // MMAs that accumulate into the same TMEM tile execute back to back, so kMmaInterleave items with
+      // different accumulators are issued round-robin, K-slice by K-slice.
+      const int m = warp - kProducers;
+      uint32_t stage = (m * kMmaInterleave) % kStages, phase = ((m * kMmaInterleave) / kStages) & 1;
+      uint32_t acc = (m * kMmaInterleave) % kEpiGroups, aphase = ((m * kMmaInterleave) / kEpiGroups) & 1;
+      for (int it = m * kMmaInterleave; it < nitems; it += kMmaWarps * kMmaInterleave) {
+        const int n = min(kMmaInterleave, nitems - it);
+        uint64_t ad[kMmaInterleave], bd[kMmaInterleave];
+        uint32_t d[kMmaInterleave], bar_e[kMmaInterleave], bar_t[kMmaInterleave];
+        {
+          uint32_t st = stage, ph = phase, ac = acc, aph = aphase;
 #pragma unroll
-          for (int k4 = 0; k4 < 4; k4++) {
-            const uint64_t ad = umma_desc_sw128(sa + kh * kATileBytes + k4 * 32);
-            const uint64_t bd = umma_desc_sw128(sb + kh * kBTileBytes + k4 * 32);
-            tc_mma_f16(tmem_base + acc * 16, ad, bd, idesc, accumulate);
-            accumulate = 1;
+          for (int g = 0; g < kMmaInterleave; g++) {
+            if (g < n) {
+              mbar_wait(&tempty[ac], aph ^ 1);
+              mbar_wait(&full[st], ph);
+            }
+            ad[g] = ad0 + (uint64_t)(st * (kStageBytes >> 4));
+            bd[g] = bd0 + (uint64_t)(st * (kStageBytes >> 4));
+            d[g] = tmem_base + ac * 16;
+            bar_e[g] = bar_base + (kStages + st) * 8;                 // &empty[st]
+            bar_t[g] = bar_base + (2 * kStages + ac) * 8;             // &tfull[ac]
+            if (++st == kStages) { st = 0; ph ^= 1; }
+            if (++ac == kEpiGroups) { ac = 0; aph ^= 1; }
           }
         }
-        tc_commit(&empty[stage]);    // smem stage may be refilled once these MMAs retire
-        tc_commit(&tfull[acc]);      // accumulator ready
+        tc_fence_after();
+#pragma unroll
+        for (int k4 = 0; k4 < 4; k4++) {
+#pragma unroll
+          for (int g = 0; g < kMmaInterleave; g++)
+            if (g < n) tc_mma_f16_elect(d[g], ad[g] + 2 * k4, bd[g] + 2 * k4, idesc, k4 ? 1u : 0u);   // +32 B per K=16 slice
+        }
+        if (khalves == 2) {
+#pragma unroll
+          for (int k4 = 0; k4 < 4; k4++) {
+#pragma unroll
+            for (int g = 0; g < kMmaInterleave; g++)
+              if (g < n) tc_mma_f16_elect(d[g], ad[g] + (kATileBytes >> 4) + 2 * k4, bd[g] + (kBTileBytes >> 4) + 2 * k4, idesc, 1u);
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < kMmaInterleave; g++) {
+          if (g < n) {
+            tc_commit_elect(bar_e[g]);     // smem stage may be refilled once the MMAs issued so far retire
+            tc_commit_elect(bar_t[g]);     // accumulator ready
+          }
+        }
+        for (int q = 0; q < kMmaWarps * kMmaInterleave; q++) {
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++acc == kEpiGroups) { acc = 0; aphase ^= 1; }
+        }
       }
-      __syncwarp();
-      if (++stage == kStages) { stage = 0; phase ^= 1; }
-      if (++acc == 2) { acc = 0; aphase ^= 1; }
     }
+    __syncwarp();
+  } else if (warp < kFirstEpiWarp) {
+    // idle filler warps (keep the epilogue warps aligned to TMEM lane quarters)
   } else {
     // =============================== epilogue: group g owns TMEM accumulator stage g ===============
-    const int grp = (warp - 2) >> 2;              // 0 or 1
-    const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
+    const int grp = (warp - kFirstEpiWarp) >> 2;  // 0 .. kEpiGroups-1
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may read (kFirstEpiWarp % 4 == 0)
     const int row = quarter * 32 + lane;          // box pixel handled by this thread
-    const int et = ((warp - 2) & 3) * 32 + lane;  // 0..127 within the group
+    const int et = quarter * 32 + lane;           // 0..127 within the group
     T* out = reinterpret_cast<T*>(prm.out);
     float* vbase = Vs + grp * 2 * kVsFloats;
     // output ownership, fixed for the whole kernel: thread -> patch pixel p and window offsets
@@ -339,17 +505,16 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
     }
     uint32_t aphase = 0;
     int buf = 0;
-    for (int item = first + grp; item < last; item += kEpiGroups) {
-      const int e = item / L, l = item - e * L;
-      Geo g = make_geo(cv.edge(e), prm.scale[l], prm.inv_scale[l], lane);
-      // per-pixel blend record, owned by lane p: offset of the window origin inside the box (or -1), fractions
-      const int ox = g.fx - kRadius - g.x0, oy = g.fy - kRadius - g.y0;
-      const int woff = (ox + 8 <= kBox && oy + 8 <= kBox) ? oy * kBox + ox : -1;
-      const int pw = __shfl_sync(0xffffffffu, woff, p);
-      const float dx = __shfl_sync(0xffffffffu, g.dx, p), dy = __shfl_sync(0xffffffffu, g.dy, p);
-      const bool any_unfit = __any_sync(0xffffffffu, lane < kPP && woff < 0);
-      int pfx = 0, pfy = 0;
-      if (any_unfit) { pfx = __shfl_sync(0xffffffffu, g.fx, p); pfy = __shfl_sync(0xffffffffu, g.fy, p); }
+    ItemCursor c;
+    c.init(first, L, grp);
+    for (; c.it < nitems; c.advance(kEpiGroups, L)) {
+      const int e = c.e, l = c.l;
+      // blend record written by the producer warp of this item (direct release/acquire through rfull)
+      mbar_wait(&rfull[c.it & (kRecRing - 1)], (uint32_t)(c.it / kRecRing) & 1u);
+      const uint32_t* rec = recs + (c.it & (kRecRing - 1)) * kRecWords;
+      const int pw = (int)rec[p];
+      const float dx = __uint_as_float(rec[kPP + p]), dy = __uint_as_float(rec[2 * kPP + p]);
+      const int pfx = (int)rec[3 * kPP + p], pfy = (int)rec[4 * kPP + p];
       const float w00 = (1.f - dx) * (1.f - dy), w01 = dx * (1.f - dy), w10 = (1.f - dx) * dy, w11 = dx * dy;
 
       mbar_wait(&tfull[grp], aphase);
@@ -368,8 +533,7 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
       float* vs = vbase + buf * kVsFloats;
 #pragma unroll
       for (int q = 0; q < kPP; q++) vs[q * 128 + row] = __uint_as_float(v[q]);
-      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // the 4 warps of this group only
-      else          asm volatile("bar.sync 2, 128;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");   // the 4 warps of this group only
 
       T* orow = out + (size_t)e * (kOut * kOut * kPP) * L + l;
       if (pw >= 0) {
@@ -408,9 +572,9 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -532,7 +696,7 @@ static int make_map(CUtensorMap* m, int dtype, int rank, const void* ptr, const 
 template <typename T>
 static int launch_fast(const CUtensorMap* maps, const FastParams& prm, cudaStream_t s) {
   const size_t smem = 1024 + (size_t)kStages * kStageBytes + (size_t)kEpiGroups * 2 * kVsFloats * sizeof(float) +
-                      (size_t)kCoordRing * kCoordFloats * sizeof(float) + 32 * sizeof(uint64_t);
+                      (size_t)kCoordRing * kSlotBytes + (size_t)kRecRing * kRecWords * 4 + 40 * sizeof(uint64_t);
   static bool configured = false;
   if (!configured) {
     DEVO_CUDA(cudaFuncSetAttribute(corr_fast_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
