@@ -192,9 +192,9 @@ static BaLayout ba_layout(int E, int nfree) {
   L.Q = off;       off += al(Em * 8);
   L.U = off;       off += al(Em * 8);
   L.Ek = off;      off += al(Em * (size_t)(n6 > 0 ? n6 : 1) * 8);
-  L.partials = off; off += al((size_t)L.grid * L.nent * 8);
+  L.partials = off; off += al((size_t)(L.grid + (L.grid + 7) / 8) * L.nent * 8);   // per-CTA + per-group partials
   L.dX = off;      off += al((size_t)(n6 > 0 ? n6 : 1) * 8);
-  L.ticket = off;  off += al(16);
+  L.ticket = off;  off += al(4 * 32);   // [0] group counter, [1..] per-group CTA counters (grid <= 148 => <= 19 groups)
   L.total = off;
   return L;
 }
@@ -219,126 +219,147 @@ __device__ __forceinline__ void tri_decode(int idx, int m, int& a, int& b) {
 // reads touch column k only, writes touch columns > k only, so no second barrier is needed.
 // Afterwards A_ik (i>k) = L_ik d_k and y = L^-1 y; warp 0 finishes x = L^-T D^-1 y with shuffles.
 // S positive definite  <=>  every pivot d_k = A_kk > 0 (same acceptance test as Cholesky).
+#ifdef DEVO_BA_TIMING
+__device__ long long g_ba_clk[16];
+#define BA_STAMP(i) do { if (threadIdx.x == 0) g_ba_clk[i] = clock64(); } while (0)
+#else
+#define BA_STAMP(i)
+#endif
+// Solve S dX = y for the reduced system held as `nparts` partial sums (fixed summation order), then retract
+// the poses.  smem: A packed lower-triangular n(n+1)/2 doubles, y[n+1], rinv[n], col[2][n+1] doubles.
+//
+// Square-root-free elimination of the augmented matrix [S | y] kept in REGISTERS: thread t owns the entries
+// e = t, t+T, ... (row gi >= column gj; row gi == n is y^T) for the whole factorisation.  At pivot step k
+// every entry with gj > k is updated as  v -= c[gi] c[gj] / d_k  where c = column k.  The owners of column
+// k+1 publish their freshly updated values into a double-buffered shared column, so there is exactly ONE
+// barrier per pivot and two shared loads + two DFMA-class instructions per entry and step.  The thread that
+// finalises the next pivot also stores 1/d (the only fp64 division of the step).  Afterwards
+// A_ik = L_ik d_k, y = L^-1 y; warp 0 finishes x = L^-T D^-1 y.  S positive definite <=> every pivot > 0
+// (the same acceptance test as Cholesky).
+// 1/d for a pivot: single-precision seed + two Newton steps in fp64 (relative error ~1e-16; about half the
+// latency of the IEEE division sequence, which sits on the critical path of every elimination step)
+__device__ __forceinline__ double pivot_rcp(double d) {
+  double r = (double)(1.0f / (float)d);
+  r = r * (2.0 - d * r);
+  r = r * (2.0 - d * r);
+  return r;
+}
+
+template <int KENT>
 __device__ void ba_solve_device(unsigned char* smem_raw, float* poses, const double* partials, double* dX,
                                 int32_t* status, int nparts, int t0, int nfree, int itr) {
+  BA_STAMP(1);
   const int n = 6 * nfree;
   const int LD = n + 1;
   const int nent = (n + 1) * (n + 2) / 2;
   double* A = reinterpret_cast<double*>(smem_raw);
-  double* y = A + (size_t)n * (n + 1) / 2;
+  double* y = A + n * (n + 1) / 2;
+  double* rinv = y + n + 1;                               // [n] reciprocals of the pivots
+  double* col = rinv + n;                                 // [2][n+1] current / next pivot column (row n = y)
   __shared__ int s_fail;
   const int tid = threadIdx.x;
   if (*status != 0) return;
   if (n == 0) return;
   if (tid == 0) s_fail = 0;
 
-  // fixed-order reduction of the per-CTA partials; entry (a,b), a<=b of the (n+1)x(n+1) augmented matrix
+  // fixed-order reduction of the partial sums; entry (a,b), a<=b of the (n+1)x(n+1) augmented matrix.
+  // 8 independent accumulators keep 8 L2 loads in flight; combined in a fixed tree => deterministic.
   for (int idx = tid; idx < nent; idx += kSolveThreads) {
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    double s8[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) s8[u] = 0.0;
     int p = 0;
-    for (; p + 4 <= nparts; p += 4) {
-      s0 += __ldcg(&partials[(size_t)(p + 0) * nent + idx]);
-      s1 += __ldcg(&partials[(size_t)(p + 1) * nent + idx]);
-      s2 += __ldcg(&partials[(size_t)(p + 2) * nent + idx]);
-      s3 += __ldcg(&partials[(size_t)(p + 3) * nent + idx]);
+    for (; p + 8 <= nparts; p += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) s8[u] += __ldcg(&partials[(size_t)(p + u) * nent + idx]);
     }
-    for (; p < nparts; p++) s0 += __ldcg(&partials[(size_t)p * nent + idx]);
-    double s = (s0 + s1) + (s2 + s3);
+    for (; p < nparts; p++) s8[0] += __ldcg(&partials[(size_t)p * nent + idx]);
+    double s = ((s8[0] + s8[1]) + (s8[2] + s8[3])) + ((s8[4] + s8[5]) + (s8[6] + s8[7]));
     int a, b;
     tri_decode(idx, LD, a, b);
     if (b == n) {
       if (a < n) y[a] = s;                                // y = v - E Q u
     } else {
       if (a == b) s += 1e-4 * s + 1.0;                    // S += I o (1e-4 S + 1)   (:517-518)
-      A[(size_t)b * (b + 1) / 2 + a] = s;                 // symmetric: store as lower (b,a)
+      A[b * (b + 1) / 2 + a] = s;                         // symmetric: store as lower (b,a)
     }
   }
   __syncthreads();
+  BA_STAMP(2);
 
-  // Fixed ownership: thread t owns lower-triangular entries e = t, t+1024, ... of the augmented matrix
-  // (row gi, column gj <= gi; the extra last row gi == n is y^T).  Entry (gi,gj) takes part in pivot step
-  // k while gj > k.  The reciprocal of the next pivot is produced by the one thread that finalises it, so the
-  // 1/d division (a long fp64 sequence) is executed once per step instead of by every warp.
-  constexpr int kEnt = ((kMaxN6 + 1) * (kMaxN6 + 2) / 2 + kSolveThreads - 1) / kSolveThreads;
-  int ent[kEnt];                                          // (gi << 16) | gj, or -1
-  const int naug = (n + 1) * (n + 2) / 2 - 1;            // lower triangle of the (n+1)x(n+1) matrix without (n,n)
+  // load the owned entries into registers; publish column 0 and the first pivot
+  const int naug = (n + 1) * (n + 2) / 2 - 1;            // lower triangle of the augmented matrix without (n,n)
+  double v[KENT];
+  int ent[KENT];                                          // (gi << 16) | gj, or -1
 #pragma unroll
-  for (int q = 0; q < kEnt; q++) {
+  for (int q = 0; q < KENT; q++) {
     const int e = tid + q * kSolveThreads;
-    int gi = 0, gj = 0;
+    ent[q] = -1;
+    v[q] = 0.0;
     if (e < naug) {
-      gi = (int)floorf((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+      int gi = (int)floorf((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
       while (gi * (gi + 1) / 2 > e) gi--;
       while ((gi + 1) * (gi + 2) / 2 <= e) gi++;
-      gj = e - gi * (gi + 1) / 2;
+      const int gj = e - gi * (gi + 1) / 2;
+      ent[q] = (gi << 16) | gj;
+      v[q] = (gi < n) ? A[gi * (gi + 1) / 2 + gj] : y[gj];
+      if (gj == 0) col[gi] = v[q];
+      if (gi == 0) {                                      // entry (0,0): first pivot
+        if (!(v[q] > 0.0) || !isfinite(v[q])) s_fail = 1;
+        rinv[0] = pivot_rcp(v[q]);
+      }
     }
-    ent[q] = (e < naug) ? ((gi << 16) | gj) : -1;
-  }
-  double* rinv = y + n + 1;                               // [n] reciprocals of the pivots
-  if (tid == 0) {
-    const double a00 = A[0];
-    if (!(a00 > 0.0) || !isfinite(a00)) s_fail = 1;
-    rinv[0] = 1.0 / a00;
   }
   __syncthreads();
+  BA_STAMP(3);
   for (int k = 0; k < n; k++) {
     if (s_fail) break;                                    // uniform (written before the last barrier)
     const double r = rinv[k];
-    const double yk = y[k];
+    const double* ck = col + (k & 1) * (n + 1);
+    double* cn = col + ((k + 1) & 1) * (n + 1);
 #pragma unroll
-    for (int q = 0; q < kEnt; q++) {
+    for (int q = 0; q < KENT; q++) {
       if (ent[q] < 0) continue;
       const int gi = ent[q] >> 16, gj = ent[q] & 0xffff;
       if (gj <= k) continue;
-      if (gi < n) {
-        const size_t at = (size_t)gi * (gi + 1) / 2;
-        const double v = A[at + gj] - A[at + k] * A[(size_t)gj * (gj + 1) / 2 + k] * r;
-        A[at + gj] = v;
-        if (gi == k + 1 && gj == k + 1) {                 // the next pivot is final now
-          if (!(v > 0.0) || !isfinite(v)) s_fail = 1;
-          rinv[k + 1] = 1.0 / v;
+      v[q] -= ck[gi] * r * ck[gj];
+      if (gj == k + 1) {
+        cn[gi] = v[q];                                    // next pivot column
+        if (gi == k + 1) {                                // next pivot, final now
+          if (!(v[q] > 0.0) || !isfinite(v[q])) s_fail = 1;
+          rinv[k + 1] = pivot_rcp(v[q]);
         }
-      } else {
-        y[gj] -= A[(size_t)gj * (gj + 1) / 2 + k] * yk * r;   // last row of the augmented matrix: y
       }
     }
     __syncthreads();
+  }
+  // write the factor back (column gj of A holds L_ij d_j, the y row holds L^-1 y)
+#pragma unroll
+  for (int q = 0; q < KENT; q++) {
+    if (ent[q] < 0) continue;
+    const int gi = ent[q] >> 16, gj = ent[q] & 0xffff;
+    if (gi < n) A[gi * (gi + 1) / 2 + gj] = v[q];
+    else y[gj] = v[q];
   }
   __syncthreads();
   if (s_fail) {
     if (tid == 0) atomicCAS(status, 0, itr + 1);
     return;
   }
-  // back substitution by warp 0: x_k = y_k/d_k - sum_{i>k} (A_ik/d_k) x_i ; lane l owns x[l + 32 m]
+  BA_STAMP(4);
+  // back substitution: w = D^-1 z, then for k = n-1..1 eliminate x_k from all rows i < k (L_ki = A_ki / d_i)
+  for (int i = tid; i < n; i += kSolveThreads) y[i] *= rinv[i];
+  __syncthreads();
   if (tid < 32) {
-    constexpr int kMaxPerLane = (kMaxN6 + 31) / 32;
-    const int nper = (n + 31) >> 5;                      // slots actually used
-    double x[kMaxPerLane], invd[kMaxPerLane];
-#pragma unroll
-    for (int mm = 0; mm < kMaxPerLane; mm++) {
-      const int i = tid + 32 * mm;
-      invd[mm] = (i < n) ? 1.0 / A[(size_t)i * (i + 1) / 2 + i] : 0.0;
-      x[mm] = (i < n) ? y[i] * invd[mm] : 0.0;                           // D^-1 y
-    }
-    for (int k = n - 1; k >= 0; k--) {
-      // x_k is final; broadcast it and eliminate it from all rows i < k
-      double xk = 0.0;
-#pragma unroll
-      for (int mm = 0; mm < kMaxPerLane; mm++)
-        if ((k >> 5) == mm) xk = __shfl_sync(0xffffffffu, x[mm], k & 31);
-#pragma unroll
-      for (int mm = 0; mm < kMaxPerLane; mm++) {
-        const int i = tid + 32 * mm;
-        if (mm < nper && i < k) x[mm] -= A[(size_t)k * (k + 1) / 2 + i] * invd[mm] * xk;
-      }
-    }
-#pragma unroll
-    for (int mm = 0; mm < kMaxPerLane; mm++) {
-      const int i = tid + 32 * mm;
-      if (i < n) y[i] = x[mm];
+    for (int k = n - 1; k >= 1; k--) {
+      const double xk = y[k];
+      const int rk = k * (k + 1) / 2;
+      for (int i = tid; i < k; i += 32) y[i] -= A[rk + i] * rinv[i] * xk;
+      __syncwarp();
     }
   }
   __syncthreads();
+  BA_STAMP(5);
   bool bad = false;
   for (int i = tid; i < n; i += kSolveThreads) {
     dX[i] = y[i];
@@ -361,6 +382,12 @@ __device__ void ba_solve_device(unsigned char* smem_raw, float* poses, const dou
     for (int c = 0; c < 7; c++) dst[c] = P[c];
   }
 }
+
+// ---- hierarchical, order-preserving reduction of the per-CTA partials ----------------------------------
+// CTAs are grouped 8 by 8; the last CTA of a group to finish adds the group's partials in index order into a
+// group partial, and the last group to finish runs the solve on the group partials.  Which CTA does the work
+// depends on timing, what is summed in which order does not.
+constexpr int kGroupCtas = 8;
 
 // ---- accumulate kernel ----------------------------------------------------------------------
 // smem: X[R][LD] doubles, coef[R] doubles, zj[R] doubles (Jz per row), batch bookkeeping
@@ -387,6 +414,9 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
   __shared__ float s_intr[4];
 
   const int tid = threadIdx.x;
+#ifdef DEVO_BA_TIMING
+  if (blockIdx.x == 0 && tid == 0) g_ba_clk[0] = clock64();
+#endif
   const int st = *status;
   if (st != 0) {               // an earlier iteration failed: do nothing (reference would have thrown)
     if (do_accumulate) {
@@ -539,21 +569,47 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
     if (idx < nent) partials[(size_t)blockIdx.x * nent + idx] = acc[q];
   }
   (void)n_poses; (void)E;
-  // ---- the last CTA to finish reduces the partials (fixed order => deterministic), solves the reduced
-  //      system and retracts the poses: one launch per Gauss-Newton iteration
+  // ---- hierarchical reduction + solve + retraction in the same launch (see kGroupCtas above)
   if (nfree > 0) {
+    const int ngrp = ((int)gridDim.x + kGroupCtas - 1) / kGroupCtas;
+    const int grp = (int)blockIdx.x / kGroupCtas;
+    const int gfirst = grp * kGroupCtas;
+    const int gsize = min(kGroupCtas, (int)gridDim.x - gfirst);
+    double* gpart = partials + (size_t)gridDim.x * nent;   // [ngrp][nent]
     __threadfence();
     __syncthreads();
-    if (tid == 0) s_batch[0] = atomicAdd(ticket, 1);
+    if (tid == 0) s_batch[0] = atomicAdd(&ticket[1 + grp], 1);
     __syncthreads();
-    if (s_batch[0] == (int)gridDim.x - 1) {
-      if (tid == 0) *ticket = 0;                 // armed for the next launch
+    if (s_batch[0] == gsize - 1) {                           // last CTA of its group
+      if (tid == 0) ticket[1 + grp] = 0;                     // armed for the next launch
       __threadfence();
-      ba_solve_device(smem_raw, poses_rw, partials, dX, status, (int)gridDim.x, t0, nfree, itr);
+      for (int idx = tid; idx < nent; idx += kAccThreads) {
+        double t8[kGroupCtas];
+#pragma unroll
+        for (int u = 0; u < kGroupCtas; u++)
+          t8[u] = (u < gsize) ? __ldcg(&partials[(size_t)(gfirst + u) * nent + idx]) : 0.0;
+        gpart[(size_t)grp * nent + idx] = ((t8[0] + t8[1]) + (t8[2] + t8[3])) + ((t8[4] + t8[5]) + (t8[6] + t8[7]));
+      }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) s_batch[1] = atomicAdd(&ticket[0], 1);
+      __syncthreads();
+      if (s_batch[1] == ngrp - 1) {                          // last group: solve
+        if (tid == 0) ticket[0] = 0;
+        __threadfence();
+        if (n6 <= 44) ba_solve_device<2>(smem_raw, poses_rw, gpart, dX, status, ngrp, t0, nfree, itr);
+        else if (n6 <= 88) ba_solve_device<8>(smem_raw, poses_rw, gpart, dX, status, ngrp, t0, nfree, itr);
+        else ba_solve_device<(((kMaxN6 + 1) * (kMaxN6 + 2) / 2) + kSolveThreads - 1) / kSolveThreads>(
+            smem_raw, poses_rw, gpart, dX, status, ngrp, t0, nfree, itr);
+        BA_STAMP(6);
+      }
     }
   }
 }
 
+}  // namespace
+
+namespace {
 // ---- reproject (:368-418) ---------------------------------------------------------------------
 __global__ void reproject_kernel(const float* __restrict__ poses, const float* __restrict__ patches,
                                  const float* __restrict__ intrinsics, const int64_t* __restrict__ ii,
@@ -672,6 +728,10 @@ static int launch_accumulate(const BaLayout& L, char* w, float* poses, float* pa
 
 extern "C" {
 
+#ifdef DEVO_BA_TIMING
+int devo_ba_debug_clocks(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_ba_clk, sizeof(long long) * 16); }
+#endif
+
 size_t devo_ba_workspace(int E, int n_free_poses) { return ba_layout(E, n_free_poses).total; }
 
 static int ba_forward_impl(float* poses, float* patches, const float* intrinsics, const float* target,
@@ -735,9 +795,9 @@ static int ba_forward_impl(float* poses, float* patches, const float* intrinsics
   } while (0)
 
   DEVO_REQUIRE(ept <= 24, DEVO_ECAPACITY, "ba_forward: system too large (%d entries)", L.nent);
-  const size_t smem_solve = ((size_t)n6 * (n6 + 1) / 2 + 2 * n6 + 4) * 8;
+  const size_t smem_solve = ((size_t)n6 * (n6 + 1) / 2 + 4 * n6 + 8) * 8;
   DEVO_REQUIRE(smem_solve <= smem_acc, DEVO_ECAPACITY, "ba_forward: solver does not fit the accumulate CTA's shared memory");
-  DEVO_CUDA(cudaMemsetAsync(w + L.ticket, 0, 16, s));
+  DEVO_CUDA(cudaMemsetAsync(w + L.ticket, 0, 4 * 32, s));
   for (int itr = 0; itr < iterations; itr++) {
     ACC_DISPATCH(itr > 0 ? 1 : 0, 1, itr);   // accumulate + (last CTA) solve + retraction
   }
