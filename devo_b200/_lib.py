@@ -37,6 +37,11 @@ SIGNATURES = {
     "devo_ba_forward_planned": (_i, [_vp] * 9 + [_i] * 7 + [_vp] * 4 + [_vp, _sz, _vp, _vp]),
     "devo_reproject": (_i, [_vp] * 7 + [_i, _i, _vp]),
     "devo_transform_forward": (_i, [_vp] * 11 + [_i] * 4 + [_vp]),
+    "devo_glue_layernorm": (_i, [_i, _i] + [_vp] * 6 + [_c.c_float, _vp, _vp, _i, _i, _vp]),
+    "devo_glue_gather_mask_cast": (_i, [_i, _vp, _vp, _vp, _i, _i, _vp]),
+    "devo_glue_residual_add": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "devo_glue_gated_residual": (_i, [_i, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "devo_glue_relu_cast": (_i, [_i, _vp, _vp, _i64, _i, _vp]),
     "devo_segment_softmax_sum": (_i, [_vp] * 5 + [_i, _vp, _i, _i, _i, _vp]),
 }
 for _n, _a in (("expm", 2), ("logm", 2), ("inv", 2), ("as_matrix", 2), ("projector", 2),

@@ -24,7 +24,7 @@ from .update import FrozenCast
 
 class UpdateOperator:
     def __init__(self, update, n_frames, patches_per_frame, n_edges, H, W, C=128, dim=384, levels=(1, 4),
-                 device="cuda", feat_dtype=torch.float16, ba_iterations=2, t0=1, t1=None):
+                 device="cuda", feat_dtype=torch.float16, ba_iterations=2, t0=1, t1=None, fused_gru=True):
         self.update = update
         self.Nf, self.M, self.E = n_frames, patches_per_frame, n_edges
         self.Np = n_frames * patches_per_frame
@@ -33,6 +33,7 @@ class UpdateOperator:
         self.device = torch.device(device)
         self.feat_dtype = feat_dtype
         self.ba_iterations = ba_iterations
+        self.fused_gru = fused_gru
         self.t0 = t0
         self.t1 = n_frames if t1 is None else t1
         dev, f32, i64 = self.device, torch.float32, torch.int64
@@ -107,9 +108,14 @@ class UpdateOperator:
         cur.wait_stream(self._side)
         # (3) GRU: cached fp16 weights, autocast-identical dtype flow, no host sync
         ctx = self.imap[:, self.kk]
-        net, (delta, weight, _) = self.update.forward_planned(
-            self.net, ctx, corr.view(1, self.E, -1), self.plan_kk, self.plan_ij, self.Np, self.Nf * self.Nf, self.fc)
-        self.net.copy_(net)
+        if self.fused_gru:
+            net, (delta, weight, _) = self.update.forward_fused(
+                self.net, ctx, corr.view(1, self.E, -1), self.plan_kk, self.plan_ij, self.Np, self.Nf * self.Nf,
+                self.fc, net_out=self.net)
+        else:
+            net, (delta, weight, _) = self.update.forward_planned(
+                self.net, ctx, corr.view(1, self.E, -1), self.plan_kk, self.plan_ij, self.Np, self.Nf * self.Nf, self.fc)
+            self.net.copy_(net)
         # (4) BA targets and in-place Gauss-Newton (reuses the kk/jj plan: one sort serves neighbours,
         #     SoftAgg and the Schur grouping)
         target = coords[:, :, :, 1, 1] + delta.float()

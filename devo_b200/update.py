@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import cuda_ba, fastba
+from . import cuda_ba, fastba, glue
 from .scatter import scatter_softmax, scatter_sum
 
 DIM = 384
@@ -43,6 +43,10 @@ class FrozenCast:
     @staticmethod
     def layer_norm(layer, x):
         return F.layer_norm(x.float(), layer.normalized_shape, layer.weight, layer.bias, layer.eps)
+
+    def linear_relu(self, layer, x2d):
+        """Linear + ReLU with the ReLU in the cuBLASLt epilogue (identical result: max(.,0) commutes with rounding)"""
+        return torch._addmm_activation(self.get(layer.bias), x2d, self.get(layer.weight).t(), use_gelu=False)
 
     def run(self, module, x):
         """evaluate an nn.Sequential / layer of the update operator with autocast semantics"""
@@ -156,3 +160,35 @@ class Update(nn.Module):
         net = net + self.agg_ij.forward_planned(net, plan_ij, max_pairs, fc)
         net = run(self.gru, net)
         return net, (run(self.d, net), run(self.w, net), None)
+
+    def forward_fused(self, net16, inp16, corr16, plan_kk, plan_ij, max_patches, max_pairs, fc, net_out=None):
+        """forward_planned with the element-wise glue fused into hand-written kernels (devo_b200.glue) and
+        ReLUs folded into GEMM epilogues.  Inputs are [1,E,*] tensors of the autocast dtype; returns
+        (net float32 [1,E,dim], (delta, weight, None)); `net_out` optionally receives the new hidden state
+        rounded to the autocast dtype.  Same rounding points as autocast; inference only."""
+        E, D, hd = net16.shape[1], self.dim, fc.dtype
+        lin, lin_relu = fc.linear, fc.linear_relu
+        c = lin_relu(self.corr[0], corr16.reshape(E, -1))
+        c = lin(self.corr[2], c)
+        c = glue.layernorm_relu_half(c, self.corr[3])
+        c = lin(self.corr[5], c)
+        net = glue.layernorm_add3(net16.reshape(E, D), inp16.reshape(E, D), c, self.norm)       # float32 [E,D]
+        for seq, idx in ((self.c1, plan_kk.ix), (self.c2, plan_kk.jx)):
+            g = glue.gather_mask_cast(net, idx, hd)
+            y = lin(seq[2], lin_relu(seq[0], g))
+            x16 = glue.residual_add_(net, y, want_half=seq is self.c2)
+        for agg, plan, mg in ((self.agg_kk, plan_kk, max_patches), (self.agg_ij, plan_ij, max_pairs)):
+            y = cuda_ba.segment_softmax_sum(lin(agg.g, x16), lin(agg.f, x16), plan, mg)
+            hy = lin(agg.h, y.reshape(mg, D))
+            x16 = glue.residual_add_(net, hy, gid=plan.gid, want_half=agg is self.agg_kk)
+        for ln, gr in ((self.gru[0], self.gru[1]), (self.gru[2], self.gru[3])):
+            n32, n16 = glue.layernorm_f32(net, ln, hd)
+            gate = lin(gr.gate[0], n16)
+            res = lin(gr.res[2], lin_relu(gr.res[0], n16))
+            net = glue.gated_residual(n32, gate, res)
+        h16 = glue.relu_cast(net, hd, relu=True)
+        delta = lin(self.d[1], h16)
+        weight = torch.sigmoid(lin(self.w[1], h16))
+        if net_out is not None:
+            glue.relu_cast(net, hd, relu=False, out=net_out.reshape(E, D))
+        return net.view(1, E, D), (delta.view(1, E, 2), weight.view(1, E, 2), None)

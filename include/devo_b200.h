@@ -169,6 +169,23 @@ int devo_segment_softmax_sum(const void* g, const void* f, const int32_t* perm, 
                              const int32_t* ngroups, int max_groups, void* y_out, int dtype,
                              int n_rows, int dim, void* stream);
 
+/* ------------------------------------------------------------------ GRU glue */
+/* Fused element-wise chains between the cuBLAS Linear layers of `Update` (devo/enet.py:80-99,
+ * devo/blocks.py:15-29).  dtype = the autocast type (DEVO_F16 / DEVO_BF16); rounding points follow
+ * torch.autocast's dtype flow.  rows x dim row-major.
+ * layernorm modes: 0: LN(T(T(a+b)+c)) -> out32 ; 1: LN(x32) -> out32 (+ out16 copy) ; 2: T(relu(LN(a))) -> out16 */
+int devo_glue_layernorm(int mode, int dtype, const void* a, const void* b, const void* c, const float* x32,
+                        const float* gamma, const float* beta, float eps, float* out32, void* out16,
+                        int rows, int dim, void* stream);
+/* out16[e,:] = idx[e] >= 0 ? T(x32[idx[e],:]) : 0   (mask * net[:, ix], enet.py:87-91) */
+int devo_glue_gather_mask_cast(int dtype, const float* x32, const int64_t* idx, void* out16, int rows, int dim, void* stream);
+/* net32[e,:] += y16[gid ? gid[e] : e, :] ; optional T copy of the sum in out16 */
+int devo_glue_residual_add(int dtype, float* net32, const void* y16, const int32_t* gid, void* out16, int rows, int dim, void* stream);
+/* out32 = x32 + T(T(sigmoid(gate_pre)) * res)   (GatedResidual, blocks.py:15-29) */
+int devo_glue_gated_residual(int dtype, const float* x32, const void* gate_pre, const void* res, float* out32, int64_t total, void* stream);
+/* out16 = T(relu ? max(x32,0) : x32) */
+int devo_glue_relu_cast(int dtype, const float* x32, void* out16, int64_t total, int relu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -257,3 +257,30 @@ def test_ba_with_shared_plan_is_bitwise_identical():
     plan = cuda_ba.GraphPlan(P["kk"].cuda(), P["jj"].cuda(), 100, 5)
     st = cuda_ba.forward_async(p2, x2, *rest, plan=plan)
     assert int(st.item()) == 0 and torch.equal(p1, p2) and torch.equal(x1, x2)
+
+
+def test_fused_gru_equals_planned_path():
+    """forward_fused (hand-written glue kernels, ReLU in GEMM epilogues) == forward_planned (ATen ops)"""
+    from devo_b200 import cuda_ba
+    from devo_b200.update import Update, FrozenCast
+    torch.manual_seed(2)
+    ii, jj, kk = [t.cuda() for t in fully_connected_graph(5, 16)]
+    E = ii.numel()
+    perm = torch.randperm(E, device="cuda")
+    ii, jj, kk = ii[perm], jj[perm], kk[perm]
+    up = Update(3).cuda().eval()
+    net = (0.3 * torch.randn(1, E, 384, device="cuda")).half()
+    inp = (0.3 * torch.randn(1, E, 384, device="cuda")).half()
+    corr = torch.randn(1, E, 882, device="cuda").half()
+    pk = cuda_ba.GraphPlan(kk, jj, 80, 5)
+    pij = cuda_ba.GraphPlan(ii * 12345 + jj, torch.zeros_like(kk), -1, 1, want_neighbors=False)
+    fc = FrozenCast(torch.float16)
+    out16 = torch.empty_like(net)
+    with torch.no_grad():
+        n1, (d1, w1, _) = up.forward_planned(net, inp, corr, pk, pij, 80, 25, fc)
+        n2, (d2, w2, _) = up.forward_fused(net, inp, corr, pk, pij, 80, 25, fc, net_out=out16)
+    assert n1.dtype == n2.dtype == torch.float32 and d2.dtype == torch.float16 and w2.dtype == torch.float16
+    assert torch.allclose(n1, n2, atol=2e-2, rtol=2e-2), (n1 - n2).abs().max()
+    assert (n1 - n2).abs().mean() < 2e-3
+    assert torch.allclose(d1.float(), d2.float(), atol=1e-2) and torch.allclose(w1.float(), w2.float(), atol=5e-3)
+    assert torch.equal(out16, n2.half())
