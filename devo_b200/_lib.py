@@ -42,6 +42,7 @@ SIGNATURES = {
     "devo_glue_residual_add": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "devo_glue_gated_residual": (_i, [_i, _vp, _vp, _vp, _vp, _i64, _vp]),
     "devo_glue_relu_cast": (_i, [_i, _vp, _vp, _i64, _i, _vp]),
+    "devo_glue_heads": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "devo_segment_softmax_sum": (_i, [_vp] * 5 + [_i, _vp, _i, _i, _i, _vp]),
 }
 for _n, _a in (("expm", 2), ("logm", 2), ("inv", 2), ("as_matrix", 2), ("projector", 2),

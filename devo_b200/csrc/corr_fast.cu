@@ -612,11 +612,12 @@ __global__ void __launch_bounds__(256) pyramid_pack_kernel(const T* __restrict__
 template <typename T, int POOL>
 __global__ void __launch_bounds__(256) pyramid_pack_vec_kernel(const T* __restrict__ in, T* __restrict__ out,
                                                                int C, int H, int W, int Ho, int Wo) {
-  extern __shared__ float tile[];   // [32][C+1]
-  const int n = blockIdx.z, yo = blockIdx.y, x0 = blockIdx.x * 32;
-  const int nx = min(32, Wo - x0);
+  extern __shared__ float tile[];   // [TW][C+1]
+  constexpr int TW = (POOL >= 4) ? 8 : 32;          // output pixels per CTA: narrow tiles for pooled (small) levels => more CTAs
+  const int n = blockIdx.z, yo = blockIdx.y, x0 = blockIdx.x * TW;
+  const int nx = min(TW, Wo - x0);
   constexpr int OPC = 8 / POOL;                     // output pixels per 16-byte chunk
-  constexpr int CHUNKS = 32 / OPC;                  // chunks per (channel, input row) of this tile
+  constexpr int CHUNKS = TW / OPC;                  // chunks per (channel, input row) of this tile
   const T* src = in + (size_t)n * C * H * W;
   for (int q = threadIdx.x; q < C * CHUNKS; q += blockDim.x) {
     const int ch = q % CHUNKS, c = q / CHUNKS;
@@ -721,10 +722,11 @@ int devo_pyramid_pack(const void* fmap_planar, void* out_pixel_major, int dtype,
   DEVO_REQUIRE(Ho <= 65535 && N <= 65535, DEVO_EINVAL, "pyramid_pack: dims too large");
   const size_t smem = (size_t)32 * (C + 1) * sizeof(float);
   DEVO_REQUIRE(smem <= 48 * 1024, DEVO_ECAPACITY, "pyramid_pack: C too large");
-  dim3 grid((Wo + 31) / 32, Ho, N);
   cudaStream_t s = (cudaStream_t)stream;
   const bool vec_ok = (W % 8 == 0) && (C % 8 == 0) && (pool == 1 || pool == 2 || pool == 4 || pool == 8) &&
                       (((uintptr_t)fmap_planar & 15) == 0) && (((uintptr_t)out_pixel_major & 15) == 0);
+  const int tw = (vec_ok && pool >= 4) ? 8 : 32;
+  dim3 grid((Wo + tw - 1) / tw, Ho, N);
 #define PACK_VEC(T, POOL) pyramid_pack_vec_kernel<T, POOL><<<grid, 256, smem, s>>>((const T*)fmap_planar, (T*)out_pixel_major, C, H, W, Ho, Wo)
 #define PACK_ANY(T) do { if (!vec_ok) pyramid_pack_kernel<T><<<grid, 256, smem, s>>>((const T*)fmap_planar, (T*)out_pixel_major, C, H, W, Ho, Wo, pool); \
     else if (pool == 1) PACK_VEC(T, 1); else if (pool == 2) PACK_VEC(T, 2); else if (pool == 4) PACK_VEC(T, 4); else PACK_VEC(T, 8); } while (0)

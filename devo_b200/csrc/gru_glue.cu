@@ -78,57 +78,104 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ a,
   }
 }
 
+// ---- vectorised row kernels: blockDim = (dim/4, rows_per_cta); one thread = 4 consecutive channels
+// (16-byte float4 loads/stores, 8-byte loads/stores of 4 T).  dim % 4 == 0.
+template <typename T> struct alignas(8) Vec4 { T v[4]; };
+
+template <typename T> __device__ __forceinline__ float4 ld4(const T* p) {
+  const Vec4<T> r = *reinterpret_cast<const Vec4<T>*>(p);
+  return make_float4(ElemTraits<T>::to_float(r.v[0]), ElemTraits<T>::to_float(r.v[1]), ElemTraits<T>::to_float(r.v[2]), ElemTraits<T>::to_float(r.v[3]));
+}
+template <typename T> __device__ __forceinline__ void st4(T* p, float4 f) {
+  Vec4<T> r;
+  r.v[0] = ElemTraits<T>::from_float(f.x); r.v[1] = ElemTraits<T>::from_float(f.y);
+  r.v[2] = ElemTraits<T>::from_float(f.z); r.v[3] = ElemTraits<T>::from_float(f.w);
+  *reinterpret_cast<Vec4<T>*>(p) = r;
+}
+
 // out[e,:] = idx[e] >= 0 ? T(x32[idx[e],:]) : 0      (mask * net[:, ix] then the Linear's input cast)
 template <typename T>
 __global__ void gather_mask_cast_kernel(const float* __restrict__ x32, const int64_t* __restrict__ idx,
                                         T* __restrict__ out, int rows, int dim) {
-  const long long total = (long long)rows * dim;
-  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
-    const int e = (int)(q / dim), c = (int)(q - (long long)e * dim);
-    const long long j = idx[e];
-    out[q] = ElemTraits<T>::from_float(j >= 0 ? x32[(size_t)j * dim + c] : 0.f);
-  }
+  const int e = blockIdx.x * blockDim.y + threadIdx.y, c = threadIdx.x * 4;
+  if (e >= rows || c >= dim) return;
+  const long long j = idx[e];
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (j >= 0) v = *reinterpret_cast<const float4*>(x32 + (size_t)j * dim + c);
+  st4<T>(out + (size_t)e * dim + c, v);
 }
 
 // net32[e,:] += float(y16[g,:]) with g = gid ? gid[e] : e   (residual add, optionally through a group gather)
 template <typename T>
 __global__ void residual_add_kernel(float* __restrict__ net32, const T* __restrict__ y16, const int32_t* __restrict__ gid,
                                     T* __restrict__ out16, int rows, int dim) {
-  const long long total = (long long)rows * dim;
-  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
-    const int e = (int)(q / dim), c = (int)(q - (long long)e * dim);
-    const size_t src = gid ? (size_t)gid[e] * dim + c : (size_t)q;
-    const float v = net32[q] + ElemTraits<T>::to_float(y16[src]);
-    net32[q] = v;
-    if (out16) out16[q] = ElemTraits<T>::from_float(v);      // the next Linear's input cast, for free
-  }
+  const int e = blockIdx.x * blockDim.y + threadIdx.y, c = threadIdx.x * 4;
+  if (e >= rows || c >= dim) return;
+  const size_t at = (size_t)e * dim + c;
+  const size_t src = gid ? (size_t)gid[e] * dim + c : at;
+  float4 v = *reinterpret_cast<const float4*>(net32 + at);
+  const float4 y = ld4<T>(y16 + src);
+  v.x += y.x; v.y += y.y; v.z += y.z; v.w += y.w;
+  *reinterpret_cast<float4*>(net32 + at) = v;
+  if (out16) st4<T>(out16 + at, v);                    // the next Linear's input cast, for free
 }
 
 // out32 = x32 + float( T( T(sigmoid(gate16)) * res16 ) )      (GatedResidual: x + gate(x) * res(x))
 template <typename T>
 __global__ void gated_residual_kernel(const float* __restrict__ x32, const T* __restrict__ gate_pre,
                                       const T* __restrict__ res, float* __restrict__ out32, long long total) {
-  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
-    const float g = rnd<T>(1.0f / (1.0f + expf(-ElemTraits<T>::to_float(gate_pre[q]))));
-    const float p = rnd<T>(g * ElemTraits<T>::to_float(res[q]));
-    out32[q] = x32[q] + p;
-  }
+  const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (q >= total) return;
+  float4 x = *reinterpret_cast<const float4*>(x32 + q);
+  const float4 g = ld4<T>(gate_pre + q), r = ld4<T>(res + q);
+  x.x += rnd<T>(rnd<T>(1.0f / (1.0f + expf(-g.x))) * r.x);
+  x.y += rnd<T>(rnd<T>(1.0f / (1.0f + expf(-g.y))) * r.y);
+  x.z += rnd<T>(rnd<T>(1.0f / (1.0f + expf(-g.z))) * r.z);
+  x.w += rnd<T>(rnd<T>(1.0f / (1.0f + expf(-g.w))) * r.w);
+  *reinterpret_cast<float4*>(out32 + q) = x;
 }
 
 // out16 = T(relu(x32))
 template <typename T>
 __global__ void relu_cast_kernel(const float* __restrict__ x32, T* __restrict__ out16, long long total, int relu) {
-  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
-    const float v = x32[q];
-    out16[q] = ElemTraits<T>::from_float(relu ? fmaxf(v, 0.f) : v);
+  const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (q >= total) return;
+  float4 v = *reinterpret_cast<const float4*>(x32 + q);
+  if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+  st4<T>(out16 + q, v);
+}
+
+// heads: delta = T(W_d . T(relu(x32)) + b_d),  weight = T(sigmoid(T(W_w . T(relu(x32)) + b_w)))   (enet.py:68-77)
+// one warp per row; W16 = [4, dim] (rows: d.x, d.y, w.x, w.y), fp32 accumulation like the GEMM it replaces
+template <typename T>
+__global__ void __launch_bounds__(256) heads_kernel(const float* __restrict__ x32, const T* __restrict__ W16,
+                                                    const T* __restrict__ b16, T* __restrict__ delta,
+                                                    T* __restrict__ weight, int rows, int dim) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = lane * 4; c < dim; c += 128) {
+    float4 v = *reinterpret_cast<const float4*>(x32 + (size_t)row * dim + c);
+    const float h0 = rnd<T>(fmaxf(v.x, 0.f)), h1 = rnd<T>(fmaxf(v.y, 0.f)), h2 = rnd<T>(fmaxf(v.z, 0.f)), h3 = rnd<T>(fmaxf(v.w, 0.f));
+#pragma unroll
+    for (int o = 0; o < 4; o++) {
+      const float4 w = ld4<T>(W16 + (size_t)o * dim + c);
+      acc[o] += h0 * w.x + h1 * w.y + h2 * w.z + h3 * w.w;
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 4; o++) acc[o] = warp_sum(acc[o]);
+  if (lane == 0) {
+    const float d0 = rnd<T>(acc[0] + ElemTraits<T>::to_float(b16[0])), d1 = rnd<T>(acc[1] + ElemTraits<T>::to_float(b16[1]));
+    const float w0 = rnd<T>(acc[2] + ElemTraits<T>::to_float(b16[2])), w1 = rnd<T>(acc[3] + ElemTraits<T>::to_float(b16[3]));
+    delta[(size_t)row * 2 + 0] = ElemTraits<T>::from_float(d0);
+    delta[(size_t)row * 2 + 1] = ElemTraits<T>::from_float(d1);
+    weight[(size_t)row * 2 + 0] = ElemTraits<T>::from_float(1.0f / (1.0f + expf(-w0)));
+    weight[(size_t)row * 2 + 1] = ElemTraits<T>::from_float(1.0f / (1.0f + expf(-w1)));
   }
 }
 
-static int ew_grid(long long total) {
-  long long b = (total + 255) / 256;
-  if (b > 148 * 8) b = 148 * 8;
-  return (int)(b < 1 ? 1 : b);
-}
 }  // namespace
 
 #define GLUE_DISPATCH(dtype, NAME, ...)                                                            \
@@ -158,28 +205,44 @@ int devo_glue_layernorm(int mode, int dtype, const void* a, const void* b, const
 int devo_glue_gather_mask_cast(int dtype, const float* x32, const int64_t* idx, void* out16, int rows, int dim, void* stream) {
   if (rows <= 0) return DEVO_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  DEVO_REQUIRE(dim % 4 == 0 && dim <= 4096, DEVO_EINVAL, "glue_gather_mask_cast: dim must be a multiple of 4");
+  const int tx = dim / 4, ty = tx >= 256 ? 1 : 256 / tx;
+  dim3 block(tx, ty), grid((rows + ty - 1) / ty);
   GLUE_DISPATCH(dtype, "glue_gather_mask_cast",
-                (gather_mask_cast_kernel<T><<<ew_grid((long long)rows * dim), 256, 0, s>>>(x32, idx, (T*)out16, rows, dim)))
+                (gather_mask_cast_kernel<T><<<grid, block, 0, s>>>(x32, idx, (T*)out16, rows, dim)))
 }
 
 int devo_glue_residual_add(int dtype, float* net32, const void* y16, const int32_t* gid, void* out16, int rows, int dim, void* stream) {
   if (rows <= 0) return DEVO_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  DEVO_REQUIRE(dim % 4 == 0 && dim <= 4096, DEVO_EINVAL, "glue_residual_add: dim must be a multiple of 4");
+  const int tx = dim / 4, ty = tx >= 256 ? 1 : 256 / tx;
+  dim3 block(tx, ty), grid((rows + ty - 1) / ty);
   GLUE_DISPATCH(dtype, "glue_residual_add",
-                (residual_add_kernel<T><<<ew_grid((long long)rows * dim), 256, 0, s>>>(net32, (const T*)y16, gid, (T*)out16, rows, dim)))
+                (residual_add_kernel<T><<<grid, block, 0, s>>>(net32, (const T*)y16, gid, (T*)out16, rows, dim)))
 }
 
 int devo_glue_gated_residual(int dtype, const float* x32, const void* gate_pre, const void* res, float* out32, int64_t total, void* stream) {
   if (total <= 0) return DEVO_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  DEVO_REQUIRE(total % 4 == 0, DEVO_EINVAL, "glue_gated_residual: element count must be a multiple of 4");
   GLUE_DISPATCH(dtype, "glue_gated_residual",
-                (gated_residual_kernel<T><<<ew_grid(total), 256, 0, s>>>(x32, (const T*)gate_pre, (const T*)res, out32, total)))
+                (gated_residual_kernel<T><<<(int)((total / 4 + 255) / 256), 256, 0, s>>>(x32, (const T*)gate_pre, (const T*)res, out32, total)))
 }
 
 int devo_glue_relu_cast(int dtype, const float* x32, void* out16, int64_t total, int relu, void* stream) {
   if (total <= 0) return DEVO_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  GLUE_DISPATCH(dtype, "glue_relu_cast", (relu_cast_kernel<T><<<ew_grid(total), 256, 0, s>>>(x32, (T*)out16, total, relu)))
+  DEVO_REQUIRE(total % 4 == 0, DEVO_EINVAL, "glue_relu_cast: element count must be a multiple of 4");
+  GLUE_DISPATCH(dtype, "glue_relu_cast", (relu_cast_kernel<T><<<(int)((total / 4 + 255) / 256), 256, 0, s>>>(x32, (T*)out16, total, relu)))
+}
+
+int devo_glue_heads(int dtype, const float* x32, const void* W16, const void* b16, void* delta, void* weight, int rows, int dim, void* stream) {
+  DEVO_REQUIRE(dim % 4 == 0, DEVO_EINVAL, "glue_heads: dim must be a multiple of 4");
+  if (rows <= 0) return DEVO_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  GLUE_DISPATCH(dtype, "glue_heads",
+                (heads_kernel<T><<<(rows + 7) / 8, 256, 0, s>>>(x32, (const T*)W16, (const T*)b16, (T*)delta, (T*)weight, rows, dim)))
 }
 
 }  // extern "C"

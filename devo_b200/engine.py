@@ -57,6 +57,7 @@ class UpdateOperator:
         self.zeros_e = torch.zeros(self.E, dtype=i64, device=dev)
         self.fc = FrozenCast(feat_dtype)
         self._side = torch.cuda.Stream(device=dev)
+        self._side2 = torch.cuda.Stream(device=dev)
         self._ba_ws = torch.empty(_lib.lib().devo_ba_workspace(self.E, max(self.t1 - self.t0, 0)), dtype=torch.uint8, device=dev)
         self._graph = None
         self._pristine = None
@@ -98,14 +99,17 @@ class UpdateOperator:
         #     it only depends on ii/jj/kk, so it overlaps the reprojection and the correlation lookup
         cur = torch.cuda.current_stream(self.device)
         self._side.wait_stream(cur)
+        self._side2.wait_stream(cur)
         with torch.cuda.stream(self._side):
             self.plan_kk.update()
+        with torch.cuda.stream(self._side2):
             self.plan_ij.update()
         # (1) reproject: [1,E,2,3,3]
         coords = pops.transform_fused(self.poses, self.patches, self.intrinsics, self.ii, self.jj, self.kk, layout=1)
         # (2) correlation lookup over all levels, output already in the GRU's [E, 882] layout
         corr = cuda_corr.lookup_fused(self.gmap_pm, self.levels_pm, self.levels, coords[0], self.kk, self.jj)
         cur.wait_stream(self._side)
+        cur.wait_stream(self._side2)
         # (3) GRU: cached fp16 weights, autocast-identical dtype flow, no host sync
         ctx = self.imap[:, self.kk]
         if self.fused_gru:

@@ -69,3 +69,13 @@ def relu_cast(x32, half_dtype, relu=True, out=None):
     _lib.check(_lib.lib().devo_glue_relu_cast(_dt(out), x32.data_ptr(), out.data_ptr(), x32.numel(), int(relu),
                                               _lib.stream_ptr(x32.device)), "glue_relu_cast")
     return out
+
+
+def heads(x32, W16, b16):
+    """(delta [rows,2], weight [rows,2]) of the update operator's two heads from the float32 hidden state"""
+    rows, dim = x32.shape
+    delta = torch.empty(rows, 2, dtype=W16.dtype, device=x32.device)
+    weight = torch.empty(rows, 2, dtype=W16.dtype, device=x32.device)
+    _lib.check(_lib.lib().devo_glue_heads(_dt(W16), x32.data_ptr(), W16.data_ptr(), b16.data_ptr(), delta.data_ptr(),
+                                          weight.data_ptr(), rows, dim, _lib.stream_ptr(x32.device)), "glue_heads")
+    return delta, weight

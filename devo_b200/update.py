@@ -37,6 +37,16 @@ class FrozenCast:
             self._cache[id(p)] = hit
         return hit[1]
 
+    def get_cat(self, params):
+        """cached low-precision concatenation of several parameters along dim 0"""
+        key = tuple(id(p) for p in params)
+        ver = tuple(p._version for p in params)
+        hit = self._cache.get(key)
+        if hit is None or hit[0] != ver or hit[1].device != params[0].device:
+            hit = (ver, torch.cat([p.detach().to(self.dtype) for p in params], 0).contiguous())
+            self._cache[key] = hit
+        return hit[1]
+
     def linear(self, layer, x):
         return F.linear(x.to(self.dtype), self.get(layer.weight), self.get(layer.bias))
 
@@ -186,9 +196,7 @@ class Update(nn.Module):
             gate = lin(gr.gate[0], n16)
             res = lin(gr.res[2], lin_relu(gr.res[0], n16))
             net = glue.gated_residual(n32, gate, res)
-        h16 = glue.relu_cast(net, hd, relu=True)
-        delta = lin(self.d[1], h16)
-        weight = torch.sigmoid(lin(self.w[1], h16))
+        delta, weight = glue.heads(net, fc.get_cat((self.d[1].weight, self.w[1].weight)), fc.get_cat((self.d[1].bias, self.w[1].bias)))
         if net_out is not None:
             glue.relu_cast(net, hd, relu=False, out=net_out.reshape(E, D))
         return net.view(1, E, D), (delta.view(1, E, 2), weight.view(1, E, 2), None)

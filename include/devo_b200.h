@@ -185,6 +185,10 @@ int devo_glue_residual_add(int dtype, float* net32, const void* y16, const int32
 int devo_glue_gated_residual(int dtype, const float* x32, const void* gate_pre, const void* res, float* out32, int64_t total, void* stream);
 /* out16 = T(relu ? max(x32,0) : x32) */
 int devo_glue_relu_cast(int dtype, const float* x32, void* out16, int64_t total, int relu, void* stream);
+/* both heads of Update in one pass (enet.py:68-77): h = T(relu(x32)); delta[rows,2] = T(W[0:2].h + b[0:2]);
+ * weight[rows,2] = T(sigmoid(T(W[2:4].h + b[2:4]))); W16 [4,dim], b16 [4] */
+int devo_glue_heads(int dtype, const float* x32, const void* W16, const void* b16, void* delta, void* weight,
+                    int rows, int dim, void* stream);
 
 #ifdef __cplusplus
 }
