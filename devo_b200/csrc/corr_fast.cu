@@ -78,6 +78,7 @@ struct FastParams {
   int H[DEVO_MAX_LEVELS], W[DEVO_MAX_LEVELS];
   float scale[DEVO_MAX_LEVELS];
   float inv_scale[DEVO_MAX_LEVELS];         // 1/scale when that is exact (power of two), else 0 => divide
+  int ld_out;                               // output row stride in elements (>= 49*9*L)
   const float* coords;
   const int64_t* ii;
   const int64_t* jj;
@@ -535,7 +536,7 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
       for (int q = 0; q < kPP; q++) vs[q * 128 + row] = __uint_as_float(v[q]);
       asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");   // the 4 warps of this group only
 
-      T* orow = out + (size_t)e * (kOut * kOut * kPP) * L + l;
+      T* orow = out + (size_t)e * prm.ld_out + l;
       if (pw >= 0) {
         const float* sp = vs + p * 128 + pw;
 #pragma unroll
@@ -754,6 +755,12 @@ int devo_gmap_pack(const void* gmap_planar, void* out, int dtype, int Np, int C,
 int devo_corr_lookup_fused(const void* gmap_pm, const devo_pyramid_t* pyr, const float* coords,
                            const int64_t* ii, const int64_t* jj, void* out, int dtype, int Np, int Nf, int C,
                            int E, void* stream) {
+  return devo_corr_lookup_fused_ld(gmap_pm, pyr, coords, ii, jj, out, 0, dtype, Np, Nf, C, E, stream);
+}
+
+int devo_corr_lookup_fused_ld(const void* gmap_pm, const devo_pyramid_t* pyr, const float* coords,
+                              const int64_t* ii, const int64_t* jj, void* out, int ld_out, int dtype, int Np, int Nf,
+                              int C, int E, void* stream) {
   DEVO_REQUIRE(pyr != nullptr && pyr->n_levels >= 1 && pyr->n_levels <= DEVO_MAX_LEVELS, DEVO_EINVAL,
                "corr_lookup_fused: bad pyramid");
   DEVO_REQUIRE(dtype == DEVO_F16 || dtype == DEVO_BF16, DEVO_EUNSUPPORTED, "corr_lookup_fused: dtype must be f16 or bf16");
@@ -764,6 +771,8 @@ int devo_corr_lookup_fused(const void* gmap_pm, const devo_pyramid_t* pyr, const
   FastParams prm;
   prm.E = E; prm.L = pyr->n_levels; prm.items = E * pyr->n_levels; prm.khalves = C / 64; prm.C = C;
   prm.coords = coords; prm.ii = ii; prm.jj = jj; prm.out = out; prm.gmap_pm = gmap_pm;
+  prm.ld_out = ld_out > 0 ? ld_out : kOut * kOut * kPP * pyr->n_levels;
+  DEVO_REQUIRE(prm.ld_out >= kOut * kOut * kPP * pyr->n_levels, DEVO_EINVAL, "corr_lookup_fused: ld_out too small");
   {
     cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)kPP, (cuuint64_t)Np};
     cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * kPP};

@@ -68,15 +68,19 @@ def _cached(t, fn):
     return out
 
 
-def lookup_fused(gmap_pm, levels_pm, scales, coords, ii, jj):
+def lookup_fused(gmap_pm, levels_pm, scales, coords, ii, jj, out=None):
     """fused multi-level lookup on pixel-major buffers.
     gmap_pm [Np,9,C]; levels_pm: list of [Nf,H_l,W_l,C]; coords [E,2,3,3] f32 (level-1 resolution).
+    `out`: optional preallocated [E, >= 49*9*L] buffer (row padding beyond 49*9*L is left untouched).
     returns [E, 49*9*L] (dtype of the features), levels interleaved on the last axis exactly like
     torch.stack(corrs, -1).view(1, E, -1) in devo/devo.py:217."""
     L = len(levels_pm)
     E = coords.shape[0]
     Np, _, C = gmap_pm.shape
-    out = torch.empty(E, 49 * 9 * L, dtype=gmap_pm.dtype, device=gmap_pm.device)
+    if out is None:
+        out = torch.empty(E, 49 * 9 * L, dtype=gmap_pm.dtype, device=gmap_pm.device)
+    elif out.dim() != 2 or out.shape[0] != E or out.shape[1] < 49 * 9 * L or out.stride(1) != 1:
+        raise RuntimeError("cuda_corr.lookup_fused: out must be [E, >= 441*L] with unit inner stride")
     pyr = _lib.PyramidStruct()
     pyr.n_levels = L
     for l, lv in enumerate(levels_pm):
@@ -85,10 +89,10 @@ def lookup_fused(gmap_pm, levels_pm, scales, coords, ii, jj):
         pyr.W[l] = lv.shape[2]
         pyr.scale[l] = float(scales[l])
     import ctypes
-    _lib.check(_lib.lib().devo_corr_lookup_fused(gmap_pm.data_ptr(), ctypes.addressof(pyr), coords.data_ptr(),
-                                                 ii.data_ptr(), jj.data_ptr(), out.data_ptr(),
-                                                 _lib.dtype_code(gmap_pm), Np, levels_pm[0].shape[0], C, E,
-                                                 _lib.stream_ptr(gmap_pm.device)), "corr_lookup_fused")
+    _lib.check(_lib.lib().devo_corr_lookup_fused_ld(gmap_pm.data_ptr(), ctypes.addressof(pyr), coords.data_ptr(),
+                                                    ii.data_ptr(), jj.data_ptr(), out.data_ptr(), out.stride(0),
+                                                    _lib.dtype_code(gmap_pm), Np, levels_pm[0].shape[0], C, E,
+                                                    _lib.stream_ptr(gmap_pm.device)), "corr_lookup_fused")
     return out
 
 

@@ -49,6 +49,11 @@ class UpdateOperator:
         self.imap = torch.zeros(1, self.Np, dim, dtype=feat_dtype, device=dev)
         self.gmap_pm = torch.zeros(self.Np, 9, C, dtype=feat_dtype, device=dev)
         self.levels_pm = [torch.zeros(self.Nf, H // s, W // s, C, dtype=feat_dtype, device=dev) for s in self.levels]
+        # correlation features, rows zero-padded from 441*L to a multiple of 64 so the first Linear of the corr MLP
+        # (K = 882) runs as an aligned tensor-core GEMM; the lookup kernel never touches the padding
+        self.corr_k = 441 * len(self.levels)
+        self.corr_ld = (self.corr_k + 63) // 64 * 64
+        self.corr_buf = torch.zeros(self.E, self.corr_ld, dtype=feat_dtype, device=dev)
         self.lmbda = torch.as_tensor([1e-4], dtype=f32, device=dev)
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
         self.status_sticky = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -107,7 +112,8 @@ class UpdateOperator:
         # (1) reproject: [1,E,2,3,3]
         coords = pops.transform_fused(self.poses, self.patches, self.intrinsics, self.ii, self.jj, self.kk, layout=1)
         # (2) correlation lookup over all levels, output already in the GRU's [E, 882] layout
-        corr = cuda_corr.lookup_fused(self.gmap_pm, self.levels_pm, self.levels, coords[0], self.kk, self.jj)
+        cuda_corr.lookup_fused(self.gmap_pm, self.levels_pm, self.levels, coords[0], self.kk, self.jj, out=self.corr_buf)
+        corr = self.corr_buf if self.fused_gru else self.corr_buf[:, :self.corr_k]
         cur.wait_stream(self._side)
         cur.wait_stream(self._side2)
         # (3) GRU: cached fp16 weights, autocast-identical dtype flow, no host sync
@@ -118,7 +124,7 @@ class UpdateOperator:
                 self.fc, net_out=self.net)
         else:
             net, (delta, weight, _) = self.update.forward_planned(
-                self.net, ctx, corr.view(1, self.E, -1), self.plan_kk, self.plan_ij, self.Np, self.Nf * self.Nf, self.fc)
+                self.net, ctx, corr.reshape(1, self.E, -1), self.plan_kk, self.plan_ij, self.Np, self.Nf * self.Nf, self.fc)
             self.net.copy_(net)
         # (4) BA targets and in-place Gauss-Newton (reuses the kk/jj plan: one sort serves neighbours,
         #     SoftAgg and the Schur grouping)

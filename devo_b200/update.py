@@ -47,6 +47,17 @@ class FrozenCast:
             self._cache[key] = hit
         return hit[1]
 
+    def get_padded_t(self, w, k_padded):
+        """cached low-precision W^T with the input dimension zero-padded to k_padded: [k_padded, out]"""
+        key = (id(w), "padT", k_padded)
+        hit = self._cache.get(key)
+        if hit is None or hit[0] != w._version or hit[1].device != w.device:
+            wp = torch.zeros(w.shape[0], k_padded, dtype=self.dtype, device=w.device)
+            wp[:, :w.shape[1]] = w.detach().to(self.dtype)
+            hit = (w._version, wp.t())
+            self._cache[key] = hit
+        return hit[1]
+
     def linear(self, layer, x):
         return F.linear(x.to(self.dtype), self.get(layer.weight), self.get(layer.bias))
 
@@ -178,7 +189,11 @@ class Update(nn.Module):
         rounded to the autocast dtype.  Same rounding points as autocast; inference only."""
         E, D, hd = net16.shape[1], self.dim, fc.dtype
         lin, lin_relu = fc.linear, fc.linear_relu
-        c = lin_relu(self.corr[0], corr16.reshape(E, -1))
+        c2d = corr16.reshape(E, -1)
+        if c2d.shape[1] == self.corr[0].in_features:
+            c = lin_relu(self.corr[0], c2d)
+        else:   # rows zero-padded to a GEMM-friendly K (e.g. 882 -> 896): multiply by the zero-padded weight
+            c = torch._addmm_activation(fc.get(self.corr[0].bias), c2d, fc.get_padded_t(self.corr[0].weight, c2d.shape[1]), use_gelu=False)
         c = lin(self.corr[2], c)
         c = glue.layernorm_relu_half(c, self.corr[3])
         c = lin(self.corr[5], c)

@@ -86,6 +86,12 @@ int devo_corr_lookup_fused(const void* gmap_pm, const devo_pyramid_t* pyr, const
                            const int64_t* ii, const int64_t* jj, void* out, int dtype,
                            int Np, int Nf, int C, int E, void* stream);
 
+/* same with an explicit output row stride ld_out >= 49*P*P*n_levels (elements): lets the caller keep the
+ * rows padded to a GEMM-friendly K (882 -> 896) for the first Linear of the corr MLP (enet.py:60). */
+int devo_corr_lookup_fused_ld(const void* gmap_pm, const devo_pyramid_t* pyr, const float* coords,
+                              const int64_t* ii, const int64_t* jj, void* out, int ld_out, int dtype,
+                              int Np, int Nf, int C, int E, void* stream);
+
 /* ------------------------------------------------------------------ fastba (cuda_ba) */
 /* Edge-graph analysis shared by neighbors / BA / segment softmax: edges sorted by
  * (ka, kb, edge index).  All outputs are device arrays; any may be NULL.
