@@ -44,6 +44,7 @@ constexpr int kAccThreads = 512;
 constexpr int kSolveThreads = kAccThreads;   // the solve runs inside the last accumulate CTA
 constexpr int kMaxN6 = 150;            // 25 free poses
 constexpr size_t kAccSmemBudget = 200 * 1024;
+constexpr int kMaxGroupsPerCta = 1023;   // group starts cached in shared memory (falls back to global beyond)
 
 // ---- fastba's own SE3 helpers (un-normalised quaternions; ba_cuda.cu:18-156) ----------------
 __device__ __forceinline__ void rot(const float* q, const float* X, float* Y) {
@@ -347,16 +348,38 @@ __device__ void ba_solve_device(unsigned char* smem_raw, float* poses, const dou
     return;
   }
   BA_STAMP(4);
-  // back substitution: w = D^-1 z, then for k = n-1..1 eliminate x_k from all rows i < k (L_ki = A_ki / d_i)
+  // back substitution  x = L^-T D^-1 z.  All threads first turn the stored columns into L (A_ki <- A_ki / d_i)
+  // and z into w = D^-1 z; warp 0 then eliminates x_k from the rows i < k with x held in registers
+  // (lane l owns x[l + 32 m]) and the finished x_k broadcast by shuffle: one shared load per row and step.
+  for (int e = tid; e < n * (n + 1) / 2; e += kSolveThreads) {
+    int gi = (int)floorf((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+    while (gi * (gi + 1) / 2 > e) gi--;
+    while ((gi + 1) * (gi + 2) / 2 <= e) gi++;
+    const int gj = e - gi * (gi + 1) / 2;
+    if (gj < gi) A[e] *= rinv[gj];
+  }
   for (int i = tid; i < n; i += kSolveThreads) y[i] *= rinv[i];
   __syncthreads();
   if (tid < 32) {
+    constexpr int kSlots = (kMaxN6 + 31) / 32;
+    double x[kSlots];
+#pragma unroll
+    for (int mm = 0; mm < kSlots; mm++) x[mm] = (tid + 32 * mm < n) ? y[tid + 32 * mm] : 0.0;
     for (int k = n - 1; k >= 1; k--) {
-      const double xk = y[k];
+      double xk = 0.0;
+#pragma unroll
+      for (int mm = 0; mm < kSlots; mm++)
+        if ((k >> 5) == mm) xk = __shfl_sync(0xffffffffu, x[mm], k & 31);     // warp-uniform branch
       const int rk = k * (k + 1) / 2;
-      for (int i = tid; i < k; i += 32) y[i] -= A[rk + i] * rinv[i] * xk;
-      __syncwarp();
+#pragma unroll
+      for (int mm = 0; mm < kSlots; mm++) {
+        const int i = tid + 32 * mm;
+        if (32 * mm < k && i < k) x[mm] -= A[rk + i] * xk;
+      }
     }
+#pragma unroll
+    for (int mm = 0; mm < kSlots; mm++)
+      if (tid + 32 * mm < n) y[tid + 32 * mm] = x[mm];
   }
   __syncthreads();
   BA_STAMP(5);
@@ -412,6 +435,7 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
   double* zj = coef + RCAP;
   __shared__ int s_batch[3];   // gs, ge, bad
   __shared__ float s_intr[4];
+  __shared__ int s_gstart[kMaxGroupsPerCta + 1];
 
   const int tid = threadIdx.x;
 #ifdef DEVO_BA_TIMING
@@ -432,6 +456,10 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
   const int g1 = min(G, g0 + gpc);
   const float lm = lmbda[0];
   const int nent = (n6 + 1) * (n6 + 2) / 2;
+  const bool gs_cached = (g1 - g0) <= kMaxGroupsPerCta;
+  if (gs_cached)
+    for (int q = tid; q <= g1 - g0; q += kAccThreads) s_gstart[q] = gstart[g0 + q];
+  auto GS = [&](int g) { return gs_cached ? s_gstart[g - g0] : gstart[g]; };
 
   // ---- prologue: apply the previous iteration's depth update to the patches this CTA owns
   if (apply_update) {
@@ -468,9 +496,9 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
   while (gs < g1) {
     // ---- choose a batch of whole groups: <= EB edges, <= GB groups
     if (tid == 0) {
-      const int base = gstart[gs];
+      const int base = GS(gs);
       int ge = gs;
-      while (ge < g1 && (ge - gs) < GB && (gstart[ge + 1] - base) <= EB) ge++;
+      while (ge < g1 && (ge - gs) < GB && (GS(ge + 1) - base) <= EB) ge++;
       s_batch[0] = gs; s_batch[1] = ge; s_batch[2] = (ge == gs);
     }
     __syncthreads();
@@ -479,8 +507,8 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
       if (tid == 0) atomicCAS(status, 0, DEVO_ECAPACITY);
       break;
     }
-    const int ebase = gstart[gs];
-    const int ne = gstart[ge] - ebase;
+    const int ebase = GS(gs);
+    const int ne = GS(ge) - ebase;
     const int ng = ge - gs;
     const int R = 2 * ne + ng;
 
@@ -523,7 +551,7 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
       const int warp = tid >> 5, lane = tid & 31;
       for (int gi = warp; gi < ng; gi += kAccThreads / 32) {
         const int g = gs + gi;
-        const int r0 = 2 * (gstart[g] - ebase), r1 = 2 * (gstart[g + 1] - ebase);
+        const int r0 = 2 * (GS(g) - ebase), r1 = 2 * (GS(g + 1) - ebase);
         double C = 0.0, u = 0.0;
         for (int r = r0; r < r1; r++) {
           const double wz = coef[r] * zj[r];

@@ -51,7 +51,7 @@ constexpr int kProducers = DEVO_CORR_PRODUCERS;   // TMA producer warps (warps 0
 #define DEVO_CORR_MMA_WARPS 1
 #endif
 #ifndef DEVO_CORR_MMA_INTERLEAVE
-#define DEVO_CORR_MMA_INTERLEAVE 2
+#define DEVO_CORR_MMA_INTERLEAVE 1
 #endif
 constexpr int kMmaWarps = DEVO_CORR_MMA_WARPS;     // MMA-issuing warps (items alternate between them)
 constexpr int kMmaInterleave = DEVO_CORR_MMA_INTERLEAVE;   // items (accumulators) one MMA warp issues round-robin

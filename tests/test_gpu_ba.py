@@ -284,3 +284,29 @@ def test_fused_gru_equals_planned_path():
     assert (n1 - n2).abs().mean() < 2e-3
     assert torch.allclose(d1.float(), d2.float(), atol=1e-2) and torch.allclose(w1.float(), w2.float(), atol=5e-3)
     assert torch.equal(out16, n2.half())
+
+
+def test_s22_steady_state_shape():
+    """DEVO steady state ("S22"): 22 source frames, ~45k edges, BA window of 10 poses -- exercises the
+    multi-kernel graph-plan path (E > 16384), multi-batch accumulate CTAs and a 60x60 solve."""
+    from devo_b200 import cuda_ba, fastba
+    nf, m = 22, 96
+    P = ba_problem(n_frames=nf, patches_per_frame=m, seed=22, init="perturbed", noise=0.3)
+    # keep only edges within a 12-frame lifetime window, like PATCH_LIFETIME does
+    keep = (P["ii"] - P["jj"]).abs() <= 12
+    for k in ("ii", "jj", "kk"):
+        P[k] = P[k][keep]
+    P["targets"] = P["targets"][:, keep]
+    P["weights"] = P["weights"][:, keep]
+    E = P["ii"].numel()
+    assert E > 16384
+    ix, jx = fastba.neighbors(P["kk"].cuda(), P["jj"].cuda())
+    rx, ry = onb.neighbors(P["kk"], P["jj"])
+    assert torch.equal(ix.cpu(), rx) and torch.equal(jx.cpu(), ry)
+    t0 = nf - 10
+    poses, patches = _run_ba(P, t0, nf, 2)
+    po, xo, st = _oracle_ba(P, t0, nf, 2)
+    assert st == 0
+    assert (poses[0].double().cpu() - po).abs().max().item() <= 1e-5
+    assert (patches[0, :, 2].double().cpu() - xo[:, 2]).abs().max().item() <= 1e-5
+    assert torch.equal(poses[0, :t0].cpu(), P["poses0"][0, :t0].float())
