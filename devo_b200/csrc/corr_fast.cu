@@ -37,8 +37,9 @@ namespace {
 #ifndef DEVO_CORR_STAGES
 #define DEVO_CORR_STAGES 4
 #endif
-constexpr int kBox = DEVO_CORR_BOX;          // box edge in pixels: 8 + floor-span 3
-constexpr int kBoxPix = kBox * kBox;        // 121 rows used of the M=128 tile
+constexpr int kBox = DEVO_CORR_BOX;          // largest box edge in pixels: 8 + floor-span 3 (box_edge() picks per level)
+constexpr int kBoxPix = kBox * kBox;        // at most 121 rows used of the M=128 tile
+static_assert(kBoxPix <= 128, "box must fit the M=128 tile");
 constexpr int kStages = DEVO_CORR_STAGES;
 #ifndef DEVO_CORR_PRODUCERS
 #define DEVO_CORR_PRODUCERS 3
@@ -73,11 +74,24 @@ constexpr int kRecRing = 16;                // per-item blend records (producer 
 constexpr int kRecWords = 48;               // 9 pixels x {woff, dx, dy, fx, fy} = 45 words, padded
 static_assert(kRecRing >= kProducers + kStages + kEpiGroups, "blend-record ring too small");
 
+#ifdef DEVO_CORR_TIMING
+__device__ long long g_corr_clk[148 * 16];
+#define CT_DECL long long ct_acc[6] = {0, 0, 0, 0, 0, 0}; const long long ct_start = clock64();
+#define CT_WAIT(slot, stmt) do { const long long ct_t0 = clock64(); stmt; ct_acc[slot] += clock64() - ct_t0; } while (0)
+#define CT_STORE(base, n) do { if (lane == 0 && blockIdx.x < 148) { for (int q = 0; q < (n); q++) g_corr_clk[blockIdx.x * 16 + (base) + q] = ct_acc[q]; \
+                               g_corr_clk[blockIdx.x * 16 + (base) + (n)] = clock64() - ct_start; } } while (0)
+#else
+#define CT_DECL
+#define CT_WAIT(slot, stmt) stmt
+#define CT_STORE(base, n)
+#endif
+
 struct FastParams {
   int E, L, items, khalves;                 // khalves = C / 64
   int H[DEVO_MAX_LEVELS], W[DEVO_MAX_LEVELS];
   float scale[DEVO_MAX_LEVELS];
   float inv_scale[DEVO_MAX_LEVELS];         // 1/scale when that is exact (power of two), else 0 => divide
+  int box[DEVO_MAX_LEVELS];                 // TMA box edge of the level (<= kBox), see box_edge()
   int ld_out;                               // output row stride in elements (>= 49*9*L)
   const float* coords;
   const int64_t* ii;
@@ -372,16 +386,20 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
     if (warp == 0) {
       for (; issued < min(nb, 2); issued++) issue_coords(issued);
     }
-    const uint32_t bytes = (uint32_t)khalves * (kBoxPix * 128 + kPP * 128);
     ItemCursor c;
     c.init(first, L, warp);
+    CT_DECL
     uint32_t stage = warp % kStages, phase = (warp / kStages) & 1;
     for (; c.it < nitems; c.advance(kProducers, L)) {
       if (warp == 0) {
         const int b = (c.e - eb0) >> 3;
         if (b + 2 > issued && issued < nb) { issue_coords(issued); issued++; }   // stay one batch ahead
       }
-      Geo g = make_geo(cv.edge(c.e), prm.scale[c.l], prm.inv_scale[c.l], lane);
+      const float* cs_edge;
+      CT_WAIT(0, cs_edge = cv.edge(c.e));
+      Geo g = make_geo(cs_edge, prm.scale[c.l], prm.inv_scale[c.l], lane);
+      const int bx = prm.box[c.l];
+      const uint32_t bytes = (uint32_t)khalves * (uint32_t)(bx * bx * 128 + kPP * 128);
       {
         // blend record of this item for the epilogue: lane p owns pixel p.  Slot reuse needs no "empty" barrier:
         // a producer writing item R has passed empty[] for item R-kProducers, so the MMA warp finished item
@@ -389,7 +407,7 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
         uint32_t* rec = recs + (c.it & (kRecRing - 1)) * kRecWords;
         if (lane < kPP) {
           const int ox = g.fx - kRadius - g.x0, oy = g.fy - kRadius - g.y0;   // window origin inside the box (>= 0)
-          rec[lane] = (uint32_t)((ox + 8 <= kBox && oy + 8 <= kBox) ? oy * kBox + ox : -1);
+          rec[lane] = (uint32_t)((ox + 8 <= bx && oy + 8 <= bx) ? oy * bx + ox : -1);
           rec[kPP + lane] = __float_as_uint(g.dx);
           rec[2 * kPP + lane] = __float_as_uint(g.dy);
           rec[3 * kPP + lane] = (uint32_t)g.fx;
@@ -403,7 +421,7 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
         const int patch = __shfl_sync(0xffffffffu, cv.patch(), 0);
         const uint32_t st = smem_u32(tiles) + stage * kStageBytes;
         const uint32_t fb = smem_u32(&full[stage]);
-        mbar_wait(&empty[stage], phase ^ 1);
+        CT_WAIT(1, mbar_wait(&empty[stage], phase ^ 1));
         mbar_arrive_expect_tx_elect(fb, bytes);
         tma_load_4d_elect(st, tm, fb, 0, g.x0, g.y0, frame);
         tma_load_3d_elect(st + 2 * kATileBytes, &tm_g, fb, 0, 0, patch);
@@ -415,6 +433,7 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
       stage += kProducers;
       while (stage >= kStages) { stage -= kStages; phase ^= 1; }
     }
+    if (warp == 0) CT_STORE(0, 2);
   } else if (warp < kProducers + kMmaWarps) {
     // =============================== MMA issuers (items alternate between the kMmaWarps warps) ===========
     // instruction descriptor: D=f32, A=B=f16|bf16, K-major both, N=16, M=128
@@ -428,6 +447,7 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
       // MMAs that accumulate into the same TMEM tile execute back to back, so kMmaInterleave items with
       // different accumulators are issued round-robin, K-slice by K-slice.
       const int m = warp - kProducers;
+      CT_DECL
       uint32_t stage = (m * kMmaInterleave) % kStages, phase = ((m * kMmaInterleave) / kStages) & 1;
       uint32_t acc = (m * kMmaInterleave) % kEpiGroups, aphase = ((m * kMmaInterleave) / kEpiGroups) & 1;
       for (int it = m * kMmaInterleave; it < nitems; it += kMmaWarps * kMmaInterleave) {
@@ -439,8 +459,8 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
 #pragma unroll
           for (int g = 0; g < kMmaInterleave; g++) {
             if (g < n) {
-              mbar_wait(&tempty[ac], aph ^ 1);
-              mbar_wait(&full[st], ph);
+              CT_WAIT(0, mbar_wait(&tempty[ac], aph ^ 1));
+              CT_WAIT(1, mbar_wait(&full[st], ph));
             }
             ad[g] = ad0 + (uint64_t)(st * (kStageBytes >> 4));
             bd[g] = bd0 + (uint64_t)(st * (kStageBytes >> 4));
@@ -478,6 +498,7 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
           if (++acc == kEpiGroups) { acc = 0; aphase ^= 1; }
         }
       }
+      if (m == 0) CT_STORE(3, 2);
     }
     __syncwarp();
   } else if (warp < kFirstEpiWarp) {
@@ -496,29 +517,31 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
     const bool owner = et < 14 * kPP;
     const int p = owner ? et % kPP : 0;
     const int s14 = et / kPP;
-    int soff[4], ooff[4];
+    int sxo[4], syo[4], ooff[4];       // window offset (xo, yo) of output k; sxo < 0: no output
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const int o = s14 + 14 * k;
       const int yo = o / kOut, xo = o - yo * kOut;
-      soff[k] = (owner && o < kOut * kOut) ? yo * kBox + xo : -1;
+      sxo[k] = (owner && o < kOut * kOut) ? xo : -1;
+      syo[k] = yo;
       ooff[k] = ((xo * kOut + yo) * kPP + p) * L;
     }
     uint32_t aphase = 0;
     int buf = 0;
     ItemCursor c;
     c.init(first, L, grp);
+    CT_DECL
     for (; c.it < nitems; c.advance(kEpiGroups, L)) {
       const int e = c.e, l = c.l;
       // blend record written by the producer warp of this item (direct release/acquire through rfull)
-      mbar_wait(&rfull[c.it & (kRecRing - 1)], (uint32_t)(c.it / kRecRing) & 1u);
+      CT_WAIT(0, mbar_wait(&rfull[c.it & (kRecRing - 1)], (uint32_t)(c.it / kRecRing) & 1u));
       const uint32_t* rec = recs + (c.it & (kRecRing - 1)) * kRecWords;
       const int pw = (int)rec[p];
       const float dx = __uint_as_float(rec[kPP + p]), dy = __uint_as_float(rec[2 * kPP + p]);
       const int pfx = (int)rec[3 * kPP + p], pfy = (int)rec[4 * kPP + p];
       const float w00 = (1.f - dx) * (1.f - dy), w01 = dx * (1.f - dy), w10 = (1.f - dx) * dy, w11 = dx * dy;
 
-      mbar_wait(&tfull[grp], aphase);
+      CT_WAIT(1, mbar_wait(&tfull[grp], aphase));
       tc_fence_after();
       uint32_t v[16];
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + grp * 16;
@@ -527,23 +550,24 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
           : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
             "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
           : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      CT_WAIT(2, asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[grp]);   // accumulator stage free for the MMA warp
       float* vs = vbase + buf * kVsFloats;
 #pragma unroll
       for (int q = 0; q < kPP; q++) vs[q * 128 + row] = __uint_as_float(v[q]);
-      asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");   // the 4 warps of this group only
+      CT_WAIT(3, asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"));   // the 4 warps of this group only
 
       T* orow = out + (size_t)e * prm.ld_out + l;
       if (pw >= 0) {
         const float* sp = vs + p * 128 + pw;
+        const int bx = prm.box[l];        // accumulator row of box pixel (y, x) is y * bx + x
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-          if (soff[k] >= 0) {
-            const float* s4 = sp + soff[k];
-            const float r = w00 * s4[0] + w01 * s4[1] + w10 * s4[kBox] + w11 * s4[kBox + 1];
+          if (sxo[k] >= 0) {
+            const float* s4 = sp + syo[k] * bx + sxo[k];
+            const float r = w00 * s4[0] + w01 * s4[1] + w10 * s4[bx] + w11 * s4[bx + 1];
             orow[ooff[k]] = from_f<T>(r);
           }
         }
@@ -569,6 +593,7 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
       buf ^= 1;
       aphase ^= 1;
     }
+    if (warp == kFirstEpiWarp) CT_STORE(6, 4);
   }
 
   tc_fence_before();
@@ -695,6 +720,14 @@ static int make_map(CUtensorMap* m, int dtype, int rank, const void* ptr, const 
   return DEVO_OK;
 }
 
+// Box edge for a pyramid level: the 7x7 window plus the bilinear neighbour spans 8 pixels from the floor of a
+// patch pixel, and the floors of the 3x3 patch pixels (2/scale apart corner to corner) differ by at most
+// floor(span)+1.  A 1.5x stretch is budgeted; pixels that still do not fit take the direct path in the epilogue.
+static int box_edge(float scale) {
+  const int b = 8 + (int)floorf(3.0f / scale) + 1;
+  return b < 9 ? 9 : (b > kBox ? kBox : b);
+}
+
 template <typename T>
 static int launch_fast(const CUtensorMap* maps, const FastParams& prm, cudaStream_t s) {
   const size_t smem = 1024 + (size_t)kStages * kStageBytes + (size_t)kEpiGroups * 2 * kVsFloats * sizeof(float) +
@@ -792,7 +825,8 @@ int devo_corr_lookup_fused_ld(const void* gmap_pm, const devo_pyramid_t* pyr, co
     }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)pyr->W[ls], (cuuint64_t)pyr->H[ls], (cuuint64_t)Nf};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * pyr->W[ls], (cuuint64_t)C * 2 * pyr->W[ls] * pyr->H[ls]};
-    cuuint32_t box[4] = {64, kBox, kBox, 1};
+    prm.box[l] = box_edge(pyr->scale[ls]);
+    cuuint32_t box[4] = {64, (cuuint32_t)prm.box[l], (cuuint32_t)prm.box[l], 1};
     int rc = make_map(&maps[1 + l], dtype, 4, pyr->level[ls], dims, strides, box);
     if (rc != DEVO_OK) return rc;
   }
@@ -800,5 +834,9 @@ int devo_corr_lookup_fused_ld(const void* gmap_pm, const devo_pyramid_t* pyr, co
   if (dtype == DEVO_F16) return launch_fast<__half>(maps, prm, s);
   return launch_fast<__nv_bfloat16>(maps, prm, s);
 }
+
+#ifdef DEVO_CORR_TIMING
+void devo_corr_debug_clocks(long long* out) { cudaMemcpyFromSymbol(out, g_corr_clk, sizeof(long long) * 148 * 16); }
+#endif
 
 }  // extern "C"
