@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
     double* __restrict__ Qg, double* __restrict__ Ug, double* __restrict__ Ekg,
     double* __restrict__ partials, double* dX, int32_t* __restrict__ ticket,
     int32_t* __restrict__ status, int E, int PP, int centre, int t0, int nfree, int n_poses,
-    int EB, int GB, int apply_update, int do_accumulate, int itr) {
+    int EB, int GB, int apply_update, int do_accumulate, int itr, double* __restrict__ sys_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const float* poses = poses_rw;
   const int n6 = 6 * nfree;
@@ -446,6 +446,10 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
     if (do_accumulate) {
       const int nent = (n6 + 1) * (n6 + 2) / 2;
       for (int q = tid; q < nent; q += kAccThreads) partials[(size_t)blockIdx.x * nent + q] = 0.0;
+      if (sys_out && blockIdx.x == 0) {   // sharded form: peers must see a system and this rank's failure
+        for (int q = tid; q < nent; q += kAccThreads) sys_out[q] = 0.0;
+        if (tid == 0) sys_out[nent] = 1.0;
+      }
     }
     return;
   }
@@ -625,7 +629,16 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
       if (s_batch[1] == ngrp - 1) {                          // last group: solve
         if (tid == 0) ticket[0] = 0;
         __threadfence();
-        if (n6 <= 44) ba_solve_device<2>(smem_raw, poses_rw, gpart, dX, status, ngrp, t0, nfree, itr);
+        if (sys_out) {
+          // edge-sharded form: publish this rank's partial of [S|y] (fixed summation order, no
+          // damping yet) + its status word; the all-reduce over ranks and devo_ba_sharded_solve follow.
+          for (int idx = tid; idx < nent; idx += kAccThreads) {
+            double sacc = 0.0;
+            for (int p = 0; p < ngrp; p++) sacc += __ldcg(&gpart[(size_t)p * nent + idx]);
+            sys_out[idx] = sacc;
+          }
+          if (tid == 0) sys_out[nent] = (*(volatile int32_t*)status != 0) ? 1.0 : 0.0;
+        } else if (n6 <= 44) ba_solve_device<2>(smem_raw, poses_rw, gpart, dX, status, ngrp, t0, nfree, itr);
         else if (n6 <= 88) ba_solve_device<8>(smem_raw, poses_rw, gpart, dX, status, ngrp, t0, nfree, itr);
         else ba_solve_device<(((kMaxN6 + 1) * (kMaxN6 + 2) / 2) + kSolveThreads - 1) / kSolveThreads>(
             smem_raw, poses_rw, gpart, dX, status, ngrp, t0, nfree, itr);
@@ -633,6 +646,20 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
       }
     }
   }
+}
+
+// ---- stand-alone solve for the edge-sharded form: `sys` = [S|y] already summed over ranks ------------------
+template <int KENT>
+__global__ void __launch_bounds__(kSolveThreads, 1) ba_solve_kernel(float* poses, const double* __restrict__ sys,
+                                                                    double* dX, int32_t* status, int t0, int nfree, int itr) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n6 = 6 * nfree;
+  const int nent = (n6 + 1) * (n6 + 2) / 2;
+  if (sys[nent] != 0.0) {                  // some rank failed in accumulate: every rank stops here, identically
+    if (threadIdx.x == 0) atomicCAS(status, 0, DEVO_ECAPACITY);
+    return;
+  }
+  ba_solve_device<KENT>(smem_raw, poses, sys, dX, status, 1, t0, nfree, itr);
 }
 
 }  // namespace
@@ -740,7 +767,7 @@ static int launch_accumulate(const BaLayout& L, char* w, float* poses, float* pa
                              const int64_t* jj, const int64_t* kk, int32_t* status, int E, int PP, int centre,
                              int t0, int nfree, int n_poses, int EB, int GB, size_t smem, int apply_update,
                              int do_accumulate, int itr, cudaStream_t s, const int32_t* perm_p, const int32_t* gstart_p,
-                             const int64_t* gkey_p, const int32_t* ngroups_p) {
+                             const int64_t* gkey_p, const int32_t* ngroups_p, double* sys_out = nullptr) {
   static size_t configured = 0;
   if (smem > configured) {
     DEVO_CUDA(cudaFuncSetAttribute(ba_accumulate_kernel<EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -749,7 +776,7 @@ static int launch_accumulate(const BaLayout& L, char* w, float* poses, float* pa
   ba_accumulate_kernel<EPT><<<L.grid, kAccThreads, smem, s>>>(
       poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, perm_p, gstart_p, gkey_p, ngroups_p,
       (double*)(w + L.Q), (double*)(w + L.U), (double*)(w + L.Ek), (double*)(w + L.partials),
-      (double*)(w + L.dX), (int32_t*)(w + L.ticket), status, E, PP, centre, t0, nfree, n_poses, EB, GB, apply_update, do_accumulate, itr);
+      (double*)(w + L.dX), (int32_t*)(w + L.ticket), status, E, PP, centre, t0, nfree, n_poses, EB, GB, apply_update, do_accumulate, itr, sys_out);
   DEVO_LAUNCH_CHECK("ba_accumulate");
   return DEVO_OK;
 }
@@ -832,6 +859,106 @@ static int ba_forward_impl(float* poses, float* patches, const float* intrinsics
   ACC_DISPATCH(1, 0, iterations);   // final depth update only
 #undef ACC
 #undef ACC_DISPATCH
+  return DEVO_OK;
+}
+
+// ---- edge-sharded BA: one frame graph split over ranks by owning patch ---------------------------
+// Depth blocks C,u and the columns of E are rank-local, so the Schur complement distributes:
+//   S = sum_g (B_g - E_g Q_g E_g^T),  y = sum_g (v_g - E_g Q_g u_g).
+// Per Gauss-Newton iteration: devo_ba_sharded_accumulate (local edges -> sys_out, fp64) -> ONE all-reduce of
+// devo_ba_system_doubles(nfree) doubles over the ranks (NCCL, host side) -> devo_ba_sharded_solve (identical on every
+// rank: damping, LDL^T, retraction of the replicated poses).  The depth update of the local patches is applied in the
+// prologue of the next accumulate call (flags bit 0) or by a final call with flags = 1 (no accumulate).
+size_t devo_ba_system_doubles(int n_free_poses) {
+  const int n6 = 6 * (n_free_poses > 0 ? n_free_poses : 0);
+  return (size_t)(n6 + 1) * (n6 + 2) / 2 + 1;   // upper triangle of [S|y] (+ the y^T y corner) + a status word
+}
+
+int devo_ba_sharded_accumulate(float* poses, float* patches, const float* intrinsics, const float* target,
+                               const float* weight, const float* lmbda, const int64_t* ii, const int64_t* jj,
+                               const int64_t* kk, int E, int n_poses, int n_patches, int P, int t0, int t1, int itr,
+                               int flags, double* sys_out, void* workspace, size_t workspace_bytes, int32_t* status,
+                               void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const int apply_update = flags & 1, do_accumulate = (flags >> 1) & 1, replan = (flags >> 2) & 1;
+  DEVO_REQUIRE(status != nullptr, DEVO_EINVAL, "ba_sharded_accumulate: status pointer is NULL");
+  const int nfree = t1 - t0;
+  DEVO_REQUIRE(nfree > 0, DEVO_EINVAL, "ba_sharded_accumulate: needs at least one free pose (structure-only BA has no exchange)");
+  DEVO_REQUIRE(P >= 1 && P <= 8, DEVO_EINVAL, "ba_sharded_accumulate: patch size %d unsupported", P);
+  DEVO_REQUIRE(6 * nfree <= kMaxN6, DEVO_ECAPACITY, "ba_sharded_accumulate: %d free poses exceed the solver capacity (%d)",
+               nfree, kMaxN6 / 6);
+  DEVO_REQUIRE(t0 >= 0 && t1 <= n_poses, DEVO_EINVAL, "ba_sharded_accumulate: pose window [%d,%d) outside [0,%d)", t0, t1, n_poses);
+  DEVO_REQUIRE(!do_accumulate || sys_out != nullptr, DEVO_EINVAL, "ba_sharded_accumulate: sys_out is NULL");
+  BaLayout L = ba_layout(E, nfree);
+  if (replan) DEVO_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), s));
+  if (E <= 0) {   // a rank without edges contributes a zero system
+    if (do_accumulate) DEVO_CUDA(cudaMemsetAsync(sys_out, 0, devo_ba_system_doubles(nfree) * 8, s));
+    return DEVO_OK;
+  }
+  DEVO_REQUIRE(workspace && workspace_bytes >= L.total, DEVO_EWORKSPACE,
+               "ba_sharded_accumulate: workspace too small (%zu < %zu)", workspace_bytes, L.total);
+  char* w = (char*)workspace;
+  const int PP = P * P;
+  const int centre = (P == 3) ? 4 : (1 * P + 1 < PP ? 1 * P + 1 : 0);
+  int rc = DEVO_OK;
+  if (replan) {
+    rc = devo_graph_plan(kk, jj, E, n_patches, n_poses, (int32_t*)(w + L.perm), nullptr, (int32_t*)(w + L.gstart),
+                         (int64_t*)(w + L.gkey), (int32_t*)(w + L.ngroups), nullptr, nullptr, w + L.plan_ws,
+                         L.plan_bytes, stream);
+    if (rc != DEVO_OK) return rc;
+    DEVO_CUDA(cudaMemsetAsync(w + L.ticket, 0, 4 * 32, s));
+  }
+  const int n6 = L.n6, LD = n6 + 1;
+  int rows_cap = (int)(kAccSmemBudget / ((size_t)(LD + 2) * 8));
+  int EB = rows_cap * 2 / 5;
+  if (EB > kAccThreads) EB = kAccThreads;
+  int GB = rows_cap - 2 * EB;
+  if (GB > EB) GB = EB;
+  DEVO_REQUIRE(EB >= 8 && GB >= 1, DEVO_ECAPACITY, "ba_sharded_accumulate: system too large for shared memory");
+  const size_t smem_acc = (size_t)(2 * EB + GB) * (LD + 2) * 8;
+  const int ept = (L.nent + kAccThreads - 1) / kAccThreads;
+  DEVO_REQUIRE(ept <= 24, DEVO_ECAPACITY, "ba_sharded_accumulate: system too large (%d entries)", L.nent);
+#define ACCS(EPT_)                                                                                                \
+  launch_accumulate<EPT_>(L, w, poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, status, E, PP, centre, \
+                          t0, nfree, n_poses, EB, GB, smem_acc, apply_update, do_accumulate, itr, s,                \
+                          (const int32_t*)(w + L.perm), (const int32_t*)(w + L.gstart), (const int64_t*)(w + L.gkey), \
+                          (const int32_t*)(w + L.ngroups), sys_out)
+  if (ept <= 2) rc = ACCS(2);
+  else if (ept <= 4) rc = ACCS(4);
+  else if (ept <= 8) rc = ACCS(8);
+  else if (ept <= 16) rc = ACCS(16);
+  else rc = ACCS(24);
+#undef ACCS
+  return rc;
+}
+
+int devo_ba_sharded_solve(float* poses, const double* sys, int E, int n_poses, int t0, int t1, int itr, void* workspace,
+                          size_t workspace_bytes, int32_t* status, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nfree = t1 - t0;
+  DEVO_REQUIRE(status != nullptr && sys != nullptr, DEVO_EINVAL, "ba_sharded_solve: NULL pointer");
+  DEVO_REQUIRE(nfree > 0 && 6 * nfree <= kMaxN6, DEVO_ECAPACITY, "ba_sharded_solve: %d free poses unsupported", nfree);
+  DEVO_REQUIRE(t0 >= 0 && t1 <= n_poses, DEVO_EINVAL, "ba_sharded_solve: pose window [%d,%d) outside [0,%d)", t0, t1, n_poses);
+  BaLayout L = ba_layout(E, nfree);   // same E as the accumulate calls: dX is read back by their depth-update prologue
+  DEVO_REQUIRE(workspace && workspace_bytes >= L.total, DEVO_EWORKSPACE,
+               "ba_sharded_solve: workspace too small (%zu < %zu)", workspace_bytes, L.total);
+  const int n6 = 6 * nfree;
+  const size_t smem = ((size_t)n6 * (n6 + 1) / 2 + 4 * n6 + 8) * 8;
+  double* dX = (double*)((char*)workspace + L.dX);
+#define SOLVE(K_)                                                                                              \
+  do {                                                                                                         \
+    static size_t configured = 0;                                                                              \
+    if (smem > configured) {                                                                                   \
+      DEVO_CUDA(cudaFuncSetAttribute(ba_solve_kernel<K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      configured = smem;                                                                                       \
+    }                                                                                                          \
+    ba_solve_kernel<K_><<<1, kSolveThreads, smem, s>>>(poses, sys, dX, status, t0, nfree, itr);                \
+  } while (0)
+  if (n6 <= 44) SOLVE(2);
+  else if (n6 <= 88) SOLVE(8);
+  else SOLVE((((kMaxN6 + 1) * (kMaxN6 + 2) / 2) + kSolveThreads - 1) / kSolveThreads);
+#undef SOLVE
+  DEVO_LAUNCH_CHECK("ba_sharded_solve");
   return DEVO_OK;
 }
 

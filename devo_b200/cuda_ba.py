@@ -82,6 +82,81 @@ def forward(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, t0, t
     return []
 
 
+class ShardedBA:
+    """One rank's side of an edge-sharded Gauss-Newton BA: this rank holds only the edges it owns -- all
+    edges of a patch live on one rank (devo_b200.dist.shard_edges_by_patch) -- and the full, replicated
+    `poses`/`patches`.  Per iteration: `accumulate(itr)` (local edges -> `self.system`, fp64 partial of the reduced
+    system [S|y] + a status word) -> ONE all-reduce(sum) of `self.system` over the ranks -> `solve(itr)` (identical on
+    every rank: damping, LDL^T, pose retraction).  `finish()` applies the last depth update to the local patches.
+    Nothing synchronises with the host."""
+
+    def __init__(self, poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, t0, t1, status=None):
+        self.poses = _f32c(poses, "poses", True)
+        self.patches = _f32c(patches, "patches", True)
+        self.intrinsics = _f32c(intrinsics, "intrinsics")
+        self.target = _f32c(target, "target")
+        self.weight = _f32c(weight, "weight")
+        self.lmbda = _f32c(lmbda.reshape(-1), "lmbda")
+        self.ii, self.jj, self.kk = _idx(ii, "ii"), _idx(jj, "jj"), _idx(kk, "kk")
+        E = self.E = self.ii.numel()
+        if self.target.numel() != 2 * E or self.weight.numel() != 2 * E or self.jj.numel() != E or self.kk.numel() != E:
+            raise RuntimeError("cuda_ba.ShardedBA: target/weight/ii/jj/kk sizes disagree")
+        self.t0, self.t1 = int(t0), int(t1)
+        if self.t1 - self.t0 <= 0:
+            raise RuntimeError("cuda_ba.ShardedBA: needs a free pose (structure-only BA has nothing to exchange)")
+        self.P = self.patches.shape[-1]
+        self.n_poses = self.poses.numel() // 7
+        self.n_patches = self.patches.numel() // (3 * self.P * self.P)
+        dev = self.poses.device
+        L = _lib.lib()
+        self.status = status if status is not None else torch.zeros(1, dtype=torch.int32, device=dev)
+        self._ws = torch.empty(max(L.devo_ba_workspace(E, self.t1 - self.t0), 256), dtype=torch.uint8, device=dev)
+        self.system = torch.zeros(L.devo_ba_system_doubles(self.t1 - self.t0), dtype=torch.float64, device=dev)
+
+    def _acc(self, itr, flags):
+        L = _lib.lib()
+        _lib.check(L.devo_ba_sharded_accumulate(
+            self.poses.data_ptr(), self.patches.data_ptr(), self.intrinsics.data_ptr(), self.target.data_ptr(),
+            self.weight.data_ptr(), self.lmbda.data_ptr(), self.ii.data_ptr(), self.jj.data_ptr(), self.kk.data_ptr(),
+            self.E, self.n_poses, self.n_patches, self.P, self.t0, self.t1, int(itr), int(flags), self.system.data_ptr(),
+            self._ws.data_ptr(), self._ws.numel(), self.status.data_ptr(), _lib.stream_ptr(self.poses.device)),
+            "ba_sharded_accumulate")
+
+    def accumulate(self, itr):
+        self._acc(itr, 2 | (1 if itr > 0 else 0) | (4 if itr == 0 else 0))
+        return self.system
+
+    def solve(self, itr):
+        _lib.check(_lib.lib().devo_ba_sharded_solve(
+            self.poses.data_ptr(), self.system.data_ptr(), self.E, self.n_poses, self.t0, self.t1, int(itr),
+            self._ws.data_ptr(), self._ws.numel(), self.status.data_ptr(), _lib.stream_ptr(self.poses.device)),
+            "ba_sharded_solve")
+
+    def finish(self, iterations):
+        self._acc(iterations, 1)
+
+
+def forward_sharded(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, t0, t1, iterations, group=None,
+                    status=None):
+    """fastba.BA for ONE frame graph split over the ranks of `group` (north_star: "a single NCCL all-reduce of the
+    pose-block Hessian"): see ShardedBA.  The all-reduce runs on NCCL over NVLink (fp64 sum, 7.2 KB at 7 free poses);
+    poses stay bitwise replicated; only the depths of the local patches change (dist.gather_patch_depths exchanges
+    them when the caller needs all of them).  Returns the device status tensor."""
+    import torch.distributed as dist
+    if int(t1) - int(t0) <= 0:      # structure-only BA: depths are rank-local, nothing to exchange
+        return forward_async(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, t0, t1, iterations, status=status)
+    ba = ShardedBA(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, t0, t1, status=status)
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    for itr in range(int(iterations)):
+        ba.accumulate(itr)
+        if multi:
+            dist.all_reduce(ba.system, op=dist.ReduceOp.SUM, group=group)
+        ba.solve(itr)
+    if iterations > 0:
+        ba.finish(int(iterations))
+    return ba.status
+
+
 def neighbors(ii, jj):
     """-> [ix, jx] int64 CUDA tensors (previous / next edge of the same ii in jj order, -1 at the ends)"""
     ii, jj = _idx(ii, "ii"), _idx(jj, "jj")

@@ -31,6 +31,45 @@ def shard_sequences(n_sequences, rank, world):
     return list(range(start, start + base + (1 if rank < rem else 0)))
 
 
+def patch_owner(n_patches, world):
+    """owner rank of every patch: contiguous, balanced blocks (= source-frame blocks when patches are frame-major,
+    SURVEY 8e).  int64 [n_patches]"""
+    base, rem = divmod(n_patches, world)
+    sizes = torch.tensor([base + (1 if r < rem else 0) for r in range(world)], dtype=torch.int64)
+    return torch.repeat_interleave(torch.arange(world, dtype=torch.int64), sizes)
+
+
+def patch_range(n_patches, rank, world):
+    base, rem = divmod(n_patches, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_edges_by_patch(kk, n_patches, rank, world):
+    """indices (ascending, so the edge order inside a patch is kept) of the edges owned by `rank`: every edge of a
+    patch lives on the patch's owner, which keeps the depth blocks C,u and the columns of E rank-local."""
+    lo, hi = patch_range(n_patches, rank, world)
+    return torch.nonzero((kk >= lo) & (kk < hi)).reshape(-1)
+
+
+def gather_patch_depths(patches, n_patches, group=None):
+    """after a sharded BA: every rank broadcasts the depth channel of the patches it owns (in place on `patches`
+    [1,Np,3,P,P] / [Np,3,P,P]) so the replicas agree again.  Bit-exact: owners' values are copied, not summed."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return patches
+    world = dist.get_world_size(group)
+    if world == 1:
+        return patches
+    p = patches.view(-1, 3, patches.shape[-2], patches.shape[-1])
+    for r in range(world):
+        lo, hi = patch_range(n_patches, r, world)
+        if hi > lo:
+            buf = p[lo:hi, 2].contiguous()
+            dist.broadcast(buf, src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+            p[lo:hi, 2] = buf
+    return patches
+
+
 def max_over_ranks(value, device=None):
     """device-timed durations are combined as the max over ranks (never wall clock)"""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:

@@ -127,6 +127,24 @@ int devo_ba_forward_planned(float* poses, float* patches, const float* intrinsic
                             int E, int n_poses, int n_patches, int P, int t0, int t1, int iterations,
                             const int32_t* perm, const int32_t* gstart, const int64_t* gkey, const int32_t* ngroups,
                             void* workspace, size_t workspace_bytes, int32_t* status, void* stream);
+/* Edge-sharded form of cuda_ba.forward for ONE frame graph split over several GPUs by owning patch (the reference has
+ * no such path: train.py:90-93 runs one sequence per DDP rank; BASELINE.json north_star / SURVEY 8e ask for it).
+ * Per Gauss-Newton iteration, on every rank:
+ *   devo_ba_sharded_accumulate  local edges -> sys_out, fp64 [devo_ba_system_doubles(t1-t0)]: this rank's partial of the
+ *                               reduced system [S|y] (upper triangle, undamped) + a status word
+ *   all-reduce(sum) of sys_out over the ranks  (the single collective; host side, NCCL)
+ *   devo_ba_sharded_solve       damping, LDL^T, pose retraction -- identical on every rank (poses are replicated)
+ * flags: bit0 = apply the previous iteration's depth update to the local patches first, bit1 = accumulate,
+ * bit2 = first call for this edge list (re-plan, reset status).  Finish with flags=1 (depth update only).
+ * Same workspace (devo_ba_workspace(E, t1-t0)) and E for all calls of one BA. */
+size_t devo_ba_system_doubles(int n_free_poses);
+int devo_ba_sharded_accumulate(float* poses, float* patches, const float* intrinsics, const float* target,
+                               const float* weight, const float* lmbda,
+                               const int64_t* ii, const int64_t* jj, const int64_t* kk,
+                               int E, int n_poses, int n_patches, int P, int t0, int t1, int itr, int flags,
+                               double* sys_out, void* workspace, size_t workspace_bytes, int32_t* status, void* stream);
+int devo_ba_sharded_solve(float* poses, const double* sys, int E, int n_poses, int t0, int t1, int itr,
+                          void* workspace, size_t workspace_bytes, int32_t* status, void* stream);
 /* cuda_ba.reproject (devo/fastba/ba.cpp:155, ba_cuda.cu:368-418,543-575) -> coords [E,2,P,P] f32 */
 int devo_reproject(const float* poses, const float* patches, const float* intrinsics,
                    const int64_t* ii, const int64_t* jj, const int64_t* kk, float* coords,

@@ -310,3 +310,110 @@ def test_s22_steady_state_shape():
     assert (poses[0].double().cpu() - po).abs().max().item() <= 1e-5
     assert (patches[0, :, 2].double().cpu() - xo[:, 2]).abs().max().item() <= 1e-5
     assert torch.equal(poses[0, :t0].cpu(), P["poses0"][0, :t0].float())
+
+
+# ---- edge-sharded BA: one frame graph split over ranks by owning patch ------------------------------
+def _sharded_inputs(P, rank, world, dev):
+    from devo_b200 import dist as d
+    Np = P["patches0"].shape[1]
+    sel = d.shard_edges_by_patch(P["kk"], Np, rank, world)
+    f = lambda t: t.float().to(dev).contiguous()
+    return dict(poses=f(P["poses0"]), patches=f(P["patches0"]), intr=f(P["intrinsics"]),
+                target=f(P["targets"][:, sel]), weight=f(P["weights"][:, sel]),
+                ii=P["ii"][sel].to(dev), jj=P["jj"][sel].to(dev), kk=P["kk"][sel].to(dev), sel=sel)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("nf,m,t0,iters", [(8, 96, 1, 2), (5, 7, 2, 3)])
+def test_sharded_ba_simulated_ranks_match_single_gpu(world, nf, m, t0, iters):
+    """`world` ranks simulated on one GPU: each owns the edges of its patch block, the all-reduce is a plain sum of the
+    per-rank systems.  Result must equal the single-GPU fastba.BA (same arithmetic, fp64 partial sums regrouped) and
+    the poses must stay bitwise replicated across ranks."""
+    from devo_b200 import cuda_ba, dist as d
+    P = ba_problem(n_frames=nf, patches_per_frame=m, seed=77 + nf, init="perturbed", noise=0.3)
+    ref_poses, ref_patches = _run_ba(P, t0, nf, iters)
+    lm = torch.tensor([1e-4], device="cuda")
+    ranks = []
+    for r in range(world):
+        I = _sharded_inputs(P, r, world, "cuda")
+        I["ba"] = cuda_ba.ShardedBA(I["poses"], I["patches"], I["intr"], I["target"], I["weight"], lm, I["ii"], I["jj"], I["kk"], t0, nf)
+        ranks.append(I)
+    for itr in range(iters):
+        total = sum(I["ba"].accumulate(itr).clone() for I in ranks)
+        for I in ranks:
+            I["ba"].system.copy_(total)
+            I["ba"].solve(itr)
+    for I in ranks:
+        I["ba"].finish(iters)
+        assert int(I["ba"].status.item()) == 0
+    Np = nf * m
+    for r, I in enumerate(ranks):
+        assert torch.equal(I["poses"], ranks[0]["poses"])                       # replicated, bitwise
+        assert (I["poses"] - ref_poses).abs().max().item() <= 1e-6
+        lo, hi = d.patch_range(Np, r, world)
+        assert (I["patches"][0, lo:hi] - ref_patches[0, lo:hi]).abs().max().item() <= 1e-6 if hi > lo else True
+        other = torch.ones(Np, dtype=torch.bool)
+        other[lo:hi] = False
+        assert torch.equal(I["patches"][0, other].cpu(), P["patches0"][0, other].float())   # foreign patches untouched
+
+
+def test_sharded_ba_failure_is_seen_by_every_rank():
+    """a rank whose accumulate fails (here: NaN weights -> non-PD system after the sum) stops all ranks identically"""
+    from devo_b200 import cuda_ba
+    P = ba_problem(n_frames=4, patches_per_frame=8, seed=5, init="perturbed")
+    lm = torch.tensor([1e-4], device="cuda")
+    ranks = []
+    for r in range(2):
+        I = _sharded_inputs(P, r, 2, "cuda")
+        if r == 1:
+            I["weight"].fill_(float("nan"))
+        I["ba"] = cuda_ba.ShardedBA(I["poses"], I["patches"], I["intr"], I["target"], I["weight"], lm, I["ii"], I["jj"], I["kk"], 1, 4)
+        ranks.append(I)
+    total = sum(I["ba"].accumulate(0).clone() for I in ranks)
+    for I in ranks:
+        I["ba"].system.copy_(total)
+        I["ba"].solve(0)
+        assert int(I["ba"].status.item()) != 0
+        assert torch.equal(I["poses"].cpu(), P["poses0"].float())               # nothing applied
+
+
+def _nccl_worker(rank, world, port, q):
+    import os
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from devo_b200 import cuda_ba, dist as d
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    P = ba_problem(n_frames=8, patches_per_frame=96, seed=85, init="perturbed", noise=0.3)
+    I = _sharded_inputs(P, rank, world, torch.device("cuda", rank))
+    st = cuda_ba.forward_sharded(I["poses"], I["patches"], I["intr"], I["target"], I["weight"], torch.tensor([1e-4], device=I["poses"].device),
+                                 I["ii"], I["jj"], I["kk"], 1, 8, 2)
+    d.gather_patch_depths(I["patches"], 8 * 96)
+    torch.cuda.synchronize()
+    q.put((rank, int(st.item()), I["poses"].cpu(), I["patches"].cpu()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_ba_two_gpus_nccl():
+    """the real thing: 2 processes, 2 GPUs, NCCL all-reduce of [S|y] per iteration (skipped on a 1-GPU box)"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import os
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 300)
+    ps = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    out = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
+    for p in ps:
+        p.join(120)
+        assert p.exitcode == 0
+    P = ba_problem(n_frames=8, patches_per_frame=96, seed=85, init="perturbed", noise=0.3)
+    ref_poses, ref_patches = _run_ba(P, 1, 8, 2)
+    assert out[0][1] == 0 and out[1][1] == 0
+    assert torch.equal(out[0][2], out[1][2]) and torch.equal(out[0][3], out[1][3])     # replicas agree bitwise
+    assert (out[0][2] - ref_poses.cpu()).abs().max().item() <= 1e-6
+    assert (out[0][3] - ref_patches.cpu()).abs().max().item() <= 1e-6
