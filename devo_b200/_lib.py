@@ -48,6 +48,8 @@ SIGNATURES = {
     "devo_glue_relu_cast": (_i, [_i, _vp, _vp, _i64, _i, _vp]),
     "devo_glue_heads": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "devo_segment_softmax_sum": (_i, [_vp] * 5 + [_i, _vp, _i, _i, _i, _vp]),
+    "devo_gru_workspace": (_sz, [_i, _i]),
+    "devo_gru_update": (_i, [_vp, _vp, _i, _vp, _sz, _vp]),
 }
 for _n, _a in (("expm", 2), ("logm", 2), ("inv", 2), ("as_matrix", 2), ("projector", 2),
                ("expm_backward", 3), ("logm_backward", 3), ("inv_backward", 3),
@@ -60,6 +62,21 @@ for _n, _a in (("expm", 2), ("logm", 2), ("inv", 2), ("as_matrix", 2), ("project
 class PyramidStruct(ctypes.Structure):
     """devo_pyramid_t"""
     _fields_ = [("n_levels", _i), ("level", _vp * 4), ("H", _i * 4), ("W", _i * 4), ("scale", _c.c_float * 4)]
+
+
+class GruWeightsStruct(ctypes.Structure):
+    """devo_gru_weights_t"""
+    _fields_ = [("W", _vp), ("W0", _vp), ("bias", _vp), ("ln_gamma", _vp), ("ln_beta", _vp), ("ln_eps", _c.c_float),
+                ("head_W", _vp), ("head_b", _vp)]
+
+
+class GruIoStruct(ctypes.Structure):
+    """devo_gru_io_t"""
+    _fields_ = [("E", _i), ("dim", _i), ("corr_ld", _i), ("corr16", _vp), ("net16", _vp), ("imap16", _vp), ("kk", _vp),
+                ("ix", _vp), ("jx", _vp),
+                ("perm_kk", _vp), ("gstart_kk", _vp), ("ngroups_kk", _vp), ("gid_kk", _vp), ("max_groups_kk", _i),
+                ("perm_ij", _vp), ("gstart_ij", _vp), ("ngroups_ij", _vp), ("gid_ij", _vp), ("max_groups_ij", _i),
+                ("net16_out", _vp), ("delta", _vp), ("weight", _vp)]
 
 
 _lib = None

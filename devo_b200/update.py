@@ -90,6 +90,50 @@ class FrozenCast:
         return module(x)
 
 
+class PackedUpdateWeights:
+    """The update operator's parameters in the layout devo_gru_update wants (include/devo_b200.h
+    devo_gru_weights_t): all 384x384 Linear weights stacked, corr[0] zero-padded along its input dimension,
+    biases stacked, the four LayerNorms stacked, both heads concatenated.  Rebuilt only when a parameter changes."""
+
+    def __init__(self, update, dtype, corr_ld):
+        self.update, self.dtype, self.corr_ld = update, dtype, corr_ld
+        self._ver = None
+        self.refresh()
+
+    def _layers(self):
+        u = self.update
+        return [u.corr[2], u.corr[5], u.c1[0], u.c1[2], u.c2[0], u.c2[2], u.agg_kk.g, u.agg_kk.f, u.agg_kk.h,
+                u.agg_ij.g, u.agg_ij.f, u.agg_ij.h, u.gru[1].gate[0], u.gru[1].res[0], u.gru[1].res[2],
+                u.gru[3].gate[0], u.gru[3].res[0], u.gru[3].res[2]]
+
+    def _version(self):
+        return tuple(p._version for p in self.update.parameters()) + (next(self.update.parameters()).device,)
+
+    def refresh(self):
+        v = self._version()
+        if v == self._ver:
+            return self
+        u, dt = self.update, self.dtype
+        with torch.no_grad():
+            L = self._layers()
+            self.W = torch.cat([l.weight.detach().to(dt) for l in L], 0).contiguous()
+            w0 = u.corr[0].weight.detach()
+            self.W0 = torch.zeros(w0.shape[0], self.corr_ld, dtype=dt, device=w0.device)
+            self.W0[:, :w0.shape[1]] = w0.to(dt)
+            self.bias = torch.stack([u.corr[0].bias.detach().to(dt)] + [l.bias.detach().to(dt) for l in L], 0).contiguous()
+            lns = [u.corr[3], u.norm, u.gru[0], u.gru[2]]
+            self.ln_gamma = torch.stack([l.weight.detach().float() for l in lns], 0).contiguous()
+            self.ln_beta = torch.stack([l.bias.detach().float() for l in lns], 0).contiguous()
+            self.ln_eps = float(u.norm.eps)
+            self.head_W = torch.cat([u.d[1].weight.detach().to(dt), u.w[1].weight.detach().to(dt)], 0).contiguous()
+            self.head_b = torch.cat([u.d[1].bias.detach().to(dt), u.w[1].bias.detach().to(dt)], 0).contiguous()
+        from . import _lib
+        self.struct = _lib.GruWeightsStruct(self.W.data_ptr(), self.W0.data_ptr(), self.bias.data_ptr(), self.ln_gamma.data_ptr(),
+                                            self.ln_beta.data_ptr(), self.ln_eps, self.head_W.data_ptr(), self.head_b.data_ptr())
+        self._ver = v
+        return self
+
+
 class _ClipGrad(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
@@ -181,6 +225,42 @@ class Update(nn.Module):
         net = net + self.agg_ij.forward_planned(net, plan_ij, max_pairs, fc)
         net = run(self.gru, net)
         return net, (run(self.d, net), run(self.w, net), None)
+
+    def forward_mma(self, net16, imap16, kk, corr16, plan_kk, plan_ij, max_patches, max_pairs, packed, net_out=None,
+                    workspace=None):
+        """The whole forward as fused tcgen05 kernels (csrc/gru_mma.cu, devo_gru_update): net16 [1,E,384] hidden state,
+        imap16 [1,Np,384] context features (inp = imap16[:, kk], gathered inside), corr16 [E, corr_ld] zero-padded
+        correlation rows.  Returns (net_out [1,E,384] autocast dtype, (delta, weight, None)).  Inference only; same
+        rounding points as forward_fused."""
+        import ctypes
+        from . import _lib
+        E, D = net16.shape[1], self.dim
+        dt = packed.dtype
+        for t in (net16, imap16, corr16):
+            _lib.require_cuda(t)
+            _lib.require_dtype(t, dt, "forward_mma input")
+            _lib.require_contiguous(t=t)
+        if corr16.shape[-1] != packed.corr_ld:
+            raise RuntimeError("forward_mma: correlation rows must be padded to %d" % packed.corr_ld)
+        dev = net16.device
+        if net_out is None:
+            net_out = torch.empty(1, E, D, dtype=dt, device=dev)
+        delta = torch.empty(1, E, 2, dtype=dt, device=dev)
+        weight = torch.empty(1, E, 2, dtype=dt, device=dev)
+        L = _lib.lib()
+        nbytes = L.devo_gru_workspace(E, max(max_patches, max_pairs))
+        ws = workspace if workspace is not None else _lib.workspace(nbytes, dev, "gru")
+        if ws.numel() < nbytes:
+            raise RuntimeError("forward_mma: workspace too small")
+        packed.refresh()
+        io = _lib.GruIoStruct(E, D, packed.corr_ld, corr16.data_ptr(), net16.data_ptr(), imap16.data_ptr(), kk.data_ptr(),
+                              plan_kk.ix.data_ptr(), plan_kk.jx.data_ptr(),
+                              plan_kk.perm.data_ptr(), plan_kk.gstart.data_ptr(), plan_kk.ngroups.data_ptr(), plan_kk.gid.data_ptr(), int(max_patches),
+                              plan_ij.perm.data_ptr(), plan_ij.gstart.data_ptr(), plan_ij.ngroups.data_ptr(), plan_ij.gid.data_ptr(), int(max_pairs),
+                              net_out.data_ptr(), delta.data_ptr(), weight.data_ptr())
+        _lib.check(L.devo_gru_update(ctypes.byref(packed.struct), ctypes.byref(io), _lib.dtype_code(net16), ws.data_ptr(),
+                                     ws.numel(), _lib.stream_ptr(dev)), "gru_update")
+        return net_out, (delta, weight, None)
 
     def forward_fused(self, net16, inp16, corr16, plan_kk, plan_ij, max_patches, max_pairs, fc, net_out=None):
         """forward_planned with the element-wise glue fused into hand-written kernels (devo_b200.glue) and

@@ -214,6 +214,42 @@ int devo_glue_relu_cast(int dtype, const float* x32, void* out16, int64_t total,
 int devo_glue_heads(int dtype, const float* x32, const void* W16, const void* b16, void* delta, void* weight,
                     int rows, int dim, void* stream);
 
+/* ------------------------------------------------------------------ fused update operator */
+/* The whole of Update.forward (devo/enet.py:80-99: corr MLP, norm, neighbour convolutions c1/c2, the two SoftAgg
+ * aggregations, the gated-residual GRU and both heads) as fused tcgen05 kernels: one CTA keeps a tile of 128 edges
+ * resident (activations in shared memory, accumulator in TMEM) through a whole chain of Linear layers, weights
+ * streamed by TMA.  Inference only, autocast rounding points (see devo_b200/update.py::forward_fused).
+ * Stacked layer order of W [18*384,384] and bias rows 1..18: corr[2], corr[5], c1[0], c1[2], c2[0], c2[2],
+ * agg_kk.g, agg_kk.f, agg_kk.h, agg_ij.g, agg_ij.f, agg_ij.h, gru[1].gate[0], gru[1].res[0], gru[1].res[2],
+ * gru[3].gate[0], gru[3].res[0], gru[3].res[2].  LayerNorm rows: corr[3], norm, gru[0], gru[2]. */
+typedef struct {
+  const void* W;          /* [18*384, 384] (out, in) row-major, autocast dtype */
+  const void* W0;         /* corr[0] weight [384, corr_ld], input dim zero-padded to corr_ld */
+  const void* bias;       /* [19, 384]: row 0 = corr[0], rows 1..18 = the stacked layers */
+  const float* ln_gamma;  /* [4, 384] f32 */
+  const float* ln_beta;   /* [4, 384] f32 */
+  float ln_eps;
+  const void* head_W;     /* [4, 384]: d.x d.y w.x w.y */
+  const void* head_b;     /* [4] */
+} devo_gru_weights_t;
+typedef struct {
+  int E, dim, corr_ld;
+  const void* corr16;     /* [E, corr_ld] correlation features (rows zero-padded) */
+  const void* net16;      /* [E, 384] hidden state in */
+  const void* imap16;     /* [n_patches, 384] context features; inp = imap16[kk] */
+  const int64_t* kk;      /* [E] */
+  const int64_t* ix;      /* [E] neighbours from devo_graph_plan(kk, jj): previous / next edge or -1 */
+  const int64_t* jx;
+  const int32_t* perm_kk; const int32_t* gstart_kk; const int32_t* ngroups_kk; const int32_t* gid_kk; int max_groups_kk;
+  const int32_t* perm_ij; const int32_t* gstart_ij; const int32_t* ngroups_ij; const int32_t* gid_ij; int max_groups_ij;
+  void* net16_out;        /* [E, 384] hidden state out (may alias net16) */
+  void* delta;            /* [E, 2] */
+  void* weight;           /* [E, 2] */
+} devo_gru_io_t;
+size_t devo_gru_workspace(int E, int max_groups);
+int devo_gru_update(const devo_gru_weights_t* weights, const devo_gru_io_t* io, int dtype, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

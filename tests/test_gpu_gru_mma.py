@@ -1,0 +1,76 @@
+"""GPU: the fused tcgen05 update operator (csrc/gru_mma.cu, devo_gru_update) against (a) the cuBLAS + glue-kernel path
+(forward_fused, identical rounding points) and (b) the reference-shaped module forward under torch.autocast
+(devo/enet.py:80-99).  Tolerances are half-precision noise: the two paths only differ in the summation order
+inside the dot products (fp32 accumulation in both)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(nf, m, seed, dt=torch.float16):
+    from devo_b200 import cuda_ba
+    from devo_b200.update import Update
+    from problems import fully_connected_graph
+    torch.manual_seed(seed)
+    ii, jj, kk = [t.cuda() for t in fully_connected_graph(nf, m)]
+    if seed % 2:      # ragged graph: drop a random fifth of the edges (keyframe removal leaves such graphs)
+        keep = torch.rand(ii.numel(), device="cuda") > 0.2
+        ii, jj, kk = ii[keep], jj[keep], kk[keep]
+    E, Np = ii.numel(), nf * m
+    up = Update(3).cuda().eval()
+    with torch.no_grad():
+        for p in up.parameters():      # non-trivial LayerNorm affine + biases
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    net = (0.5 * torch.randn(1, E, 384, device="cuda")).to(dt)
+    imap = (0.25 * torch.randn(1, Np, 384, device="cuda")).to(dt)
+    corr = torch.zeros(E, 896, device="cuda", dtype=dt)
+    corr[:, :882] = (2.0 * torch.randn(E, 882, device="cuda")).to(dt)
+    plan_kk = cuda_ba.GraphPlan(kk, jj, Np, nf)
+    plan_ij = cuda_ba.GraphPlan(ii * 12345 + jj, torch.zeros_like(ii), -1, 1, want_neighbors=False)
+    return up, net, imap, corr, ii, jj, kk, plan_kk, plan_ij, Np, nf * nf
+
+
+@pytest.mark.parametrize("nf,m,seed", [(8, 96, 0), (4, 24, 1), (3, 5, 2), (5, 31, 3)])
+def test_gru_mma_matches_cublas_path(nf, m, seed):
+    from devo_b200.update import FrozenCast, PackedUpdateWeights
+    up, net, imap, corr, ii, jj, kk, plan_kk, plan_ij, Np, pairs = _problem(nf, m, seed)
+    fc = FrozenCast(torch.float16)
+    with torch.no_grad():
+        ref_net, (ref_d, ref_w, _) = up.forward_fused(net, imap[:, kk], corr.view(1, -1, 896), plan_kk, plan_ij, Np, pairs, fc)
+        packed = PackedUpdateWeights(up, torch.float16, 896)
+        out_net, (d, w, _) = up.forward_mma(net, imap, kk, corr, plan_kk, plan_ij, Np, pairs, packed)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out_net).all() and torch.isfinite(d).all() and torch.isfinite(w).all()
+    scale = ref_net.abs().max().item()
+    assert (out_net.float() - ref_net).abs().max().item() <= 2e-2 * max(scale, 1.0)
+    assert (out_net.float() - ref_net).abs().mean().item() <= 1e-3 * max(scale, 1.0)
+    assert (d.float() - ref_d.float()).abs().max().item() <= 2e-2
+    assert (w.float() - ref_w.float()).abs().max().item() <= 1e-2
+
+
+def test_gru_mma_matches_module_forward_under_autocast():
+    from devo_b200.update import PackedUpdateWeights
+    up, net, imap, corr, ii, jj, kk, plan_kk, plan_ij, Np, pairs = _problem(4, 24, 4)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        ref_net, (ref_d, ref_w, _) = up(net, imap[:, kk], corr[:, :882].reshape(1, -1, 882), None, ii, jj, kk)
+    with torch.no_grad():
+        out_net, (d, w, _) = up.forward_mma(net, imap, kk, corr, plan_kk, plan_ij, Np, pairs, PackedUpdateWeights(up, torch.float16, 896))
+    assert (out_net.float() - ref_net.float()).abs().max().item() <= 3e-2 * max(ref_net.abs().max().item(), 1.0)
+    assert (d.float() - ref_d.float()).abs().max().item() <= 2e-2
+    assert (w.float() - ref_w.float()).abs().max().item() <= 1e-2
+
+
+def test_gru_mma_bf16_and_in_place_hidden_state():
+    from devo_b200.update import FrozenCast, PackedUpdateWeights
+    up, net, imap, corr, ii, jj, kk, plan_kk, plan_ij, Np, pairs = _problem(4, 24, 6, dt=torch.bfloat16)
+    fc = FrozenCast(torch.bfloat16)
+    with torch.no_grad():
+        ref_net, (ref_d, ref_w, _) = up.forward_fused(net, imap[:, kk], corr.view(1, -1, 896), plan_kk, plan_ij, Np, pairs, fc)
+        state = net.clone()
+        out_net, (d, w, _) = up.forward_mma(state, imap, kk, corr, plan_kk, plan_ij, Np, pairs,
+                                            PackedUpdateWeights(up, torch.bfloat16, 896), net_out=state)
+    assert out_net.data_ptr() == state.data_ptr()
+    assert (state.float() - ref_net).abs().max().item() <= 1e-1 * max(ref_net.abs().max().item(), 1.0)
+    assert (d.float() - ref_d.float()).abs().max().item() <= 1e-1
