@@ -42,8 +42,11 @@ constexpr int kNH = 192;                   // N per MMA / per weight stage
 constexpr int kABlk = kRows * 128;         // one K-block of A: 128 rows x 64 halfs = 16 KB
 constexpr int kASlots = kD / 64;           // 6
 constexpr int kWStage = kNH * 128;         // 24 KB
-constexpr int kWStages = 5;
-constexpr int kThreads = 256;
+constexpr int kWStages = 4;
+constexpr int kEpiPer = 2;                 // epilogue warps per TMEM lane quarter (each owns a share of the columns)
+constexpr int kEpiThreads = 128 * kEpiPer;
+constexpr int kThreads = 128 + kEpiThreads;
+constexpr int kCB = kD / 32;               // 32-column blocks per row (12)
 constexpr int kMaxLayers = 6;
 constexpr int kChunks = kD / 8;            // 16-byte chunks per row (48)
 constexpr int kCol4 = kD / 4;              // float4 groups per row (96)
@@ -106,10 +109,13 @@ __device__ __forceinline__ uint32_t a_off(int r, int c) {
 __device__ __forceinline__ size_t t32(int tile, int q, int r) { return (((size_t)tile * kCol4 + q) * kRows + r) * 4; }
 __device__ __forceinline__ size_t t16(int tile, int c, int r) { return (((size_t)tile * kChunks + c) * kRows + r) * 8; }
 
+__device__ __forceinline__ float4 as_f4(uint4 u) {
+  return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+}
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // the 128 epilogue threads only
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_constant__ CUtensorMap tm_w,
@@ -127,8 +133,13 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
   uint64_t* a_empty = a_full + kASlots;       // [kASlots]
   uint64_t* acc_full = a_empty + kASlots;     // [1]
   uint64_t* a_ready = acc_full + 1;           // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
-  int* s_idx = reinterpret_cast<int*>(tmem_slot + 2);   // [128] gather sources of the tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);    // bars: 24 x 8 B = 192 B; slot + pad = 16 B
+  int* s_idx = reinterpret_cast<int*>(tmem_slot + 4);   // [128] gather sources of the tile
+  float* s_stat = reinterpret_cast<float*>(s_idx + kRows);            // [kEpiPer][128][2] LayerNorm partials
+  float* s_hacc = s_stat + kEpiPer * kRows * 2;                       // [kEpiPer][128][4] head partials
+  float* s_ln = s_hacc + kEpiPer * kRows * 4;                         // [2][2][384]: gamma, beta of the program's LayerNorms
+  T* s_bias = reinterpret_cast<T*>(s_ln + 4 * kD);                    // [kMaxLayers][384]
+  T* s_head = s_bias + kMaxLayers * kD;                               // [4][384] + [4] (+4 pad)
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -145,6 +156,24 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else if (warp >= 2) {
+    // stage the program's small parameters (biases, LayerNorm affine, heads) in shared memory once: the epilogues
+    // read them as broadcasts instead of dependent global loads
+    const int t = threadIdx.x - 64, nt = kThreads - 64;
+    for (int l = 0; l < P.n_layers; l++)
+      for (int q = t; q < kD / 8; q += nt)
+        reinterpret_cast<uint4*>(s_bias + l * kD)[q] = __ldg(reinterpret_cast<const uint4*>(P.bias[l]) + q);
+    for (int k = 0; k < 2; k++) {
+      if (P.ln_g[k] == nullptr) continue;
+      for (int q = t; q < kD / 4; q += nt) {
+        reinterpret_cast<float4*>(s_ln + (2 * k) * kD)[q] = __ldg(reinterpret_cast<const float4*>(P.ln_g[k]) + q);
+        reinterpret_cast<float4*>(s_ln + (2 * k + 1) * kD)[q] = __ldg(reinterpret_cast<const float4*>(P.ln_b[k]) + q);
+      }
+    }
+    if (P.headW != nullptr) {
+      for (int q = t; q < 4 * kD / 8; q += nt) reinterpret_cast<uint4*>(s_head)[q] = __ldg(reinterpret_cast<const uint4*>(P.headW) + q);
+      if (t < 4) s_head[4 * kD + t] = P.headB[t];
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -212,84 +241,132 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // =========================== prologue + epilogues: one thread per row ======================================
-    const int et = threadIdx.x - 128;               // 0..127 = tile row = TMEM lane
+    // =========================== prologue + epilogues ==========================================================
+    // kEpiPer warps per TMEM lane quarter; a thread owns one row and the column blocks [cb0, cb1) of 32 columns.
     const int quarter = warp & 3;
-    const int r = et;
+    const int part = (warp - 4) >> 2;               // 0 .. kEpiPer-1
+    const int et = threadIdx.x - 128;               // 0 .. kEpiThreads-1
+    const int r = quarter * 32 + lane;              // tile row = TMEM lane
     const int grow = row0 + r;                      // global row
     const bool live = grow < P.rows;
+    const int cb0 = part * (kCB / kEpiPer), cb1 = cb0 + kCB / kEpiPer;
     const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
     unsigned char* arow = As;                       // + a_off(r, c)
 
+    // row statistics of a LayerNorm: combine the partial (sum, sum of squares) of the kEpiPer threads of a row
+    auto ln_stats = [&](float s1, float s2, float& mean, float& rstd) {
+      if (kEpiPer > 1) {
+        s_stat[(part * kRows + r) * 2 + 0] = s1;
+        s_stat[(part * kRows + r) * 2 + 1] = s2;
+        epi_bar();
+        s1 = 0.f; s2 = 0.f;
+#pragma unroll
+        for (int p = 0; p < kEpiPer; p++) { s1 += s_stat[(p * kRows + r) * 2 + 0]; s2 += s_stat[(p * kRows + r) * 2 + 1]; }
+        epi_bar();                                  // s_stat may be reused right away
+      }
+      mean = s1 * (1.0f / kD);
+      rstd = rsqrtf(fmaxf(s2 * (1.0f / kD) - mean * mean, 0.f) + P.eps);
+    };
+
     // ---------------- prologue ----------------
     if (P.pro == PRO_GATHER) {
-      int src = -1;
-      if (live) {
-        const long long j = P.idx64 ? (long long)P.idx64[grow] : (long long)grow;
-        src = (j >= 0 && j < (long long)P.src_rows) ? (int)j : -1;
+      if (et < kRows) {
+        const int gr = row0 + et;
+        int src = -1;
+        if (gr < P.rows) {
+          const long long j = P.idx64 ? (long long)P.idx64[gr] : (long long)gr;
+          src = (j >= 0 && j < (long long)P.src_rows) ? (int)j : -1;
+        }
+        s_idx[et] = src;
       }
-      s_idx[r] = src;
       epi_bar();
-      // cooperative: 48 consecutive threads copy one 768-byte source row
-#pragma unroll 4
-      for (int q = et; q < kRows * kChunks; q += 128) {
-        const int rr = q / kChunks, c = q - rr * kChunks;
-        const int s = s_idx[rr];
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (s >= 0) v = *reinterpret_cast<const uint4*>(P.x16_in + (size_t)s * kD + c * 8);
-        *reinterpret_cast<uint4*>(As + a_off(rr, c)) = v;
+      // cooperative: 48 consecutive threads copy one 768-byte source row; 12 independent 16-byte loads in flight
+      constexpr int kPer = kRows * kChunks / kEpiThreads;     // chunks per thread
+      constexpr int kBatch = 12;
+      static_assert(kPer % kBatch == 0, "gather batches");
+#pragma unroll 1
+      for (int b = 0; b < kPer / kBatch; b++) {
+        uint4 v[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; u++) {
+          const int q = et + (b * kBatch + u) * kEpiThreads;
+          const int rr = q / kChunks, c = q - rr * kChunks;
+          const int s = s_idx[rr];
+          v[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (s >= 0) v[u] = *reinterpret_cast<const uint4*>(P.x16_in + (size_t)s * kD + c * 8);
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; u++) {
+          const int q = et + (b * kBatch + u) * kEpiThreads;
+          const int rr = q / kChunks, c = q - rr * kChunks;
+          *reinterpret_cast<uint4*>(As + a_off(rr, c)) = v[u];
+        }
       }
     } else if (P.pro == PRO_CAST || P.pro == PRO_RESID || P.pro == PRO_RESID_LN) {
       const bool resid = (P.pro != PRO_CAST);
+      const bool with_ln = (P.pro == PRO_RESID_LN);
       const int g = (resid && live) ? P.gid[grow] : 0;
       const T* yrow = resid ? P.y16 + (size_t)g * kD : nullptr;
-      float sum = 0.f;
-#pragma unroll 2
-      for (int c = 0; c < kChunks; c++) {
-        float v[8];
-        const float4 a = *reinterpret_cast<const float4*>(P.net32 + t32(tile, 2 * c, r));
-        const float4 b = *reinterpret_cast<const float4*>(P.net32 + t32(tile, 2 * c + 1, r));
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        if (resid) {
-          float y[8];
-          uint4 yu = make_uint4(0u, 0u, 0u, 0u);
-          if (live) yu = *reinterpret_cast<const uint4*>(yrow + c * 8);
-          unpack8<T>(yu, y);
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int cb = cb0; cb < cb1; cb++) {
+        float4 f[8];
+        uint4 yu[4];
 #pragma unroll
-          for (int k = 0; k < 8; k++) v[k] += y[k];
-          *reinterpret_cast<float4*>(P.net32 + t32(tile, 2 * c, r)) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(P.net32 + t32(tile, 2 * c + 1, r)) = make_float4(v[4], v[5], v[6], v[7]);
+        for (int j = 0; j < 4; j++) {
+          const int c = cb * 4 + j;
+          f[2 * j] = *reinterpret_cast<const float4*>(P.net32 + t32(tile, 2 * c, r));
+          f[2 * j + 1] = *reinterpret_cast<const float4*>(P.net32 + t32(tile, 2 * c + 1, r));
+          yu[j] = make_uint4(0u, 0u, 0u, 0u);
+          if (resid && live) yu[j] = *reinterpret_cast<const uint4*>(yrow + c * 8);
         }
-        if (P.pro == PRO_RESID_LN) {
+        uint32_t st[32];
 #pragma unroll
-          for (int k = 0; k < 8; k++) sum += v[k];
-        } else {
-          *reinterpret_cast<uint4*>(arow + a_off(r, c)) = pack8<T>(v);
+        for (int j = 0; j < 4; j++) {
+          const int c = cb * 4 + j;
+          float v[8] = {f[2 * j].x, f[2 * j].y, f[2 * j].z, f[2 * j].w, f[2 * j + 1].x, f[2 * j + 1].y, f[2 * j + 1].z, f[2 * j + 1].w};
+          if (resid) {
+            float y[8];
+            unpack8<T>(yu[j], y);
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] += y[k];
+          }
+          if (with_ln) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) { s1 += v[k]; s2 += v[k] * v[k]; st[j * 8 + k] = __float_as_uint(v[k]); }
+          } else {
+            if (resid) {
+              *reinterpret_cast<float4*>(P.net32 + t32(tile, 2 * c, r)) = make_float4(v[0], v[1], v[2], v[3]);
+              *reinterpret_cast<float4*>(P.net32 + t32(tile, 2 * c + 1, r)) = make_float4(v[4], v[5], v[6], v[7]);
+            }
+            *reinterpret_cast<uint4*>(arow + a_off(r, c)) = pack8<T>(v);
+          }
         }
+        if (with_ln) tmem_st32(trow + cb * 32, st);      // park the fp32 row in TMEM (free until the first MMA)
       }
-      if (P.pro == PRO_RESID_LN) {     // n = LayerNorm(net) -> n32 (float) and the A tile (half); two-pass variance
-        const float mean = sum * (1.0f / kD);
-        float q2 = 0.f;
-#pragma unroll 4
-        for (int q = 0; q < kCol4; q++) {
-          const float4 a = *reinterpret_cast<const float4*>(P.net32 + t32(tile, q, r));
-          const float d0 = a.x - mean, d1 = a.y - mean, d2 = a.z - mean, d3 = a.w - mean;
-          q2 += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
-        }
-        const float rstd = rsqrtf(q2 * (1.0f / kD) + P.eps);
-        const float* gm = P.ln_g[0];
-        const float* bt = P.ln_b[0];
-#pragma unroll 2
-        for (int c = 0; c < kChunks; c++) {
-          const float4 a = *reinterpret_cast<const float4*>(P.net32 + t32(tile, 2 * c, r));
-          const float4 b = *reinterpret_cast<const float4*>(P.net32 + t32(tile, 2 * c + 1, r));
-          float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      if (with_ln) {     // n = LayerNorm(net) -> n32 (float, needed by the gated residual) and the A tile (half)
+        tmem_wait_st();
+        float mean, rstd;
+        ln_stats(s1, s2, mean, rstd);
+        const float* gm = s_ln;
+        const float* bt = s_ln + kD;
+#pragma unroll 1
+        for (int cb = cb0; cb < cb1; cb++) {
+          uint32_t raw[32];
+          tmem_ld32(trow + cb * 32, raw);
+          tmem_wait_ld();
 #pragma unroll
-          for (int k = 0; k < 8; k++) v[k] = (v[k] - mean) * rstd * __ldg(gm + c * 8 + k) + __ldg(bt + c * 8 + k);
-          *reinterpret_cast<float4*>(P.n32 + t32(tile, 2 * c, r)) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(P.n32 + t32(tile, 2 * c + 1, r)) = make_float4(v[4], v[5], v[6], v[7]);
-          *reinterpret_cast<uint4*>(arow + a_off(r, c)) = pack8<T>(v);
+          for (int j = 0; j < 4; j++) {
+            const int c = cb * 4 + j;
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = (__uint_as_float(raw[j * 8 + k]) - mean) * rstd * gm[c * 8 + k] + bt[c * 8 + k];
+            *reinterpret_cast<float4*>(P.n32 + t32(tile, 2 * c, r)) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(P.n32 + t32(tile, 2 * c + 1, r)) = make_float4(v[4], v[5], v[6], v[7]);
+            *reinterpret_cast<uint4*>(arow + a_off(r, c)) = pack8<T>(v);
+          }
         }
+        tc_fence_before();
       }
     }
     if (has_pro) {
@@ -302,10 +379,8 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
     int ln_used = (P.pro == PRO_RESID_LN) ? 1 : 0;
     for (int l = 0; l < P.n_layers; l++) {
       const int epi = P.epi[l];
-      const T* bias = P.bias[l];
-      mbar_wait(acc_full, (uint32_t)(l & 1));
-      tc_fence_after();
-      float sum = 0.f;
+      const T* bias = s_bias + l * kD;
+      float s1 = 0.f, s2 = 0.f;
       float hacc[4] = {0.f, 0.f, 0.f, 0.f};
       const T* netrow = nullptr;
       const T* inprow = nullptr;
@@ -318,10 +393,35 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
         if (epi == EPI_STORE_A || epi == EPI_RESID || epi == EPI_GATED_HEADS || epi == EPI_ADD3_LN) orow = P.out16_a ? P.out16_a + (size_t)grow * kD : nullptr;
         if (epi == EPI_STORE_B) orow = P.out16_b ? P.out16_b + (size_t)grow * kD : nullptr;
       }
+      // per-row operands of the element-wise tail, fetched one column block ahead of their use
+      struct Aux { uint4 q[12]; };     // RESID: q[0..7] net32 ; GATED: q[0..7] n32, q[8..11] gate ; ADD3: q[0..3] net16, q[4..7] inp16
+      auto load_aux = [&](int cb, Aux& a) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int c = cb * 4 + j;
+          if (epi == EPI_RESID) {
+            a.q[2 * j] = *reinterpret_cast<const uint4*>(P.net32 + t32(tile, 2 * c, r));
+            a.q[2 * j + 1] = *reinterpret_cast<const uint4*>(P.net32 + t32(tile, 2 * c + 1, r));
+          } else if (epi == EPI_GATED_LN || epi == EPI_GATED_HEADS) {
+            a.q[2 * j] = *reinterpret_cast<const uint4*>(P.n32 + t32(tile, 2 * c, r));
+            a.q[2 * j + 1] = *reinterpret_cast<const uint4*>(P.n32 + t32(tile, 2 * c + 1, r));
+            a.q[8 + j] = *reinterpret_cast<const uint4*>(P.gate16 + t16(tile, c, r));
+          } else if (epi == EPI_ADD3_LN) {
+            a.q[j] = make_uint4(0u, 0u, 0u, 0u);
+            a.q[4 + j] = a.q[j];
+            if (live) { a.q[j] = *reinterpret_cast<const uint4*>(netrow + c * 8); a.q[4 + j] = __ldg(reinterpret_cast<const uint4*>(inprow + c * 8)); }
+          }
+        }
+      };
+      Aux cur, nxt;
+      load_aux(cb0, cur);                           // issued before the accumulator is ready: overlaps the MMAs
+      mbar_wait(acc_full, (uint32_t)(l & 1));
+      tc_fence_after();
 #pragma unroll 1
-      for (int cb = 0; cb < kD / 32; cb++) {
+      for (int cb = cb0; cb < cb1; cb++) {
         uint32_t raw[32];
         tmem_ld32(trow + cb * 32, raw);
+        if (cb + 1 < cb1) load_aux(cb + 1, nxt);
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -329,7 +429,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
           float o[8];
           {
             float bv[8];
-            unpack8<T>(__ldg(reinterpret_cast<const uint4*>(bias + c * 8)), bv);
+            unpack8<T>(*reinterpret_cast<const uint4*>(bias + c * 8), bv);
 #pragma unroll
             for (int k = 0; k < 8; k++) o[k] = rnd<T>(__uint_as_float(raw[j * 8 + k]) + bv[k]);   // Linear output (half)
           }
@@ -339,20 +439,17 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
             *reinterpret_cast<uint4*>(arow + a_off(r, c)) = pack8<T>(o);
           } else if (epi == EPI_LNRELU_A) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) sum += o[k];
+            for (int k = 0; k < 8; k++) { s1 += o[k]; s2 += o[k] * o[k]; }
             *reinterpret_cast<uint4*>(arow + a_off(r, c)) = pack8<T>(o);
           } else if (epi == EPI_ADD3_LN) {
             float a[8], b[8];
-            uint4 au = make_uint4(0u, 0u, 0u, 0u), bu = au;
-            if (live) { au = *reinterpret_cast<const uint4*>(netrow + c * 8); bu = __ldg(reinterpret_cast<const uint4*>(inprow + c * 8)); }
-            unpack8<T>(au, a);
-            unpack8<T>(bu, b);
+            unpack8<T>(cur.q[j], a);
+            unpack8<T>(cur.q[4 + j], b);
 #pragma unroll
-            for (int k = 0; k < 8; k++) { o[k] = rnd<T>(rnd<T>(a[k] + b[k]) + o[k]); sum += o[k]; }
+            for (int k = 0; k < 8; k++) { o[k] = rnd<T>(rnd<T>(a[k] + b[k]) + o[k]); s1 += o[k]; s2 += o[k] * o[k]; }
             *reinterpret_cast<uint4*>(arow + a_off(r, c)) = pack8<T>(o);
           } else if (epi == EPI_RESID) {
-            float4 a = *reinterpret_cast<const float4*>(P.net32 + t32(tile, 2 * c, r));
-            float4 b = *reinterpret_cast<const float4*>(P.net32 + t32(tile, 2 * c + 1, r));
+            float4 a = as_f4(cur.q[2 * j]), b = as_f4(cur.q[2 * j + 1]);
             a.x += o[0]; a.y += o[1]; a.z += o[2]; a.w += o[3]; b.x += o[4]; b.y += o[5]; b.z += o[6]; b.w += o[7];
             *reinterpret_cast<float4*>(P.net32 + t32(tile, 2 * c, r)) = a;
             *reinterpret_cast<float4*>(P.net32 + t32(tile, 2 * c + 1, r)) = b;
@@ -366,17 +463,14 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
             *reinterpret_cast<uint4*>(P.gate16 + t16(tile, c, r)) = pack8<T>(o);
           } else {   // EPI_GATED_LN / EPI_GATED_HEADS:  x = n + half(half(sigmoid(gate)) * res)
             float g[8];
-            unpack8<T>(*reinterpret_cast<const uint4*>(P.gate16 + t16(tile, c, r)), g);
-            const float4 a = *reinterpret_cast<const float4*>(P.n32 + t32(tile, 2 * c, r));
-            const float4 b = *reinterpret_cast<const float4*>(P.n32 + t32(tile, 2 * c + 1, r));
+            unpack8<T>(cur.q[8 + j], g);
+            const float4 a = as_f4(cur.q[2 * j]), b = as_f4(cur.q[2 * j + 1]);
             float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
             for (int k = 0; k < 8; k++) x[k] += rnd<T>(rnd<T>(sigmoidf_(g[k])) * o[k]);
             if (epi == EPI_GATED_LN) {
 #pragma unroll
-              for (int k = 0; k < 8; k++) sum += x[k];
-              *reinterpret_cast<float4*>(P.net32 + t32(tile, 2 * c, r)) = make_float4(x[0], x[1], x[2], x[3]);
-              *reinterpret_cast<float4*>(P.net32 + t32(tile, 2 * c + 1, r)) = make_float4(x[4], x[5], x[6], x[7]);
+              for (int k = 0; k < 8; k++) { s1 += x[k]; s2 += x[k] * x[k]; raw[j * 8 + k] = __float_as_uint(x[k]); }
             } else {
               if (orow) *reinterpret_cast<uint4*>(orow + c * 8) = pack8<T>(x);       // new hidden state (half)
               float hw[8];
@@ -384,36 +478,29 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
               for (int k = 0; k < 8; k++) x[k] = rnd<T>(fmaxf(x[k], 0.f));
 #pragma unroll
               for (int o4 = 0; o4 < 4; o4++) {
-                unpack8<T>(__ldg(reinterpret_cast<const uint4*>(P.headW + (size_t)o4 * kD + c * 8)), hw);
+                unpack8<T>(*reinterpret_cast<const uint4*>(s_head + o4 * kD + c * 8), hw);
 #pragma unroll
                 for (int k = 0; k < 8; k++) hacc[o4] += x[k] * hw[k];
               }
             }
           }
         }
+        if (epi == EPI_GATED_LN) tmem_st32(trow + cb * 32, raw);  // fp32 row parked in its own accumulator columns
+        if (cb + 1 < cb1) cur = nxt;
       }
-      tc_fence_before();
       // ---------------- row-wise tails ----------------
       if (epi == EPI_LNRELU_A || epi == EPI_ADD3_LN) {
-        // the row (half values) sits in this thread's slice of the A tile: two more passes over shared memory
-        const float mean = sum * (1.0f / kD);
-        float q2 = 0.f;
-#pragma unroll 4
-        for (int c = 0; c < kChunks; c++) {
-          float v[8];
-          unpack8<T>(*reinterpret_cast<const uint4*>(arow + a_off(r, c)), v);
-#pragma unroll
-          for (int k = 0; k < 8; k++) { const float d = v[k] - mean; q2 += d * d; }
-        }
-        const float rstd = rsqrtf(q2 * (1.0f / kD) + P.eps);
-        const float* gm = P.ln_g[ln_used];
-        const float* bt = P.ln_b[ln_used];
+        // the row (half values) sits in this thread's slice of the A tile: one more pass over shared memory
+        float mean, rstd;
+        ln_stats(s1, s2, mean, rstd);
+        const float* gm = s_ln + ln_used * 2 * kD;
+        const float* bt = gm + kD;
 #pragma unroll 2
-        for (int c = 0; c < kChunks; c++) {
+        for (int c = cb0 * 4; c < cb1 * 4; c++) {
           float v[8];
           unpack8<T>(*reinterpret_cast<const uint4*>(arow + a_off(r, c)), v);
 #pragma unroll
-          for (int k = 0; k < 8; k++) v[k] = (v[k] - mean) * rstd * __ldg(gm + c * 8 + k) + __ldg(bt + c * 8 + k);
+          for (int k = 0; k < 8; k++) v[k] = (v[k] - mean) * rstd * gm[c * 8 + k] + bt[c * 8 + k];
           if (epi == EPI_LNRELU_A) {
 #pragma unroll
             for (int k = 0; k < 8; k++) v[k] = fmaxf(v[k], 0.f);
@@ -426,41 +513,52 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
         }
         ln_used++;
       } else if (epi == EPI_GATED_LN) {
-        const float mean = sum * (1.0f / kD);
-        float q2 = 0.f;
-#pragma unroll 4
-        for (int q = 0; q < kCol4; q++) {
-          const float4 a = *reinterpret_cast<const float4*>(P.net32 + t32(tile, q, r));
-          const float d0 = a.x - mean, d1 = a.y - mean, d2 = a.z - mean, d3 = a.w - mean;
-          q2 += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
-        }
-        const float rstd = rsqrtf(q2 * (1.0f / kD) + P.eps);
-        const float* gm = P.ln_g[ln_used];
-        const float* bt = P.ln_b[ln_used];
-#pragma unroll 2
-        for (int c = 0; c < kChunks; c++) {
-          const float4 a = *reinterpret_cast<const float4*>(P.net32 + t32(tile, 2 * c, r));
-          const float4 b = *reinterpret_cast<const float4*>(P.net32 + t32(tile, 2 * c + 1, r));
-          float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        tmem_wait_st();
+        float mean, rstd;
+        ln_stats(s1, s2, mean, rstd);
+        const float* gm = s_ln + ln_used * 2 * kD;
+        const float* bt = gm + kD;
+#pragma unroll 1
+        for (int cb = cb0; cb < cb1; cb++) {
+          uint32_t raw[32];
+          tmem_ld32(trow + cb * 32, raw);
+          tmem_wait_ld();
 #pragma unroll
-          for (int k = 0; k < 8; k++) v[k] = (v[k] - mean) * rstd * __ldg(gm + c * 8 + k) + __ldg(bt + c * 8 + k);
-          *reinterpret_cast<float4*>(P.n32 + t32(tile, 2 * c, r)) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(P.n32 + t32(tile, 2 * c + 1, r)) = make_float4(v[4], v[5], v[6], v[7]);
-          *reinterpret_cast<uint4*>(arow + a_off(r, c)) = pack8<T>(v);
+          for (int j = 0; j < 4; j++) {
+            const int c = cb * 4 + j;
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = (__uint_as_float(raw[j * 8 + k]) - mean) * rstd * gm[c * 8 + k] + bt[c * 8 + k];
+            *reinterpret_cast<float4*>(P.n32 + t32(tile, 2 * c, r)) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(P.n32 + t32(tile, 2 * c + 1, r)) = make_float4(v[4], v[5], v[6], v[7]);
+            *reinterpret_cast<uint4*>(arow + a_off(r, c)) = pack8<T>(v);
+          }
         }
         ln_used++;
       } else if (epi == EPI_GATED_HEADS) {
-        if (live) {
-          const float d0 = rnd<T>(hacc[0] + ElemTraits<T>::to_float(P.headB[0]));
-          const float d1 = rnd<T>(hacc[1] + ElemTraits<T>::to_float(P.headB[1]));
-          const float w0 = rnd<T>(hacc[2] + ElemTraits<T>::to_float(P.headB[2]));
-          const float w1 = rnd<T>(hacc[3] + ElemTraits<T>::to_float(P.headB[3]));
+        if (kEpiPer > 1) {
+#pragma unroll
+          for (int o4 = 0; o4 < 4; o4++) s_hacc[(part * kRows + r) * 4 + o4] = hacc[o4];
+          epi_bar();
+#pragma unroll
+          for (int o4 = 0; o4 < 4; o4++) {
+            hacc[o4] = 0.f;
+#pragma unroll
+            for (int p = 0; p < kEpiPer; p++) hacc[o4] += s_hacc[(p * kRows + r) * 4 + o4];
+          }
+        }
+        if (live && part == 0) {
+          const float d0 = rnd<T>(hacc[0] + ElemTraits<T>::to_float(s_head[4 * kD + 0]));
+          const float d1 = rnd<T>(hacc[1] + ElemTraits<T>::to_float(s_head[4 * kD + 1]));
+          const float w0 = rnd<T>(hacc[2] + ElemTraits<T>::to_float(s_head[4 * kD + 2]));
+          const float w1 = rnd<T>(hacc[3] + ElemTraits<T>::to_float(s_head[4 * kD + 3]));
           P.delta[(size_t)grow * 2 + 0] = ElemTraits<T>::from_float(d0);
           P.delta[(size_t)grow * 2 + 1] = ElemTraits<T>::from_float(d1);
           P.weight[(size_t)grow * 2 + 0] = ElemTraits<T>::from_float(sigmoidf_(w0));
           P.weight[(size_t)grow * 2 + 1] = ElemTraits<T>::from_float(sigmoidf_(w1));
         }
       }
+      tc_fence_before();
       if (l + 1 < P.n_layers) {       // hand the A tile / the TMEM accumulator back to the MMA warp
         fence_proxy_async();
         epi_bar();
@@ -507,7 +605,8 @@ static int make_map_2d(CUtensorMap* m, int dtype, const void* ptr, uint64_t rows
   return DEVO_OK;
 }
 
-constexpr size_t kSmemBytes = 1024 + (size_t)kASlots * kABlk + (size_t)kWStages * kWStage + 32 * sizeof(uint64_t) + 16 + 128 * sizeof(int);
+constexpr size_t kSmemBytes = 1024 + (size_t)kASlots * kABlk + (size_t)kWStages * kWStage + 24 * sizeof(uint64_t) + 16 + kRows * sizeof(int) +
+                              (size_t)kEpiPer * kRows * 6 * sizeof(float) + 4 * kD * sizeof(float) + (kMaxLayers * kD + 4 * kD + 8) * 2 + 64;
 
 template <typename T>
 static int launch_prog(const CUtensorMap& tw, const CUtensorMap& tw0, const CUtensorMap& ta, const GruProg<T>& P, cudaStream_t s) {

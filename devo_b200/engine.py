@@ -19,12 +19,12 @@ when it enters the ring buffer (replaces devo/devo.py:523-527 + pyramidify, util
 import torch
 
 from . import _lib, cuda_ba, cuda_corr, projective_ops as pops
-from .update import FrozenCast
+from .update import FrozenCast, PackedUpdateWeights
 
 
 class UpdateOperator:
     def __init__(self, update, n_frames, patches_per_frame, n_edges, H, W, C=128, dim=384, levels=(1, 4),
-                 device="cuda", feat_dtype=torch.float16, ba_iterations=2, t0=1, t1=None, fused_gru=True):
+                 device="cuda", feat_dtype=torch.float16, ba_iterations=2, t0=1, t1=None, fused_gru=True, gru="mma"):
         self.update = update
         self.Nf, self.M, self.E = n_frames, patches_per_frame, n_edges
         self.Np = n_frames * patches_per_frame
@@ -34,6 +34,8 @@ class UpdateOperator:
         self.feat_dtype = feat_dtype
         self.ba_iterations = ba_iterations
         self.fused_gru = fused_gru
+        # "mma": fused tcgen05 kernels (csrc/gru_mma.cu); "cublas": cuBLAS Linears + glue kernels (forward_fused)
+        self.gru_mode = gru if (fused_gru and dim == 384) else "cublas"
         self.t0 = t0
         self.t1 = n_frames if t1 is None else t1
         dev, f32, i64 = self.device, torch.float32, torch.int64
@@ -61,6 +63,9 @@ class UpdateOperator:
         self.plan_ij = None
         self.zeros_e = torch.zeros(self.E, dtype=i64, device=dev)
         self.fc = FrozenCast(feat_dtype)
+        self.packed = PackedUpdateWeights(update, feat_dtype, self.corr_ld) if self.gru_mode == "mma" else None
+        self._gru_ws = (torch.empty(_lib.lib().devo_gru_workspace(self.E, max(self.Np, self.Nf * self.Nf)), dtype=torch.uint8, device=dev)
+                        if self.gru_mode == "mma" else None)
         self._side = torch.cuda.Stream(device=dev)
         self._side2 = torch.cuda.Stream(device=dev)
         self._ba_ws = torch.empty(_lib.lib().devo_ba_workspace(self.E, max(self.t1 - self.t0, 0)), dtype=torch.uint8, device=dev)
@@ -117,12 +122,17 @@ class UpdateOperator:
         cur.wait_stream(self._side)
         cur.wait_stream(self._side2)
         # (3) GRU: cached fp16 weights, autocast-identical dtype flow, no host sync
-        ctx = self.imap[:, self.kk]
-        if self.fused_gru:
+        if self.gru_mode == "mma":
+            net, (delta, weight, _) = self.update.forward_mma(
+                self.net, self.imap, self.kk, self.corr_buf, self.plan_kk, self.plan_ij, self.Np, self.Nf * self.Nf,
+                self.packed, net_out=self.net, workspace=self._gru_ws)
+        elif self.fused_gru:
+            ctx = self.imap[:, self.kk]
             net, (delta, weight, _) = self.update.forward_fused(
                 self.net, ctx, corr.view(1, self.E, -1), self.plan_kk, self.plan_ij, self.Np, self.Nf * self.Nf,
                 self.fc, net_out=self.net)
         else:
+            ctx = self.imap[:, self.kk]
             net, (delta, weight, _) = self.update.forward_planned(
                 self.net, ctx, corr.reshape(1, self.E, -1), self.plan_kk, self.plan_ij, self.Np, self.Nf * self.Nf, self.fc)
             self.net.copy_(net)
