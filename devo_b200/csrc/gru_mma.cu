@@ -23,6 +23,7 @@
 //
 // fp32 per-row state (net32 / n32) and the gate scratch use a tile-friendly layout [tile][col/4][128 rows][4]
 // (resp. [tile][col/8][128][8] halfs) so that "one thread per row" accesses are fully coalesced.
+#include <stdlib.h>
 #include <string.h>
 #include <type_traits>
 #include "common.cuh"
@@ -38,18 +39,25 @@ using devo::ElemTraits;
 
 constexpr int kRows = 128;                 // edges per tile = MMA M
 constexpr int kD = 384;                    // hidden width: N of every layer, K of all but the first
-constexpr int kNH = 192;                   // N per MMA / per weight stage
+#ifndef DEVO_GRU_SPLIT
+#define DEVO_GRU_SPLIT 2
+#endif
+constexpr int kSplit = DEVO_GRU_SPLIT;     // CTAs per cluster: each owns kD/kSplit output columns of the same 128 rows
+constexpr int kNC = kD / kSplit;           // N per CTA (128 or 192)
 constexpr int kABlk = kRows * 128;         // one K-block of A: 128 rows x 64 halfs = 16 KB
 constexpr int kASlots = kD / 64;           // 6
-constexpr int kWStage = kNH * 128;         // 24 KB
-constexpr int kWStages = 4;
+constexpr int kWStage = kNC * 128;         // one K-block of this CTA's weight slice (16 / 24 KB)
+constexpr int kWStages = (96 * 1024) / kWStage;   // 6 / 4
 constexpr int kEpiPer = 2;                 // epilogue warps per TMEM lane quarter (each owns a share of the columns)
 constexpr int kEpiThreads = 128 * kEpiPer;
 constexpr int kThreads = 128 + kEpiThreads;
-constexpr int kCB = kD / 32;               // 32-column blocks per row (12)
 constexpr int kMaxLayers = 6;
 constexpr int kChunks = kD / 8;            // 16-byte chunks per row (48)
 constexpr int kCol4 = kD / 4;              // float4 groups per row (96)
+constexpr int kCB = kD / 32;               // 32-column blocks per row (12)
+constexpr int kCBc = kNC / 32;             // ... per CTA (4 / 6)
+constexpr int kCBp = kCBc / kEpiPer;       // ... per epilogue thread (2 / 3)
+static_assert(kD % kSplit == 0 && kNC % 32 == 0 && kCBc % kEpiPer == 0 && kNC % 16 == 0 && kNC <= 256, "bad split");
 
 enum { PRO_NONE = 0, PRO_GATHER = 1, PRO_CAST = 2, PRO_RESID = 3, PRO_RESID_LN = 4 };
 enum { EPI_RELU_A = 0, EPI_LNRELU_A = 1, EPI_ADD3_LN = 2, EPI_RESID = 3, EPI_STORE_A = 4, EPI_STORE_B = 5,
@@ -68,8 +76,10 @@ struct GruProg {
   float eps;
   const T* x16_in;                         // row-major [src_rows,384]: gather source / hidden state in (ADD3)
   const int64_t* idx64;                    // PRO_GATHER: source row per row (-1 => zero row); null => identity
-  const int32_t* gid;                      // PRO_RESID*: group of each row
-  const T* y16;                            // PRO_RESID*: [groups,384] values added through gid
+  const int32_t* gid;                      // PRO_RESID*: group of each row ...
+  const T* y16;                            // ... and the [groups,384] values added through it
+  const int32_t* gid2;                     // PRO_RESID_LN: a second (group, values) pair added after the first
+  const T* y16b;
   const T* inp16;                          // ADD3: imap [n_patches,384]
   const int64_t* kk;                       // ADD3: patch of each row
   float* net32;                            // tile layout
@@ -81,25 +91,47 @@ struct GruProg {
   const T* headB;                          // [4]
   T* delta;                                // [rows,2]
   T* weight;                               // [rows,2]
+  int dbg_mode;                            // timing experiments only (DEVO_GRU_DBG): 1 no A stores, 2 no remote A stores, 4 no tmem ld
+  long long* dbg;                          // optional: %globaltimer stamps of CTA 0 (tools/gru_timing.py)
 };
 
-template <typename T> __device__ __forceinline__ float rnd(float v) { return ElemTraits<T>::to_float(ElemTraits<T>::from_float(v)); }
+// float <-> half conversions always two at a time: cvt.rn.f16x2.f32 (F2FP.PACK_AB) runs at full rate, the scalar
+// cvt.rn.f16.f32 (F2F) only at 16 lanes/clk/SM -- with four scalar conversions per element the epilogue was bound by
+// that one pipe (measured: 2.1 us per layer for 64 elements per thread; tools/gru_timing.py).
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <typename T> __device__ __forceinline__ float2 unpack2(uint32_t u);
+template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+template <> __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u)); }
 
-template <typename T> struct Pack8 {
-  union { uint4 u; T h[8]; };
-};
 template <typename T> __device__ __forceinline__ uint4 pack8(const float* v) {
-  Pack8<T> p;
-#pragma unroll
-  for (int k = 0; k < 8; k++) p.h[k] = ElemTraits<T>::from_float(v[k]);
-  return p.u;
+  return make_uint4(pack2<T>(v[0], v[1]), pack2<T>(v[2], v[3]), pack2<T>(v[4], v[5]), pack2<T>(v[6], v[7]));
 }
 template <typename T> __device__ __forceinline__ void unpack8(uint4 u, float* v) {
-  Pack8<T> p;
-  p.u = u;
-#pragma unroll
-  for (int k = 0; k < 8; k++) v[k] = ElemTraits<T>::to_float(p.h[k]);
+  const float2 a = unpack2<T>(u.x), b = unpack2<T>(u.y), c = unpack2<T>(u.z), d = unpack2<T>(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
 }
+template <typename T> __device__ __forceinline__ uint32_t relu2(uint32_t u);
+template <> __device__ __forceinline__ uint32_t relu2<__half>(uint32_t u) {
+  const __half2 h = __hmax2(*reinterpret_cast<const __half2*>(&u), __float2half2_rn(0.f));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t relu2<__nv_bfloat16>(uint32_t u) {
+  const __nv_bfloat162 h = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&u), __float2bfloat162_rn(0.f));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <typename T> __device__ __forceinline__ uint4 relu8(uint4 u) {
+  return make_uint4(relu2<T>(u.x), relu2<T>(u.y), relu2<T>(u.z), relu2<T>(u.w));
+}
+// round eight floats to T and back (the autocast rounding point of a half-typed intermediate)
+template <typename T> __device__ __forceinline__ void rnd8(float* v) { unpack8<T>(pack8<T>(v), v); }
 
 // byte offset of 16-byte chunk c (0..47) of row r inside the A tile (K-major SWIZZLE_128B, 6 K-blocks)
 __device__ __forceinline__ uint32_t a_off(int r, int c) {
@@ -112,9 +144,16 @@ __device__ __forceinline__ size_t t16(int tile, int c, int r) { return (((size_t
 __device__ __forceinline__ float4 as_f4(uint4 u) {
   return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
 }
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ void stamp(long long* dbg, int slot) {
+  if (dbg != nullptr && blockIdx.x == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    dbg[slot] = t;
+  }
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
-// the 128 epilogue threads only
+// the epilogue threads only
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
 template <typename T>
@@ -123,34 +162,42 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
                                                               const __grid_constant__ CUtensorMap tm_a,
                                                               const __grid_constant__ GruProg<T> P) {
   extern __shared__ unsigned char smem_dyn[];
+  // identical carve-up in every CTA of the cluster (mapa addresses the same offset in a peer)
   unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* As = base;                                   // kASlots x 16 KB
-  unsigned char* Ws = base + kASlots * kABlk;                 // kWStages x 24 KB
+  unsigned char* Ws = base + kASlots * kABlk;                 // kWStages x kWStage
   uint64_t* bars = reinterpret_cast<uint64_t*>(Ws + kWStages * kWStage);
   uint64_t* w_full = bars;                    // [kWStages]
   uint64_t* w_empty = w_full + kWStages;      // [kWStages]
   uint64_t* a_full = w_empty + kWStages;      // [kASlots]
   uint64_t* a_empty = a_full + kASlots;       // [kASlots]
-  uint64_t* acc_full = a_empty + kASlots;     // [1]
-  uint64_t* a_ready = acc_full + 1;           // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);    // bars: 24 x 8 B = 192 B; slot + pad = 16 B
-  int* s_idx = reinterpret_cast<int*>(tmem_slot + 4);   // [128] gather sources of the tile
-  float* s_stat = reinterpret_cast<float*>(s_idx + kRows);            // [kEpiPer][128][2] LayerNorm partials
-  float* s_hacc = s_stat + kEpiPer * kRows * 2;                       // [kEpiPer][128][4] head partials
-  float* s_ln = s_hacc + kEpiPer * kRows * 4;                         // [2][2][384]: gamma, beta of the program's LayerNorms
-  T* s_bias = reinterpret_cast<T*>(s_ln + 4 * kD);                    // [kMaxLayers][384]
-  T* s_head = s_bias + kMaxLayers * kD;                               // [4][384] + [4] (+4 pad)
+  uint64_t* acc_full = a_empty + kASlots;     // [1] count kSplit: the MMAs of a layer are done in EVERY CTA of the cluster
+  uint64_t* a_ready = acc_full + 1;           // [1] count kSplit: every CTA's epilogue has delivered its slice of the next A
+  uint64_t* pro_ready = a_ready + 1;          // [1] local prologue finished
+  uint64_t* stat_bar = pro_ready + 1;         // [1] count kSplit: LayerNorm / head partials of all CTAs have arrived
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);      // 32 barrier slots = 256 B; slot + pad = 16 B
+  int* s_idx = reinterpret_cast<int*>(tmem_slot + 4);                 // [128] gather sources of the tile
+  float* s_stat = reinterpret_cast<float*>(s_idx + kRows);            // [kSplit][kEpiPer][128][2] LayerNorm partials
+  float* s_hacc = s_stat + kSplit * kEpiPer * kRows * 2;              // [kSplit][kEpiPer][128][4] head partials
+  float* s_ln = s_hacc + kSplit * kEpiPer * kRows * 4;                // [2][2][384]: gamma, beta of the program's LayerNorms
+  float* s_bias = s_ln + 4 * kD;                                      // [kMaxLayers][384] biases as fp32
+  T* s_head = reinterpret_cast<T*>(s_bias + kMaxLayers * kD);         // [4][384] + [4] (+4 pad)
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
+  const int rank = (int)cluster_ctarank();    // which column slice of the layer outputs this CTA computes
+  const int tile = blockIdx.x / kSplit;
   const int row0 = tile * kRows;
+  const int col0 = rank * kNC;
 
+  if (threadIdx.x == 0) stamp(P.dbg, 0);
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWStages; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int s = 0; s < kASlots; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    mbar_init(acc_full, 1);
-    mbar_init(a_ready, 1);
+    mbar_init(acc_full, kSplit);
+    mbar_init(a_ready, kSplit);
+    mbar_init(pro_ready, 1);
+    mbar_init(stat_bar, kSplit);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -161,8 +208,12 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
     // read them as broadcasts instead of dependent global loads
     const int t = threadIdx.x - 64, nt = kThreads - 64;
     for (int l = 0; l < P.n_layers; l++)
-      for (int q = t; q < kD / 8; q += nt)
-        reinterpret_cast<uint4*>(s_bias + l * kD)[q] = __ldg(reinterpret_cast<const uint4*>(P.bias[l]) + q);
+      for (int q = t; q < kD / 8; q += nt) {
+        float bv[8];
+        unpack8<T>(__ldg(reinterpret_cast<const uint4*>(P.bias[l]) + q), bv);
+        reinterpret_cast<float4*>(s_bias + l * kD)[2 * q] = make_float4(bv[0], bv[1], bv[2], bv[3]);
+        reinterpret_cast<float4*>(s_bias + l * kD)[2 * q + 1] = make_float4(bv[4], bv[5], bv[6], bv[7]);
+      }
     for (int k = 0; k < 2; k++) {
       if (P.ln_g[k] == nullptr) continue;
       for (int q = t; q < kD / 4; q += nt) {
@@ -177,18 +228,20 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  if (kSplit > 1) cluster_sync_all();         // peers' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const bool has_pro = (P.pro != PRO_NONE);
+  if (threadIdx.x == 0) stamp(P.dbg, 1);
 
   if (warp == 0) {
-    // =========================== TMA producer: weights of every layer (+ the streamed A of layer 0) ============
+    // =========================== TMA producer: this CTA's weight slice of every layer (+ the streamed A of layer 0)
     if (lane == 0) { prefetch_tensormap(&tm_w); if (P.use_w0) prefetch_tensormap(&tm_w0); if (P.stream_a0) prefetch_tensormap(&tm_a); }
     uint32_t stage = 0, phase = 0;
     for (int l = 0; l < P.n_layers; l++) {
       const int nkb = (l == 0) ? P.kblocks0 : kASlots;
       const CUtensorMap* wm = (l == 0 && P.use_w0) ? &tm_w0 : &tm_w;
-      const int wrow = P.w_row[l];
+      const int wrow = P.w_row[l] + col0;
       for (int kb = 0; kb < nkb; kb++) {
         if (l == 0 && P.stream_a0) {
           const int slot = kb % kASlots, use = kb / kASlots;
@@ -196,79 +249,111 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
           mbar_arrive_expect_tx_elect(smem_u32(&a_full[slot]), kABlk);
           tma_load_2d_elect(smem_u32(As) + slot * kABlk, &tm_a, smem_u32(&a_full[slot]), kb * 64, row0);
         }
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-          mbar_wait(&w_empty[stage], phase ^ 1u);
-          mbar_arrive_expect_tx_elect(smem_u32(&w_full[stage]), kWStage);
-          tma_load_2d_elect(smem_u32(Ws) + stage * kWStage, wm, smem_u32(&w_full[stage]), kb * 64, wrow + h * kNH);
-          if (++stage == kWStages) { stage = 0; phase ^= 1u; }
-        }
+        mbar_wait(&w_empty[stage], phase ^ 1u);
+        mbar_arrive_expect_tx_elect(smem_u32(&w_full[stage]), kWStage);
+        tma_load_2d_elect(smem_u32(Ws) + stage * kWStage, wm, smem_u32(&w_full[stage]), kb * 64, wrow);
+        if (++stage == kWStages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ====================================================================
     const uint32_t fmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
-    const uint32_t idesc = umma_idesc_f16(fmt, kNH);
+    const uint32_t idesc = umma_idesc_f16(fmt, kNC);
     const uint64_t ad0 = umma_desc_sw128(smem_u32(As));
     const uint64_t bd0 = umma_desc_sw128(smem_u32(Ws));
-    uint32_t stage = 0, phase = 0, ready_uses = 0;
+    const uint16_t all = (uint16_t)((1u << kSplit) - 1u);
+    uint32_t stage = 0, phase = 0;
     for (int l = 0; l < P.n_layers; l++) {
       const int nkb = (l == 0) ? P.kblocks0 : kASlots;
       const bool streamed = (l == 0 && P.stream_a0);
-      if (l > 0 || has_pro) {          // the A tile is written by the prologue / the previous layer's epilogue
-        mbar_wait(a_ready, ready_uses & 1u);
-        ready_uses++;
+      if (l == 0) {
+        if (has_pro) { mbar_wait(pro_ready, 0u); fence_proxy_async(); tc_fence_after(); }
+      } else {                         // the A tile now holds every CTA's slice of the previous layer's output
+        mbar_wait_cluster(a_ready, (uint32_t)((l - 1) & 1));
+        fence_proxy_async();
         tc_fence_after();
       }
+      if (lane == 0) stamp(P.dbg, 4 + 4 * l);
       for (int kb = 0; kb < nkb; kb++) {
         const int slot = kb % kASlots;
         if (streamed) { mbar_wait(&a_full[slot], (uint32_t)((kb / kASlots) & 1)); tc_fence_after(); }
         const uint64_t ad = ad0 + (uint64_t)(slot * (kABlk >> 4));
+        mbar_wait(&w_full[stage], phase);
+        tc_fence_after();
+        const uint64_t bd = bd0 + (uint64_t)(stage * (kWStage >> 4));
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-          mbar_wait(&w_full[stage], phase);
-          tc_fence_after();
-          const uint64_t bd = bd0 + (uint64_t)(stage * (kWStage >> 4));
-#pragma unroll
-          for (int k4 = 0; k4 < 4; k4++)
-            tc_mma_f16_elect(tmem_base + h * kNH, ad + 2 * k4, bd + 2 * k4, idesc, (kb > 0 || k4 > 0) ? 1u : 0u);
-          tc_commit_elect(smem_u32(&w_empty[stage]));
-          if (++stage == kWStages) { stage = 0; phase ^= 1u; }
-        }
+        for (int k4 = 0; k4 < 4; k4++)
+          tc_mma_f16_elect(tmem_base, ad + 2 * k4, bd + 2 * k4, idesc, (kb > 0 || k4 > 0) ? 1u : 0u);
+        tc_commit_elect(smem_u32(&w_empty[stage]));
+        if (++stage == kWStages) { stage = 0; phase ^= 1u; }
         if (streamed) tc_commit_elect(smem_u32(&a_empty[slot]));
       }
-      tc_commit_elect(smem_u32(acc_full));
+      if (kSplit > 1) tc_commit_mc_elect(smem_u32(acc_full), all);
+      else tc_commit_elect(smem_u32(acc_full));
+      if (lane == 0) stamp(P.dbg, 5 + 4 * l);
     }
     __syncwarp();
   } else if (warp >= 4) {
     // =========================== prologue + epilogues ==========================================================
-    // kEpiPer warps per TMEM lane quarter; a thread owns one row and the column blocks [cb0, cb1) of 32 columns.
+    // kEpiPer warps per TMEM lane quarter; a thread owns one row and kCBp column blocks (32 columns each) of this
+    // CTA's slice.
     const int quarter = warp & 3;
     const int part = (warp - 4) >> 2;               // 0 .. kEpiPer-1
     const int et = threadIdx.x - 128;               // 0 .. kEpiThreads-1
     const int r = quarter * 32 + lane;              // tile row = TMEM lane
     const int grow = row0 + r;                      // global row
     const bool live = grow < P.rows;
-    const int cb0 = part * (kCB / kEpiPer), cb1 = cb0 + kCB / kEpiPer;
+    const int lcb0 = part * kCBp;                   // first local column block of this thread
+    const int gcb0 = rank * kCBc + lcb0;            // ... as a global column block
     const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    unsigned char* arow = As;                       // + a_off(r, c)
-
-    // row statistics of a LayerNorm: combine the partial (sum, sum of squares) of the kEpiPer threads of a row
-    auto ln_stats = [&](float s1, float s2, float& mean, float& rstd) {
-      if (kEpiPer > 1) {
-        s_stat[(part * kRows + r) * 2 + 0] = s1;
-        s_stat[(part * kRows + r) * 2 + 1] = s2;
-        epi_bar();
-        s1 = 0.f; s2 = 0.f;
+    const uint32_t as_addr = smem_u32(As);
+    uint32_t peer_as[kSplit];                       // shared::cluster address of every CTA's A tile
 #pragma unroll
-        for (int p = 0; p < kEpiPer; p++) { s1 += s_stat[(p * kRows + r) * 2 + 0]; s2 += s_stat[(p * kRows + r) * 2 + 1]; }
-        epi_bar();                                  // s_stat may be reused right away
+    for (int p = 0; p < kSplit; p++) peer_as[p] = mapa(as_addr, (uint32_t)p);
+    uint32_t stat_uses = 0;
+
+    // deliver a 16-byte chunk of the next layer's A operand to every CTA of the cluster
+    auto a_store_all = [&](int c, uint4 v) {
+      const uint32_t off = a_off(r, c);
+      if (P.dbg_mode & 1) return;
+#pragma unroll
+      for (int p = 0; p < kSplit; p++) {
+        if (p == rank) *reinterpret_cast<uint4*>(As + off) = v;
+        else if (!(P.dbg_mode & 2)) st_cluster_v4(peer_as[p] + off, v);
       }
+    };
+    // exchange per-row partials (n floats at s_buf[rank][part][r][*]) between all epilogue threads of the cluster
+    auto exchange = [&](float* s_buf, int n, const float* vals) {
+      const uint32_t local = smem_u32(s_buf + ((rank * kEpiPer + part) * kRows + r) * n);
+#pragma unroll
+      for (int p = 0; p < kSplit; p++) {
+        const uint32_t dst = (p == rank) ? 0u : mapa(local, (uint32_t)p);
+        for (int k = 0; k < n; k++) {
+          if (p == rank) s_buf[((rank * kEpiPer + part) * kRows + r) * n + k] = vals[k];
+          else st_cluster_f32(dst + 4 * k, vals[k]);
+        }
+      }
+      if (kSplit > 1) {
+        fence_acq_rel_cluster();
+        epi_bar();
+        if (et < kSplit) mbar_arrive_cluster(mapa(smem_u32(stat_bar), (uint32_t)et));
+        mbar_wait_cluster(stat_bar, stat_uses & 1u);
+        stat_uses++;
+      } else {
+        epi_bar();
+      }
+    };
+    auto ln_stats = [&](float s1, float s2, float& mean, float& rstd) {
+      const float v[2] = {s1, s2};
+      exchange(s_stat, 2, v);
+      s1 = 0.f; s2 = 0.f;
+#pragma unroll
+      for (int p = 0; p < kSplit * kEpiPer; p++) { s1 += s_stat[(p * kRows + r) * 2 + 0]; s2 += s_stat[(p * kRows + r) * 2 + 1]; }
       mean = s1 * (1.0f / kD);
       rstd = rsqrtf(fmaxf(s2 * (1.0f / kD) - mean * mean, 0.f) + P.eps);
     };
 
-    // ---------------- prologue ----------------
+    // ---------------- prologue: every CTA builds the full [128 x 384] A tile itself (no exchange) ----------------
     if (P.pro == PRO_GATHER) {
       if (et < kRows) {
         const int gr = row0 + et;
@@ -303,55 +388,74 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
         }
       }
     } else if (P.pro == PRO_CAST || P.pro == PRO_RESID || P.pro == PRO_RESID_LN) {
+      // x = net32 (+ y16[gid] (+ y16b[gid2])): full rows, redundantly in every CTA of the cluster.  Nothing is written
+      // back here (a peer reads the same net32 columns concurrently): the additions are simply repeated, in the same
+      // order, by the next kernel that needs them -- bit-identical, and race-free.
       const bool resid = (P.pro != PRO_CAST);
       const bool with_ln = (P.pro == PRO_RESID_LN);
-      const int g = (resid && live) ? P.gid[grow] : 0;
-      const T* yrow = resid ? P.y16 + (size_t)g * kD : nullptr;
+      const T* yrow = (resid && live) ? P.y16 + (size_t)P.gid[grow] * kD : nullptr;
+      const T* yrow2 = (with_ln && live && P.gid2) ? P.y16b + (size_t)P.gid2[grow] * kD : nullptr;
+      const int pcb0 = part * (kCB / kEpiPer), pcb1 = pcb0 + kCB / kEpiPer;
       float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-      for (int cb = cb0; cb < cb1; cb++) {
-        float4 f[8];
-        uint4 yu[4];
+      struct Pre { uint4 f[8]; uint4 y[4]; uint4 z[4]; };
+      auto load_pre = [&](int cb, Pre& p) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const int c = cb * 4 + j;
-          f[2 * j] = *reinterpret_cast<const float4*>(P.net32 + t32(tile, 2 * c, r));
-          f[2 * j + 1] = *reinterpret_cast<const float4*>(P.net32 + t32(tile, 2 * c + 1, r));
-          yu[j] = make_uint4(0u, 0u, 0u, 0u);
-          if (resid && live) yu[j] = *reinterpret_cast<const uint4*>(yrow + c * 8);
+          p.f[2 * j] = *reinterpret_cast<const uint4*>(P.net32 + t32(tile, 2 * c, r));
+          p.f[2 * j + 1] = *reinterpret_cast<const uint4*>(P.net32 + t32(tile, 2 * c + 1, r));
+          p.y[j] = make_uint4(0u, 0u, 0u, 0u);
+          p.z[j] = p.y[j];
+          if (yrow) p.y[j] = *reinterpret_cast<const uint4*>(yrow + c * 8);
+          if (yrow2) p.z[j] = *reinterpret_cast<const uint4*>(yrow2 + c * 8);
         }
+      };
+      Pre cur, nxt;
+      load_pre(pcb0, cur);
+#pragma unroll 1
+      for (int cb = pcb0; cb < pcb1; cb++) {
+        if (cb + 1 < pcb1) load_pre(cb + 1, nxt);
         uint32_t st[32];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const int c = cb * 4 + j;
-          float v[8] = {f[2 * j].x, f[2 * j].y, f[2 * j].z, f[2 * j].w, f[2 * j + 1].x, f[2 * j + 1].y, f[2 * j + 1].z, f[2 * j + 1].w};
+          const float4 a = as_f4(cur.f[2 * j]), b = as_f4(cur.f[2 * j + 1]);
+          float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
           if (resid) {
             float y[8];
-            unpack8<T>(yu[j], y);
+            unpack8<T>(cur.y[j], y);
 #pragma unroll
             for (int k = 0; k < 8; k++) v[k] += y[k];
           }
           if (with_ln) {
+            float z[8];
+            unpack8<T>(cur.z[j], z);
 #pragma unroll
-            for (int k = 0; k < 8; k++) { s1 += v[k]; s2 += v[k] * v[k]; st[j * 8 + k] = __float_as_uint(v[k]); }
+            for (int k = 0; k < 8; k++) { v[k] += z[k]; s1 += v[k]; s2 += v[k] * v[k]; st[j * 8 + k] = __float_as_uint(v[k]); }
           } else {
-            if (resid) {
-              *reinterpret_cast<float4*>(P.net32 + t32(tile, 2 * c, r)) = make_float4(v[0], v[1], v[2], v[3]);
-              *reinterpret_cast<float4*>(P.net32 + t32(tile, 2 * c + 1, r)) = make_float4(v[4], v[5], v[6], v[7]);
-            }
-            *reinterpret_cast<uint4*>(arow + a_off(r, c)) = pack8<T>(v);
+            *reinterpret_cast<uint4*>(As + a_off(r, c)) = pack8<T>(v);
           }
         }
         if (with_ln) tmem_st32(trow + cb * 32, st);      // park the fp32 row in TMEM (free until the first MMA)
+        if (cb + 1 < pcb1) cur = nxt;
       }
       if (with_ln) {     // n = LayerNorm(net) -> n32 (float, needed by the gated residual) and the A tile (half)
         tmem_wait_st();
-        float mean, rstd;
-        ln_stats(s1, s2, mean, rstd);
+        // row statistics over the full row: the kEpiPer threads of a row combine through shared memory (CTA-local)
+        s_stat[(part * kRows + r) * 2 + 0] = s1;
+        s_stat[(part * kRows + r) * 2 + 1] = s2;
+        epi_bar();
+        s1 = 0.f; s2 = 0.f;
+#pragma unroll
+        for (int p = 0; p < kEpiPer; p++) { s1 += s_stat[(p * kRows + r) * 2 + 0]; s2 += s_stat[(p * kRows + r) * 2 + 1]; }
+        epi_bar();
+        const float mean = s1 * (1.0f / kD);
+        const float rstd = rsqrtf(fmaxf(s2 * (1.0f / kD) - mean * mean, 0.f) + P.eps);
         const float* gm = s_ln;
         const float* bt = s_ln + kD;
 #pragma unroll 1
-        for (int cb = cb0; cb < cb1; cb++) {
+        for (int cb = pcb0; cb < pcb1; cb++) {
+          const bool mine = (cb / kCBc) == rank;
           uint32_t raw[32];
           tmem_ld32(trow + cb * 32, raw);
           tmem_wait_ld();
@@ -361,9 +465,11 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
             float v[8];
 #pragma unroll
             for (int k = 0; k < 8; k++) v[k] = (__uint_as_float(raw[j * 8 + k]) - mean) * rstd * gm[c * 8 + k] + bt[c * 8 + k];
-            *reinterpret_cast<float4*>(P.n32 + t32(tile, 2 * c, r)) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(P.n32 + t32(tile, 2 * c + 1, r)) = make_float4(v[4], v[5], v[6], v[7]);
-            *reinterpret_cast<uint4*>(arow + a_off(r, c)) = pack8<T>(v);
+            if (mine) {
+              *reinterpret_cast<float4*>(P.n32 + t32(tile, 2 * c, r)) = make_float4(v[0], v[1], v[2], v[3]);
+              *reinterpret_cast<float4*>(P.n32 + t32(tile, 2 * c + 1, r)) = make_float4(v[4], v[5], v[6], v[7]);
+            }
+            *reinterpret_cast<uint4*>(As + a_off(r, c)) = pack8<T>(v);
           }
         }
         tc_fence_before();
@@ -372,14 +478,15 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
     if (has_pro) {
       fence_proxy_async();
       epi_bar();
-      if (et == 0) mbar_arrive(a_ready);
+      if (et == 0) mbar_arrive(pro_ready);
     }
+    if (et == 0) stamp(P.dbg, 2);
 
-    // ---------------- per-layer epilogues ----------------
+    // ---------------- per-layer epilogues (this CTA's column slice) ----------------
     int ln_used = (P.pro == PRO_RESID_LN) ? 1 : 0;
     for (int l = 0; l < P.n_layers; l++) {
       const int epi = P.epi[l];
-      const T* bias = s_bias + l * kD;
+      const float* bias = s_bias + l * kD;
       float s1 = 0.f, s2 = 0.f;
       float hacc[4] = {0.f, 0.f, 0.f, 0.f};
       const T* netrow = nullptr;
@@ -395,10 +502,10 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
       }
       // per-row operands of the element-wise tail, fetched one column block ahead of their use
       struct Aux { uint4 q[12]; };     // RESID: q[0..7] net32 ; GATED: q[0..7] n32, q[8..11] gate ; ADD3: q[0..3] net16, q[4..7] inp16
-      auto load_aux = [&](int cb, Aux& a) {
+      auto load_aux = [&](int gcb, Aux& a) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          const int c = cb * 4 + j;
+          const int c = gcb * 4 + j;
           if (epi == EPI_RESID) {
             a.q[2 * j] = *reinterpret_cast<const uint4*>(P.net32 + t32(tile, 2 * c, r));
             a.q[2 * j + 1] = *reinterpret_cast<const uint4*>(P.net32 + t32(tile, 2 * c + 1, r));
@@ -414,41 +521,61 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
         }
       };
       Aux cur, nxt;
-      load_aux(cb0, cur);                           // issued before the accumulator is ready: overlaps the MMAs
-      mbar_wait(acc_full, (uint32_t)(l & 1));
+      load_aux(gcb0, cur);                          // issued before the accumulator is ready: overlaps the MMAs
+      mbar_wait_cluster(acc_full, (uint32_t)(l & 1));      // every CTA of the cluster is done reading its A tile
       tc_fence_after();
+      if (et == 0) stamp(P.dbg, 6 + 4 * l);
 #pragma unroll 1
-      for (int cb = cb0; cb < cb1; cb++) {
+      for (int i = 0; i < kCBp; i++) {
+        const int lcb = lcb0 + i, gcb = gcb0 + i;
         uint32_t raw[32];
-        tmem_ld32(trow + cb * 32, raw);
-        if (cb + 1 < cb1) load_aux(cb + 1, nxt);
+        if (!(P.dbg_mode & 4)) tmem_ld32(trow + lcb * 32, raw);
+        else {
+#pragma unroll
+          for (int k = 0; k < 32; k++) raw[k] = 0x3f000000u + k;
+        }
+        if (i + 1 < kCBp) load_aux(gcb + 1, nxt);
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          const int c = cb * 4 + j;                 // 16-byte chunk index (8 columns)
+          const int c = gcb * 4 + j;                // global 16-byte chunk index (8 columns)
           float o[8];
           {
-            float bv[8];
-            unpack8<T>(*reinterpret_cast<const uint4*>(bias + c * 8), bv);
-#pragma unroll
-            for (int k = 0; k < 8; k++) o[k] = rnd<T>(__uint_as_float(raw[j * 8 + k]) + bv[k]);   // Linear output (half)
+            const float4 b0 = *reinterpret_cast<const float4*>(bias + c * 8), b1 = *reinterpret_cast<const float4*>(bias + c * 8 + 4);
+            o[0] = __uint_as_float(raw[j * 8 + 0]) + b0.x; o[1] = __uint_as_float(raw[j * 8 + 1]) + b0.y;
+            o[2] = __uint_as_float(raw[j * 8 + 2]) + b0.z; o[3] = __uint_as_float(raw[j * 8 + 3]) + b0.w;
+            o[4] = __uint_as_float(raw[j * 8 + 4]) + b1.x; o[5] = __uint_as_float(raw[j * 8 + 5]) + b1.y;
+            o[6] = __uint_as_float(raw[j * 8 + 6]) + b1.z; o[7] = __uint_as_float(raw[j * 8 + 7]) + b1.w;
           }
+          const uint4 oh = pack8<T>(o);               // the Linear output, rounded to half (autocast)
           if (epi == EPI_RELU_A) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) o[k] = fmaxf(o[k], 0.f);
-            *reinterpret_cast<uint4*>(arow + a_off(r, c)) = pack8<T>(o);
+            a_store_all(c, relu8<T>(oh));             // max(.,0) commutes with the rounding: done on packed halves
+          } else if (epi == EPI_STORE_A || epi == EPI_STORE_B) {
+            if (orow) *reinterpret_cast<uint4*>(orow + c * 8) = oh;
+          } else if (epi == EPI_GATE) {
+            *reinterpret_cast<uint4*>(P.gate16 + t16(tile, c, r)) = oh;
           } else if (epi == EPI_LNRELU_A) {
+            unpack8<T>(oh, o);
 #pragma unroll
             for (int k = 0; k < 8; k++) { s1 += o[k]; s2 += o[k] * o[k]; }
-            *reinterpret_cast<uint4*>(arow + a_off(r, c)) = pack8<T>(o);
+            *reinterpret_cast<uint4*>(As + a_off(r, c)) = oh;                   // parked in the local tile until normalised
           } else if (epi == EPI_ADD3_LN) {
             float a[8], b[8];
+            unpack8<T>(oh, o);
             unpack8<T>(cur.q[j], a);
             unpack8<T>(cur.q[4 + j], b);
 #pragma unroll
-            for (int k = 0; k < 8; k++) { o[k] = rnd<T>(rnd<T>(a[k] + b[k]) + o[k]); s1 += o[k]; s2 += o[k] * o[k]; }
-            *reinterpret_cast<uint4*>(arow + a_off(r, c)) = pack8<T>(o);
+            for (int k = 0; k < 8; k++) a[k] += b[k];
+            rnd8<T>(a);
+#pragma unroll
+            for (int k = 0; k < 8; k++) o[k] += a[k];
+            const uint4 vh = pack8<T>(o);
+            unpack8<T>(vh, o);
+#pragma unroll
+            for (int k = 0; k < 8; k++) { s1 += o[k]; s2 += o[k] * o[k]; }
+            *reinterpret_cast<uint4*>(As + a_off(r, c)) = vh;
           } else if (epi == EPI_RESID) {
+            unpack8<T>(oh, o);
             float4 a = as_f4(cur.q[2 * j]), b = as_f4(cur.q[2 * j + 1]);
             a.x += o[0]; a.y += o[1]; a.z += o[2]; a.w += o[3]; b.x += o[4]; b.y += o[5]; b.z += o[6]; b.w += o[7];
             *reinterpret_cast<float4*>(P.net32 + t32(tile, 2 * c, r)) = a;
@@ -457,17 +584,20 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
               const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
               *reinterpret_cast<uint4*>(orow + c * 8) = pack8<T>(v);
             }
-          } else if (epi == EPI_STORE_A || epi == EPI_STORE_B) {
-            if (orow) *reinterpret_cast<uint4*>(orow + c * 8) = pack8<T>(o);
-          } else if (epi == EPI_GATE) {
-            *reinterpret_cast<uint4*>(P.gate16 + t16(tile, c, r)) = pack8<T>(o);
           } else {   // EPI_GATED_LN / EPI_GATED_HEADS:  x = n + half(half(sigmoid(gate)) * res)
             float g[8];
+            unpack8<T>(oh, o);
             unpack8<T>(cur.q[8 + j], g);
             const float4 a = as_f4(cur.q[2 * j]), b = as_f4(cur.q[2 * j + 1]);
             float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int k = 0; k < 8; k++) x[k] += rnd<T>(rnd<T>(sigmoidf_(g[k])) * o[k]);
+            for (int k = 0; k < 8; k++) g[k] = sigmoidf_(g[k]);
+            rnd8<T>(g);
+#pragma unroll
+            for (int k = 0; k < 8; k++) g[k] *= o[k];
+            rnd8<T>(g);
+#pragma unroll
+            for (int k = 0; k < 8; k++) x[k] += g[k];
             if (epi == EPI_GATED_LN) {
 #pragma unroll
               for (int k = 0; k < 8; k++) { s1 += x[k]; s2 += x[k] * x[k]; raw[j * 8 + k] = __float_as_uint(x[k]); }
@@ -475,7 +605,8 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
               if (orow) *reinterpret_cast<uint4*>(orow + c * 8) = pack8<T>(x);       // new hidden state (half)
               float hw[8];
 #pragma unroll
-              for (int k = 0; k < 8; k++) x[k] = rnd<T>(fmaxf(x[k], 0.f));
+              for (int k = 0; k < 8; k++) x[k] = fmaxf(x[k], 0.f);
+              rnd8<T>(x);
 #pragma unroll
               for (int o4 = 0; o4 < 4; o4++) {
                 unpack8<T>(*reinterpret_cast<const uint4*>(s_head + o4 * kD + c * 8), hw);
@@ -485,26 +616,27 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
             }
           }
         }
-        if (epi == EPI_GATED_LN) tmem_st32(trow + cb * 32, raw);  // fp32 row parked in its own accumulator columns
-        if (cb + 1 < cb1) cur = nxt;
+        if (epi == EPI_GATED_LN) tmem_st32(trow + lcb * 32, raw);  // fp32 row parked in its own accumulator columns
+        if (i + 1 < kCBp) cur = nxt;
       }
+      if (et == 0 && l == 0) stamp(P.dbg, 28);
       // ---------------- row-wise tails ----------------
       if (epi == EPI_LNRELU_A || epi == EPI_ADD3_LN) {
-        // the row (half values) sits in this thread's slice of the A tile: one more pass over shared memory
+        // this thread's slice of the row (half values) sits in the local A tile: one more pass over shared memory
         float mean, rstd;
         ln_stats(s1, s2, mean, rstd);
         const float* gm = s_ln + ln_used * 2 * kD;
         const float* bt = gm + kD;
 #pragma unroll 2
-        for (int c = cb0 * 4; c < cb1 * 4; c++) {
+        for (int c = gcb0 * 4; c < (gcb0 + kCBp) * 4; c++) {
           float v[8];
-          unpack8<T>(*reinterpret_cast<const uint4*>(arow + a_off(r, c)), v);
+          unpack8<T>(*reinterpret_cast<const uint4*>(As + a_off(r, c)), v);
 #pragma unroll
           for (int k = 0; k < 8; k++) v[k] = (v[k] - mean) * rstd * gm[c * 8 + k] + bt[c * 8 + k];
           if (epi == EPI_LNRELU_A) {
 #pragma unroll
             for (int k = 0; k < 8; k++) v[k] = fmaxf(v[k], 0.f);
-            *reinterpret_cast<uint4*>(arow + a_off(r, c)) = pack8<T>(v);
+            a_store_all(c, pack8<T>(v));
           } else {
             *reinterpret_cast<float4*>(P.net32 + t32(tile, 2 * c, r)) = make_float4(v[0], v[1], v[2], v[3]);
             *reinterpret_cast<float4*>(P.net32 + t32(tile, 2 * c + 1, r)) = make_float4(v[4], v[5], v[6], v[7]);
@@ -519,56 +651,56 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
         const float* gm = s_ln + ln_used * 2 * kD;
         const float* bt = gm + kD;
 #pragma unroll 1
-        for (int cb = cb0; cb < cb1; cb++) {
+        for (int i = 0; i < kCBp; i++) {
+          const int lcb = lcb0 + i, gcb = gcb0 + i;
           uint32_t raw[32];
-          tmem_ld32(trow + cb * 32, raw);
+          tmem_ld32(trow + lcb * 32, raw);
           tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 4; j++) {
-            const int c = cb * 4 + j;
+            const int c = gcb * 4 + j;
             float v[8];
 #pragma unroll
             for (int k = 0; k < 8; k++) v[k] = (__uint_as_float(raw[j * 8 + k]) - mean) * rstd * gm[c * 8 + k] + bt[c * 8 + k];
             *reinterpret_cast<float4*>(P.n32 + t32(tile, 2 * c, r)) = make_float4(v[0], v[1], v[2], v[3]);
             *reinterpret_cast<float4*>(P.n32 + t32(tile, 2 * c + 1, r)) = make_float4(v[4], v[5], v[6], v[7]);
-            *reinterpret_cast<uint4*>(arow + a_off(r, c)) = pack8<T>(v);
+            a_store_all(c, pack8<T>(v));
           }
         }
         ln_used++;
       } else if (epi == EPI_GATED_HEADS) {
-        if (kEpiPer > 1) {
-#pragma unroll
-          for (int o4 = 0; o4 < 4; o4++) s_hacc[(part * kRows + r) * 4 + o4] = hacc[o4];
-          epi_bar();
+        exchange(s_hacc, 4, hacc);
+        if (live && part == 0 && rank == 0) {
 #pragma unroll
           for (int o4 = 0; o4 < 4; o4++) {
             hacc[o4] = 0.f;
 #pragma unroll
-            for (int p = 0; p < kEpiPer; p++) hacc[o4] += s_hacc[(p * kRows + r) * 4 + o4];
+            for (int p = 0; p < kSplit * kEpiPer; p++) hacc[o4] += s_hacc[(p * kRows + r) * 4 + o4];
           }
-        }
-        if (live && part == 0) {
-          const float d0 = rnd<T>(hacc[0] + ElemTraits<T>::to_float(s_head[4 * kD + 0]));
-          const float d1 = rnd<T>(hacc[1] + ElemTraits<T>::to_float(s_head[4 * kD + 1]));
-          const float w0 = rnd<T>(hacc[2] + ElemTraits<T>::to_float(s_head[4 * kD + 2]));
-          const float w1 = rnd<T>(hacc[3] + ElemTraits<T>::to_float(s_head[4 * kD + 3]));
-          P.delta[(size_t)grow * 2 + 0] = ElemTraits<T>::from_float(d0);
-          P.delta[(size_t)grow * 2 + 1] = ElemTraits<T>::from_float(d1);
-          P.weight[(size_t)grow * 2 + 0] = ElemTraits<T>::from_float(sigmoidf_(w0));
-          P.weight[(size_t)grow * 2 + 1] = ElemTraits<T>::from_float(sigmoidf_(w1));
+          const uint32_t d = pack2<T>(hacc[0] + ElemTraits<T>::to_float(s_head[4 * kD + 0]), hacc[1] + ElemTraits<T>::to_float(s_head[4 * kD + 1]));
+          const float2 w = unpack2<T>(pack2<T>(hacc[2] + ElemTraits<T>::to_float(s_head[4 * kD + 2]), hacc[3] + ElemTraits<T>::to_float(s_head[4 * kD + 3])));
+          *reinterpret_cast<uint32_t*>(P.delta + (size_t)grow * 2) = d;
+          *reinterpret_cast<uint32_t*>(P.weight + (size_t)grow * 2) = pack2<T>(1.0f / (1.0f + expf(-w.x)), 1.0f / (1.0f + expf(-w.y)));
         }
       }
       tc_fence_before();
-      if (l + 1 < P.n_layers) {       // hand the A tile / the TMEM accumulator back to the MMA warp
-        fence_proxy_async();
+      if (et == 0 && l == 0) stamp(P.dbg, 29);
+      if (l + 1 < P.n_layers) {       // hand the A tiles / the TMEM accumulator back to the MMA warps of the cluster
+        if (kSplit > 1) fence_proxy_async_all(); else fence_proxy_async();   // A-tile writes (local and peers') -> async proxy
+        if (et == 0 && l == 0) stamp(P.dbg, 30);
         epi_bar();
-        if (et == 0) mbar_arrive(a_ready);
+        if (et == 0 && l == 0) stamp(P.dbg, 31);
+        if (kSplit > 1) { if (et < kSplit) mbar_arrive_cluster(mapa(smem_u32(a_ready), (uint32_t)et)); }
+        else if (et == 0) mbar_arrive(a_ready);
       }
+      if (et == 0) stamp(P.dbg, 7 + 4 * l);
     }
   }
-  // teardown
+  // teardown: no CTA may exit while a peer can still write into its shared memory
   tc_fence_before();
   __syncthreads();
+  if (kSplit > 1) cluster_sync_all();
+  if (threadIdx.x == 0) stamp(P.dbg, 3);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
@@ -605,8 +737,12 @@ static int make_map_2d(CUtensorMap* m, int dtype, const void* ptr, uint64_t rows
   return DEVO_OK;
 }
 
-constexpr size_t kSmemBytes = 1024 + (size_t)kASlots * kABlk + (size_t)kWStages * kWStage + 24 * sizeof(uint64_t) + 16 + kRows * sizeof(int) +
-                              (size_t)kEpiPer * kRows * 6 * sizeof(float) + 4 * kD * sizeof(float) + (kMaxLayers * kD + 4 * kD + 8) * 2 + 64;
+constexpr size_t kSmemBytes = 1024 + (size_t)kASlots * kABlk + (size_t)kWStages * kWStage + 32 * sizeof(uint64_t) + 16 + kRows * sizeof(int) +
+                              (size_t)kSplit * kEpiPer * kRows * 6 * sizeof(float) + 4 * kD * sizeof(float) + kMaxLayers * kD * sizeof(float) + (4 * kD + 8) * 2 + 64;
+static_assert(kSmemBytes <= 232448, "shared memory budget");
+
+static long long* g_dbg = nullptr;     // 16 launches x 32 stamps, allocated when DEVO_GRU_TIMING is set
+static int g_dbg_launch = 0;
 
 template <typename T>
 static int launch_prog(const CUtensorMap& tw, const CUtensorMap& tw0, const CUtensorMap& ta, const GruProg<T>& P, cudaStream_t s) {
@@ -617,14 +753,28 @@ static int launch_prog(const CUtensorMap& tw, const CUtensorMap& tw0, const CUte
   }
   const int tiles = (P.rows + kRows - 1) / kRows;
   if (tiles <= 0) return DEVO_OK;
-  gru_mma_kernel<T><<<tiles, kThreads, kSmemBytes, s>>>(tw, tw0, ta, P);
+  GruProg<T> Pd = P;
+  { static int mode = -1; if (mode < 0) { const char* e = getenv("DEVO_GRU_DBG"); mode = e ? atoi(e) : 0; } Pd.dbg_mode = mode; }
+  Pd.dbg = g_dbg ? g_dbg + 32 * (g_dbg_launch++ % 16) : nullptr;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(tiles * kSplit), 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;      // kSplit CTAs share one 128-row tile
+  attr[0].val.clusterDim.x = kSplit; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DEVO_CUDA(cudaLaunchKernelEx(&cfg, gru_mma_kernel<T>, tw, tw0, ta, Pd));
   DEVO_LAUNCH_CHECK("gru_mma");
   return DEVO_OK;
 }
 
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 struct GruWs {
-  size_t net32, n32, gate16, x16a, x16b, g16, f16, y16, hy16, total;
+  size_t net32, n32, gate16, x16a, x16b, g16, f16, y16, hy16, hy16b, total;
 };
 static GruWs gru_ws(int E, int max_groups) {
   GruWs w;
@@ -640,6 +790,7 @@ static GruWs gru_ws(int E, int max_groups) {
   w.f16 = off;   off += al256((size_t)E * kD * 2);
   w.y16 = off;   off += al256(G * kD * 2);
   w.hy16 = off;  off += al256(G * kD * 2);
+  w.hy16b = off; off += al256(G * kD * 2);
   w.total = off;
   return w;
 }
@@ -659,12 +810,13 @@ static int gru_update_impl(const devo_gru_weights_t* Wt, const devo_gru_io_t* io
   T* f16 = (T*)(w + L.f16);
   T* y16 = (T*)(w + L.y16);
   T* hy16 = (T*)(w + L.hy16);
+  T* hy16b = (T*)(w + L.hy16b);
   const T* bias = (const T*)Wt->bias;            // [19,384]: row 0 = corr[0], row 1+i = stacked layer i
   auto B = [&](int layer) { return bias + (size_t)(1 + layer) * kD; };
   CUtensorMap tw, tw0, ta;
-  int rc = make_map_2d(&tw, dtype, Wt->W, 18 * kD, kD, kD, kNH);
+  int rc = make_map_2d(&tw, dtype, Wt->W, 18 * kD, kD, kD, kNC);
   if (rc != DEVO_OK) return rc;
-  rc = make_map_2d(&tw0, dtype, Wt->W0, kD, (uint64_t)io->corr_ld, (uint64_t)io->corr_ld, kNH);
+  rc = make_map_2d(&tw0, dtype, Wt->W0, kD, (uint64_t)io->corr_ld, (uint64_t)io->corr_ld, kNC);
   if (rc != DEVO_OK) return rc;
   rc = make_map_2d(&ta, dtype, io->corr16, (uint64_t)E, (uint64_t)io->corr_ld, (uint64_t)io->corr_ld, kRows);
   if (rc != DEVO_OK) return rc;
@@ -723,7 +875,7 @@ static int gru_update_impl(const devo_gru_weights_t* Wt, const devo_gru_io_t* io
       P.rows = mg; P.src_rows = mg;
       P.n_layers = 1; P.pro = PRO_GATHER; P.x16_in = y16; P.idx64 = nullptr;
       P.w_row[0] = (8 + 3 * k) * kD; P.epi[0] = EPI_STORE_A; P.bias[0] = B(8 + 3 * k);     // h
-      P.out16_a = hy16;
+      P.out16_a = k == 0 ? hy16 : hy16b;
       rc = launch_prog<T>(tw, tw0, ta, P, s);
       if (rc != DEVO_OK) return rc;
     }
@@ -732,7 +884,7 @@ static int gru_update_impl(const devo_gru_weights_t* Wt, const devo_gru_io_t* io
   {
     GruProg<T> P = base;
     P.n_layers = 6; P.pro = PRO_RESID_LN;
-    P.gid = io->gid_ij; P.y16 = hy16;
+    P.gid = io->gid_kk; P.y16 = hy16; P.gid2 = io->gid_ij; P.y16b = hy16b;     // net + agg_kk + agg_ij, in this order
     P.ln_g[0] = Wt->ln_gamma + 2 * kD; P.ln_b[0] = Wt->ln_beta + 2 * kD;
     P.ln_g[1] = Wt->ln_gamma + 3 * kD; P.ln_b[1] = Wt->ln_beta + 3 * kD;
     const int epis[6] = {EPI_GATE, EPI_RELU_A, EPI_GATED_LN, EPI_GATE, EPI_RELU_A, EPI_GATED_HEADS};
@@ -751,6 +903,32 @@ static int gru_update_impl(const devo_gru_weights_t* Wt, const devo_gru_io_t* io
 extern "C" {
 
 size_t devo_gru_workspace(int E, int max_groups) { return gru_ws(E, max_groups).total; }
+
+// debug (tools/gru_timing.py): enable / read back the %globaltimer stamps of CTA 0 of the last 16 launches
+int devo_gru_debug_timing(long long* host_out) {
+  if (!g_dbg) {
+    if (cudaMalloc(&g_dbg, 16 * 32 * sizeof(long long)) != cudaSuccess) return -1;
+    cudaMemset(g_dbg, 0, 16 * 32 * sizeof(long long));
+  }
+  g_dbg_launch = 0;
+  {
+    int nclusters = -1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(48 * kSplit, 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kSplit; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaFuncSetAttribute(gru_mma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, gru_mma_kernel<__half>, &cfg);
+    fprintf(stderr, "gru_mma: split %d, max co-resident clusters %d (%s)\n", kSplit, nclusters, cudaGetErrorString(e));
+  }
+  if (host_out) return (int)cudaMemcpy(host_out, g_dbg, 16 * 32 * sizeof(long long), cudaMemcpyDeviceToHost);
+  return 0;
+}
 
 int devo_gru_update(const devo_gru_weights_t* weights, const devo_gru_io_t* io, int dtype, void* workspace,
                     size_t workspace_bytes, void* stream) {

@@ -74,3 +74,18 @@ def test_gru_mma_bf16_and_in_place_hidden_state():
     assert out_net.data_ptr() == state.data_ptr()
     assert (state.float() - ref_net).abs().max().item() <= 1e-1 * max(ref_net.abs().max().item(), 1.0)
     assert (d.float() - ref_d.float()).abs().max().item() <= 1e-1
+
+
+def test_gru_mma_is_deterministic():
+    """cluster hand-offs (DSMEM A-tile slices, LayerNorm partials) must not race: repeated runs are bit-identical"""
+    from devo_b200.update import PackedUpdateWeights
+    up, net, imap, corr, ii, jj, kk, plan_kk, plan_ij, Np, pairs = _problem(8, 96, 0)
+    packed = PackedUpdateWeights(up, torch.float16, 896)
+    outs = []
+    with torch.no_grad():
+        for _ in range(6):
+            n, (d, w, _) = up.forward_mma(net, imap, kk, corr, plan_kk, plan_ij, Np, pairs, packed)
+            outs.append((n.clone(), d.clone(), w.clone()))
+    torch.cuda.synchronize()
+    for o in outs[1:]:
+        assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]) and torch.equal(o[2], outs[0][2])

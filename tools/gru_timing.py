@@ -1,0 +1,74 @@
+"""Where the time goes inside the fused update operator (csrc/gru_mma.cu): CUDA-event time of forward_mma vs the
+cuBLAS + glue path, and the %globaltimer stamps CTA 0 of each of the 10 launches records.
+    python tools/gru_timing.py"""
+import ctypes
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+
+
+def main():
+    from devo_b200 import _lib, cuda_ba
+    from devo_b200.update import FrozenCast, PackedUpdateWeights, Update
+    from problems import fully_connected_graph
+    torch.manual_seed(0)
+    nf, m = 8, 96
+    ii, jj, kk = [t.cuda() for t in fully_connected_graph(nf, m)]
+    E, Np = ii.numel(), nf * m
+    up = Update(3).cuda().eval()
+    net = (0.5 * torch.randn(1, E, 384, device="cuda")).half()
+    imap = (0.25 * torch.randn(1, Np, 384, device="cuda")).half()
+    corr = torch.zeros(E, 896, device="cuda", dtype=torch.float16)
+    corr[:, :882] = torch.randn(E, 882, device="cuda").half()
+    plan_kk = cuda_ba.GraphPlan(kk, jj, Np, nf)
+    plan_ij = cuda_ba.GraphPlan(ii * 12345 + jj, torch.zeros_like(ii), -1, 1, want_neighbors=False)
+    fc = FrozenCast(torch.float16)
+    packed = PackedUpdateWeights(up, torch.float16, 896)
+    ctx = imap[:, kk].contiguous()
+
+    def timeit(fn, n=50):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n * 1e3
+
+    with torch.no_grad():
+        t_mma = timeit(lambda: up.forward_mma(net, imap, kk, corr, plan_kk, plan_ij, Np, nf * nf, packed))
+        t_cub = timeit(lambda: up.forward_fused(net, ctx, corr.view(1, E, 896), plan_kk, plan_ij, Np, nf * nf, fc))
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            up.forward_mma(net, imap, kk, corr, plan_kk, plan_ij, Np, nf * nf, packed)
+        t_graph = timeit(g.replay)
+        print("forward_mma %.1f us (graph replay %.1f us)   cuBLAS+glue path %.1f us (eager)" % (t_mma, t_graph, t_cub))
+        L = _lib.lib()
+        L.devo_gru_debug_timing.argtypes = [ctypes.c_void_p]
+        L.devo_gru_debug_timing(None)
+        up.forward_mma(net, imap, kk, corr, plan_kk, plan_ij, Np, nf * nf, packed)
+        torch.cuda.synchronize()
+        buf = (ctypes.c_longlong * (16 * 32))()
+        L.devo_gru_debug_timing(buf)
+    names = ["corr+norm", "c1", "c2", "agg_kk g,f", "agg_kk h", "agg_ij g,f", "agg_ij h", "gru+heads"]
+    nl = [3, 2, 2, 2, 1, 2, 1, 6]
+    for k, (nm, n) in enumerate(zip(names, nl)):
+        s = [buf[32 * k + q] for q in range(32)]
+        t0 = s[0]
+        rel = lambda q: (s[q] - t0) / 1e3 if s[q] else float("nan")
+        line = "%-12s setup %.1f pro %.1f |" % (nm, rel(1), rel(2))
+        for l in range(n):
+            line += " L%d mma %.1f-%.1f epi %.1f-%.1f |" % (l, rel(4 + 4 * l), rel(5 + 4 * l), rel(6 + 4 * l), rel(7 + 4 * l))
+        line += " end %.1f us  [L0 epi: loop %.1f tail %.1f fences %.1f bar %.1f]" % (rel(3), rel(28), rel(29), rel(30), rel(31))
+        print(line)
+
+
+if __name__ == "__main__":
+    main()
