@@ -48,9 +48,10 @@ constexpr int kABlk = kRows * 128;         // one K-block of A: 128 rows x 64 ha
 constexpr int kASlots = kD / 64;           // 6
 constexpr int kWStage = kNC * 128;         // one K-block of this CTA's weight slice (16 / 24 KB)
 constexpr int kWStages = (96 * 1024) / kWStage;   // 6 / 4
-constexpr int kEpiPer = 2;                 // epilogue warps per TMEM lane quarter (each owns a share of the columns)
+constexpr int kEpiPer = 3;                 // epilogue warps per TMEM lane quarter (each owns a share of the columns)
 constexpr int kEpiThreads = 128 * kEpiPer;
-constexpr int kThreads = 128 + kEpiThreads;
+constexpr int kFirstEpiWarp = 2;            // warps 0 (TMA) and 1 (MMA) + the epilogue warps; any 4 consecutive warps cover the 4 TMEM lane quarters
+constexpr int kThreads = 32 * kFirstEpiWarp + kEpiThreads;
 constexpr int kMaxLayers = 6;
 constexpr int kChunks = kD / 8;            // 16-byte chunks per row (48)
 constexpr int kCol4 = kD / 4;              // float4 groups per row (96)
@@ -91,7 +92,6 @@ struct GruProg {
   const T* headB;                          // [4]
   T* delta;                                // [rows,2]
   T* weight;                               // [rows,2]
-  int dbg_mode;                            // timing experiments only (DEVO_GRU_DBG): 1 no A stores, 2 no remote A stores, 4 no tmem ld
   long long* dbg;                          // optional: %globaltimer stamps of CTA 0 (tools/gru_timing.py)
 };
 
@@ -156,6 +156,415 @@ __device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.
 // the epilogue threads only
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
+// ---- the epilogue role: one thread per (row, column share).  Every element-wise tail is a separate template
+// instantiation (constexpr EPI / PRO), selected once per layer by a warp-uniform switch: tight straight-line loops
+// instead of a branch chain per 8 columns (the first version spent ~150 instructions per 8 columns; tools/gru_timing.py).
+template <typename T>
+struct Epi {
+  const GruProg<T>& P;
+  unsigned char* As;
+  float* s_stat; float* s_hacc; const float* s_ln; const float* s_bias; const T* s_head; int* s_idx;
+  uint64_t* acc_full; uint64_t* a_ready; uint64_t* pro_ready; uint64_t* stat_bar;
+  int rank, tile, row0, quarter, part, et, r, grow;
+  bool live;
+  int lcb0, gcb0;
+  uint32_t trow;
+  uint32_t peer_as[kSplit];
+  uint32_t stat_uses;
+  int ln_used;
+  float* net_r;        // tile-layout bases of this thread's row: float4 group q at net_r + q * (kRows * 4)
+  float* n32_r;
+  T* gate_r;           // half8 chunk c at gate_r + c * (kRows * 8)
+
+  __device__ __forceinline__ Epi(const GruProg<T>& P_) : P(P_) {}
+
+  __device__ __forceinline__ static const uint4* f4(const float* base, int q) { return reinterpret_cast<const uint4*>(base + (size_t)q * (kRows * 4)); }
+  __device__ __forceinline__ static float4* f4w(float* base, int q) { return reinterpret_cast<float4*>(base + (size_t)q * (kRows * 4)); }
+
+  // deliver a 16-byte chunk of the next layer's A operand to every CTA of the cluster
+  __device__ __forceinline__ void a_store_all(int c, uint4 v) {
+    const uint32_t off = a_off(r, c);
+#pragma unroll
+    for (int p = 0; p < kSplit; p++) {
+      if (p == rank) *reinterpret_cast<uint4*>(As + off) = v;
+      else st_cluster_v4(peer_as[p] + off, v);
+    }
+  }
+  // exchange per-row partials (N floats at s_buf[rank][part][r][*]) between all epilogue threads of the cluster
+  template <int N>
+  __device__ __forceinline__ void exchange(float* s_buf, const float* vals) {
+    float* mine = s_buf + ((rank * kEpiPer + part) * kRows + r) * N;
+#pragma unroll
+    for (int k = 0; k < N; k++) mine[k] = vals[k];
+    if (kSplit > 1) {
+      const uint32_t local = smem_u32(mine);
+#pragma unroll
+      for (int p = 0; p < kSplit; p++) {
+        if (p == rank) continue;
+        const uint32_t dst = mapa(local, (uint32_t)p);
+#pragma unroll
+        for (int k = 0; k < N; k++) st_cluster_f32(dst + 4 * k, vals[k]);
+      }
+      // no acquire.cluster on the waiting side (it invalidates L1 -- CCTL.IVALL -- on every wait, and everything
+      // exchanged lives in shared memory); the release.cluster arrive after the CTA barrier publishes the stores
+      epi_bar();
+      if (et < kSplit) mbar_arrive_cluster(mapa(smem_u32(stat_bar), (uint32_t)et));
+      mbar_wait(stat_bar, stat_uses & 1u);
+      stat_uses++;
+    } else {
+      epi_bar();
+    }
+  }
+  __device__ __forceinline__ void ln_stats(float s1, float s2, float& mean, float& rstd) {
+    const float v[2] = {s1, s2};
+    exchange<2>(s_stat, v);
+    s1 = 0.f; s2 = 0.f;
+#pragma unroll
+    for (int p = 0; p < kSplit * kEpiPer; p++) { s1 += s_stat[(p * kRows + r) * 2 + 0]; s2 += s_stat[(p * kRows + r) * 2 + 1]; }
+    mean = s1 * (1.0f / kD);
+    rstd = rsqrtf(fmaxf(s2 * (1.0f / kD) - mean * mean, 0.f) + P.eps);
+  }
+
+  // ---------------- prologue: every CTA builds the full [128 x 384] A tile itself (no exchange) ----------------
+  template <int PRO>
+  __device__ __forceinline__ void prologue() {
+    if constexpr (PRO == PRO_GATHER) {
+      if (et < kRows) {
+        const int gr = row0 + et;
+        int src = -1;
+        if (gr < P.rows) {
+          const long long j = P.idx64 ? (long long)P.idx64[gr] : (long long)gr;
+          src = (j >= 0 && j < (long long)P.src_rows) ? (int)j : -1;
+        }
+        s_idx[et] = src;
+      }
+      epi_bar();
+      // cooperative: 48 consecutive threads copy one 768-byte source row; kBatch independent 16-byte loads in flight
+      constexpr int kPer = kRows * kChunks / kEpiThreads;     // chunks per thread
+      constexpr int kBatch = (kPer % 12 == 0) ? 12 : 8;
+      static_assert(kPer % kBatch == 0, "gather batches");
+#pragma unroll 1
+      for (int b = 0; b < kPer / kBatch; b++) {
+        uint4 v[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; u++) {
+          const int q = et + (b * kBatch + u) * kEpiThreads;
+          const int rr = q / kChunks, c = q - rr * kChunks;
+          const int s = s_idx[rr];
+          v[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (s >= 0) v[u] = *reinterpret_cast<const uint4*>(P.x16_in + (size_t)s * kD + c * 8);
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; u++) {
+          const int q = et + (b * kBatch + u) * kEpiThreads;
+          const int rr = q / kChunks, c = q - rr * kChunks;
+          *reinterpret_cast<uint4*>(As + a_off(rr, c)) = v[u];
+        }
+      }
+    } else {
+      // x = net32 (+ y16[gid] (+ y16b[gid2])): full rows, redundantly in every CTA of the cluster.  Nothing is written
+      // back here (a peer reads the same net32 columns concurrently): the additions are simply repeated, in the same
+      // order, by the next kernel that needs them -- bit-identical, and race-free.
+      constexpr bool resid = (PRO != PRO_CAST);
+      constexpr bool with_ln = (PRO == PRO_RESID_LN);
+      const T* yrow = (resid && live) ? P.y16 + (size_t)P.gid[grow] * kD : nullptr;
+      const T* yrow2 = (with_ln && live && P.gid2) ? P.y16b + (size_t)P.gid2[grow] * kD : nullptr;
+      constexpr int kPcb = kCB / kEpiPer;
+      const int pcb0 = part * kPcb;
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int i = 0; i < kPcb; i++) {
+        const int cb = pcb0 + i;
+        uint4 f[8], y[4], z[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int c = cb * 4 + j;
+          f[2 * j] = *f4(net_r, 2 * c);
+          f[2 * j + 1] = *f4(net_r, 2 * c + 1);
+          if (resid) { y[j] = make_uint4(0u, 0u, 0u, 0u); if (yrow) y[j] = *reinterpret_cast<const uint4*>(yrow + c * 8); }
+          if (with_ln) { z[j] = make_uint4(0u, 0u, 0u, 0u); if (yrow2) z[j] = *reinterpret_cast<const uint4*>(yrow2 + c * 8); }
+        }
+        uint32_t st[32];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int c = cb * 4 + j;
+          const float4 a = as_f4(f[2 * j]), b = as_f4(f[2 * j + 1]);
+          float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+          if (resid) {
+            float t[8];
+            unpack8<T>(y[j], t);
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] += t[k];
+          }
+          if (with_ln) {
+            float t[8];
+            unpack8<T>(z[j], t);
+#pragma unroll
+            for (int k = 0; k < 8; k++) { v[k] += t[k]; s1 += v[k]; s2 += v[k] * v[k]; st[j * 8 + k] = __float_as_uint(v[k]); }
+          } else {
+            *reinterpret_cast<uint4*>(As + a_off(r, c)) = pack8<T>(v);
+          }
+        }
+        if (with_ln) tmem_st32(trow + cb * 32, st);      // park the fp32 row in TMEM (free until the first MMA)
+      }
+      if (with_ln) {     // n = LayerNorm(net) -> n32 (float, needed by the gated residual) and the A tile (half)
+        tmem_wait_st();
+        // row statistics over the full row: the kEpiPer threads of a row combine through shared memory (CTA-local)
+        s_stat[(part * kRows + r) * 2 + 0] = s1;
+        s_stat[(part * kRows + r) * 2 + 1] = s2;
+        epi_bar();
+        s1 = 0.f; s2 = 0.f;
+#pragma unroll
+        for (int p = 0; p < kEpiPer; p++) { s1 += s_stat[(p * kRows + r) * 2 + 0]; s2 += s_stat[(p * kRows + r) * 2 + 1]; }
+        epi_bar();
+        const float mean = s1 * (1.0f / kD);
+        const float rstd = rsqrtf(fmaxf(s2 * (1.0f / kD) - mean * mean, 0.f) + P.eps);
+        const float* gm = s_ln;
+        const float* bt = s_ln + kD;
+#pragma unroll 1
+        for (int i = 0; i < kPcb; i++) {
+          const int cb = pcb0 + i;
+          const bool mine = (cb / kCBc) == rank;
+          uint32_t raw[32];
+          tmem_ld32(trow + cb * 32, raw);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int c = cb * 4 + j;
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = (__uint_as_float(raw[j * 8 + k]) - mean) * rstd * gm[c * 8 + k] + bt[c * 8 + k];
+            if (mine) {
+              *f4w(n32_r, 2 * c) = make_float4(v[0], v[1], v[2], v[3]);
+              *f4w(n32_r, 2 * c + 1) = make_float4(v[4], v[5], v[6], v[7]);
+            }
+            *reinterpret_cast<uint4*>(As + a_off(r, c)) = pack8<T>(v);
+          }
+        }
+        tc_fence_before();
+        ln_used = 1;
+      }
+    }
+    fence_proxy_async();
+    epi_bar();
+    if (et == 0) mbar_arrive(pro_ready);
+  }
+
+  // ---------------- one layer's epilogue over this thread's columns ----------------
+  // Compact loops on purpose: one 16-byte chunk (8 columns) per iteration, not unrolled.  The fully unrolled version
+  // was ~2500 straight-line instructions per gated layer and stalled on instruction fetch (ncu: 35 % "no_instructions").
+  template <int EPI>
+  __device__ __forceinline__ void layer(int l) {
+    constexpr bool kGated = (EPI == EPI_GATED_LN || EPI == EPI_GATED_HEADS);
+    constexpr int kAux = (EPI == EPI_RESID || EPI == EPI_ADD3_LN) ? 2 : (kGated ? 3 : 1);
+    constexpr int kIter = kCBp * 4;                 // 16-byte chunks per thread
+    const float* bias = s_bias + l * kD;
+    float s1 = 0.f, s2 = 0.f;
+    float hacc[4] = {0.f, 0.f, 0.f, 0.f};
+    const T* netrow = nullptr;
+    const T* inprow = nullptr;
+    if (EPI == EPI_ADD3_LN && live) {
+      netrow = P.x16_in + (size_t)grow * kD;
+      inprow = P.inp16 + (size_t)P.kk[grow] * kD;
+    }
+    T* orow = nullptr;
+    if (live) {
+      if (EPI == EPI_STORE_A || EPI == EPI_RESID || EPI == EPI_GATED_HEADS || EPI == EPI_ADD3_LN) orow = P.out16_a ? P.out16_a + (size_t)grow * kD : nullptr;
+      if (EPI == EPI_STORE_B) orow = P.out16_b ? P.out16_b + (size_t)grow * kD : nullptr;
+    }
+    const int c0 = gcb0 * 4;                        // first global chunk of this thread
+    const uint32_t tcol = trow + lcb0 * 32;         // its first accumulator column
+    // per-row operands of the element-wise tail, fetched one chunk ahead of their use
+    // RESID: q[0..1] net32 ; GATED: q[0..1] n32, q[2] gate ; ADD3: q[0] net16, q[1] inp16
+    auto load_aux = [&](int c, uint4* q) {
+      if constexpr (EPI == EPI_RESID) {
+        q[0] = *f4(net_r, 2 * c);
+        q[1] = *f4(net_r, 2 * c + 1);
+      } else if constexpr (kGated) {
+        q[0] = *f4(n32_r, 2 * c);
+        q[1] = *f4(n32_r, 2 * c + 1);
+        q[2] = *reinterpret_cast<const uint4*>(gate_r + (size_t)c * (kRows * 8));
+      } else if constexpr (EPI == EPI_ADD3_LN) {
+        q[0] = make_uint4(0u, 0u, 0u, 0u);
+        q[1] = q[0];
+        if (live) { q[0] = *reinterpret_cast<const uint4*>(netrow + c * 8); q[1] = __ldg(reinterpret_cast<const uint4*>(inprow + c * 8)); }
+      }
+    };
+    uint4 cur[kAux], nxt[kAux];
+    if constexpr (kAux > 1) load_aux(c0, cur);           // issued before the accumulator is ready: overlaps the MMAs
+    mbar_wait(acc_full, (uint32_t)(l & 1));              // every CTA of the cluster is done reading its A tile
+    tc_fence_after();
+    if (et == 0) stamp(P.dbg, 6 + 4 * l);
+    // software pipeline: the accumulator chunk and the row operands of iteration i+1 are in flight while chunk i is
+    // processed (one thread otherwise pays the TMEM + L2 latency kIter times in a row)
+    uint32_t raw[8], rawn[8];
+    tmem_ld8(tcol, raw);
+    tmem_wait_ld();
+#pragma unroll 1
+    for (int i = 0; i < kIter; i++) {
+      const int c = c0 + i;                         // global 16-byte chunk index (8 columns)
+      if (i + 1 < kIter) tmem_ld8(tcol + (i + 1) * 8, rawn);
+      if constexpr (kAux > 1) { if (i + 1 < kIter) load_aux(c + 1, nxt); }
+      float o[8];
+      {
+        const float4 b0 = *reinterpret_cast<const float4*>(bias + c * 8), b1 = *reinterpret_cast<const float4*>(bias + c * 8 + 4);
+        o[0] = __uint_as_float(raw[0]) + b0.x; o[1] = __uint_as_float(raw[1]) + b0.y;
+        o[2] = __uint_as_float(raw[2]) + b0.z; o[3] = __uint_as_float(raw[3]) + b0.w;
+        o[4] = __uint_as_float(raw[4]) + b1.x; o[5] = __uint_as_float(raw[5]) + b1.y;
+        o[6] = __uint_as_float(raw[6]) + b1.z; o[7] = __uint_as_float(raw[7]) + b1.w;
+      }
+      const uint4 oh = pack8<T>(o);                 // the Linear output, rounded to half (autocast)
+      if constexpr (EPI == EPI_RELU_A) {
+        a_store_all(c, relu8<T>(oh));               // max(.,0) commutes with the rounding: done on packed halves
+      } else if constexpr (EPI == EPI_STORE_A || EPI == EPI_STORE_B) {
+        if (orow) *reinterpret_cast<uint4*>(orow + c * 8) = oh;
+      } else if constexpr (EPI == EPI_GATE) {
+        *reinterpret_cast<uint4*>(gate_r + (size_t)c * (kRows * 8)) = oh;
+      } else if constexpr (EPI == EPI_LNRELU_A) {
+        unpack8<T>(oh, o);
+#pragma unroll
+        for (int k = 0; k < 8; k++) { s1 += o[k]; s2 += o[k] * o[k]; }
+        *reinterpret_cast<uint4*>(As + a_off(r, c)) = oh;                     // parked in the local tile until normalised
+      } else if constexpr (EPI == EPI_ADD3_LN) {
+        float a[8], b[8];
+        unpack8<T>(oh, o);
+        unpack8<T>(cur[0], a);
+        unpack8<T>(cur[1], b);
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] += b[k];
+        rnd8<T>(a);
+#pragma unroll
+        for (int k = 0; k < 8; k++) o[k] += a[k];
+        const uint4 vh = pack8<T>(o);
+        unpack8<T>(vh, o);
+#pragma unroll
+        for (int k = 0; k < 8; k++) { s1 += o[k]; s2 += o[k] * o[k]; }
+        *reinterpret_cast<uint4*>(As + a_off(r, c)) = vh;
+      } else if constexpr (EPI == EPI_RESID) {
+        unpack8<T>(oh, o);
+        float4 a = as_f4(cur[0]), b = as_f4(cur[1]);
+        a.x += o[0]; a.y += o[1]; a.z += o[2]; a.w += o[3]; b.x += o[4]; b.y += o[5]; b.z += o[6]; b.w += o[7];
+        *f4w(net_r, 2 * c) = a;
+        *f4w(net_r, 2 * c + 1) = b;
+        if (orow) {
+          const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+          *reinterpret_cast<uint4*>(orow + c * 8) = pack8<T>(v);
+        }
+      } else {   // EPI_GATED_LN / EPI_GATED_HEADS:  x = n + half(half(sigmoid(gate)) * res)
+        float g[8];
+        unpack8<T>(oh, o);
+        unpack8<T>(cur[2], g);
+        const float4 a = as_f4(cur[0]), b = as_f4(cur[1]);
+        float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int k = 0; k < 8; k++) g[k] = sigmoidf_(g[k]);
+        rnd8<T>(g);
+#pragma unroll
+        for (int k = 0; k < 8; k++) g[k] *= o[k];
+        rnd8<T>(g);
+#pragma unroll
+        for (int k = 0; k < 8; k++) x[k] += g[k];
+        if constexpr (EPI == EPI_GATED_LN) {
+#pragma unroll
+          uint32_t xs[8];
+#pragma unroll
+          for (int k = 0; k < 8; k++) { s1 += x[k]; s2 += x[k] * x[k]; xs[k] = __float_as_uint(x[k]); }
+          tmem_st8(tcol + i * 8, xs);               // fp32 row parked in its own accumulator columns
+        } else {
+          if (orow) *reinterpret_cast<uint4*>(orow + c * 8) = pack8<T>(x);         // new hidden state (half)
+          float hw[8];
+#pragma unroll
+          for (int k = 0; k < 8; k++) x[k] = fmaxf(x[k], 0.f);
+          rnd8<T>(x);
+#pragma unroll
+          for (int o4 = 0; o4 < 4; o4++) {
+            unpack8<T>(*reinterpret_cast<const uint4*>(s_head + o4 * kD + c * 8), hw);
+#pragma unroll
+            for (int k = 0; k < 8; k++) hacc[o4] += x[k] * hw[k];
+          }
+        }
+      }
+      if constexpr (kAux > 1) {
+#pragma unroll
+        for (int k = 0; k < kAux; k++) cur[k] = nxt[k];
+      }
+      tmem_wait_ld();
+#pragma unroll
+      for (int k = 0; k < 8; k++) raw[k] = rawn[k];
+    }
+    if (et == 0 && l == 0) stamp(P.dbg, 28);
+    // ---------------- row-wise tails ----------------
+    if constexpr (EPI == EPI_LNRELU_A || EPI == EPI_ADD3_LN) {
+      // this thread's slice of the row (half values) sits in the local A tile: one more pass over shared memory
+      float mean, rstd;
+      ln_stats(s1, s2, mean, rstd);
+      const float* gm = s_ln + ln_used * 2 * kD;
+      const float* bt = gm + kD;
+#pragma unroll 1
+      for (int i = 0; i < kIter; i++) {
+        const int c = c0 + i;
+        float v[8];
+        unpack8<T>(*reinterpret_cast<const uint4*>(As + a_off(r, c)), v);
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = (v[k] - mean) * rstd * gm[c * 8 + k] + bt[c * 8 + k];
+        if constexpr (EPI == EPI_LNRELU_A) {
+#pragma unroll
+          for (int k = 0; k < 8; k++) v[k] = fmaxf(v[k], 0.f);
+          a_store_all(c, pack8<T>(v));
+        } else {
+          *f4w(net_r, 2 * c) = make_float4(v[0], v[1], v[2], v[3]);
+          *f4w(net_r, 2 * c + 1) = make_float4(v[4], v[5], v[6], v[7]);
+          if (orow) *reinterpret_cast<uint4*>(orow + c * 8) = pack8<T>(v);
+        }
+      }
+      ln_used++;
+    } else if constexpr (EPI == EPI_GATED_LN) {
+      tmem_wait_st();
+      float mean, rstd;
+      ln_stats(s1, s2, mean, rstd);
+      const float* gm = s_ln + ln_used * 2 * kD;
+      const float* bt = gm + kD;
+#pragma unroll 1
+      for (int i = 0; i < kIter; i++) {
+        const int c = c0 + i;
+        uint32_t raw[8];
+        tmem_ld8(tcol + i * 8, raw);
+        tmem_wait_ld();
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = (__uint_as_float(raw[k]) - mean) * rstd * gm[c * 8 + k] + bt[c * 8 + k];
+        *f4w(n32_r, 2 * c) = make_float4(v[0], v[1], v[2], v[3]);
+        *f4w(n32_r, 2 * c + 1) = make_float4(v[4], v[5], v[6], v[7]);
+        a_store_all(c, pack8<T>(v));
+      }
+      ln_used++;
+    } else if constexpr (EPI == EPI_GATED_HEADS) {
+      exchange<4>(s_hacc, hacc);
+      if (live && part == 0 && rank == 0) {
+#pragma unroll
+        for (int o4 = 0; o4 < 4; o4++) {
+          hacc[o4] = 0.f;
+#pragma unroll
+          for (int p = 0; p < kSplit * kEpiPer; p++) hacc[o4] += s_hacc[(p * kRows + r) * 4 + o4];
+        }
+        const uint32_t d = pack2<T>(hacc[0] + ElemTraits<T>::to_float(s_head[4 * kD + 0]), hacc[1] + ElemTraits<T>::to_float(s_head[4 * kD + 1]));
+        const float2 w = unpack2<T>(pack2<T>(hacc[2] + ElemTraits<T>::to_float(s_head[4 * kD + 2]), hacc[3] + ElemTraits<T>::to_float(s_head[4 * kD + 3])));
+        *reinterpret_cast<uint32_t*>(P.delta + (size_t)grow * 2) = d;
+        *reinterpret_cast<uint32_t*>(P.weight + (size_t)grow * 2) = pack2<T>(1.0f / (1.0f + expf(-w.x)), 1.0f / (1.0f + expf(-w.y)));
+      }
+    }
+    tc_fence_before();
+    if (et == 0 && l == 0) stamp(P.dbg, 29);
+    if (l + 1 < P.n_layers) {       // hand the A tiles / the TMEM accumulator back to the MMA warps of the cluster
+      if (kSplit > 1) fence_proxy_async_cluster(); else fence_proxy_async();   // A-tile writes (local and peers') -> async proxy
+      epi_bar();
+      if (kSplit > 1) { if (et < kSplit) mbar_arrive_cluster(mapa(smem_u32(a_ready), (uint32_t)et)); }
+      else if (et == 0) mbar_arrive(a_ready);
+    }
+    if (et == 0) stamp(P.dbg, 7 + 4 * l);
+  }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_constant__ CUtensorMap tm_w,
                                                               const __grid_constant__ CUtensorMap tm_w0,
@@ -206,7 +615,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
   } else if (warp >= 2) {
     // stage the program's small parameters (biases, LayerNorm affine, heads) in shared memory once: the epilogues
     // read them as broadcasts instead of dependent global loads
-    const int t = threadIdx.x - 64, nt = kThreads - 64;
+    const int t = threadIdx.x - 32 * kFirstEpiWarp, nt = kThreads - 32 * kFirstEpiWarp;
     for (int l = 0; l < P.n_layers; l++)
       for (int q = t; q < kD / 8; q += nt) {
         float bv[8];
@@ -269,7 +678,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
       if (l == 0) {
         if (has_pro) { mbar_wait(pro_ready, 0u); fence_proxy_async(); tc_fence_after(); }
       } else {                         // the A tile now holds every CTA's slice of the previous layer's output
-        mbar_wait_cluster(a_ready, (uint32_t)((l - 1) & 1));
+        mbar_wait(a_ready, (uint32_t)((l - 1) & 1));
         fence_proxy_async();
         tc_fence_after();
       }
@@ -293,407 +702,48 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
       if (lane == 0) stamp(P.dbg, 5 + 4 * l);
     }
     __syncwarp();
-  } else if (warp >= 4) {
-    // =========================== prologue + epilogues ==========================================================
-    // kEpiPer warps per TMEM lane quarter; a thread owns one row and kCBp column blocks (32 columns each) of this
-    // CTA's slice.
-    const int quarter = warp & 3;
-    const int part = (warp - 4) >> 2;               // 0 .. kEpiPer-1
-    const int et = threadIdx.x - 128;               // 0 .. kEpiThreads-1
-    const int r = quarter * 32 + lane;              // tile row = TMEM lane
-    const int grow = row0 + r;                      // global row
-    const bool live = grow < P.rows;
-    const int lcb0 = part * kCBp;                   // first local column block of this thread
-    const int gcb0 = rank * kCBc + lcb0;            // ... as a global column block
-    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const uint32_t as_addr = smem_u32(As);
-    uint32_t peer_as[kSplit];                       // shared::cluster address of every CTA's A tile
+  } else if (warp >= kFirstEpiWarp) {
+    // =========================== prologue + epilogues (struct Epi) =============================================
+    Epi<T> e(P);
+    e.As = As; e.s_stat = s_stat; e.s_hacc = s_hacc; e.s_ln = s_ln; e.s_bias = s_bias; e.s_head = s_head; e.s_idx = s_idx;
+    e.acc_full = acc_full; e.a_ready = a_ready; e.pro_ready = pro_ready; e.stat_bar = stat_bar;
+    e.rank = rank; e.tile = tile; e.row0 = row0;
+    e.quarter = warp & 3;
+    e.part = (warp - kFirstEpiWarp) >> 2;           // 0 .. kEpiPer-1
+    e.et = threadIdx.x - 32 * kFirstEpiWarp;        // 0 .. kEpiThreads-1
+    e.r = e.quarter * 32 + lane;                    // tile row = TMEM lane
+    e.grow = row0 + e.r;
+    e.live = e.grow < P.rows;
+    e.lcb0 = e.part * kCBp;                         // first local column block of this thread
+    e.gcb0 = rank * kCBc + e.lcb0;                  // ... as a global column block
+    e.trow = tmem_base + ((uint32_t)(e.quarter * 32) << 16);
 #pragma unroll
-    for (int p = 0; p < kSplit; p++) peer_as[p] = mapa(as_addr, (uint32_t)p);
-    uint32_t stat_uses = 0;
-
-    // deliver a 16-byte chunk of the next layer's A operand to every CTA of the cluster
-    auto a_store_all = [&](int c, uint4 v) {
-      const uint32_t off = a_off(r, c);
-      if (P.dbg_mode & 1) return;
-#pragma unroll
-      for (int p = 0; p < kSplit; p++) {
-        if (p == rank) *reinterpret_cast<uint4*>(As + off) = v;
-        else if (!(P.dbg_mode & 2)) st_cluster_v4(peer_as[p] + off, v);
-      }
-    };
-    // exchange per-row partials (n floats at s_buf[rank][part][r][*]) between all epilogue threads of the cluster
-    auto exchange = [&](float* s_buf, int n, const float* vals) {
-      const uint32_t local = smem_u32(s_buf + ((rank * kEpiPer + part) * kRows + r) * n);
-#pragma unroll
-      for (int p = 0; p < kSplit; p++) {
-        const uint32_t dst = (p == rank) ? 0u : mapa(local, (uint32_t)p);
-        for (int k = 0; k < n; k++) {
-          if (p == rank) s_buf[((rank * kEpiPer + part) * kRows + r) * n + k] = vals[k];
-          else st_cluster_f32(dst + 4 * k, vals[k]);
-        }
-      }
-      if (kSplit > 1) {
-        fence_acq_rel_cluster();
-        epi_bar();
-        if (et < kSplit) mbar_arrive_cluster(mapa(smem_u32(stat_bar), (uint32_t)et));
-        mbar_wait_cluster(stat_bar, stat_uses & 1u);
-        stat_uses++;
-      } else {
-        epi_bar();
-      }
-    };
-    auto ln_stats = [&](float s1, float s2, float& mean, float& rstd) {
-      const float v[2] = {s1, s2};
-      exchange(s_stat, 2, v);
-      s1 = 0.f; s2 = 0.f;
-#pragma unroll
-      for (int p = 0; p < kSplit * kEpiPer; p++) { s1 += s_stat[(p * kRows + r) * 2 + 0]; s2 += s_stat[(p * kRows + r) * 2 + 1]; }
-      mean = s1 * (1.0f / kD);
-      rstd = rsqrtf(fmaxf(s2 * (1.0f / kD) - mean * mean, 0.f) + P.eps);
-    };
-
-    // ---------------- prologue: every CTA builds the full [128 x 384] A tile itself (no exchange) ----------------
-    if (P.pro == PRO_GATHER) {
-      if (et < kRows) {
-        const int gr = row0 + et;
-        int src = -1;
-        if (gr < P.rows) {
-          const long long j = P.idx64 ? (long long)P.idx64[gr] : (long long)gr;
-          src = (j >= 0 && j < (long long)P.src_rows) ? (int)j : -1;
-        }
-        s_idx[et] = src;
-      }
-      epi_bar();
-      // cooperative: 48 consecutive threads copy one 768-byte source row; 12 independent 16-byte loads in flight
-      constexpr int kPer = kRows * kChunks / kEpiThreads;     // chunks per thread
-      constexpr int kBatch = 12;
-      static_assert(kPer % kBatch == 0, "gather batches");
-#pragma unroll 1
-      for (int b = 0; b < kPer / kBatch; b++) {
-        uint4 v[kBatch];
-#pragma unroll
-        for (int u = 0; u < kBatch; u++) {
-          const int q = et + (b * kBatch + u) * kEpiThreads;
-          const int rr = q / kChunks, c = q - rr * kChunks;
-          const int s = s_idx[rr];
-          v[u] = make_uint4(0u, 0u, 0u, 0u);
-          if (s >= 0) v[u] = *reinterpret_cast<const uint4*>(P.x16_in + (size_t)s * kD + c * 8);
-        }
-#pragma unroll
-        for (int u = 0; u < kBatch; u++) {
-          const int q = et + (b * kBatch + u) * kEpiThreads;
-          const int rr = q / kChunks, c = q - rr * kChunks;
-          *reinterpret_cast<uint4*>(As + a_off(rr, c)) = v[u];
-        }
-      }
-    } else if (P.pro == PRO_CAST || P.pro == PRO_RESID || P.pro == PRO_RESID_LN) {
-      // x = net32 (+ y16[gid] (+ y16b[gid2])): full rows, redundantly in every CTA of the cluster.  Nothing is written
-      // back here (a peer reads the same net32 columns concurrently): the additions are simply repeated, in the same
-      // order, by the next kernel that needs them -- bit-identical, and race-free.
-      const bool resid = (P.pro != PRO_CAST);
-      const bool with_ln = (P.pro == PRO_RESID_LN);
-      const T* yrow = (resid && live) ? P.y16 + (size_t)P.gid[grow] * kD : nullptr;
-      const T* yrow2 = (with_ln && live && P.gid2) ? P.y16b + (size_t)P.gid2[grow] * kD : nullptr;
-      const int pcb0 = part * (kCB / kEpiPer), pcb1 = pcb0 + kCB / kEpiPer;
-      float s1 = 0.f, s2 = 0.f;
-      struct Pre { uint4 f[8]; uint4 y[4]; uint4 z[4]; };
-      auto load_pre = [&](int cb, Pre& p) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int c = cb * 4 + j;
-          p.f[2 * j] = *reinterpret_cast<const uint4*>(P.net32 + t32(tile, 2 * c, r));
-          p.f[2 * j + 1] = *reinterpret_cast<const uint4*>(P.net32 + t32(tile, 2 * c + 1, r));
-          p.y[j] = make_uint4(0u, 0u, 0u, 0u);
-          p.z[j] = p.y[j];
-          if (yrow) p.y[j] = *reinterpret_cast<const uint4*>(yrow + c * 8);
-          if (yrow2) p.z[j] = *reinterpret_cast<const uint4*>(yrow2 + c * 8);
-        }
-      };
-      Pre cur, nxt;
-      load_pre(pcb0, cur);
-#pragma unroll 1
-      for (int cb = pcb0; cb < pcb1; cb++) {
-        if (cb + 1 < pcb1) load_pre(cb + 1, nxt);
-        uint32_t st[32];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int c = cb * 4 + j;
-          const float4 a = as_f4(cur.f[2 * j]), b = as_f4(cur.f[2 * j + 1]);
-          float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-          if (resid) {
-            float y[8];
-            unpack8<T>(cur.y[j], y);
-#pragma unroll
-            for (int k = 0; k < 8; k++) v[k] += y[k];
-          }
-          if (with_ln) {
-            float z[8];
-            unpack8<T>(cur.z[j], z);
-#pragma unroll
-            for (int k = 0; k < 8; k++) { v[k] += z[k]; s1 += v[k]; s2 += v[k] * v[k]; st[j * 8 + k] = __float_as_uint(v[k]); }
-          } else {
-            *reinterpret_cast<uint4*>(As + a_off(r, c)) = pack8<T>(v);
-          }
-        }
-        if (with_ln) tmem_st32(trow + cb * 32, st);      // park the fp32 row in TMEM (free until the first MMA)
-        if (cb + 1 < pcb1) cur = nxt;
-      }
-      if (with_ln) {     // n = LayerNorm(net) -> n32 (float, needed by the gated residual) and the A tile (half)
-        tmem_wait_st();
-        // row statistics over the full row: the kEpiPer threads of a row combine through shared memory (CTA-local)
-        s_stat[(part * kRows + r) * 2 + 0] = s1;
-        s_stat[(part * kRows + r) * 2 + 1] = s2;
-        epi_bar();
-        s1 = 0.f; s2 = 0.f;
-#pragma unroll
-        for (int p = 0; p < kEpiPer; p++) { s1 += s_stat[(p * kRows + r) * 2 + 0]; s2 += s_stat[(p * kRows + r) * 2 + 1]; }
-        epi_bar();
-        const float mean = s1 * (1.0f / kD);
-        const float rstd = rsqrtf(fmaxf(s2 * (1.0f / kD) - mean * mean, 0.f) + P.eps);
-        const float* gm = s_ln;
-        const float* bt = s_ln + kD;
-#pragma unroll 1
-        for (int cb = pcb0; cb < pcb1; cb++) {
-          const bool mine = (cb / kCBc) == rank;
-          uint32_t raw[32];
-          tmem_ld32(trow + cb * 32, raw);
-          tmem_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const int c = cb * 4 + j;
-            float v[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) v[k] = (__uint_as_float(raw[j * 8 + k]) - mean) * rstd * gm[c * 8 + k] + bt[c * 8 + k];
-            if (mine) {
-              *reinterpret_cast<float4*>(P.n32 + t32(tile, 2 * c, r)) = make_float4(v[0], v[1], v[2], v[3]);
-              *reinterpret_cast<float4*>(P.n32 + t32(tile, 2 * c + 1, r)) = make_float4(v[4], v[5], v[6], v[7]);
-            }
-            *reinterpret_cast<uint4*>(As + a_off(r, c)) = pack8<T>(v);
-          }
-        }
-        tc_fence_before();
-      }
+    for (int p = 0; p < kSplit; p++) e.peer_as[p] = mapa(smem_u32(As), (uint32_t)p);
+    e.stat_uses = 0;
+    e.ln_used = 0;
+    e.net_r = P.net32 + t32(tile, 0, e.r);
+    e.n32_r = P.n32 + t32(tile, 0, e.r);
+    e.gate_r = P.gate16 + t16(tile, 0, e.r);
+    switch (P.pro) {                                // warp-uniform
+      case PRO_GATHER: e.template prologue<PRO_GATHER>(); break;
+      case PRO_CAST: e.template prologue<PRO_CAST>(); break;
+      case PRO_RESID: e.template prologue<PRO_RESID>(); break;
+      case PRO_RESID_LN: e.template prologue<PRO_RESID_LN>(); break;
+      default: break;
     }
-    if (has_pro) {
-      fence_proxy_async();
-      epi_bar();
-      if (et == 0) mbar_arrive(pro_ready);
-    }
-    if (et == 0) stamp(P.dbg, 2);
-
-    // ---------------- per-layer epilogues (this CTA's column slice) ----------------
-    int ln_used = (P.pro == PRO_RESID_LN) ? 1 : 0;
+    if (e.et == 0) stamp(P.dbg, 2);
     for (int l = 0; l < P.n_layers; l++) {
-      const int epi = P.epi[l];
-      const float* bias = s_bias + l * kD;
-      float s1 = 0.f, s2 = 0.f;
-      float hacc[4] = {0.f, 0.f, 0.f, 0.f};
-      const T* netrow = nullptr;
-      const T* inprow = nullptr;
-      if (epi == EPI_ADD3_LN && live) {
-        netrow = P.x16_in + (size_t)grow * kD;
-        inprow = P.inp16 + (size_t)P.kk[grow] * kD;
+      switch (P.epi[l]) {
+        case EPI_RELU_A: e.template layer<EPI_RELU_A>(l); break;
+        case EPI_LNRELU_A: e.template layer<EPI_LNRELU_A>(l); break;
+        case EPI_ADD3_LN: e.template layer<EPI_ADD3_LN>(l); break;
+        case EPI_RESID: e.template layer<EPI_RESID>(l); break;
+        case EPI_STORE_A: e.template layer<EPI_STORE_A>(l); break;
+        case EPI_STORE_B: e.template layer<EPI_STORE_B>(l); break;
+        case EPI_GATE: e.template layer<EPI_GATE>(l); break;
+        case EPI_GATED_LN: e.template layer<EPI_GATED_LN>(l); break;
+        default: e.template layer<EPI_GATED_HEADS>(l); break;
       }
-      T* orow = nullptr;
-      if (live) {
-        if (epi == EPI_STORE_A || epi == EPI_RESID || epi == EPI_GATED_HEADS || epi == EPI_ADD3_LN) orow = P.out16_a ? P.out16_a + (size_t)grow * kD : nullptr;
-        if (epi == EPI_STORE_B) orow = P.out16_b ? P.out16_b + (size_t)grow * kD : nullptr;
-      }
-      // per-row operands of the element-wise tail, fetched one column block ahead of their use
-      struct Aux { uint4 q[12]; };     // RESID: q[0..7] net32 ; GATED: q[0..7] n32, q[8..11] gate ; ADD3: q[0..3] net16, q[4..7] inp16
-      auto load_aux = [&](int gcb, Aux& a) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int c = gcb * 4 + j;
-          if (epi == EPI_RESID) {
-            a.q[2 * j] = *reinterpret_cast<const uint4*>(P.net32 + t32(tile, 2 * c, r));
-            a.q[2 * j + 1] = *reinterpret_cast<const uint4*>(P.net32 + t32(tile, 2 * c + 1, r));
-          } else if (epi == EPI_GATED_LN || epi == EPI_GATED_HEADS) {
-            a.q[2 * j] = *reinterpret_cast<const uint4*>(P.n32 + t32(tile, 2 * c, r));
-            a.q[2 * j + 1] = *reinterpret_cast<const uint4*>(P.n32 + t32(tile, 2 * c + 1, r));
-            a.q[8 + j] = *reinterpret_cast<const uint4*>(P.gate16 + t16(tile, c, r));
-          } else if (epi == EPI_ADD3_LN) {
-            a.q[j] = make_uint4(0u, 0u, 0u, 0u);
-            a.q[4 + j] = a.q[j];
-            if (live) { a.q[j] = *reinterpret_cast<const uint4*>(netrow + c * 8); a.q[4 + j] = __ldg(reinterpret_cast<const uint4*>(inprow + c * 8)); }
-          }
-        }
-      };
-      Aux cur, nxt;
-      load_aux(gcb0, cur);                          // issued before the accumulator is ready: overlaps the MMAs
-      mbar_wait_cluster(acc_full, (uint32_t)(l & 1));      // every CTA of the cluster is done reading its A tile
-      tc_fence_after();
-      if (et == 0) stamp(P.dbg, 6 + 4 * l);
-#pragma unroll 1
-      for (int i = 0; i < kCBp; i++) {
-        const int lcb = lcb0 + i, gcb = gcb0 + i;
-        uint32_t raw[32];
-        if (!(P.dbg_mode & 4)) tmem_ld32(trow + lcb * 32, raw);
-        else {
-#pragma unroll
-          for (int k = 0; k < 32; k++) raw[k] = 0x3f000000u + k;
-        }
-        if (i + 1 < kCBp) load_aux(gcb + 1, nxt);
-        tmem_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int c = gcb * 4 + j;                // global 16-byte chunk index (8 columns)
-          float o[8];
-          {
-            const float4 b0 = *reinterpret_cast<const float4*>(bias + c * 8), b1 = *reinterpret_cast<const float4*>(bias + c * 8 + 4);
-            o[0] = __uint_as_float(raw[j * 8 + 0]) + b0.x; o[1] = __uint_as_float(raw[j * 8 + 1]) + b0.y;
-            o[2] = __uint_as_float(raw[j * 8 + 2]) + b0.z; o[3] = __uint_as_float(raw[j * 8 + 3]) + b0.w;
-            o[4] = __uint_as_float(raw[j * 8 + 4]) + b1.x; o[5] = __uint_as_float(raw[j * 8 + 5]) + b1.y;
-            o[6] = __uint_as_float(raw[j * 8 + 6]) + b1.z; o[7] = __uint_as_float(raw[j * 8 + 7]) + b1.w;
-          }
-          const uint4 oh = pack8<T>(o);               // the Linear output, rounded to half (autocast)
-          if (epi == EPI_RELU_A) {
-            a_store_all(c, relu8<T>(oh));             // max(.,0) commutes with the rounding: done on packed halves
-          } else if (epi == EPI_STORE_A || epi == EPI_STORE_B) {
-            if (orow) *reinterpret_cast<uint4*>(orow + c * 8) = oh;
-          } else if (epi == EPI_GATE) {
-            *reinterpret_cast<uint4*>(P.gate16 + t16(tile, c, r)) = oh;
-          } else if (epi == EPI_LNRELU_A) {
-            unpack8<T>(oh, o);
-#pragma unroll
-            for (int k = 0; k < 8; k++) { s1 += o[k]; s2 += o[k] * o[k]; }
-            *reinterpret_cast<uint4*>(As + a_off(r, c)) = oh;                   // parked in the local tile until normalised
-          } else if (epi == EPI_ADD3_LN) {
-            float a[8], b[8];
-            unpack8<T>(oh, o);
-            unpack8<T>(cur.q[j], a);
-            unpack8<T>(cur.q[4 + j], b);
-#pragma unroll
-            for (int k = 0; k < 8; k++) a[k] += b[k];
-            rnd8<T>(a);
-#pragma unroll
-            for (int k = 0; k < 8; k++) o[k] += a[k];
-            const uint4 vh = pack8<T>(o);
-            unpack8<T>(vh, o);
-#pragma unroll
-            for (int k = 0; k < 8; k++) { s1 += o[k]; s2 += o[k] * o[k]; }
-            *reinterpret_cast<uint4*>(As + a_off(r, c)) = vh;
-          } else if (epi == EPI_RESID) {
-            unpack8<T>(oh, o);
-            float4 a = as_f4(cur.q[2 * j]), b = as_f4(cur.q[2 * j + 1]);
-            a.x += o[0]; a.y += o[1]; a.z += o[2]; a.w += o[3]; b.x += o[4]; b.y += o[5]; b.z += o[6]; b.w += o[7];
-            *reinterpret_cast<float4*>(P.net32 + t32(tile, 2 * c, r)) = a;
-            *reinterpret_cast<float4*>(P.net32 + t32(tile, 2 * c + 1, r)) = b;
-            if (orow) {
-              const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-              *reinterpret_cast<uint4*>(orow + c * 8) = pack8<T>(v);
-            }
-          } else {   // EPI_GATED_LN / EPI_GATED_HEADS:  x = n + half(half(sigmoid(gate)) * res)
-            float g[8];
-            unpack8<T>(oh, o);
-            unpack8<T>(cur.q[8 + j], g);
-            const float4 a = as_f4(cur.q[2 * j]), b = as_f4(cur.q[2 * j + 1]);
-            float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int k = 0; k < 8; k++) g[k] = sigmoidf_(g[k]);
-            rnd8<T>(g);
-#pragma unroll
-            for (int k = 0; k < 8; k++) g[k] *= o[k];
-            rnd8<T>(g);
-#pragma unroll
-            for (int k = 0; k < 8; k++) x[k] += g[k];
-            if (epi == EPI_GATED_LN) {
-#pragma unroll
-              for (int k = 0; k < 8; k++) { s1 += x[k]; s2 += x[k] * x[k]; raw[j * 8 + k] = __float_as_uint(x[k]); }
-            } else {
-              if (orow) *reinterpret_cast<uint4*>(orow + c * 8) = pack8<T>(x);       // new hidden state (half)
-              float hw[8];
-#pragma unroll
-              for (int k = 0; k < 8; k++) x[k] = fmaxf(x[k], 0.f);
-              rnd8<T>(x);
-#pragma unroll
-              for (int o4 = 0; o4 < 4; o4++) {
-                unpack8<T>(*reinterpret_cast<const uint4*>(s_head + o4 * kD + c * 8), hw);
-#pragma unroll
-                for (int k = 0; k < 8; k++) hacc[o4] += x[k] * hw[k];
-              }
-            }
-          }
-        }
-        if (epi == EPI_GATED_LN) tmem_st32(trow + lcb * 32, raw);  // fp32 row parked in its own accumulator columns
-        if (i + 1 < kCBp) cur = nxt;
-      }
-      if (et == 0 && l == 0) stamp(P.dbg, 28);
-      // ---------------- row-wise tails ----------------
-      if (epi == EPI_LNRELU_A || epi == EPI_ADD3_LN) {
-        // this thread's slice of the row (half values) sits in the local A tile: one more pass over shared memory
-        float mean, rstd;
-        ln_stats(s1, s2, mean, rstd);
-        const float* gm = s_ln + ln_used * 2 * kD;
-        const float* bt = gm + kD;
-#pragma unroll 2
-        for (int c = gcb0 * 4; c < (gcb0 + kCBp) * 4; c++) {
-          float v[8];
-          unpack8<T>(*reinterpret_cast<const uint4*>(As + a_off(r, c)), v);
-#pragma unroll
-          for (int k = 0; k < 8; k++) v[k] = (v[k] - mean) * rstd * gm[c * 8 + k] + bt[c * 8 + k];
-          if (epi == EPI_LNRELU_A) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) v[k] = fmaxf(v[k], 0.f);
-            a_store_all(c, pack8<T>(v));
-          } else {
-            *reinterpret_cast<float4*>(P.net32 + t32(tile, 2 * c, r)) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(P.net32 + t32(tile, 2 * c + 1, r)) = make_float4(v[4], v[5], v[6], v[7]);
-            if (orow) *reinterpret_cast<uint4*>(orow + c * 8) = pack8<T>(v);
-          }
-        }
-        ln_used++;
-      } else if (epi == EPI_GATED_LN) {
-        tmem_wait_st();
-        float mean, rstd;
-        ln_stats(s1, s2, mean, rstd);
-        const float* gm = s_ln + ln_used * 2 * kD;
-        const float* bt = gm + kD;
-#pragma unroll 1
-        for (int i = 0; i < kCBp; i++) {
-          const int lcb = lcb0 + i, gcb = gcb0 + i;
-          uint32_t raw[32];
-          tmem_ld32(trow + lcb * 32, raw);
-          tmem_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const int c = gcb * 4 + j;
-            float v[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) v[k] = (__uint_as_float(raw[j * 8 + k]) - mean) * rstd * gm[c * 8 + k] + bt[c * 8 + k];
-            *reinterpret_cast<float4*>(P.n32 + t32(tile, 2 * c, r)) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(P.n32 + t32(tile, 2 * c + 1, r)) = make_float4(v[4], v[5], v[6], v[7]);
-            a_store_all(c, pack8<T>(v));
-          }
-        }
-        ln_used++;
-      } else if (epi == EPI_GATED_HEADS) {
-        exchange(s_hacc, 4, hacc);
-        if (live && part == 0 && rank == 0) {
-#pragma unroll
-          for (int o4 = 0; o4 < 4; o4++) {
-            hacc[o4] = 0.f;
-#pragma unroll
-            for (int p = 0; p < kSplit * kEpiPer; p++) hacc[o4] += s_hacc[(p * kRows + r) * 4 + o4];
-          }
-          const uint32_t d = pack2<T>(hacc[0] + ElemTraits<T>::to_float(s_head[4 * kD + 0]), hacc[1] + ElemTraits<T>::to_float(s_head[4 * kD + 1]));
-          const float2 w = unpack2<T>(pack2<T>(hacc[2] + ElemTraits<T>::to_float(s_head[4 * kD + 2]), hacc[3] + ElemTraits<T>::to_float(s_head[4 * kD + 3])));
-          *reinterpret_cast<uint32_t*>(P.delta + (size_t)grow * 2) = d;
-          *reinterpret_cast<uint32_t*>(P.weight + (size_t)grow * 2) = pack2<T>(1.0f / (1.0f + expf(-w.x)), 1.0f / (1.0f + expf(-w.y)));
-        }
-      }
-      tc_fence_before();
-      if (et == 0 && l == 0) stamp(P.dbg, 29);
-      if (l + 1 < P.n_layers) {       // hand the A tiles / the TMEM accumulator back to the MMA warps of the cluster
-        if (kSplit > 1) fence_proxy_async_all(); else fence_proxy_async();   // A-tile writes (local and peers') -> async proxy
-        if (et == 0 && l == 0) stamp(P.dbg, 30);
-        epi_bar();
-        if (et == 0 && l == 0) stamp(P.dbg, 31);
-        if (kSplit > 1) { if (et < kSplit) mbar_arrive_cluster(mapa(smem_u32(a_ready), (uint32_t)et)); }
-        else if (et == 0) mbar_arrive(a_ready);
-      }
-      if (et == 0) stamp(P.dbg, 7 + 4 * l);
     }
   }
   // teardown: no CTA may exit while a peer can still write into its shared memory
@@ -754,7 +804,6 @@ static int launch_prog(const CUtensorMap& tw, const CUtensorMap& tw0, const CUte
   const int tiles = (P.rows + kRows - 1) / kRows;
   if (tiles <= 0) return DEVO_OK;
   GruProg<T> Pd = P;
-  { static int mode = -1; if (mode < 0) { const char* e = getenv("DEVO_GRU_DBG"); mode = e ? atoi(e) : 0; } Pd.dbg_mode = mode; }
   Pd.dbg = g_dbg ? g_dbg + 32 * (g_dbg_launch++ % 16) : nullptr;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

@@ -49,7 +49,11 @@ def main():
         with torch.cuda.graph(g):
             up.forward_mma(net, imap, kk, corr, plan_kk, plan_ij, Np, nf * nf, packed)
         t_graph = timeit(g.replay)
-        print("forward_mma %.1f us (graph replay %.1f us)   cuBLAS+glue path %.1f us (eager)" % (t_mma, t_graph, t_cub))
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2):
+            up.forward_fused(net, ctx, corr.view(1, E, 896), plan_kk, plan_ij, Np, nf * nf, fc)
+        t_cub_graph = timeit(g2.replay)
+        print("forward_mma %.1f us (graph replay %.1f us)   cuBLAS+glue path %.1f us eager, %.1f us graph replay" % (t_mma, t_graph, t_cub, t_cub_graph))
         L = _lib.lib()
         L.devo_gru_debug_timing.argtypes = [ctypes.c_void_p]
         L.devo_gru_debug_timing(None)
