@@ -48,7 +48,7 @@ constexpr int kABlk = kRows * 128;         // one K-block of A: 128 rows x 64 ha
 constexpr int kASlots = kD / 64;           // 6
 constexpr int kWStage = kNC * 128;         // one K-block of this CTA's weight slice (16 / 24 KB)
 constexpr int kWStages = (96 * 1024) / kWStage;   // 6 / 4
-constexpr int kEpiPer = 3;                 // epilogue warps per TMEM lane quarter (each owns a share of the columns)
+constexpr int kEpiPer = 2;                 // epilogue warps per TMEM lane quarter (each owns a share of the columns)
 constexpr int kEpiThreads = 128 * kEpiPer;
 constexpr int kFirstEpiWarp = 2;            // warps 0 (TMA) and 1 (MMA) + the epilogue warps; any 4 consecutive warps cover the 4 TMEM lane quarters
 constexpr int kThreads = 32 * kFirstEpiWarp + kEpiThreads;
@@ -92,6 +92,9 @@ struct GruProg {
   const T* headB;                          // [4]
   T* delta;                                // [rows,2]
   T* weight;                               // [rows,2]
+  const float* coords;                     // optional [rows,2,3,3]: target32 = centre coordinate + delta
+  float* target32;                         // optional [rows,2]
+  float* weight32;                         // optional [rows,2]
   long long* dbg;                          // optional: %globaltimer stamps of CTA 0 (tools/gru_timing.py)
 };
 
@@ -395,16 +398,14 @@ struct Epi {
     mbar_wait(acc_full, (uint32_t)(l & 1));              // every CTA of the cluster is done reading its A tile
     tc_fence_after();
     if (et == 0) stamp(P.dbg, 6 + 4 * l);
-    // software pipeline: the accumulator chunk and the row operands of iteration i+1 are in flight while chunk i is
-    // processed (one thread otherwise pays the TMEM + L2 latency kIter times in a row)
-    uint32_t raw[8], rawn[8];
-    tmem_ld8(tcol, raw);
-    tmem_wait_ld();
+    // (prefetching the next accumulator chunk as well was measured slower: 168 instead of 126 registers, +7 %)
 #pragma unroll 1
     for (int i = 0; i < kIter; i++) {
       const int c = c0 + i;                         // global 16-byte chunk index (8 columns)
-      if (i + 1 < kIter) tmem_ld8(tcol + (i + 1) * 8, rawn);
+      uint32_t raw[8];
+      tmem_ld8(tcol + i * 8, raw);
       if constexpr (kAux > 1) { if (i + 1 < kIter) load_aux(c + 1, nxt); }
+      tmem_wait_ld();
       float o[8];
       {
         const float4 b0 = *reinterpret_cast<const float4*>(bias + c * 8), b1 = *reinterpret_cast<const float4*>(bias + c * 8 + 4);
@@ -488,9 +489,6 @@ struct Epi {
 #pragma unroll
         for (int k = 0; k < kAux; k++) cur[k] = nxt[k];
       }
-      tmem_wait_ld();
-#pragma unroll
-      for (int k = 0; k < 8; k++) raw[k] = rawn[k];
     }
     if (et == 0 && l == 0) stamp(P.dbg, 28);
     // ---------------- row-wise tails ----------------
@@ -550,7 +548,14 @@ struct Epi {
         const uint32_t d = pack2<T>(hacc[0] + ElemTraits<T>::to_float(s_head[4 * kD + 0]), hacc[1] + ElemTraits<T>::to_float(s_head[4 * kD + 1]));
         const float2 w = unpack2<T>(pack2<T>(hacc[2] + ElemTraits<T>::to_float(s_head[4 * kD + 2]), hacc[3] + ElemTraits<T>::to_float(s_head[4 * kD + 3])));
         *reinterpret_cast<uint32_t*>(P.delta + (size_t)grow * 2) = d;
-        *reinterpret_cast<uint32_t*>(P.weight + (size_t)grow * 2) = pack2<T>(1.0f / (1.0f + expf(-w.x)), 1.0f / (1.0f + expf(-w.y)));
+        const uint32_t wh = pack2<T>(1.0f / (1.0f + expf(-w.x)), 1.0f / (1.0f + expf(-w.y)));
+        *reinterpret_cast<uint32_t*>(P.weight + (size_t)grow * 2) = wh;
+        if (P.target32 != nullptr) {            // BA inputs, fused: target = reprojected centre + delta (devo.py:326-331)
+          const float2 df = unpack2<T>(d), wf = unpack2<T>(wh);
+          const float* cr = P.coords + (size_t)grow * 18;
+          *reinterpret_cast<float2*>(P.target32 + (size_t)grow * 2) = make_float2(cr[4] + df.x, cr[13] + df.y);
+          *reinterpret_cast<float2*>(P.weight32 + (size_t)grow * 2) = wf;
+        }
       }
     }
     tc_fence_before();
@@ -587,8 +592,8 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);      // 32 barrier slots = 256 B; slot + pad = 16 B
   int* s_idx = reinterpret_cast<int*>(tmem_slot + 4);                 // [128] gather sources of the tile
   float* s_stat = reinterpret_cast<float*>(s_idx + kRows);            // [kSplit][kEpiPer][128][2] LayerNorm partials
-  float* s_hacc = s_stat + kSplit * kEpiPer * kRows * 2;              // [kSplit][kEpiPer][128][4] head partials
-  float* s_ln = s_hacc + kSplit * kEpiPer * kRows * 4;                // [2][2][384]: gamma, beta of the program's LayerNorms
+  float* s_hacc = s_stat;                                             // [kSplit][kEpiPer][128][4] head partials (last layer only: same storage)
+  float* s_ln = s_stat + kSplit * kEpiPer * kRows * 4;                // [2][2][384]: gamma, beta of the program's LayerNorms
   float* s_bias = s_ln + 4 * kD;                                      // [kMaxLayers][384] biases as fp32
   T* s_head = reinterpret_cast<T*>(s_bias + kMaxLayers * kD);         // [4][384] + [4] (+4 pad)
 
@@ -788,7 +793,7 @@ static int make_map_2d(CUtensorMap* m, int dtype, const void* ptr, uint64_t rows
 }
 
 constexpr size_t kSmemBytes = 1024 + (size_t)kASlots * kABlk + (size_t)kWStages * kWStage + 32 * sizeof(uint64_t) + 16 + kRows * sizeof(int) +
-                              (size_t)kSplit * kEpiPer * kRows * 6 * sizeof(float) + 4 * kD * sizeof(float) + kMaxLayers * kD * sizeof(float) + (4 * kD + 8) * 2 + 64;
+                              (size_t)kSplit * kEpiPer * kRows * 4 * sizeof(float) + 4 * kD * sizeof(float) + kMaxLayers * kD * sizeof(float) + (4 * kD + 8) * 2 + 64;
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 static long long* g_dbg = nullptr;     // 16 launches x 32 stamps, allocated when DEVO_GRU_TIMING is set
@@ -941,6 +946,7 @@ static int gru_update_impl(const devo_gru_weights_t* Wt, const devo_gru_io_t* io
     P.out16_a = (T*)io->net16_out;
     P.headW = (const T*)Wt->head_W; P.headB = (const T*)Wt->head_b;
     P.delta = (T*)io->delta; P.weight = (T*)io->weight;
+    if (io->coords && io->target32 && io->weight32) { P.coords = io->coords; P.target32 = io->target32; P.weight32 = io->weight32; }
     rc = launch_prog<T>(tw, tw0, ta, P, s);
     if (rc != DEVO_OK) return rc;
   }

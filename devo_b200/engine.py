@@ -122,10 +122,11 @@ class UpdateOperator:
         cur.wait_stream(self._side)
         cur.wait_stream(self._side2)
         # (3) GRU: cached fp16 weights, autocast-identical dtype flow, no host sync
-        if self.gru_mode == "mma":
-            net, (delta, weight, _) = self.update.forward_mma(
+        target = None
+        if self.gru_mode == "mma":      # target / weight for BA come out of the heads epilogue of the same launch
+            net, (delta, weight16, (target, weight)) = self.update.forward_mma(
                 self.net, self.imap, self.kk, self.corr_buf, self.plan_kk, self.plan_ij, self.Np, self.Nf * self.Nf,
-                self.packed, net_out=self.net, workspace=self._gru_ws)
+                self.packed, net_out=self.net, workspace=self._gru_ws, coords=coords)
         elif self.fused_gru:
             ctx = self.imap[:, self.kk]
             net, (delta, weight, _) = self.update.forward_fused(
@@ -138,8 +139,9 @@ class UpdateOperator:
             self.net.copy_(net)
         # (4) BA targets and in-place Gauss-Newton (reuses the kk/jj plan: one sort serves neighbours,
         #     SoftAgg and the Schur grouping)
-        target = coords[:, :, :, 1, 1] + delta.float()
-        weight = weight.float()
+        if target is None:
+            target = coords[:, :, :, 1, 1] + delta.float()
+            weight = weight.float()
         cuda_ba.forward_async(self.poses, self.patches, self.intrinsics, target, weight, self.lmbda,
                               self.ii, self.jj, self.kk, self.t0, self.t1, self.ba_iterations, status=self.status,
                               plan=self.plan_kk, workspace=self._ba_ws)

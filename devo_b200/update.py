@@ -227,11 +227,12 @@ class Update(nn.Module):
         return net, (run(self.d, net), run(self.w, net), None)
 
     def forward_mma(self, net16, imap16, kk, corr16, plan_kk, plan_ij, max_patches, max_pairs, packed, net_out=None,
-                    workspace=None):
+                    workspace=None, coords=None):
         """The whole forward as fused tcgen05 kernels (csrc/gru_mma.cu, devo_gru_update): net16 [1,E,384] hidden state,
         imap16 [1,Np,384] context features (inp = imap16[:, kk], gathered inside), corr16 [E, corr_ld] zero-padded
         correlation rows.  Returns (net_out [1,E,384] autocast dtype, (delta, weight, None)).  Inference only; same
-        rounding points as forward_fused."""
+        rounding points as forward_fused.  With `coords` ([1,E,2,3,3] f32, the reprojection) the BA inputs are produced
+        by the same launch and returned as the third element: (target f32 [1,E,2], weight f32 [1,E,2])."""
         import ctypes
         from . import _lib
         E, D = net16.shape[1], self.dim
@@ -257,10 +258,18 @@ class Update(nn.Module):
                               plan_kk.ix.data_ptr(), plan_kk.jx.data_ptr(),
                               plan_kk.perm.data_ptr(), plan_kk.gstart.data_ptr(), plan_kk.ngroups.data_ptr(), plan_kk.gid.data_ptr(), int(max_patches),
                               plan_ij.perm.data_ptr(), plan_ij.gstart.data_ptr(), plan_ij.ngroups.data_ptr(), plan_ij.gid.data_ptr(), int(max_pairs),
-                              net_out.data_ptr(), delta.data_ptr(), weight.data_ptr())
+                              net_out.data_ptr(), delta.data_ptr(), weight.data_ptr(), 0, 0, 0)
+        extra = None
+        if coords is not None:
+            _lib.require_dtype(coords, torch.float32, "coords")
+            _lib.require_contiguous(coords=coords)
+            if coords.numel() != E * 18:
+                raise RuntimeError("forward_mma: coords must be [1,E,2,3,3]")
+            extra = (torch.empty(1, E, 2, dtype=torch.float32, device=dev), torch.empty(1, E, 2, dtype=torch.float32, device=dev))
+            io.coords, io.target32, io.weight32 = coords.data_ptr(), extra[0].data_ptr(), extra[1].data_ptr()
         _lib.check(L.devo_gru_update(ctypes.byref(packed.struct), ctypes.byref(io), _lib.dtype_code(net16), ws.data_ptr(),
                                      ws.numel(), _lib.stream_ptr(dev)), "gru_update")
-        return net_out, (delta, weight, None)
+        return net_out, (delta, weight, extra)
 
     def forward_fused(self, net16, inp16, corr16, plan_kk, plan_ij, max_patches, max_pairs, fc, net_out=None):
         """forward_planned with the element-wise glue fused into hand-written kernels (devo_b200.glue) and

@@ -245,6 +245,10 @@ typedef struct {
   void* net16_out;        /* [E, 384] hidden state out (may alias net16) */
   void* delta;            /* [E, 2] */
   void* weight;           /* [E, 2] */
+  /* optional fused BA inputs (devo.py:326-331): target = coords[:, :, 1, 1] + float(delta), weight as f32 */
+  const float* coords;    /* [E, 2, 3, 3] reprojected patch coordinates, or NULL */
+  float* target32;        /* [E, 2] or NULL */
+  float* weight32;        /* [E, 2] or NULL */
 } devo_gru_io_t;
 size_t devo_gru_workspace(int E, int max_groups);
 int devo_gru_update(const devo_gru_weights_t* weights, const devo_gru_io_t* io, int dtype, void* workspace,
