@@ -255,8 +255,6 @@ __device__ void ba_solve_device(unsigned char* smem_raw, float* poses, const dou
   const int nent = (n + 1) * (n + 2) / 2;
   double* A = reinterpret_cast<double*>(smem_raw);
   double* y = A + n * (n + 1) / 2;
-  double* rinv = y + n + 1;                               // [n] reciprocals of the pivots
-  double* col = rinv + n;                                 // [2][n+1] current / next pivot column (row n = y)
   __shared__ int s_fail;
   const int tid = threadIdx.x;
   if (*status != 0) return;
@@ -288,8 +286,20 @@ __device__ void ba_solve_device(unsigned char* smem_raw, float* poses, const dou
   __syncthreads();
   BA_STAMP(2);
 
-  // load the owned entries into registers; publish column 0 and the first pivot
+  // ---- block-6 LDL^T of the augmented matrix [S | y] (one 6x6 pose block per pivot step) -----------------------
+  // Thread t owns the entries e = t, t+T, ... of the lower triangle (row gi >= column gj; row n is y^T) in REGISTERS
+  // for the whole factorisation.  Step k (pivot block K = [6k, 6k+6)):
+  //   * the owners of column block K have published it as C[(n+1) x 6] (double-buffered by k)
+  //   * every thread factors the 6x6 block C[K,:] = L D L^T redundantly in registers (56 DFMA + 6 reciprocals; the
+  //     pivots are the scalar LDL^T pivots: positive  <=>  S positive definite), the threads t < #rows each solve
+  //     one row  W_i = C_i (L D L^T)^-1  (36 DFMA)                                         -> barrier
+  //   * every entry right of the block:  v -= W[gi] . C[gj]  (6 DFMA); the freshly final entries of column block K+1
+  //     are published for the next step; the entries of column block K are replaced by W (= L_iK; row n: D^-1 z)  -> barrier
+  // 2 barriers per pose block instead of 1 per scalar pivot: 14 instead of 42 at 7 free poses, and the pivot
+  // reciprocals leave the critical path of the trailing update.
   const int naug = (n + 1) * (n + 2) / 2 - 1;            // lower triangle of the augmented matrix without (n,n)
+  double* Cb = y + n + 1;                                 // [2][(n+1)][6] published column blocks
+  double* Wb = Cb + 2 * (n + 1) * 6;                      // [(n+1)][6]
   double v[KENT];
   int ent[KENT];                                          // (gi << 16) | gj, or -1
 #pragma unroll
@@ -304,37 +314,86 @@ __device__ void ba_solve_device(unsigned char* smem_raw, float* poses, const dou
       const int gj = e - gi * (gi + 1) / 2;
       ent[q] = (gi << 16) | gj;
       v[q] = (gi < n) ? A[gi * (gi + 1) / 2 + gj] : y[gj];
-      if (gj == 0) col[gi] = v[q];
-      if (gi == 0) {                                      // entry (0,0): first pivot
-        if (!(v[q] > 0.0) || !isfinite(v[q])) s_fail = 1;
-        rinv[0] = pivot_rcp(v[q]);
+      if (gj < 6) {                                       // column block 0
+        Cb[gi * 6 + gj] = v[q];
+        if (gi < 6) Cb[gj * 6 + gi] = v[q];               // symmetric fill of the pivot block
       }
     }
   }
   __syncthreads();
   BA_STAMP(3);
-  for (int k = 0; k < n; k++) {
-    if (s_fail) break;                                    // uniform (written before the last barrier)
-    const double r = rinv[k];
-    const double* ck = col + (k & 1) * (n + 1);
-    double* cn = col + ((k + 1) & 1) * (n + 1);
+  for (int k = 0; k < nfree; k++) {
+    const int K0 = 6 * k;
+    const double* C = Cb + (k & 1) * (n + 1) * 6;
+    double* Cn = Cb + ((k + 1) & 1) * (n + 1) * 6;
+    // 6x6 pivot block -> unit-lower L (below the diagonal of Sm) and reciprocal pivots, in registers
+    double Sm[6][6], rp[6];
+    bool okp = true;
+#pragma unroll
+    for (int a = 0; a < 6; a++)
+#pragma unroll
+      for (int c = 0; c <= a; c++) Sm[a][c] = C[(K0 + a) * 6 + c];
+#pragma unroll
+    for (int pcol = 0; pcol < 6; pcol++) {
+      const double d = Sm[pcol][pcol];
+      okp = okp && (d > 0.0) && isfinite(d);
+      rp[pcol] = pivot_rcp(d);
+#pragma unroll
+      for (int a = pcol + 1; a < 6; a++) {
+        const double l = Sm[a][pcol] * rp[pcol];
+#pragma unroll
+        for (int c = pcol + 1; c <= a; c++) Sm[a][c] -= l * Sm[c][pcol];     // column pcol still unscaled here
+      }
+#pragma unroll
+      for (int a = pcol + 1; a < 6; a++) Sm[a][pcol] *= rp[pcol];            // now L
+    }
+    if (tid == 0 && !okp) s_fail = 1;
+    // one row of W = C (L D L^T)^-1 per thread: rows below the pivot block and the y row
+    {
+      const int i = K0 + 6 + tid;
+      if (i <= n) {
+        double w[6];
+#pragma unroll
+        for (int a = 0; a < 6; a++) w[a] = C[i * 6 + a];
+#pragma unroll
+        for (int a = 1; a < 6; a++)
+#pragma unroll
+          for (int c = 0; c < a; c++) w[a] -= Sm[a][c] * w[c];           // L u = c
+#pragma unroll
+        for (int a = 0; a < 6; a++) w[a] *= rp[a];                       // D^-1
+#pragma unroll
+        for (int a = 4; a >= 0; a--)
+#pragma unroll
+          for (int c = a + 1; c < 6; c++) w[a] -= Sm[c][a] * w[c];       // L^T w = u
+#pragma unroll
+        for (int a = 0; a < 6; a++) Wb[i * 6 + a] = w[a];
+      }
+    }
+    __syncthreads();
+    if (s_fail) break;                                    // uniform (written before the barrier)
 #pragma unroll
     for (int q = 0; q < KENT; q++) {
       if (ent[q] < 0) continue;
       const int gi = ent[q] >> 16, gj = ent[q] & 0xffff;
-      if (gj <= k) continue;
-      v[q] -= ck[gi] * r * ck[gj];
-      if (gj == k + 1) {
-        cn[gi] = v[q];                                    // next pivot column
-        if (gi == k + 1) {                                // next pivot, final now
-          if (!(v[q] > 0.0) || !isfinite(v[q])) s_fail = 1;
-          rinv[k + 1] = pivot_rcp(v[q]);
-        }
+      if (gj < K0) continue;
+      if (gj < K0 + 6) {                                  // column block K: final, becomes the factor block
+        if (gi >= K0 + 6) v[q] = Wb[gi * 6 + (gj - K0)];
+        continue;
+      }
+      const double* wi = Wb + gi * 6;
+      const double* cj = C + gj * 6;
+      double acc = v[q];
+#pragma unroll
+      for (int a = 0; a < 6; a++) acc -= wi[a] * cj[a];
+      v[q] = acc;
+      if (gj < K0 + 12) {                                 // next pivot block's columns
+        Cn[gi * 6 + (gj - K0 - 6)] = acc;
+        if (gi < K0 + 12) Cn[gj * 6 + (gi - K0 - 6)] = acc;
       }
     }
     __syncthreads();
   }
-  // write the factor back (column gj of A holds L_ij d_j, the y row holds L^-1 y)
+  // write the factor back: A_iK = L_iK (rows below each pivot block), y = D^-1 L^-1 y
 #pragma unroll
   for (int q = 0; q < KENT; q++) {
     if (ent[q] < 0) continue;
@@ -348,38 +407,26 @@ __device__ void ba_solve_device(unsigned char* smem_raw, float* poses, const dou
     return;
   }
   BA_STAMP(4);
-  // back substitution  x = L^-T D^-1 z.  All threads first turn the stored columns into L (A_ki <- A_ki / d_i)
-  // and z into w = D^-1 z; warp 0 then eliminates x_k from the rows i < k with x held in registers
-  // (lane l owns x[l + 32 m]) and the finished x_k broadcast by shuffle: one shared load per row and step.
-  for (int e = tid; e < n * (n + 1) / 2; e += kSolveThreads) {
-    int gi = (int)floorf((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-    while (gi * (gi + 1) / 2 > e) gi--;
-    while ((gi + 1) * (gi + 2) / 2 <= e) gi++;
-    const int gj = e - gi * (gi + 1) / 2;
-    if (gj < gi) A[e] *= rinv[gj];
-  }
-  for (int i = tid; i < n; i += kSolveThreads) y[i] *= rinv[i];
-  __syncthreads();
+  // back substitution  x_K = w_K - sum_{i >= 6k+6} L[i,K]^T x_i, pose blocks in descending order; warp 0, lanes over
+  // rows i, fixed-order shuffle reduction (deterministic)
   if (tid < 32) {
-    constexpr int kSlots = (kMaxN6 + 31) / 32;
-    double x[kSlots];
+    for (int k = nfree - 2; k >= 0; k--) {
+      const int K0 = 6 * k;
+      double part[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      for (int i = K0 + 6 + tid; i < n; i += 32) {
+        const double xi = y[i];
+        const double* li = A + i * (i + 1) / 2 + K0;
 #pragma unroll
-    for (int mm = 0; mm < kSlots; mm++) x[mm] = (tid + 32 * mm < n) ? y[tid + 32 * mm] : 0.0;
-    for (int k = n - 1; k >= 1; k--) {
-      double xk = 0.0;
-#pragma unroll
-      for (int mm = 0; mm < kSlots; mm++)
-        if ((k >> 5) == mm) xk = __shfl_sync(0xffffffffu, x[mm], k & 31);     // warp-uniform branch
-      const int rk = k * (k + 1) / 2;
-#pragma unroll
-      for (int mm = 0; mm < kSlots; mm++) {
-        const int i = tid + 32 * mm;
-        if (32 * mm < k && i < k) x[mm] -= A[rk + i] * xk;
+        for (int a = 0; a < 6; a++) part[a] += li[a] * xi;
       }
-    }
 #pragma unroll
-    for (int mm = 0; mm < kSlots; mm++)
-      if (tid + 32 * mm < n) y[tid + 32 * mm] = x[mm];
+      for (int a = 0; a < 6; a++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part[a] += __shfl_xor_sync(0xffffffffu, part[a], o);
+      }
+      if (tid < 6) y[K0 + tid] -= part[tid];
+      __syncwarp();
+    }
   }
   __syncthreads();
   BA_STAMP(5);
@@ -850,7 +897,7 @@ static int ba_forward_impl(float* poses, float* patches, const float* intrinsics
   } while (0)
 
   DEVO_REQUIRE(ept <= 24, DEVO_ECAPACITY, "ba_forward: system too large (%d entries)", L.nent);
-  const size_t smem_solve = ((size_t)n6 * (n6 + 1) / 2 + 4 * n6 + 8) * 8;
+  const size_t smem_solve = ((size_t)n6 * (n6 + 1) / 2 + (n6 + 1) + 18 * (n6 + 1) + 8) * 8;   // A, y, 2 column blocks + W
   DEVO_REQUIRE(smem_solve <= smem_acc, DEVO_ECAPACITY, "ba_forward: solver does not fit the accumulate CTA's shared memory");
   DEVO_CUDA(cudaMemsetAsync(w + L.ticket, 0, 4 * 32, s));
   for (int itr = 0; itr < iterations; itr++) {
@@ -943,7 +990,7 @@ int devo_ba_sharded_solve(float* poses, const double* sys, int E, int n_poses, i
   DEVO_REQUIRE(workspace && workspace_bytes >= L.total, DEVO_EWORKSPACE,
                "ba_sharded_solve: workspace too small (%zu < %zu)", workspace_bytes, L.total);
   const int n6 = 6 * nfree;
-  const size_t smem = ((size_t)n6 * (n6 + 1) / 2 + 4 * n6 + 8) * 8;
+  const size_t smem = ((size_t)n6 * (n6 + 1) / 2 + (n6 + 1) + 18 * (n6 + 1) + 8) * 8;   // A, y, 2 column blocks + W
   double* dX = (double*)((char*)workspace + L.dX);
 #define SOLVE(K_)                                                                                              \
   do {                                                                                                         \
