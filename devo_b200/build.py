@@ -23,6 +23,10 @@ NVCC_FLAGS = [
 ]
 
 
+# extra flags for instrumented builds, e.g. DEVO_NVCC_EXTRA="-DDEVO_BA_TIMING" (tools/ba_timing.py)
+NVCC_FLAGS += os.environ.get("DEVO_NVCC_EXTRA", "").split()
+
+
 def _nvcc():
     n = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(n):

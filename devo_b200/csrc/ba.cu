@@ -290,9 +290,9 @@ __device__ void ba_solve_device(unsigned char* smem_raw, float* poses, const dou
   // Thread t owns the entries e = t, t+T, ... of the lower triangle (row gi >= column gj; row n is y^T) in REGISTERS
   // for the whole factorisation.  Step k (pivot block K = [6k, 6k+6)):
   //   * the owners of column block K have published it as C[(n+1) x 6] (double-buffered by k)
-  //   * every thread factors the 6x6 block C[K,:] = L D L^T redundantly in registers (56 DFMA + 6 reciprocals; the
-  //     pivots are the scalar LDL^T pivots: positive  <=>  S positive definite), the threads t < #rows each solve
-  //     one row  W_i = C_i (L D L^T)^-1  (36 DFMA)                                         -> barrier
+  //   * each thread t < #rows factors the 6x6 block C[K,:] = L D L^T in registers (56 DFMA + 6 reciprocals; the
+  //     pivots are the scalar LDL^T pivots: positive  <=>  S positive definite) and solves one row
+  //     W_i = C_i (L D L^T)^-1  (36 DFMA)                                                  -> barrier
   //   * every entry right of the block:  v -= W[gi] . C[gj]  (6 DFMA); the freshly final entries of column block K+1
   //     are published for the next step; the entries of column block K are replaced by W (= L_iK; row n: D^-1 z)  -> barrier
   // 2 barriers per pose block instead of 1 per scalar pivot: 14 instead of 42 at 7 free poses, and the pivot
@@ -326,32 +326,32 @@ __device__ void ba_solve_device(unsigned char* smem_raw, float* poses, const dou
     const int K0 = 6 * k;
     const double* C = Cb + (k & 1) * (n + 1) * 6;
     double* Cn = Cb + ((k + 1) & 1) * (n + 1) * 6;
-    // 6x6 pivot block -> unit-lower L (below the diagonal of Sm) and reciprocal pivots, in registers
-    double Sm[6][6], rp[6];
-    bool okp = true;
-#pragma unroll
-    for (int a = 0; a < 6; a++)
-#pragma unroll
-      for (int c = 0; c <= a; c++) Sm[a][c] = C[(K0 + a) * 6 + c];
-#pragma unroll
-    for (int pcol = 0; pcol < 6; pcol++) {
-      const double d = Sm[pcol][pcol];
-      okp = okp && (d > 0.0) && isfinite(d);
-      rp[pcol] = pivot_rcp(d);
-#pragma unroll
-      for (int a = pcol + 1; a < 6; a++) {
-        const double l = Sm[a][pcol] * rp[pcol];
-#pragma unroll
-        for (int c = pcol + 1; c <= a; c++) Sm[a][c] -= l * Sm[c][pcol];     // column pcol still unscaled here
-      }
-#pragma unroll
-      for (int a = pcol + 1; a < 6; a++) Sm[a][pcol] *= rp[pcol];            // now L
-    }
-    if (tid == 0 && !okp) s_fail = 1;
-    // one row of W = C (L D L^T)^-1 per thread: rows below the pivot block and the y row
+    // The threads that own a row below the pivot block (and the y row) factor the 6x6 block C[K,:] = L D L^T in
+    // registers (unit-lower L below the diagonal of Sm, reciprocal pivots rp) and solve their row W_i = C_i (L D L^T)^-1
     {
       const int i = K0 + 6 + tid;
       if (i <= n) {
+        double Sm[6][6], rp[6];
+        bool okp = true;
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+          for (int c = 0; c <= a; c++) Sm[a][c] = C[(K0 + a) * 6 + c];
+#pragma unroll
+        for (int pcol = 0; pcol < 6; pcol++) {
+          const double d = Sm[pcol][pcol];
+          okp = okp && (d > 0.0) && isfinite(d);
+          rp[pcol] = pivot_rcp(d);
+#pragma unroll
+          for (int a = pcol + 1; a < 6; a++) {
+            const double l = Sm[a][pcol] * rp[pcol];
+#pragma unroll
+            for (int c = pcol + 1; c <= a; c++) Sm[a][c] -= l * Sm[c][pcol];     // column pcol still unscaled here
+          }
+#pragma unroll
+          for (int a = pcol + 1; a < 6; a++) Sm[a][pcol] *= rp[pcol];            // now L
+        }
+        if (tid == 0 && !okp) s_fail = 1;                 // thread 0 always owns a row (at least the y row)
         double w[6];
 #pragma unroll
         for (int a = 0; a < 6; a++) w[a] = C[i * 6 + a];
