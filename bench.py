@@ -241,6 +241,39 @@ def run_ours(args, rank, world, local_rank):
                     note="window gathers overlap ~6x: L2->SM bytes, not HBM bytes, bound this kernel (DESIGN.md)")
 
 
+    # ---- tensor roofline of the fused update operator (gru_mma_kernel x8: the largest share of a step), timed alone
+    roofline_gru = None
+    if args.gru == "mma":
+        with torch.no_grad():
+            gg = torch.cuda.CUDAGraph()
+            scratch = torch.empty_like(op.net)
+            with torch.cuda.graph(gg):
+                op.update.forward_mma(op.net, op.imap, op.kk, op.corr_buf, op.plan_kk, op.plan_ij, op.Np, op.Nf * op.Nf,
+                                      op.packed, net_out=scratch, workspace=op._gru_ws)
+            gt = []
+            for _ in range(30):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                gg.replay()
+                e1.record(stream)
+                gt.append((e0, e1))
+            torch.cuda.synchronize(dev)
+            gms = sorted(x.elapsed_time(y) for x, y in gt[5:])
+            g_ms = sum(gms) / len(gms)
+        fl = synthetic.gru_flops(wl["E"], op.Np, op.Nf * op.Nf, wl["dim"], op.corr_ld)
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                tpeak, tsrc = float(json.load(f)["bf16_tflops_sustained"]), "measured sustained bf16 (MEASURED_PEAKS.json)"
+        except Exception:
+            tpeak, tsrc = 1368.0, "fallback (B200_PROFILING.md)"
+        roofline_gru = dict(bound="tensor", kernel="gru_mma_kernel x8 + segment_softmax_sum x2 (devo_gru_update)",
+                            achieved=round(fl / (g_ms * 1e-3) / 1e12, 2), peak=tpeak, unit="TFLOP/s",
+                            frac=round(fl / (g_ms * 1e-3) / 1e12 / tpeak, 4), traffic=None, flops=fl, kernel_ms=round(g_ms, 5),
+                            peak_source=tsrc,
+                            note="latency-bound chain of 17 small GEMMs ([6144,384]x[384,384]): MMA -> epilogue -> cluster hand-off "
+                                 "serialise per layer on 96 SMs (DESIGN.md 2.6); L2 flushed before each replay")
+
     value = world * args.steps / (total_ms * 1e-3)
     line = dict(metric=METRIC, value=round(value, 2), unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=round(total_ms / args.steps, 5), higher_is_better=True, scaling="weak", vs_baseline=None,
@@ -249,7 +282,7 @@ def run_ours(args, rank, world, local_rank):
                             parallelism="replicas: one sequence per GPU, no data-path collective",
                             step="ingest of 1 frame + 1 update iteration, one CUDA-graph replay", gru=args.gru,
                             ba_status=status, value_l2_warm=round(world * args.steps / (warm_ms * 1e-3), 2)),
-                roofline=roofline, e2e=e2e, gpu_launches=int(launches_per_step * args.steps), clocks=clocks)
+                roofline=roofline, roofline_gru=roofline_gru, e2e=e2e, gpu_launches=int(launches_per_step * args.steps), clocks=clocks)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_once()
     return line

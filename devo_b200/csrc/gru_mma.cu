@@ -208,11 +208,10 @@ struct Epi {
 #pragma unroll
         for (int k = 0; k < N; k++) st_cluster_f32(dst + 4 * k, vals[k]);
       }
-      // no acquire.cluster on the waiting side (it invalidates L1 -- CCTL.IVALL -- on every wait, and everything
-      // exchanged lives in shared memory); the release.cluster arrive after the CTA barrier publishes the stores
+      // the release.cluster arrive after the CTA barrier publishes every thread's stores to the peers
       epi_bar();
       if (et < kSplit) mbar_arrive_cluster(mapa(smem_u32(stat_bar), (uint32_t)et));
-      mbar_wait(stat_bar, stat_uses & 1u);
+      mbar_wait_cluster(stat_bar, stat_uses & 1u);          // the peers' partials: acquire at cluster scope
       stat_uses++;
     } else {
       epi_bar();
@@ -683,7 +682,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
       if (l == 0) {
         if (has_pro) { mbar_wait(pro_ready, 0u); fence_proxy_async(); tc_fence_after(); }
       } else {                         // the A tile now holds every CTA's slice of the previous layer's output
-        mbar_wait(a_ready, (uint32_t)((l - 1) & 1));
+        mbar_wait_cluster(a_ready, (uint32_t)((l - 1) & 1));   // peers' DSMEM stores: acquire at cluster scope
         fence_proxy_async();
         tc_fence_after();
       }

@@ -98,3 +98,9 @@ def corr_algorithmic_bytes(n_frames, patches_per_frame, E, C, H4, W4, levels, el
     Np = n_frames * patches_per_frame
     pyr = sum(n_frames * C * (H4 // s) * (W4 // s) for s in levels)
     return elem_bytes * (Np * C * P * P + pyr) + 4 * (E * 2 * P * P) + 8 * (2 * E) + elem_bytes * (E * len(levels) * 49 * P * P)
+
+
+def gru_flops(E, n_groups_kk, n_groups_ij, dim=384, corr_k=896):
+    """dense-layer FLOPs of one Update.forward (enet.py:80-99): per edge corr[0] (K = corr_k, zero-padded) + 16 layers of
+    dim x dim (corr[2], corr[5], c1 x2, c2 x2, agg_kk.g/f, agg_ij.g/f, 2 x (gate, res[0], res[2])); per group agg.h"""
+    return 2 * E * dim * (corr_k + 16 * dim) + 2 * (n_groups_kk + n_groups_ij) * dim * dim

@@ -14,3 +14,15 @@ $T 600 compute-sanitizer --tool racecheck --error-exitcode 9 --launch-timeout 12
    > gpurun_out/sanitize_racecheck.log 2>&1
 echo "racecheck exit $?"
 grep -E "RACECHECK SUMMARY|passed|failed" gpurun_out/sanitize_racecheck.log | tail -3
+# fused update operator (tcgen05 / TMA / 2-CTA clusters with DSMEM) and the edge-sharded BA
+$T 900 compute-sanitizer --tool memcheck --error-exitcode 9 --launch-timeout 120 \
+   python -m pytest tests/test_gpu_gru_mma.py tests/test_gpu_ba.py -q -m gpu -p no:cacheprovider \
+   -k "(matches_cublas_path and (3-5 or 4-24)) or deterministic or (simulated_ranks and 5-7)" \
+   > gpurun_out/sanitize_memcheck_gru.log 2>&1
+echo "memcheck(gru) exit $?"
+grep -E "ERROR SUMMARY|passed|failed" gpurun_out/sanitize_memcheck_gru.log | tail -3
+$T 600 compute-sanitizer --tool racecheck --error-exitcode 9 --launch-timeout 120 \
+   python -m pytest tests/test_gpu_gru_mma.py -q -m gpu -p no:cacheprovider -k "matches_cublas_path and 3-5" \
+   > gpurun_out/sanitize_racecheck_gru.log 2>&1
+echo "racecheck(gru) exit $?"
+grep -E "RACECHECK SUMMARY|passed|failed" gpurun_out/sanitize_racecheck_gru.log | tail -3
