@@ -31,24 +31,31 @@ def _check_common(fmap1, fmap2, coords, ii, jj):
         raise RuntimeError("cuda_corr: ii/jj length must equal coords.shape[1]")
 
 
-def pack_pixel_major(fmap, pool=1):
-    """planar [N,C,H,W] -> pixel-major [N,H//pool,W//pool,C] (average pooled); f16/bf16"""
+def pack_pixel_major(fmap, pool=1, out=None):
+    """planar [N,C,H,W] -> pixel-major [N,H//pool,W//pool,C] (average pooled); f16/bf16.
+    `out`: contiguous destination (e.g. a slot of the pyramid ring buffer) to pack into directly"""
     _lib.require_cuda(fmap)
     fmap = fmap.contiguous()
     N, C, H, W = fmap.shape
-    out = torch.empty(N, H // pool, W // pool, C, dtype=fmap.dtype, device=fmap.device)
+    if out is None:
+        out = torch.empty(N, H // pool, W // pool, C, dtype=fmap.dtype, device=fmap.device)
+    elif (not out.is_contiguous()) or out.dtype != fmap.dtype or out.numel() != N * (H // pool) * (W // pool) * C:
+        raise RuntimeError("pack_pixel_major: out must be a contiguous [N,H/pool,W/pool,C] tensor of the input dtype")
     _lib.check(_lib.lib().devo_pyramid_pack(fmap.data_ptr(), out.data_ptr(), _lib.dtype_code(fmap),
                                             N, C, H, W, pool, _lib.stream_ptr(fmap.device)), "pyramid_pack")
     return out
 
 
-def pack_gmap(gmap):
-    """planar [Np,C,P,P] -> [Np,P*P,C]"""
+def pack_gmap(gmap, out=None):
+    """planar [Np,C,P,P] -> [Np,P*P,C]  (`out`: contiguous destination to pack into directly)"""
     _lib.require_cuda(gmap)
     gmap = gmap.contiguous()
     Np, C = gmap.shape[0], gmap.shape[1]
     PP = gmap.shape[2] * gmap.shape[3]
-    out = torch.empty(Np, PP, C, dtype=gmap.dtype, device=gmap.device)
+    if out is None:
+        out = torch.empty(Np, PP, C, dtype=gmap.dtype, device=gmap.device)
+    elif (not out.is_contiguous()) or out.dtype != gmap.dtype or out.numel() != Np * PP * C:
+        raise RuntimeError("pack_gmap: out must be a contiguous [Np,P*P,C] tensor of the input dtype")
     _lib.check(_lib.lib().devo_gmap_pack(gmap.data_ptr(), out.data_ptr(), _lib.dtype_code(gmap), Np, C, PP,
                                          _lib.stream_ptr(gmap.device)), "gmap_pack")
     return out

@@ -90,10 +90,10 @@ class UpdateOperator:
         """fmap [C,H,W] planar features of frame `idx` -> all pixel-major pyramid levels;
         gmap_patches [M,C,3,3], imap_patches [M,dim] -> patch feature buffers"""
         f = fmap.reshape(1, self.C, self.H, self.W).to(self.feat_dtype)
-        for l, s in enumerate(self.levels):
-            self.levels_pm[l][idx:idx + 1].copy_(cuda_corr.pack_pixel_major(f, s))
+        for l, s in enumerate(self.levels):        # packed straight into the ring-buffer slot (no staging copy)
+            cuda_corr.pack_pixel_major(f, s, out=self.levels_pm[l][idx:idx + 1])
         if gmap_patches is not None:
-            self.gmap_pm[idx * self.M:(idx + 1) * self.M].copy_(cuda_corr.pack_gmap(gmap_patches.to(self.feat_dtype)))
+            cuda_corr.pack_gmap(gmap_patches.to(self.feat_dtype), out=self.gmap_pm[idx * self.M:(idx + 1) * self.M])
         if imap_patches is not None:
             self.imap[0, idx * self.M:(idx + 1) * self.M].copy_(imap_patches.to(self.feat_dtype))
 
