@@ -646,10 +646,14 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_slot;
   const bool has_pro = (P.pro != PRO_NONE);
   if (threadIdx.x == 0) stamp(P.dbg, 1);
+  // PDL: everything above (barriers, TMEM, parameters) and the weight stream below only touch constants, so this grid
+  // may start while its predecessor still runs; the next grid of the stream may start now as well.
+  if (threadIdx.x == 0) pdl_launch_dependents();
 
   if (warp == 0) {
     // =========================== TMA producer: this CTA's weight slice of every layer (+ the streamed A of layer 0)
     if (lane == 0) { prefetch_tensormap(&tm_w); if (P.use_w0) prefetch_tensormap(&tm_w0); if (P.stream_a0) prefetch_tensormap(&tm_a); }
+    if (P.stream_a0) pdl_wait();                    // the streamed A operand is the previous kernel's output
     uint32_t stage = 0, phase = 0;
     for (int l = 0; l < P.n_layers; l++) {
       const int nkb = (l == 0) ? P.kblocks0 : kASlots;
@@ -728,6 +732,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
     e.net_r = P.net32 + t32(tile, 0, e.r);
     e.n32_r = P.n32 + t32(tile, 0, e.r);
     e.gate_r = P.gate16 + t16(tile, 0, e.r);
+    pdl_wait();                                     // first use of the previous kernels' results (and first global writes)
     switch (P.pro) {                                // warp-uniform
       case PRO_GATHER: e.template prologue<PRO_GATHER>(); break;
       case PRO_CAST: e.template prologue<PRO_CAST>(); break;
@@ -815,11 +820,15 @@ static int launch_prog(const CUtensorMap& tw, const CUtensorMap& tw0, const CUte
   cfg.blockDim = dim3(kThreads, 1, 1);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;      // kSplit CTAs share one 128-row tile
   attr[0].val.clusterDim.x = kSplit; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap the set-up with the previous kernel's tail
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  static int use_pdl = -1;
+  if (use_pdl < 0) { const char* e = getenv("DEVO_GRU_PDL"); use_pdl = (e && e[0] == '0') ? 0 : 1; }
+  cfg.numAttrs = use_pdl ? 2 : 1;
   DEVO_CUDA(cudaLaunchKernelEx(&cfg, gru_mma_kernel<T>, tw, tw0, ta, Pd));
   DEVO_LAUNCH_CHECK("gru_mma");
   return DEVO_OK;

@@ -17,6 +17,9 @@ __global__ void segment_softmax_sum_kernel(const T* __restrict__ g, const T* __r
                                            const int32_t* __restrict__ perm, const int32_t* __restrict__ gstart,
                                            const int32_t* __restrict__ ngroups, T* __restrict__ y, int dim) {
   extern __shared__ float red[];   // [parts][3][blockDim.x]
+  // PDL: a dependent kernel launched with programmatic stream serialisation (the h GEMM of the update operator) may
+  // begin its set-up now; it waits (griddepcontrol.wait) for this grid's completion before reading y
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int grp = blockIdx.x;
   const int G = *ngroups;
   const int parts = blockDim.y, part = threadIdx.y;
