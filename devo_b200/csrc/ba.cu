@@ -485,6 +485,8 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
   __shared__ int s_gstart[kMaxGroupsPerCta + 1];
 
   const int tid = threadIdx.x;
+  DEVO_PDL_WAIT();       // launched with programmatic stream serialisation: the previous iteration's results are needed from here on
+  DEVO_PDL_TRIGGER();
 #ifdef DEVO_BA_TIMING
   if (blockIdx.x == 0 && tid == 0) g_ba_clk[0] = clock64();
 #endif
@@ -750,6 +752,7 @@ __global__ void transform_kernel(const float* __restrict__ poses, const float* _
                                  float* __restrict__ coords, float* __restrict__ valid, float* __restrict__ Ji_o,
                                  float* __restrict__ Jj_o, float* __restrict__ Jz_o, int E, int P, int layout, int tonly) {
   const int PP = P * P;
+  DEVO_PDL_TRIGGER();   // the lookup kernel that follows may set up its barriers / TMEM while this grid runs
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= E * PP) return;
   const int n = t / PP, p = t - n * PP;
@@ -820,10 +823,10 @@ static int launch_accumulate(const BaLayout& L, char* w, float* poses, float* pa
     DEVO_CUDA(cudaFuncSetAttribute(ba_accumulate_kernel<EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  ba_accumulate_kernel<EPT><<<L.grid, kAccThreads, smem, s>>>(
+  DEVO_CUDA(devo::launch_pdl(ba_accumulate_kernel<EPT>, dim3(L.grid), dim3(kAccThreads), smem, s,
       poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, perm_p, gstart_p, gkey_p, ngroups_p,
       (double*)(w + L.Q), (double*)(w + L.U), (double*)(w + L.Ek), (double*)(w + L.partials),
-      (double*)(w + L.dX), (int32_t*)(w + L.ticket), status, E, PP, centre, t0, nfree, n_poses, EB, GB, apply_update, do_accumulate, itr, sys_out);
+      (double*)(w + L.dX), (int32_t*)(w + L.ticket), status, E, PP, centre, t0, nfree, n_poses, EB, GB, apply_update, do_accumulate, itr, sys_out));
   DEVO_LAUNCH_CHECK("ba_accumulate");
   return DEVO_OK;
 }

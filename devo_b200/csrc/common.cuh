@@ -71,6 +71,21 @@ static inline int elem_size(int dtype) {
   return 0;
 }
 
+// Launch with programmatic stream serialisation (PDL): the grid may start while its predecessor in the stream is still
+// running; the kernel must execute griddepcontrol.wait before it touches anything the predecessor produced.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define DEVO_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define DEVO_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace devo

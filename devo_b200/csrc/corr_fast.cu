@@ -345,6 +345,8 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  DEVO_PDL_WAIT();       // PDL: barriers / TMEM are set up while the reprojection kernel finishes; its coords are read below
+  DEVO_PDL_TRIGGER();
   CoordView cv{cring, cfull, eb0, -1, cring, 0};
 
   if (warp < kProducers) {
@@ -738,7 +740,7 @@ static int launch_fast(const CUtensorMap* maps, const FastParams& prm, cudaStrea
     configured = true;
   }
   int grid = prm.items < 148 ? prm.items : 148;
-  corr_fast_kernel<T><<<grid, kThreads, smem, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], prm);
+  DEVO_CUDA(devo::launch_pdl(corr_fast_kernel<T>, dim3(grid), dim3(kThreads), smem, s, maps[0], maps[1], maps[2], maps[3], maps[4], prm));
   DEVO_LAUNCH_CHECK("corr_lookup_fused");
   return DEVO_OK;
 }
