@@ -45,7 +45,7 @@ constexpr int kStages = DEVO_CORR_STAGES;
 #define DEVO_CORR_PRODUCERS 3
 #endif
 #ifndef DEVO_CORR_EPI_GROUPS
-#define DEVO_CORR_EPI_GROUPS 3
+#define DEVO_CORR_EPI_GROUPS 4
 #endif
 constexpr int kProducers = DEVO_CORR_PRODUCERS;   // TMA producer warps (warps 0..kProducers-1), kProducers <= 3
 #ifndef DEVO_CORR_MMA_WARPS
