@@ -52,7 +52,7 @@ constexpr int kEpiPer = 2;                 // epilogue warps per TMEM lane quart
 constexpr int kEpiThreads = 128 * kEpiPer;
 constexpr int kFirstEpiWarp = 2;            // warps 0 (TMA) and 1 (MMA) + the epilogue warps; any 4 consecutive warps cover the 4 TMEM lane quarters
 constexpr int kThreads = 32 * kFirstEpiWarp + kEpiThreads;
-constexpr int kMaxLayers = 6;
+constexpr int kMaxLayers = 7;
 constexpr int kChunks = kD / 8;            // 16-byte chunks per row (48)
 constexpr int kCol4 = kD / 4;              // float4 groups per row (96)
 constexpr int kCB = kD / 32;               // 32-column blocks per row (12)
@@ -62,7 +62,7 @@ static_assert(kD % kSplit == 0 && kNC % 32 == 0 && kCBc % kEpiPer == 0 && kNC % 
 
 enum { PRO_NONE = 0, PRO_GATHER = 1, PRO_CAST = 2, PRO_RESID = 3, PRO_RESID_LN = 4 };
 enum { EPI_RELU_A = 0, EPI_LNRELU_A = 1, EPI_ADD3_LN = 2, EPI_RESID = 3, EPI_STORE_A = 4, EPI_STORE_B = 5,
-       EPI_GATE = 6, EPI_GATED_LN = 7, EPI_GATED_HEADS = 8 };
+       EPI_GATE = 6, EPI_GATED_LN = 7, EPI_GATED_HEADS = 8, EPI_RESID_A = 9, EPI_RESID_LN_A = 10 };
 
 template <typename T>
 struct GruProg {
@@ -77,6 +77,7 @@ struct GruProg {
   float eps;
   const T* x16_in;                         // row-major [src_rows,384]: gather source / hidden state in (ADD3)
   const int64_t* idx64;                    // PRO_GATHER: source row per row (-1 => zero row); null => identity
+  const int32_t* idx32;                    // PRO_GATHER: ... or a 32-bit index (the group of each row) when idx64 is null
   const int32_t* gid;                      // PRO_RESID*: group of each row ...
   const T* y16;                            // ... and the [groups,384] values added through it
   const int32_t* gid2;                     // PRO_RESID_LN: a second (group, values) pair added after the first
@@ -235,7 +236,7 @@ struct Epi {
         const int gr = row0 + et;
         int src = -1;
         if (gr < P.rows) {
-          const long long j = P.idx64 ? (long long)P.idx64[gr] : (long long)gr;
+          const long long j = P.idx64 ? (long long)P.idx64[gr] : (P.idx32 ? (long long)P.idx32[gr] : (long long)gr);
           src = (j >= 0 && j < (long long)P.src_rows) ? (int)j : -1;
         }
         s_idx[et] = src;
@@ -358,7 +359,8 @@ struct Epi {
   template <int EPI>
   __device__ __forceinline__ void layer(int l) {
     constexpr bool kGated = (EPI == EPI_GATED_LN || EPI == EPI_GATED_HEADS);
-    constexpr int kAux = (EPI == EPI_RESID || EPI == EPI_ADD3_LN) ? 2 : (kGated ? 3 : 1);
+    constexpr bool kResid = (EPI == EPI_RESID || EPI == EPI_RESID_A || EPI == EPI_RESID_LN_A);
+    constexpr int kAux = (kResid || EPI == EPI_ADD3_LN) ? 2 : (kGated ? 3 : 1);
     constexpr int kIter = kCBp * 4;                 // 16-byte chunks per thread
     const float* bias = s_bias + l * kD;
     float s1 = 0.f, s2 = 0.f;
@@ -379,7 +381,7 @@ struct Epi {
     // per-row operands of the element-wise tail, fetched one chunk ahead of their use
     // RESID: q[0..1] net32 ; GATED: q[0..1] n32, q[2] gate ; ADD3: q[0] net16, q[1] inp16
     auto load_aux = [&](int c, uint4* q) {
-      if constexpr (EPI == EPI_RESID) {
+      if constexpr (kResid) {
         q[0] = *f4(net_r, 2 * c);
         q[1] = *f4(net_r, 2 * c + 1);
       } else if constexpr (kGated) {
@@ -450,6 +452,22 @@ struct Epi {
           const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
           *reinterpret_cast<uint4*>(orow + c * 8) = pack8<T>(v);
         }
+      } else if constexpr (EPI == EPI_RESID_A || EPI == EPI_RESID_LN_A) {
+        // net += half Linear output (the SoftAgg `h` layer applied per edge: h(y)[:, gid] == h(y[:, gid]), row by row
+        // bit-identical to the per-group product), then the sum becomes the next A operand (optionally after LayerNorm)
+        unpack8<T>(oh, o);
+        const float4 a = as_f4(cur[0]), b = as_f4(cur[1]);
+        float x[8] = {a.x + o[0], a.y + o[1], a.z + o[2], a.w + o[3], b.x + o[4], b.y + o[5], b.z + o[6], b.w + o[7]};
+        if constexpr (EPI == EPI_RESID_A) {
+          *f4w(net_r, 2 * c) = make_float4(x[0], x[1], x[2], x[3]);      // own column slice only: nobody else reads it here
+          *f4w(net_r, 2 * c + 1) = make_float4(x[4], x[5], x[6], x[7]);
+          a_store_all(c, pack8<T>(x));
+        } else {
+          uint32_t xs[8];
+#pragma unroll
+          for (int k = 0; k < 8; k++) { s1 += x[k]; s2 += x[k] * x[k]; xs[k] = __float_as_uint(x[k]); }
+          tmem_st8(tcol + i * 8, xs);
+        }
       } else {   // EPI_GATED_LN / EPI_GATED_HEADS:  x = n + half(half(sigmoid(gate)) * res)
         float g[8];
         unpack8<T>(oh, o);
@@ -489,7 +507,7 @@ struct Epi {
         for (int k = 0; k < kAux; k++) cur[k] = nxt[k];
       }
     }
-    if (et == 0 && l == 0) stamp(P.dbg, 28);
+    if (et == 0 && l == 0) stamp(P.dbg, 40);
     // ---------------- row-wise tails ----------------
     if constexpr (EPI == EPI_LNRELU_A || EPI == EPI_ADD3_LN) {
       // this thread's slice of the row (half values) sits in the local A tile: one more pass over shared memory
@@ -515,7 +533,7 @@ struct Epi {
         }
       }
       ln_used++;
-    } else if constexpr (EPI == EPI_GATED_LN) {
+    } else if constexpr (EPI == EPI_GATED_LN || EPI == EPI_RESID_LN_A) {
       tmem_wait_st();
       float mean, rstd;
       ln_stats(s1, s2, mean, rstd);
@@ -558,7 +576,7 @@ struct Epi {
       }
     }
     tc_fence_before();
-    if (et == 0 && l == 0) stamp(P.dbg, 29);
+    if (et == 0 && l == 0) stamp(P.dbg, 41);
     if (l + 1 < P.n_layers) {       // hand the A tiles / the TMEM accumulator back to the MMA warps of the cluster
       if (kSplit > 1) fence_proxy_async_cluster(); else fence_proxy_async();   // A-tile writes (local and peers') -> async proxy
       epi_bar();
@@ -751,6 +769,8 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
         case EPI_STORE_B: e.template layer<EPI_STORE_B>(l); break;
         case EPI_GATE: e.template layer<EPI_GATE>(l); break;
         case EPI_GATED_LN: e.template layer<EPI_GATED_LN>(l); break;
+        case EPI_RESID_A: e.template layer<EPI_RESID_A>(l); break;
+        case EPI_RESID_LN_A: e.template layer<EPI_RESID_LN_A>(l); break;
         default: e.template layer<EPI_GATED_HEADS>(l); break;
       }
     }
@@ -800,7 +820,7 @@ constexpr size_t kSmemBytes = 1024 + (size_t)kASlots * kABlk + (size_t)kWStages 
                               (size_t)kSplit * kEpiPer * kRows * 4 * sizeof(float) + 4 * kD * sizeof(float) + kMaxLayers * kD * sizeof(float) + (4 * kD + 8) * 2 + 64;
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
-static long long* g_dbg = nullptr;     // 16 launches x 32 stamps, allocated when DEVO_GRU_TIMING is set
+static long long* g_dbg = nullptr;     // 16 launches x 48 stamps, allocated when DEVO_GRU_TIMING is set
 static int g_dbg_launch = 0;
 
 template <typename T>
@@ -813,7 +833,7 @@ static int launch_prog(const CUtensorMap& tw, const CUtensorMap& tw0, const CUte
   const int tiles = (P.rows + kRows - 1) / kRows;
   if (tiles <= 0) return DEVO_OK;
   GruProg<T> Pd = P;
-  Pd.dbg = g_dbg ? g_dbg + 32 * (g_dbg_launch++ % 16) : nullptr;
+  Pd.dbg = g_dbg ? g_dbg + 48 * (g_dbg_launch++ % 16) : nullptr;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(tiles * kSplit), 1, 1);
@@ -914,43 +934,40 @@ static int gru_update_impl(const devo_gru_weights_t* Wt, const devo_gru_io_t* io
     rc = launch_prog<T>(tw, tw0, ta, P, s);
     if (rc != DEVO_OK) return rc;
   }
-  // (4,5) net += SoftAgg(net) over patches, then over frame pairs  (enet.py:93-94, blocks.py:40-48)
-  for (int k = 0; k < 2; k++) {
-    const int32_t* perm = k == 0 ? io->perm_kk : io->perm_ij;
-    const int32_t* gstart = k == 0 ? io->gstart_kk : io->gstart_ij;
-    const int32_t* ngroups = k == 0 ? io->ngroups_kk : io->ngroups_ij;
-    const int mg = k == 0 ? io->max_groups_kk : io->max_groups_ij;
-    {
-      GruProg<T> P = base;
-      P.n_layers = 2; P.pro = k == 0 ? PRO_CAST : PRO_RESID;
-      P.gid = io->gid_kk; P.y16 = hy16;                       // k == 1: the patch-wise aggregate is added first
-      P.w_row[0] = (6 + 3 * k) * kD; P.epi[0] = EPI_STORE_A; P.bias[0] = B(6 + 3 * k);     // g
-      P.w_row[1] = (7 + 3 * k) * kD; P.epi[1] = EPI_STORE_B; P.bias[1] = B(7 + 3 * k);     // f
-      P.out16_a = g16; P.out16_b = f16;
-      rc = launch_prog<T>(tw, tw0, ta, P, s);
-      if (rc != DEVO_OK) return rc;
-    }
-    rc = devo_segment_softmax_sum(g16, f16, perm, gstart, ngroups, mg, y16, dtype, E, kD, (void*)s);
-    if (rc != DEVO_OK) return rc;
-    {
-      GruProg<T> P = base;
-      P.rows = mg; P.src_rows = mg;
-      P.n_layers = 1; P.pro = PRO_GATHER; P.x16_in = y16; P.idx64 = nullptr;
-      P.w_row[0] = (8 + 3 * k) * kD; P.epi[0] = EPI_STORE_A; P.bias[0] = B(8 + 3 * k);     // h
-      P.out16_a = k == 0 ? hy16 : hy16b;
-      rc = launch_prog<T>(tw, tw0, ta, P, s);
-      if (rc != DEVO_OK) return rc;
-    }
-  }
-  // (6) gru: LN, GatedResidual, LN, GatedResidual; heads  (enet.py:68-77,96-99)
+  // (4,5,6) net += SoftAgg(net) over patches, then over frame pairs; gru + heads  (enet.py:93-99, blocks.py:40-48).
+  // The `h` layer of a SoftAgg is applied per EDGE inside the kernel that consumes it (h(y)[:, gid] == h(y[:, gid])):
+  // its A operand is the gathered group row y[gid[e]], its epilogue adds the result to the fp32 state.
   {
-    GruProg<T> P = base;
-    P.n_layers = 6; P.pro = PRO_RESID_LN;
-    P.gid = io->gid_kk; P.y16 = hy16; P.gid2 = io->gid_ij; P.y16b = hy16b;     // net + agg_kk + agg_ij, in this order
+    GruProg<T> P = base;                                      // g, f of the patch-wise aggregation
+    P.n_layers = 2; P.pro = PRO_CAST;
+    P.w_row[0] = 6 * kD; P.epi[0] = EPI_STORE_A; P.bias[0] = B(6);
+    P.w_row[1] = 7 * kD; P.epi[1] = EPI_STORE_B; P.bias[1] = B(7);
+    P.out16_a = g16; P.out16_b = f16;
+    rc = launch_prog<T>(tw, tw0, ta, P, s);
+    if (rc != DEVO_OK) return rc;
+  }
+  rc = devo_segment_softmax_sum(g16, f16, io->perm_kk, io->gstart_kk, io->ngroups_kk, io->max_groups_kk, y16, dtype, E, kD, (void*)s);
+  if (rc != DEVO_OK) return rc;
+  {
+    GruProg<T> P = base;                                      // net += h_kk(y_kk)[gid_kk]; g, f of the pair-wise aggregation
+    P.n_layers = 3; P.pro = PRO_GATHER; P.x16_in = y16; P.idx32 = io->gid_kk; P.src_rows = io->max_groups_kk;
+    P.w_row[0] = 8 * kD;  P.epi[0] = EPI_RESID_A; P.bias[0] = B(8);
+    P.w_row[1] = 9 * kD;  P.epi[1] = EPI_STORE_A; P.bias[1] = B(9);
+    P.w_row[2] = 10 * kD; P.epi[2] = EPI_STORE_B; P.bias[2] = B(10);
+    P.out16_a = g16; P.out16_b = f16;
+    rc = launch_prog<T>(tw, tw0, ta, P, s);
+    if (rc != DEVO_OK) return rc;
+  }
+  rc = devo_segment_softmax_sum(g16, f16, io->perm_ij, io->gstart_ij, io->ngroups_ij, io->max_groups_ij, hy16, dtype, E, kD, (void*)s);
+  if (rc != DEVO_OK) return rc;
+  {
+    GruProg<T> P = base;                                      // net += h_ij(y_ij)[gid_ij]; LN, GatedResidual x2; heads
+    P.n_layers = 7; P.pro = PRO_GATHER; P.x16_in = hy16; P.idx32 = io->gid_ij; P.src_rows = io->max_groups_ij;
     P.ln_g[0] = Wt->ln_gamma + 2 * kD; P.ln_b[0] = Wt->ln_beta + 2 * kD;
     P.ln_g[1] = Wt->ln_gamma + 3 * kD; P.ln_b[1] = Wt->ln_beta + 3 * kD;
+    P.w_row[0] = 11 * kD; P.epi[0] = EPI_RESID_LN_A; P.bias[0] = B(11);
     const int epis[6] = {EPI_GATE, EPI_RELU_A, EPI_GATED_LN, EPI_GATE, EPI_RELU_A, EPI_GATED_HEADS};
-    for (int l = 0; l < 6; l++) { P.w_row[l] = (12 + l) * kD; P.epi[l] = epis[l]; P.bias[l] = B(12 + l); }
+    for (int l = 0; l < 6; l++) { P.w_row[1 + l] = (12 + l) * kD; P.epi[1 + l] = epis[l]; P.bias[1 + l] = B(12 + l); }
     P.out16_a = (T*)io->net16_out;
     P.headW = (const T*)Wt->head_W; P.headB = (const T*)Wt->head_b;
     P.delta = (T*)io->delta; P.weight = (T*)io->weight;
@@ -970,8 +987,8 @@ size_t devo_gru_workspace(int E, int max_groups) { return gru_ws(E, max_groups).
 // debug (tools/gru_timing.py): enable / read back the %globaltimer stamps of CTA 0 of the last 16 launches
 int devo_gru_debug_timing(long long* host_out) {
   if (!g_dbg) {
-    if (cudaMalloc(&g_dbg, 16 * 32 * sizeof(long long)) != cudaSuccess) return -1;
-    cudaMemset(g_dbg, 0, 16 * 32 * sizeof(long long));
+    if (cudaMalloc(&g_dbg, 16 * 48 * sizeof(long long)) != cudaSuccess) return -1;
+    cudaMemset(g_dbg, 0, 16 * 48 * sizeof(long long));
   }
   g_dbg_launch = 0;
   {
@@ -989,7 +1006,7 @@ int devo_gru_debug_timing(long long* host_out) {
     cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, gru_mma_kernel<__half>, &cfg);
     fprintf(stderr, "gru_mma: split %d, max co-resident clusters %d (%s)\n", kSplit, nclusters, cudaGetErrorString(e));
   }
-  if (host_out) return (int)cudaMemcpy(host_out, g_dbg, 16 * 32 * sizeof(long long), cudaMemcpyDeviceToHost);
+  if (host_out) return (int)cudaMemcpy(host_out, g_dbg, 16 * 48 * sizeof(long long), cudaMemcpyDeviceToHost);
   return 0;
 }
 

@@ -1,5 +1,5 @@
 """Where the time goes inside the fused update operator (csrc/gru_mma.cu): CUDA-event time of forward_mma vs the
-cuBLAS + glue path, and the %globaltimer stamps CTA 0 of each of the 10 launches records.
+cuBLAS + glue path, and the %globaltimer stamps CTA 0 of each of the 6 gru_mma launches records.
     python tools/gru_timing.py"""
 import ctypes
 import os
@@ -59,18 +59,18 @@ def main():
         L.devo_gru_debug_timing(None)
         up.forward_mma(net, imap, kk, corr, plan_kk, plan_ij, Np, nf * nf, packed)
         torch.cuda.synchronize()
-        buf = (ctypes.c_longlong * (16 * 32))()
+        buf = (ctypes.c_longlong * (16 * 48))()
         L.devo_gru_debug_timing(buf)
-    names = ["corr+norm", "c1", "c2", "agg_kk g,f", "agg_kk h", "agg_ij g,f", "agg_ij h", "gru+heads"]
-    nl = [3, 2, 2, 2, 1, 2, 1, 6]
+    names = ["corr+norm", "c1", "c2", "agg_kk g,f", "h_kk+agg_ij g,f", "h_ij+gru+heads"]
+    nl = [3, 2, 2, 2, 3, 7]
     for k, (nm, n) in enumerate(zip(names, nl)):
-        s = [buf[32 * k + q] for q in range(32)]
+        s = [buf[48 * k + q] for q in range(48)]
         t0 = s[0]
         rel = lambda q: (s[q] - t0) / 1e3 if s[q] else float("nan")
         line = "%-12s setup %.1f pro %.1f |" % (nm, rel(1), rel(2))
         for l in range(n):
             line += " L%d mma %.1f-%.1f epi %.1f-%.1f |" % (l, rel(4 + 4 * l), rel(5 + 4 * l), rel(6 + 4 * l), rel(7 + 4 * l))
-        line += " end %.1f us  [L0 epi: loop %.1f tail %.1f fences %.1f bar %.1f]" % (rel(3), rel(28), rel(29), rel(30), rel(31))
+        line += " end %.1f us  [L0 epi: loop %.1f tail %.1f fences %.1f bar %.1f]" % (rel(3), rel(40), rel(41), rel(42), rel(43))
         print(line)
 
 
