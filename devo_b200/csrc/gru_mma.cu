@@ -39,6 +39,9 @@ using devo::ElemTraits;
 
 constexpr int kRows = 128;                 // edges per tile = MMA M
 constexpr int kD = 384;                    // hidden width: N of every layer, K of all but the first
+#ifndef DEVO_GRU_CHUNKS_PER_ITER
+#define DEVO_GRU_CHUNKS_PER_ITER 1
+#endif
 #ifndef DEVO_GRU_SPLIT
 #define DEVO_GRU_SPLIT 2
 #endif
@@ -377,7 +380,7 @@ struct Epi {
       if (EPI == EPI_STORE_B) orow = P.out16_b ? P.out16_b + (size_t)grow * kD : nullptr;
     }
     const int c0 = gcb0 * 4;                        // first global chunk of this thread
-    const uint32_t tcol = trow + lcb0 * 32;         // its first accumulator column
+    const uint32_t tcol = trow + (uint32_t)(l & 1) * kNC + lcb0 * 32;   // its first column of this layer's accumulator
     // per-row operands of the element-wise tail, fetched one chunk ahead of their use
     // RESID: q[0..1] net32 ; GATED: q[0..1] n32, q[2] gate ; ADD3: q[0] net16, q[1] inp16
     auto load_aux = [&](int c, uint4* q) {
@@ -394,19 +397,37 @@ struct Epi {
         if (live) { q[0] = *reinterpret_cast<const uint4*>(netrow + c * 8); q[1] = __ldg(reinterpret_cast<const uint4*>(inprow + c * 8)); }
       }
     };
-    uint4 cur[kAux], nxt[kAux];
-    if constexpr (kAux > 1) load_aux(c0, cur);           // issued before the accumulator is ready: overlaps the MMAs
-    mbar_wait(acc_full, (uint32_t)(l & 1));              // every CTA of the cluster is done reading its A tile
+    // kU chunks per loop iteration.  kU = 2 (two independent instruction streams per thread) was measured SLOWER:
+    // 168 registers with spills, gated layers 12 us instead of 8.8 us -- so one chunk per iteration it is.
+    constexpr int kU = DEVO_GRU_CHUNKS_PER_ITER;
+    static_assert(kIter % kU == 0, "chunks per iteration");
+    uint4 cur[kU][kAux], nxt[kU][kAux];
+    if constexpr (kAux > 1) {                            // issued before the accumulator is ready: overlaps the MMAs
+#pragma unroll
+      for (int u = 0; u < kU; u++) load_aux(c0 + u, cur[u]);
+    }
+    mbar_wait(&acc_full[l & 1], (uint32_t)((l >> 1) & 1));   // every CTA of the cluster is done reading its A tile
     tc_fence_after();
     if (et == 0) stamp(P.dbg, 6 + 4 * l);
     // (prefetching the next accumulator chunk as well was measured slower: 168 instead of 126 registers, +7 %)
 #pragma unroll 1
-    for (int i = 0; i < kIter; i++) {
-      const int c = c0 + i;                         // global 16-byte chunk index (8 columns)
-      uint32_t raw[8];
-      tmem_ld8(tcol + i * 8, raw);
-      if constexpr (kAux > 1) { if (i + 1 < kIter) load_aux(c + 1, nxt); }
+    for (int i0 = 0; i0 < kIter; i0 += kU) {
+      uint32_t rawu[kU][8];
+#pragma unroll
+      for (int u = 0; u < kU; u++) tmem_ld8(tcol + (i0 + u) * 8, rawu[u]);
+      if constexpr (kAux > 1) {
+        if (i0 + kU < kIter) {
+#pragma unroll
+          for (int u = 0; u < kU; u++) load_aux(c0 + i0 + kU + u, nxt[u]);
+        }
+      }
       tmem_wait_ld();
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+      const int i = i0 + u;
+      const int c = c0 + i;                         // global 16-byte chunk index (8 columns)
+      uint32_t (&raw)[8] = rawu[u];
+      uint4 (&cur_)[kAux] = cur[u];
       float o[8];
       {
         const float4 b0 = *reinterpret_cast<const float4*>(bias + c * 8), b1 = *reinterpret_cast<const float4*>(bias + c * 8 + 4);
@@ -430,8 +451,8 @@ struct Epi {
       } else if constexpr (EPI == EPI_ADD3_LN) {
         float a[8], b[8];
         unpack8<T>(oh, o);
-        unpack8<T>(cur[0], a);
-        unpack8<T>(cur[1], b);
+        unpack8<T>(cur_[0], a);
+        unpack8<T>(cur_[1], b);
 #pragma unroll
         for (int k = 0; k < 8; k++) a[k] += b[k];
         rnd8<T>(a);
@@ -444,7 +465,7 @@ struct Epi {
         *reinterpret_cast<uint4*>(As + a_off(r, c)) = vh;
       } else if constexpr (EPI == EPI_RESID) {
         unpack8<T>(oh, o);
-        float4 a = as_f4(cur[0]), b = as_f4(cur[1]);
+        float4 a = as_f4(cur_[0]), b = as_f4(cur_[1]);
         a.x += o[0]; a.y += o[1]; a.z += o[2]; a.w += o[3]; b.x += o[4]; b.y += o[5]; b.z += o[6]; b.w += o[7];
         *f4w(net_r, 2 * c) = a;
         *f4w(net_r, 2 * c + 1) = b;
@@ -456,7 +477,7 @@ struct Epi {
         // net += half Linear output (the SoftAgg `h` layer applied per edge: h(y)[:, gid] == h(y[:, gid]), row by row
         // bit-identical to the per-group product), then the sum becomes the next A operand (optionally after LayerNorm)
         unpack8<T>(oh, o);
-        const float4 a = as_f4(cur[0]), b = as_f4(cur[1]);
+        const float4 a = as_f4(cur_[0]), b = as_f4(cur_[1]);
         float x[8] = {a.x + o[0], a.y + o[1], a.z + o[2], a.w + o[3], b.x + o[4], b.y + o[5], b.z + o[6], b.w + o[7]};
         if constexpr (EPI == EPI_RESID_A) {
           *f4w(net_r, 2 * c) = make_float4(x[0], x[1], x[2], x[3]);      // own column slice only: nobody else reads it here
@@ -471,8 +492,8 @@ struct Epi {
       } else {   // EPI_GATED_LN / EPI_GATED_HEADS:  x = n + half(half(sigmoid(gate)) * res)
         float g[8];
         unpack8<T>(oh, o);
-        unpack8<T>(cur[2], g);
-        const float4 a = as_f4(cur[0]), b = as_f4(cur[1]);
+        unpack8<T>(cur_[2], g);
+        const float4 a = as_f4(cur_[0]), b = as_f4(cur_[1]);
         float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
         for (int k = 0; k < 8; k++) g[k] = sigmoidf_(g[k]);
@@ -502,9 +523,12 @@ struct Epi {
           }
         }
       }
+      }
       if constexpr (kAux > 1) {
 #pragma unroll
-        for (int k = 0; k < kAux; k++) cur[k] = nxt[k];
+        for (int u = 0; u < kU; u++)
+#pragma unroll
+          for (int k = 0; k < kAux; k++) cur[u][k] = nxt[u][k];
       }
     }
     if (et == 0 && l == 0) stamp(P.dbg, 40);
@@ -602,8 +626,8 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
   uint64_t* w_empty = w_full + kWStages;      // [kWStages]
   uint64_t* a_full = w_empty + kWStages;      // [kASlots]
   uint64_t* a_empty = a_full + kASlots;       // [kASlots]
-  uint64_t* acc_full = a_empty + kASlots;     // [1] count kSplit: the MMAs of a layer are done in EVERY CTA of the cluster
-  uint64_t* a_ready = acc_full + 1;           // [1] count kSplit: every CTA's epilogue has delivered its slice of the next A
+  uint64_t* acc_full = a_empty + kASlots;     // [2] (one per TMEM accumulator) count kSplit: the MMAs of a layer are done in EVERY CTA of the cluster
+  uint64_t* a_ready = acc_full + 2;           // [1] count kSplit: every CTA's epilogue has delivered its slice of the next A
   uint64_t* pro_ready = a_ready + 1;          // [1] local prologue finished
   uint64_t* stat_bar = pro_ready + 1;         // [1] count kSplit: LayerNorm / head partials of all CTAs have arrived
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);      // 32 barrier slots = 256 B; slot + pad = 16 B
@@ -625,7 +649,8 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWStages; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int s = 0; s < kASlots; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    mbar_init(acc_full, kSplit);
+    mbar_init(&acc_full[0], kSplit);
+    mbar_init(&acc_full[1], kSplit);
     mbar_init(a_ready, kSplit);
     mbar_init(pro_ready, 1);
     mbar_init(stat_bar, kSplit);
@@ -697,17 +722,27 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
     const uint64_t ad0 = umma_desc_sw128(smem_u32(As));
     const uint64_t bd0 = umma_desc_sw128(smem_u32(Ws));
     const uint16_t all = (uint16_t)((1u << kSplit) - 1u);
-    uint32_t stage = 0, phase = 0;
+    uint32_t stage = 0, phase = 0, waited = 0;
     for (int l = 0; l < P.n_layers; l++) {
       const int nkb = (l == 0) ? P.kblocks0 : kASlots;
       const bool streamed = (l == 0 && P.stream_a0);
+      // Two TMEM accumulators (layer l uses l & 1): when the previous epilogue does not rewrite the A tile (gate, g/f
+      // stores) this layer's MMAs run WHILE that epilogue still reads the other accumulator.  `waited` counts the
+      // epilogues (a_ready phases) consumed so far; phases are never skipped, only deferred.
       if (l == 0) {
         if (has_pro) { mbar_wait(pro_ready, 0u); fence_proxy_async(); tc_fence_after(); }
-      } else {                         // the A tile now holds every CTA's slice of the previous layer's output
-        mbar_wait_cluster(a_ready, (uint32_t)((l - 1) & 1));   // peers' DSMEM stores: acquire at cluster scope
+      } else {
+        const int pe = P.epi[l - 1];
+        const bool writes_a = (pe == EPI_RELU_A || pe == EPI_LNRELU_A || pe == EPI_GATED_LN || pe == EPI_RESID_A || pe == EPI_RESID_LN_A);
+        const int need = writes_a ? l - 1 : l - 2;     // last epilogue that must be complete: A operand / accumulator reuse
+        while ((int)waited <= need) {
+          mbar_wait_cluster(a_ready, waited & 1u);     // peers' DSMEM stores: acquire at cluster scope
+          waited++;
+        }
         fence_proxy_async();
         tc_fence_after();
       }
+      const uint32_t tacc = tmem_base + (uint32_t)(l & 1) * kNC;
       if (lane == 0) stamp(P.dbg, 4 + 4 * l);
       for (int kb = 0; kb < nkb; kb++) {
         const int slot = kb % kASlots;
@@ -718,13 +753,13 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
         const uint64_t bd = bd0 + (uint64_t)(stage * (kWStage >> 4));
 #pragma unroll
         for (int k4 = 0; k4 < 4; k4++)
-          tc_mma_f16_elect(tmem_base, ad + 2 * k4, bd + 2 * k4, idesc, (kb > 0 || k4 > 0) ? 1u : 0u);
+          tc_mma_f16_elect(tacc, ad + 2 * k4, bd + 2 * k4, idesc, (kb > 0 || k4 > 0) ? 1u : 0u);
         tc_commit_elect(smem_u32(&w_empty[stage]));
         if (++stage == kWStages) { stage = 0; phase ^= 1u; }
         if (streamed) tc_commit_elect(smem_u32(&a_empty[slot]));
       }
-      if (kSplit > 1) tc_commit_mc_elect(smem_u32(acc_full), all);
-      else tc_commit_elect(smem_u32(acc_full));
+      if (kSplit > 1) tc_commit_mc_elect(smem_u32(&acc_full[l & 1]), all);
+      else tc_commit_elect(smem_u32(&acc_full[l & 1]));
       if (lane == 0) stamp(P.dbg, 5 + 4 * l);
     }
     __syncwarp();
