@@ -39,13 +39,25 @@ class UpdateOperator:
         self.t0 = t0
         self.t1 = n_frames if t1 is None else t1
         dev, f32, i64 = self.device, torch.float32, torch.int64
-        self.poses = torch.zeros(1, self.Nf, 7, dtype=f32, device=dev)
+        # geometry + edge list live in ONE contiguous arena (256-byte aligned views), so that a host caller can refresh
+        # all of it with a single H2D copy of `state_arena` (layout: `state_layout`, name -> (offset, shape, dtype))
+        spec = [("poses", (1, self.Nf, 7), f32), ("patches", (1, self.Np, 3, 3, 3), f32), ("intrinsics", (1, self.Nf, 4), f32),
+                ("ii", (self.E,), i64), ("jj", (self.E,), i64), ("kk", (self.E,), i64)]
+        self.state_layout, off = {}, 0
+        for name, shape, dt in spec:
+            n = 1
+            for d in shape:
+                n *= d
+            self.state_layout[name] = (off, shape, dt)
+            off += (n * torch.empty((), dtype=dt).element_size() + 255) // 256 * 256
+        self.state_arena = torch.zeros(off, dtype=torch.uint8, device=dev)
+        for name, (o, shape, dt) in self.state_layout.items():
+            n = 1
+            for d in shape:
+                n *= d
+            nbytes = n * torch.empty((), dtype=dt).element_size()
+            setattr(self, name, self.state_arena[o:o + nbytes].view(dt).view(shape))
         self.poses[..., 6] = 1.0
-        self.patches = torch.zeros(1, self.Np, 3, 3, 3, dtype=f32, device=dev)
-        self.intrinsics = torch.zeros(1, self.Nf, 4, dtype=f32, device=dev)
-        self.ii = torch.zeros(self.E, dtype=i64, device=dev)
-        self.jj = torch.zeros(self.E, dtype=i64, device=dev)
-        self.kk = torch.zeros(self.E, dtype=i64, device=dev)
         self.pair_key = torch.zeros(self.E, dtype=i64, device=dev)
         self.net = torch.zeros(1, self.E, dim, dtype=feat_dtype, device=dev)
         self.imap = torch.zeros(1, self.Np, dim, dtype=feat_dtype, device=dev)
