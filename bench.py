@@ -241,7 +241,7 @@ def run_ours(args, rank, world, local_rank):
                     note="window gathers overlap ~6x: L2->SM bytes, not HBM bytes, bound this kernel (DESIGN.md)")
 
 
-    # ---- tensor roofline of the fused update operator (gru_mma_kernel x8: the largest share of a step), timed alone
+    # ---- tensor roofline of the fused update operator (gru_mma_kernel x6: the largest share of a step), timed alone
     roofline_gru = None
     if args.gru == "mma":
         with torch.no_grad():
@@ -267,7 +267,7 @@ def run_ours(args, rank, world, local_rank):
                 tpeak, tsrc = float(json.load(f)["bf16_tflops_sustained"]), "measured sustained bf16 (MEASURED_PEAKS.json)"
         except Exception:
             tpeak, tsrc = 1368.0, "fallback (B200_PROFILING.md)"
-        roofline_gru = dict(bound="tensor", kernel="gru_mma_kernel x8 + segment_softmax_sum x2 (devo_gru_update)",
+        roofline_gru = dict(bound="tensor", kernel="gru_mma_kernel x6 + segment_softmax_sum x2 (devo_gru_update)",
                             achieved=round(fl / (g_ms * 1e-3) / 1e12, 2), peak=tpeak, unit="TFLOP/s",
                             frac=round(fl / (g_ms * 1e-3) / 1e12 / tpeak, 4), traffic=None, flops=fl, kernel_ms=round(g_ms, 5),
                             peak_source=tsrc,
