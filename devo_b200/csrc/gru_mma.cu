@@ -15,7 +15,7 @@
 //                into the A tile for the next layer.  A LayerNorm sees a whole row inside one thread: no shuffles.
 //
 // Kernel boundaries remain only where rows of different tiles meet: the neighbour gathers (net[ix], net[jx]) and
-// the two SoftAgg segment reductions.  10 launches per update instead of ~60.
+// the two SoftAgg segment reductions.  8 launches per update (6 of this kernel + 2 segment reductions) instead of ~60.
 //
 // Rounding points follow torch.autocast exactly as devo_b200/update.py::forward_fused does (Linear outputs are
 // rounded to half, LayerNorm in float32, element-wise ops round to their promoted type); accumulation is fp32 in
@@ -63,7 +63,7 @@ constexpr int kCBc = kNC / 32;             // ... per CTA (4 / 6)
 constexpr int kCBp = kCBc / kEpiPer;       // ... per epilogue thread (2 / 3)
 static_assert(kD % kSplit == 0 && kNC % 32 == 0 && kCBc % kEpiPer == 0 && kNC % 16 == 0 && kNC <= 256, "bad split");
 
-enum { PRO_NONE = 0, PRO_GATHER = 1, PRO_CAST = 2, PRO_RESID = 3, PRO_RESID_LN = 4 };
+enum { PRO_NONE = 0, PRO_GATHER = 1, PRO_CAST = 2 };
 enum { EPI_RELU_A = 0, EPI_LNRELU_A = 1, EPI_ADD3_LN = 2, EPI_RESID = 3, EPI_STORE_A = 4, EPI_STORE_B = 5,
        EPI_GATE = 6, EPI_GATED_LN = 7, EPI_GATED_HEADS = 8, EPI_RESID_A = 9, EPI_RESID_LN_A = 10 };
 
@@ -81,10 +81,6 @@ struct GruProg {
   const T* x16_in;                         // row-major [src_rows,384]: gather source / hidden state in (ADD3)
   const int64_t* idx64;                    // PRO_GATHER: source row per row (-1 => zero row); null => identity
   const int32_t* idx32;                    // PRO_GATHER: ... or a 32-bit index (the group of each row) when idx64 is null
-  const int32_t* gid;                      // PRO_RESID*: group of each row ...
-  const T* y16;                            // ... and the [groups,384] values added through it
-  const int32_t* gid2;                     // PRO_RESID_LN: a second (group, values) pair added after the first
-  const T* y16b;
   const T* inp16;                          // ADD3: imap [n_patches,384]
   const int64_t* kk;                       // ADD3: patch of each row
   float* net32;                            // tile layout
@@ -268,87 +264,27 @@ struct Epi {
         }
       }
     } else {
-      // x = net32 (+ y16[gid] (+ y16b[gid2])): full rows, redundantly in every CTA of the cluster.  Nothing is written
-      // back here (a peer reads the same net32 columns concurrently): the additions are simply repeated, in the same
-      // order, by the next kernel that needs them -- bit-identical, and race-free.
-      constexpr bool resid = (PRO != PRO_CAST);
-      constexpr bool with_ln = (PRO == PRO_RESID_LN);
-      const T* yrow = (resid && live) ? P.y16 + (size_t)P.gid[grow] * kD : nullptr;
-      const T* yrow2 = (with_ln && live && P.gid2) ? P.y16b + (size_t)P.gid2[grow] * kD : nullptr;
+      // PRO_CAST: A = half(net32), full rows, redundantly in every CTA of the cluster (nothing is written back: a peer
+      // reads the same net32 columns concurrently)
       constexpr int kPcb = kCB / kEpiPer;
       const int pcb0 = part * kPcb;
-      float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
       for (int i = 0; i < kPcb; i++) {
         const int cb = pcb0 + i;
-        uint4 f[8], y[4], z[4];
+        uint4 f[8];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const int c = cb * 4 + j;
           f[2 * j] = *f4(net_r, 2 * c);
           f[2 * j + 1] = *f4(net_r, 2 * c + 1);
-          if (resid) { y[j] = make_uint4(0u, 0u, 0u, 0u); if (yrow) y[j] = *reinterpret_cast<const uint4*>(yrow + c * 8); }
-          if (with_ln) { z[j] = make_uint4(0u, 0u, 0u, 0u); if (yrow2) z[j] = *reinterpret_cast<const uint4*>(yrow2 + c * 8); }
         }
-        uint32_t st[32];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const int c = cb * 4 + j;
           const float4 a = as_f4(f[2 * j]), b = as_f4(f[2 * j + 1]);
-          float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-          if (resid) {
-            float t[8];
-            unpack8<T>(y[j], t);
-#pragma unroll
-            for (int k = 0; k < 8; k++) v[k] += t[k];
-          }
-          if (with_ln) {
-            float t[8];
-            unpack8<T>(z[j], t);
-#pragma unroll
-            for (int k = 0; k < 8; k++) { v[k] += t[k]; s1 += v[k]; s2 += v[k] * v[k]; st[j * 8 + k] = __float_as_uint(v[k]); }
-          } else {
-            *reinterpret_cast<uint4*>(As + a_off(r, c)) = pack8<T>(v);
-          }
+          const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+          *reinterpret_cast<uint4*>(As + a_off(r, c)) = pack8<T>(v);
         }
-        if (with_ln) tmem_st32(trow + cb * 32, st);      // park the fp32 row in TMEM (free until the first MMA)
-      }
-      if (with_ln) {     // n = LayerNorm(net) -> n32 (float, needed by the gated residual) and the A tile (half)
-        tmem_wait_st();
-        // row statistics over the full row: the kEpiPer threads of a row combine through shared memory (CTA-local)
-        s_stat[(part * kRows + r) * 2 + 0] = s1;
-        s_stat[(part * kRows + r) * 2 + 1] = s2;
-        epi_bar();
-        s1 = 0.f; s2 = 0.f;
-#pragma unroll
-        for (int p = 0; p < kEpiPer; p++) { s1 += s_stat[(p * kRows + r) * 2 + 0]; s2 += s_stat[(p * kRows + r) * 2 + 1]; }
-        epi_bar();
-        const float mean = s1 * (1.0f / kD);
-        const float rstd = rsqrtf(fmaxf(s2 * (1.0f / kD) - mean * mean, 0.f) + P.eps);
-        const float* gm = s_ln;
-        const float* bt = s_ln + kD;
-#pragma unroll 1
-        for (int i = 0; i < kPcb; i++) {
-          const int cb = pcb0 + i;
-          const bool mine = (cb / kCBc) == rank;
-          uint32_t raw[32];
-          tmem_ld32(trow + cb * 32, raw);
-          tmem_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const int c = cb * 4 + j;
-            float v[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) v[k] = (__uint_as_float(raw[j * 8 + k]) - mean) * rstd * gm[c * 8 + k] + bt[c * 8 + k];
-            if (mine) {
-              *f4w(n32_r, 2 * c) = make_float4(v[0], v[1], v[2], v[3]);
-              *f4w(n32_r, 2 * c + 1) = make_float4(v[4], v[5], v[6], v[7]);
-            }
-            *reinterpret_cast<uint4*>(As + a_off(r, c)) = pack8<T>(v);
-          }
-        }
-        tc_fence_before();
-        ln_used = 1;
       }
     }
     fence_proxy_async();
@@ -789,8 +725,6 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
     switch (P.pro) {                                // warp-uniform
       case PRO_GATHER: e.template prologue<PRO_GATHER>(); break;
       case PRO_CAST: e.template prologue<PRO_CAST>(); break;
-      case PRO_RESID: e.template prologue<PRO_RESID>(); break;
-      case PRO_RESID_LN: e.template prologue<PRO_RESID_LN>(); break;
       default: break;
     }
     if (e.et == 0) stamp(P.dbg, 2);
@@ -891,7 +825,7 @@ static int launch_prog(const CUtensorMap& tw, const CUtensorMap& tw0, const CUte
 
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 struct GruWs {
-  size_t net32, n32, gate16, x16a, x16b, g16, f16, y16, hy16, hy16b, total;
+  size_t net32, n32, gate16, x16a, x16b, g16, f16, y16, hy16, total;
 };
 static GruWs gru_ws(int E, int max_groups) {
   GruWs w;
@@ -907,7 +841,6 @@ static GruWs gru_ws(int E, int max_groups) {
   w.f16 = off;   off += al256((size_t)E * kD * 2);
   w.y16 = off;   off += al256(G * kD * 2);
   w.hy16 = off;  off += al256(G * kD * 2);
-  w.hy16b = off; off += al256(G * kD * 2);
   w.total = off;
   return w;
 }
@@ -927,7 +860,6 @@ static int gru_update_impl(const devo_gru_weights_t* Wt, const devo_gru_io_t* io
   T* f16 = (T*)(w + L.f16);
   T* y16 = (T*)(w + L.y16);
   T* hy16 = (T*)(w + L.hy16);
-  T* hy16b = (T*)(w + L.hy16b);
   const T* bias = (const T*)Wt->bias;            // [19,384]: row 0 = corr[0], row 1+i = stacked layer i
   auto B = [&](int layer) { return bias + (size_t)(1 + layer) * kD; };
   CUtensorMap tw, tw0, ta;

@@ -64,14 +64,19 @@ def pack_gmap(gmap, out=None):
 def _cached(t, fn):
     if not _USE_CACHE:
         return fn(t)
-    key = (t.data_ptr(), tuple(t.shape), t.dtype, t.device)
+    # The entry keeps the SOURCE tensor alive: while it is cached its memory cannot be handed to another tensor, so an
+    # equal (data_ptr, shape, dtype) can only be the same storage (views share the version counter).  Without that
+    # reference a new tensor allocated at a recycled address with the same shape and version hit a stale entry.
+    key = (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t.dtype, t.device)
     hit = _pack_cache.get(key)
     if hit is not None and hit[0] == t._version:
+        _pack_cache[key] = _pack_cache.pop(key)          # most recently used last
         return hit[1]
     out = fn(t)
-    if len(_pack_cache) > 16:
-        _pack_cache.clear()
-    _pack_cache[key] = (t._version, out)
+    _pack_cache.pop(key, None)
+    while len(_pack_cache) >= 8:
+        _pack_cache.pop(next(iter(_pack_cache)))         # evict the least recently used entry
+    _pack_cache[key] = (t._version, out, t)
     return out
 
 

@@ -164,3 +164,22 @@ def test_full_size_properties_s8():
             for l, s in enumerate((1, 4))]
     ref = torch.stack(refs, -1).reshape(64, -1)
     assert _rel(out[sel.cuda()], ref) <= 2e-3
+
+
+def test_pack_cache_is_not_fooled_by_recycled_addresses():
+    """the drop-in cuda_corr.forward caches the pixel-major copy of its inputs; a NEW tensor that the caching allocator
+    places at the address of a freed one (same shape, same version counter) must not hit the old entry"""
+    from devo_b200 import cuda_corr
+    P = corr_problem(n_frames=2, patches_per_frame=4, H4=24, W4=32, seed=5)
+    ii, jj = P["kk"].cuda(), P["jj"].cuda()
+    coords = P["coords"].cuda()
+    outs, ptrs = [], []
+    for rep in range(4):
+        g = torch.Generator(device="cuda").manual_seed(rep)
+        gmap = (torch.randn(P["gmap"].shape, device="cuda", generator=g) / 4).half()
+        fmap = (torch.randn(P["pyramid"][0].shape, device="cuda", generator=g) / 4).half()
+        ptrs.append(fmap.data_ptr())
+        (got,) = cuda_corr.forward(gmap, fmap, coords, ii, jj, 3)
+        ref = ocorr.corr_forward(gmap.cpu(), fmap.cpu(), coords.cpu(), P["kk"], P["jj"], 3)
+        assert (got.cpu().double() - ref.double()).abs().max().item() <= 2e-2, rep
+        del gmap, fmap, got
