@@ -30,10 +30,12 @@ class FrozenCast:
         self.dtype = dtype
         self._cache = {}
 
+    # Entries hold a reference to the parameter objects they were made from: id() of a dead object can be reused by a
+    # new one (same _version), which must not hit the old entry.
     def get(self, p):
         hit = self._cache.get(id(p))
-        if hit is None or hit[0] != p._version or hit[1].device != p.device:
-            hit = (p._version, p.detach().to(self.dtype))
+        if hit is None or hit[2] is not p or hit[0] != p._version or hit[1].device != p.device:
+            hit = (p._version, p.detach().to(self.dtype), p)
             self._cache[id(p)] = hit
         return hit[1]
 
@@ -42,8 +44,9 @@ class FrozenCast:
         key = tuple(id(p) for p in params)
         ver = tuple(p._version for p in params)
         hit = self._cache.get(key)
-        if hit is None or hit[0] != ver or hit[1].device != params[0].device:
-            hit = (ver, torch.cat([p.detach().to(self.dtype) for p in params], 0).contiguous())
+        if (hit is None or hit[0] != ver or hit[1].device != params[0].device
+                or any(a is not b for a, b in zip(hit[2], params))):
+            hit = (ver, torch.cat([p.detach().to(self.dtype) for p in params], 0).contiguous(), tuple(params))
             self._cache[key] = hit
         return hit[1]
 
@@ -51,10 +54,10 @@ class FrozenCast:
         """cached low-precision W^T with the input dimension zero-padded to k_padded: [k_padded, out]"""
         key = (id(w), "padT", k_padded)
         hit = self._cache.get(key)
-        if hit is None or hit[0] != w._version or hit[1].device != w.device:
+        if hit is None or hit[2] is not w or hit[0] != w._version or hit[1].device != w.device:
             wp = torch.zeros(w.shape[0], k_padded, dtype=self.dtype, device=w.device)
             wp[:, :w.shape[1]] = w.detach().to(self.dtype)
-            hit = (w._version, wp.t())
+            hit = (w._version, wp.t(), w)
             self._cache[key] = hit
         return hit[1]
 
