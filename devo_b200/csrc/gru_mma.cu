@@ -51,7 +51,7 @@ constexpr int kABlk = kRows * 128;         // one K-block of A: 128 rows x 64 ha
 constexpr int kASlots = kD / 64;           // 6
 constexpr int kWStage = kNC * 128;         // one K-block of this CTA's weight slice (16 / 24 KB)
 constexpr int kWStages = (96 * 1024) / kWStage;   // 6 / 4
-constexpr int kEpiPer = 2;                 // epilogue warps per TMEM lane quarter (each owns a share of the columns)
+constexpr int kEpiPer = 3;                 // epilogue warps per TMEM lane quarter (each owns a share of the columns)
 constexpr int kEpiThreads = 128 * kEpiPer;
 constexpr int kFirstEpiWarp = 2;            // warps 0 (TMA) and 1 (MMA) + the epilogue warps; any 4 consecutive warps cover the 4 TMEM lane quarters
 constexpr int kThreads = 32 * kFirstEpiWarp + kEpiThreads;
