@@ -222,7 +222,8 @@ __device__ __forceinline__ void tri_decode(int idx, int m, int& a, int& b) {
 // S positive definite  <=>  every pivot d_k = A_kk > 0 (same acceptance test as Cholesky).
 #ifdef DEVO_BA_TIMING
 __device__ long long g_ba_clk[16];
-#define BA_STAMP(i) do { if (threadIdx.x == 0) g_ba_clk[i] = clock64(); } while (0)
+__device__ __forceinline__ long long ba_now() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define BA_STAMP(i) do { if (threadIdx.x == 0) g_ba_clk[i] = ba_now(); } while (0)   /* ns, comparable across SMs */
 #else
 #define BA_STAMP(i)
 #endif
@@ -480,6 +481,7 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
   double* X = reinterpret_cast<double*>(smem_raw);
   double* coef = X + (size_t)RCAP * LD;
   double* zj = coef + RCAP;
+  unsigned int* rmask = reinterpret_cast<unsigned int*>(zj + RCAP);   // per row: which 6-column pose blocks are non-zero (bit 30: the residual column)
   __shared__ int s_batch[3];   // gs, ge, bad
   __shared__ float s_intr[4];
   __shared__ int s_gstart[kMaxGroupsPerCta + 1];
@@ -488,7 +490,7 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
   DEVO_PDL_WAIT();       // launched with programmatic stream serialisation: the previous iteration's results are needed from here on
   DEVO_PDL_TRIGGER();
 #ifdef DEVO_BA_TIMING
-  if (blockIdx.x == 0 && tid == 0) g_ba_clk[0] = clock64();
+  if (blockIdx.x == 0 && tid == 0) g_ba_clk[0] = ba_now();
 #endif
   const int st = *status;
   if (st != 0) {               // an earlier iteration failed: do nothing (reference would have thrown)
@@ -535,7 +537,7 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
 
   // entries owned by this thread
   double acc[EPT];
-  unsigned int ab[EPT];
+  unsigned int ab[EPT], need[EPT];
 #pragma unroll
   for (int q = 0; q < EPT; q++) {
     acc[q] = 0.0;
@@ -543,6 +545,8 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
     int a = 0, b = 0;
     if (idx < nent) tri_decode(idx, LD, a, b);
     ab[q] = ((unsigned)a << 16) | (unsigned)b;
+    // an edge row only touches the pose blocks of its two frames (12 of the 6N columns): entry (a,b) needs both blocks
+    need[q] = (idx < nent) ? ((1u << (a / 6)) | ((b == n6) ? (1u << 30) : (1u << (b / 6)))) : 0xffffffffu;
   }
 
   int gs = g0;
@@ -595,10 +599,14 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
         }
         coef[r] = on ? (double)T.w[rho] : 0.0;
         zj[r] = on ? (double)T.Jz[rho] : 0.0;
+        rmask[r] = (1u << 30) | (fi ? (1u << bi) : 0u) | (fj ? (1u << bj) : 0u);
       }
     }
     __syncthreads();
 
+#ifdef DEVO_BA_TIMING
+    if (blockIdx.x == 0 && tid == 0 && gs == g0) g_ba_clk[8] = ba_now();
+#endif
     // ---- per patch: C_k, u_k, Q_k and the dense vector E_k (one warp per patch, lanes over columns)
     {
       const int warp = tid >> 5, lane = tid & 31;
@@ -622,6 +630,7 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
         if (lane == 0) {
           erow[n6] = u;
           coef[2 * ne + gi] = -Q;
+          rmask[2 * ne + gi] = 0xffffffffu;               // E_k is dense
           Qg[g] = Q;
           Ug[g] = u;
         }
@@ -629,10 +638,32 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
     }
     __syncthreads();
 
+#ifdef DEVO_BA_TIMING
+    if (blockIdx.x == 0 && tid == 0 && gs == g0) g_ba_clk[9] = ba_now();
+#endif
     // ---- reduced-system partial: acc(a,b) += coef_r * X[r][a] * X[r][b]
-    for (int r = 0; r < R; r++) {
+    // An edge row only touches the pose blocks of its two frames, so most (row, entry) pairs are exact zeros: one
+    // block-mask test per EDGE (its two residual rows share the mask) decides whether an entry takes part at all.
+    // The loop is instruction-issue bound (measured 12 us for 136 rows with a test per row and entry), hence the
+    // pairing and the unrolling; the summation order (row index ascending) is unchanged => same bits as before.
+#pragma unroll 4
+    for (int e = 0; e < ne; e++) {
+      const double c0 = coef[2 * e], c1 = coef[2 * e + 1];
+      const unsigned int m = rmask[2 * e];
+      const double* row0 = X + (size_t)(2 * e) * LD;
+      const double* row1 = row0 + LD;
+#pragma unroll
+      for (int q = 0; q < EPT; q++) {
+        if ((m & need[q]) == need[q]) {
+          const int a = ab[q] >> 16, b = ab[q] & 0xffff;
+          if (c0 != 0.0) acc[q] += c0 * row0[a] * row0[b];
+          if (c1 != 0.0) acc[q] += c1 * row1[a] * row1[b];
+        }
+      }
+    }
+    for (int r = 2 * ne; r < R; r++) {                 // the dense per-patch rows E_k (coefficient -Q_k)
       const double c = coef[r];
-      if (c == 0.0) continue;            // block-uniform branch
+      if (c == 0.0) continue;
       const double* row = X + (size_t)r * LD;
 #pragma unroll
       for (int q = 0; q < EPT; q++) {
@@ -650,6 +681,9 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
     if (idx < nent) partials[(size_t)blockIdx.x * nent + idx] = acc[q];
   }
   (void)n_poses; (void)E;
+#ifdef DEVO_BA_TIMING
+  if (blockIdx.x == 0 && tid == 0) g_ba_clk[10] = ba_now();
+#endif
   // ---- hierarchical reduction + solve + retraction in the same launch (see kGroupCtas above)
   if (nfree > 0) {
     const int ngrp = ((int)gridDim.x + kGroupCtas - 1) / kGroupCtas;
@@ -661,6 +695,9 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
     __syncthreads();
     if (tid == 0) s_batch[0] = atomicAdd(&ticket[1 + grp], 1);
     __syncthreads();
+#ifdef DEVO_BA_TIMING
+    if (blockIdx.x == 0 && tid == 0) g_ba_clk[11] = ba_now();
+#endif
     if (s_batch[0] == gsize - 1) {                           // last CTA of its group
       if (tid == 0) ticket[1 + grp] = 0;                     // armed for the next launch
       __threadfence();
@@ -877,13 +914,13 @@ static int ba_forward_impl(float* poses, float* patches, const float* intrinsics
   }
 
   const int n6 = L.n6, LD = n6 + 1;
-  int rows_cap = (int)(kAccSmemBudget / ((size_t)(LD + 2) * 8));
+  int rows_cap = (int)(kAccSmemBudget / ((size_t)(LD + 3) * 8));
   int EB = rows_cap * 2 / 5;
   if (EB > kAccThreads) EB = kAccThreads;
   int GB = rows_cap - 2 * EB;
   if (GB > EB) GB = EB;
   DEVO_REQUIRE(EB >= 8 && GB >= 1, DEVO_ECAPACITY, "ba_forward: system too large for shared memory");
-  size_t smem_acc = (size_t)(2 * EB + GB) * (LD + 2) * 8;
+  size_t smem_acc = (size_t)(2 * EB + GB) * (LD + 3) * 8;
   const int ept = (L.nent + kAccThreads - 1) / kAccThreads;
 
 #define ACC(EPT_, APPLY, DOACC, ITR)                                                                         \
@@ -959,13 +996,13 @@ int devo_ba_sharded_accumulate(float* poses, float* patches, const float* intrin
     DEVO_CUDA(cudaMemsetAsync(w + L.ticket, 0, 4 * 32, s));
   }
   const int n6 = L.n6, LD = n6 + 1;
-  int rows_cap = (int)(kAccSmemBudget / ((size_t)(LD + 2) * 8));
+  int rows_cap = (int)(kAccSmemBudget / ((size_t)(LD + 3) * 8));
   int EB = rows_cap * 2 / 5;
   if (EB > kAccThreads) EB = kAccThreads;
   int GB = rows_cap - 2 * EB;
   if (GB > EB) GB = EB;
   DEVO_REQUIRE(EB >= 8 && GB >= 1, DEVO_ECAPACITY, "ba_sharded_accumulate: system too large for shared memory");
-  const size_t smem_acc = (size_t)(2 * EB + GB) * (LD + 2) * 8;
+  const size_t smem_acc = (size_t)(2 * EB + GB) * (LD + 3) * 8;
   const int ept = (L.nent + kAccThreads - 1) / kAccThreads;
   DEVO_REQUIRE(ept <= 24, DEVO_ECAPACITY, "ba_sharded_accumulate: system too large (%d entries)", L.nent);
 #define ACCS(EPT_)                                                                                                \
