@@ -569,17 +569,22 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
     const int ng = ge - gs;
     const int R = 2 * ne + ng;
 
+    // ---- one thread per edge: residual and Jacobians in registers (a chain of dependent global loads: perm -> ii/jj/kk
+    //      -> poses/patch), issued BEFORE the rows are zeroed so that the zeroing by all threads hides that latency
+    EdgeTerms T;
+    int bi = 0, bj = 0;
+    if (tid < ne) {
+      const int n = perm[ebase + tid];
+      const int i = (int)ii[n], j = (int)jj[n], k = (int)kk[n];
+      edge_terms(poses, patches, fx, fy, cx, cy, target, weight, i, j, k, n, PP, centre, T);
+      bi = i - t0; bj = j - t0;
+    }
     // zero the dense rows
     for (int q = tid; q < R * LD; q += kAccThreads) X[q] = 0.0;
     __syncthreads();
 
-    // ---- one thread per edge: Jacobians -> two dense rows
+    // ---- two dense rows per edge
     if (tid < ne) {
-      const int n = perm[ebase + tid];
-      const int i = (int)ii[n], j = (int)jj[n], k = (int)kk[n];
-      EdgeTerms T;
-      edge_terms(poses, patches, fx, fy, cx, cy, target, weight, i, j, k, n, PP, centre, T);
-      const int bi = i - t0, bj = j - t0;
       const bool fi = (bi >= 0 && bi < nfree), fj = (bj >= 0 && bj < nfree);
 #pragma unroll
       for (int rho = 0; rho < 2; rho++) {
