@@ -32,7 +32,7 @@ def _problem(nf, m, seed, dt=torch.float16):
     return up, net, imap, corr, ii, jj, kk, plan_kk, plan_ij, Np, nf * nf
 
 
-@pytest.mark.parametrize("nf,m,seed", [(8, 96, 0), (4, 24, 1), (3, 5, 2), (5, 31, 3)])
+@pytest.mark.parametrize("nf,m,seed", [(8, 96, 0), (4, 24, 1), (3, 5, 2), (5, 31, 3), (22, 96, 7)])   # last: S22, ragged, several waves of clusters
 def test_gru_mma_matches_cublas_path(nf, m, seed):
     from devo_b200.update import FrozenCast, PackedUpdateWeights
     up, net, imap, corr, ii, jj, kk, plan_kk, plan_ij, Np, pairs = _problem(nf, m, seed)
