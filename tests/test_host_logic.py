@@ -151,3 +151,39 @@ def test_scatter_and_shims():
     assert cuda_corr.forward is devo_b200.cuda_corr.forward and hasattr(cuda_ba, "neighbors") and hasattr(torch_scatter, "scatter_softmax")
     for n in ("cuda_ba", "cuda_corr", "lietorch_backends", "torch_scatter"):
         sys.modules.pop(n, None)
+
+
+def test_packed_update_weights_layout_matches_header_order():
+    """host logic of the fused update operator: the parameter pack handed to devo_gru_update (include/devo_b200.h,
+    devo_gru_weights_t) -- stacking order, zero padding of corr[0], refresh on parameter change.  CPU tensors suffice."""
+    import torch
+    from devo_b200.update import PackedUpdateWeights, Update
+    torch.manual_seed(0)
+    up = Update(3)
+    pk = PackedUpdateWeights(up, torch.float16, 896)
+    order = [up.corr[2], up.corr[5], up.c1[0], up.c1[2], up.c2[0], up.c2[2], up.agg_kk.g, up.agg_kk.f, up.agg_kk.h,
+             up.agg_ij.g, up.agg_ij.f, up.agg_ij.h, up.gru[1].gate[0], up.gru[1].res[0], up.gru[1].res[2],
+             up.gru[3].gate[0], up.gru[3].res[0], up.gru[3].res[2]]
+    assert pk.W.shape == (18 * 384, 384) and pk.bias.shape == (19, 384) and pk.W0.shape == (384, 896)
+    for k, layer in enumerate(order):
+        assert torch.equal(pk.W[k * 384:(k + 1) * 384], layer.weight.detach().half())
+        assert torch.equal(pk.bias[1 + k], layer.bias.detach().half())
+    assert torch.equal(pk.bias[0], up.corr[0].bias.detach().half())
+    assert torch.equal(pk.W0[:, :882], up.corr[0].weight.detach().half()) and (pk.W0[:, 882:] == 0).all()
+    assert torch.equal(pk.ln_gamma[1], up.norm.weight.detach()) and torch.equal(pk.ln_beta[3], up.gru[2].bias.detach())
+    assert torch.equal(pk.head_W[:2], up.d[1].weight.detach().half()) and torch.equal(pk.head_W[2:], up.w[1].weight.detach().half())
+    w_ptr = pk.W.data_ptr()
+    pk.refresh()
+    assert pk.W.data_ptr() == w_ptr                          # nothing changed: no repacking
+    with torch.no_grad():
+        up.c1[0].weight.mul_(2.0)
+    pk.refresh()
+    assert torch.equal(pk.W[2 * 384:3 * 384], up.c1[0].weight.detach().half())
+
+
+def test_patch_range_and_gru_flops_helpers():
+    from devo_b200 import synthetic
+    from devo_b200.dist import patch_range
+    assert [patch_range(10, r, 3) for r in range(3)] == [(0, 4), (4, 7), (7, 10)]
+    # S8: 6144 edges x (896 + 16*384) + (768 + 64) group rows x 384, all x 2*384
+    assert synthetic.gru_flops(6144, 768, 64, 384, 896) == 2 * 6144 * 384 * (896 + 16 * 384) + 2 * (768 + 64) * 384 * 384
