@@ -61,6 +61,8 @@ constexpr int kCol4 = kD / 4;              // float4 groups per row (96)
 constexpr int kCB = kD / 32;               // 32-column blocks per row (12)
 constexpr int kCBc = kNC / 32;             // ... per CTA (4 / 6)
 constexpr int kCBp = kCBc / kEpiPer;       // ... per epilogue thread (2 / 3)
+constexpr int kStageStride = kNC / 8 + 1;  // output staging tile: 16-byte chunks per row (+1: bank-conflict padding)
+constexpr int kStageBytes = kRows * kStageStride * 16;
 static_assert(kD % kSplit == 0 && kNC % 32 == 0 && kCBc % kEpiPer == 0 && kNC % 16 == 0 && kNC <= 256, "bad split");
 
 enum { PRO_NONE = 0, PRO_GATHER = 1, PRO_CAST = 2 };
@@ -166,6 +168,7 @@ template <typename T>
 struct Epi {
   const GruProg<T>& P;
   unsigned char* As;
+  unsigned char* Ws;           // the weight ring: idle during the LAST layer's epilogue, reused as an output staging tile
   float* s_stat; float* s_hacc; const float* s_ln; const float* s_bias; const T* s_head; int* s_idx;
   uint64_t* acc_full; uint64_t* a_ready; uint64_t* pro_ready; uint64_t* stat_bar;
   int rank, tile, row0, quarter, part, et, r, grow;
@@ -311,10 +314,20 @@ struct Epi {
       inprow = P.inp16 + (size_t)P.kk[grow] * kD;
     }
     T* orow = nullptr;
-    if (live) {
-      if (EPI == EPI_STORE_A || EPI == EPI_RESID || EPI == EPI_GATED_HEADS || EPI == EPI_ADD3_LN) orow = P.out16_a ? P.out16_a + (size_t)grow * kD : nullptr;
-      if (EPI == EPI_STORE_B) orow = P.out16_b ? P.out16_b + (size_t)grow * kD : nullptr;
-    }
+    T* obase = nullptr;
+    if (EPI == EPI_STORE_A || EPI == EPI_RESID || EPI == EPI_GATED_HEADS || EPI == EPI_ADD3_LN) obase = P.out16_a;
+    if (EPI == EPI_STORE_B) obase = P.out16_b;
+    if (live && obase) orow = obase + (size_t)grow * kD;
+    // Row-major [rows,384] outputs: one thread per row means a warp's 16-byte stores hit 32 different rows (32 sectors
+    // per instruction, ~1.5 us per layer).  In the LAST layer of a launch the weight ring is idle (every stage has been
+    // consumed), so the slice is staged there ([128 rows][kNC/8 + 1 chunks], padded against bank conflicts) and copied
+    // out with fully coalesced stores after the loop.
+    const bool staged = (obase != nullptr) && (l + 1 == P.n_layers) && (kStageBytes <= kWStages * kWStage);
+    uint4* stage = reinterpret_cast<uint4*>(Ws);
+    auto out_store = [&](int c, uint4 v) {          // c: global 16-byte chunk index
+      if (staged) stage[r * kStageStride + (c - rank * (kNC / 8))] = v;
+      else if (orow) *reinterpret_cast<uint4*>(orow + c * 8) = v;
+    };
     const int c0 = gcb0 * 4;                        // first global chunk of this thread
     const uint32_t tcol = trow + (uint32_t)(l & 1) * kNC + lcb0 * 32;   // its first column of this layer's accumulator
     // per-row operands of the element-wise tail, fetched one chunk ahead of their use
@@ -376,7 +389,7 @@ struct Epi {
       if constexpr (EPI == EPI_RELU_A) {
         a_store_all(c, relu8<T>(oh));               // max(.,0) commutes with the rounding: done on packed halves
       } else if constexpr (EPI == EPI_STORE_A || EPI == EPI_STORE_B) {
-        if (orow) *reinterpret_cast<uint4*>(orow + c * 8) = oh;
+        out_store(c, oh);
       } else if constexpr (EPI == EPI_GATE) {
         *reinterpret_cast<uint4*>(gate_r + (size_t)c * (kRows * 8)) = oh;
       } else if constexpr (EPI == EPI_LNRELU_A) {
@@ -405,9 +418,9 @@ struct Epi {
         a.x += o[0]; a.y += o[1]; a.z += o[2]; a.w += o[3]; b.x += o[4]; b.y += o[5]; b.z += o[6]; b.w += o[7];
         *f4w(net_r, 2 * c) = a;
         *f4w(net_r, 2 * c + 1) = b;
-        if (orow) {
+        if (obase) {
           const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-          *reinterpret_cast<uint4*>(orow + c * 8) = pack8<T>(v);
+          out_store(c, pack8<T>(v));
         }
       } else if constexpr (EPI == EPI_RESID_A || EPI == EPI_RESID_LN_A) {
         // net += half Linear output (the SoftAgg `h` layer applied per edge: h(y)[:, gid] == h(y[:, gid]), row by row
@@ -446,7 +459,7 @@ struct Epi {
           for (int k = 0; k < 8; k++) { s1 += x[k]; s2 += x[k] * x[k]; xs[k] = __float_as_uint(x[k]); }
           tmem_st8(tcol + i * 8, xs);               // fp32 row parked in its own accumulator columns
         } else {
-          if (orow) *reinterpret_cast<uint4*>(orow + c * 8) = pack8<T>(x);         // new hidden state (half)
+          out_store(c, pack8<T>(x));                  // new hidden state (half)
           float hw[8];
 #pragma unroll
           for (int k = 0; k < 8; k++) x[k] = fmaxf(x[k], 0.f);
@@ -489,7 +502,7 @@ struct Epi {
         } else {
           *f4w(net_r, 2 * c) = make_float4(v[0], v[1], v[2], v[3]);
           *f4w(net_r, 2 * c + 1) = make_float4(v[4], v[5], v[6], v[7]);
-          if (orow) *reinterpret_cast<uint4*>(orow + c * 8) = pack8<T>(v);
+          out_store(c, pack8<T>(v));
         }
       }
       ln_used++;
@@ -533,6 +546,15 @@ struct Epi {
           *reinterpret_cast<float2*>(P.target32 + (size_t)grow * 2) = make_float2(cr[4] + df.x, cr[13] + df.y);
           *reinterpret_cast<float2*>(P.weight32 + (size_t)grow * 2) = wf;
         }
+      }
+    }
+    if (staged) {                                   // coalesced copy-out of the staged slice (kNC/8 chunks per row)
+      epi_bar();
+      constexpr int kCpr = kNC / 8;
+      T* dst = obase + (size_t)row0 * kD + rank * kNC;
+      for (int q = et; q < kRows * kCpr; q += kEpiThreads) {
+        const int rr = q / kCpr, ch = q - rr * kCpr;
+        if (row0 + rr < P.rows) *reinterpret_cast<uint4*>(dst + (size_t)rr * kD + ch * 8) = stage[rr * kStageStride + ch];
       }
     }
     tc_fence_before();
@@ -702,7 +724,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
   } else if (warp >= kFirstEpiWarp) {
     // =========================== prologue + epilogues (struct Epi) =============================================
     Epi<T> e(P);
-    e.As = As; e.s_stat = s_stat; e.s_hacc = s_hacc; e.s_ln = s_ln; e.s_bias = s_bias; e.s_head = s_head; e.s_idx = s_idx;
+    e.As = As; e.Ws = Ws; e.s_stat = s_stat; e.s_hacc = s_hacc; e.s_ln = s_ln; e.s_bias = s_bias; e.s_head = s_head; e.s_idx = s_idx;
     e.acc_full = acc_full; e.a_ready = a_ready; e.pro_ready = pro_ready; e.stat_bar = stat_bar;
     e.rank = rank; e.tile = tile; e.row0 = row0;
     e.quarter = warp & 3;

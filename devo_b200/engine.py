@@ -157,7 +157,7 @@ class UpdateOperator:
         cuda_ba.forward_async(self.poses, self.patches, self.intrinsics, target, weight, self.lmbda,
                               self.ii, self.jj, self.kk, self.t0, self.t1, self.ba_iterations, status=self.status,
                               plan=self.plan_kk, workspace=self._ba_ws)
-        torch.maximum(self.status_sticky, self.status.abs(), out=self.status_sticky)
+        torch.bitwise_or(self.status_sticky, self.status, out=self.status_sticky)     # non-zero once any iteration failed (one launch)
         self.coords, self.delta, self.weight = coords, delta, weight
 
     @torch.no_grad()
