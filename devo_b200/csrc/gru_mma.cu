@@ -156,7 +156,14 @@ __device__ __forceinline__ void stamp(long long* dbg, int slot) {
     dbg[slot] = t;
   }
 }
-__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// sigmoid in 4 instructions (FMUL, MUFU.EX2, FADD, MUFU.RCP): the .ftz forms skip the denormal range fix-ups of
+// __expf / __fdividef; the result is rounded to half right away, far coarser than the approximation error
+__device__ __forceinline__ float sigmoidf_(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
 
 // the epilogue threads only
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }

@@ -37,3 +37,10 @@ def test_sm100a_cubin_with_blackwell_instructions():
     assert "sm_100a" in out
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
         assert mnemonic in out, mnemonic
+    # the fused update operator: tcgen05 MMA, TMEM load AND store, TMA, cluster barrier, tcgen05.commit
+    i = out.find("gru_mma_kernel")
+    assert i >= 0
+    j = out.find("Function :", i + 10)
+    gru = out[i:j if j > 0 else len(out)]
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "STTM", "UCGABAR_ARV", "UTCBAR"):
+        assert mnemonic in gru, mnemonic
