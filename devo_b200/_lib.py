@@ -39,6 +39,7 @@ SIGNATURES = {
     "devo_ba_system_doubles": (_sz, [_i]),
     "devo_ba_sharded_accumulate": (_i, [_vp] * 9 + [_i] * 8 + [_vp, _vp, _sz, _vp, _vp]),
     "devo_ba_sharded_solve": (_i, [_vp, _vp] + [_i] * 5 + [_vp, _sz, _vp, _vp]),
+    "devo_ba_sharded_solve_peer": (_i, [_vp, _vp, _i, _i, _c.c_uint64] + [_i] * 5 + [_vp, _sz, _vp, _vp]),
     "devo_reproject": (_i, [_vp] * 7 + [_i, _i, _vp]),
     "devo_transform_forward": (_i, [_vp] * 11 + [_i] * 4 + [_vp]),
     "devo_glue_layernorm": (_i, [_i, _i] + [_vp] * 6 + [_c.c_float, _vp, _vp, _i, _i, _vp]),

@@ -753,6 +753,67 @@ __global__ void __launch_bounds__(kSolveThreads, 1) ba_solve_kernel(float* poses
   ba_solve_device<KENT>(smem_raw, poses, sys, dX, status, 1, t0, nfree, itr);
 }
 
+// ---- the same solve with the all-reduce FUSED in, over NVLink peer memory ----------------------------------------------
+// Every rank keeps its partial system in a symmetric (peer-mapped) buffer: [2][nsys] doubles (double-buffered by
+// iteration parity) + one 64-bit epoch flag per parity.  The kernel publishes this rank's flag, waits until every
+// peer's flag has reached the epoch (ld.acquire.sys over NVLink), adds the partial systems IN RANK ORDER with peer
+// loads (so every rank forms bitwise the same sum), and solves -- no NCCL launch, no separate reduction kernel.
+// Double buffering is enough: a rank can only reach iteration k+2 after every peer has published k+1, i.e. after it
+// finished reading iteration k.  A peer that never arrives trips a time-out (status DEVO_ECAPACITY) instead of a hang.
+template <int KENT>
+__global__ void __launch_bounds__(kSolveThreads, 1) ba_solve_peer_kernel(
+    float* poses, const unsigned long long* __restrict__ peer_ptrs, int world, int rank, unsigned long long epoch,
+    int parity, size_t nsys, double* sum_buf, double* dX, int32_t* status, int t0, int nfree, int itr) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_timeout;
+  const int tid = threadIdx.x;
+  const int n6 = 6 * nfree;
+  const int nent = (n6 + 1) * (n6 + 2) / 2;
+  if (tid == 0) s_timeout = 0;
+  __syncthreads();
+  if (tid == 0) {                          // this rank's partial (written by the previous kernel of the stream) is complete
+    unsigned long long* my_flag = reinterpret_cast<unsigned long long*>(peer_ptrs[rank]) + 2 * nsys + parity;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(my_flag), "l"(epoch) : "memory");
+  }
+  if (tid < world) {
+    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(peer_ptrs[tid]) + 2 * nsys + parity;
+    long long t_start;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+    unsigned long long v = 0;
+    while (true) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+      if (v >= epoch) break;
+      long long t_now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+      if (t_now - t_start > 2000000000LL) { s_timeout = 1; break; }       // 2 s: a peer is gone
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  if (s_timeout) {
+    if (tid == 0) atomicCAS(status, 0, DEVO_ECAPACITY);
+    return;
+  }
+  for (int idx = tid; idx <= nent; idx += kSolveThreads) {                // rank order => identical bits on every rank
+    double acc = 0.0;
+    for (int p = 0; p < world; p++) {
+      const double* src = reinterpret_cast<const double*>(peer_ptrs[p]) + (size_t)parity * nsys;
+      double v;
+      asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(src + idx) : "memory");
+      acc += v;
+    }
+    sum_buf[idx] = acc;
+  }
+  __threadfence();
+  __syncthreads();
+  if (sum_buf[nent] != 0.0) {              // some rank failed in accumulate: every rank stops here, identically
+    if (tid == 0) atomicCAS(status, 0, DEVO_ECAPACITY);
+    return;
+  }
+  ba_solve_device<KENT>(smem_raw, poses, sum_buf, dX, status, 1, t0, nfree, itr);
+}
+
 }  // namespace
 
 namespace {
@@ -1051,6 +1112,42 @@ int devo_ba_sharded_solve(float* poses, const double* sys, int E, int n_poses, i
   else SOLVE((((kMaxN6 + 1) * (kMaxN6 + 2) / 2) + kSolveThreads - 1) / kSolveThreads);
 #undef SOLVE
   DEVO_LAUNCH_CHECK("ba_sharded_solve");
+  return DEVO_OK;
+}
+
+int devo_ba_sharded_solve_peer(float* poses, const void* peer_ptrs_dev, int world, int rank, uint64_t epoch, int E,
+                               int n_poses, int t0, int t1, int itr, void* workspace, size_t workspace_bytes,
+                               int32_t* status, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nfree = t1 - t0;
+  DEVO_REQUIRE(status != nullptr && peer_ptrs_dev != nullptr, DEVO_EINVAL, "ba_sharded_solve_peer: NULL pointer");
+  DEVO_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world, DEVO_EINVAL, "ba_sharded_solve_peer: bad rank/world");
+  DEVO_REQUIRE(nfree > 0 && 6 * nfree <= kMaxN6, DEVO_ECAPACITY, "ba_sharded_solve_peer: %d free poses unsupported", nfree);
+  DEVO_REQUIRE(t0 >= 0 && t1 <= n_poses, DEVO_EINVAL, "ba_sharded_solve_peer: pose window [%d,%d) outside [0,%d)", t0, t1, n_poses);
+  BaLayout L = ba_layout(E, nfree);
+  DEVO_REQUIRE(workspace && workspace_bytes >= L.total, DEVO_EWORKSPACE,
+               "ba_sharded_solve_peer: workspace too small (%zu < %zu)", workspace_bytes, L.total);
+  const int n6 = 6 * nfree;
+  const size_t nsys = devo_ba_system_doubles(nfree);
+  const size_t smem = ((size_t)n6 * (n6 + 1) / 2 + (n6 + 1) + 18 * (n6 + 1) + 8) * 8;
+  double* dX = (double*)((char*)workspace + L.dX);
+  double* sum_buf = (double*)((char*)workspace + L.partials);   // the per-CTA partials are dead once the system is exported
+  const int parity = (int)(epoch & 1);
+#define SOLVEP(K_)                                                                                              \
+  do {                                                                                                          \
+    static size_t configured = 0;                                                                               \
+    if (smem > configured) {                                                                                    \
+      DEVO_CUDA(cudaFuncSetAttribute(ba_solve_peer_kernel<K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      configured = smem;                                                                                        \
+    }                                                                                                           \
+    ba_solve_peer_kernel<K_><<<1, kSolveThreads, smem, s>>>(poses, (const unsigned long long*)peer_ptrs_dev, world, rank, \
+                                                            (unsigned long long)epoch, parity, nsys, sum_buf, dX, status, t0, nfree, itr); \
+  } while (0)
+  if (n6 <= 44) SOLVEP(2);
+  else if (n6 <= 88) SOLVEP(8);
+  else SOLVEP((((kMaxN6 + 1) * (kMaxN6 + 2) / 2) + kSolveThreads - 1) / kSolveThreads);
+#undef SOLVEP
+  DEVO_LAUNCH_CHECK("ba_sharded_solve_peer");
   return DEVO_OK;
 }
 

@@ -135,9 +135,40 @@ class ShardedBA:
     def finish(self, iterations):
         self._acc(iterations, 1)
 
+    # ---- all-reduce fused into the solve over NVLink peer memory (no NCCL call on the data path) --------------------
+    def enable_peer(self, group=None):
+        """Put the partial system into torch symmetric memory (peer-mapped on every rank of `group`): [2][nsys] doubles,
+        double-buffered by iteration parity, + two 64-bit epoch flags.  Collective: every rank must call it."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        nsys = _lib.lib().devo_ba_system_doubles(self.t1 - self.t0)
+        dev = self.poses.device
+        self._nsys = nsys
+        self._sym = symm_mem.empty(2 * nsys + 2, dtype=torch.float64, device=dev)
+        self._sym.zero_()
+        self._hdl = symm_mem.rendezvous(self._sym, group if group is not None else dist.group.WORLD)
+        self._epoch = 0
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)                      # every buffer is zeroed (flags = 0) before anybody polls a peer
+        return self
+
+    def accumulate_peer(self, itr):
+        self._epoch += 1
+        par = self._epoch & 1
+        self.system = self._sym[par * self._nsys:(par + 1) * self._nsys]
+        return self.accumulate(itr)
+
+    def solve_peer(self, itr):
+        """flag handshake + rank-ordered peer reduction + solve in ONE kernel (devo_ba_sharded_solve_peer)"""
+        h = self._hdl
+        _lib.check(_lib.lib().devo_ba_sharded_solve_peer(
+            self.poses.data_ptr(), int(h.buffer_ptrs_dev), int(h.world_size), int(h.rank), int(self._epoch), self.E,
+            self.n_poses, self.t0, self.t1, int(itr), self._ws.data_ptr(), self._ws.numel(), self.status.data_ptr(),
+            _lib.stream_ptr(self.poses.device)), "ba_sharded_solve_peer")
+
 
 def forward_sharded(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, t0, t1, iterations, group=None,
-                    status=None):
+                    status=None, peer=False):
     """fastba.BA for ONE frame graph split over the ranks of `group` (north_star: "a single NCCL all-reduce of the
     pose-block Hessian"): see ShardedBA.  The all-reduce runs on NCCL over NVLink (fp64 sum, 7.2 KB at 7 free poses);
     poses stay bitwise replicated; only the depths of the local patches change (dist.gather_patch_depths exchanges
@@ -147,6 +178,16 @@ def forward_sharded(poses, patches, intrinsics, target, weight, lmbda, ii, jj, k
         return forward_async(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, t0, t1, iterations, status=status)
     ba = ShardedBA(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, t0, t1, status=status)
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if peer and multi:          # peer=True: no NCCL on the data path -- the reduction happens inside the solve kernel
+        ba.enable_peer(group)
+        for itr in range(int(iterations)):
+            ba.accumulate_peer(itr)
+            ba.solve_peer(itr)
+        if iterations > 0:
+            ba.finish(int(iterations))
+        torch.cuda.synchronize(ba.poses.device)
+        dist.barrier(group)     # the symmetric buffer is released below: no peer may still be reading it
+        return ba.status
     for itr in range(int(iterations)):
         ba.accumulate(itr)
         if multi:

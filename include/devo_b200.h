@@ -145,6 +145,14 @@ int devo_ba_sharded_accumulate(float* poses, float* patches, const float* intrin
                                double* sys_out, void* workspace, size_t workspace_bytes, int32_t* status, void* stream);
 int devo_ba_sharded_solve(float* poses, const double* sys, int E, int n_poses, int t0, int t1, int itr,
                           void* workspace, size_t workspace_bytes, int32_t* status, void* stream);
+/* The same solve with the all-reduce fused in over NVLink peer memory (no NCCL call): every rank's partial lives in a
+ * symmetric, peer-mapped buffer laid out as [2][devo_ba_system_doubles()] doubles + 2 u64 epoch flags (double-buffered by
+ * the parity of `epoch`, which the caller increments once per Gauss-Newton iteration, starting at 1, in lockstep on all
+ * ranks).  devo_ba_sharded_accumulate must have written sys_out = own buffer + (epoch & 1) * nsys.  peer_ptrs_dev: device
+ * array of `world` u64 device pointers to the ranks' buffers (e.g. torch symmetric memory `buffer_ptrs_dev`). */
+int devo_ba_sharded_solve_peer(float* poses, const void* peer_ptrs_dev, int world, int rank, uint64_t epoch, int E,
+                               int n_poses, int t0, int t1, int itr, void* workspace, size_t workspace_bytes,
+                               int32_t* status, void* stream);
 /* cuda_ba.reproject (devo/fastba/ba.cpp:155, ba_cuda.cu:368-418,543-575) -> coords [E,2,P,P] f32 */
 int devo_reproject(const float* poses, const float* patches, const float* intrinsics,
                    const int64_t* ii, const int64_t* jj, const int64_t* kk, float* coords,

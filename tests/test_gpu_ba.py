@@ -377,7 +377,7 @@ def test_sharded_ba_failure_is_seen_by_every_rank():
         assert torch.equal(I["poses"].cpu(), P["poses0"].float())               # nothing applied
 
 
-def _nccl_worker(rank, world, port, q):
+def _nccl_worker(rank, world, port, q, peer=False):
     import os
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import torch.distributed as dist
@@ -387,7 +387,7 @@ def _nccl_worker(rank, world, port, q):
     P = ba_problem(n_frames=8, patches_per_frame=96, seed=85, init="perturbed", noise=0.3)
     I = _sharded_inputs(P, rank, world, torch.device("cuda", rank))
     st = cuda_ba.forward_sharded(I["poses"], I["patches"], I["intr"], I["target"], I["weight"], torch.tensor([1e-4], device=I["poses"].device),
-                                 I["ii"], I["jj"], I["kk"], 1, 8, 2)
+                                 I["ii"], I["jj"], I["kk"], 1, 8, 2, peer=peer)
     d.gather_patch_depths(I["patches"], 8 * 96)
     torch.cuda.synchronize()
     q.put((rank, int(st.item()), I["poses"].cpu(), I["patches"].cpu()))
@@ -405,6 +405,31 @@ def test_sharded_ba_two_gpus_nccl():
     q = ctx.Queue()
     port = 29600 + (os.getpid() % 300)
     ps = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    out = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
+    for p in ps:
+        p.join(120)
+        assert p.exitcode == 0
+    P = ba_problem(n_frames=8, patches_per_frame=96, seed=85, init="perturbed", noise=0.3)
+    ref_poses, ref_patches = _run_ba(P, 1, 8, 2)
+    assert out[0][1] == 0 and out[1][1] == 0
+    assert torch.equal(out[0][2], out[1][2]) and torch.equal(out[0][3], out[1][3])     # replicas agree bitwise
+    assert (out[0][2] - ref_poses.cpu()).abs().max().item() <= 1e-6
+    assert (out[0][3] - ref_patches.cpu()).abs().max().item() <= 1e-6
+
+
+def test_sharded_ba_two_gpus_peer_memory():
+    """the all-reduce fused into the solve kernel over NVLink peer memory (torch symmetric memory; no NCCL call on the
+    data path): same result as the NCCL form and as a single GPU, replicas bitwise identical"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import os
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 250)
+    ps = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q, True)) for r in range(2)]
     for p in ps:
         p.start()
     out = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
