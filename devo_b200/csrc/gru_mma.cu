@@ -2,20 +2,30 @@
 // handful of fused tensor-core kernels.
 //
 // Reference: ~17 cuBLAS GEMMs of [E,384]x[384,384] plus ~40 ATen element-wise launches per iteration; every
-// intermediate [E,384] tensor makes a round trip through HBM/L2.  Here one CTA owns a tile of 128 edges and
-// walks it through a whole CHAIN of layers without leaving the SM:
+// intermediate [E,384] tensor makes a round trip through HBM/L2.  Here a CLUSTER OF 2 CTAs owns a tile of 128 edges and
+// walks it through a whole CHAIN of layers without leaving the two SMs; each CTA computes 192 of the 384 output columns:
 //
-//   A operand  : the tile's activations, [128 rows x 384] f16 in shared memory (6 K-blocks of 128 x 64, the
-//                UMMA K-major SWIZZLE_128B canonical layout), written by the epilogue of the previous layer
-//   B operand  : the layer's weights W[384 out, K in] (K-major as stored by nn.Linear), streamed from L2 by TMA in
-//                [192 x 64] boxes through a 5-stage mbarrier ring (the producer warp runs ahead across layers)
-//   accumulator: [128 x 384] f32 in TMEM (two N=192 halves), tcgen05.mma issued by one elected lane of warp 1
-//   epilogue   : 4 warps, one thread per row: tcgen05.ld 32 columns at a time, bias, then the layer's element-wise
-//                tail (ReLU / LayerNorm / residual / gate / heads) in registers, and the result goes straight back
-//                into the A tile for the next layer.  A LayerNorm sees a whole row inside one thread: no shuffles.
+//   A operand  : the tile's activations, [128 rows x 384] f16 in shared memory of BOTH CTAs (6 K-blocks of 128 x 64,
+//                the UMMA K-major SWIZZLE_128B canonical layout); the epilogue of layer l writes the next A operand
+//                in place -- its own column slice locally, the peer's copy through distributed shared memory
+//   B operand  : this CTA's slice of the layer's weights W[384 out, K in] (K-major as stored by nn.Linear), streamed
+//                from L2 by TMA in [192 x 64] boxes through a 4-stage mbarrier ring (the producer warp runs ahead
+//                across layers: weights do not depend on activations)
+//   accumulator: two [128 x 192] f32 tiles in TMEM (layer l uses l & 1); tcgen05.mma issued by one elected lane of
+//                warp 1; tcgen05.commit multicast to both CTAs says "this layer's MMAs are done everywhere", which is
+//                what allows a CTA to overwrite its peer's A tile.  When an epilogue leaves the A tile alone (gate,
+//                g/f stores) the next layer's MMAs run while it still reads the other accumulator.
+//   epilogue   : 12 warps, one thread per row and column share: tcgen05.ld 8 columns at a time, bias, then the
+//                layer's element-wise tail (ReLU / LayerNorm / residual / gate / heads) in registers.  LayerNorm row
+//                statistics are exchanged between the two CTAs through DSMEM + an mbarrier; the fp32 row waits in
+//                the thread's own TMEM columns between the two passes.
+//   launches   : programmatic dependent launch -- barrier / TMEM / parameter set-up and the weight prefetch of a
+//                launch overlap the tail of its predecessor (griddepcontrol).
 //
 // Kernel boundaries remain only where rows of different tiles meet: the neighbour gathers (net[ix], net[jx]) and
-// the two SoftAgg segment reductions.  8 launches per update (6 of this kernel + 2 segment reductions) instead of ~60.
+// the two SoftAgg segment reductions (their `h` layers are applied per edge inside the consuming kernel).  8 launches per
+// update (6 of this kernel + 2 segment reductions) instead of ~60.  History, measurements and rejected variants:
+// DESIGN.md 2.6, profiles/r01_notes.md, tools/gru_timing.py.
 //
 // Rounding points follow torch.autocast exactly as devo_b200/update.py::forward_fused does (Linear outputs are
 // rounded to half, LayerNorm in float32, element-wise ops round to their promoted type); accumulation is fp32 in
