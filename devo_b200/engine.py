@@ -80,6 +80,8 @@ class UpdateOperator:
                         if self.gru_mode == "mma" else None)
         self._side = torch.cuda.Stream(device=dev)
         self._side2 = torch.cuda.Stream(device=dev)
+        self._side3 = torch.cuda.Stream(device=dev)
+        self._ingest_pending = False
         self._ba_ws = torch.empty(_lib.lib().devo_ba_workspace(self.E, max(self.t1 - self.t0, 0)), dtype=torch.uint8, device=dev)
         self._graph = None
         self._pristine = None
@@ -98,9 +100,18 @@ class UpdateOperator:
             self.plan_kk = cuda_ba.GraphPlan(self.kk, self.jj, self.Np, self.Nf)
             self.plan_ij = cuda_ba.GraphPlan(self.pair_key, self.zeros_e, -1, 1, want_neighbors=False)
 
-    def ingest_frame(self, idx, fmap, gmap_patches=None, imap_patches=None):
+    def ingest_frame(self, idx, fmap, gmap_patches=None, imap_patches=None, overlap=False):
         """fmap [C,H,W] planar features of frame `idx` -> all pixel-major pyramid levels;
-        gmap_patches [M,C,3,3], imap_patches [M,dim] -> patch feature buffers"""
+        gmap_patches [M,C,3,3], imap_patches [M,dim] -> patch feature buffers.
+        overlap=True: the packing runs on a side stream; the next iteration joins it right before the correlation
+        lookup (its first consumer), so it overlaps the graph analysis and the reprojection."""
+        if overlap:
+            cur = torch.cuda.current_stream(self.device)
+            self._side3.wait_stream(cur)
+            with torch.cuda.stream(self._side3):
+                self.ingest_frame(idx, fmap, gmap_patches, imap_patches, overlap=False)
+            self._ingest_pending = True
+            return
         f = fmap.reshape(1, self.C, self.H, self.W).to(self.feat_dtype)
         for l, s in enumerate(self.levels):        # packed straight into the ring-buffer slot (no staging copy)
             cuda_corr.pack_pixel_major(f, s, out=self.levels_pm[l][idx:idx + 1])
@@ -129,6 +140,9 @@ class UpdateOperator:
         # (1) reproject: [1,E,2,3,3]
         coords = pops.transform_fused(self.poses, self.patches, self.intrinsics, self.ii, self.jj, self.kk, layout=1)
         # (2) correlation lookup over all levels, output already in the GRU's [E, 882] layout
+        if self._ingest_pending:                    # an overlapped frame ingest: the lookup is its first consumer
+            cur.wait_stream(self._side3)
+            self._ingest_pending = False
         cuda_corr.lookup_fused(self.gmap_pm, self.levels_pm, self.levels, coords[0], self.kk, self.jj, out=self.corr_buf)
         corr = self.corr_buf if self.fused_gru else self.corr_buf[:, :self.corr_k]
         cur.wait_stream(self._side)

@@ -65,3 +65,18 @@ def test_graph_replay_equals_eager():
     torch.cuda.synchronize()
     assert torch.equal(op.poses, ref[0]) and torch.equal(op.patches, ref[1]) and torch.equal(op.net, ref[2])
     assert int(op.status_sticky.item()) == 0
+
+
+def test_overlapped_ingest_equals_serial_ingest():
+    """ingest_frame(overlap=True) packs the new frame on a side stream that the iteration joins before the lookup"""
+    res = []
+    for overlap in (False, True):
+        op, up, P, C, imap = _build(seed=9)
+        m = op.M
+        new = (torch.randn_like(C["fmap"][0, 1]) / 4).cuda()
+        op.ingest_frame(1, new, C["gmap"][0, m:2 * m].cuda(), imap[m:2 * m], overlap=overlap)
+        op.step()
+        torch.cuda.synchronize()
+        res.append((op.poses.clone(), op.patches.clone(), op.net.clone(), op.levels_pm[0].clone()))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
