@@ -20,6 +20,7 @@ __global__ void segment_softmax_sum_kernel(const T* __restrict__ g, const T* __r
   // PDL: a dependent kernel launched with programmatic stream serialisation (the h GEMM of the update operator) may
   // begin its set-up now; it waits (griddepcontrol.wait) for this grid's completion before reading y
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  DEVO_PDL_WAIT();                 // launched with PDL itself: g / f are the previous kernel's outputs
   const int grp = blockIdx.x;
   const int G = *ngroups;
   const int parts = blockDim.y, part = threadIdx.y;
@@ -90,7 +91,7 @@ extern "C" int devo_segment_softmax_sum(const void* g, const void* f, const int3
   dim3 block(tx, parts);
   dim3 grid(max_groups, (dim + tx - 1) / tx);
   const size_t smem = (size_t)parts * 3 * tx * sizeof(float);
-#define SEG(T) segment_softmax_sum_kernel<T><<<grid, block, smem, s>>>((const T*)g, (const T*)f, perm, gstart, ngroups, (T*)y_out, dim)
+#define SEG(T) DEVO_CUDA(devo::launch_pdl(segment_softmax_sum_kernel<T>, grid, block, smem, s, (const T*)g, (const T*)f, perm, gstart, ngroups, (T*)y_out, dim))
   switch (dtype) {
     case DEVO_F16: SEG(__half); break;
     case DEVO_BF16: SEG(__nv_bfloat16); break;
