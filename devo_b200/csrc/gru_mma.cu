@@ -204,13 +204,35 @@ struct Epi {
   __device__ __forceinline__ static const uint4* f4(const float* base, int q) { return reinterpret_cast<const uint4*>(base + (size_t)q * (kRows * 4)); }
   __device__ __forceinline__ static float4* f4w(float* base, int q) { return reinterpret_cast<float4*>(base + (size_t)q * (kRows * 4)); }
 
-  // deliver a 16-byte chunk of the next layer's A operand to every CTA of the cluster
+  // a 16-byte chunk of the next layer's A operand: written into the LOCAL tile only; the finished column slice is
+  // pushed to the peer CTAs by bulk DSMEM copies at the end of the layer (deliver_slice)
   __device__ __forceinline__ void a_store_all(int c, uint4 v) {
-    const uint32_t off = a_off(r, c);
+    *reinterpret_cast<uint4*>(As + a_off(r, c)) = v;
+  }
+  // end of an epilogue that rewrote this CTA's slice of the A tile (K-blocks rank*kKBc .. +kKBc): one thread arms the
+  // local a_ready barrier for the bytes the peers will send and pushes the own slice into every peer's tile with
+  // cp.async.bulk (shared::cta -> shared::cluster), which completes the bytes on the PEER's a_ready barrier.
+  // The MMA warp of a CTA therefore starts the next layer when its own epilogue has arrived and every slice has landed.
+  __device__ __forceinline__ void deliver_slice(bool wrote_a) {
+    constexpr int kKBc = kNC / 64;                 // K-blocks per CTA slice (3 at kSplit = 2)
+    constexpr uint32_t kSliceBytes = kKBc * kABlk;
+    if (wrote_a) fence_proxy_async();              // generic-proxy writes of the tile -> async proxy (bulk copy, UMMA)
+    epi_bar();
+    if (et == 0) {
+      if (wrote_a && kSplit > 1) {
+        mbar_arrive_expect_tx(a_ready, (kSplit - 1) * kSliceBytes);
+        const uint32_t src = smem_u32(As) + (uint32_t)rank * kSliceBytes;
 #pragma unroll
-    for (int p = 0; p < kSplit; p++) {
-      if (p == rank) *reinterpret_cast<uint4*>(As + off) = v;
-      else st_cluster_v4(peer_as[p] + off, v);
+        for (int p = 0; p < kSplit; p++) {
+          if (p == rank) continue;
+          const uint32_t bar = mapa(smem_u32(a_ready), (uint32_t)p);
+#pragma unroll
+          for (int j = 0; j < kKBc; j++)
+            bulk_copy_to_peer(peer_as[p] + (uint32_t)rank * kSliceBytes + j * kABlk, src + j * kABlk, kABlk, bar);
+        }
+      } else {
+        mbar_arrive(a_ready);
+      }
     }
   }
   // exchange per-row partials (N floats at s_buf[rank][part][r][*]) between all epilogue threads of the cluster
@@ -577,10 +599,9 @@ struct Epi {
     tc_fence_before();
     if (et == 0 && l == 0) stamp(P.dbg, 41);
     if (l + 1 < P.n_layers) {       // hand the A tiles / the TMEM accumulator back to the MMA warps of the cluster
-      if (kSplit > 1) fence_proxy_async_cluster(); else fence_proxy_async();   // A-tile writes (local and peers') -> async proxy
-      epi_bar();
-      if (kSplit > 1) { if (et < kSplit) mbar_arrive_cluster(mapa(smem_u32(a_ready), (uint32_t)et)); }
-      else if (et == 0) mbar_arrive(a_ready);
+      constexpr bool kWritesA = (EPI == EPI_RELU_A || EPI == EPI_LNRELU_A || EPI == EPI_GATED_LN || EPI == EPI_RESID_A ||
+                                 EPI == EPI_RESID_LN_A);
+      deliver_slice(kWritesA);
     }
     if (et == 0) stamp(P.dbg, 7 + 4 * l);
   }
@@ -602,7 +623,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
   uint64_t* a_full = w_empty + kWStages;      // [kASlots]
   uint64_t* a_empty = a_full + kASlots;       // [kASlots]
   uint64_t* acc_full = a_empty + kASlots;     // [2] (one per TMEM accumulator) count kSplit: the MMAs of a layer are done in EVERY CTA of the cluster
-  uint64_t* a_ready = acc_full + 2;           // [1] count kSplit: every CTA's epilogue has delivered its slice of the next A
+  uint64_t* a_ready = acc_full + 2;           // [1] own epilogue done + the peers' slices of the next A have landed (tx bytes)
   uint64_t* pro_ready = a_ready + 1;          // [1] local prologue finished
   uint64_t* stat_bar = pro_ready + 1;         // [1] count kSplit: LayerNorm / head partials of all CTAs have arrived
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);      // 32 barrier slots = 256 B; slot + pad = 16 B
@@ -626,7 +647,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
     for (int s = 0; s < kASlots; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     mbar_init(&acc_full[0], kSplit);
     mbar_init(&acc_full[1], kSplit);
-    mbar_init(a_ready, kSplit);
+    mbar_init(a_ready, 1);                         // local epilogue arrival (+ the bytes of the peers' slices)
     mbar_init(pro_ready, 1);
     mbar_init(stat_bar, kSplit);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -711,7 +732,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
         const bool writes_a = (pe == EPI_RELU_A || pe == EPI_LNRELU_A || pe == EPI_GATED_LN || pe == EPI_RESID_A || pe == EPI_RESID_LN_A);
         const int need = writes_a ? l - 1 : l - 2;     // last epilogue that must be complete: A operand / accumulator reuse
         while ((int)waited <= need) {
-          mbar_wait_cluster(a_ready, waited & 1u);     // peers' DSMEM stores: acquire at cluster scope
+          mbar_wait(a_ready, waited & 1u);             // own epilogue arrived and the peers' slices (bulk copies) landed
           waited++;
         }
         fence_proxy_async();

@@ -154,6 +154,15 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
       "DONE:\n\t"
       "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// bulk copy of `bytes` from this CTA's shared memory into a peer CTA's shared memory (both given as 32-bit shared
+// addresses: src in shared::cta, dst / barrier already mapped with mapa); completes `bytes` on the peer's mbarrier
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 // commit the MMAs issued so far; the arrive is multicast to the barrier at the same offset in every CTA of `mask`
 __device__ __forceinline__ void tc_commit_mc_elect(uint32_t bar_addr, uint16_t mask) {
