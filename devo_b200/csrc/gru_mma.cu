@@ -242,18 +242,21 @@ struct Epi {
 #pragma unroll
     for (int k = 0; k < N; k++) mine[k] = vals[k];
     if (kSplit > 1) {
-      const uint32_t local = smem_u32(mine);
-#pragma unroll
-      for (int p = 0; p < kSplit; p++) {
-        if (p == rank) continue;
-        const uint32_t dst = mapa(local, (uint32_t)p);
-#pragma unroll
-        for (int k = 0; k < N; k++) st_cluster_f32(dst + 4 * k, vals[k]);
-      }
-      // the release.cluster arrive after the CTA barrier publishes every thread's stores to the peers
+      // this CTA's block of partials ([kEpiPer][128][N] floats, contiguous) goes to every peer as ONE bulk DSMEM copy
+      // that completes on the peer's stat_bar; the local arrival carries the bytes expected from the peers
+      constexpr uint32_t kBlockBytes = kEpiPer * kRows * N * 4;
+      fence_proxy_async();
       epi_bar();
-      if (et < kSplit) mbar_arrive_cluster(mapa(smem_u32(stat_bar), (uint32_t)et));
-      mbar_wait_cluster(stat_bar, stat_uses & 1u);          // the peers' partials: acquire at cluster scope
+      if (et == 0) {
+        mbar_arrive_expect_tx(stat_bar, (kSplit - 1) * kBlockBytes);
+        const uint32_t src = smem_u32(s_buf) + (uint32_t)rank * kBlockBytes;
+#pragma unroll
+        for (int p = 0; p < kSplit; p++) {
+          if (p == rank) continue;
+          bulk_copy_to_peer(mapa(src, (uint32_t)p), src, kBlockBytes, mapa(smem_u32(stat_bar), (uint32_t)p));
+        }
+      }
+      mbar_wait(stat_bar, stat_uses & 1u);
       stat_uses++;
     } else {
       epi_bar();
@@ -649,7 +652,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
     mbar_init(&acc_full[1], kSplit);
     mbar_init(a_ready, 1);                         // local epilogue arrival (+ the bytes of the peers' slices)
     mbar_init(pro_ready, 1);
-    mbar_init(stat_bar, kSplit);
+    mbar_init(stat_bar, 1);                        // local arrival (+ the bytes of the peers' partials)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
