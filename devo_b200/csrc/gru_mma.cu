@@ -187,7 +187,7 @@ struct Epi {
   unsigned char* As;
   unsigned char* Ws;           // the weight ring: idle during the LAST layer's epilogue, reused as an output staging tile
   float* s_stat; float* s_hacc; const float* s_ln; const float* s_bias; const T* s_head; int* s_idx;
-  uint64_t* acc_full; uint64_t* a_ready; uint64_t* pro_ready; uint64_t* stat_bar;
+  uint64_t* acc_full; uint64_t* a_ready; uint64_t* a_local; uint64_t* pro_ready; uint64_t* stat_bar;
   int rank, tile, row0, quarter, part, et, r, grow;
   bool live;
   int lcb0, gcb0;
@@ -219,6 +219,7 @@ struct Epi {
     if (wrote_a) fence_proxy_async();              // generic-proxy writes of the tile -> async proxy (bulk copy, UMMA)
     epi_bar();
     if (et == 0) {
+      mbar_arrive(a_local);                        // the MMA warp may start on the K-blocks of the local slice right away
       if (wrote_a && kSplit > 1) {
         mbar_arrive_expect_tx(a_ready, (kSplit - 1) * kSliceBytes);
         const uint32_t src = smem_u32(As) + (uint32_t)rank * kSliceBytes;
@@ -628,6 +629,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
   uint64_t* acc_full = a_empty + kASlots;     // [2] (one per TMEM accumulator) count kSplit: the MMAs of a layer are done in EVERY CTA of the cluster
   uint64_t* a_ready = acc_full + 2;           // [1] own epilogue done + the peers' slices of the next A have landed (tx bytes)
   uint64_t* pro_ready = a_ready + 1;          // [1] local prologue finished
+  uint64_t* a_local = pro_ready + 2;          // [1] own epilogue done: this CTA's slice of the next A is in place, accumulator free
   uint64_t* stat_bar = pro_ready + 1;         // [1] count kSplit: LayerNorm / head partials of all CTAs have arrived
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);      // 32 barrier slots = 256 B; slot + pad = 16 B
   int* s_idx = reinterpret_cast<int*>(tmem_slot + 4);                 // [128] gather sources of the tile
@@ -652,6 +654,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
     mbar_init(&acc_full[1], kSplit);
     mbar_init(a_ready, 1);                         // local epilogue arrival (+ the bytes of the peers' slices)
     mbar_init(pro_ready, 1);
+    mbar_init(a_local, 1);
     mbar_init(stat_bar, 1);                        // local arrival (+ the bytes of the peers' partials)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -710,7 +713,9 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
         }
         mbar_wait(&w_empty[stage], phase ^ 1u);
         mbar_arrive_expect_tx_elect(smem_u32(&w_full[stage]), kWStage);
-        tma_load_2d_elect(smem_u32(Ws) + stage * kWStage, wm, smem_u32(&w_full[stage]), kb * 64, wrow);
+        // layers > 0 consume the K-blocks of the LOCAL slice first (they are ready before the peer's slice has landed)
+        const int kbw = (l == 0) ? kb : (rank * (kNC / 64) + kb) % kASlots;
+        tma_load_2d_elect(smem_u32(Ws) + stage * kWStage, wm, smem_u32(&w_full[stage]), kbw * 64, wrow);
         if (++stage == kWStages) { stage = 0; phase ^= 1u; }
       }
     }
@@ -721,7 +726,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
     const uint64_t ad0 = umma_desc_sw128(smem_u32(As));
     const uint64_t bd0 = umma_desc_sw128(smem_u32(Ws));
     const uint16_t all = (uint16_t)((1u << kSplit) - 1u);
-    uint32_t stage = 0, phase = 0, waited = 0;
+    uint32_t stage = 0, phase = 0, waited = 0, waited_r = 0;
     for (int l = 0; l < P.n_layers; l++) {
       const int nkb = (l == 0) ? P.kblocks0 : kASlots;
       const bool streamed = (l == 0 && P.stream_a0);
@@ -735,7 +740,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
         const bool writes_a = (pe == EPI_RELU_A || pe == EPI_LNRELU_A || pe == EPI_GATED_LN || pe == EPI_RESID_A || pe == EPI_RESID_LN_A);
         const int need = writes_a ? l - 1 : l - 2;     // last epilogue that must be complete: A operand / accumulator reuse
         while ((int)waited <= need) {
-          mbar_wait(a_ready, waited & 1u);             // own epilogue arrived and the peers' slices (bulk copies) landed
+          mbar_wait(a_local, waited & 1u);             // own epilogue arrived: local slice in place, accumulator free
           waited++;
         }
         fence_proxy_async();
@@ -744,7 +749,17 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
       const uint32_t tacc = tmem_base + (uint32_t)(l & 1) * kNC;
       if (lane == 0) stamp(P.dbg, 4 + 4 * l);
       for (int kb = 0; kb < nkb; kb++) {
-        const int slot = kb % kASlots;
+        if (l > 0 && kb == kNC / 64) {                 // the remaining K-blocks belong to the peers' slices
+          const int pe = P.epi[l - 1];
+          const bool writes_a = (pe == EPI_RELU_A || pe == EPI_LNRELU_A || pe == EPI_GATED_LN || pe == EPI_RESID_A || pe == EPI_RESID_LN_A);
+          const int need = writes_a ? l - 1 : l - 2;
+          while ((int)waited_r <= need) {
+            mbar_wait(a_ready, waited_r & 1u);         // the peers' slices (bulk copies) have landed
+            waited_r++;
+          }
+          tc_fence_after();
+        }
+        const int slot = (l == 0) ? kb % kASlots : (rank * (kNC / 64) + kb) % kASlots;
         if (streamed) { mbar_wait(&a_full[slot], (uint32_t)((kb / kASlots) & 1)); tc_fence_after(); }
         const uint64_t ad = ad0 + (uint64_t)(slot * (kABlk >> 4));
         mbar_wait(&w_full[stage], phase);
@@ -766,7 +781,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
     // =========================== prologue + epilogues (struct Epi) =============================================
     Epi<T> e(P);
     e.As = As; e.Ws = Ws; e.s_stat = s_stat; e.s_hacc = s_hacc; e.s_ln = s_ln; e.s_bias = s_bias; e.s_head = s_head; e.s_idx = s_idx;
-    e.acc_full = acc_full; e.a_ready = a_ready; e.pro_ready = pro_ready; e.stat_bar = stat_bar;
+    e.acc_full = acc_full; e.a_ready = a_ready; e.a_local = a_local; e.pro_ready = pro_ready; e.stat_bar = stat_bar;
     e.rank = rank; e.tile = tile; e.row0 = row0;
     e.quarter = warp & 3;
     e.part = (warp - kFirstEpiWarp) >> 2;           // 0 .. kEpiPer-1
