@@ -374,16 +374,19 @@ def run_e2e(op, wl, dev, steps):
 
         run(4)
         torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        run(steps)
-        torch.cuda.synchronize(dev)
-        dt = time.perf_counter() - t0
+        dts = []
+        for _ in range(3):                       # wall-clock timing is exposed to host hiccups: median of three runs
+            t0 = time.perf_counter()
+            run(steps)
+            torch.cuda.synchronize(dev)
+            dts.append(time.perf_counter() - t0)
+        dt = sorted(dts)[1]
     return dict(value=round(steps / dt, 2), unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                 steps=steps, seconds=dt,
                 note="host pinned inputs every step: new frame's features (prefetched on a copy stream, double-buffered) + poses, "
                      "patches, intrinsics and edge list (uploaded in order; the recurrent hidden state stays on the device, as "
                      "in the reference); result = poses + depths read back; "
-                     "wall clock between device synchronisations, <= 2 steps in flight")
+                     "wall clock between device synchronisations, <= 2 steps in flight; median of 3 runs of `steps` steps")
 
 
 # ----------------------------------------------------------------------------------------------
