@@ -213,26 +213,27 @@ struct Epi {
   // local a_ready barrier for the bytes the peers will send and pushes the own slice into every peer's tile with
   // cp.async.bulk (shared::cta -> shared::cluster), which completes the bytes on the PEER's a_ready barrier.
   // The MMA warp of a CTA therefore starts the next layer when its own epilogue has arrived and every slice has landed.
-  __device__ __forceinline__ void deliver_slice(bool wrote_a) {
+  __device__ __forceinline__ void deliver_slice(bool wrote_a, int l) {
     constexpr int kKBc = kNC / 64;                 // K-blocks per CTA slice (3 at kSplit = 2)
     constexpr uint32_t kSliceBytes = kKBc * kABlk;
     if (wrote_a) fence_proxy_async();              // generic-proxy writes of the tile -> async proxy (bulk copy, UMMA)
     epi_bar();
     if (et == 0) {
-      mbar_arrive(a_local);                        // the MMA warp may start on the K-blocks of the local slice right away
+      uint64_t* a_ready_l = a_ready + (l & 1);
+      mbar_arrive(a_local + (l & 1));              // the MMA warp may start on the K-blocks of the local slice right away
       if (wrote_a && kSplit > 1) {
-        mbar_arrive_expect_tx(a_ready, (kSplit - 1) * kSliceBytes);
+        mbar_arrive_expect_tx(a_ready_l, (kSplit - 1) * kSliceBytes);
         const uint32_t src = smem_u32(As) + (uint32_t)rank * kSliceBytes;
 #pragma unroll
         for (int p = 0; p < kSplit; p++) {
           if (p == rank) continue;
-          const uint32_t bar = mapa(smem_u32(a_ready), (uint32_t)p);
+          const uint32_t bar = mapa(smem_u32(a_ready_l), (uint32_t)p);
 #pragma unroll
           for (int j = 0; j < kKBc; j++)
             bulk_copy_to_peer(peer_as[p] + (uint32_t)rank * kSliceBytes + j * kABlk, src + j * kABlk, kABlk, bar);
         }
       } else {
-        mbar_arrive(a_ready);
+        mbar_arrive(a_ready_l);
       }
     }
   }
@@ -605,7 +606,7 @@ struct Epi {
     if (l + 1 < P.n_layers) {       // hand the A tiles / the TMEM accumulator back to the MMA warps of the cluster
       constexpr bool kWritesA = (EPI == EPI_RELU_A || EPI == EPI_LNRELU_A || EPI == EPI_GATED_LN || EPI == EPI_RESID_A ||
                                  EPI == EPI_RESID_LN_A);
-      deliver_slice(kWritesA);
+      deliver_slice(kWritesA, l);
     }
     if (et == 0) stamp(P.dbg, 7 + 4 * l);
   }
@@ -627,9 +628,12 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
   uint64_t* a_full = w_empty + kWStages;      // [kASlots]
   uint64_t* a_empty = a_full + kASlots;       // [kASlots]
   uint64_t* acc_full = a_empty + kASlots;     // [2] (one per TMEM accumulator) count kSplit: the MMAs of a layer are done in EVERY CTA of the cluster
-  uint64_t* a_ready = acc_full + 2;           // [1] own epilogue done + the peers' slices of the next A have landed (tx bytes)
-  uint64_t* pro_ready = a_ready + 1;          // [1] local prologue finished
-  uint64_t* a_local = pro_ready + 2;          // [1] own epilogue done: this CTA's slice of the next A is in place, accumulator free
+  // a_ready / a_local exist twice: the epilogue of layer q signals barrier q & 1, so each barrier only sees every other
+  // hand-off.  The MMA warp may legitimately run two hand-offs behind (it skips waiting for an epilogue that leaves the
+  // A tile alone); on a single phase-parity barrier a two-phase lag is indistinguishable from "not yet" and would hang.
+  uint64_t* a_ready = acc_full + 2;           // [2] own epilogue done + the peers' slices of the next A have landed (tx bytes)
+  uint64_t* pro_ready = a_ready + 2;          // [1] local prologue finished
+  uint64_t* a_local = pro_ready + 2;          // [2] own epilogue done: this CTA's slice of the next A is in place, accumulator free
   uint64_t* stat_bar = pro_ready + 1;         // [1] count kSplit: LayerNorm / head partials of all CTAs have arrived
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);      // 32 barrier slots = 256 B; slot + pad = 16 B
   int* s_idx = reinterpret_cast<int*>(tmem_slot + 4);                 // [128] gather sources of the tile
@@ -652,9 +656,11 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
     for (int s = 0; s < kASlots; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     mbar_init(&acc_full[0], kSplit);
     mbar_init(&acc_full[1], kSplit);
-    mbar_init(a_ready, 1);                         // local epilogue arrival (+ the bytes of the peers' slices)
+    mbar_init(&a_ready[0], 1);                     // local epilogue arrival (+ the bytes of the peers' slices)
+    mbar_init(&a_ready[1], 1);
     mbar_init(pro_ready, 1);
-    mbar_init(a_local, 1);
+    mbar_init(&a_local[0], 1);
+    mbar_init(&a_local[1], 1);
     mbar_init(stat_bar, 1);                        // local arrival (+ the bytes of the peers' partials)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -740,7 +746,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
         const bool writes_a = (pe == EPI_RELU_A || pe == EPI_LNRELU_A || pe == EPI_GATED_LN || pe == EPI_RESID_A || pe == EPI_RESID_LN_A);
         const int need = writes_a ? l - 1 : l - 2;     // last epilogue that must be complete: A operand / accumulator reuse
         while ((int)waited <= need) {
-          mbar_wait(a_local, waited & 1u);             // own epilogue arrived: local slice in place, accumulator free
+          mbar_wait(&a_local[waited & 1u], (waited >> 1) & 1u);   // own epilogue arrived: local slice in place, accumulator free
           waited++;
         }
         fence_proxy_async();
@@ -754,7 +760,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
           const bool writes_a = (pe == EPI_RELU_A || pe == EPI_LNRELU_A || pe == EPI_GATED_LN || pe == EPI_RESID_A || pe == EPI_RESID_LN_A);
           const int need = writes_a ? l - 1 : l - 2;
           while ((int)waited_r <= need) {
-            mbar_wait(a_ready, waited_r & 1u);         // the peers' slices (bulk copies) have landed
+            mbar_wait(&a_ready[waited_r & 1u], (waited_r >> 1) & 1u);   // the peers' slices (bulk copies) have landed
             waited_r++;
           }
           tc_fence_after();
