@@ -44,3 +44,13 @@ def test_sm100a_cubin_with_blackwell_instructions():
     gru = out[i:j if j > 0 else len(out)]
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "STTM", "UCGABAR_ARV", "UTCBAR"):
         assert mnemonic in gru, mnemonic
+
+
+def test_integration_doc_maps_every_symbol():
+    """INTEGRATION.md names every exported entry point (lie functions through the `devo_lie_*` row)"""
+    hdr = open(os.path.join(ROOT, "include", "devo_b200.h")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    declared = set(re.findall(r"\b(devo_[a-z0-9_A-Z]+)\s*\(", hdr))
+    assert "devo_lie_*" in doc
+    missing = sorted(s for s in declared if s not in doc and not s.startswith("devo_lie_"))
+    assert not missing, missing
