@@ -54,3 +54,38 @@ def test_integration_doc_maps_every_symbol():
     assert "devo_lie_*" in doc
     missing = sorted(s for s in declared if s not in doc and not s.startswith("devo_lie_"))
     assert not missing, missing
+
+
+def test_hot_kernels_do_not_spill():
+    """static resources of the per-iteration kernels (cuobjdump --dump-resource-usage): no stack frame (= no register
+    spills) in the tensor-core kernels the bench runs, and the fused update operator fits 448 threads per SM"""
+    import shutil
+    import subprocess
+    from devo_b200 import _lib
+    cu = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cu):
+        return
+    txt = subprocess.run([cu, "--dump-resource-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    res = {}
+    fn = None
+    for line in txt.splitlines():
+        m = re.match(r"\s*Function (\S+):", line)
+        if m:
+            fn = m.group(1)
+            continue
+        m = re.search(r"REG:(\d+) STACK:(\d+)", line)
+        if m and fn:
+            res[fn] = (int(m.group(1)), int(m.group(2)))
+            fn = None
+
+    def find(*parts):
+        hits = [v for k, v in res.items() if all(p in k for p in parts)]
+        assert hits, parts
+        return hits
+
+    for reg, stack in find("gru_mma_kernel", "6__half"):
+        assert stack == 0 and reg <= 128, (reg, stack)       # 448 threads x 128 registers <= 64 K per SM
+    for reg, stack in find("corr_fast_kernel"):
+        assert stack == 0, (reg, stack)
+    for reg, stack in find("segment_softmax_sum_kernel") + find("transform_kernel"):
+        assert stack == 0, (reg, stack)
