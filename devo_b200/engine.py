@@ -120,6 +120,14 @@ class UpdateOperator:
         if imap_patches is not None:
             self.imap[0, idx * self.M:(idx + 1) * self.M].copy_(imap_patches.to(self.feat_dtype))
 
+    def set_net(self, net):
+        """install the recurrent hidden state ([1,E,dim], any float dtype)"""
+        self.net.copy_(net)
+
+    def get_net(self):
+        """the recurrent hidden state as a row-major [1,E,dim] tensor"""
+        return self.net
+
     def snapshot_geometry(self):
         self._pristine = (self.poses.clone(), self.patches.clone())
 

@@ -240,6 +240,8 @@ class Update(nn.Module):
         from . import _lib
         E, D = net16.shape[1], self.dim
         dt = packed.dtype
+        if net16.dtype == torch.float32:
+            net16 = net16.to(dt)
         for t in (net16, imap16, corr16):
             _lib.require_cuda(t)
             _lib.require_dtype(t, dt, "forward_mma input")

@@ -20,6 +20,13 @@ README.md:71-73, setup.py:27-29), which is not on this machine.
 
 Outputs: oracle/_ref/cuda_corr_ref*.so, oracle/_ref/cuda_ba_ref*.so
 (git-ignored, travel to the GPU box with gpurun).
+
+`stage_python()` additionally stages an UNMODIFIED copy of the reference's Python callers
+(devo/*.py, devo/{altcorr,fastba,lietorch}/*.py, utils/*.py, config/default.yaml) under
+oracle/_ref/devo_py/ -- git-ignored like the rest of oracle/_ref, so the sources never enter
+the history, but they travel to the GPU box, where /root/reference does not exist.  The GPU
+tests (tests/test_gpu_reference_callers.py) import them on top of devo_b200.install_shims()
+to prove that the reference's own callers run unchanged on this library.
 """
 import os
 import shutil
@@ -56,6 +63,7 @@ def build(verbose=False):
     if not os.path.isdir(REF):
         return False
     os.makedirs(OUT, exist_ok=True)
+    stage_python()
     have = [f for f in os.listdir(OUT) if f.endswith(".so")]
     if any(f.startswith("cuda_corr_ref") for f in have) and any(f.startswith("cuda_ba_ref") for f in have):
         return True
@@ -78,6 +86,23 @@ def build(verbose=False):
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     return True
+
+
+PY_OUT = os.path.join(OUT, "devo_py")
+
+
+def stage_python():
+    """copy the reference's Python callers (verbatim) to oracle/_ref/devo_py/; returns the directory or None"""
+    if not os.path.isdir(os.path.join(REF, "devo")):
+        return PY_OUT if os.path.isdir(os.path.join(PY_OUT, "devo")) else None
+    for sub in ("devo", "devo/altcorr", "devo/fastba", "devo/lietorch", "utils", "config"):
+        src = os.path.join(REF, sub)
+        dst = os.path.join(PY_OUT, sub)
+        os.makedirs(dst, exist_ok=True)
+        for f in os.listdir(src):
+            if f.endswith((".py", ".yaml")) and os.path.isfile(os.path.join(src, f)):
+                shutil.copyfile(os.path.join(src, f), os.path.join(dst, f))
+    return PY_OUT
 
 
 def load_ref(name):
