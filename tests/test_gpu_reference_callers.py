@@ -53,8 +53,9 @@ def test_reference_altcorr_backward_and_patchify_on_this_library():
         g = Pm["gmap"].cuda().requires_grad_(True)
         f = Pm["pyramid"][0].cuda().requires_grad_(True)
         out = ns.altcorr.corr(g, f, Pm["coords"].cuda(), Pm["kk"].cuda(), Pm["jj"].cuda(), 3, 1)
-        torch.manual_seed(0)
-        (out * torch.randn_like(out)).sum().backward()
+        # (the reference returns a permuted view: randn_like would follow its strides, so draw the noise by shape)
+        noise = torch.randn(out.shape, generator=torch.Generator().manual_seed(0)).cuda()
+        (out * noise).sum().backward()
         net = Pm["pyramid"][0][0].cuda()
         xy = torch.stack([torch.randint(1, 62, (3, 20)), torch.randint(1, 46, (3, 20))], -1).float().cuda()
         grads[kind] = (g.grad.clone(), f.grad.clone(), ns.altcorr.patchify(net, xy, 1), ns.altcorr.patchify(net, xy + 0.25, 1))

@@ -132,3 +132,37 @@ def test_fastba_vs_reference(nf, m, iters):
     assert (ours[0] - r1[0]).abs().max().item() <= 1e-5 + 4 * self_p + 2 * ep_ref
     assert (ours[1] - r1[1]).abs().max().item() <= 1e-5 + 4 * self_d + 2 * ed_ref
     assert ep_ours <= max(ep_ref, 1e-5) * 1.5 and ed_ours <= max(ed_ref, 1e-5) * 1.5
+
+
+@pytest.mark.parametrize("oob", [False, True])
+def test_corr_fast_fp16_full_s8_all_edges_vs_reference(oob):
+    """BASELINE.json config 2 at FULL size: all 6144 edges x both pyramid levels [1,4], reprojected and out-of-bounds-stress
+    coordinates -- the TMA + tcgen05 lookup (drop-in per-level call AND the engine's fused multi-level call) against the
+    reference's compiled kernel on the same fp16 inputs.  The reference accumulates in half, this library in fp32: both are
+    measured against the fp64 oracle; ours must not be worse, and the two must agree to within the sum of their errors."""
+    ref = _ref("cuda_corr_ref")
+    from devo_b200 import cuda_corr
+    Pm = corr_problem(seed=1234, oob_stress=oob)
+    gm, ii, jj = Pm["gmap"].cuda(), Pm["kk"].cuda(), Pm["jj"].cuda()
+    per_level = []
+    for lvl, s in enumerate((1, 4)):
+        c = (Pm["coords"] / s).cuda()
+        (r,) = ref.forward(gm, Pm["pyramid"][lvl].cuda(), c, ii, jj, 3)
+        (o,) = cuda_corr.forward(gm, Pm["pyramid"][lvl].cuda(), c, ii, jj, 3)
+        exact = ocorr.corr_forward(Pm["gmap"], Pm["pyramid"][lvl], Pm["coords"] / s, Pm["kk"], Pm["jj"], 3)
+        assert o.shape == r.shape == (1, 6144, 7, 7, 3, 3) and o.dtype == r.dtype
+        scale = exact.abs().max().item()
+        e_ref = (r.double().cpu() - exact).abs().max().item() / scale
+        e_ours = (o.double().cpu() - exact).abs().max().item() / scale
+        assert e_ours <= max(e_ref, 1e-3), (lvl, e_ours, e_ref)
+        assert (o.double() - r.double()).abs().max().item() / scale <= e_ref + e_ours + 1e-3
+        per_level.append(o)
+    fused = cuda_corr.lookup_fused(cuda_corr.pack_gmap(gm[0]), [cuda_corr.pack_pixel_major(Pm["fmap"][0].cuda(), s) for s in (1, 4)],
+                                   (1, 4), Pm["coords"].cuda()[0], ii, jj)
+    want = torch.stack(per_level, -1).view(6144, -1)                           # devo.py:217 layout
+    if not oob:
+        assert torch.equal(fused, want)          # reprojected patches: every window fits the staged box in both calls
+    else:
+        # random per-pixel coordinates: which pixels take the in-box tensor-core path and which the direct path depends on
+        # the box edge of the call (per-level call: scale 1; fused call: scale 4 => smaller box) -- summation order only
+        assert (fused.float() - want.float()).abs().max().item() <= 2e-3 * want.float().abs().max().item()
