@@ -125,7 +125,7 @@ def load_state(op, wl, dev):
     fmap, gmap, imap = wl["fmap"].to(dev), wl["gmap"].to(dev), wl["imap"].to(dev)
     for f in range(wl["n_frames"]):
         op.ingest_frame(f, fmap[f], gmap[f * M:(f + 1) * M], imap[f * M:(f + 1) * M])
-    op.net.copy_(wl["net"].to(dev)[None])
+    op.set_net(wl["net"].to(dev)[None])
     op.snapshot_geometry()
     return fmap, gmap, imap
 
@@ -247,10 +247,11 @@ def run_ours(args, rank, world, local_rank):
     if args.gru == "mma":
         with torch.no_grad():
             gg = torch.cuda.CUDAGraph()
-            scratch = torch.empty_like(op.net)
+            from devo_b200.update import GruState
+            scratch = GruState(op.E, dev).set(op.get_net())
             with torch.cuda.graph(gg):
-                op.update.forward_mma(op.net, op.imap, op.kk, op.corr_buf, op.plan_kk, op.plan_ij, op.Np, op.Nf * op.Nf,
-                                      op.packed, net_out=scratch, workspace=op._gru_ws)
+                op.update.forward_mma(None, op.imap, op.kk, op.corr_buf, op.plan_kk, op.plan_ij, op.Np, op.Nf * op.Nf,
+                                      op.packed, workspace=op._gru_ws, state=scratch)
             gt = []
             for _ in range(30):
                 flush.zero_()

@@ -50,6 +50,8 @@ SIGNATURES = {
     "devo_glue_heads": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "devo_segment_softmax_sum": (_i, [_vp] * 5 + [_i, _vp, _i, _i, _i, _vp]),
     "devo_gru_workspace": (_sz, [_i, _i]),
+    "devo_gru_state_floats": (_sz, [_i]),
+    "devo_gru_state_gather": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _vp]),
     "devo_gru_update": (_i, [_vp, _vp, _i, _vp, _sz, _vp]),
 }
 for _n, _a in (("expm", 2), ("logm", 2), ("inv", 2), ("as_matrix", 2), ("projector", 2),
@@ -73,7 +75,7 @@ class GruWeightsStruct(ctypes.Structure):
 
 class GruIoStruct(ctypes.Structure):
     """devo_gru_io_t"""
-    _fields_ = [("E", _i), ("dim", _i), ("corr_ld", _i), ("corr16", _vp), ("net16", _vp), ("imap16", _vp), ("kk", _vp),
+    _fields_ = [("E", _i), ("dim", _i), ("corr_ld", _i), ("corr16", _vp), ("state32", _vp), ("net16", _vp), ("imap16", _vp), ("kk", _vp),
                 ("ix", _vp), ("jx", _vp),
                 ("perm_kk", _vp), ("gstart_kk", _vp), ("ngroups_kk", _vp), ("gid_kk", _vp), ("max_groups_kk", _i),
                 ("perm_ij", _vp), ("gstart_ij", _vp), ("ngroups_ij", _vp), ("gid_ij", _vp), ("max_groups_ij", _i),

@@ -11,7 +11,7 @@ the layout the TMA-staged lookup kernel wants; `ingest_frame` converts a planar 
 when it enters the ring buffer (replaces devo/devo.py:523-527 + pyramidify, utils.py:70-79).
 
   poses      f32 [1, n_frames, 7]        patches  f32 [1, n_patches, 3, 3, 3]
-  intrinsics f32 [1, n_frames, 4]        net      f16 [1, E, 384]
+  intrinsics f32 [1, n_frames, 4]        state    f32 tile layout (GruState; the hidden state, [1, E, 384] logically)
   imap       f16 [1, n_patches, 384]     gmap_pm  f16 [n_patches, 9, C]
   levels_pm  f16 [n_frames, H/s, W/s, C] for s in levels
   ii, jj, kk i64 [E]
@@ -19,7 +19,7 @@ when it enters the ring buffer (replaces devo/devo.py:523-527 + pyramidify, util
 import torch
 
 from . import _lib, cuda_ba, cuda_corr, projective_ops as pops
-from .update import FrozenCast, PackedUpdateWeights
+from .update import FrozenCast, GruState, PackedUpdateWeights
 
 
 class UpdateOperator:
@@ -59,7 +59,10 @@ class UpdateOperator:
             setattr(self, name, self.state_arena[o:o + nbytes].view(dt).view(shape))
         self.poses[..., 6] = 1.0
         self.pair_key = torch.zeros(self.E, dtype=i64, device=dev)
-        self.net = torch.zeros(1, self.E, dim, dtype=feat_dtype, device=dev)
+        # the recurrent hidden state: float32 like the reference's (devo.py:232-233,308-316), held in the tile layout the
+        # fused update operator reads and writes in place; the cuBLAS comparison paths keep a row-major copy
+        self.state = GruState(self.E, dev, dim) if self.gru_mode == "mma" else None
+        self.net = None if self.gru_mode == "mma" else torch.zeros(1, self.E, dim, dtype=torch.float32, device=dev)
         self.imap = torch.zeros(1, self.Np, dim, dtype=feat_dtype, device=dev)
         self.gmap_pm = torch.zeros(self.Np, 9, C, dtype=feat_dtype, device=dev)
         self.levels_pm = [torch.zeros(self.Nf, H // s, W // s, C, dtype=feat_dtype, device=dev) for s in self.levels]
@@ -75,7 +78,7 @@ class UpdateOperator:
         self.plan_ij = None
         self.zeros_e = torch.zeros(self.E, dtype=i64, device=dev)
         self.fc = FrozenCast(feat_dtype)
-        self.packed = PackedUpdateWeights(update, feat_dtype, self.corr_ld) if self.gru_mode == "mma" else None
+        self.packed = PackedUpdateWeights(update, feat_dtype, self.corr_ld) if (fused_gru and dim == 384 and gru == "mma") else None
         self._gru_ws = (torch.empty(_lib.lib().devo_gru_workspace(self.E, max(self.Np, self.Nf * self.Nf)), dtype=torch.uint8, device=dev)
                         if self.gru_mode == "mma" else None)
         self._side = torch.cuda.Stream(device=dev)
@@ -121,12 +124,15 @@ class UpdateOperator:
             self.imap[0, idx * self.M:(idx + 1) * self.M].copy_(imap_patches.to(self.feat_dtype))
 
     def set_net(self, net):
-        """install the recurrent hidden state ([1,E,dim], any float dtype)"""
-        self.net.copy_(net)
+        """install the recurrent hidden state ([1,E,dim], any float dtype; kept as float32)"""
+        if self.state is not None:
+            self.state.set(net)
+        else:
+            self.net.copy_(net)
 
     def get_net(self):
-        """the recurrent hidden state as a row-major [1,E,dim] tensor"""
-        return self.net
+        """the recurrent hidden state as a row-major float32 [1,E,dim] tensor"""
+        return self.state.get() if self.state is not None else self.net
 
     def snapshot_geometry(self):
         self._pristine = (self.poses.clone(), self.patches.clone())
@@ -158,14 +164,15 @@ class UpdateOperator:
         # (3) GRU: cached fp16 weights, autocast-identical dtype flow, no host sync
         target = None
         if self.gru_mode == "mma":      # target / weight for BA come out of the heads epilogue of the same launch
-            net, (delta, weight16, (target, weight)) = self.update.forward_mma(
-                self.net, self.imap, self.kk, self.corr_buf, self.plan_kk, self.plan_ij, self.Np, self.Nf * self.Nf,
-                self.packed, net_out=self.net, workspace=self._gru_ws, coords=coords)
+            _, (delta, weight16, (target, weight)) = self.update.forward_mma(
+                None, self.imap, self.kk, self.corr_buf, self.plan_kk, self.plan_ij, self.Np, self.Nf * self.Nf,
+                self.packed, workspace=self._gru_ws, coords=coords, state=self.state)
         elif self.fused_gru:
             ctx = self.imap[:, self.kk]
             net, (delta, weight, _) = self.update.forward_fused(
-                self.net, ctx, corr.view(1, self.E, -1), self.plan_kk, self.plan_ij, self.Np, self.Nf * self.Nf,
-                self.fc, net_out=self.net)
+                self.net.to(self.feat_dtype), ctx, corr.view(1, self.E, -1), self.plan_kk, self.plan_ij, self.Np, self.Nf * self.Nf,
+                self.fc)
+            self.net.copy_(net)
         else:
             ctx = self.imap[:, self.kk]
             net, (delta, weight, _) = self.update.forward_planned(

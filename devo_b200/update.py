@@ -137,6 +137,45 @@ class PackedUpdateWeights:
         return self
 
 
+class GruState:
+    """The recurrent hidden state of the fused update operator: float32, in the tile layout devo_gru_update reads and
+    writes in place ([tiles of 64 rows][96 float4 groups][64][4], include/devo_b200.h).  `set` / `get` convert from / to the
+    reference's row-major [1,E,384]; `gather` implements `net[:, ~m]` / `torch.cat([net, zeros])` (devo.py:225-239) on the
+    device without leaving the layout."""
+
+    def __init__(self, E, device, dim=DIM):
+        from . import _lib
+        self.E, self.dim, self.device = int(E), dim, torch.device(device)
+        self.buf = torch.zeros(max(_lib.lib().devo_gru_state_floats(self.E), 4), dtype=torch.float32, device=self.device)
+
+    def _gather(self, src, src_layout, src_rows, idx, dst, dst_layout, dst_rows):
+        from . import _lib
+        _lib.check(_lib.lib().devo_gru_state_gather(src.data_ptr(), src_layout, int(src_rows), _lib.ptr(idx), dst.data_ptr(),
+                                                    dst_layout, int(dst_rows), _lib.stream_ptr(self.device)), "gru_state_gather")
+
+    def set(self, net):
+        """net: [1,E,384] (any float dtype; stored as float32)"""
+        net = net.detach().reshape(self.E, self.dim).to(device=self.device, dtype=torch.float32).contiguous()
+        self._gather(net, 0, self.E, None, self.buf, 1, self.E)
+        return self
+
+    def get(self):
+        out = torch.empty(1, self.E, self.dim, dtype=torch.float32, device=self.device)
+        self._gather(self.buf, 1, self.E, None, out, 0, self.E)
+        return out
+
+    def zero_(self):
+        self.buf.zero_()
+        return self
+
+    def gather(self, idx):
+        """new state whose row e is row idx[e] of this one (idx[e] < 0 => zeros)"""
+        idx = idx.to(device=self.device, dtype=torch.int64).contiguous()
+        out = GruState(idx.numel(), self.device, self.dim)
+        self._gather(self.buf, 1, self.E, idx, out.buf, 1, out.E)
+        return out
+
+
 class _ClipGrad(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
@@ -229,28 +268,41 @@ class Update(nn.Module):
         net = run(self.gru, net)
         return net, (run(self.d, net), run(self.w, net), None)
 
-    def forward_mma(self, net16, imap16, kk, corr16, plan_kk, plan_ij, max_patches, max_pairs, packed, net_out=None,
-                    workspace=None, coords=None):
-        """The whole forward as fused tcgen05 kernels (csrc/gru_mma.cu, devo_gru_update): net16 [1,E,384] hidden state,
+    def forward_mma(self, net, imap16, kk, corr16, plan_kk, plan_ij, max_patches, max_pairs, packed, net_out=None,
+                    workspace=None, coords=None, state=None):
+        """The whole forward as fused tcgen05 kernels (csrc/gru_mma.cu, devo_gru_update).
+        net: the hidden state [1,E,384] -- float32 (every update but the first: enet.py GatedResidual returns float32 under
+             autocast) or the autocast dtype (the half zero-state of the first update; follows the half dtype flow) --
+             or None when `state` (a GruState, the engine's persistent tile-layout float32 buffer) already holds it.
         imap16 [1,Np,384] context features (inp = imap16[:, kk], gathered inside), corr16 [E, corr_ld] zero-padded
-        correlation rows.  Returns (net_out [1,E,384] autocast dtype, (delta, weight, None)).  Inference only; same
-        rounding points as forward_fused.  With `coords` ([1,E,2,3,3] f32, the reprojection) the BA inputs are produced
-        by the same launch and returned as the third element: (target f32 [1,E,2], weight f32 [1,E,2])."""
+        correlation rows.  Returns (new state float32 [1,E,384] (or `state` itself when given), (delta, weight, None)).
+        Inference only; autocast rounding points.  With `coords` ([1,E,2,3,3] f32, the reprojection) the BA inputs are
+        produced by the same launch and returned as the third element: (target f32 [1,E,2], weight f32 [1,E,2])."""
         import ctypes
         from . import _lib
-        E, D = net16.shape[1], self.dim
+        E, D = corr16.shape[0], self.dim
         dt = packed.dtype
-        if net16.dtype == torch.float32:
-            net16 = net16.to(dt)
-        for t in (net16, imap16, corr16):
+        for t in (imap16, corr16):
             _lib.require_cuda(t)
             _lib.require_dtype(t, dt, "forward_mma input")
             _lib.require_contiguous(t=t)
         if corr16.shape[-1] != packed.corr_ld:
             raise RuntimeError("forward_mma: correlation rows must be padded to %d" % packed.corr_ld)
-        dev = net16.device
-        if net_out is None:
-            net_out = torch.empty(1, E, D, dtype=dt, device=dev)
+        dev = corr16.device
+        own_state = state is None
+        if own_state:
+            state = GruState(E, dev)
+        net16_ptr = 0
+        if net is not None:
+            _lib.require_cuda(net)
+            if net.numel() != E * D:
+                raise RuntimeError("forward_mma: the hidden state must be [1,E,%d]" % D)
+            if net.dtype == torch.float32:
+                state.set(net)
+            else:
+                _lib.require_dtype(net, dt, "forward_mma hidden state")
+                net = net.contiguous()
+                net16_ptr = net.data_ptr()
         delta = torch.empty(1, E, 2, dtype=dt, device=dev)
         weight = torch.empty(1, E, 2, dtype=dt, device=dev)
         L = _lib.lib()
@@ -259,11 +311,14 @@ class Update(nn.Module):
         if ws.numel() < nbytes:
             raise RuntimeError("forward_mma: workspace too small")
         packed.refresh()
-        io = _lib.GruIoStruct(E, D, packed.corr_ld, corr16.data_ptr(), net16.data_ptr(), imap16.data_ptr(), kk.data_ptr(),
+        io = _lib.GruIoStruct(E, D, packed.corr_ld, corr16.data_ptr(), state.buf.data_ptr(), net16_ptr, imap16.data_ptr(), kk.data_ptr(),
                               plan_kk.ix.data_ptr(), plan_kk.jx.data_ptr(),
                               plan_kk.perm.data_ptr(), plan_kk.gstart.data_ptr(), plan_kk.ngroups.data_ptr(), plan_kk.gid.data_ptr(), int(max_patches),
                               plan_ij.perm.data_ptr(), plan_ij.gstart.data_ptr(), plan_ij.ngroups.data_ptr(), plan_ij.gid.data_ptr(), int(max_pairs),
-                              net_out.data_ptr(), delta.data_ptr(), weight.data_ptr(), 0, 0, 0)
+                              0 if net_out is None else net_out.data_ptr(), delta.data_ptr(), weight.data_ptr(), 0, 0, 0)
+        if net_out is not None:
+            _lib.require_dtype(net_out, dt, "forward_mma net_out")
+            _lib.require_contiguous(net_out=net_out)
         extra = None
         if coords is not None:
             _lib.require_dtype(coords, torch.float32, "coords")
@@ -272,9 +327,9 @@ class Update(nn.Module):
                 raise RuntimeError("forward_mma: coords must be [1,E,2,3,3]")
             extra = (torch.empty(1, E, 2, dtype=torch.float32, device=dev), torch.empty(1, E, 2, dtype=torch.float32, device=dev))
             io.coords, io.target32, io.weight32 = coords.data_ptr(), extra[0].data_ptr(), extra[1].data_ptr()
-        _lib.check(L.devo_gru_update(ctypes.byref(packed.struct), ctypes.byref(io), _lib.dtype_code(net16), ws.data_ptr(),
+        _lib.check(L.devo_gru_update(ctypes.byref(packed.struct), ctypes.byref(io), _lib.dtype_code(corr16), ws.data_ptr(),
                                      ws.numel(), _lib.stream_ptr(dev)), "gru_update")
-        return net_out, (delta, weight, extra)
+        return (state.get() if own_state else state), (delta, weight, extra)
 
     def forward_fused(self, net16, inp16, corr16, plan_kk, plan_ij, max_patches, max_pairs, fc, net_out=None):
         """forward_planned with the element-wise glue fused into hand-written kernels (devo_b200.glue) and

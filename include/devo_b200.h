@@ -224,9 +224,12 @@ int devo_glue_heads(int dtype, const float* x32, const void* W16, const void* b1
 
 /* ------------------------------------------------------------------ fused update operator */
 /* The whole of Update.forward (devo/enet.py:80-99: corr MLP, norm, neighbour convolutions c1/c2, the two SoftAgg
- * aggregations, the gated-residual GRU and both heads) as fused tcgen05 kernels: one CTA keeps a tile of 128 edges
- * resident (activations in shared memory, accumulator in TMEM) through a whole chain of Linear layers, weights
- * streamed by TMA.  Inference only, autocast rounding points (see devo_b200/update.py::forward_fused).
+ * aggregations, the gated-residual GRU and both heads) as fused tcgen05 kernels: a pair of CTAs (cta_group::2 MMAs,
+ * 64 whole rows per CTA) keeps a tile of 128 edges resident (activations in shared memory, accumulators in TMEM)
+ * through a whole chain of Linear layers, weights streamed by TMA.  Inference only, autocast rounding points.
+ * The recurrent hidden state is FLOAT32 in a TILE layout [ceil(E/128)*2 tiles][96 float4 groups][64 rows][4]
+ * (devo_gru_state_floats(E) floats; convert / gather rows with devo_gru_state_gather): the reference's state is float32
+ * from the second update on (GatedResidual returns float32 under autocast; devo.py:232-233 concatenates half zeros).
  * Stacked layer order of W [18*384,384] and bias rows 1..18: corr[2], corr[5], c1[0], c1[2], c2[0], c2[2],
  * agg_kk.g, agg_kk.f, agg_kk.h, agg_ij.g, agg_ij.f, agg_ij.h, gru[1].gate[0], gru[1].res[0], gru[1].res[2],
  * gru[3].gate[0], gru[3].res[0], gru[3].res[2].  LayerNorm rows: corr[3], norm, gru[0], gru[2]. */
@@ -243,14 +246,16 @@ typedef struct {
 typedef struct {
   int E, dim, corr_ld;
   const void* corr16;     /* [E, corr_ld] correlation features (rows zero-padded) */
-  const void* net16;      /* [E, 384] hidden state in */
+  float* state32;         /* hidden state, float32, tile layout: read (unless net16 is given) and overwritten in place */
+  const void* net16;      /* optional [E, 384] row-major hidden state in the autocast dtype (the first update of a sequence:
+                             half dtype flow); NULL => the input is state32 */
   const void* imap16;     /* [n_patches, 384] context features; inp = imap16[kk] */
   const int64_t* kk;      /* [E] */
   const int64_t* ix;      /* [E] neighbours from devo_graph_plan(kk, jj): previous / next edge or -1 */
   const int64_t* jx;
   const int32_t* perm_kk; const int32_t* gstart_kk; const int32_t* ngroups_kk; const int32_t* gid_kk; int max_groups_kk;
   const int32_t* perm_ij; const int32_t* gstart_ij; const int32_t* ngroups_ij; const int32_t* gid_ij; int max_groups_ij;
-  void* net16_out;        /* [E, 384] hidden state out (may alias net16) */
+  void* net16_out;        /* optional [E, 384] row-major copy of the new hidden state in the autocast dtype, or NULL */
   void* delta;            /* [E, 2] */
   void* weight;           /* [E, 2] */
   /* optional fused BA inputs (devo.py:326-331): target = coords[:, :, 1, 1] + float(delta), weight as f32 */
@@ -259,6 +264,11 @@ typedef struct {
   float* weight32;        /* [E, 2] or NULL */
 } devo_gru_io_t;
 size_t devo_gru_workspace(int E, int max_groups);
+size_t devo_gru_state_floats(int E);
+/* dst row e = idx ? (idx[e] >= 0 ? src row idx[e] : 0) : src row e ; layouts: 0 = row-major [rows,384], 1 = tile layout.
+ * Packs / unpacks the hidden state and implements net[:, ~m] / torch.cat([net, zeros]) of devo.py:225-239 on the device. */
+int devo_gru_state_gather(const float* src, int src_layout, int src_rows, const int64_t* idx, float* dst, int dst_layout,
+                          int dst_rows, void* stream);
 int devo_gru_update(const devo_gru_weights_t* weights, const devo_gru_io_t* io, int dtype, void* workspace,
                     size_t workspace_bytes, void* stream);
 

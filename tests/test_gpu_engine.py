@@ -24,14 +24,14 @@ def _build(nf=4, m=24, H=60, W=80, seed=5):
     imap = (torch.randn(nf * m, 384) / 4).half().cuda()
     for f in range(nf):
         op.ingest_frame(f, C["fmap"][0, f].cuda(), C["gmap"][0, f * m:(f + 1) * m].cuda(), imap[f * m:(f + 1) * m])
-    op.net.normal_(0, 0.1)
+    op.set_net(0.1 * torch.randn(1, E, 384, device="cuda"))
     return op, up, P, C, imap
 
 
 def test_step_equals_op_by_op_composition():
     from devo_b200 import altcorr, fastba, projective_ops as pops, lietorch as lt
     op, up, P, C, imap = _build()
-    net0 = op.net.clone()
+    net0 = op.get_net().clone()
     poses, patches = op.poses.clone(), op.patches.clone()
     ii, jj, kk = op.ii, op.jj, op.kk
     # ---- reference-shaped composition (devo.py:210-223,308-338)
@@ -48,22 +48,22 @@ def test_step_equals_op_by_op_composition():
     op.step()
     assert int(op.status.item()) == 0
     assert torch.allclose(op.coords, coords, atol=1e-4)
-    assert torch.allclose(op.net.float(), net.float(), atol=2e-2, rtol=2e-2)
+    assert torch.allclose(op.get_net(), net.float(), atol=2e-2, rtol=2e-2)
     assert torch.allclose(op.poses, poses, atol=2e-4) and torch.allclose(op.patches, patches, atol=2e-3)
 
 
 def test_graph_replay_equals_eager():
     op, up, P, C, imap = _build(seed=8)
     op.snapshot_geometry()
-    net0 = op.net.clone()
+    net0 = op.get_net().clone()
     op.step(reset_geometry=True)
-    ref = (op.poses.clone(), op.patches.clone(), op.net.clone())
-    op.net.copy_(net0)
+    ref = (op.poses.clone(), op.patches.clone(), op.get_net().clone())
+    op.set_net(net0)
     op.capture(reset_geometry=True, warmup=2)
-    op.net.copy_(net0)
+    op.set_net(net0)
     op.replay()
     torch.cuda.synchronize()
-    assert torch.equal(op.poses, ref[0]) and torch.equal(op.patches, ref[1]) and torch.equal(op.net, ref[2])
+    assert torch.equal(op.poses, ref[0]) and torch.equal(op.patches, ref[1]) and torch.equal(op.get_net(), ref[2])
     assert int(op.status_sticky.item()) == 0
 
 
@@ -77,6 +77,6 @@ def test_overlapped_ingest_equals_serial_ingest():
         op.ingest_frame(1, new, C["gmap"][0, m:2 * m].cuda(), imap[m:2 * m], overlap=overlap)
         op.step()
         torch.cuda.synchronize()
-        res.append((op.poses.clone(), op.patches.clone(), op.net.clone(), op.levels_pm[0].clone()))
+        res.append((op.poses.clone(), op.patches.clone(), op.get_net().clone(), op.levels_pm[0].clone()))
     for a, b in zip(*res):
         assert torch.equal(a, b)

@@ -62,22 +62,39 @@ def test_gru_mma_matches_module_forward_under_autocast():
     assert (w.float() - ref_w.float()).abs().max().item() <= 1e-2
 
 
-def test_gru_mma_bf16_and_in_place_hidden_state():
-    from devo_b200.update import FrozenCast, PackedUpdateWeights
+def test_gru_mma_bf16_and_persistent_state():
+    """bf16 weights / activations; the hidden state lives in a GruState (tile-layout float32) that the kernel updates in
+    place, and the optional half copy of the new state (net_out) is written by the same launch"""
+    from devo_b200.update import FrozenCast, GruState, PackedUpdateWeights
     up, net, imap, corr, ii, jj, kk, plan_kk, plan_ij, Np, pairs = _problem(4, 24, 6, dt=torch.bfloat16)
     fc = FrozenCast(torch.bfloat16)
     with torch.no_grad():
         ref_net, (ref_d, ref_w, _) = up.forward_fused(net, imap[:, kk], corr.view(1, -1, 896), plan_kk, plan_ij, Np, pairs, fc)
-        state = net.clone()
-        out_net, (d, w, _) = up.forward_mma(state, imap, kk, corr, plan_kk, plan_ij, Np, pairs,
-                                            PackedUpdateWeights(up, torch.bfloat16, 896), net_out=state)
-    assert out_net.data_ptr() == state.data_ptr()
-    assert (state.float() - ref_net).abs().max().item() <= 1e-1 * max(ref_net.abs().max().item(), 1.0)
+        state = GruState(net.shape[1], "cuda")
+        copy16 = torch.empty_like(net)
+        ret, (d, w, _) = up.forward_mma(net, imap, kk, corr, plan_kk, plan_ij, Np, pairs,
+                                        PackedUpdateWeights(up, torch.bfloat16, 896), net_out=copy16, state=state)
+    assert ret is state
+    assert (state.get() - ref_net).abs().max().item() <= 1e-1 * max(ref_net.abs().max().item(), 1.0)
+    assert torch.equal(copy16.float(), state.get().to(torch.bfloat16).float())
     assert (d.float() - ref_d.float()).abs().max().item() <= 1e-1
 
 
+def test_gru_state_pack_unpack_and_gather():
+    """GruState: row-major <-> tile layout round trip is exact; gather implements net[:, ~m] and zero rows for new edges"""
+    from devo_b200.update import GruState
+    for E in (1, 63, 64, 129, 6144, 777):
+        x = torch.randn(1, E, 384, device="cuda")
+        st = GruState(E, "cuda").set(x)
+        assert torch.equal(st.get(), x)
+        idx = torch.randint(-1, E, (E + 5,), device="cuda")
+        got = st.gather(idx).get()[0]
+        want = torch.where((idx >= 0)[:, None], x[0][idx.clamp_min(0)], torch.zeros(1, device="cuda"))
+        assert torch.equal(got, want)
+
+
 def test_gru_mma_is_deterministic():
-    """cluster hand-offs (DSMEM A-tile slices, LayerNorm partials) must not race: repeated runs are bit-identical"""
+    """pair hand-offs (A-operand double buffer, TMEM sets, staged TMA stores) must not race: repeated runs are bit-identical"""
     from devo_b200.update import PackedUpdateWeights
     up, net, imap, corr, ii, jj, kk, plan_kk, plan_ij, Np, pairs = _problem(8, 96, 0)
     packed = PackedUpdateWeights(up, torch.float16, 896)
@@ -86,6 +103,7 @@ def test_gru_mma_is_deterministic():
         for _ in range(6):
             n, (d, w, _) = up.forward_mma(net, imap, kk, corr, plan_kk, plan_ij, Np, pairs, packed)
             outs.append((n.clone(), d.clone(), w.clone()))
+            torch.cuda.synchronize()
     torch.cuda.synchronize()
     for o in outs[1:]:
         assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]) and torch.equal(o[2], outs[0][2])

@@ -17,7 +17,7 @@ def test_update_loop_three_iterations_equals_composition():
     from devo_b200 import altcorr, fastba, projective_ops as pops, lietorch as lt
     from test_gpu_engine import _build
     op, up, P, C, imap = _build(seed=11)
-    net = op.net.clone()
+    net = op.get_net().clone()
     poses, patches = op.poses.clone(), op.patches.clone()
     ii, jj, kk = op.ii, op.jj, op.kk
     lm = torch.as_tensor([1e-4], device="cuda")
@@ -29,7 +29,6 @@ def test_update_loop_three_iterations_equals_composition():
                 c2 = altcorr.corr(C["gmap"].cuda(), C["pyramid"][1].cuda(), coords / 4, kk, jj, 3)
                 corr = torch.stack([c1, c2], -1).view(1, len(kk), -1)
                 net, (delta, weight, _) = up(net, imap[None][:, kk], corr, None, ii, jj, kk)
-            net = net.half()
             target = coords[..., 1, 1] + delta.float()
             fastba.BA(poses, patches, op.intrinsics, target, weight.float(), lm, ii, jj, kk, 1, op.Nf, 2)
             op.step()
@@ -38,7 +37,7 @@ def test_update_loop_three_iterations_equals_composition():
     # for a single step (tests/test_gpu_engine.py)
     assert torch.allclose(op.poses, poses, atol=2e-3), (op.poses - poses).abs().max().item()
     assert torch.allclose(op.patches, patches, atol=2e-2), (op.patches - patches).abs().max().item()
-    assert (op.net.float() - net.float()).abs().mean().item() < 2e-2
+    assert (op.get_net() - net.float()).abs().mean().item() < 2e-2
 
 
 def _training_graph(dtype, seed=3):

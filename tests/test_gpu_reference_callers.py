@@ -48,6 +48,7 @@ def test_reference_altcorr_backward_and_patchify_on_this_library():
     ns = ref_callers.load()
     Pm = corr_problem(n_frames=3, patches_per_frame=16, seed=5, dtype=torch.float32, H4=48, W4=64)
     grads = {}
+    xy = torch.stack([torch.randint(1, 62, (3, 20)), torch.randint(1, 46, (3, 20))], -1).float().cuda()
     for kind in ("ref_ext", "ours"):
         ref_callers.use_backend(kind)
         g = Pm["gmap"].cuda().requires_grad_(True)
@@ -57,7 +58,6 @@ def test_reference_altcorr_backward_and_patchify_on_this_library():
         noise = torch.randn(out.shape, generator=torch.Generator().manual_seed(0)).cuda()
         (out * noise).sum().backward()
         net = Pm["pyramid"][0][0].cuda()
-        xy = torch.stack([torch.randint(1, 62, (3, 20)), torch.randint(1, 46, (3, 20))], -1).float().cuda()
         grads[kind] = (g.grad.clone(), f.grad.clone(), ns.altcorr.patchify(net, xy, 1), ns.altcorr.patchify(net, xy + 0.25, 1))
     ref_callers.use_backend("ours")
     assert _rel(grads["ours"][0], grads["ref_ext"][0]) <= 1e-4

@@ -20,7 +20,7 @@ def main():
     ii, jj, kk = [t.cuda() for t in fully_connected_graph(nf, m)]
     E, Np = ii.numel(), nf * m
     up = Update(3).cuda().eval()
-    net = (0.5 * torch.randn(1, E, 384, device="cuda")).half()
+    net = 0.5 * torch.randn(1, E, 384, device="cuda")
     imap = (0.25 * torch.randn(1, Np, 384, device="cuda")).half()
     corr = torch.zeros(E, 896, device="cuda", dtype=torch.float16)
     corr[:, :882] = torch.randn(E, 882, device="cuda").half()
@@ -43,21 +43,24 @@ def main():
         return a.elapsed_time(b) / n * 1e3
 
     with torch.no_grad():
-        t_mma = timeit(lambda: up.forward_mma(net, imap, kk, corr, plan_kk, plan_ij, Np, nf * nf, packed))
-        t_cub = timeit(lambda: up.forward_fused(net, ctx, corr.view(1, E, 896), plan_kk, plan_ij, Np, nf * nf, fc))
+        from devo_b200.update import GruState
+        st = GruState(E, "cuda").set(net)
+        t_mma = timeit(lambda: up.forward_mma(None, imap, kk, corr, plan_kk, plan_ij, Np, nf * nf, packed, state=st))
+        net16 = net.half()
+        t_cub = timeit(lambda: up.forward_fused(net16, ctx, corr.view(1, E, 896), plan_kk, plan_ij, Np, nf * nf, fc))
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            up.forward_mma(net, imap, kk, corr, plan_kk, plan_ij, Np, nf * nf, packed)
+            up.forward_mma(None, imap, kk, corr, plan_kk, plan_ij, Np, nf * nf, packed, state=st)
         t_graph = timeit(g.replay)
         g2 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g2):
-            up.forward_fused(net, ctx, corr.view(1, E, 896), plan_kk, plan_ij, Np, nf * nf, fc)
+            up.forward_fused(net16, ctx, corr.view(1, E, 896), plan_kk, plan_ij, Np, nf * nf, fc)
         t_cub_graph = timeit(g2.replay)
         print("forward_mma %.1f us (graph replay %.1f us)   cuBLAS+glue path %.1f us eager, %.1f us graph replay" % (t_mma, t_graph, t_cub, t_cub_graph))
         L = _lib.lib()
         L.devo_gru_debug_timing.argtypes = [ctypes.c_void_p]
         L.devo_gru_debug_timing(None)
-        up.forward_mma(net, imap, kk, corr, plan_kk, plan_ij, Np, nf * nf, packed)
+        up.forward_mma(None, imap, kk, corr, plan_kk, plan_ij, Np, nf * nf, packed, state=st)
         torch.cuda.synchronize()
         buf = (ctypes.c_longlong * (16 * 48))()
         L.devo_gru_debug_timing(buf)
@@ -67,10 +70,12 @@ def main():
         s = [buf[48 * k + q] for q in range(48)]
         t0 = s[0]
         rel = lambda q: (s[q] - t0) / 1e3 if s[q] else float("nan")
-        line = "%-12s setup %.1f pro %.1f |" % (nm, rel(1), rel(2))
+        # per layer: MMA issue start - issue end | epilogue: N-tile 0 ready, N-tile 1 ready, chunk loop done, layer done
+        line = "%-16s setup %.1f pro %.1f |" % (nm, rel(1), rel(2))
         for l in range(n):
-            line += " L%d mma %.1f-%.1f epi %.1f-%.1f |" % (l, rel(4 + 4 * l), rel(5 + 4 * l), rel(6 + 4 * l), rel(7 + 4 * l))
-        line += " end %.1f us  [L0 epi: loop %.1f tail %.1f fences %.1f bar %.1f]" % (rel(3), rel(40), rel(41), rel(42), rel(43))
+            b = 4 + 6 * l
+            line += " L%d mma %.1f-%.1f epi %.1f/%.1f loop %.1f end %.1f |" % (l, rel(b), rel(b + 1), rel(b + 2), rel(b + 3), rel(b + 4), rel(b + 5))
+        line += " exit %.1f us" % rel(3)
         print(line)
 
 
