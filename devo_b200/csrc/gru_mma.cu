@@ -6,7 +6,9 @@
 // owns a tile of 128 edges -- 64 WHOLE ROWS per CTA -- and walks it through a chain of layers without leaving the SMs:
 //
 //   MMA        : tcgen05.mma.cta_group::2.kind::f16, M = 128 (64 rows per CTA), N = 192 (two N-tiles per layer), K = 16,
-//                issued by one elected lane of the LEADER CTA for the pair.  Measured (tools/umma_probe.cu,
+//                issued by elected lanes of the LEADER CTA for the pair -- ONE ISSUING WARP PER N-TILE, each with its own
+//                weight ring: a 57-cycle MMA is shorter than the ~75-130 cycles one thread needs to wait for a stage,
+//                build descriptors and issue it (measured: a single issuer ran the tensor pipe at 40 %).  Measured (tools/umma_probe.cu,
 //                profiles/r02_umma_probe.txt): 48 cycles per instruction = 4092 MAC/cycle/SM, i.e. full rate, while
 //                each CTA stages only HALF of every weight block (the tensor cores read the B operand from both CTAs'
 //                shared memory).  Every output row is local to one CTA: no activation exchange between the CTAs,
@@ -63,12 +65,14 @@ constexpr int kKB = kD / 64;               // 6 K-blocks
 constexpr int kABuf = kKB * kABlk;         // 48 KB
 constexpr int kASlots = 2 * kKB;           // both buffers as a ring for the streamed first layer
 constexpr int kWStage = kNTc * 128;        // this CTA's half of a [192 x 64] weight block: 96 rows x 64 halfs = 12 KB
-constexpr int kWStages = 8;
+constexpr int kRing = 4;                   // weight stages per N-tile ring (each N-tile has its own MMA-issuing warp)
+constexpr int kWStages = 2 * kRing;
 constexpr int kParts = 4;                  // epilogue warps per TMEM lane quarter: each takes 24 of the 96 columns
 constexpr int kEpiWarps = 4 * kParts;
 constexpr int kEpiThreads = 32 * kEpiWarps;
-constexpr int kFirstEpiWarp = 2;           // warp 0: TMA producer, warp 1: MMA issuer (leader CTA) + TMEM allocation
-constexpr int kThreads = 32 * kFirstEpiWarp + kEpiThreads;
+constexpr int kFirstEpiWarp = 2;           // warp 0: TMA producer, warp 1: MMA issuer of N-tile 0 (leader CTA) + TMEM allocation
+constexpr int kMma1Warp = kFirstEpiWarp + kEpiWarps;      // the last warp: MMA issuer of N-tile 1 (leader CTA)
+constexpr int kThreads = 32 * (kMma1Warp + 1);
 constexpr int kMaxLayers = 7;
 constexpr int kChunks = kD / 8;            // 16-byte chunks per row (48)
 constexpr int kCol4 = kD / 4;              // float4 groups per row (96)
@@ -95,11 +99,6 @@ static_assert(kBarProReady < 56, "barrier slots");
 enum { PRO_NONE = 0, PRO_GATHER = 1, PRO_CAST = 2 };
 enum { EPI_RELU_A = 0, EPI_LNRELU_A = 1, EPI_ADD3_LN = 2, EPI_RESID = 3, EPI_STORE_A = 4, EPI_STORE_B = 5,
        EPI_GATE = 6, EPI_GATED_LN = 7, EPI_GATED_HEADS = 8, EPI_RESID_A = 9, EPI_RESID_LN_A = 10 };
-// MMA issue order of a layer (the weight producers follow the same order)
-enum { ORD_SIMPLE = 0,     // N-tile outer, K-block inner
-       ORD_STREAM = 1,     // K-block outer, N-tile inner (layer 0 with a TMA-streamed A operand: every K-block is staged once)
-       ORD_WAVE = 2 };     // (h0,kb0-2) (h1,kb0-2) (h0,kb3-5) (h1,kb3-5): the first half only needs N-tile 0 of the previous epilogue
-
 __host__ __device__ constexpr bool epi_writes_a(int e) {
   return e == EPI_RELU_A || e == EPI_LNRELU_A || e == EPI_GATED_LN || e == EPI_RESID_A || e == EPI_RESID_LN_A;
 }
@@ -188,6 +187,7 @@ __device__ __forceinline__ void stamp(long long* dbg, int slot) {
     long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     dbg[slot] = t;
+    dbg[16 * 48 + slot] = clock64();        // SM cycles next to wall time: separates clock ramps from pipeline stalls
   }
 }
 // sigmoid in 4 instructions (FMUL, MUFU.EX2, FADD, MUFU.RCP); the result is rounded to half right away
@@ -199,17 +199,20 @@ __device__ __forceinline__ float sigmoidf_(float x) {
 }
 
 // ---- pair-scope synchronisation helpers ---------------------------------------------------------------------------
-// arrive on an mbarrier of the LEADER CTA (address already mapped with mapa); release at cluster scope so that the
-// leader's MMA warp, which acquires at cluster scope, sees this CTA's shared-memory / TMEM traffic as complete
+// arrive on an mbarrier of the LEADER CTA (address already mapped with mapa).  Default (.release.cta) semantics, like
+// CUTLASS's ClusterBarrier::arrive(cta_id): what the leader's MMA warp consumes is shared memory read by the tensor cores
+// through the async proxy (ordered by the writer's fence.proxy.async) and TMEM (ordered by tcgen05.fence).  A
+// .release.cluster arrive compiles to MEMBAR.ALL.GPU and waits for every outstanding GLOBAL store of the thread (measured:
+// the top stall of the epilogue warps), a cluster-scope acquire on the waiting side to a CCTL.IVALL per wait.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_cluster) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred P1;\n\t"
       "LAB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
       "@P1 bra DONE;\n\t"
       "bra LAB_WAIT;\n\t"
       "DONE:\n\t"
@@ -253,18 +256,6 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 __device__ __forceinline__ void epi_bar_all() { asm volatile("bar.sync 3, %0;" ::"n"(kEpiThreads) : "memory"); }
 // the 8 warps that share the rows of one row half (LayerNorm statistics, head partials)
 __device__ __forceinline__ void epi_bar_half(int rowhalf) { asm volatile("bar.sync %0, %1;" ::"r"(1 + rowhalf), "n"(kEpiThreads / 2) : "memory"); }
-
-// (N-tile, K-block) of the i-th weight block of a layer
-__device__ __forceinline__ void sched(int ord, int nkb, int i, int& h, int& kb) {
-  if (ord == ORD_WAVE) { const int g = i / 3; h = g & 1; kb = (g >> 1) * 3 + (i - g * 3); }
-  else if (ord == ORD_STREAM) { kb = i >> 1; h = i & 1; }
-  else { h = i / nkb; kb = i - h * nkb; }
-}
-template <typename T>
-__device__ __forceinline__ int layer_order(const GruProg<T>& P, int l) {
-  if (l == 0) return P.stream_a0 ? ORD_STREAM : ORD_SIMPLE;
-  return epi_writes_a(P.epi[l - 1]) ? ORD_WAVE : ORD_SIMPLE;
-}
 
 // ---- the epilogue role ---------------------------------------------------------------------------------------------
 template <typename T>
@@ -457,6 +448,8 @@ struct Epi {
       const int h = i / kCPT, j = i - h * kCPT;
       const int c = chunk_of(h, j);                         // global 16-byte chunk index (8 columns)
       if (j == 0) {
+        // a streamed layer's epilogue overwrites A ring slots: BOTH tiles' MMAs must be done before the first store
+        if (l == 0 && P.stream_a0 && h == 0) mbar_wait(acc_full() + set * 2 + 1, accph);
         mbar_wait(acc_full() + set * 2 + h, accph);           // N-tile h of this layer is complete in TMEM (both CTAs)
         tc_fence_after();
         if (et == 0) stamp(P.dbg, 6 + 6 * l + h);
@@ -683,7 +676,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
   if (threadIdx.x == 0) stamp(P.dbg, 0);
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWStages; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    for (int s = 0; s < kASlots; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < kASlots; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 2); }     // a_empty: both MMA warps
     for (int s = 0; s < 4; s++) { mbar_init(&acc_full[s], 1); mbar_init(&a_ready[s], 2 * kEpiWarps); }
     mbar_init(&epi_done[0], 2 * kEpiWarps);
     mbar_init(&epi_done[1], 2 * kEpiWarps);
@@ -731,41 +724,54 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
     // Completion bytes of BOTH CTAs are credited to the leader's barrier; the leader arms it for the pair.
     if (lane == 0) { prefetch_tensormap(&tm_w); if (P.use_w0) prefetch_tensormap(&tm_w0); if (P.stream_a0) prefetch_tensormap(&tm_a); }
     if (P.stream_a0) pdl_wait();                    // the streamed A operand is the previous kernel's output
-    uint32_t stage = 0, phase = 0;
+    // one ring of kRing stages per N-tile (stage index h * kRing + st[h]); K-blocks in ascending order for both tiles
+    uint32_t st0 = 0, st1 = 0, ph0 = 0, ph1 = 0;
     for (int l = 0; l < P.n_layers; l++) {
       const int nkb = (l == 0) ? P.kblocks0 : kKB;
-      const int ord = layer_order(P, l);
       const CUtensorMap* wm = (l == 0 && P.use_w0) ? &tm_w0 : &tm_w;
-      for (int i = 0; i < 2 * nkb; i++) {
-        int h, kb;
-        sched(ord, nkb, i, h, kb);
-        if (l == 0 && P.stream_a0 && h == 0) {
+      const bool streamed = (l == 0 && P.stream_a0);
+      for (int kb = 0; kb < nkb; kb++) {
+        if (streamed) {
           const int slot = kb % kASlots, use = kb / kASlots;
           mbar_wait(&a_empty[slot], (uint32_t)(use & 1) ^ 1u);
           if (rank == 0) mbar_arrive_expect_tx_elect(smem_u32(&a_full[slot]), 2 * kABlk);
           tma_load_2d_pair_elect(smem_u32(As) + slot * kABlk, &tm_a, mapa(smem_u32(&a_full[slot]), 0u), kb * 64, row0);
         }
-        mbar_wait(&w_empty[stage], phase ^ 1u);
-        if (rank == 0) mbar_arrive_expect_tx_elect(smem_u32(&w_full[stage]), 2 * kWStage);
-        tma_load_2d_pair_elect(smem_u32(Ws) + stage * kWStage, wm, mapa(smem_u32(&w_full[stage]), 0u), kb * 64,
-                               P.w_row[l] + h * kNT + rank * kNTc);
-        if (++stage == kWStages) { stage = 0; phase ^= 1u; }
+        {
+          mbar_wait(&w_empty[st0], ph0 ^ 1u);
+          if (rank == 0) mbar_arrive_expect_tx_elect(smem_u32(&w_full[st0]), 2 * kWStage);
+          tma_load_2d_pair_elect(smem_u32(Ws) + st0 * kWStage, wm, mapa(smem_u32(&w_full[st0]), 0u), kb * 64,
+                                 P.w_row[l] + rank * kNTc);
+          if (++st0 == kRing) { st0 = 0; ph0 ^= 1u; }
+        }
+        {
+          mbar_wait(&w_empty[kRing + st1], ph1 ^ 1u);
+          if (rank == 0) mbar_arrive_expect_tx_elect(smem_u32(&w_full[kRing + st1]), 2 * kWStage);
+          tma_load_2d_pair_elect(smem_u32(Ws) + (kRing + st1) * kWStage, wm, mapa(smem_u32(&w_full[kRing + st1]), 0u), kb * 64,
+                                 P.w_row[l] + kNT + rank * kNTc);
+          if (++st1 == kRing) { st1 = 0; ph1 ^= 1u; }
+        }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == kMma1Warp) {
     if (rank == 0) {
-      // =========================== MMA issuer (leader CTA; one elected lane issues for the pair) ====================
+      // =========================== MMA issuers (leader CTA): warp 1 owns N-tile 0, the last warp N-tile 1; one elected
+      // lane issues for the pair.  The two instruction streams touch different accumulators and different weight rings;
+      // they share the A operand and the barriers that guard it.
+      const int h = (warp == 1) ? 0 : 1;
       const uint32_t fmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kNT >> 3) << 17) | ((128u >> 4) << 24);
       const uint64_t ad0 = umma_desc_sw128(smem_u32(As));
-      const uint64_t bd0 = umma_desc_sw128(smem_u32(Ws));
+      const uint64_t bd0 = umma_desc_sw128(smem_u32(Ws) + h * kRing * kWStage);
+      uint64_t* wf = w_full + h * kRing;
+      uint64_t* we = w_empty + h * kRing;
       uint32_t stage = 0, phase = 0;
       int cur = P.stream_a0 ? 1 : 0;            // A buffer read by the current layer (a streamed layer 0 uses both as a ring)
       int na = 0;                               // A-writing epilogues before this layer
       for (int l = 0; l < P.n_layers; l++) {
         const int nkb = (l == 0) ? P.kblocks0 : kKB;
-        const int ord = layer_order(P, l);
         const bool streamed = (l == 0 && P.stream_a0);
+        const bool wave = (l > 0) && epi_writes_a(P.epi[l - 1]);
         const int set = l & 1;
         if (l == 0) {
           if (has_pro) { mbar_wait_cluster(pro_ready, 0u); tc_fence_after(); }
@@ -773,46 +779,38 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
           mbar_wait_cluster(&epi_done[set], (uint32_t)(((l - 2) >> 1) & 1));    // TMEM set free again
           tc_fence_after();
         }
-        if (lane == 0) stamp(P.dbg, 4 + 6 * l);
+        if (lane == 0 && h == 0) stamp(P.dbg, 4 + 6 * l);
         const uint32_t abase = streamed ? 0u : (uint32_t)(cur * (kABuf >> 4));
-        uint32_t fresh = 3u;                    // bit h: the next MMA of N-tile h is its first (overwrites the accumulator)
-        for (int i = 0; i < 2 * nkb; i++) {
-          int h, kb;
-          sched(ord, nkb, i, h, kb);
-          if (ord == ORD_WAVE && (i == 0 || i == 6)) {
-            // K-blocks 0-2 come from N-tile 0 of the previous epilogue, 3-5 from N-tile 1
-            const int pa = na - 1;
-            mbar_wait_cluster(&a_ready[(pa & 1) * 2 + (i ? 1 : 0)], (uint32_t)((pa >> 1) & 1));
+        const uint32_t tacc = tmem_base + (uint32_t)(set * kNT + h * kNTc);
+        const int pa = na - 1;
+        for (int kb = 0; kb < nkb; kb++) {
+          if (wave && (kb == 0 || kb == kKB / 2)) {
+            // K-blocks 0-2 are written by N-tile 0 of the previous epilogue, 3-5 by N-tile 1: the first half of this layer
+            // runs under the second half of that epilogue
+            mbar_wait_cluster(&a_ready[(pa & 1) * 2 + (kb ? 1 : 0)], (uint32_t)((pa >> 1) & 1));
             tc_fence_after();
           }
           const int slot = streamed ? kb % kASlots : kb;
-          if (streamed && h == 0) { mbar_wait_cluster(&a_full[slot], (uint32_t)((kb / kASlots) & 1)); tc_fence_after(); }
-          mbar_wait_cluster(&w_full[stage], phase);
+          // w_full / a_full are completed by TMA transaction bytes
+          if (streamed) { mbar_wait(&a_full[slot], (uint32_t)((kb / kASlots) & 1)); tc_fence_after(); }
+          mbar_wait(&wf[stage], phase);
           tc_fence_after();
           const uint64_t ad = ad0 + (uint64_t)(abase + (uint32_t)slot * (kABlk >> 4));
           const uint64_t bd = bd0 + (uint64_t)(stage * (kWStage >> 4));
-          const uint32_t tacc = tmem_base + (uint32_t)(set * kNT + h * kNTc);
 #pragma unroll
           for (int k4 = 0; k4 < 4; k4++)
-            tc_mma2_f16_elect(tacc, ad + 2 * k4, bd + 2 * k4, idesc, (((fresh >> h) & 1u) && k4 == 0) ? 0u : 1u);
-          fresh &= ~(1u << h);
-          tc_commit2_elect(smem_u32(&w_empty[stage]));
-          if (++stage == kWStages) { stage = 0; phase ^= 1u; }
-          if (streamed && h == 1) tc_commit2_elect(smem_u32(&a_empty[slot]));
-          // N-tile complete?  A streamed layer publishes both tiles only after its LAST MMA: its epilogue overwrites
-          // ring slots that the other tile's final K-block still reads.
-          if (ord == ORD_STREAM) {
-            if (i == 2 * nkb - 1) { tc_commit2_elect(smem_u32(&acc_full[set * 2 + 0])); tc_commit2_elect(smem_u32(&acc_full[set * 2 + 1])); }
-          } else if (kb == nkb - 1) {
-            tc_commit2_elect(smem_u32(&acc_full[set * 2 + h]));
-          }
+            tc_mma2_f16_elect(tacc, ad + 2 * k4, bd + 2 * k4, idesc, (kb == 0 && k4 == 0) ? 0u : 1u);
+          tc_commit2_elect(smem_u32(&we[stage]));
+          if (++stage == kRing) { stage = 0; phase ^= 1u; }
+          if (streamed) tc_commit2_elect(smem_u32(&a_empty[slot]));
         }
+        tc_commit2_elect(smem_u32(&acc_full[set * 2 + h]));
         if (epi_writes_a(P.epi[l])) { cur ^= 1; na++; }
-        if (lane == 0) stamp(P.dbg, 5 + 6 * l);
+        if (lane == 0 && h == 0) stamp(P.dbg, 5 + 6 * l);
       }
       __syncwarp();
     }
-  } else {
+  } else if (warp >= kFirstEpiWarp) {
     // =========================== prologue + epilogues (struct Epi) =============================================
     Epi<T> e(P);
     e.tm_oa = &tm_oa; e.tm_ob = &tm_ob;
@@ -923,7 +921,7 @@ static int make_map_2d(CUtensorMap* m, int dtype, const void* ptr, uint64_t rows
 constexpr size_t kSmemBytes = 1024 + (size_t)kOffEnd + 64;
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
-static long long* g_dbg = nullptr;     // 16 launches x 48 stamps, allocated when DEVO_GRU_TIMING is set
+static long long* g_dbg = nullptr;     // 16 launches x 48 stamps (ns), then the same in SM cycles
 static int g_dbg_launch = 0;
 
 template <typename T>
@@ -1109,11 +1107,11 @@ int devo_gru_state_gather(const float* src, int src_layout, int src_rows, const 
 // debug (tools/gru_timing.py): enable / read back the %globaltimer stamps of CTA 0 of the last 16 launches
 int devo_gru_debug_timing(long long* host_out) {
   if (!g_dbg) {
-    if (cudaMalloc(&g_dbg, 16 * 48 * sizeof(long long)) != cudaSuccess) return -1;
-    cudaMemset(g_dbg, 0, 16 * 48 * sizeof(long long));
+    if (cudaMalloc(&g_dbg, 2 * 16 * 48 * sizeof(long long)) != cudaSuccess) return -1;
+    cudaMemset(g_dbg, 0, 2 * 16 * 48 * sizeof(long long));
   }
   g_dbg_launch = 0;
-  if (host_out) return (int)cudaMemcpy(host_out, g_dbg, 16 * 48 * sizeof(long long), cudaMemcpyDeviceToHost);
+  if (host_out) return (int)cudaMemcpy(host_out, g_dbg, 2 * 16 * 48 * sizeof(long long), cudaMemcpyDeviceToHost);
   return 0;
 }
 

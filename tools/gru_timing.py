@@ -16,7 +16,7 @@ def main():
     from devo_b200.update import FrozenCast, PackedUpdateWeights, Update
     from problems import fully_connected_graph
     torch.manual_seed(0)
-    nf, m = 8, 96
+    nf, m = int(os.environ.get('GRU_NF', 8)), int(os.environ.get('GRU_M', 96))
     ii, jj, kk = [t.cuda() for t in fully_connected_graph(nf, m)]
     E, Np = ii.numel(), nf * m
     up = Update(3).cuda().eval()
@@ -60,14 +60,19 @@ def main():
         L = _lib.lib()
         L.devo_gru_debug_timing.argtypes = [ctypes.c_void_p]
         L.devo_gru_debug_timing(None)
-        up.forward_mma(None, imap, kk, corr, plan_kk, plan_ij, Np, nf * nf, packed, state=st)
+        for _ in range(int(os.environ.get("GRU_REPS", 32))):      # the stamps of the LAST update survive (16-launch ring): clocks are up by then
+            up.forward_mma(None, imap, kk, corr, plan_kk, plan_ij, Np, nf * nf, packed, state=st)
         torch.cuda.synchronize()
-        buf = (ctypes.c_longlong * (16 * 48))()
+        buf = (ctypes.c_longlong * (2 * 16 * 48))()
         L.devo_gru_debug_timing(buf)
     names = ["corr+norm", "c1", "c2", "agg_kk g,f", "h_kk+agg_ij g,f", "h_ij+gru+heads"]
     nl = [3, 2, 2, 2, 3, 7]
+    reps = int(os.environ.get("GRU_REPS", 32))
     for k, (nm, n) in enumerate(zip(names, nl)):
-        s = [buf[48 * k + q] for q in range(48)]
+        k16 = (6 * (reps - 1) + k) % 16
+        s = [buf[48 * k16 + q] for q in range(48)]
+        cyc = [buf[16 * 48 + 48 * k16 + q] for q in range(48)]
+        mhz = (cyc[3] - cyc[0]) / max(s[3] - s[0], 1) * 1e3
         t0 = s[0]
         rel = lambda q: (s[q] - t0) / 1e3 if s[q] else float("nan")
         # per layer: MMA issue start - issue end | epilogue: N-tile 0 ready, N-tile 1 ready, chunk loop done, layer done
@@ -75,8 +80,10 @@ def main():
         for l in range(n):
             b = 4 + 6 * l
             line += " L%d mma %.1f-%.1f epi %.1f/%.1f loop %.1f end %.1f |" % (l, rel(b), rel(b + 1), rel(b + 2), rel(b + 3), rel(b + 4), rel(b + 5))
-        line += " exit %.1f us" % rel(3)
+        line += " exit %.1f us  (SM clock %.0f MHz)" % (rel(3), mhz)
         print(line)
+        if n == 2 and s[20]:
+            print("    L0 blocks: data ready -> issued (us): " + " ".join("%.2f>%.2f" % (rel(20 + b), rel(32 + b)) for b in range(12)))
 
 
 if __name__ == "__main__":

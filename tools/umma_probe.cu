@@ -38,28 +38,37 @@ __device__ __forceinline__ void commit_all(uint32_t bar) {
   }
 }
 
+constexpr int kRot = 4;     // distinct operand buffers the rate loop rotates through (defeats any operand reuse inside the MMA unit)
+
 template <int CG, int M, int N>
-__global__ void __launch_bounds__(128, 1) probe(const __half* A, const __half* B, float* Draw, int iters, long long* cyc) {
+__global__ void __launch_bounds__(640, 1) probe(const __half* A, const __half* B, float* Draw, int iters, long long* cyc, int rot) {
   constexpr int RA = M / CG, RB = N / CG;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* As = base;
-  unsigned char* Bs = base + RA * 128;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(Bs + RB * 128);
-  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 2);
+  unsigned char* Bs = base + kRot * RA * 128;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(Bs + kRot * RB * 128);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 4);
+  volatile int* done = reinterpret_cast<volatile int*>(bar + 6);
+  unsigned char* scratch = reinterpret_cast<unsigned char*>(bar + 8);     // 32 KB written by the 'store' warps
   const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // K-major SWIZZLE_128B: 16-byte chunk c of row r at r*128 + ((c ^ (r & 7)) << 4)
   for (int q = threadIdx.x; q < RA * 8; q += blockDim.x) {
     const int r = q >> 3, c = q & 7;
-    *reinterpret_cast<uint4*>(As + r * 128 + ((c ^ (r & 7)) << 4)) = *reinterpret_cast<const uint4*>(A + (size_t)(rank * RA + r) * 64 + c * 8);
+    for (int b = 0; b < kRot; b++)
+      *reinterpret_cast<uint4*>(As + b * RA * 128 + r * 128 + ((c ^ (r & 7)) << 4)) = *reinterpret_cast<const uint4*>(A + (size_t)(rank * RA + r) * 64 + c * 8);
   }
   for (int q = threadIdx.x; q < RB * 8; q += blockDim.x) {
     const int r = q >> 3, c = q & 7;
-    *reinterpret_cast<uint4*>(Bs + r * 128 + ((c ^ (r & 7)) << 4)) = *reinterpret_cast<const uint4*>(B + (size_t)(rank * RB + r) * 64 + c * 8);
+    for (int b = 0; b < kRot; b++)
+      *reinterpret_cast<uint4*>(Bs + b * RB * 128 + r * 128 + ((c ^ (r & 7)) << 4)) = *reinterpret_cast<const uint4*>(B + (size_t)(rank * RB + r) * 64 + c * 8);
   }
   if (threadIdx.x == 0) {
+    *done = 0;
     mbar_init(bar, 1);
+    mbar_init(bar + 1, 1);
+    mbar_init(bar + 2, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -88,7 +97,7 @@ __global__ void __launch_bounds__(128, 1) probe(const __half* A, const __half* B
   tc_fence_after();
   // dump this warp's 32 lanes x 512 columns... only the first NC columns are meaningful
   constexpr int NC = (CG == 2 && M == 128) ? N / 2 : N;
-  for (int c0 = 0; c0 < NC; c0 += 8) {
+  for (int c0 = 0; c0 < NC && warp < 4; c0 += 8) {
     uint32_t v[8];
     tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
     tmem_wait_ld();
@@ -101,12 +110,35 @@ __global__ void __launch_bounds__(128, 1) probe(const __half* A, const __half* B
   // ---- rate: iters x 4 MMAs back to back
   if (rank == 0 && threadIdx.x == 0) {
     const long long t0 = clock64();
-    for (int it = 0; it < iters; it++)
-      for (int k4 = 0; k4 < 4; k4++) mma_issue<CG>(tmem, ad + 2 * k4, bd + 2 * k4, idesc, 1u);
+    for (int it = 0; it < iters; it++) {
+      const int b = (rot & 1) ? (it % kRot) : 0;
+      const uint64_t a2 = ad + (uint64_t)(b * ((RA * 128) >> 4)), b2 = bd + (uint64_t)(b * ((RB * 128) >> 4));
+      for (int k4 = 0; k4 < 4; k4++) mma_issue<CG>(tmem, a2 + 2 * k4, b2 + 2 * k4, idesc, 1u);
+      if (rot & 2) commit_all<CG>(smem_u32(bar + 1));      // a stage-release commit after every 4 MMAs, like a GEMM main loop
+    }
     commit_all<CG>(smem_u32(bar));
     mbar_wait(bar, phase);
     const long long t1 = clock64();
     cyc[blockIdx.x / CG] = t1 - t0;
+    *done = 1;
+  } else if (threadIdx.x == 0) {
+    mbar_wait(bar, phase);      // the peer CTA: the multicast commit lands here too; release this CTA's background warps
+    *done = 1;
+  } else if (warp >= 4 && warp < 8 && (rot & 8)) {
+    // background shared-memory writes (what a TMA weight stream does to the banks): 4 warps x 512 B per instruction
+    uint4 v = make_uint4(threadIdx.x, 1, 2, 3);
+    int o = 0;
+    while (!*done) {
+      *reinterpret_cast<uint4*>(scratch + (warp - 4) * 8192 + ((o * 512 + lane * 16) & 8191)) = v;
+      o++;
+    }
+  } else if (warp >= 8 && (rot & 4)) {
+    // pollers: warps spinning on an mbarrier phase that never completes (what idle epilogue warps do)
+    uint32_t ok = 0;
+    while (!*done && !ok) {
+      asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
+                   : "=r"(ok) : "r"(smem_u32(bar + 2)), "r"(0u) : "memory");
+    }
   } else {
     mbar_wait(bar, phase);
   }
@@ -121,7 +153,7 @@ __global__ void __launch_bounds__(128, 1) probe(const __half* A, const __half* B
 }
 
 template <int CG, int M, int N>
-static int run(const char* name, int nclusters) {
+static int run(const char* name, int nclusters, int rot) {
   std::vector<__half> hA((size_t)M * 64), hB((size_t)N * 64);
   for (int r = 0; r < M; r++) for (int k = 0; k < 64; k++) hA[(size_t)r * 64 + k] = __float2half((float)((r * 7 + k * 3) % 5 - 2));
   for (int n = 0; n < N; n++) for (int k = 0; k < 64; k++) hB[(size_t)n * 64 + k] = __float2half((float)((n * 5 + k) % 7 - 3));
@@ -131,16 +163,16 @@ static int run(const char* name, int nclusters) {
   CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemset(dD, 0, (size_t)CG * 128 * 512 * 4));
-  const size_t smem = 1024 + (size_t)(M / CG + N / CG) * 128 + 64;
+  const size_t smem = 1024 + (size_t)kRot * (M / CG + N / CG) * 128 + 128 + 32768;
   CK(cudaFuncSetAttribute(probe<CG, M, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int iters = 2000;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(nclusters * CG); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem;
+  cfg.gridDim = dim3(nclusters * CG); cfg.blockDim = dim3(640); cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  CK(cudaLaunchKernelEx(&cfg, probe<CG, M, N>, (const __half*)dA, (const __half*)dB, dD, iters, dC));
+  CK(cudaLaunchKernelEx(&cfg, probe<CG, M, N>, (const __half*)dA, (const __half*)dB, dD, iters, dC, rot));
   CK(cudaDeviceSynchronize());
   std::vector<float> hD((size_t)CG * 128 * 512);
   std::vector<long long> hC(256);
@@ -161,7 +193,7 @@ static int run(const char* name, int nclusters) {
   long long cmin = hC[0], cmax = hC[0];
   for (int i = 0; i < nclusters; i++) { if (hC[i] < cmin) cmin = hC[i]; if (hC[i] > cmax) cmax = hC[i]; }
   const double per = (double)cmin / (iters * 4.0);
-  printf("%-22s clusters %3d  layout %s (%d bad)  cycles/MMA(K=16) min %.1f max %.1f  => %.0f MAC/cyc/SM\n", name, nclusters,
+  printf("%-14s rot %d clusters %3d  layout %s (%d bad)  cycles/MMA(K=16) min %.1f max %.1f  => %.0f MAC/cyc/SM\n", name, rot, nclusters,
          bad ? "MISMATCH" : "ok", bad, per, (double)cmax / (iters * 4.0), (double)M * N * 16 / per / CG);
   cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dC);
   return bad;
@@ -169,17 +201,15 @@ static int run(const char* name, int nclusters) {
 
 int main() {
   int bad = 0;
-  for (int nc : {1, 48, 74}) {
-    bad += run<1, 128, 128>("cg1 M128 N128", nc);
-    bad += run<1, 128, 192>("cg1 M128 N192", nc);
-    bad += run<1, 128, 256>("cg1 M128 N256", nc);
-    bad += run<2, 128, 64>("cg2 M128 N64", nc);
-    bad += run<2, 128, 128>("cg2 M128 N128", nc);
-    bad += run<2, 128, 192>("cg2 M128 N192", nc);
-    bad += run<2, 128, 256>("cg2 M128 N256", nc);
-    bad += run<2, 256, 128>("cg2 M256 N128", nc);
-    bad += run<2, 256, 256>("cg2 M256 N256", nc);
-  }
+  // rot bits: 1 rotate operands, 2 commit per 4 MMAs, 4 sixteen polling warps, 8 four warps streaming st.shared
+  for (int rot : {3, 7, 11, 15})
+    for (int nc : {1}) {
+      bad += run<1, 128, 192>("cg1 M128 N192", nc, rot);
+      bad += run<2, 128, 192>("cg2 M128 N192", nc, rot);
+      bad += run<2, 128, 256>("cg2 M128 N256", nc, rot);
+      bad += run<2, 256, 192>("cg2 M256 N192", nc, rot);
+      bad += run<2, 256, 256>("cg2 M256 N256", nc, rot);
+    }
   printf(bad ? "PROBE: LAYOUT MISMATCH\n" : "PROBE: all layouts as assumed\n");
   return bad ? 1 : 0;
 }
