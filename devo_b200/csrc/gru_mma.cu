@@ -168,6 +168,19 @@ template <> __device__ __forceinline__ uint32_t relu2<__nv_bfloat16>(uint32_t u)
 template <typename T> __device__ __forceinline__ uint4 relu8(uint4 u) {
   return make_uint4(relu2<T>(u.x), relu2<T>(u.y), relu2<T>(u.z), relu2<T>(u.w));
 }
+// eight products of packed halves, each rounded to T (HMUL2 / HMUL2.BF16)
+template <typename T> __device__ __forceinline__ uint32_t mul2(uint32_t a, uint32_t b);
+template <> __device__ __forceinline__ uint32_t mul2<__half>(uint32_t a, uint32_t b) {
+  const __half2 h = __hmul2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t mul2<__nv_bfloat16>(uint32_t a, uint32_t b) {
+  const __nv_bfloat162 h = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <typename T> __device__ __forceinline__ uint4 mul8(uint4 a, uint4 b) {
+  return make_uint4(mul2<T>(a.x, b.x), mul2<T>(a.y, b.y), mul2<T>(a.z, b.z), mul2<T>(a.w, b.w));
+}
 // round eight floats to T and back (the autocast rounding point of a half-typed intermediate)
 template <typename T> __device__ __forceinline__ void rnd8(float* v) { unpack8<T>(pack8<T>(v), v); }
 
@@ -296,10 +309,14 @@ struct Epi {
     __syncwarp();
     if (lane == 0) mbar_arrive_remote(bars_l + (uint32_t)((kBarAReady + (na & 1) * 2 + h) * 8));
   }
-  // row statistics over the 8 threads that share a row (they sit in 8 different warps of the same row half)
+  // Row reductions over the 8 threads that share a row (they sit in 8 different warps of the same row half).
+  // The scratch is NOT reused without an intervening data dependency: the launch's LayerNorm #k uses the [8][64][2] block
+  // k (k = 0, 1), the head partials ([8][64][4]) use both blocks -- and between two uses every epilogue warp of the CTA has
+  // passed an accumulator barrier that itself depends on all warps having finished the earlier use (A-writing layers
+  // signal the MMA warp only after their second pass).  So ONE named barrier per reduction suffices.
   template <int N>
-  __device__ __forceinline__ void row_reduce(float* vals) {
-    float* mine = s_stat() + (slot * kRows + r) * N;
+  __device__ __forceinline__ void row_reduce(float* buf, float* vals) {
+    float* mine = buf + (slot * kRows + r) * N;
 #pragma unroll
     for (int k = 0; k < N; k++) mine[k] = vals[k];
     epi_bar_half(rowhalf);
@@ -308,12 +325,11 @@ struct Epi {
 #pragma unroll
     for (int p = 0; p < kSlots; p++)
 #pragma unroll
-      for (int k = 0; k < N; k++) vals[k] += s_stat()[(p * kRows + r) * N + k];
-    epi_bar_half(rowhalf);           // the buffer may be rewritten by the next reduction
+      for (int k = 0; k < N; k++) vals[k] += buf[(p * kRows + r) * N + k];
   }
   __device__ __forceinline__ void ln_stats(float s1, float s2, float& mean, float& rstd) {
     float v[2] = {s1, s2};
-    row_reduce<2>(v);
+    row_reduce<2>(s_stat() + (ln_used & 1) * (kSlots * kRows * 2), v);
     mean = v[0] * (1.0f / kD);
     rstd = rsqrtf(fmaxf(v[1] * (1.0f / kD) - mean * mean, 0.f) + P.eps);
   }
@@ -438,141 +454,137 @@ struct Epi {
         else { q[0] = *f4(net_r, 2 * c); q[1] = *f4(net_r, 2 * c + 1); }
       }
     };
-    uint4 cur_[kAux], nxt[kAux];
-    uint4 inp_c = make_uint4(0u, 0u, 0u, 0u), inp_n = inp_c;
-    if constexpr (kAux > 1) load_aux(chunk_of(0, 0), cur_);         // issued before the accumulator is ready: overlaps the MMAs
-    if constexpr (EPI == EPI_ADD3_LN) { if (live) inp_c = __ldg(reinterpret_cast<const uint4*>(inprow + chunk_of(0, 0) * 8)); }
     if (writes_smem) settle_store();
 #pragma unroll 1
-    for (int i = 0; i < kIter; i++) {
-      const int h = i / kCPT, j = i - h * kCPT;
-      const int c = chunk_of(h, j);                         // global 16-byte chunk index (8 columns)
-      if (j == 0) {
-        // a streamed layer's epilogue overwrites A ring slots: BOTH tiles' MMAs must be done before the first store
-        if (l == 0 && P.stream_a0 && h == 0) mbar_wait(acc_full() + set * 2 + 1, accph);
-        mbar_wait(acc_full() + set * 2 + h, accph);           // N-tile h of this layer is complete in TMEM (both CTAs)
-        tc_fence_after();
-        if (et == 0) stamp(P.dbg, 6 + 6 * l + h);
-      }
-      uint32_t raw[8];
-      tmem_ld8(tcol + h * kNTc + j * 8, raw);
-      if (i + 1 < kIter) {
-        const int cn = chunk_of((i + 1) / kCPT, (i + 1) % kCPT);
-        if constexpr (kAux > 1) load_aux(cn, nxt);
-        if constexpr (EPI == EPI_ADD3_LN) { if (live) inp_n = __ldg(reinterpret_cast<const uint4*>(inprow + cn * 8)); }
-      }
-      tmem_wait_ld();
-      float o[8];
-      {
-        const float4 b0 = *reinterpret_cast<const float4*>(bias + c * 8), b1 = *reinterpret_cast<const float4*>(bias + c * 8 + 4);
-        o[0] = __uint_as_float(raw[0]) + b0.x; o[1] = __uint_as_float(raw[1]) + b0.y;
-        o[2] = __uint_as_float(raw[2]) + b0.z; o[3] = __uint_as_float(raw[3]) + b0.w;
-        o[4] = __uint_as_float(raw[4]) + b1.x; o[5] = __uint_as_float(raw[5]) + b1.y;
-        o[6] = __uint_as_float(raw[6]) + b1.z; o[7] = __uint_as_float(raw[7]) + b1.w;
-      }
-      const uint4 oh = pack8<T>(o);                 // the Linear output, rounded to half (autocast)
-      if constexpr (EPI == EPI_RELU_A) {
-        *reinterpret_cast<uint4*>(An + a_off(r, c)) = relu8<T>(oh);   // max(.,0) commutes with the rounding
-      } else if constexpr (EPI == EPI_STORE_A || EPI == EPI_STORE_B) {
-        *reinterpret_cast<uint4*>(An + a_off(r, c)) = oh;             // staging image, written out by TMA below
-      } else if constexpr (EPI == EPI_GATE) {
-        *reinterpret_cast<uint4*>(gate_r + (size_t)c * (kRows * 8)) = oh;
-      } else if constexpr (EPI == EPI_LNRELU_A) {
-        unpack8<T>(oh, o);
+    for (int h = 0; h < 2; h++) {
+      // every per-row operand of this N-tile's three chunks is requested BEFORE the accumulator wait: the L2 round trips
+      // (state, gate, context rows) overlap the MMAs instead of serialising chunk by chunk
+      uint4 aux[kCPT][kAux];
+      uint4 inp[kCPT];
 #pragma unroll
-        for (int k = 0; k < 8; k++) { s1 += o[k]; s2 += o[k] * o[k]; }
-        *reinterpret_cast<uint4*>(An + a_off(r, c)) = oh;             // parked (half) until normalised
-      } else if constexpr (EPI == EPI_ADD3_LN) {
-        float x[8], b[8];
-        unpack8<T>(oh, o);
-        unpack8<T>(inp_c, b);
-        if (P.state_half) {        // half state: T(T(net + inp) + corr)   (the very first update of a sequence)
-          unpack8<T>(cur_[0], x);
-#pragma unroll
-          for (int k = 0; k < 8; k++) x[k] += b[k];
-          rnd8<T>(x);
-#pragma unroll
-          for (int k = 0; k < 8; k++) x[k] += o[k];
-          rnd8<T>(x);
-        } else {                   // float32 state: (net + float(inp)) + float(corr), no rounding
-          const float4 a0 = as_f4(cur_[0]), a1 = as_f4(cur_[1]);
-          const float n8[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-          for (int k = 0; k < 8; k++) x[k] = (n8[k] + b[k]) + o[k];
+      for (int j = 0; j < kCPT; j++) {
+        const int c = chunk_of(h, j);
+        if constexpr (kAux > 1) load_aux(c, aux[j]);
+        if constexpr (EPI == EPI_ADD3_LN) {
+          inp[j] = make_uint4(0u, 0u, 0u, 0u);
+          if (live) inp[j] = __ldg(reinterpret_cast<const uint4*>(inprow + c * 8));
         }
-        uint32_t xs[8];
+      }
+      // a streamed layer's epilogue overwrites A ring slots: BOTH tiles' MMAs must be done before the first store
+      if (l == 0 && P.stream_a0 && h == 0) mbar_wait(acc_full() + set * 2 + 1, accph);
+      mbar_wait(acc_full() + set * 2 + h, accph);           // N-tile h of this layer is complete in TMEM (both CTAs)
+      tc_fence_after();
+      if (et == 0) stamp(P.dbg, 6 + 6 * l + h);
 #pragma unroll
-        for (int k = 0; k < 8; k++) { s1 += x[k]; s2 += x[k] * x[k]; xs[k] = __float_as_uint(x[k]); }
-        tmem_st8(tcol + h * kNTc + j * 8, xs);      // fp32 row parked in its own accumulator columns
-      } else if constexpr (EPI == EPI_RESID) {
-        unpack8<T>(oh, o);
-        float4 a = as_f4(cur_[0]), b = as_f4(cur_[1]);
-        a.x += o[0]; a.y += o[1]; a.z += o[2]; a.w += o[3]; b.x += o[4]; b.y += o[5]; b.z += o[6]; b.w += o[7];
-        *f4w(net_r, 2 * c) = a;
-        *f4w(net_r, 2 * c + 1) = b;
-        if (out_img) {
-          const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-          *reinterpret_cast<uint4*>(An + a_off(r, c)) = pack8<T>(v);
+      for (int j = 0; j < kCPT; j++) {
+        const int c = chunk_of(h, j);                         // global 16-byte chunk index (8 columns)
+        uint4 (&cur_)[kAux] = aux[j];
+        uint32_t raw[8];
+        tmem_ld8(tcol + h * kNTc + j * 8, raw);
+        tmem_wait_ld();
+        float o[8];
+        {
+          const float4 b0 = *reinterpret_cast<const float4*>(bias + c * 8), b1 = *reinterpret_cast<const float4*>(bias + c * 8 + 4);
+          o[0] = __uint_as_float(raw[0]) + b0.x; o[1] = __uint_as_float(raw[1]) + b0.y;
+          o[2] = __uint_as_float(raw[2]) + b0.z; o[3] = __uint_as_float(raw[3]) + b0.w;
+          o[4] = __uint_as_float(raw[4]) + b1.x; o[5] = __uint_as_float(raw[5]) + b1.y;
+          o[6] = __uint_as_float(raw[6]) + b1.z; o[7] = __uint_as_float(raw[7]) + b1.w;
         }
-      } else if constexpr (EPI == EPI_RESID_A || EPI == EPI_RESID_LN_A) {
-        // net += half Linear output (the SoftAgg `h` layer applied per edge: h(y)[:, gid] == h(y[:, gid]), row by row
-        // bit-identical to the per-group product), then the sum becomes the next A operand (optionally after LayerNorm)
-        unpack8<T>(oh, o);
-        const float4 a = as_f4(cur_[0]), b = as_f4(cur_[1]);
-        float x[8] = {a.x + o[0], a.y + o[1], a.z + o[2], a.w + o[3], b.x + o[4], b.y + o[5], b.z + o[6], b.w + o[7]};
-        if constexpr (EPI == EPI_RESID_A) {
-          *f4w(net_r, 2 * c) = make_float4(x[0], x[1], x[2], x[3]);
-          *f4w(net_r, 2 * c + 1) = make_float4(x[4], x[5], x[6], x[7]);
-          *reinterpret_cast<uint4*>(An + a_off(r, c)) = pack8<T>(x);
-        } else {
+        const uint4 oh = pack8<T>(o);                 // the Linear output, rounded to half (autocast)
+        if constexpr (EPI == EPI_RELU_A) {
+          *reinterpret_cast<uint4*>(An + a_off(r, c)) = relu8<T>(oh);   // max(.,0) commutes with the rounding
+        } else if constexpr (EPI == EPI_STORE_A || EPI == EPI_STORE_B) {
+          *reinterpret_cast<uint4*>(An + a_off(r, c)) = oh;             // staging image, written out by TMA below
+        } else if constexpr (EPI == EPI_GATE) {
+          *reinterpret_cast<uint4*>(gate_r + (size_t)c * (kRows * 8)) = oh;
+        } else if constexpr (EPI == EPI_LNRELU_A) {
+          unpack8<T>(oh, o);
+#pragma unroll
+          for (int k = 0; k < 8; k++) { s1 += o[k]; s2 += o[k] * o[k]; }
+          *reinterpret_cast<uint4*>(An + a_off(r, c)) = oh;             // parked (half) until normalised
+        } else if constexpr (EPI == EPI_ADD3_LN) {
+          float x[8], b[8];
+          unpack8<T>(oh, o);
+          unpack8<T>(inp[j], b);
+          if (P.state_half) {        // half state: T(T(net + inp) + corr)   (the very first update of a sequence)
+            unpack8<T>(cur_[0], x);
+#pragma unroll
+            for (int k = 0; k < 8; k++) x[k] += b[k];
+            rnd8<T>(x);
+#pragma unroll
+            for (int k = 0; k < 8; k++) x[k] += o[k];
+            rnd8<T>(x);
+          } else {                   // float32 state: (net + float(inp)) + float(corr), no rounding
+            const float4 a0 = as_f4(cur_[0]), a1 = as_f4(cur_[1]);
+            const float n8[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+            for (int k = 0; k < 8; k++) x[k] = (n8[k] + b[k]) + o[k];
+          }
           uint32_t xs[8];
 #pragma unroll
           for (int k = 0; k < 8; k++) { s1 += x[k]; s2 += x[k] * x[k]; xs[k] = __float_as_uint(x[k]); }
-          tmem_st8(tcol + h * kNTc + j * 8, xs);
-        }
-      } else {   // EPI_GATED_LN / EPI_GATED_HEADS:  x = n + half(half(sigmoid(gate)) * res)
-        float g[8];
-        unpack8<T>(oh, o);
-        unpack8<T>(cur_[2], g);
-        const float4 a = as_f4(cur_[0]), b = as_f4(cur_[1]);
-        float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+          tmem_st8(tcol + h * kNTc + j * 8, xs);      // fp32 row parked in its own accumulator columns
+        } else if constexpr (EPI == EPI_RESID) {
+          unpack8<T>(oh, o);
+          float4 a = as_f4(cur_[0]), b = as_f4(cur_[1]);
+          a.x += o[0]; a.y += o[1]; a.z += o[2]; a.w += o[3]; b.x += o[4]; b.y += o[5]; b.z += o[6]; b.w += o[7];
+          *f4w(net_r, 2 * c) = a;
+          *f4w(net_r, 2 * c + 1) = b;
+          if (out_img) {
+            const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            *reinterpret_cast<uint4*>(An + a_off(r, c)) = pack8<T>(v);
+          }
+        } else if constexpr (EPI == EPI_RESID_A || EPI == EPI_RESID_LN_A) {
+          // net += half Linear output (the SoftAgg `h` layer applied per edge: h(y)[:, gid] == h(y[:, gid]), row by row
+          // bit-identical to the per-group product), then the sum becomes the next A operand (optionally after LayerNorm)
+          unpack8<T>(oh, o);
+          const float4 a = as_f4(cur_[0]), b = as_f4(cur_[1]);
+          float x[8] = {a.x + o[0], a.y + o[1], a.z + o[2], a.w + o[3], b.x + o[4], b.y + o[5], b.z + o[6], b.w + o[7]};
+          if constexpr (EPI == EPI_RESID_A) {
+            *f4w(net_r, 2 * c) = make_float4(x[0], x[1], x[2], x[3]);
+            *f4w(net_r, 2 * c + 1) = make_float4(x[4], x[5], x[6], x[7]);
+            *reinterpret_cast<uint4*>(An + a_off(r, c)) = pack8<T>(x);
+          } else {
+            uint32_t xs[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) g[k] = sigmoidf_(g[k]);
-        rnd8<T>(g);
+            for (int k = 0; k < 8; k++) { s1 += x[k]; s2 += x[k] * x[k]; xs[k] = __float_as_uint(x[k]); }
+            tmem_st8(tcol + h * kNTc + j * 8, xs);
+          }
+        } else {   // EPI_GATED_LN / EPI_GATED_HEADS:  x = n + half(half(sigmoid(gate)) * res)
+          float g[8];
+          unpack8<T>(cur_[2], g);
 #pragma unroll
-        for (int k = 0; k < 8; k++) g[k] *= o[k];
-        rnd8<T>(g);
+          for (int k = 0; k < 8; k++) g[k] = sigmoidf_(g[k]);
+          // half(sigmoid) * half(res) rounded to half: one packed multiply per pair is exactly that rounding
+          const uint4 gh = pack8<T>(g);
+          unpack8<T>(mul8<T>(gh, oh), g);
+          const float4 a = as_f4(cur_[0]), b = as_f4(cur_[1]);
+          float x[8] = {a.x + g[0], a.y + g[1], a.z + g[2], a.w + g[3], b.x + g[4], b.y + g[5], b.z + g[6], b.w + g[7]};
+          if constexpr (EPI == EPI_GATED_LN) {
+            uint32_t xs[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) x[k] += g[k];
-        if constexpr (EPI == EPI_GATED_LN) {
-          uint32_t xs[8];
+            for (int k = 0; k < 8; k++) { s1 += x[k]; s2 += x[k] * x[k]; xs[k] = __float_as_uint(x[k]); }
+            tmem_st8(tcol + h * kNTc + j * 8, xs);
+          } else {
+            *f4w(net_r, 2 * c) = make_float4(x[0], x[1], x[2], x[3]);          // the new hidden state (float32)
+            *f4w(net_r, 2 * c + 1) = make_float4(x[4], x[5], x[6], x[7]);
+            if (out_img) *reinterpret_cast<uint4*>(An + a_off(r, c)) = pack8<T>(x);
+            float hw[8];
 #pragma unroll
-          for (int k = 0; k < 8; k++) { s1 += x[k]; s2 += x[k] * x[k]; xs[k] = __float_as_uint(x[k]); }
-          tmem_st8(tcol + h * kNTc + j * 8, xs);
-        } else {
-          *f4w(net_r, 2 * c) = make_float4(x[0], x[1], x[2], x[3]);          // the new hidden state (float32)
-          *f4w(net_r, 2 * c + 1) = make_float4(x[4], x[5], x[6], x[7]);
-          if (out_img) *reinterpret_cast<uint4*>(An + a_off(r, c)) = pack8<T>(x);
-          float hw[8];
+            for (int k = 0; k < 8; k++) x[k] = fmaxf(x[k], 0.f);
+            rnd8<T>(x);
 #pragma unroll
-          for (int k = 0; k < 8; k++) x[k] = fmaxf(x[k], 0.f);
-          rnd8<T>(x);
+            for (int o4 = 0; o4 < 4; o4++) {
+              unpack8<T>(*reinterpret_cast<const uint4*>(s_head() + o4 * kD + c * 8), hw);
 #pragma unroll
-          for (int o4 = 0; o4 < 4; o4++) {
-            unpack8<T>(*reinterpret_cast<const uint4*>(s_head() + o4 * kD + c * 8), hw);
-#pragma unroll
-            for (int k = 0; k < 8; k++) hacc[o4] += x[k] * hw[k];
+              for (int k = 0; k < 8; k++) hacc[o4] += x[k] * hw[k];
+            }
           }
         }
       }
       if constexpr (kWritesA && !kTwoPass) {
-        if (j == kCPT - 1 && l + 1 < P.n_layers) signal_a(h);     // the MMA warp may start on the K-blocks fed by this N-tile
+        if (l + 1 < P.n_layers) signal_a(h);     // the MMA warps may start on the K-blocks fed by this N-tile
       }
-      if constexpr (kAux > 1) {
-#pragma unroll
-        for (int k = 0; k < kAux; k++) cur_[k] = nxt[k];
-      }
-      if constexpr (EPI == EPI_ADD3_LN) inp_c = inp_n;
     }
     if (et == 0) stamp(P.dbg, 8 + 6 * l);
     // ---------------- row-wise tails ----------------
@@ -584,10 +596,12 @@ struct Epi {
 #pragma unroll 1
       for (int i = 0; i < kIter; i++) {
         const int c = chunk_of(i / kCPT, i % kCPT);
-        float v[8];
+        float v[8], gk[8], bk[8];
         unpack8<T>(*reinterpret_cast<const uint4*>(An + a_off(r, c)), v);
+        *reinterpret_cast<float4*>(gk) = *reinterpret_cast<const float4*>(gm + c * 8); *reinterpret_cast<float4*>(gk + 4) = *reinterpret_cast<const float4*>(gm + c * 8 + 4);
+        *reinterpret_cast<float4*>(bk) = *reinterpret_cast<const float4*>(bt + c * 8); *reinterpret_cast<float4*>(bk + 4) = *reinterpret_cast<const float4*>(bt + c * 8 + 4);
 #pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = fmaxf((v[k] - mean) * rstd * gm[c * 8 + k] + bt[c * 8 + k], 0.f);
+        for (int k = 0; k < 8; k++) v[k] = fmaxf((v[k] - mean) * rstd * gk[k] + bk[k], 0.f);
         *reinterpret_cast<uint4*>(An + a_off(r, c)) = pack8<T>(v);
       }
       ln_used++;
@@ -599,22 +613,28 @@ struct Epi {
       const float* bt = gm + kD;
       float* dst = (EPI == EPI_ADD3_LN) ? net_r : n32_r;
 #pragma unroll 1
-      for (int i = 0; i < kIter; i++) {
-        const int h = i / kCPT, j = i - h * kCPT;
-        const int c = chunk_of(h, j);
-        uint32_t raw[8];
-        tmem_ld8(tcol + h * kNTc + j * 8, raw);
-        tmem_wait_ld();
-        float v[8];
+      for (int h = 0; h < 2; h++) {
+        uint32_t raw3[kCPT][8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = (__uint_as_float(raw[k]) - mean) * rstd * gm[c * 8 + k] + bt[c * 8 + k];
+        for (int j = 0; j < kCPT; j++) tmem_ld8(tcol + h * kNTc + j * 8, raw3[j]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < kCPT; j++) {
+        const int c = chunk_of(h, j);
+        uint32_t (&raw)[8] = raw3[j];
+        float v[8], gk[8], bk[8];
+        *reinterpret_cast<float4*>(gk) = *reinterpret_cast<const float4*>(gm + c * 8); *reinterpret_cast<float4*>(gk + 4) = *reinterpret_cast<const float4*>(gm + c * 8 + 4);
+        *reinterpret_cast<float4*>(bk) = *reinterpret_cast<const float4*>(bt + c * 8); *reinterpret_cast<float4*>(bk + 4) = *reinterpret_cast<const float4*>(bt + c * 8 + 4);
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = (__uint_as_float(raw[k]) - mean) * rstd * gk[k] + bk[k];
         *f4w(dst, 2 * c) = make_float4(v[0], v[1], v[2], v[3]);
         *f4w(dst, 2 * c + 1) = make_float4(v[4], v[5], v[6], v[7]);
         if (EPI != EPI_ADD3_LN || out_img) *reinterpret_cast<uint4*>(An + a_off(r, c)) = pack8<T>(v);
+        }
       }
       ln_used++;
     } else if constexpr (EPI == EPI_GATED_HEADS) {
-      row_reduce<4>(hacc);
+      row_reduce<4>(s_stat(), hacc);
       if (live && slot == 0) {
         const uint32_t d = pack2<T>(hacc[0] + ElemTraits<T>::to_float(s_head()[4 * kD + 0]), hacc[1] + ElemTraits<T>::to_float(s_head()[4 * kD + 1]));
         const float2 w = unpack2<T>(pack2<T>(hacc[2] + ElemTraits<T>::to_float(s_head()[4 * kD + 2]), hacc[3] + ElemTraits<T>::to_float(s_head()[4 * kD + 3])));
@@ -858,7 +878,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
         default: e.template layer<EPI_GATED_HEADS>(l); break;
       }
     }
-    if (e.et == 0 && e.store_pending) tma_store_wait_all();   // the staging buffer must outlive the bulk stores
+    if (e.et == 0 && e.store_pending) tma_store_wait_read();  // the staging buffer must outlive the bulk stores' reads (CUTLASS's tma_store_wait<0>)
   }
   // teardown: no CTA of the pair may exit (or free TMEM) while the other can still be using its shared memory / TMEM
   tc_fence_before();

@@ -10,6 +10,94 @@
 namespace {
 using devo::ElemTraits;
 
+// 16-byte loads of 16-bit types: blockDim = (16 chunk-threads, parts); a CTA owns 128 channels (16 chunks of 8) of one
+// group; part p scans rows s0+p, s0+p+parts, ... with a running-max softmax per channel, 4 rows (8 independent 16-byte
+// loads) in flight per thread; the parts are merged through shared memory.
+template <typename T> __device__ __forceinline__ void unpack8f(uint4 u, float* v);
+template <> __device__ __forceinline__ void unpack8f<__half>(uint4 u, float* v) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int k = 0; k < 4; k++) { const float2 f = __half22float2(h[k]); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
+}
+template <> __device__ __forceinline__ void unpack8f<__nv_bfloat16>(uint4 u, float* v) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int k = 0; k < 4; k++) { const float2 f = __bfloat1622float2(h[k]); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
+}
+template <typename T>
+__global__ void __launch_bounds__(128) segment_softmax_sum_vec_kernel(const T* __restrict__ g, const T* __restrict__ f,
+                                                                      const int32_t* __restrict__ perm, const int32_t* __restrict__ gstart,
+                                                                      const int32_t* __restrict__ ngroups, T* __restrict__ y, int dim) {
+  extern __shared__ float red[];   // [parts][3][128]
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  DEVO_PDL_WAIT();
+  const int grp = blockIdx.x;
+  const int G = *ngroups;
+  const int parts = blockDim.y, part = threadIdx.y;
+  const int c0 = (blockIdx.y * 16 + threadIdx.x) * 8;        // first of this thread's 8 channels
+  T* yo = y + (size_t)grp * dim + c0;
+  if (grp >= G) {   // padding rows of the fixed-size output
+    if (part == 0) *reinterpret_cast<uint4*>(yo) = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
+  const int s0 = gstart[grp], s1 = gstart[grp + 1];
+  float m[8], den[8], num[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) { m[k] = -INFINITY; den[k] = 0.f; num[k] = 0.f; }
+  for (int s = s0 + part; s < s1; s += 4 * parts) {
+    uint4 gq[4], fq[4];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int ss = s + u * parts;
+      ok[u] = ss < s1;
+      if (ok[u]) {
+        const size_t r = (size_t)perm[ss] * dim + c0;
+        gq[u] = *reinterpret_cast<const uint4*>(g + r);
+        fq[u] = *reinterpret_cast<const uint4*>(f + r);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (!ok[u]) continue;
+      float gv[8], fv[8];
+      unpack8f<T>(gq[u], gv);
+      unpack8f<T>(fq[u], fv);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        if (gv[k] > m[k]) {
+          const float sc = __expf(m[k] - gv[k]);   // exp(-inf) = 0 on the first row
+          den[k] *= sc; num[k] *= sc; m[k] = gv[k];
+        }
+        const float e = __expf(gv[k] - m[k]);
+        den[k] += e;
+        num[k] += e * fv[k];
+      }
+    }
+  }
+  const int t = threadIdx.x * 8;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    red[(part * 3 + 0) * 128 + t + k] = m[k];
+    red[(part * 3 + 1) * 128 + t + k] = den[k];
+    red[(part * 3 + 2) * 128 + t + k] = num[k];
+  }
+  __syncthreads();
+  // merge: thread (x, part) finishes channel t' = part * 16 + x ... all 128 channels over the block's threads
+  for (int ch = threadIdx.y * 16 + threadIdx.x; ch < 128; ch += 16 * parts) {
+    float mm = -INFINITY;
+    for (int p = 0; p < parts; p++) mm = fmaxf(mm, red[(p * 3 + 0) * 128 + ch]);
+    float d = 0.f, n = 0.f;
+    for (int p = 0; p < parts; p++) {
+      const float mp = red[(p * 3 + 0) * 128 + ch];
+      const float sc = (mp > -INFINITY) ? __expf(mp - mm) : 0.f;
+      d += sc * red[(p * 3 + 1) * 128 + ch];
+      n += sc * red[(p * 3 + 2) * 128 + ch];
+    }
+    y[(size_t)grp * dim + blockIdx.y * 128 + ch] = ElemTraits<T>::from_float(d > 0.f ? n / d : 0.f);
+  }
+}
+
 // blockDim = (dim_threads, parts): part p of a group scans rows s0+p, s0+p+parts, ... with a running-max
 // softmax; the parts are merged through shared memory.  Loads are issued 4 rows ahead of use.
 template <typename T>
@@ -92,6 +180,17 @@ extern "C" int devo_segment_softmax_sum(const void* g, const void* f, const int3
   dim3 grid(max_groups, (dim + tx - 1) / tx);
   const size_t smem = (size_t)parts * 3 * tx * sizeof(float);
 #define SEG(T) DEVO_CUDA(devo::launch_pdl(segment_softmax_sum_kernel<T>, grid, block, smem, s, (const T*)g, (const T*)f, perm, gstart, ngroups, (T*)y_out, dim))
+  if ((dtype == DEVO_F16 || dtype == DEVO_BF16) && dim % 128 == 0 &&
+      ((((uintptr_t)g | (uintptr_t)f | (uintptr_t)y_out) & 15) == 0)) {
+    dim3 vblock(16, parts), vgrid(max_groups, dim / 128);
+    const size_t vsmem = (size_t)parts * 3 * 128 * sizeof(float);
+    if (dtype == DEVO_F16)
+      DEVO_CUDA(devo::launch_pdl(segment_softmax_sum_vec_kernel<__half>, vgrid, vblock, vsmem, s, (const __half*)g, (const __half*)f, perm, gstart, ngroups, (__half*)y_out, dim));
+    else
+      DEVO_CUDA(devo::launch_pdl(segment_softmax_sum_vec_kernel<__nv_bfloat16>, vgrid, vblock, vsmem, s, (const __nv_bfloat16*)g, (const __nv_bfloat16*)f, perm, gstart, ngroups, (__nv_bfloat16*)y_out, dim));
+    DEVO_LAUNCH_CHECK("segment_softmax_sum");
+    return DEVO_OK;
+  }
   switch (dtype) {
     case DEVO_F16: SEG(__half); break;
     case DEVO_BF16: SEG(__nv_bfloat16); break;
