@@ -31,8 +31,8 @@
 //                launch overlap the tail of its predecessor (griddepcontrol).
 //
 // Kernel boundaries remain only where rows of different tiles meet: the neighbour gathers (net[ix], net[jx]) and
-// the two SoftAgg segment reductions (their `h` layers are applied per edge inside the consuming kernel).  8 launches per
-// update (6 of this kernel + 2 segment reductions) instead of ~60.
+// the two SoftAgg segment reductions (their `h` layers are applied per edge inside the consuming kernel).  7 launches per
+// update (5 of this kernel + 2 segment reductions) instead of ~60.
 //
 // Rounding points follow torch.autocast exactly as the reference's module forward does (Linear outputs are rounded to
 // half, LayerNorm in float32, element-wise ops round to their promoted type); accumulation is fp32, only the summation
@@ -1052,25 +1052,29 @@ static int gru_update_impl(const devo_gru_weights_t* Wt, const devo_gru_io_t* io
     rc = launch_prog<T>(tw, tw0, ta, t_x16a, t_x16a, P, s);
     if (rc != DEVO_OK) return rc;
   }
-  // (2,3) net += c1(mask * net[ix]) ; net += c2(mask * net[jx])   (enet.py:86-91)
-  for (int k = 0; k < 2; k++) {
+  // (2) net += c1(mask * net[ix])   (enet.py:86-88)
+  {
     GruProg<T> P = base;
     P.n_layers = 2; P.pro = PRO_GATHER;
-    P.w_row[0] = (2 + 2 * k) * kD; P.epi[0] = EPI_RELU_A; P.bias[0] = B(2 + 2 * k);
-    P.w_row[1] = (3 + 2 * k) * kD; P.epi[1] = EPI_RESID;  P.bias[1] = B(3 + 2 * k);
-    P.x16_in = k == 0 ? x16a : x16b; P.idx64 = k == 0 ? io->ix : io->jx;
-    P.out_a = k == 0 ? 1 : 0;
+    P.w_row[0] = 2 * kD; P.epi[0] = EPI_RELU_A; P.bias[0] = B(2);
+    P.w_row[1] = 3 * kD; P.epi[1] = EPI_RESID;  P.bias[1] = B(3);
+    P.x16_in = x16a; P.idx64 = io->ix;
+    P.out_a = 1;
     rc = launch_prog<T>(tw, tw0, ta, t_x16b, t_x16b, P, s);
     if (rc != DEVO_OK) return rc;
   }
-  // (4,5,6) net += SoftAgg(net) over patches, then over frame pairs; gru + heads  (enet.py:93-99, blocks.py:40-48).
-  // The `h` layer of a SoftAgg is applied per EDGE inside the kernel that consumes it (h(y)[:, gid] == h(y[:, gid])):
-  // its A operand is the gathered group row y[gid[e]], its epilogue adds the result to the fp32 state.
+  // (3) net += c2(mask * net[jx]); then g, f of the patch-wise aggregation on the same rows -- no other tile's rows are
+  // needed between the two, so they share one launch: the residual epilogue leaves half(net) as the next A operand
+  // (enet.py:89-93, blocks.py:40-43).  The `h` layer of a SoftAgg is applied per EDGE inside the kernel that consumes it
+  // (h(y)[:, gid] == h(y[:, gid])): its A operand is the gathered group row y[gid[e]], its epilogue adds to the fp32 state.
   {
-    GruProg<T> P = base;                                      // g, f of the patch-wise aggregation
-    P.n_layers = 2; P.pro = PRO_CAST;
-    P.w_row[0] = 6 * kD; P.epi[0] = EPI_STORE_A; P.bias[0] = B(6);
-    P.w_row[1] = 7 * kD; P.epi[1] = EPI_STORE_B; P.bias[1] = B(7);
+    GruProg<T> P = base;
+    P.n_layers = 4; P.pro = PRO_GATHER;
+    P.w_row[0] = 4 * kD; P.epi[0] = EPI_RELU_A;  P.bias[0] = B(4);
+    P.w_row[1] = 5 * kD; P.epi[1] = EPI_RESID_A; P.bias[1] = B(5);
+    P.w_row[2] = 6 * kD; P.epi[2] = EPI_STORE_A; P.bias[2] = B(6);
+    P.w_row[3] = 7 * kD; P.epi[3] = EPI_STORE_B; P.bias[3] = B(7);
+    P.x16_in = x16b; P.idx64 = io->jx;
     P.out_a = 1; P.out_b = 1;
     rc = launch_prog<T>(tw, tw0, ta, t_g16, t_f16, P, s);
     if (rc != DEVO_OK) return rc;

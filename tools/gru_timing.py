@@ -65,11 +65,11 @@ def main():
         torch.cuda.synchronize()
         buf = (ctypes.c_longlong * (2 * 16 * 48))()
         L.devo_gru_debug_timing(buf)
-    names = ["corr+norm", "c1", "c2", "agg_kk g,f", "h_kk+agg_ij g,f", "h_ij+gru+heads"]
-    nl = [3, 2, 2, 2, 3, 7]
+    names = ["corr+norm", "c1", "c2+agg_kk g,f", "h_kk+agg_ij g,f", "h_ij+gru+heads"]
+    nl = [3, 2, 4, 3, 7]
     reps = int(os.environ.get("GRU_REPS", 32))
     for k, (nm, n) in enumerate(zip(names, nl)):
-        k16 = (6 * (reps - 1) + k) % 16
+        k16 = (len(names) * (reps - 1) + k) % 16
         s = [buf[48 * k16 + q] for q in range(48)]
         cyc = [buf[16 * 48 + 48 * k16 + q] for q in range(48)]
         mhz = (cyc[3] - cyc[0]) / max(s[3] - s[0], 1) * 1e3
@@ -82,8 +82,7 @@ def main():
             line += " L%d mma %.1f-%.1f epi %.1f/%.1f loop %.1f end %.1f |" % (l, rel(b), rel(b + 1), rel(b + 2), rel(b + 3), rel(b + 4), rel(b + 5))
         line += " exit %.1f us  (SM clock %.0f MHz)" % (rel(3), mhz)
         print(line)
-        if n == 2 and s[20]:
-            print("    L0 blocks: data ready -> issued (us): " + " ".join("%.2f>%.2f" % (rel(20 + b), rel(32 + b)) for b in range(12)))
+
 
 
 if __name__ == "__main__":
