@@ -15,11 +15,15 @@ before update(), devo.py:523-527).  The whole step is one CUDA-graph replay.
   e2e       same step through the public API with HOST (pinned) inputs: H2D of the new frame's features
             (copy stream, double-buffered) and of the state the operator takes (poses, patches, intrinsics,
             edge list), the step, D2H of the updated poses/depths; wall clock.
-  roofline  the dominant kernel of ours (corr_fast_kernel): algorithmic bytes / measured duration
-            vs the measured HBM peak (MEASURED_PEAKS.json).
+  roofline  the dominant kernels of ours, the fused update operator (gru_mma_kernel x5 + 2 segment reductions: ~45 % of a
+            step): dense-layer FLOPs / measured duration vs the measured sustained bf16 tensor peak; `roofline_corr`:
+            the correlation lookup's algorithmic bytes / duration vs the measured HBM peak (MEASURED_PEAKS.json).
+  per_op_us each stage of the step alone;  ref_cuda: the reference's own CUDA extensions (oracle/_ref, compiled from
+            /root/reference) timed on the same GPU and inputs -- a baseline measurement, never on the product path;
+            extra: the other BASELINE.json configs (4-level stress pyramid, fastba 10 iterations, ...).
   cpu_baseline / --impl reference
-            the reference's CPU path restated by the oracle (oracle/: corr + torch-CPU GRU +
-            ba.py Gauss-Newton), timed on the host cores on a bounded sample of the same workload.
+            the reference's CPU path restated by the oracle (oracle/: correlation in C + OpenMP, torch-CPU GRU,
+            devo/ba.py Gauss-Newton), timed on the host cores on COMPLETE S8 iterations (all 6144 edges).
 """
 import argparse
 import json
@@ -95,11 +99,12 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic_bytes():
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture"""
-    p = os.path.join(ROOT, "profiles", "corr_fast_traffic.json")
+def ncu_traffic_bytes(which="corr"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per update of the kernel(s), from the committed `ncu --set full`
+    capture of this round (profiles/*_traffic.json, written by tools/ncu_traffic.py); None when there is no capture"""
+    name = "corr_fast_traffic.json" if which == "corr" else "r02_gru_traffic.json"
     try:
-        with open(p) as f:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
             return float(json.load(f)["dram_bytes_per_launch"])
     except Exception:
         return None
@@ -128,6 +133,150 @@ def load_state(op, wl, dev):
     op.set_net(wl["net"].to(dev)[None])
     op.snapshot_geometry()
     return fmap, gmap, imap
+
+
+def time_us(fn, stream, flush=None, warm=5, n=30, reduce="median"):
+    """CUDA-event time of fn() on `stream` in microseconds; `flush` (a > L2-size buffer) is zeroed before every call"""
+    for _ in range(warm):
+        fn()
+    ev = []
+    for _ in range(n):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        fn()
+        e1.record(stream)
+        ev.append((e0, e1))
+    torch.cuda.synchronize()
+    t = sorted(a.elapsed_time(b) * 1e3 for a, b in ev)
+    return t[len(t) // 2] if reduce == "median" else sum(t) / len(t)
+
+
+def per_op_times(op, wl, dev, stream, flush):
+    """each stage of the step alone (CUDA graph of that stage only, L2 flushed before every replay), microseconds"""
+    from devo_b200 import cuda_ba, cuda_corr, projective_ops as pops
+    out = {}
+
+    def graphed(fn):
+        fn()
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        return g.replay
+
+    with torch.no_grad():
+        coords = op.coords.clone()
+        out["transform"] = time_us(graphed(lambda: pops.transform_fused(op.poses, op.patches, op.intrinsics, op.ii, op.jj, op.kk, layout=1)), stream, flush)
+        out["graph_plan_kk"] = time_us(graphed(lambda: op.plan_kk.update()), stream, flush)
+        out["graph_plan_ij"] = time_us(graphed(lambda: op.plan_ij.update()), stream, flush)
+        out["corr_lookup"] = time_us(graphed(lambda: cuda_corr.lookup_fused(op.gmap_pm, op.levels_pm, op.levels, coords[0], op.kk, op.jj, out=op.corr_buf)), stream, flush)
+        if op.gru_mode == "mma":
+            from devo_b200.update import GruState
+            scratch = GruState(op.E, dev).set(op.get_net())
+            out["update_operator"] = time_us(graphed(lambda: op.update.forward_mma(
+                None, op.imap, op.kk, op.corr_buf, op.plan_kk, op.plan_ij, op.Np, op.Nf * op.Nf, op.packed, workspace=op._gru_ws,
+                state=scratch, coords=coords)), stream, flush)
+        target = (coords[:, :, :, 1, 1] + op.delta.float()).contiguous()
+        weight = op.weight.float().contiguous()
+        p0, x0 = op._pristine
+
+        def ba(iters):
+            op.poses.copy_(p0)
+            op.patches.copy_(x0)
+            cuda_ba.forward_async(op.poses, op.patches, op.intrinsics, target, weight, op.lmbda, op.ii, op.jj, op.kk, op.t0, op.t1,
+                                  iters, status=op.status, plan=op.plan_kk, workspace=op._ba_ws)
+        t0 = time_us(graphed(lambda: ba(0)), stream, flush)          # the two state copies
+        t2 = time_us(graphed(lambda: ba(2)), stream, flush)
+        t10 = time_us(graphed(lambda: ba(10)), stream, flush)
+        out["fastba_2_iterations"] = t2 - t0
+        out["fastba_10_iterations"] = t10 - t0
+        out["fastba_per_iteration"] = (t10 - t2) / 8.0
+        ing = wl["n_frames"] - 1
+        M = wl["patches_per_frame"]
+        fmap, gmap, imap = wl["fmap"].to(dev), wl["gmap"].to(dev), wl["imap"].to(dev)
+        out["ingest_frame"] = time_us(graphed(lambda: op.ingest_frame(ing, fmap[ing], gmap[ing * M:(ing + 1) * M], imap[ing * M:(ing + 1) * M])), stream, flush)
+    return {k: round(v, 2) for k, v in out.items()}
+
+
+def ref_cuda_times(op, wl, dev, stream, flush):
+    """The reference's OWN CUDA extensions (devo/altcorr, devo/fastba compiled for sm_100a from /root/reference into
+    oracle/_ref by oracle/build_ref.py) timed on this GPU on the same S8 inputs: CUDA events, 20 warm-up + 100 timed calls,
+    median, L2 flushed before every call.  A baseline measurement only -- nothing here is on the product path.
+    lietorch cannot be built (Eigen absent), so the reference's reprojection has no native timing."""
+    try:
+        from oracle.build_ref import load_ref
+        rc, rb = load_ref("cuda_corr_ref"), load_ref("cuda_ba_ref")
+        if rc is None or rb is None:
+            return dict(unavailable="oracle/_ref extensions not built")
+    except Exception as e:  # noqa: BLE001
+        return dict(unavailable="oracle/_ref: %s" % str(e)[:100])
+    out = {}
+    with torch.no_grad():
+        gmap = wl["gmap"].to(dev)[None].contiguous()                               # [1,768,128,3,3] planar, as the reference holds it
+        fm = wl["fmap"].to(dev)
+        pyr = [fm[None].contiguous(), torch.nn.functional.avg_pool2d(fm.float(), 4, 4).to(fm.dtype)[None].contiguous()]
+        coords = op.coords.clone()                                                 # [1,E,2,3,3]
+        ii, jj, kk = op.ii, op.jj, op.kk
+
+        def corr():       # DEVO.corr (devo.py:210-217): two levels + stack + view
+            c1 = rc.forward(gmap, pyr[0], coords / 1, kk, jj, 3)[0]
+            c2 = rc.forward(gmap, pyr[1], coords / 4, kk, jj, 3)[0]
+            return torch.stack([c1, c2], -1).view(1, len(kk), -1)
+        out["altcorr_2_levels_fp16"] = time_us(corr, stream, flush, warm=20, n=100)
+        gm32, p32 = gmap.float(), [p.float() for p in pyr]
+
+        def corr32():
+            c1 = rc.forward(gm32, p32[0], coords / 1, kk, jj, 3)[0]
+            c2 = rc.forward(gm32, p32[1], coords / 4, kk, jj, 3)[0]
+            return torch.stack([c1, c2], -1).view(1, len(kk), -1)
+        out["altcorr_2_levels_fp32"] = time_us(corr32, stream, flush, warm=5, n=30)
+        out["fastba_neighbors"] = time_us(lambda: rb.neighbors(kk, jj), stream, flush, warm=20, n=100)
+        target = (coords[:, :, :, 1, 1] + op.delta.float()).contiguous()
+        weight = op.weight.float().contiguous()
+        p0, x0 = op._pristine
+        poses, patches = p0.clone(), x0.clone()
+
+        def ba(iters):
+            poses.copy_(p0)
+            patches.copy_(x0)
+            if iters:
+                rb.forward(poses, patches, op.intrinsics, target, weight, op.lmbda, ii, jj, kk, op.t0, op.t1, iters)
+        t0 = time_us(lambda: ba(0), stream, flush, warm=20, n=100)
+        out["fastba_2_iterations"] = time_us(lambda: ba(2), stream, flush, warm=20, n=100) - t0
+        out["fastba_10_iterations"] = time_us(lambda: ba(10), stream, flush, warm=5, n=30) - t0
+    out = {k: round(v, 2) for k, v in out.items()}
+    out["unit"] = "us"
+    out["how"] = ("reference extensions compiled from /root/reference (oracle/_ref), same S8 tensors, CUDA events, median, "
+                  "L2 flushed before every call; eager calls as the reference makes them (it has no CUDA-graph path)")
+    return out
+
+
+def extra_configs(op, wl, dev, stream, flush, per_op):
+    """BASELINE.json configs beside the headline one (config 2: 4-level stress pyramid; config 3: fastba 10 iterations;
+    configs 1/4/5 are reported by cpu_baseline / the `devo_loop` and `training_step` blocks)"""
+    from devo_b200 import cuda_corr, synthetic
+    out = {}
+    with torch.no_grad():
+        fm = wl["fmap"].to(dev)
+        lv = [cuda_corr.pack_pixel_major(fm, s) for s in (1, 2, 4, 8)]
+        coords = op.coords[0].clone()
+        buf = torch.empty(op.E, 441 * 4, dtype=fm.dtype, device=dev)
+        g = torch.cuda.CUDAGraph()
+        cuda_corr.lookup_fused(op.gmap_pm, lv, (1, 2, 4, 8), coords, op.kk, op.jj, out=buf)
+        torch.cuda.synchronize(dev)
+        with torch.cuda.graph(g):
+            cuda_corr.lookup_fused(op.gmap_pm, lv, (1, 2, 4, 8), coords, op.kk, op.jj, out=buf)
+        us = time_us(g.replay, stream, flush)
+        alg = synthetic.corr_algorithmic_bytes(wl["n_frames"], wl["patches_per_frame"], wl["E"], wl["C"], wl["H4"], wl["W4"], (1, 2, 4, 8), 2)
+        peak, _ = measured_peak_gbs()
+        out["config2_altcorr_levels_1_2_4_8_fp16"] = dict(us=round(us, 2), algorithmic_bytes=alg, gbs=round(alg / us / 1e3, 1),
+                                                          hbm_frac=round(alg / us / 1e3 / peak, 4))
+    out["config2_altcorr_levels_1_4_fp16"] = dict(us=per_op["corr_lookup"])
+    out["config3_fastba_10_iterations"] = dict(us=per_op["fastba_10_iterations"], us_per_iteration=per_op["fastba_per_iteration"],
+                                               launches_per_iteration=1, algorithmic_bytes_per_iteration=330000)
+    return out
 
 
 def run_ours(args, rank, world, local_rank):
@@ -236,7 +385,7 @@ def run_ours(args, rank, world, local_rank):
     alg = synthetic.corr_algorithmic_bytes(Nf, M, wl["E"], wl["C"], wl["H4"], wl["W4"], (1, 4), 2)
     peak, peak_src = measured_peak_gbs()
     achieved = alg / (k_ms * 1e-3) / 1e9
-    roofline = dict(bound="hbm", kernel="corr_fast_kernel (devo_corr_lookup_fused)", achieved=round(achieved, 1),
+    roofline_corr = dict(bound="hbm", kernel="corr_fast_kernel (devo_corr_lookup_fused)", achieved=round(achieved, 1),
                     peak=peak, unit="GB/s", frac=round(achieved / peak, 4), traffic=ncu_traffic_bytes(),
                     algorithmic_bytes=alg, kernel_ms=round(k_ms, 5), peak_source=peak_src,
                     note="window gathers overlap ~6x: L2->SM bytes, not HBM bytes, bound this kernel (DESIGN.md)")
@@ -269,13 +418,19 @@ def run_ours(args, rank, world, local_rank):
                 tpeak, tsrc = float(json.load(f)["bf16_tflops_sustained"]), "measured sustained bf16 (MEASURED_PEAKS.json)"
         except Exception:
             tpeak, tsrc = 1368.0, "fallback (B200_PROFILING.md)"
-        roofline_gru = dict(bound="tensor", kernel="gru_mma_kernel x6 + segment_softmax_sum x2 (devo_gru_update)",
+        roofline_gru = dict(bound="tensor", kernel="gru_mma_kernel x5 + segment_softmax_sum x2 (devo_gru_update)",
                             achieved=round(fl / (g_ms * 1e-3) / 1e12, 2), peak=tpeak, unit="TFLOP/s",
-                            frac=round(fl / (g_ms * 1e-3) / 1e12 / tpeak, 4), traffic=None, flops=fl, kernel_ms=round(g_ms, 5),
-                            peak_source=tsrc,
-                            note="latency-bound chain of 17 small GEMMs ([6144,384]x[384,384]): MMA -> epilogue -> cluster hand-off "
-                                 "serialise per layer on 96 SMs (DESIGN.md 2.6); L2 flushed before each replay")
+                            frac=round(fl / (g_ms * 1e-3) / 1e12 / tpeak, 4), traffic=ncu_traffic_bytes("gru"), flops=fl,
+                            kernel_ms=round(g_ms, 5), peak_source=tsrc,
+                            note="the update operator is the largest share of a step; a chain of 19 dependent Linear layers "
+                                 "([6144,384]x[384,384], one with K=896) on 48 CTA pairs (cta_group::2 MMAs): per layer MMA -> epilogue "
+                                 "-> next layer's MMA (DESIGN.md 2.6); L2 flushed before each replay")
 
+    per_op = ref_cuda = extra = None
+    if world == 1:
+        per_op = per_op_times(op, wl, dev, stream, flush)
+        ref_cuda = ref_cuda_times(op, wl, dev, stream, flush)
+        extra = extra_configs(op, wl, dev, stream, flush, per_op)
     value = world * args.steps / (total_ms * 1e-3)
     line = dict(metric=METRIC, value=round(value, 2), unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=round(total_ms / args.steps, 5), higher_is_better=True, scaling="weak", vs_baseline=None,
@@ -284,7 +439,11 @@ def run_ours(args, rank, world, local_rank):
                             parallelism="replicas: one sequence per GPU, no data-path collective",
                             step="ingest of 1 frame + 1 update iteration, one CUDA-graph replay", gru=args.gru,
                             ba_status=status, value_l2_warm=round(world * args.steps / (warm_ms * 1e-3), 2)),
-                roofline=roofline, roofline_gru=roofline_gru, e2e=e2e, gpu_launches=int(launches_per_step * args.steps), clocks=clocks)
+                roofline=(roofline_gru if roofline_gru is not None else roofline_corr), roofline_corr=roofline_corr, e2e=e2e, gpu_launches=int(launches_per_step * args.steps), clocks=clocks)
+    if per_op is not None:
+        line["per_op_us"] = per_op
+        line["ref_cuda"] = ref_cuda
+        line["extra"] = extra
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_once()
     return line
@@ -391,12 +550,15 @@ def run_e2e(op, wl, dev, steps):
 
 
 # ----------------------------------------------------------------------------------------------
-def cpu_iteration(wl, up_cpu, edge_stride):
-    """one update iteration of the reference algorithm on the CPU (oracle port), on every
-    `edge_stride`-th edge of the S8 graph.  Returns seconds (and a per-stage breakdown)."""
+def cpu_iteration(wl, up_cpu, edge_stride=1):
+    """one update iteration of the reference algorithm on the CPU, on every `edge_stride`-th edge of the graph (1 = the
+    whole S8 graph, which is what is reported; a stride is only used to warm up).  Stages: reproject (oracle port of
+    projective_ops.transform), correlation (oracle/corr_c.c: plain C + OpenMP restatement of correlation_kernel.cu -- the
+    reference has no CPU altcorr), Update.forward (torch CPU, fp32), devo/ba.py Gauss-Newton x2 (oracle port; the reference's
+    own CPU path).  Returns seconds and the per-stage breakdown."""
     from oracle import ba as oba
-    from oracle import corr as ocorr
-    from oracle import neighbors as onb  # noqa: F401
+    from oracle import corr_c
+    from oracle import neighbors as onb
     from oracle import pops as opops
     sel = torch.arange(0, wl["E"], edge_stride)
     ii, jj, kk = wl["ii"][sel], wl["jj"][sel], wl["kk"][sel]
@@ -404,7 +566,6 @@ def cpu_iteration(wl, up_cpu, edge_stride):
     poses = wl["poses0"][None].to(f32)
     patches = wl["patches0"][None].to(f32)
     intr = wl["intrinsics"][None].to(f32)
-    M, Nf = wl["patches_per_frame"], wl["n_frames"]
     fmap = wl["fmap"].float()
     pyr = [fmap[None], torch.nn.functional.avg_pool2d(fmap, 4, 4)[None]]
     gmap = wl["gmap"].float()[None]
@@ -413,7 +574,7 @@ def cpu_iteration(wl, up_cpu, edge_stride):
     coords = opops.transform(poses, patches, intr, ii, jj, kk).permute(0, 1, 4, 2, 3).contiguous()
     t["reproject"] = time.perf_counter() - t0
     t0 = time.perf_counter()
-    cs = [ocorr.corr_forward(gmap, pyr[l], coords / s, kk, jj, 3, compute_dtype=f32) for l, s in enumerate((1, 4))]
+    cs = [corr_c.corr_forward(gmap, pyr[l], coords / s, kk, jj, 3) for l, s in enumerate((1, 4))]
     corr = torch.stack(cs, -1).reshape(1, ii.numel(), -1)
     t["corr"] = time.perf_counter() - t0
     t0 = time.perf_counter()
@@ -437,42 +598,75 @@ def cpu_iteration(wl, up_cpu, edge_stride):
     return sum(t.values()), t
 
 
-def cpu_baseline_once(edge_stride=8):
+def cpu_ba_py(n_frames, patches_per_frame, steps=2, reps=5):
+    """the reference's own CPU path in isolation -- devo/ba.py Gauss-Newton (oracle port, bit-identical to the reference's
+    Python in fp64, tests/test_oracle_golden.py) -- seconds per `steps` GN steps, with all host threads and with one"""
+    from devo_b200 import synthetic
+    from oracle import ba as oba
+    wl = synthetic.make_workload(n_frames=n_frames, patches_per_frame=patches_per_frame, seed=WORKLOAD["seed"])
+    f32 = torch.float32
+    intr = wl["intrinsics"][None].to(f32)
+    target, weight = wl["targets"][None].to(f32), wl["weights"][None].to(f32)
+    bounds = [-64, -64, wl["W4"] + 64, wl["H4"] + 64]
+    out = {}
+    for label, nthreads in (("all", os.cpu_count() or 1), ("one", 1)):
+        torch.set_num_threads(nthreads)
+        best = None
+        for _ in range(reps):
+            poses, patches = wl["poses0"][None].to(f32), wl["patches0"][None].to(f32)
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                poses, patches = oba.ba_step(poses, patches, intr, target, weight, 1e-4, wl["ii"], wl["jj"], wl["kk"], bounds, ep=10.0, fixedp=1)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        out["ms_%s_threads" % label] = round(1e3 * best, 3)
+    torch.set_num_threads(os.cpu_count() or 1)
+    out.update(E=int(wl["E"]), gn_steps=steps, cores=os.cpu_count() or 1)
+    return out
+
+
+def cpu_baseline_once():
     from devo_b200 import synthetic
     torch.set_num_threads(os.cpu_count() or 1)
     wl = synthetic.make_workload(seed=WORKLOAD["seed"])
     up = synthetic.make_update_module(seed=WORKLOAD["seed"]).eval()
-    cpu_iteration(wl, up, 64)                     # warm-up
-    secs, parts = cpu_iteration(wl, up, edge_stride)
-    full, parts_full = (secs, parts) if edge_stride == 1 else (None, None)
-    its = 1.0 / (secs * edge_stride)
-    return dict(value=round(its, 4), unit=UNIT, cores=torch.get_num_threads(), kind="port",
-                sample="one S8 update iteration on every %dth edge (%d of 6144 edges) on the host cores, scaled by %d; "
-                       "oracle port: reproject %.2fs corr %.2fs gru(torch-cpu) %.2fs ba.py x2 %.2fs"
-                       % (edge_stride, 6144 // edge_stride, edge_stride, parts["reproject"], parts["corr"], parts["gru"], parts["ba"]))
+    cpu_iteration(wl, up, 16)                     # warm-up (thread pools, allocator) on a sixteenth of the edges
+    runs = [cpu_iteration(wl, up, 1) for _ in range(3)]      # the whole S8 graph, no extrapolation
+    secs, parts = min(runs, key=lambda r: r[0])
+    return dict(value=round(1.0 / secs, 4), unit=UNIT, cores=torch.get_num_threads(), kind="port",
+                sample="best of 3 complete S8 update iterations (all 6144 edges) on the host cores: reproject %.3fs, "
+                       "correlation (oracle/corr_c.c, C + OpenMP) %.3fs, Update.forward (torch CPU fp32) %.3fs, devo/ba.py "
+                       "Gauss-Newton x2 %.3fs" % (parts["reproject"], parts["corr"], parts["gru"], parts["ba"]),
+                stage_seconds={k: round(v, 4) for k, v in parts.items()},
+                ba_py_config1=cpu_ba_py(2, 32), ba_py_s8=cpu_ba_py(8, 96))
 
 
 def run_reference(args, rank, world):
+    """the reference arm: the path's CPU implementation on the host cores, on the SAME config (complete S8 iterations)"""
     if rank != 0:
         return None
     from devo_b200 import synthetic
     torch.set_num_threads(os.cpu_count() or 1)
     wl = synthetic.make_workload(seed=WORKLOAD["seed"])
     up = synthetic.make_update_module(seed=WORKLOAD["seed"]).eval()
-    stride = 8
-    for _ in range(min(args.warmup, 2)):
-        cpu_iteration(wl, up, 64)
+    for _ in range(max(1, min(args.warmup, 3))):
+        cpu_iteration(wl, up, 4)
     t0 = time.perf_counter()
+    parts = {}
     for _ in range(args.steps):
-        cpu_iteration(wl, up, stride)
+        _, p = cpu_iteration(wl, up, 1)
+        for k, v in p.items():
+            parts[k] = parts.get(k, 0.0) + v
     dt = time.perf_counter() - t0
-    value = args.steps / (dt * stride)
+    value = args.steps / dt
     cb = dict(value=round(value, 4), unit=UNIT, cores=torch.get_num_threads(), kind="port",
-              sample="each step = one S8 update iteration restricted to every %dth edge (768 of 6144), scaled by %d; "
-                     "oracle port of corr + torch-CPU GRU + devo/ba.py Gauss-Newton x2 (the reference's CPU path); the "
-                     "reference's altcorr/fastba have no CPU implementation and lietorch's needs Eigen (absent)" % (stride, stride))
+              sample="every step = one complete S8 update iteration (all 6144 edges): oracle port of projective_ops.transform, "
+                     "correlation in plain C + OpenMP (oracle/corr_c.c; the reference has no CPU altcorr / fastba and its "
+                     "lietorch CPU backend needs Eigen, absent), Update.forward on torch CPU, devo/ba.py Gauss-Newton x2 "
+                     "(the reference's own CPU path)",
+              stage_seconds_per_step={k: round(v / args.steps, 4) for k, v in parts.items()})
     return dict(metric=METRIC, value=round(value, 4), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                ms_per_step=round(1e3 * dt * stride / args.steps, 3), higher_is_better=True, scaling="weak", vs_baseline=None,
+                ms_per_step=round(1e3 * dt / args.steps, 3), higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32", data="synthetic", impl="reference", config=dict(WORKLOAD), cpu_baseline=cb,
                 e2e=dict(value=round(value, 4), unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
 

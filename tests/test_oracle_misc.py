@@ -153,3 +153,18 @@ def test_scatter_ops():
     w = osc.scatter_softmax(x, idx, dim=1)
     for g in range(4):
         assert torch.allclose(w[0, idx == g], torch.softmax(x[0, idx == g], dim=0), atol=1e-6)
+
+
+def test_c_corr_oracle_matches_torch_oracle():
+    """oracle/corr_c.c (the C + OpenMP restatement bench.py's CPU arm times) against oracle/corr.py (pinned on the GPU box
+    against the reference's compiled extension): reprojected and out-of-bounds coordinates, both pyramid levels"""
+    from oracle import corr as ocorr, corr_c
+    from problems import corr_problem
+    corr_c.build()
+    for oob in (False, True):
+        P = corr_problem(n_frames=3, patches_per_frame=16, seed=3, dtype=torch.float32, H4=48, W4=64, oob_stress=oob)
+        for l, s in enumerate((1, 4)):
+            a = ocorr.corr_forward(P["gmap"], P["pyramid"][l], P["coords"] / s, P["kk"], P["jj"], 3)
+            b = corr_c.corr_forward(P["gmap"], P["pyramid"][l], P["coords"] / s, P["kk"], P["jj"], 3)
+            assert b.shape == a.shape
+            assert (a - b.double()).abs().max().item() <= 1e-5 * max(a.abs().max().item(), 1.0)
