@@ -232,31 +232,50 @@ def reproject(poses, patches, intrinsics, ii, jj, kk):
 
 class GraphPlan:
     """device-side analysis of an edge list grouped by `ka` and ordered by `kb`
-    (replaces torch.unique / fastba.neighbors host round trips; see include/devo_b200.h)"""
+    (replaces torch.unique / fastba.neighbors host round trips; see include/devo_b200.h).
+    `capacity`: allocate the outputs for up to that many edges, so that `rebind` can follow an edge list that grows and
+    shrinks (DEVO.append_factors / remove_factors) without reallocating; the public tensors are views of the first E."""
 
-    def __init__(self, ka, kb, max_ka=-1, max_kb=-1, want_neighbors=True):
+    def __init__(self, ka, kb, max_ka=-1, max_kb=-1, want_neighbors=True, capacity=None):
+        ka, kb = _idx(ka, "ka"), _idx(kb, "kb")
+        dev = ka.device
+        cap = max(int(capacity or 0), ka.numel(), 1)
+        self.capacity = cap
+        self._perm = torch.empty(cap, dtype=torch.int32, device=dev)
+        self._gid = torch.empty(cap, dtype=torch.int32, device=dev)
+        self._gstart = torch.empty(cap + 1, dtype=torch.int32, device=dev)
+        self._gkey = torch.empty(cap, dtype=torch.int64, device=dev)
+        self.ngroups = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._ix = torch.empty(cap, dtype=torch.int64, device=dev) if want_neighbors else None
+        self._jx = torch.empty(cap, dtype=torch.int64, device=dev) if want_neighbors else None
+        self._ws = torch.empty(max(_lib.lib().devo_graph_plan_workspace(cap), 256), dtype=torch.uint8, device=dev)
+        self.rebind(ka, kb, max_ka, max_kb)
+
+    def rebind(self, ka, kb, max_ka=None, max_kb=None):
+        """analyse a (new) edge list of at most `capacity` edges"""
         ka, kb = _idx(ka, "ka"), _idx(kb, "kb")
         E = ka.numel()
-        dev = ka.device
+        if E > self.capacity or kb.numel() != E:
+            raise RuntimeError("GraphPlan.rebind: %d edges exceed the capacity %d (or ka/kb lengths differ)" % (E, self.capacity))
         self.E = E
-        self.perm = torch.empty(E, dtype=torch.int32, device=dev)
-        self.gid = torch.empty(E, dtype=torch.int32, device=dev)
-        self.gstart = torch.empty(E + 1, dtype=torch.int32, device=dev)
-        self.gkey = torch.empty(E, dtype=torch.int64, device=dev)
-        self.ngroups = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.ix = torch.empty(E, dtype=torch.int64, device=dev) if want_neighbors else None
-        self.jx = torch.empty(E, dtype=torch.int64, device=dev) if want_neighbors else None
-        self._ka, self._kb, self._max = ka, kb, (int(max_ka), int(max_kb))
-        L = _lib.lib()
-        self._ws = torch.empty(max(L.devo_graph_plan_workspace(E), 256), dtype=torch.uint8, device=dev)
-        self.update()
+        self._ka, self._kb = ka, kb
+        if max_ka is not None:
+            self._max = (int(max_ka), int(-1 if max_kb is None else max_kb))
+        self.perm, self.gid, self.gkey = self._perm[:E], self._gid[:E], self._gkey[:E]
+        self.gstart = self._gstart[:E + 1]
+        self.ix = None if self._ix is None else self._ix[:E]
+        self.jx = None if self._jx is None else self._jx[:E]
+        return self.update()
 
     def update(self):
         """recompute in place (same buffers: CUDA-graph friendly)"""
+        if self.E == 0:
+            self.ngroups.zero_()
+            return self
         _lib.check(_lib.lib().devo_graph_plan(self._ka.data_ptr(), self._kb.data_ptr(), self.E, self._max[0],
-                                              self._max[1], self.perm.data_ptr(), self.gid.data_ptr(),
-                                              self.gstart.data_ptr(), self.gkey.data_ptr(), self.ngroups.data_ptr(),
-                                              _lib.ptr(self.ix), _lib.ptr(self.jx), self._ws.data_ptr(),
+                                              self._max[1], self._perm.data_ptr(), self._gid.data_ptr(),
+                                              self._gstart.data_ptr(), self._gkey.data_ptr(), self.ngroups.data_ptr(),
+                                              _lib.ptr(self._ix), _lib.ptr(self._jx), self._ws.data_ptr(),
                                               self._ws.numel(), _lib.stream_ptr(self._ka.device)), "graph_plan")
         return self
 

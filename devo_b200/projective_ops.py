@@ -39,11 +39,15 @@ def proj(X, intrinsics, depth=False):
     return torch.stack([x, y], dim=-1)
 
 
-def _fused_ok(poses, patches, intrinsics, depth):
+def _fused_ok(poses, patches, intrinsics, depth, index_tensors=()):
     if depth or not isinstance(poses, SE3):
         return False
     ts = (poses.data, patches, intrinsics)
     if any((not t.is_cuda) or t.dtype != torch.float32 for t in ts):
+        return False
+    # the kernel dereferences ii/jj/kk as device int64 arrays; the reference API also accepts CPU / int32 index tensors
+    # (`patches[:, kk]` works with them), which must take the composed path
+    if any((not torch.is_tensor(t)) or (not t.is_cuda) or t.dtype != torch.int64 or t.device != patches.device for t in index_tensors):
         return False
     if torch.is_grad_enabled() and any(t.requires_grad for t in ts):
         return False
@@ -78,7 +82,7 @@ def transform_fused(poses_data, patches, intrinsics, ii, jj, kk, jacobian=False,
 
 def transform(poses, patches, intrinsics, ii, jj, kk, depth=False, valid=False, jacobian=False, tonly=False):
     """reproject patch kk from frame ii into frame jj -> [b,E,P,P,2] (+valid / +Jacobians)"""
-    if _fused_ok(poses, patches, intrinsics, depth):
+    if _fused_ok(poses, patches, intrinsics, depth, (ii, jj, kk)):
         return transform_fused(poses.data, patches, intrinsics, ii, jj, kk, jacobian=jacobian, valid=valid, tonly=tonly)
 
     X0 = iproj(patches[:, kk], intrinsics[:, ii])

@@ -269,3 +269,101 @@ def test_reference_devo_call_runs_unchanged_config4():
     assert slam.net.dtype == torch.float32 and slam.net.shape[1] == slam.ii.numel()
     poses, tstamps = slam.terminate()
     assert poses.shape == (15, 7)
+
+
+def test_patch_graph_vo_matches_reference_devo_loop():
+    """BASELINE.json config 4 through THIS package's frame loop (devo_b200.vo.PatchGraphVO: pixel-major ring-buffer ingest,
+    device-side graph analysis and hidden-state bookkeeping, fused update operator) against the reference's own DEVO class
+    on the same frames, the same network and the same per-frame front-end outputs: identical edge lists and keyframe
+    decisions, poses / depths within the half-precision noise that 19 recurrent updates accumulate."""
+    from devo_b200.update import Update
+    from devo_b200.vo import PatchGraphVO, frontend_from_reference_network
+    ns = ref_callers.use_backend("ours")
+    slam, cfg = _make_devo(ns, 3)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    intr = torch.tensor([320.0, 320.0, 320.0, 240.0], device="cuda")
+    frames = [(torch.rand(5, 480, 640, device="cuda", generator=g) < 0.1).float() * torch.randn(5, 480, 640, device="cuda", generator=g)
+              for _ in range(15)]
+    # one front-end pass per frame, shared by both loops
+    fe = frontend_from_reference_network(slam.network, cfg)
+    with torch.no_grad():
+        cached = [fe(f) for f in frames]
+    it = iter(cached)
+
+    def ref_patchify(image, **kw):
+        c = next(it)
+        return (c["fmap"][None, None].clone(), c["gmap"][None].clone(), c["imap"][None, :, :, None, None].clone(),
+                c["patches"][None].clone(), None, c["clr"])
+    import types
+    net = slam.network
+    slam.network = types.SimpleNamespace(patchify=ref_patchify, update=net.update)     # DEVO only calls these two
+    slam.motion_probe = lambda: 10.0
+    torch.manual_seed(5)
+    with torch.no_grad():
+        for t, f in enumerate(frames):
+            slam(float(t), f, intr)
+    # ---- ours
+    ours_up = Update(3).cuda().eval()
+    ours_up.load_state_dict(net.update.state_dict())
+    it2 = iter(cached)
+    vo = PatchGraphVO(cfg, ours_up, lambda image: next(it2))
+    vo.motion_probe = lambda: 10.0
+    torch.manual_seed(5)
+    for t, f in enumerate(frames):
+        vo(float(t), f, intr)
+    torch.cuda.synchronize()
+    assert vo.n_updates == 12 + 7 and vo.is_initialized
+    assert vo.n == slam.n and vo.m == slam.m
+    assert torch.equal(vo.ii, slam.ii) and torch.equal(vo.jj, slam.jj) and torch.equal(vo.kk, slam.kk)
+    assert torch.isfinite(vo.poses_[:vo.n]).all()
+    dp = (vo.poses_[:vo.n] - slam.poses_[:slam.n]).abs().max().item()
+    dd = (vo.patches_[:vo.n, :, 2] - slam.patches_[:slam.n, :, 2]).abs().max().item()
+    net_ref = slam.net.float()
+    dn = (vo.state.get() - net_ref).abs().mean().item() / max(net_ref.abs().mean().item(), 1e-6)
+    print("PatchGraphVO vs reference DEVO after 15 frames: pose %.2e depth %.2e hidden-state rel %.2e" % (dp, dd, dn))
+    assert dp <= 5e-2 and dn <= 0.1
+    p1, _ = vo.terminate()
+    p2, _ = slam.terminate()
+    assert p1.shape == p2.shape == (15, 7)
+
+
+def test_patch_graph_vo_motion_probe_matches_reference():
+    """devo.py:241-256 through our loop: same median flow as the reference's motion_probe on the same state"""
+    from devo_b200.update import Update
+    from devo_b200.vo import PatchGraphVO, frontend_from_reference_network
+    ns = ref_callers.use_backend("ours")
+    slam, cfg = _make_devo(ns, 4)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    intr = torch.tensor([320.0, 320.0, 320.0, 240.0], device="cuda")
+    frames = [(torch.rand(5, 480, 640, device="cuda", generator=g) < 0.1).float() * torch.randn(5, 480, 640, device="cuda", generator=g)
+              for _ in range(2)]
+    fe = frontend_from_reference_network(slam.network, cfg)
+    with torch.no_grad():
+        cached = [fe(f) for f in frames]
+    probes = {}
+    it = iter(cached)
+
+    def ref_patchify(image, **kw):
+        c = next(it)
+        return (c["fmap"][None, None].clone(), c["gmap"][None].clone(), c["imap"][None, :, :, None, None].clone(),
+                c["patches"][None].clone(), None, c["clr"])
+    import types
+    net = slam.network
+    slam.network = types.SimpleNamespace(patchify=ref_patchify, update=net.update)
+    orig = slam.motion_probe
+    slam.motion_probe = lambda: probes.setdefault("ref", orig())
+    torch.manual_seed(1)
+    with torch.no_grad():
+        for t, f in enumerate(frames):
+            slam(float(t), f, intr)
+    ours_up = Update(3).cuda().eval()
+    ours_up.load_state_dict(net.update.state_dict())
+    it2 = iter(cached)
+    vo = PatchGraphVO(cfg, ours_up, lambda image: next(it2))
+    orig2 = vo.motion_probe
+    vo.motion_probe = lambda: probes.setdefault("ours", orig2())
+    torch.manual_seed(1)
+    for t, f in enumerate(frames):
+        vo(float(t), f, intr)
+    a, b = float(probes["ref"]), float(probes["ours"])
+    assert abs(a - b) <= 2e-2 * max(abs(a), 1.0), (a, b)
