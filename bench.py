@@ -279,6 +279,108 @@ def extra_configs(op, wl, dev, stream, flush, per_op):
     return out
 
 
+def synthetic_frontend(dev, M=96, C=128, dim=384, H4=120, W4=160, seed=0):
+    """per-frame features of the right shapes without the encoders (outside the update-operator path)"""
+    g = torch.Generator(device=dev).manual_seed(seed)
+
+    def patchify(image):
+        x = torch.randint(1, W4 - 1, (M,), device=dev, generator=g).float()
+        y = torch.randint(1, H4 - 1, (M,), device=dev, generator=g).float()
+        off = torch.arange(-1, 2, device=dev).float()
+        px = (x[:, None, None] + off[None, None, :]).expand(M, 3, 3)
+        py = (y[:, None, None] + off[None, :, None]).expand(M, 3, 3)
+        patches = torch.stack([px, py, torch.ones_like(px)], 1)
+        return dict(fmap=(torch.randn(C, H4, W4, device=dev, generator=g) / 4).half(),
+                    gmap=(torch.randn(M, C, 3, 3, device=dev, generator=g) / 4).half(),
+                    imap=(torch.randn(M, dim, device=dev, generator=g) / 4).half(), patches=patches, clr=None)
+    return patchify
+
+
+def devo_loop_times(dev, frames=15):
+    """BASELINE.json config 4: the DEVO frame loop (8 frames to initialise -> 12 updates -> 7 x (update + keyframe)) on
+    synthetic per-frame features, through this package's PatchGraphVO; CUDA events around every update() call."""
+    from devo_b200 import synthetic
+    from devo_b200.vo import PatchGraphVO, VOConfig
+    out = {}
+    up = synthetic.make_update_module(seed=WORKLOAD["seed"]).to(dev).eval()
+    intr = torch.tensor([320.0, 320.0, 320.0, 240.0], device=dev)
+    for rep in range(2):                                   # the second pass is the measured one (allocator, lazy init)
+        vo = PatchGraphVO(VOConfig(), up, synthetic_frontend(dev, seed=rep), device=dev)
+        vo.motion_probe = lambda: 10.0                     # random-init weights: force initialisation, as the tests do
+        ev, orig = [], vo.update
+
+        def timed():
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            orig()
+            b.record()
+            ev.append((a, b, vo.ii.numel()))
+        vo.update = timed
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for t in range(frames):
+            vo(float(t), None, intr)
+        torch.cuda.synchronize(dev)
+        wall = time.perf_counter() - t0
+    ms = [a.elapsed_time(b) for a, b, _ in ev]
+    out.update(frames=frames, updates=len(ms), update_ms_total=round(sum(ms), 3), update_ms_median=round(sorted(ms)[len(ms) // 2], 4),
+               iterations_per_s=round(len(ms) / (sum(ms) * 1e-3), 1), edges_last=int(ev[-1][2]), loop_wall_s=round(wall, 4),
+               how="eager host-driven loop (the edge count changes every frame), device time of every update() by CUDA events")
+    return out
+
+
+def devo_loop_reference(dev, frames=15):
+    """the same config through the REFERENCE's own DEVO class and Python (staged copy, oracle/_ref/devo_py), once on the
+    reference's compiled CUDA extensions (lietorch on this library: Eigen is absent) and once on this library's drop-in
+    modules.  Baseline measurement only."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import ref_callers
+        if not ref_callers.available():
+            return dict(unavailable="oracle/_ref/devo_py not staged")
+        out = {}
+        intr = torch.tensor([320.0, 320.0, 320.0, 240.0], device=dev)
+        import types
+        for kind in ("ref_ext", "ours"):
+            ns = ref_callers.use_backend(kind)
+            for rep in range(2):
+                torch.manual_seed(WORKLOAD["seed"])
+                cfg = ref_callers.default_cfg()
+                net = ns.enet.eVONet(patch_selector=cfg.PATCH_SELECTOR.lower())
+                slam = ns.devo.DEVO(cfg, net, evs=True, ht=480, wd=640)
+                fe = synthetic_frontend(dev, seed=rep)
+
+                def ref_patchify(image, **kw):
+                    c = fe(image)
+                    return (c["fmap"][None, None], c["gmap"][None], c["imap"][None, :, :, None, None], c["patches"][None], None,
+                            torch.zeros(1, 96, 1, device=dev))
+                slam.network = types.SimpleNamespace(patchify=ref_patchify, update=net.update)
+                slam.motion_probe = lambda: 10.0
+                ev, orig = [], slam.update
+
+                def timed():
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    orig()
+                    b.record()
+                    ev.append((a, b))
+                slam.update = timed
+                vox = torch.zeros(5, 480, 640, device=dev)
+                vox[:, ::3, ::3] = 1.0                        # passes the reference's "enough events" check (devo.py:407-417)
+                with torch.no_grad():
+                    for t in range(frames):
+                        slam(float(t), vox.clone(), intr)
+                torch.cuda.synchronize(dev)
+            ms = [a.elapsed_time(b) for a, b in ev]
+            out["reference_python_on_%s" % ("reference_cuda_extensions" if kind == "ref_ext" else "this_library_dropins")] = dict(
+                updates=len(ms), update_ms_total=round(sum(ms), 3), update_ms_median=round(sorted(ms)[len(ms) // 2], 4),
+                iterations_per_s=round(len(ms) / (sum(ms) * 1e-3), 1))
+        ref_callers.use_backend("ours")
+        return out
+    except Exception as e:  # noqa: BLE001
+        return dict(unavailable="%s: %s" % (type(e).__name__, str(e)[:160]))
+
+
 def run_ours(args, rank, world, local_rank):
     from devo_b200 import _lib, cuda_corr, synthetic
     dev = torch.device("cuda", local_rank)
@@ -431,6 +533,8 @@ def run_ours(args, rank, world, local_rank):
         per_op = per_op_times(op, wl, dev, stream, flush)
         ref_cuda = ref_cuda_times(op, wl, dev, stream, flush)
         extra = extra_configs(op, wl, dev, stream, flush, per_op)
+        extra["config4_devo_loop_N15"] = devo_loop_times(dev)
+        ref_cuda["config4_devo_loop_N15"] = devo_loop_reference(dev)
     value = world * args.steps / (total_ms * 1e-3)
     line = dict(metric=METRIC, value=round(value, 2), unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=round(total_ms / args.steps, 5), higher_is_better=True, scaling="weak", vs_baseline=None,
