@@ -381,6 +381,68 @@ def devo_loop_reference(dev, frames=15):
         return dict(unavailable="%s: %s" % (type(e).__name__, str(e)[:160]))
 
 
+def training_iteration_times(dev, n_frames=15, M=96):
+    """BASELINE.json config 5 on one GPU: forward + backward of ONE iteration of the training loop body (devo/enet.py:341-372)
+    at the training shape -- N=15 frames x 96 patches, all-pairs graph (21 600 edges), float32 (train.py runs with autocast
+    off): reprojection, correlation lookup with autograd (both levels), Update.forward, two differentiable ba.BA steps, the
+    reprojection loss against ground truth.  With the fused geometry Function (one forward + one backward launch per
+    projective transform) and with the composed autograd path (how the reference differentiates)."""
+    from devo_b200 import altcorr, ba as dba, lietorch as lt, projective_ops as pops, synthetic
+    wl = synthetic.make_workload(n_frames=n_frames, patches_per_frame=M, seed=WORKLOAD["seed"], feat_dtype=torch.float32)
+    up = synthetic.make_update_module(seed=WORKLOAD["seed"]).to(dev)
+    ii, jj, kk = wl["ii"].to(dev), wl["jj"].to(dev), wl["kk"].to(dev)
+    E = ii.numel()
+    f32 = torch.float32
+    fmap0, gmap0 = wl["fmap"].to(dev)[None].to(f32), wl["gmap"].to(dev)[None].to(f32)
+    imap = wl["imap"].to(dev)[None].to(f32)
+    poses0, patches0, intr = wl["poses0"].to(dev)[None], wl["patches0"].to(dev)[None], wl["intrinsics"].to(dev)[None]
+    poses_gt = lt.SE3(wl["poses_gt"].to(dev)[None])
+    bounds = [-64, -64, wl["W4"] + 64, wl["H4"] + 64]
+
+    def iteration():
+        fmap = fmap0.clone().requires_grad_(True)
+        gmap = gmap0.clone().requires_grad_(True)
+        pyr = [fmap, torch.nn.functional.avg_pool2d(fmap[0], 4, 4)[None]]
+        poses, patches = lt.SE3(poses0.clone()), patches0.clone()
+        net = torch.zeros(1, E, 384, device=dev)
+        coords = pops.transform(poses, patches, intr, ii, jj, kk).permute(0, 1, 4, 2, 3).contiguous()
+        c1 = altcorr.corr(gmap, pyr[0], coords / 1, kk, jj, 3)
+        c2 = altcorr.corr(gmap, pyr[1], coords / 4, kk, jj, 3)
+        corr = torch.stack([c1, c2], -1).view(1, E, -1)
+        net, (delta, weight, _) = up(net, imap[:, kk], corr, None, ii, jj, kk)
+        target = coords[..., 1, 1].detach() + delta
+        for _ in range(2):
+            poses, patches = dba.BA(poses, patches, intr, target, weight, 1e-4, ii, jj, kk, bounds, ep=10.0, fixedp=1)
+        gt = pops.transform(poses_gt, patches0, intr, ii, jj, kk)
+        est = pops.transform(poses, patches, intr, ii, jj, kk)
+        loss = (est - gt).norm(dim=-1).mean()
+        loss.backward()
+        up.zero_grad(set_to_none=True)
+        return loss
+
+    out = {}
+    for label, fused in (("fused_geometry", True), ("composed_autograd", False)):
+        pops.FUSED_AUTOGRAD = fused
+        for _ in range(3):
+            iteration()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 8
+        a.record()
+        for _ in range(n):
+            loss = iteration()
+        b.record()
+        torch.cuda.synchronize(dev)
+        out["ms_per_iteration_" + label] = round(a.elapsed_time(b) / n, 3)
+    pops.FUSED_AUTOGRAD = True
+    grad_bytes = 4 * sum(p.numel() for p in up.parameters())
+    out.update(edges=E, frames=n_frames, patches_per_frame=M, dtype="f32", loss=round(float(loss), 4),
+               note="one update iteration of the training loop, forward + backward, eager; the full step (train.py) runs "
+                    "STEPS=18 of these plus the encoders; the only collective of the reference's 8-GPU training is DDP's "
+                    "gradient all-reduce (update operator: %.1f MB fp32 per step)" % (grad_bytes / 1e6))
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     from devo_b200 import _lib, cuda_corr, synthetic
     dev = torch.device("cuda", local_rank)
@@ -534,6 +596,7 @@ def run_ours(args, rank, world, local_rank):
         ref_cuda = ref_cuda_times(op, wl, dev, stream, flush)
         extra = extra_configs(op, wl, dev, stream, flush, per_op)
         extra["config4_devo_loop_N15"] = devo_loop_times(dev)
+        extra["config5_training_iteration_N15"] = training_iteration_times(dev)
         ref_cuda["config4_devo_loop_N15"] = devo_loop_reference(dev)
     value = world * args.steps / (total_ms * 1e-3)
     line = dict(metric=METRIC, value=round(value, 2), unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),

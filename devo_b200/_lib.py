@@ -42,6 +42,7 @@ SIGNATURES = {
     "devo_ba_sharded_solve_peer": (_i, [_vp, _vp, _i, _i, _c.c_uint64] + [_i] * 5 + [_vp, _sz, _vp, _vp]),
     "devo_reproject": (_i, [_vp] * 7 + [_i, _i, _vp]),
     "devo_transform_forward": (_i, [_vp] * 11 + [_i] * 4 + [_vp]),
+    "devo_transform_backward": (_i, [_vp] * 12 + [_i] * 4 + [_vp]),
     "devo_glue_layernorm": (_i, [_i, _i] + [_vp] * 6 + [_c.c_float, _vp, _vp, _i, _i, _vp]),
     "devo_glue_gather_mask_cast": (_i, [_i, _vp, _vp, _vp, _i, _i, _vp]),
     "devo_glue_residual_add": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _vp]),

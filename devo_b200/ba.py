@@ -22,24 +22,23 @@ from .scatter import scatter_sum
 
 
 class CholeskySolver(torch.autograd.Function):
-    """x = H^-1 b via Cholesky; zero (and no gradient) when H is not positive definite"""
+    """x = H^-1 b via Cholesky; zero (and zero gradient) when H is not positive definite (devo/ba.py:12-37).
+    No host synchronisation: the factorisation's `info` stays on the device and selects the result."""
 
     @staticmethod
     def forward(ctx, H, b):
         U, info = torch.linalg.cholesky_ex(H)
-        ctx.failed = bool(torch.any(info))
-        if ctx.failed:
-            return torch.zeros_like(b)
-        xs = torch.cholesky_solve(b, U)
-        ctx.save_for_backward(U, xs)
+        ok = (info == 0).view(-1, 1, 1)
+        xs = torch.where(ok, torch.cholesky_solve(b, torch.where(ok, U, torch.eye(U.shape[-1], dtype=U.dtype, device=U.device))),
+                         torch.zeros_like(b))
+        ctx.save_for_backward(U, xs, ok)
         return xs
 
     @staticmethod
     def backward(ctx, grad_x):
-        if ctx.failed:
-            return None, None
-        U, xs = ctx.saved_tensors
-        dz = torch.cholesky_solve(grad_x, U)
+        U, xs, ok = ctx.saved_tensors
+        Us = torch.where(ok, U, torch.eye(U.shape[-1], dtype=U.dtype, device=U.device))
+        dz = torch.where(ok, torch.cholesky_solve(grad_x, Us), torch.zeros_like(grad_x))
         return -torch.matmul(xs, dz.transpose(-1, -2)), dz
 
 
@@ -52,7 +51,16 @@ def _block_rows(J, blk, nfree, sign):
 
 def BA(poses, patches, intrinsics, targets, weights, lmbda, ii, jj, kk, bounds, ep=100.0, PRINT=False,
        fixedp=1, structure_only=False):
-    n_frames = max(ii.max().item(), jj.max().item()) + 1
+    """One damped Gauss-Newton step, differentiable, WITHOUT host synchronisation on CUDA:
+      * the geometry (reprojection + centre-pixel Jacobians) is one fused forward / one fused backward launch
+        (projective_ops._TransformFn) instead of ~60 autograd nodes;
+      * the reference sizes the system by `max(ii.max().item(), jj.max().item()) + 1` and by `torch.unique(kk)` (two host
+        round trips): here every pose of `poses` after the first `fixedp` and every patch of `patches` is an unknown --
+        frames / patches without edges contribute empty rows, the damping (ep on the diagonal, lambda in C) makes their update
+        exactly zero, and the blocks of the others are unchanged, so the result is the reference's;
+      * a failed factorisation selects the zero update on the device (CholeskySolver)."""
+    sync_free = poses.data.is_cuda and not (isinstance(lmbda, torch.Tensor) and lmbda.numel() > 1)
+    n_frames = poses.data.shape[1] if sync_free else max(ii.max().item(), jj.max().item()) + 1
     coords, ok, (Ji, Jj, Jz) = pops.transform(poses, patches, intrinsics, ii, jj, kk, jacobian=True)
     c = coords.shape[3] // 2
     centre = coords[..., c, c, :]
@@ -70,8 +78,11 @@ def BA(poses, patches, intrinsics, targets, weights, lmbda, ii, jj, kk, bounds, 
     w = (ok[..., None] * weights).reshape(1, 2 * E, 1)
     z = Jz.reshape(1, 2 * E, 1)
 
-    kx, kq = torch.unique(kk, return_inverse=True, sorted=True)
-    m = kx.numel()
+    if sync_free:
+        kx, kq, m = None, kk, patches.shape[1]              # segment id = the patch index itself
+    else:
+        kx, kq = torch.unique(kk, return_inverse=True, sorted=True)
+        m = kx.numel()
     rows_k = kq.repeat_interleave(2)
     C = scatter_sum(w * z * z, rows_k, dim=1, dim_size=m)
     u = scatter_sum(w * r * z, rows_k, dim=1, dim_size=m)
@@ -96,8 +107,11 @@ def BA(poses, patches, intrinsics, targets, weights, lmbda, ii, jj, kk, bounds, 
         dX = dX.view(1, nfree, 6)
 
     x, y_, disps = patches.unbind(dim=2)
-    step = scatter_sum(dZ.view(1, m, 1, 1).expand(-1, -1, disps.shape[2], disps.shape[3]), kx.to(dZ.device),
-                       dim=1, dim_size=disps.shape[1])
+    if sync_free:
+        step = dZ.view(1, m, 1, 1).expand(-1, -1, disps.shape[2], disps.shape[3])
+    else:
+        step = scatter_sum(dZ.view(1, m, 1, 1).expand(-1, -1, disps.shape[2], disps.shape[3]), kx.to(dZ.device),
+                           dim=1, dim_size=disps.shape[1])
     patches = torch.stack([x, y_, (disps + step).clamp(min=1e-3, max=10.0)], dim=2)
     if dX is not None:
         full = torch.zeros(1, poses.shape[1], 6, device=dX.device, dtype=dX.dtype)

@@ -10,6 +10,7 @@ from . import _lib
 from .lietorch import SE3
 
 MIN_DEPTH = 0.2
+FUSED_AUTOGRAD = True      # transform under autograd: one fused forward + one fused backward launch (False: composed path)
 
 
 def extract_intrinsics(intrinsics):
@@ -39,7 +40,7 @@ def proj(X, intrinsics, depth=False):
     return torch.stack([x, y], dim=-1)
 
 
-def _fused_ok(poses, patches, intrinsics, depth, index_tensors=()):
+def _fused_ok(poses, patches, intrinsics, depth, index_tensors=(), allow_grad=False):
     if depth or not isinstance(poses, SE3):
         return False
     ts = (poses.data, patches, intrinsics)
@@ -50,7 +51,8 @@ def _fused_ok(poses, patches, intrinsics, depth, index_tensors=()):
     if any((not torch.is_tensor(t)) or (not t.is_cuda) or t.dtype != torch.int64 or t.device != patches.device for t in index_tensors):
         return False
     if torch.is_grad_enabled() and any(t.requires_grad for t in ts):
-        return False
+        if not allow_grad or intrinsics.requires_grad:       # the fused backward has no intrinsics gradient
+            return False
     return poses.data.dim() == 3 and poses.data.shape[0] == 1 and patches.dim() == 5 and patches.shape[0] == 1
 
 
@@ -80,10 +82,50 @@ def transform_fused(poses_data, patches, intrinsics, ii, jj, kk, jacobian=False,
     return coords
 
 
+class _TransformFn(torch.autograd.Function):
+    """projective_ops.transform (+ centre-pixel Jacobians) as ONE fused forward and ONE fused backward launch
+    (csrc/ba.cu::transform_kernel, csrc/transform_grad.cu).  The pose gradient follows lietorch's convention (gradient
+    w.r.t. a left tangent perturbation, slots 0..5 of the 7), so it composes with the group_ops Functions."""
+
+    @staticmethod
+    def forward(ctx, poses_data, patches, intrinsics, ii, jj, kk, jacobian, tonly):
+        poses_data, patches, intrinsics = poses_data.contiguous(), patches.contiguous(), intrinsics.contiguous()
+        ii, jj, kk = ii.contiguous(), jj.contiguous(), kk.contiguous()
+        coords, v, (Ji, Jj, Jz) = transform_fused(poses_data, patches, intrinsics, ii, jj, kk, jacobian=True, tonly=tonly)
+        ctx.save_for_backward(poses_data, patches, intrinsics, ii, jj, kk)
+        ctx.tonly, ctx.jacobian = bool(tonly), bool(jacobian)
+        ctx.mark_non_differentiable(v)
+        return coords, v, Ji, Jj, Jz
+
+    @staticmethod
+    def backward(ctx, g_coords, _gv, g_Ji, g_Jj, g_Jz):
+        poses_data, patches, intrinsics, ii, jj, kk = ctx.saved_tensors
+        gp = torch.zeros_like(poses_data)
+        gx = torch.zeros_like(patches)
+
+        def c(t):
+            return None if t is None else t.contiguous().float()
+        g_coords, g_Ji, g_Jj, g_Jz = c(g_coords), c(g_Ji), c(g_Jj), c(g_Jz)
+        _lib.check(_lib.lib().devo_transform_backward(
+            poses_data.data_ptr(), patches.data_ptr(), intrinsics.data_ptr(), ii.data_ptr(), jj.data_ptr(), kk.data_ptr(),
+            _lib.ptr(g_coords), _lib.ptr(g_Ji), _lib.ptr(g_Jj), _lib.ptr(g_Jz), gp.data_ptr(), gx.data_ptr(),
+            ii.numel(), patches.shape[-1], 0, int(ctx.tonly), _lib.stream_ptr(patches.device)), "transform_backward")
+        return gp, gx, None, None, None, None, None, None
+
+
 def transform(poses, patches, intrinsics, ii, jj, kk, depth=False, valid=False, jacobian=False, tonly=False):
     """reproject patch kk from frame ii into frame jj -> [b,E,P,P,2] (+valid / +Jacobians)"""
     if _fused_ok(poses, patches, intrinsics, depth, (ii, jj, kk)):
         return transform_fused(poses.data, patches, intrinsics, ii, jj, kk, jacobian=jacobian, valid=valid, tonly=tonly)
+    # (translation-only + autograd keeps the composed path: the reference overwrites the rotation slots of Gij IN PLACE,
+    #  which cuts the tangent-space gradient in a way only that graph reproduces; flow_mag, its one caller, runs without grad)
+    if FUSED_AUTOGRAD and not tonly and _fused_ok(poses, patches, intrinsics, depth, (ii, jj, kk), allow_grad=True):
+        coords, v, Ji, Jj, Jz = _TransformFn.apply(poses.data, patches, intrinsics, ii, jj, kk, jacobian, tonly)
+        if jacobian:
+            return coords, v, (Ji, Jj, Jz)
+        if valid:
+            return coords, v
+        return coords
 
     X0 = iproj(patches[:, kk], intrinsics[:, ii])
     Gij = poses[:, jj] * poses[:, ii].inv()

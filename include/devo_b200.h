@@ -168,6 +168,15 @@ int devo_transform_forward(const float* poses, const float* patches, const float
                            const int64_t* ii, const int64_t* jj, const int64_t* kk,
                            float* coords_out, float* valid_out, float* Ji, float* Jj, float* Jz,
                            int E, int P, int layout, int tonly, void* stream);
+/* backward of devo_transform_forward for training (projective_ops.transform under autograd, called 6-8x per training
+ * iteration, enet.py:341,363-372, and inside ba.BA): g_coords [E,P,P,2] (layout 0) / [E,2,P,P] (layout 1), g_Ji / g_Jj
+ * [E,2,6], g_Jz [E,2] -- any may be NULL -- are accumulated (atomicAdd; the caller zeroes) into grad_poses [n_poses,7]
+ * (lietorch convention: gradient w.r.t. a LEFT tangent perturbation in slots 0..5, slot 6 untouched) and grad_patches
+ * [n_patches,3,P,P]. */
+int devo_transform_backward(const float* poses, const float* patches, const float* intrinsics,
+                            const int64_t* ii, const int64_t* jj, const int64_t* kk,
+                            const float* g_coords, const float* g_Ji, const float* g_Jj, const float* g_Jz,
+                            float* grad_poses, float* grad_patches, int E, int P, int layout, int tonly, void* stream);
 
 /* ------------------------------------------------------------------ lietorch_backends */
 /* The 19 entry points of devo/lietorch/src/lietorch.cpp:286-316.  `n` = batch (rows).
