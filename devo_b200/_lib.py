@@ -50,6 +50,9 @@ SIGNATURES = {
     "devo_glue_relu_cast": (_i, [_i, _vp, _vp, _i64, _i, _vp]),
     "devo_glue_heads": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "devo_segment_softmax_sum": (_i, [_vp] * 5 + [_i, _vp, _i, _i, _i, _vp]),
+    "devo_voxel_workspace": (_sz, [_i]),
+    "devo_voxel_normalize": (_i, [_vp, _vp, _c.c_longlong, _i, _i, _vp, _vp, _sz, _vp]),
+    "devo_events_to_voxel": (_i, [_vp, _vp, _vp, _vp, _c.c_longlong, _vp, _i, _i, _i, _vp]),
     "devo_gru_workspace": (_sz, [_i, _i]),
     "devo_gru_state_floats": (_sz, [_i]),
     "devo_gru_state_gather": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _vp]),

@@ -20,7 +20,7 @@ path: `patchify(image)` is any callable returning the per-frame features (the re
 """
 import torch
 
-from . import cuda_ba, cuda_corr, projective_ops as pops
+from . import cuda_ba, cuda_corr, projective_ops as pops  # noqa: I001
 from .lietorch import SE3
 from .update import GruState, PackedUpdateWeights
 
@@ -37,6 +37,7 @@ class VOConfig:
     MOTION_MODEL = "DAMPED_LINEAR"
     MOTION_DAMPING = 0.5
     MIXED_PRECISION = True
+    NORM = "std"
 
     def __init__(self, **kw):
         for k, v in kw.items():
@@ -237,6 +238,12 @@ class PatchGraphVO:
     def __call__(self, tstamp, image, intrinsics, scale=1.0):
         if (self.n + 1) >= self.N:
             raise RuntimeError("PatchGraphVO: keyframe buffer too small")
+        if torch.is_tensor(image):                        # voxel normalisation of the frame (devo.py:419-452), on the device
+            from . import voxel
+            image = voxel.normalize_frame(image[None, None].float(), self.cfg.NORM)
+            if image is None:
+                return                                    # 'rescale' with an empty polarity: the reference skips the frame
+            image = image[0, 0]
         fe = self.patchify(image)
         n, M, mem = self.n, self.M, self.mem
         self.tlist.append(tstamp)

@@ -281,6 +281,19 @@ int devo_gru_state_gather(const float* src, int src_layout, int src_rows, const 
 int devo_gru_update(const devo_gru_weights_t* weights, const devo_gru_io_t* io, int dtype, void* workspace,
                     size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ frame front */
+/* Voxel-grid normalisation (utils/voxel_utils.py:6-52; devo/devo.py:419-452): x, y [groups][n_per_group] f32 (y may alias x).
+ * mode 0 "std": standardise the NON-ZERO entries of each group with their own mean / std (zeros stay zero), applied only if
+ * every group has a non-zero entry (voxel_utils.py:18); mode 1 "rescale": positives / max, negatives / -min (1e-5 when a
+ * polarity is absent).  stats_out (optional) [groups][5] = nnz, sum, sumsq, max, min.  Deterministic; two launches. */
+size_t devo_voxel_workspace(int groups);
+int devo_voxel_normalize(const float* x, float* y, long long n_per_group, int groups, int mode, float* stats_out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+/* Event stream -> voxel grid (utils/event_utils.py:180-231): xs, ys f32, ts f64 (sorted), ps f32 (0 or -1: negative) of
+ * n_events events are ACCUMULATED into grid [bins][H][W] f32 (the caller zeroes) with trilinear weights. */
+int devo_events_to_voxel(const float* xs, const float* ys, const double* ts, const float* ps, long long n_events,
+                         float* grid, int bins, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

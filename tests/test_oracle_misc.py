@@ -168,3 +168,20 @@ def test_c_corr_oracle_matches_torch_oracle():
             b = corr_c.corr_forward(P["gmap"], P["pyramid"][l], P["coords"] / s, P["kk"], P["jj"], 3)
             assert b.shape == a.shape
             assert (a - b.double()).abs().max().item() <= 1e-5 * max(a.abs().max().item(), 1.0)
+
+
+def test_voxel_oracle_matches_reference_golden():
+    """oracle/voxel.py against tests/golden/voxel.pt, generated by the reference's own utils/voxel_utils.py::std / rescale and
+    utils/event_utils.py::to_voxel_grid (tests/golden/make_golden_voxel.py)"""
+    import os
+    from oracle import voxel as ovox
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "voxel.pt"), weights_only=False)
+    assert torch.equal(ovox.std(g["vox"]), g["std_seq"])
+    assert torch.equal(ovox.std(g["vox"], sequence=False), g["std_frame"])
+    assert torch.equal(ovox.rescale(g["vox"]), g["rescale"])
+    e = g["events"]
+    assert torch.equal(ovox.to_voxel_grid(e["xs"], e["ys"], e["ts"], e["ps"].copy(), H=24, W=32, nb_of_time_bins=5), g["grid"])
+    # an empty group leaves std untouched (voxel_utils.py:18)
+    z = g["vox"].clone()
+    z[1] = 0
+    assert torch.equal(ovox.std(z), z)
