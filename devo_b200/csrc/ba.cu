@@ -921,10 +921,9 @@ static int launch_accumulate(const BaLayout& L, char* w, float* poses, float* pa
                              int t0, int nfree, int n_poses, int EB, int GB, size_t smem, int apply_update,
                              int do_accumulate, int itr, cudaStream_t s, const int32_t* perm_p, const int32_t* gstart_p,
                              const int64_t* gkey_p, const int32_t* ngroups_p, double* sys_out = nullptr) {
-  static size_t configured = 0;
-  if (smem > configured) {
+  static devo::SmemConfig configured;
+  if (configured.need(smem)) {
     DEVO_CUDA(cudaFuncSetAttribute(ba_accumulate_kernel<EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
   }
   DEVO_CUDA(devo::launch_pdl(ba_accumulate_kernel<EPT>, dim3(L.grid), dim3(kAccThreads), smem, s,
       poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, perm_p, gstart_p, gkey_p, ngroups_p,
@@ -1100,10 +1099,9 @@ int devo_ba_sharded_solve(float* poses, const double* sys, int E, int n_poses, i
   double* dX = (double*)((char*)workspace + L.dX);
 #define SOLVE(K_)                                                                                              \
   do {                                                                                                         \
-    static size_t configured = 0;                                                                              \
-    if (smem > configured) {                                                                                   \
+    static devo::SmemConfig configured;                                                                        \
+    if (configured.need(smem)) {                                                                               \
       DEVO_CUDA(cudaFuncSetAttribute(ba_solve_kernel<K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      configured = smem;                                                                                       \
     }                                                                                                          \
     ba_solve_kernel<K_><<<1, kSolveThreads, smem, s>>>(poses, sys, dX, status, t0, nfree, itr);                \
   } while (0)
@@ -1135,10 +1133,9 @@ int devo_ba_sharded_solve_peer(float* poses, const void* peer_ptrs_dev, int worl
   const int parity = (int)(epoch & 1);
 #define SOLVEP(K_)                                                                                              \
   do {                                                                                                          \
-    static size_t configured = 0;                                                                               \
-    if (smem > configured) {                                                                                    \
+    static devo::SmemConfig configured;                                                                         \
+    if (configured.need(smem)) {                                                                                \
       DEVO_CUDA(cudaFuncSetAttribute(ba_solve_peer_kernel<K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      configured = smem;                                                                                        \
     }                                                                                                           \
     ba_solve_peer_kernel<K_><<<1, kSolveThreads, smem, s>>>(poses, (const unsigned long long*)peer_ptrs_dev, world, rank, \
                                                             (unsigned long long)epoch, parity, nsys, sum_buf, dX, status, t0, nfree, itr); \

@@ -86,6 +86,19 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
 #define DEVO_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
 #define DEVO_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: remember, per device ordinal, the largest size
+// already configured for one kernel (a process-wide flag would leave every device but the first unconfigured).
+struct SmemConfig {
+  size_t hw[64] = {};
+  // true when the attribute has to be (re)set on the current device to cover `smem` bytes
+  bool need(size_t smem) {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if (smem > hw[d]) { hw[d] = smem; return true; }
+    return false;
+  }
+};
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace devo

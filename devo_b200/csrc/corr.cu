@@ -244,10 +244,9 @@ static int corr_fwd_launch(const void* fmap1, const void* fmap2, const float* co
   const int PP = P * P, D = 2 * R + 2;
   const size_t smem = ((size_t)C * PP + (size_t)PP * D * D) * sizeof(acc_t) + (size_t)PP * 16;
   DEVO_REQUIRE(smem <= 200 * 1024, DEVO_ECAPACITY, "corr_forward: C*P*P too large for shared memory");
-  static size_t configured = 0;
-  if (smem > configured) {
+  static devo::SmemConfig configured;
+  if (configured.need(smem)) {
     DEVO_CUDA(cudaFuncSetAttribute(corr_forward_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
   }
   corr_forward_kernel<T><<<dim3(E, B), kCorrThreads, smem, s>>>((const T*)fmap1, (const T*)fmap2, coords, ii, jj,
                                                                 (T*)out, Np, Nf, C, H, W, E, P, R);
@@ -266,10 +265,9 @@ static int corr_bwd_launch(const void* fmap1, const void* fmap2, const float* co
   if (E == 0) return DEVO_OK;
   const size_t smem = ((size_t)C * PP + (size_t)PP * D * D) * sizeof(acc_t) + (size_t)PP * 16;
   DEVO_REQUIRE(smem <= 200 * 1024, DEVO_ECAPACITY, "corr_backward: C*P*P too large for shared memory");
-  static size_t configured = 0;
-  if (smem > configured) {
+  static devo::SmemConfig configured;
+  if (configured.need(smem)) {
     DEVO_CUDA(cudaFuncSetAttribute(corr_backward_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
   }
   corr_backward_kernel<T><<<dim3(E, B), kCorrThreads, smem, s>>>((const T*)fmap1, (const T*)fmap2, coords, ii, jj,
                                                                  grad, (T*)g1, (T*)g2, Np, Nf, C, H, W, E, P, R);

@@ -734,11 +734,8 @@ template <typename T>
 static int launch_fast(const CUtensorMap* maps, const FastParams& prm, cudaStream_t s) {
   const size_t smem = 1024 + (size_t)kStages * kStageBytes + (size_t)kEpiGroups * 2 * kVsFloats * sizeof(float) +
                       (size_t)kCoordRing * kSlotBytes + (size_t)kRecRing * kRecWords * 4 + 40 * sizeof(uint64_t);
-  static bool configured = false;
-  if (!configured) {
-    DEVO_CUDA(cudaFuncSetAttribute(corr_fast_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  static devo::SmemConfig configured;
+  if (configured.need(smem)) DEVO_CUDA(cudaFuncSetAttribute(corr_fast_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = prm.items < 148 ? prm.items : 148;
   DEVO_CUDA(devo::launch_pdl(corr_fast_kernel<T>, dim3(grid), dim3(kThreads), smem, s, maps[0], maps[1], maps[2], maps[3], maps[4], prm));
   DEVO_LAUNCH_CHECK("corr_lookup_fused");

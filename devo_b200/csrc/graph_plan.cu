@@ -210,12 +210,9 @@ static int launch_small(const int64_t* ka, const int64_t* kb, int E, int32_t* pe
                         int32_t* gstart, int64_t* gkey, int32_t* ngroups, int64_t* ix, int64_t* jx,
                         void* ws, cudaStream_t s) {
   using P = PlanSmall<NT, IPT>;
-  static bool configured = false;
+  static devo::SmemConfig configured;
   const int smem = (int)sizeof(typename P::Temp);
-  if (!configured) {
-    DEVO_CUDA(cudaFuncSetAttribute(plan_small_kernel<NT, IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  if (configured.need((size_t)smem)) DEVO_CUDA(cudaFuncSetAttribute(plan_small_kernel<NT, IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int64_t* sorted_a = (int64_t*)ws;
   int32_t* perm_ws = (int32_t*)((char*)ws + align_up((size_t)E * 8));
   plan_small_kernel<NT, IPT><<<1, NT, smem, s>>>(ka, kb, E, perm, gid, gstart, gkey, ngroups, ix, jx,

@@ -113,6 +113,9 @@ class UpdateOperator:
             self._side3.wait_stream(cur)
             with torch.cuda.stream(self._side3):
                 self.ingest_frame(idx, fmap, gmap_patches, imap_patches, overlap=False)
+            for t in (fmap, gmap_patches, imap_patches):
+                if t is not None and t.is_cuda:          # the caller may drop its inputs right away: the caching allocator must
+                    t.record_stream(self._side3)         # not hand their memory out while the packing kernels still read it
             self._ingest_pending = True
             return
         f = fmap.reshape(1, self.C, self.H, self.W).to(self.feat_dtype)
@@ -210,4 +213,7 @@ class UpdateOperator:
         return g
 
     def replay(self):
+        if self._ingest_pending:                         # an overlapped ingest issued OUTSIDE the captured graph: join it here
+            torch.cuda.current_stream(self.device).wait_stream(self._side3)
+            self._ingest_pending = False
         self._graph.replay()
