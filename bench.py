@@ -619,61 +619,78 @@ def run_ours(args, rank, world, local_rank):
 def run_e2e(op, wl, dev, steps):
     """The same step as `value` (ingest of the newly arrived frame + one update iteration), end to end from HOST buffers:
 
-      copy stream     H2D of the new frame's features (fmap, gmap, imap) from pinned memory into a double-buffered
-                      staging area -- sensor data, independent of the previous step, so it is prefetched while the
-                      previous step computes
-      compute stream  H2D of the state the operator API takes and that the caller may have edited since the last step
-                      (poses, patches, intrinsics, edge list: uploaded in order), the captured step, D2H of the updated
-                      poses and depths into pinned memory.  The recurrent hidden state stays on the device.
+      copy stream     ONE H2D copy per step of a pinned host arena -- the new frame's features (fmap, gmap, imap: sensor data,
+                      independent of the previous step, so the copy runs while the previous step computes) followed by the
+                      state the operator API takes and that the caller may have edited since the last step (poses, patches,
+                      intrinsics, edge list) -- into a double-buffered device staging arena
+      compute stream  one CUDA-graph replay per step (one graph per staging buffer): state refresh from the staging arena,
+                      frame ingest, graph plans, update iteration, and the D2H copy of the updated poses and depths into
+                      pinned memory (a memcpy node of the same graph).  The recurrent hidden state stays on the device.
       host            consumes step k-1's result while step k runs (at most two steps in flight)
 
     Every step's copies are inside the timed region (wall clock between two device synchronisations)."""
     M, Nf = wl["patches_per_frame"], wl["n_frames"]
     f = Nf - 1
-    pin = lambda t: t.contiguous().pin_memory()
-    host_frame = dict(fmap=pin(wl["fmap"][f]), gmap=pin(wl["gmap"][f * M:(f + 1) * M]), imap=pin(wl["imap"][f * M:(f + 1) * M]))
-    # The hidden state `net` is the operator's own recurrent state: it is written by the update operator only and never
-    # exists on the host in the reference either (devo.py keeps pg.net on the device), so it is not re-uploaded.
-    # one pinned mirror of the engine's state arena (poses, patches, intrinsics, edge list): ONE H2D copy per step
-    host_arena = torch.zeros(op.state_arena.numel(), dtype=torch.uint8).pin_memory()
+    feats = dict(fmap=wl["fmap"][f].contiguous(), gmap=wl["gmap"][f * M:(f + 1) * M].contiguous(), imap=wl["imap"][f * M:(f + 1) * M].contiguous())
+    # ---- one pinned host arena: [frame features | state arena]
+    lay, off = {}, 0
+    for k, v in feats.items():
+        lay[k] = (off, v.shape, v.dtype)
+        off += (v.numel() * v.element_size() + 255) // 256 * 256
+    state_off = off
+    total = off + op.state_arena.numel()
+    host_in = torch.zeros(total, dtype=torch.uint8).pin_memory()
+    for k, v in feats.items():
+        o, shape, dt = lay[k]
+        host_in[o:o + v.numel() * v.element_size()].view(dt).view(shape).copy_(v)
     for name, src in (("poses", wl["poses0"][None]), ("patches", wl["patches0"][None]), ("intrinsics", wl["intrinsics"][None]),
                       ("ii", wl["ii"]), ("jj", wl["jj"]), ("kk", wl["kk"])):
         o, shape, dt = op.state_layout[name]
         v = src.to(dt).contiguous()
-        host_arena[o:o + v.numel() * v.element_size()].view(dt).view(shape).copy_(v)
+        host_in[state_off + o:state_off + o + v.numel() * v.element_size()].view(dt).view(shape).copy_(v)
     state_bytes = sum(int(torch.tensor(shape).prod()) * torch.empty((), dtype=dt).element_size() for _, shape, dt in op.state_layout.values())
-    stage = [{k: torch.empty_like(v, device=dev) for k, v in host_frame.items()} for _ in range(2)]
-    inbox = {k: torch.empty_like(v, device=dev) for k, v in host_frame.items()}
-    out_p = [torch.empty(Nf, 7, dtype=torch.float32).pin_memory() for _ in range(2)]
-    out_d = [torch.empty(Nf * M, dtype=torch.float32).pin_memory() for _ in range(2)]
-    h2d = sum(v.numel() * v.element_size() for v in host_frame.values()) + state_bytes
-    d2h = out_p[0].numel() * 4 + out_d[0].numel() * 4
+    h2d = sum(v.numel() * v.element_size() for v in feats.values()) + state_bytes
+    stage = [torch.empty(total, dtype=torch.uint8, device=dev) for _ in range(2)]
+
+    def view(buf, k):
+        o, shape, dt = lay[k]
+        n = 1
+        for d in shape:
+            n *= d
+        return buf[o:o + n * torch.empty((), dtype=dt).element_size()].view(dt).view(shape)
+    out_host = [torch.empty(Nf * 7 + Nf * M, dtype=torch.float32).pin_memory() for _ in range(2)]
+    out_dev = torch.empty(Nf * 7 + Nf * M, dtype=torch.float32, device=dev)
+    d2h = out_host[0].numel() * 4
     cur = torch.cuda.current_stream(dev)
     copy_s = torch.cuda.Stream(device=dev)
 
-    def body():
-        # state upload from pinned host memory: ONE memcpy node of the step's CUDA graph (fixed host address)
-        op.state_arena.copy_(host_arena, non_blocking=True)
+    def body(b):
+        op.state_arena.copy_(stage[b][state_off:], non_blocking=True)      # the state the caller uploaded this step
         torch.add(op.ii * 12345, op.jj, out=op.pair_key)
-        op.ingest_frame(f, inbox["fmap"], inbox["gmap"], inbox["imap"], overlap=True)
+        op.ingest_frame(f, view(stage[b], "fmap"), view(stage[b], "gmap"), view(stage[b], "imap"), overlap=True)
         op._iteration(reset_geometry=False)
+        out_dev[:Nf * 7].copy_(op.poses.view(-1))
+        out_dev[Nf * 7:].copy_(op.patches[0, :, 2, 1, 1])
+        out_host[b].copy_(out_dev, non_blocking=True)                        # D2H of the result: a node of the step's graph
 
     with torch.no_grad():
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            for k in host_frame:
-                inbox[k].copy_(host_frame[k])
-            body()
-            body()
+            for b in range(2):
+                stage[b].copy_(host_in)
+            body(0)
+            body(1)
         cur.wait_stream(side)
         torch.cuda.synchronize(dev)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            body()
+        graphs = []
+        for b in range(2):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body(b)
+            graphs.append(g)
         ev_in = [torch.cuda.Event() for _ in range(2)]
-        ev_free = [torch.cuda.Event() for _ in range(2)]
-        ev_out = [torch.cuda.Event() for _ in range(2)]
+        ev_done = [torch.cuda.Event() for _ in range(2)]
         results = []
 
         def run(n):
@@ -681,23 +698,17 @@ def run_e2e(op, wl, dev, steps):
                 b = k & 1
                 with torch.cuda.stream(copy_s):
                     if k >= 2:
-                        copy_s.wait_event(ev_free[b])              # staging buffer b was consumed by step k-2
-                    for name, v in host_frame.items():
-                        stage[b][name].copy_(v, non_blocking=True)
+                        copy_s.wait_event(ev_done[b])              # staging buffer b was consumed by step k-2
+                    stage[b].copy_(host_in, non_blocking=True)     # H2D of this step's inputs
                     ev_in[b].record(copy_s)
                 cur.wait_event(ev_in[b])
-                for name in host_frame:
-                    inbox[name].copy_(stage[b][name], non_blocking=True)
-                ev_free[b].record(cur)
-                g.replay()                                         # state H2D + frame ingest + update iteration
-                out_p[b].copy_(op.poses[0], non_blocking=True)
-                out_d[b].copy_(op.patches[0, :, 2, 1, 1], non_blocking=True)
-                ev_out[b].record(cur)
+                graphs[b].replay()                                 # state refresh + ingest + update iteration + D2H of the result
+                ev_done[b].record(cur)
                 if k >= 1:
-                    ev_out[b ^ 1].synchronize()                    # the host reads step k-1's result while step k runs
-                    results.append(float(out_p[b ^ 1][Nf - 1, 0]))
-            ev_out[(n - 1) & 1].synchronize()
-            results.append(float(out_p[(n - 1) & 1][Nf - 1, 0]))
+                    ev_done[b ^ 1].synchronize()                   # the host reads step k-1's result while step k runs
+                    results.append(float(out_host[b ^ 1][(Nf - 1) * 7]))
+            ev_done[(n - 1) & 1].synchronize()
+            results.append(float(out_host[(n - 1) & 1][(Nf - 1) * 7]))
 
         run(4)
         torch.cuda.synchronize(dev)
@@ -710,10 +721,11 @@ def run_e2e(op, wl, dev, steps):
         dt = sorted(dts)[1]
     return dict(value=round(steps / dt, 2), unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                 steps=steps, seconds=dt,
-                note="host pinned inputs every step: new frame's features (prefetched on a copy stream, double-buffered) + poses, "
-                     "patches, intrinsics and edge list (uploaded in order; the recurrent hidden state stays on the device, as "
-                     "in the reference); result = poses + depths read back; "
-                     "wall clock between device synchronisations, <= 2 steps in flight; median of 3 runs of `steps` steps")
+                note="host pinned inputs every step: ONE H2D copy of the new frame's features + poses, patches, intrinsics and "
+                     "edge list (copy stream, double-buffered staging; the recurrent hidden state stays on the device, as in the "
+                     "reference); one CUDA-graph replay (state refresh, ingest, plans, update iteration, D2H of poses + depths "
+                     "into pinned memory); wall clock between device synchronisations, <= 2 steps in flight; median of 3 "
+                     "runs of `steps` steps")
 
 
 # ----------------------------------------------------------------------------------------------
