@@ -24,77 +24,85 @@ template <> __device__ __forceinline__ void unpack8f<__nv_bfloat16>(uint4 u, flo
 #pragma unroll
   for (int k = 0; k < 4; k++) { const float2 f = __bfloat1622float2(h[k]); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
 }
+// blockDim = (16 chunk-threads, P row-parts, GPC groups): a CTA owns 128 channels of GPC consecutive groups; part p of a
+// group scans its rows s0+p, s0+p+P, ... -- P is chosen so that a part has <= 4 rows, i.e. ALL loads of a thread (perm,
+// then 8 independent 16-byte g / f loads) are in flight at once: the kernel is two L2 round trips plus a shared-memory merge.
 template <typename T>
-__global__ void __launch_bounds__(128) segment_softmax_sum_vec_kernel(const T* __restrict__ g, const T* __restrict__ f,
+__global__ void __launch_bounds__(512) segment_softmax_sum_vec_kernel(const T* __restrict__ g, const T* __restrict__ f,
                                                                       const int32_t* __restrict__ perm, const int32_t* __restrict__ gstart,
-                                                                      const int32_t* __restrict__ ngroups, T* __restrict__ y, int dim) {
-  extern __shared__ float red[];   // [parts][3][128]
+                                                                      const int32_t* __restrict__ ngroups, T* __restrict__ y, int dim, int max_groups) {
+  extern __shared__ float red[];   // [GPC][P][3][128]
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   DEVO_PDL_WAIT();
-  const int grp = blockIdx.x;
+  const int P = blockDim.y, part = threadIdx.y, gl = threadIdx.z;
+  const int grp = blockIdx.x * blockDim.z + gl;
   const int G = *ngroups;
-  const int parts = blockDim.y, part = threadIdx.y;
   const int c0 = (blockIdx.y * 16 + threadIdx.x) * 8;        // first of this thread's 8 channels
-  T* yo = y + (size_t)grp * dim + c0;
-  if (grp >= G) {   // padding rows of the fixed-size output
-    if (part == 0) *reinterpret_cast<uint4*>(yo) = make_uint4(0u, 0u, 0u, 0u);
-    return;
-  }
-  const int s0 = gstart[grp], s1 = gstart[grp + 1];
+  const bool in_range = grp < max_groups;
+  const bool live = in_range && grp < G;
   float m[8], den[8], num[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) { m[k] = -INFINITY; den[k] = 0.f; num[k] = 0.f; }
-  for (int s = s0 + part; s < s1; s += 4 * parts) {
-    uint4 gq[4], fq[4];
-    bool ok[4];
+  if (live) {
+    const int s0 = gstart[grp], s1 = gstart[grp + 1];
+    for (int s = s0 + part; s < s1; s += 4 * P) {
+      uint4 gq[4], fq[4];
+      int rows[4];
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int ss = s + u * parts;
-      ok[u] = ss < s1;
-      if (ok[u]) {
-        const size_t r = (size_t)perm[ss] * dim + c0;
-        gq[u] = *reinterpret_cast<const uint4*>(g + r);
-        fq[u] = *reinterpret_cast<const uint4*>(f + r);
-      }
-    }
+      for (int u = 0; u < 4; u++) { const int ss = s + u * P; rows[u] = ss < s1 ? perm[ss] : -1; }
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      if (!ok[u]) continue;
-      float gv[8], fv[8];
-      unpack8f<T>(gq[u], gv);
-      unpack8f<T>(fq[u], fv);
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        if (gv[k] > m[k]) {
-          const float sc = __expf(m[k] - gv[k]);   // exp(-inf) = 0 on the first row
-          den[k] *= sc; num[k] *= sc; m[k] = gv[k];
+      for (int u = 0; u < 4; u++) {
+        if (rows[u] >= 0) {
+          const size_t r = (size_t)rows[u] * dim + c0;
+          gq[u] = *reinterpret_cast<const uint4*>(g + r);
+          fq[u] = *reinterpret_cast<const uint4*>(f + r);
         }
-        const float e = __expf(gv[k] - m[k]);
-        den[k] += e;
-        num[k] += e * fv[k];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (rows[u] < 0) continue;
+        float gv[8], fv[8];
+        unpack8f<T>(gq[u], gv);
+        unpack8f<T>(fq[u], fv);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          if (gv[k] > m[k]) {
+            const float sc = __expf(m[k] - gv[k]);   // exp(-inf) = 0 on the first row
+            den[k] *= sc; num[k] *= sc; m[k] = gv[k];
+          }
+          const float e = __expf(gv[k] - m[k]);
+          den[k] += e;
+          num[k] += e * fv[k];
+        }
       }
     }
   }
+  float* rg = red + (size_t)gl * P * 3 * 128;
   const int t = threadIdx.x * 8;
 #pragma unroll
   for (int k = 0; k < 8; k++) {
-    red[(part * 3 + 0) * 128 + t + k] = m[k];
-    red[(part * 3 + 1) * 128 + t + k] = den[k];
-    red[(part * 3 + 2) * 128 + t + k] = num[k];
+    rg[(part * 3 + 0) * 128 + t + k] = m[k];
+    rg[(part * 3 + 1) * 128 + t + k] = den[k];
+    rg[(part * 3 + 2) * 128 + t + k] = num[k];
   }
   __syncthreads();
-  // merge: thread (x, part) finishes channel t' = part * 16 + x ... all 128 channels over the block's threads
-  for (int ch = threadIdx.y * 16 + threadIdx.x; ch < 128; ch += 16 * parts) {
-    float mm = -INFINITY;
-    for (int p = 0; p < parts; p++) mm = fmaxf(mm, red[(p * 3 + 0) * 128 + ch]);
-    float d = 0.f, n = 0.f;
-    for (int p = 0; p < parts; p++) {
-      const float mp = red[(p * 3 + 0) * 128 + ch];
-      const float sc = (mp > -INFINITY) ? __expf(mp - mm) : 0.f;
-      d += sc * red[(p * 3 + 1) * 128 + ch];
-      n += sc * red[(p * 3 + 2) * 128 + ch];
+  if (!in_range) return;
+  // merge the parts: the 16 x P threads of a group share its 128 channels
+  for (int ch = part * 16 + threadIdx.x; ch < 128; ch += 16 * P) {
+    float out = 0.f;
+    if (live) {
+      float mm = -INFINITY;
+      for (int p = 0; p < P; p++) mm = fmaxf(mm, rg[(p * 3 + 0) * 128 + ch]);
+      float d = 0.f, n = 0.f;
+      for (int p = 0; p < P; p++) {
+        const float mp = rg[(p * 3 + 0) * 128 + ch];
+        const float sc = (mp > -INFINITY) ? __expf(mp - mm) : 0.f;
+        d += sc * rg[(p * 3 + 1) * 128 + ch];
+        n += sc * rg[(p * 3 + 2) * 128 + ch];
+      }
+      out = d > 0.f ? n / d : 0.f;
     }
-    y[(size_t)grp * dim + blockIdx.y * 128 + ch] = ElemTraits<T>::from_float(d > 0.f ? n / d : 0.f);
+    y[(size_t)grp * dim + blockIdx.y * 128 + ch] = ElemTraits<T>::from_float(out);     // padding groups: zeros
   }
 }
 
@@ -182,12 +190,15 @@ extern "C" int devo_segment_softmax_sum(const void* g, const void* f, const int3
 #define SEG(T) DEVO_CUDA(devo::launch_pdl(segment_softmax_sum_kernel<T>, grid, block, smem, s, (const T*)g, (const T*)f, perm, gstart, ngroups, (T*)y_out, dim))
   if ((dtype == DEVO_F16 || dtype == DEVO_BF16) && dim % 128 == 0 &&
       ((((uintptr_t)g | (uintptr_t)f | (uintptr_t)y_out) & 15) == 0)) {
-    dim3 vblock(16, parts), vgrid(max_groups, dim / 128);
-    const size_t vsmem = (size_t)parts * 3 * 128 * sizeof(float);
+    int P = 1;                                              // row-parts: <= 4 rows per part, at most 32
+    while (P < 32 && P * 4 < avg_rows) P <<= 1;
+    const int GPC = 32 / P;                                 // groups per CTA: 512 threads
+    dim3 vblock(16, P, GPC), vgrid((max_groups + GPC - 1) / GPC, dim / 128);
+    const size_t vsmem = (size_t)32 * 3 * 128 * sizeof(float);
     if (dtype == DEVO_F16)
-      DEVO_CUDA(devo::launch_pdl(segment_softmax_sum_vec_kernel<__half>, vgrid, vblock, vsmem, s, (const __half*)g, (const __half*)f, perm, gstart, ngroups, (__half*)y_out, dim));
+      DEVO_CUDA(devo::launch_pdl(segment_softmax_sum_vec_kernel<__half>, vgrid, vblock, vsmem, s, (const __half*)g, (const __half*)f, perm, gstart, ngroups, (__half*)y_out, dim, max_groups));
     else
-      DEVO_CUDA(devo::launch_pdl(segment_softmax_sum_vec_kernel<__nv_bfloat16>, vgrid, vblock, vsmem, s, (const __nv_bfloat16*)g, (const __nv_bfloat16*)f, perm, gstart, ngroups, (__nv_bfloat16*)y_out, dim));
+      DEVO_CUDA(devo::launch_pdl(segment_softmax_sum_vec_kernel<__nv_bfloat16>, vgrid, vblock, vsmem, s, (const __nv_bfloat16*)g, (const __nv_bfloat16*)f, perm, gstart, ngroups, (__nv_bfloat16*)y_out, dim, max_groups));
     DEVO_LAUNCH_CHECK("segment_softmax_sum");
     return DEVO_OK;
   }
