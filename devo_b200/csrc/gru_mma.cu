@@ -181,6 +181,30 @@ template <> __device__ __forceinline__ uint32_t mul2<__nv_bfloat16>(uint32_t a, 
 template <typename T> __device__ __forceinline__ uint4 mul8(uint4 a, uint4 b) {
   return make_uint4(mul2<T>(a.x, b.x), mul2<T>(a.y, b.y), mul2<T>(a.z, b.z), mul2<T>(a.w, b.w));
 }
+// sigmoid of eight packed 16-bit values, rounded to T:  0.5 * tanh(0.5 x) + 0.5  with ONE MUFU per PAIR (tanh.approx.f16x2 /
+// .bf16x2) instead of ex2 + rcp per element.  The gated layers were MUFU-bound (16 MUFU per 8 columns at 4 lanes/clk/SMSP =
+// 512 cycles per chunk round with 4 warps per scheduler: tools/gru_timing.py).  Absolute error <= 2^-11 (tanh.approx) / 2,
+// i.e. below half an ulp of T for sigmoid values >= 0.25 and <= 2.5e-4 absolute everywhere.
+template <typename T> __device__ __forceinline__ uint32_t sigmoid2(uint32_t x);
+template <> __device__ __forceinline__ uint32_t sigmoid2<__half>(uint32_t x) {
+  const __half2 half = __float2half2_rn(0.5f);
+  __half2 h = __hmul2(*reinterpret_cast<const __half2*>(&x), half);
+  uint32_t t, hu = *reinterpret_cast<const uint32_t*>(&h);
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(hu));
+  const __half2 r = __hfma2(*reinterpret_cast<const __half2*>(&t), half, half);
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+template <> __device__ __forceinline__ uint32_t sigmoid2<__nv_bfloat16>(uint32_t x) {
+  const __nv_bfloat162 half = __float2bfloat162_rn(0.5f);
+  __nv_bfloat162 h = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&x), half);
+  uint32_t t, hu = *reinterpret_cast<const uint32_t*>(&h);
+  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(t) : "r"(hu));
+  const __nv_bfloat162 r = __hfma2(*reinterpret_cast<const __nv_bfloat162*>(&t), half, half);
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+template <typename T> __device__ __forceinline__ uint4 sigmoid8(uint4 u) {
+  return make_uint4(sigmoid2<T>(u.x), sigmoid2<T>(u.y), sigmoid2<T>(u.z), sigmoid2<T>(u.w));
+}
 // round eight floats to T and back (the autocast rounding point of a half-typed intermediate)
 template <typename T> __device__ __forceinline__ void rnd8(float* v) { unpack8<T>(pack8<T>(v), v); }
 
@@ -552,12 +576,8 @@ struct Epi {
           }
         } else {   // EPI_GATED_LN / EPI_GATED_HEADS:  x = n + half(half(sigmoid(gate)) * res)
           float g[8];
-          unpack8<T>(cur_[2], g);
-#pragma unroll
-          for (int k = 0; k < 8; k++) g[k] = sigmoidf_(g[k]);
-          // half(sigmoid) * half(res) rounded to half: one packed multiply per pair is exactly that rounding
-          const uint4 gh = pack8<T>(g);
-          unpack8<T>(mul8<T>(gh, oh), g);
+          // half(sigmoid(gate)) * half(res) rounded to half: packed 16-bit arithmetic is exactly that dtype flow
+          unpack8<T>(mul8<T>(sigmoid8<T>(cur_[2]), oh), g);
           const float4 a = as_f4(cur_[0]), b = as_f4(cur_[1]);
           float x[8] = {a.x + g[0], a.y + g[1], a.z + g[2], a.w + g[3], b.x + g[4], b.y + g[5], b.z + g[6], b.w + g[7]};
           if constexpr (EPI == EPI_GATED_LN) {
