@@ -68,12 +68,28 @@ def main():
     names = ["corr+norm", "c1", "c2+agg_kk g,f", "h_kk+agg_ij g,f", "h_ij+gru+heads"]
     nl = [3, 2, 4, 3, 7]
     reps = int(os.environ.get("GRU_REPS", 32))
+    # absolute view (ns clock shared by all SMs): when CTA 0 of each launch started, finished its prologue, issued its first
+    # MMA, finished its last epilogue and exited -- the distance between "last epilogue of launch k" and "first MMA of
+    # launch k+1" is what a kernel boundary (+ the gather prologue, + a segment reduction for two of them) costs
+    base = None
+    rows = []
+    for k, n in enumerate(nl):
+        k16 = (len(names) * (reps - 1) + k) % 16
+        s_ = [buf[48 * k16 + q] for q in range(48)]
+        if base is None:
+            base = s_[0]
+        s0 = s_[0] if s_[0] else base                     # fused launch: only program 0 has the kernel-start stamp
+        rows.append((names[k], (s0 - base) / 1e3, (s_[2] - base) / 1e3, (s_[4] - base) / 1e3, (s_[9 + 6 * (n - 1)] - base) / 1e3, (s_[3] - base) / 1e3))
+    print("absolute (us): launch            start   pro-done  first-mma  last-epi   exit   | boundary = next first-mma - last-epi")
+    for i, r in enumerate(rows):
+        nxt = "%.1f" % (rows[i + 1][3] - r[4]) if i + 1 < len(rows) else "-"
+        print("               %-16s %7.1f %9.1f %10.1f %9.1f %7.1f  | %s" % (r + (nxt,)))
     for k, (nm, n) in enumerate(zip(names, nl)):
         k16 = (len(names) * (reps - 1) + k) % 16
         s = [buf[48 * k16 + q] for q in range(48)]
         cyc = [buf[16 * 48 + 48 * k16 + q] for q in range(48)]
         mhz = (cyc[3] - cyc[0]) / max(s[3] - s[0], 1) * 1e3
-        t0 = s[0]
+        t0 = s[0] if s[0] else base
         rel = lambda q: (s[q] - t0) / 1e3 if s[q] else float("nan")
         # per layer: MMA issue start - issue end | epilogue: N-tile 0 ready, N-tile 1 ready, chunk loop done, layer done
         line = "%-16s setup %.1f pro %.1f |" % (nm, rel(1), rel(2))
