@@ -34,10 +34,12 @@
 //   * pose block indices >= t1 are treated as fixed (the reference would write out of bounds).
 //   * a non-positive-definite system sets *status = iteration+1 and skips the remaining
 //     iterations instead of throwing from inside the launch sequence.
+#include <cooperative_groups.h>
 #include "common.cuh"
 
 extern "C" size_t devo_graph_plan_workspace(int E);
 
+namespace cg = cooperative_groups;
 namespace {
 
 constexpr int kAccThreads = 512;
@@ -172,7 +174,8 @@ static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 static int acc_grid(int E) {
   int g = (E + 63) / 64;
   if (g < 1) g = 1;
-  if (g > 148) g = 148;
+  g = (g + 7) / 8 * 8;         // whole clusters of kGroupCtas CTAs (the partial systems are reduced through DSMEM)
+  if (g > 144) g = 144;
   return g;
 }
 
@@ -193,11 +196,26 @@ static BaLayout ba_layout(int E, int nfree) {
   L.Q = off;       off += al(Em * 8);
   L.U = off;       off += al(Em * 8);
   L.Ek = off;      off += al(Em * (size_t)(n6 > 0 ? n6 : 1) * 8);
-  L.partials = off; off += al((size_t)(L.grid + (L.grid + 7) / 8) * L.nent * 8);   // per-CTA + per-group partials
+  L.partials = off; off += al((size_t)((L.grid + 7) / 8) * L.nent * 8);   // one partial system per cluster of 8 CTAs
   L.dX = off;      off += al((size_t)(n6 > 0 ? n6 : 1) * 8);
-  L.ticket = off;  off += al(4 * 32);   // [0] group counter, [1..] per-group CTA counters (grid <= 148 => <= 19 groups)
+  L.ticket = off;  off += al(4 * 32);   // [0]: how many CTAs of the running launch have delivered their slice
   L.total = off;
   return L;
+}
+
+// shared memory of the accumulate CTA: RCAP = 2 EB + GB dense rows of LD doubles, coef[RCAP], zj[RCAP], then the selection
+// bitsets (one per pair of pose blocks, EB bits each)
+static bool acc_shape(int n6, int nfree, int& EB, int& GB, size_t& smem) {
+  const int LD = n6 + 1;
+  const size_t nblk = (size_t)(nfree > 0 ? nfree : 0) + 1;
+  const size_t sel_max = nblk * (nblk + 1) / 2 * (size_t)(kAccThreads / 32) * 4;
+  const int rows_cap = (int)((kAccSmemBudget - sel_max) / ((size_t)(LD + 2) * 8));
+  EB = rows_cap * 2 / 5;
+  if (EB > kAccThreads) EB = kAccThreads;
+  GB = rows_cap - 2 * EB;
+  if (GB > EB) GB = EB;
+  smem = (size_t)(2 * EB + GB) * (LD + 2) * 8 + nblk * (nblk + 1) / 2 * (size_t)((EB + 31) / 32) * 4;
+  return EB >= 8 && GB >= 1;
 }
 
 // upper-triangular (row-major, a<=b) linear index -> (a,b) for an m x m matrix
@@ -221,7 +239,7 @@ __device__ __forceinline__ void tri_decode(int idx, int m, int& a, int& b) {
 // Afterwards A_ik (i>k) = L_ik d_k and y = L^-1 y; warp 0 finishes x = L^-T D^-1 y with shuffles.
 // S positive definite  <=>  every pivot d_k = A_kk > 0 (same acceptance test as Cholesky).
 #ifdef DEVO_BA_TIMING
-__device__ long long g_ba_clk[16];
+__device__ long long g_ba_clk[24];
 __device__ __forceinline__ long long ba_now() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define BA_STAMP(i) do { if (threadIdx.x == 0) g_ba_clk[i] = ba_now(); } while (0)   /* ns, comparable across SMs */
 #else
@@ -238,12 +256,15 @@ __device__ __forceinline__ long long ba_now() { long long t; asm volatile("mov.u
 // finalises the next pivot also stores 1/d (the only fp64 division of the step).  Afterwards
 // A_ik = L_ik d_k, y = L^-1 y; warp 0 finishes x = L^-T D^-1 y.  S positive definite <=> every pivot > 0
 // (the same acceptance test as Cholesky).
-// 1/d for a pivot: single-precision seed + two Newton steps in fp64 (relative error ~1e-16; about half the
-// latency of the IEEE division sequence, which sits on the critical path of every elimination step)
+// 1/d for a pivot.  It sits on the critical path of every elimination step, so its latency was measured on B200
+// (tools/fp64_probe.cu): single-precision seed + two Newton steps 144 cycles (the two F2F conversions dominate), IEEE
+// division 80 cycles, `rcp.approx.ftz.f64` (MUFU.RCP64H, ~20 good bits) + two Newton steps in fp64 (relative error
+// ~1e-16 for normal d; the callers reject d <= 0 and non-finite d before using it) is what is used here.
 __device__ __forceinline__ double pivot_rcp(double d) {
-  double r = (double)(1.0f / (float)d);
-  r = r * (2.0 - d * r);
-  r = r * (2.0 - d * r);
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  r = fma(r, fma(-d, r, 1.0), r);
+  r = fma(r, fma(-d, r, 1.0), r);
   return r;
 }
 
@@ -258,22 +279,27 @@ __device__ void ba_solve_device(unsigned char* smem_raw, float* poses, const dou
   double* y = A + n * (n + 1) / 2;
   __shared__ int s_fail;
   const int tid = threadIdx.x;
-  if (*status != 0) return;
   if (n == 0) return;
   if (tid == 0) s_fail = 0;
+  // (another CTA of this launch may have flagged a failure: the load is issued here and consumed after the reduction
+  //  below, so its L2 round trip overlaps the partial sums')
+  const int st_in = *(volatile int32_t*)status;
 
   // fixed-order reduction of the partial sums; entry (a,b), a<=b of the (n+1)x(n+1) augmented matrix.
   // 8 independent accumulators keep 8 L2 loads in flight; combined in a fixed tree => deterministic.
   for (int idx = tid; idx < nent; idx += kSolveThreads) {
+    // (<= 19 group partials of a 148-CTA grid: all loads of an entry are issued at once, predicated, and summed in a
+    //  fixed tree)
     double s8[8];
 #pragma unroll
     for (int u = 0; u < 8; u++) s8[u] = 0.0;
-    int p = 0;
-    for (; p + 8 <= nparts; p += 8) {
+    for (int p = 0; p < nparts; p += 24) {
+      double t[24];
 #pragma unroll
-      for (int u = 0; u < 8; u++) s8[u] += __ldcg(&partials[(size_t)(p + u) * nent + idx]);
+      for (int u = 0; u < 24; u++) t[u] = (p + u < nparts) ? __ldcg(&partials[(size_t)(p + u) * nent + idx]) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 24; u++) s8[u & 7] += t[u];
     }
-    for (; p < nparts; p++) s8[0] += __ldcg(&partials[(size_t)p * nent + idx]);
     double s = ((s8[0] + s8[1]) + (s8[2] + s8[3])) + ((s8[4] + s8[5]) + (s8[6] + s8[7]));
     int a, b;
     tri_decode(idx, LD, a, b);
@@ -284,6 +310,7 @@ __device__ void ba_solve_device(unsigned char* smem_raw, float* poses, const dou
       A[b * (b + 1) / 2 + a] = s;                         // symmetric: store as lower (b,a)
     }
   }
+  if (st_in != 0) return;                                 // uniform
   __syncthreads();
   BA_STAMP(2);
 
@@ -408,24 +435,23 @@ __device__ void ba_solve_device(unsigned char* smem_raw, float* poses, const dou
     return;
   }
   BA_STAMP(4);
-  // back substitution  x_K = w_K - sum_{i >= 6k+6} L[i,K]^T x_i, pose blocks in descending order; warp 0, lanes over
-  // rows i, fixed-order shuffle reduction (deterministic)
+  // back substitution  x_K = w_K - sum_{i >= 6k+6} L[i,K]^T x_i, pose blocks in descending order, by warp 0: lane
+  // (part, a) = (lane / 6, lane % 6) sums every 5th row of column a (a chain of <= ceil(n/5) DFMAs), the 5 parts are added
+  // in a fixed order through shared memory.  (Lanes over rows with a 5-level double-precision shuffle tree per column
+  // took ~1000 cycles per pose block: 3.1 us of the solve at 7 free poses.)
   if (tid < 32) {
+    double* part = Wb;                                    // [5][6] scratch (the factor blocks are no longer needed)
+    const int a = tid % 6, pr = tid / 6;
     for (int k = nfree - 2; k >= 0; k--) {
       const int K0 = 6 * k;
-      double part[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-      for (int i = K0 + 6 + tid; i < n; i += 32) {
-        const double xi = y[i];
-        const double* li = A + i * (i + 1) / 2 + K0;
-#pragma unroll
-        for (int a = 0; a < 6; a++) part[a] += li[a] * xi;
+      if (tid < 30) {
+        double acc = 0.0;
+#pragma unroll 8
+        for (int i = K0 + 6 + pr; i < n; i += 5) acc += A[i * (i + 1) / 2 + K0 + a] * y[i];
+        part[pr * 6 + a] = acc;
       }
-#pragma unroll
-      for (int a = 0; a < 6; a++) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part[a] += __shfl_xor_sync(0xffffffffu, part[a], o);
-      }
-      if (tid < 6) y[K0 + tid] -= part[tid];
+      __syncwarp();
+      if (tid < 6) y[K0 + tid] -= (((part[tid] + part[6 + tid]) + (part[12 + tid] + part[18 + tid])) + part[24 + tid]);
       __syncwarp();
     }
   }
@@ -481,43 +507,66 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
   double* X = reinterpret_cast<double*>(smem_raw);
   double* coef = X + (size_t)RCAP * LD;
   double* zj = coef + RCAP;
-  unsigned int* rmask = reinterpret_cast<unsigned int*>(zj + RCAP);   // per row: which 6-column pose blocks are non-zero (bit 30: the residual column)
+  // per (pose block A <= pose block B) pair -- the residual column counts as block `nfree` --: the bitset of the batch's
+  // edges whose two residual rows are non-zero in both blocks
+  unsigned int* sel = reinterpret_cast<unsigned int*>(zj + RCAP);
+  const int nblk = nfree + 1;
+  const int npairs = nblk * (nblk + 1) / 2;
   __shared__ int s_batch[3];   // gs, ge, bad
   __shared__ float s_intr[4];
   __shared__ int s_gstart[kMaxGroupsPerCta + 1];
 
   const int tid = threadIdx.x;
-  DEVO_PDL_WAIT();       // launched with programmatic stream serialisation: the previous iteration's results are needed from here on
-  DEVO_PDL_TRIGGER();
-#ifdef DEVO_BA_TIMING
-  if (blockIdx.x == 0 && tid == 0) g_ba_clk[0] = ba_now();
-#endif
-  const int st = *status;
-  if (st != 0) {               // an earlier iteration failed: do nothing (reference would have thrown)
-    if (do_accumulate) {
-      const int nent = (n6 + 1) * (n6 + 2) / 2;
-      for (int q = tid; q < nent; q += kAccThreads) partials[(size_t)blockIdx.x * nent + q] = 0.0;
-      if (sys_out && blockIdx.x == 0) {   // sharded form: peers must see a system and this rank's failure
-        for (int q = tid; q < nent; q += kAccThreads) sys_out[q] = 0.0;
-        if (tid == 0) sys_out[nent] = 1.0;
+  const int nent = (n6 + 1) * (n6 + 2) / 2;
+  // Launched with programmatic stream serialisation.  What the previous Gauss-Newton iteration writes (poses, depths, dX,
+  // Q/u/E_k, partials, tickets, status) may only be touched after the wait; the edge list and its grouping are inputs of
+  // the whole call, so from the second iteration on (`itr > 0`: the predecessor is this kernel) the chain of dependent
+  // index loads perm -> ii/jj/kk is issued BEFORE the wait and overlaps the predecessor's solve.
+  int pre_n = -1, pre_i = 0, pre_j = 0, pre_k = 0, pre_G = 0;
+  bool pre = false;
+  if (itr > 0 && do_accumulate) {
+    pre = true;
+    pre_G = *ngroups_p;
+    const int gpc_ = (pre_G + gridDim.x - 1) / gridDim.x;
+    const int g0_ = blockIdx.x * gpc_, g1_ = min(pre_G, g0_ + gpc_);
+    if (g0_ < g1_) {
+      const int eb_ = gstart[g0_];
+      if (eb_ + tid < gstart[g1_]) {          // (a superset of the first batch; unused values are simply dropped)
+        pre_n = perm[eb_ + tid];
+        pre_i = (int)ii[pre_n]; pre_j = (int)jj[pre_n]; pre_k = (int)kk[pre_n];
       }
     }
-    return;
+    if (tid < 4) s_intr[tid] = intrinsics[tid];
   }
-  if (tid < 4) s_intr[tid] = intrinsics[tid];   // only intrinsics[0] is used (:232-238)
-  const int G = *ngroups_p;
+  DEVO_PDL_WAIT();
+  DEVO_PDL_TRIGGER();
+#ifdef DEVO_BA_TIMING
+  if (blockIdx.x == (gridDim.x >> 1) && tid == 0) g_ba_clk[0] = ba_now();
+  if (blockIdx.x == (gridDim.x >> 1) && tid == 0 && do_accumulate) g_ba_clk[16] = ba_now();
+#endif
+  const int st = *status;
+  if (st != 0 && (!do_accumulate || nfree <= 0)) return;
+  // An earlier iteration (or, for a CTA that starts late, another CTA of this launch) failed: the reference would have
+  // thrown.  The CTA does no work but still takes part in the cluster reduction below -- its peers wait for it -- with a
+  // zero partial; the solving CTA sees the status and leaves the poses alone.
+  const bool skip = (st != 0);
+  if (skip && sys_out && blockIdx.x == 0) {   // sharded form: peers must see a system and this rank's failure
+    for (int q = tid; q < nent; q += kAccThreads) sys_out[q] = 0.0;
+    if (tid == 0) sys_out[nent] = 1.0;
+  }
+  if (!pre && tid < 4) s_intr[tid] = intrinsics[tid];   // only intrinsics[0] is used (:232-238)
+  const int G = pre ? pre_G : *ngroups_p;
   const int gpc = (G + gridDim.x - 1) / gridDim.x;
   const int g0 = blockIdx.x * gpc;
-  const int g1 = min(G, g0 + gpc);
+  const int g1 = skip ? g0 : min(G, g0 + gpc);
   const float lm = lmbda[0];
-  const int nent = (n6 + 1) * (n6 + 2) / 2;
   const bool gs_cached = (g1 - g0) <= kMaxGroupsPerCta;
   if (gs_cached)
     for (int q = tid; q <= g1 - g0; q += kAccThreads) s_gstart[q] = gstart[g0 + q];
   auto GS = [&](int g) { return gs_cached ? s_gstart[g - g0] : gstart[g]; };
 
   // ---- prologue: apply the previous iteration's depth update to the patches this CTA owns
-  if (apply_update) {
+  if (apply_update && !skip) {
     for (int g = g0 + tid; g < g1; g += kAccThreads) {
       double acc = Ug[g];
       const double* ek = Ekg + (size_t)g * (n6 > 0 ? n6 : 1);
@@ -532,22 +581,51 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
     }
   }
   if (!do_accumulate) return;
+#ifdef DEVO_BA_TIMING
+  if (blockIdx.x == (gridDim.x >> 1) && tid == 0) g_ba_clk[17] = ba_now();
+#endif
   __syncthreads();   // depth updates of this CTA's patches are visible to its own threads; s_intr ready
   const float fx = s_intr[0], fy = s_intr[1], cx = s_intr[2], cy = s_intr[3];
 
-  // entries owned by this thread
-  double acc[EPT];
-  unsigned int ab[EPT], need[EPT];
+  // ---- who sums what.  Every entry (a,b) of the upper triangle of [S|y] is summed by NC adjacent lanes ("chunks"): lane
+  // c takes the c-th part of the batch's edge slots and every NC-th per-patch row; the NC partial sums are combined in
+  // a fixed tree at the end, so the result does not depend on timing.  Entries are dealt PAIR-MAJOR (all entries of
+  // block pair (0,0), then (0,1), ...): a warp holds 32/NC entries of one or two block pairs, i.e. its lanes walk the same
+  // edge lists below.  Measured at S8 (tools/ba_timing.py): NC = 1 -> the accumulate phase takes 5.3 us (the lists of
+  // the CTA's own source frame, 64 edges, are a serial chain in one warp); NC = 4 balances the lanes but pays the
+  // per-slot set-up four times and most rounds of four edges run half empty: 3.2 us for the lists yet a slower
+  // iteration overall (43.8 vs 42.0 us).  NC = 1 it is.
+  constexpr int NC = 1;
+  constexpr int SL = EPT * NC;                          // (entry, chunk) slots per thread
+  constexpr int EPS = kAccThreads / NC;                 // entries per round of slots
+  const int chunk = tid & (NC - 1);
+  double acc[SL];
+  unsigned int ab[SL];                                  // (a << 16) | b; an empty slot points at (0,0) and is never stored
+  unsigned int live = 0u;                               // bit q: slot q holds an entry
 #pragma unroll
-  for (int q = 0; q < EPT; q++) {
+  for (int q = 0; q < SL; q++) {
     acc[q] = 0.0;
-    int idx = tid + q * kAccThreads;
-    int a = 0, b = 0;
-    if (idx < nent) tri_decode(idx, LD, a, b);
-    ab[q] = ((unsigned)a << 16) | (unsigned)b;
-    // an edge row only touches the pose blocks of its two frames (12 of the 6N columns): entry (a,b) needs both blocks
-    need[q] = (idx < nent) ? ((1u << (a / 6)) | ((b == n6) ? (1u << 30) : (1u << (b / 6)))) : 0xffffffffu;
+    ab[q] = 0u;
+    const int idx = tid / NC + q * EPS;
+    if (idx < nent) {
+      // block row A: a diagonal pair (21 entries), nfree-1-A off-diagonal pairs (36) and the residual-column pair (6)
+      int a, b, A = 0, off = 0;
+      while (A < nfree && off + 27 + 36 * (nfree - 1 - A) <= idx) { off += 27 + 36 * (nfree - 1 - A); A++; }
+      int r = idx - off;
+      if (A == nfree) { a = n6; b = n6; }                                  // the y^T y corner
+      else if (r < 21) {                                                   // diagonal block: x <= y
+        int x = 0;
+        while (r >= 6 - x) { r -= 6 - x; x++; }
+        a = 6 * A + x; b = 6 * A + x + r;
+      } else if (r < 21 + 36 * (nfree - 1 - A)) {
+        r -= 21;
+        a = 6 * A + (r % 36) / 6; b = 6 * (A + 1 + r / 36) + (r % 6);
+      } else { a = 6 * A + (r - 21 - 36 * (nfree - 1 - A)); b = n6; }
+      ab[q] = ((unsigned)a << 16) | (unsigned)b;
+      live |= 1u << q;
+    }
   }
+  const int SW = (EB + 31) >> 5;                        // bitset words per pair
 
   int gs = g0;
   while (gs < g1) {
@@ -574,13 +652,15 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
     EdgeTerms T;
     int bi = 0, bj = 0;
     if (tid < ne) {
-      const int n = perm[ebase + tid];
-      const int i = (int)ii[n], j = (int)jj[n], k = (int)kk[n];
+      int n, i, j, k;
+      if (pre && gs == g0 && pre_n >= 0) { n = pre_n; i = pre_i; j = pre_j; k = pre_k; }
+      else { n = perm[ebase + tid]; i = (int)ii[n]; j = (int)jj[n]; k = (int)kk[n]; }
       edge_terms(poses, patches, fx, fy, cx, cy, target, weight, i, j, k, n, PP, centre, T);
       bi = i - t0; bj = j - t0;
     }
-    // zero the dense rows
+    // zero the dense rows and the selection bitsets
     for (int q = tid; q < R * LD; q += kAccThreads) X[q] = 0.0;
+    for (int q = tid; q < npairs * SW; q += kAccThreads) sel[q] = 0u;
     __syncthreads();
 
     // ---- two dense rows per edge
@@ -604,13 +684,29 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
         }
         coef[r] = on ? (double)T.w[rho] : 0.0;
         zj[r] = on ? (double)T.Jz[rho] : 0.0;
-        rmask[r] = (1u << 30) | (fi ? (1u << bi) : 0u) | (fj ? (1u << bj) : 0u);
+      }
+      if (T.active) {                                   // an inactive edge has zero coefficients: listed nowhere
+        // the blocks this edge's rows touch, ascending and distinct; every pair of them gets the edge's bit
+        int blk[3];
+        int nb = 0;
+        const int b0 = fi ? bi : -1, b1 = fj ? bj : -1;
+        if (b0 >= 0 && b1 >= 0 && b0 != b1) { blk[nb++] = min(b0, b1); blk[nb++] = max(b0, b1); }
+        else if (b0 >= 0) blk[nb++] = b0;
+        else if (b1 >= 0) blk[nb++] = b1;
+        blk[nb++] = nfree;
+        const unsigned int bit = 1u << (tid & 31);
+        const int word = tid >> 5;
+        for (int x = 0; x < nb; x++)
+          for (int y2 = x; y2 < nb; y2++) {
+            const int A = blk[x], B = blk[y2];
+            atomicOr(&sel[(A * nblk - A * (A - 1) / 2 + (B - A)) * SW + word], bit);
+          }
       }
     }
     __syncthreads();
 
 #ifdef DEVO_BA_TIMING
-    if (blockIdx.x == 0 && tid == 0 && gs == g0) g_ba_clk[8] = ba_now();
+    if (blockIdx.x == (gridDim.x >> 1) && tid == 0 && gs == g0) g_ba_clk[8] = ba_now();
 #endif
     // ---- per patch: C_k, u_k, Q_k and the dense vector E_k (one warp per patch, lanes over columns)
     {
@@ -635,7 +731,6 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
         if (lane == 0) {
           erow[n6] = u;
           coef[2 * ne + gi] = -Q;
-          rmask[2 * ne + gi] = 0xffffffffu;               // E_k is dense
           Qg[g] = Q;
           Ug[g] = u;
         }
@@ -644,81 +739,129 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
     __syncthreads();
 
 #ifdef DEVO_BA_TIMING
-    if (blockIdx.x == 0 && tid == 0 && gs == g0) g_ba_clk[9] = ba_now();
+    if (blockIdx.x == (gridDim.x >> 1) && tid == 0 && gs == g0) g_ba_clk[9] = ba_now();
 #endif
     // ---- reduced-system partial: acc(a,b) += coef_r * X[r][a] * X[r][b]
-    // An edge row only touches the pose blocks of its two frames, so most (row, entry) pairs are exact zeros: one
-    // block-mask test per EDGE (its two residual rows share the mask) decides whether an entry takes part at all.
-    // The loop is instruction-issue bound (measured 12 us for 136 rows with a test per row and entry), hence the
-    // pairing and the unrolling; the summation order (row index ascending) is unchanged => same bits as before.
-#pragma unroll 4
-    for (int e = 0; e < ne; e++) {
-      const double c0 = coef[2 * e], c1 = coef[2 * e + 1];
-      const unsigned int m = rmask[2 * e];
-      const double* row0 = X + (size_t)(2 * e) * LD;
-      const double* row1 = row0 + LD;
+    // An edge row only touches the pose blocks of its two frames, so most (row, entry) pairs are exact zeros: each slot
+    // walks the bitset of its block pair, restricted to its chunk of the edge slots -- only edges that do contribute, in
+    // ascending order.  (A mask test per edge and entry made this loop instruction-issue bound: 7.8 us at S8.)
+    const int cw = (ne + NC - 1) / NC;
+    const int lo = chunk * cw, hi = min(ne, lo + cw);
 #pragma unroll
-      for (int q = 0; q < EPT; q++) {
-        if ((m & need[q]) == need[q]) {
-          const int a = ab[q] >> 16, b = ab[q] & 0xffff;
-          if (c0 != 0.0) acc[q] += c0 * row0[a] * row0[b];
-          if (c1 != 0.0) acc[q] += c1 * row1[a] * row1[b];
+    for (int q = 0; q < SL; q++) {
+      if (!((live >> q) & 1u) || lo >= hi) continue;
+      const int a = ab[q] >> 16, b = ab[q] & 0xffff;
+      const int A = a / 6, B = b / 6;                     // a == n6 / b == n6: block nfree (the residual column)
+      const unsigned int* sp = sel + (A * nblk - A * (A - 1) / 2 + (B - A)) * SW;
+      double s_ = acc[q];
+      for (int w = lo >> 5; w <= (hi - 1) >> 5; w++) {
+        unsigned int bits = sp[w];
+        if ((w << 5) < lo) bits &= 0xffffffffu << (lo & 31);
+        if (((w + 1) << 5) > hi) bits &= 0xffffffffu >> (32 - (hi & 31));      // (here hi & 31 != 0)
+        while (bits) {
+          // four listed edges per round: all 24 shared loads are issued before the (ordered) chain of 8 DFMAs
+          int e4[4];
+          bool ok[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            ok[u] = bits != 0u;
+            e4[u] = ok[u] ? (w << 5) + __ffs(bits) - 1 : 0;
+            bits &= bits - 1u;                            // (0 & 0xffffffff == 0)
+          }
+          double c0[4], c1[4], x0a[4], x0b[4], x1a[4], x1b[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const double* row0 = X + (size_t)(2 * e4[u]) * LD;
+            c0[u] = coef[2 * e4[u]]; c1[u] = coef[2 * e4[u] + 1];
+            x0a[u] = row0[a]; x0b[u] = row0[b]; x1a[u] = row0[LD + a]; x1b[u] = row0[LD + b];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            if (ok[u] && c0[u] != 0.0) s_ += c0[u] * x0a[u] * x0b[u];
+            if (ok[u] && c1[u] != 0.0) s_ += c1[u] * x1a[u] * x1b[u];
+          }
         }
       }
+      acc[q] = s_;
     }
-    for (int r = 2 * ne; r < R; r++) {                 // the dense per-patch rows E_k (coefficient -Q_k)
+#ifdef DEVO_BA_TIMING
+    if (blockIdx.x == (gridDim.x >> 1) && tid == 0 && gs == g0) g_ba_clk[12] = ba_now();
+    if (blockIdx.x == (gridDim.x >> 1) && tid == 433 && gs == g0) g_ba_clk[14] = ba_now();
+#endif
+    for (int r = 2 * ne + chunk; r < R; r += NC) {     // the dense per-patch rows E_k (coefficient -Q_k)
       const double c = coef[r];
       if (c == 0.0) continue;
       const double* row = X + (size_t)r * LD;
 #pragma unroll
-      for (int q = 0; q < EPT; q++) {
+      for (int q = 0; q < SL; q++) {
         const int a = ab[q] >> 16, b = ab[q] & 0xffff;
         acc[q] += c * row[a] * row[b];
       }
     }
+#ifdef DEVO_BA_TIMING
+    if (blockIdx.x == (gridDim.x >> 1) && tid == 0 && gs == g0) g_ba_clk[13] = ba_now();
+    if (blockIdx.x == (gridDim.x >> 1) && tid == 433 && gs == g0) g_ba_clk[15] = ba_now();
+#endif
     __syncthreads();
+#ifdef DEVO_BA_TIMING
+    if (blockIdx.x == (gridDim.x >> 1) && tid == 0 && gs == g0) g_ba_clk[7] = ba_now();
+#endif
     gs = ge;
   }
 
-#pragma unroll
-  for (int q = 0; q < EPT; q++) {
-    int idx = tid + q * kAccThreads;
-    if (idx < nent) partials[(size_t)blockIdx.x * nent + idx] = acc[q];
-  }
+  // ---- reduction of the per-CTA partials + solve + retraction in the same launch ---------------------------------
+  // The grid is launched as clusters of kGroupCtas CTAs.  Every CTA parks its partial system in its own shared memory;
+  // after a cluster barrier CTA r of a cluster adds slice r of the 8 partials in rank order with DSMEM loads and writes
+  // it to the cluster's partial in global memory; one atomic ticket per CTA then elects the last CTA of the grid, which
+  // adds the cluster partials in index order and solves.  What is summed in which order never depends on timing.
+  // (Before: partials through L2, a ticket per group of 8 and a second ticket over the groups -- two fence + atomic +
+  // reload round trips, ~10 us from the first CTA's ticket to the assembled system at S8.)
   (void)n_poses; (void)E;
+  if (nfree <= 0) return;
+  double* Ps = reinterpret_cast<double*>(smem_raw);       // [nent]; the dense rows are dead (barrier at the loop end)
+#pragma unroll
+  for (int q = 0; q < SL; q++) {
+    double v = acc[q];
+    if (NC >= 2) v += __shfl_xor_sync(0xffffffffu, v, 1);          // (c0 + c1), (c2 + c3): IEEE addition commutes, so both
+    if (NC >= 4) v += __shfl_xor_sync(0xffffffffu, v, 2);          // lanes of a pair hold the same bits
+    if (chunk == 0 && ((live >> q) & 1u)) {
+      const int a = ab[q] >> 16, b = ab[q] & 0xffff;
+      Ps[a * LD - a * (a - 1) / 2 + (b - a)] = v;
+    }
+  }
 #ifdef DEVO_BA_TIMING
-  if (blockIdx.x == 0 && tid == 0) g_ba_clk[10] = ba_now();
+  if (blockIdx.x == (gridDim.x >> 1) && tid == 0) g_ba_clk[10] = ba_now();
 #endif
-  // ---- hierarchical reduction + solve + retraction in the same launch (see kGroupCtas above)
-  if (nfree > 0) {
-    const int ngrp = ((int)gridDim.x + kGroupCtas - 1) / kGroupCtas;
+  {
+    cg::cluster_group cl = cg::this_cluster();
+    const int ngrp = (int)gridDim.x / kGroupCtas;
     const int grp = (int)blockIdx.x / kGroupCtas;
-    const int gfirst = grp * kGroupCtas;
-    const int gsize = min(kGroupCtas, (int)gridDim.x - gfirst);
-    double* gpart = partials + (size_t)gridDim.x * nent;   // [ngrp][nent]
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_batch[0] = atomicAdd(&ticket[1 + grp], 1);
-    __syncthreads();
-#ifdef DEVO_BA_TIMING
-    if (blockIdx.x == 0 && tid == 0) g_ba_clk[11] = ba_now();
-#endif
-    if (s_batch[0] == gsize - 1) {                           // last CTA of its group
-      if (tid == 0) ticket[1 + grp] = 0;                     // armed for the next launch
-      __threadfence();
-      for (int idx = tid; idx < nent; idx += kAccThreads) {
+    const int rank = (int)cl.block_rank();
+    double* gpart = partials;                                // [ngrp][nent]
+    cl.sync();                                               // every partial of the cluster is in place (release/acquire)
+    const int slice = (nent + kGroupCtas - 1) / kGroupCtas;
+    for (int q = tid; q < slice; q += kAccThreads) {
+      const int idx = rank * slice + q;
+      if (idx < nent) {
         double t8[kGroupCtas];
 #pragma unroll
-        for (int u = 0; u < kGroupCtas; u++)
-          t8[u] = (u < gsize) ? __ldcg(&partials[(size_t)(gfirst + u) * nent + idx]) : 0.0;
+        for (int u = 0; u < kGroupCtas; u++) t8[u] = cl.map_shared_rank(Ps, u)[idx];
         gpart[(size_t)grp * nent + idx] = ((t8[0] + t8[1]) + (t8[2] + t8[3])) + ((t8[4] + t8[5]) + (t8[6] + t8[7]));
       }
-      __threadfence();
-      __syncthreads();
-      if (tid == 0) s_batch[1] = atomicAdd(&ticket[0], 1);
-      __syncthreads();
-      if (s_batch[1] == ngrp - 1) {                          // last group: solve
-        if (tid == 0) ticket[0] = 0;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_batch[1] = atomicAdd(&ticket[0], 1);
+    __syncthreads();
+#ifdef DEVO_BA_TIMING
+    if (blockIdx.x == (gridDim.x >> 1) && tid == 0) g_ba_clk[11] = ba_now();
+#endif
+    // nobody may leave (or reuse its shared memory) while a peer still reads its partial: a CTA that has its ticket has
+    // finished reading, so the last CTA of the grid may go on at once; the others wait for their cluster at the end
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    {
+      if (s_batch[1] == (int)gridDim.x - 1) {                // last CTA of the grid: solve
+        if (tid == 0) ticket[0] = 0;                         // armed for the next launch
         __threadfence();
         if (sys_out) {
           // edge-sharded form: publish this rank's partial of [S|y] (fixed summation order, no
@@ -736,6 +879,7 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
         BA_STAMP(6);
       }
     }
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   }
 }
 
@@ -925,7 +1069,7 @@ static int launch_accumulate(const BaLayout& L, char* w, float* poses, float* pa
   if (configured.need(smem)) {
     DEVO_CUDA(cudaFuncSetAttribute(ba_accumulate_kernel<EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  DEVO_CUDA(devo::launch_pdl(ba_accumulate_kernel<EPT>, dim3(L.grid), dim3(kAccThreads), smem, s,
+  DEVO_CUDA(devo::launch_pdl_cluster(ba_accumulate_kernel<EPT>, dim3(L.grid), dim3(kAccThreads), kGroupCtas, smem, s,
       poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, perm_p, gstart_p, gkey_p, ngroups_p,
       (double*)(w + L.Q), (double*)(w + L.U), (double*)(w + L.Ek), (double*)(w + L.partials),
       (double*)(w + L.dX), (int32_t*)(w + L.ticket), status, E, PP, centre, t0, nfree, n_poses, EB, GB, apply_update, do_accumulate, itr, sys_out));
@@ -936,7 +1080,7 @@ static int launch_accumulate(const BaLayout& L, char* w, float* poses, float* pa
 extern "C" {
 
 #ifdef DEVO_BA_TIMING
-int devo_ba_debug_clocks(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_ba_clk, sizeof(long long) * 16); }
+int devo_ba_debug_clocks(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_ba_clk, sizeof(long long) * 24); }
 #endif
 
 size_t devo_ba_workspace(int E, int n_free_poses) { return ba_layout(E, n_free_poses).total; }
@@ -978,14 +1122,10 @@ static int ba_forward_impl(float* poses, float* patches, const float* intrinsics
     if (rc != DEVO_OK) return rc;
   }
 
-  const int n6 = L.n6, LD = n6 + 1;
-  int rows_cap = (int)(kAccSmemBudget / ((size_t)(LD + 3) * 8));
-  int EB = rows_cap * 2 / 5;
-  if (EB > kAccThreads) EB = kAccThreads;
-  int GB = rows_cap - 2 * EB;
-  if (GB > EB) GB = EB;
-  DEVO_REQUIRE(EB >= 8 && GB >= 1, DEVO_ECAPACITY, "ba_forward: system too large for shared memory");
-  size_t smem_acc = (size_t)(2 * EB + GB) * (LD + 3) * 8;
+  const int n6 = L.n6;
+  int EB = 0, GB = 0;
+  size_t smem_acc = 0;
+  DEVO_REQUIRE(acc_shape(n6, nfree, EB, GB, smem_acc), DEVO_ECAPACITY, "ba_forward: system too large for shared memory");
   const int ept = (L.nent + kAccThreads - 1) / kAccThreads;
 
 #define ACC(EPT_, APPLY, DOACC, ITR)                                                                         \
@@ -1060,14 +1200,10 @@ int devo_ba_sharded_accumulate(float* poses, float* patches, const float* intrin
     if (rc != DEVO_OK) return rc;
     DEVO_CUDA(cudaMemsetAsync(w + L.ticket, 0, 4 * 32, s));
   }
-  const int n6 = L.n6, LD = n6 + 1;
-  int rows_cap = (int)(kAccSmemBudget / ((size_t)(LD + 3) * 8));
-  int EB = rows_cap * 2 / 5;
-  if (EB > kAccThreads) EB = kAccThreads;
-  int GB = rows_cap - 2 * EB;
-  if (GB > EB) GB = EB;
-  DEVO_REQUIRE(EB >= 8 && GB >= 1, DEVO_ECAPACITY, "ba_sharded_accumulate: system too large for shared memory");
-  const size_t smem_acc = (size_t)(2 * EB + GB) * (LD + 3) * 8;
+  const int n6 = L.n6;
+  int EB = 0, GB = 0;
+  size_t smem_acc = 0;
+  DEVO_REQUIRE(acc_shape(n6, nfree, EB, GB, smem_acc), DEVO_ECAPACITY, "ba_sharded_accumulate: system too large for shared memory");
   const int ept = (L.nent + kAccThreads - 1) / kAccThreads;
   DEVO_REQUIRE(ept <= 24, DEVO_ECAPACITY, "ba_sharded_accumulate: system too large (%d entries)", L.nent);
 #define ACCS(EPT_)                                                                                                \

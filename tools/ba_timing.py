@@ -48,10 +48,13 @@ for iters in (1, 2):
     print("fastba S8, %d iteration(s), graph replay incl. 2 state-reset copies: %.1f us  (status %d)" % (iters, a.elapsed_time(b) * 10, int(status.item())))
 h = ctypes.CDLL(_lib.LIB_PATH)
 if hasattr(h, "devo_ba_debug_clocks"):
-    buf = (ctypes.c_longlong * 16)()
+    buf = (ctypes.c_longlong * 24)()
     h.devo_ba_debug_clocks(buf)
     c = list(buf)
     r = lambda i: (c[i] - c[0]) / 1e3
-    print("CTA 0 (us since kernel start): edge terms done %.1f | E_k done %.1f | partial accumulated %.1f | ticket taken %.1f" % (r(8), r(9), r(10), r(11)))
+    print("last accumulate launch, CTA grid/2: after the PDL wait %.1f | depth update applied %.1f" % (r(16), r(17)))
+    print("CTA grid/2 (us since kernel start): edge terms done %.1f | E_k done %.1f | partial accumulated %.1f | ticket taken %.1f" % (r(8), r(9), r(10), r(11)))
+    print("CTA grid/2 accumulate phase: thread 0 lists done %.1f, E_k rows done %.1f | thread 433 (y^T y corner) lists done %.1f, E_k rows done %.1f | barrier passed %.1f" %
+          (r(12), r(13), r(14), r(15), r(7)))
     print("solving CTA: solve start %.1f | reduced %.1f | owned %.1f | eliminated %.1f | back-substituted %.1f | retracted %.1f" %
           (r(1), r(2), r(3), r(4), r(5), r(6)))
