@@ -203,18 +203,21 @@ static BaLayout ba_layout(int E, int nfree) {
   return L;
 }
 
-// shared memory of the accumulate CTA: RCAP = 2 EB + GB dense rows of LD doubles, coef[RCAP], zj[RCAP], then the selection
-// bitsets (one per pair of pose blocks, EB bits each)
+// shared memory of the accumulate CTA: RCAP = 2 EB + GB dense rows of LD doubles, coef[RCAP], zj[RCAP], the per-patch
+// pre-sums Hg[GB][28], the selection bitsets (one per pair of pose blocks, EB bits each), blk[EB], gbi[GB]
+constexpr int kPre = 28;    // 21 entries of the source frame's diagonal block, 6 of its residual column, the y^T y corner
 static bool acc_shape(int n6, int nfree, int& EB, int& GB, size_t& smem) {
   const int LD = n6 + 1;
   const size_t nblk = (size_t)(nfree > 0 ? nfree : 0) + 1;
-  const size_t sel_max = nblk * (nblk + 1) / 2 * (size_t)(kAccThreads / 32) * 4;
-  const int rows_cap = (int)((kAccSmemBudget - sel_max) / ((size_t)(LD + 2) * 8));
-  EB = rows_cap * 2 / 5;
+  const size_t npairs = nblk * (nblk + 1) / 2;
+  const size_t sel_max = npairs * (size_t)(kAccThreads / 32) * 4;
+  const size_t per_edge = 2 * (size_t)(LD + 2) * 8 + 4, per_group = (size_t)(LD + 2 + kPre) * 8 + 4;
+  const size_t avail = kAccSmemBudget - sel_max;
+  EB = (int)(avail / (per_edge + per_group / 2));
   if (EB > kAccThreads) EB = kAccThreads;
-  GB = rows_cap - 2 * EB;
+  GB = (int)((avail - (size_t)EB * per_edge) / per_group);
   if (GB > EB) GB = EB;
-  smem = (size_t)(2 * EB + GB) * (LD + 2) * 8 + nblk * (nblk + 1) / 2 * (size_t)((EB + 31) / 32) * 4;
+  smem = (size_t)EB * per_edge + (size_t)GB * per_group + npairs * (size_t)((EB + 31) / 32) * 4 + 16;
   return EB >= 8 && GB >= 1;
 }
 
@@ -509,9 +512,12 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
   double* zj = coef + RCAP;
   // per (pose block A <= pose block B) pair -- the residual column counts as block `nfree` --: the bitset of the batch's
   // edges whose two residual rows are non-zero in both blocks
-  unsigned int* sel = reinterpret_cast<unsigned int*>(zj + RCAP);
+  double* Hg = zj + RCAP;                                             // [GB][kPre] per-patch pre-sums (see below)
+  unsigned int* sel = reinterpret_cast<unsigned int*>(Hg + (size_t)GB * kPre);
   const int nblk = nfree + 1;
   const int npairs = nblk * (nblk + 1) / 2;
+  int* s_blk = reinterpret_cast<int*>(sel + (size_t)npairs * ((EB + 31) >> 5));   // [EB] (bi+1) | (bj+1) << 8 | active << 16
+  int* s_gbi = s_blk + EB;                                           // [GB] the patch's free source block, or -1
   __shared__ int s_batch[3];   // gs, ge, bad
   __shared__ float s_intr[4];
   __shared__ int s_gstart[kMaxGroupsPerCta + 1];
@@ -600,7 +606,9 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
   constexpr int EPS = kAccThreads / NC;                 // entries per round of slots
   const int chunk = tid & (NC - 1);
   double acc[SL];
-  unsigned int ab[SL];                                  // (a << 16) | b; an empty slot points at (0,0) and is never stored
+  // a | b << 8 | hcode << 16 | (a / 6) << 24 ; hcode: 0, or 1 + the entry's index in a patch's pre-sums (when the entry
+  // lies in a diagonal block, in the residual column, or is the corner).  An empty slot points at (0,0), never stored.
+  unsigned int ab[SL];
   unsigned int live = 0u;                               // bit q: slot q holds an entry
 #pragma unroll
   for (int q = 0; q < SL; q++) {
@@ -609,19 +617,20 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
     const int idx = tid / NC + q * EPS;
     if (idx < nent) {
       // block row A: a diagonal pair (21 entries), nfree-1-A off-diagonal pairs (36) and the residual-column pair (6)
-      int a, b, A = 0, off = 0;
+      int a, b, hcode = 0, A = 0, off = 0;
       while (A < nfree && off + 27 + 36 * (nfree - 1 - A) <= idx) { off += 27 + 36 * (nfree - 1 - A); A++; }
       int r = idx - off;
-      if (A == nfree) { a = n6; b = n6; }                                  // the y^T y corner
+      if (A == nfree) { a = n6; b = n6; hcode = kPre; }                    // the y^T y corner
       else if (r < 21) {                                                   // diagonal block: x <= y
+        hcode = 1 + r;
         int x = 0;
         while (r >= 6 - x) { r -= 6 - x; x++; }
         a = 6 * A + x; b = 6 * A + x + r;
       } else if (r < 21 + 36 * (nfree - 1 - A)) {
         r -= 21;
         a = 6 * A + (r % 36) / 6; b = 6 * (A + 1 + r / 36) + (r % 6);
-      } else { a = 6 * A + (r - 21 - 36 * (nfree - 1 - A)); b = n6; }
-      ab[q] = ((unsigned)a << 16) | (unsigned)b;
+      } else { a = 6 * A + (r - 21 - 36 * (nfree - 1 - A)); b = n6; hcode = 22 + (a - 6 * A); }
+      ab[q] = (unsigned)a | ((unsigned)b << 8) | ((unsigned)hcode << 16) | ((unsigned)A << 24);
       live |= 1u << q;
     }
   }
@@ -685,54 +694,92 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
         coef[r] = on ? (double)T.w[rho] : 0.0;
         zj[r] = on ? (double)T.Jz[rho] : 0.0;
       }
-      if (T.active) {                                   // an inactive edge has zero coefficients: listed nowhere
-        // the blocks this edge's rows touch, ascending and distinct; every pair of them gets the edge's bit
-        int blk[3];
-        int nb = 0;
-        const int b0 = fi ? bi : -1, b1 = fj ? bj : -1;
-        if (b0 >= 0 && b1 >= 0 && b0 != b1) { blk[nb++] = min(b0, b1); blk[nb++] = max(b0, b1); }
-        else if (b0 >= 0) blk[nb++] = b0;
-        else if (b1 >= 0) blk[nb++] = b1;
-        blk[nb++] = nfree;
-        const unsigned int bit = 1u << (tid & 31);
-        const int word = tid >> 5;
-        for (int x = 0; x < nb; x++)
-          for (int y2 = x; y2 < nb; y2++) {
-            const int A = blk[x], B = blk[y2];
-            atomicOr(&sel[(A * nblk - A * (A - 1) / 2 + (B - A)) * SW + word], bit);
-          }
-      }
+      s_blk[tid] = (fi ? bi + 1 : 0) | ((fj ? bj + 1 : 0) << 8) | (T.active ? (1 << 16) : 0);
     }
     __syncthreads();
 
 #ifdef DEVO_BA_TIMING
     if (blockIdx.x == (gridDim.x >> 1) && tid == 0 && gs == g0) g_ba_clk[8] = ba_now();
 #endif
-    // ---- per patch: C_k, u_k, Q_k and the dense vector E_k (one warp per patch, lanes over columns)
+    // ---- per patch, two warp roles:
+    //  role 0: C_k, u_k, Q_k and the dense vector E_k (lanes over columns)
+    //  role 1: the patch's PRE-SUMS.  In the patch graph every edge of a patch leaves from the patch's own frame, so the
+    //          diagonal block and the residual column of that frame get a term from EVERY edge of the patch -- at S8 a
+    //          list of all 64 edges of the CTA, summed by the one warp that owns those 27 entries (5 us, the critical
+    //          path of the launch).  Here a warp adds them up per patch (28 lanes: 21 + 6 entries and the y^T y corner,
+    //          <= 2 x edges-of-the-patch terms each); the entry owners below then add one number per patch.  The warp
+    //          also files the patch's edges into the block-pair lists -- except under the pairs it has pre-summed.  A
+    //          patch whose edges leave from different (or fixed) frames gets no pre-sum but the corner and keeps its lists.
     {
       const int warp = tid >> 5, lane = tid & 31;
-      for (int gi = warp; gi < ng; gi += kAccThreads / 32) {
+      for (int item = warp; item < 2 * ng; item += kAccThreads / 32) {
+        const int gi = item >> 1;
         const int g = gs + gi;
-        const int r0 = 2 * (GS(g) - ebase), r1 = 2 * (GS(g + 1) - ebase);
-        double C = 0.0, u = 0.0;
-        for (int r = r0; r < r1; r++) {
-          const double wz = coef[r] * zj[r];
-          C += wz * zj[r];
-          u += wz * X[(size_t)r * LD + n6];
-        }
-        const double Q = 1.0 / (C + (double)lm);
-        double* erow = X + (size_t)(2 * ne + gi) * LD;
-        for (int c = lane; c < n6; c += 32) {
-          double e = 0.0;
-          for (int r = r0; r < r1; r++) e += coef[r] * zj[r] * X[(size_t)r * LD + c];
-          erow[c] = e;
-          Ekg[(size_t)g * n6 + c] = e;
-        }
-        if (lane == 0) {
-          erow[n6] = u;
-          coef[2 * ne + gi] = -Q;
-          Qg[g] = Q;
-          Ug[g] = u;
+        const int e0 = GS(g) - ebase, e1 = GS(g + 1) - ebase;
+        const int r0 = 2 * e0, r1 = 2 * e1;
+        if ((item & 1) == 0) {
+          double C = 0.0, u = 0.0;
+          for (int r = r0; r < r1; r++) {
+            const double wz = coef[r] * zj[r];
+            C += wz * zj[r];
+            u += wz * X[(size_t)r * LD + n6];
+          }
+          const double Q = 1.0 / (C + (double)lm);
+          double* erow = X + (size_t)(2 * ne + gi) * LD;
+          for (int c = lane; c < n6; c += 32) {
+            double e = 0.0;
+            for (int r = r0; r < r1; r++) e += coef[r] * zj[r] * X[(size_t)r * LD + c];
+            erow[c] = e;
+            Ekg[(size_t)g * n6 + c] = e;
+          }
+          if (lane == 0) {
+            erow[n6] = u;
+            coef[2 * ne + gi] = -Q;
+            Qg[g] = Q;
+            Ug[g] = u;
+          }
+        } else {
+          const int f = (s_blk[e0] & 0xff) - 1;             // free source block of the first edge, or -1
+          bool same = true;
+          for (int e = e0 + lane; e < e1; e += 32) same = same && (((s_blk[e] & 0xff) - 1) == f);
+          const int gb = (__all_sync(0xffffffffu, same) && f >= 0) ? f : -1;
+          if (lane == 0) s_gbi[gi] = gb;
+          if (lane < kPre && (gb >= 0 || lane == kPre - 1)) {
+            int ca, cb;
+            if (lane < 21) {
+              int x = 0, r = lane;
+              while (r >= 6 - x) { r -= 6 - x; x++; }
+              ca = 6 * gb + x; cb = ca + r;
+            } else if (lane < 27) { ca = 6 * gb + (lane - 21); cb = n6; }
+            else { ca = n6; cb = n6; }
+            double h = 0.0;
+            for (int r = r0; r < r1; r++) {
+              const double* row = X + (size_t)r * LD;
+              h += coef[r] * row[ca] * row[cb];
+            }
+            Hg[gi * kPre + lane] = h;
+          }
+          for (int e = e0 + lane; e < e1; e += 32) {
+            const int blk = s_blk[e];
+            if (!(blk >> 16)) continue;                     // an inactive edge has zero coefficients: listed nowhere
+            // the blocks this edge's rows touch, ascending and distinct (+ the residual column); every pair of them gets
+            // the edge's bit, unless the patch's pre-sums cover the pair
+            int bl[3];
+            int nb = 0;
+            const int b0 = (blk & 0xff) - 1, b1 = ((blk >> 8) & 0xff) - 1;
+            if (b0 >= 0 && b1 >= 0 && b0 != b1) { bl[nb++] = min(b0, b1); bl[nb++] = max(b0, b1); }
+            else if (b0 >= 0) bl[nb++] = b0;
+            else if (b1 >= 0) bl[nb++] = b1;
+            bl[nb++] = nfree;
+            const unsigned int bit = 1u << (e & 31);
+            for (int x = 0; x < nb; x++)
+              for (int y2 = x; y2 < nb; y2++) {
+                const int A = bl[x], B = bl[y2];
+                if (A == nfree) continue;                                   // the corner is always pre-summed
+                if (A == gb && (B == gb || B == nfree)) continue;
+                atomicOr(&sel[(A * nblk - A * (A - 1) / 2 + (B - A)) * SW + (e >> 5)], bit);
+              }
+          }
         }
       }
     }
@@ -750,8 +797,9 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
 #pragma unroll
     for (int q = 0; q < SL; q++) {
       if (!((live >> q) & 1u) || lo >= hi) continue;
-      const int a = ab[q] >> 16, b = ab[q] & 0xffff;
-      const int A = a / 6, B = b / 6;                     // a == n6 / b == n6: block nfree (the residual column)
+      const int a = ab[q] & 0xff, b = (ab[q] >> 8) & 0xff;
+      const int A = ab[q] >> 24, B = b / 6;               // b == n6: block nfree (the residual column)
+      if (A == nfree) continue;                           // the corner has no list (pre-summed per patch)
       const unsigned int* sp = sel + (A * nblk - A * (A - 1) / 2 + (B - A)) * SW;
       double s_ = acc[q];
       for (int w = lo >> 5; w <= (hi - 1) >> 5; w++) {
@@ -788,14 +836,18 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
     if (blockIdx.x == (gridDim.x >> 1) && tid == 0 && gs == g0) g_ba_clk[12] = ba_now();
     if (blockIdx.x == (gridDim.x >> 1) && tid == 433 && gs == g0) g_ba_clk[14] = ba_now();
 #endif
-    for (int r = 2 * ne + chunk; r < R; r += NC) {     // the dense per-patch rows E_k (coefficient -Q_k)
+    for (int gi = chunk; gi < ng; gi += NC) {          // per patch: the dense row E_k (coefficient -Q_k) and the pre-sums
+      const int r = 2 * ne + gi;
       const double c = coef[r];
-      if (c == 0.0) continue;
       const double* row = X + (size_t)r * LD;
+      const double* hg = Hg + gi * kPre;
+      const int gb = s_gbi[gi];
 #pragma unroll
       for (int q = 0; q < SL; q++) {
-        const int a = ab[q] >> 16, b = ab[q] & 0xffff;
+        const int a = ab[q] & 0xff, b = (ab[q] >> 8) & 0xff;
+        const int hcode = (ab[q] >> 16) & 0xff, A = ab[q] >> 24;
         acc[q] += c * row[a] * row[b];
+        if (hcode != 0 && (A == gb || hcode == kPre)) acc[q] += hg[hcode - 1];
       }
     }
 #ifdef DEVO_BA_TIMING
@@ -825,7 +877,7 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
     if (NC >= 2) v += __shfl_xor_sync(0xffffffffu, v, 1);          // (c0 + c1), (c2 + c3): IEEE addition commutes, so both
     if (NC >= 4) v += __shfl_xor_sync(0xffffffffu, v, 2);          // lanes of a pair hold the same bits
     if (chunk == 0 && ((live >> q) & 1u)) {
-      const int a = ab[q] >> 16, b = ab[q] & 0xffff;
+      const int a = ab[q] & 0xff, b = (ab[q] >> 8) & 0xff;
       Ps[a * LD - a * (a - 1) / 2 + (b - a)] = v;
     }
   }
