@@ -287,6 +287,12 @@ __device__ void ba_solve_device(unsigned char* smem_raw, float* poses, const dou
   // (another CTA of this launch may have flagged a failure: the load is issued here and consumed after the reduction
   //  below, so its L2 round trip overlaps the partial sums')
   const int st_in = *(volatile int32_t*)status;
+  // the pose this thread will retract at the very end (tid < nfree <= 25): its L2 round trip is paid here, not there
+  float Pret[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
+  if (tid < nfree) {
+#pragma unroll
+    for (int c = 0; c < 7; c++) Pret[c] = __ldcg(poses + (size_t)(t0 + tid) * 7 + c);
+  }
 
   // fixed-order reduction of the partial sums; entry (a,b), a<=b of the (n+1)x(n+1) augmented matrix.
   // 8 independent accumulators keep 8 L2 loads in flight; combined in a fixed tree => deterministic.
@@ -449,8 +455,18 @@ __device__ void ba_solve_device(unsigned char* smem_raw, float* poses, const dou
       const int K0 = 6 * k;
       if (tid < 30) {
         double acc = 0.0;
-#pragma unroll 8
-        for (int i = K0 + 6 + pr; i < n; i += 5) acc += A[i * (i + 1) / 2 + K0 + a] * y[i];
+        for (int base = K0 + 6 + pr; base < n; base += 40) {
+          double l8[8], x8[8];
+#pragma unroll
+          for (int t = 0; t < 8; t++) {                   // all 16 loads in flight, then the ordered chain
+            const int i = base + 5 * t;
+            const bool in = i < n;
+            l8[t] = in ? A[i * (i + 1) / 2 + K0 + a] : 0.0;
+            x8[t] = in ? y[i] : 0.0;
+          }
+#pragma unroll
+          for (int t = 0; t < 8; t++) acc += l8[t] * x8[t];
+        }
         part[pr * 6 + a] = acc;
       }
       __syncwarp();
@@ -470,16 +486,14 @@ __device__ void ba_solve_device(unsigned char* smem_raw, float* poses, const dou
     return;
   }
   // pose retraction  T <- Exp(dX) T   (:160-188)
-  for (int p = tid; p < nfree; p += kSolveThreads) {
-    float xi[6], P[7];
+  if (tid < nfree) {                                      // (nfree <= kMaxN6 / 6 < kSolveThreads)
+    float xi[6];
 #pragma unroll
-    for (int c = 0; c < 6; c++) xi[c] = (float)y[6 * p + c];
-    float* dst = poses + (size_t)(t0 + p) * 7;
+    for (int c = 0; c < 6; c++) xi[c] = (float)y[6 * tid + c];
+    float* dst = poses + (size_t)(t0 + tid) * 7;
+    retract_pose(xi, Pret);
 #pragma unroll
-    for (int c = 0; c < 7; c++) P[c] = dst[c];
-    retract_pose(xi, P);
-#pragma unroll
-    for (int c = 0; c < 7; c++) dst[c] = P[c];
+    for (int c = 0; c < 7; c++) dst[c] = Pret[c];
   }
 }
 
@@ -524,76 +538,7 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
 
   const int tid = threadIdx.x;
   const int nent = (n6 + 1) * (n6 + 2) / 2;
-  // Launched with programmatic stream serialisation.  What the previous Gauss-Newton iteration writes (poses, depths, dX,
-  // Q/u/E_k, partials, tickets, status) may only be touched after the wait; the edge list and its grouping are inputs of
-  // the whole call, so from the second iteration on (`itr > 0`: the predecessor is this kernel) the chain of dependent
-  // index loads perm -> ii/jj/kk is issued BEFORE the wait and overlaps the predecessor's solve.
-  int pre_n = -1, pre_i = 0, pre_j = 0, pre_k = 0, pre_G = 0;
-  bool pre = false;
-  if (itr > 0 && do_accumulate) {
-    pre = true;
-    pre_G = *ngroups_p;
-    const int gpc_ = (pre_G + gridDim.x - 1) / gridDim.x;
-    const int g0_ = blockIdx.x * gpc_, g1_ = min(pre_G, g0_ + gpc_);
-    if (g0_ < g1_) {
-      const int eb_ = gstart[g0_];
-      if (eb_ + tid < gstart[g1_]) {          // (a superset of the first batch; unused values are simply dropped)
-        pre_n = perm[eb_ + tid];
-        pre_i = (int)ii[pre_n]; pre_j = (int)jj[pre_n]; pre_k = (int)kk[pre_n];
-      }
-    }
-    if (tid < 4) s_intr[tid] = intrinsics[tid];
-  }
-  DEVO_PDL_WAIT();
-  DEVO_PDL_TRIGGER();
-#ifdef DEVO_BA_TIMING
-  if (blockIdx.x == (gridDim.x >> 1) && tid == 0) g_ba_clk[0] = ba_now();
-  if (blockIdx.x == (gridDim.x >> 1) && tid == 0 && do_accumulate) g_ba_clk[16] = ba_now();
-#endif
-  const int st = *status;
-  if (st != 0 && (!do_accumulate || nfree <= 0)) return;
-  // An earlier iteration (or, for a CTA that starts late, another CTA of this launch) failed: the reference would have
-  // thrown.  The CTA does no work but still takes part in the cluster reduction below -- its peers wait for it -- with a
-  // zero partial; the solving CTA sees the status and leaves the poses alone.
-  const bool skip = (st != 0);
-  if (skip && sys_out && blockIdx.x == 0) {   // sharded form: peers must see a system and this rank's failure
-    for (int q = tid; q < nent; q += kAccThreads) sys_out[q] = 0.0;
-    if (tid == 0) sys_out[nent] = 1.0;
-  }
-  if (!pre && tid < 4) s_intr[tid] = intrinsics[tid];   // only intrinsics[0] is used (:232-238)
-  const int G = pre ? pre_G : *ngroups_p;
-  const int gpc = (G + gridDim.x - 1) / gridDim.x;
-  const int g0 = blockIdx.x * gpc;
-  const int g1 = skip ? g0 : min(G, g0 + gpc);
-  const float lm = lmbda[0];
-  const bool gs_cached = (g1 - g0) <= kMaxGroupsPerCta;
-  if (gs_cached)
-    for (int q = tid; q <= g1 - g0; q += kAccThreads) s_gstart[q] = gstart[g0 + q];
-  auto GS = [&](int g) { return gs_cached ? s_gstart[g - g0] : gstart[g]; };
-
-  // ---- prologue: apply the previous iteration's depth update to the patches this CTA owns
-  if (apply_update && !skip) {
-    for (int g = g0 + tid; g < g1; g += kAccThreads) {
-      double acc = Ug[g];
-      const double* ek = Ekg + (size_t)g * (n6 > 0 ? n6 : 1);
-      for (int c = 0; c < n6; c++) acc -= ek[c] * dX[c];
-      const float dz = (float)(Qg[g] * acc);
-      float* pk = patches + (size_t)gkey[g] * 3 * PP + 2 * PP;
-      float d = pk[0];
-      d = d + dz;
-      d = (d > 20) ? 1.0f : d;
-      d = fmaxf(d, 1e-4f);
-      for (int c = 0; c < PP; c++) pk[c] = d;
-    }
-  }
-  if (!do_accumulate) return;
-#ifdef DEVO_BA_TIMING
-  if (blockIdx.x == (gridDim.x >> 1) && tid == 0) g_ba_clk[17] = ba_now();
-#endif
-  __syncthreads();   // depth updates of this CTA's patches are visible to its own threads; s_intr ready
-  const float fx = s_intr[0], fy = s_intr[1], cx = s_intr[2], cy = s_intr[3];
-
-  // ---- who sums what.  Every entry (a,b) of the upper triangle of [S|y] is summed by NC adjacent lanes ("chunks"): lane
+  // ---- who sums what (pure index arithmetic: done before the wait for the previous launch).  Every entry (a,b) of the upper triangle of [S|y] is summed by NC adjacent lanes ("chunks"): lane
   // c takes the c-th part of the batch's edge slots and every NC-th per-patch row; the NC partial sums are combined in
   // a fixed tree at the end, so the result does not depend on timing.  Entries are dealt PAIR-MAJOR (all entries of
   // block pair (0,0), then (0,1), ...): a warp holds 32/NC entries of one or two block pairs, i.e. its lanes walk the same
@@ -634,6 +579,86 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
       live |= 1u << q;
     }
   }
+  // Launched with programmatic stream serialisation.  What the previous Gauss-Newton iteration writes (poses, depths, dX,
+  // Q/u/E_k, partials, tickets, status) may only be touched after the wait; the edge list and its grouping are inputs of
+  // the whole call, so from the second iteration on (`itr > 0`: the predecessor is this kernel) the chain of dependent
+  // index loads perm -> ii/jj/kk is issued BEFORE the wait and overlaps the predecessor's solve.
+  int pre_n = -1, pre_i = 0, pre_j = 0, pre_k = 0, pre_G = 0;
+  long long pre_key = -1;                                // patch of the first group this warp updates
+  bool pre = false;
+  if (itr > 0 && do_accumulate) {
+    pre = true;
+    pre_G = *ngroups_p;
+    const int gpc_ = (pre_G + gridDim.x - 1) / gridDim.x;
+    const int g0_ = blockIdx.x * gpc_, g1_ = min(pre_G, g0_ + gpc_);
+    if (g0_ < g1_) {
+      const int eb_ = gstart[g0_];
+      if (eb_ + tid < gstart[g1_]) {          // (a superset of the first batch; unused values are simply dropped)
+        pre_n = perm[eb_ + tid];
+        pre_i = (int)ii[pre_n]; pre_j = (int)jj[pre_n]; pre_k = (int)kk[pre_n];
+      }
+    }
+    if (tid < 4) s_intr[tid] = intrinsics[tid];
+    if (apply_update && g0_ + (tid >> 5) < g1_) pre_key = gkey[g0_ + (tid >> 5)];
+  }
+  DEVO_PDL_WAIT();
+  DEVO_PDL_TRIGGER();
+#ifdef DEVO_BA_TIMING
+  if (blockIdx.x == (gridDim.x >> 1) && tid == 0) g_ba_clk[0] = ba_now();
+  if (blockIdx.x == (gridDim.x >> 1) && tid == 0 && do_accumulate) g_ba_clk[16] = ba_now();
+#endif
+  const int st = *(volatile int32_t*)status;               // (consumed below, after the loads of the depth update are out)
+  if (!pre && tid < 4) s_intr[tid] = intrinsics[tid];   // only intrinsics[0] is used (:232-238)
+  const int G = pre ? pre_G : *ngroups_p;
+  const int gpc = (G + gridDim.x - 1) / gridDim.x;
+  const int g0 = blockIdx.x * gpc;
+  const int g1u = min(G, g0 + gpc);
+  const float lm = lmbda[0];
+
+  // ---- prologue: apply the previous iteration's depth update  dZ_k = Q_k (u_k - E_k . dX)  to the patches this CTA
+  // owns: one warp per patch, lanes over the columns of E_k (fixed-order shuffle tree); the loads do not wait for the
+  // status word, only the store does
+  if (apply_update) {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int g = g0 + warp; g < g1u; g += kAccThreads / 32) {
+      const double* ek = Ekg + (size_t)g * (n6 > 0 ? n6 : 1);
+      double part = 0.0;
+      for (int c = lane; c < n6; c += 32) part += __ldcg(ek + c) * __ldcg(dX + c);
+      const double ug = __ldcg(Ug + g), qg = __ldcg(Qg + g);
+      const long long key = (pre_key >= 0 && g == g0 + warp) ? pre_key : gkey[g];
+      float* pk = patches + (size_t)key * 3 * PP + 2 * PP;
+      float d = pk[0];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      if (st == 0) {
+        d = d + (float)(qg * (ug - part));
+        d = (d > 20) ? 1.0f : d;
+        d = fmaxf(d, 1e-4f);
+        for (int c = lane; c < PP; c += 32) pk[c] = d;
+      }
+    }
+  }
+  if (st != 0 && (!do_accumulate || nfree <= 0)) return;
+  // An earlier iteration (or, for a CTA that starts late, another CTA of this launch) failed: the reference would have
+  // thrown.  The CTA does no work but still takes part in the cluster reduction below -- its peers wait for it -- with a
+  // zero partial; the solving CTA sees the status and leaves the poses alone.
+  const bool skip = (st != 0);
+  if (skip && sys_out && blockIdx.x == 0) {   // sharded form: peers must see a system and this rank's failure
+    for (int q = tid; q < nent; q += kAccThreads) sys_out[q] = 0.0;
+    if (tid == 0) sys_out[nent] = 1.0;
+  }
+  const int g1 = skip ? g0 : g1u;
+  const bool gs_cached = (g1 - g0) <= kMaxGroupsPerCta;
+  if (gs_cached)
+    for (int q = tid; q <= g1 - g0; q += kAccThreads) s_gstart[q] = gstart[g0 + q];
+  auto GS = [&](int g) { return gs_cached ? s_gstart[g - g0] : gstart[g]; };
+  if (!do_accumulate) return;
+#ifdef DEVO_BA_TIMING
+  if (blockIdx.x == (gridDim.x >> 1) && tid == 0) g_ba_clk[17] = ba_now();
+#endif
+  __syncthreads();   // depth updates of this CTA's patches are visible to its own threads; s_intr ready
+  const float fx = s_intr[0], fy = s_intr[1], cx = s_intr[2], cy = s_intr[3];
+
   const int SW = (EB + 31) >> 5;                        // bitset words per pair
 
   int gs = g0;
