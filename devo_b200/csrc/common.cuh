@@ -100,6 +100,10 @@ static inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid
 #define DEVO_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
 #define DEVO_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 
+// csrc/segment.cu: devo_segment_softmax_sum with one more promise from the caller (see the kernel)
+int segment_softmax_sum(const void* g, const void* f, const int32_t* perm, const int32_t* gstart, const int32_t* ngroups,
+                        int max_groups, void* y_out, int dtype, int n_rows, int dim, void* stream, int plan_is_older);
+
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: remember, per device ordinal, the largest size
 // already configured for one kernel (a process-wide flag would leave every device but the first unconfigured).
 struct SmemConfig {

@@ -379,20 +379,26 @@ struct Epi {
   }
 
   // ---------------- prologue: build the full [64 x 384] A tile of layer 0 in buffer 0 ----------------
+  // the source row of every tile row of a gather prologue.  The index arrays (neighbour links, group ids) belong to the
+  // graph plan -- inputs of the whole update, complete before its first program started -- so this runs BEFORE the wait
+  // for the previous program and its L2 round trip is off the boundary between two programs.
+  __device__ __forceinline__ void prologue_index() {
+    if (et < kRows) {
+      const int gr = row0 + et;
+      int src = -1;
+      if (gr < P.rows) {
+        const long long j = P.idx64 ? (long long)P.idx64[gr] : (P.idx32 ? (long long)P.idx32[gr] : (long long)gr);
+        src = (j >= 0 && j < (long long)P.src_rows) ? (int)j : -1;
+      }
+      s_idx()[et] = src;
+    }
+    epi_bar_all();
+  }
+
   template <int PRO>
   __device__ __forceinline__ void prologue() {
     unsigned char* A0 = As;
     if constexpr (PRO == PRO_GATHER) {
-      if (et < kRows) {
-        const int gr = row0 + et;
-        int src = -1;
-        if (gr < P.rows) {
-          const long long j = P.idx64 ? (long long)P.idx64[gr] : (P.idx32 ? (long long)P.idx32[gr] : (long long)gr);
-          src = (j >= 0 && j < (long long)P.src_rows) ? (int)j : -1;
-        }
-        s_idx()[et] = src;
-      }
-      epi_bar_all();
       // cooperative: 48 consecutive threads copy one 768-byte source row; all 6 loads of a thread are in flight together
       constexpr int kPer = kRows * kChunks / kEpiThreads;     // 6
       uint4 v[kPer];
@@ -876,6 +882,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
     e.n32_r = P.n32 + t32((int)blockIdx.x, 0, e.r);
     e.gate_r = P.gate16 + t16((int)blockIdx.x, 0, e.r);
     if (lane == 0 && P.out_a) prefetch_tensormap(&tm_oa);
+    if (P.pro == PRO_GATHER) e.prologue_index();
     pdl_wait();                                     // first use of the previous kernels' results (and first global writes)
     switch (P.pro) {                                // warp-uniform
       case PRO_GATHER: e.template prologue<PRO_GATHER>(); break;
@@ -1099,7 +1106,7 @@ static int gru_update_impl(const devo_gru_weights_t* Wt, const devo_gru_io_t* io
     rc = launch_prog<T>(tw, tw0, ta, t_g16, t_f16, P, s);
     if (rc != DEVO_OK) return rc;
   }
-  rc = devo_segment_softmax_sum(g16, f16, io->perm_kk, io->gstart_kk, io->ngroups_kk, io->max_groups_kk, y16, dtype, E, kD, (void*)s);
+  rc = devo::segment_softmax_sum(g16, f16, io->perm_kk, io->gstart_kk, io->ngroups_kk, io->max_groups_kk, y16, dtype, E, kD, (void*)s, 1);
   if (rc != DEVO_OK) return rc;
   {
     GruProg<T> P = base;                                      // net += h_kk(y_kk)[gid_kk]; g, f of the pair-wise aggregation
@@ -1111,7 +1118,7 @@ static int gru_update_impl(const devo_gru_weights_t* Wt, const devo_gru_io_t* io
     rc = launch_prog<T>(tw, tw0, ta, t_g16, t_f16, P, s);
     if (rc != DEVO_OK) return rc;
   }
-  rc = devo_segment_softmax_sum(g16, f16, io->perm_ij, io->gstart_ij, io->ngroups_ij, io->max_groups_ij, hy16, dtype, E, kD, (void*)s);
+  rc = devo::segment_softmax_sum(g16, f16, io->perm_ij, io->gstart_ij, io->ngroups_ij, io->max_groups_ij, hy16, dtype, E, kD, (void*)s, 1);
   if (rc != DEVO_OK) return rc;
   {
     GruProg<T> P = base;                                      // net += h_ij(y_ij)[gid_ij]; LN, GatedResidual x2; heads
