@@ -30,6 +30,9 @@ SIGNATURES = {
     "devo_gmap_pack": (_i, [_vp, _vp] + [_i] * 4 + [_vp]),
     "devo_corr_lookup_fused": (_i, [_vp] * 6 + [_i] * 5 + [_vp]),
     "devo_corr_lookup_fused_ld": (_i, [_vp] * 6 + [_i] * 6 + [_vp]),
+    "devo_pyramid_pack_split": (_i, [_vp] * 3 + [_i] * 5 + [_vp]),
+    "devo_gmap_pack_split": (_i, [_vp] * 3 + [_i] * 3 + [_vp]),
+    "devo_corr_lookup_fused_split": (_i, [_vp] * 8 + [_i] * 5 + [_vp]),
     "devo_graph_plan_workspace": (_sz, [_i]),
     "devo_graph_plan": (_i, [_vp, _vp, _i, _i64, _i64] + [_vp] * 8 + [_sz, _vp]),
     "devo_neighbors": (_i, [_vp] * 4 + [_i, _vp, _sz, _vp]),

@@ -93,6 +93,8 @@ struct FastParams {
   float inv_scale[DEVO_MAX_LEVELS];         // 1/scale when that is exact (power of two), else 0 => divide
   int box[DEVO_MAX_LEVELS];                 // TMA box edge of the level (<= kBox), see box_edge()
   int ld_out;                               // output row stride in elements (>= 49*9*L)
+  int out_mode;                             // 0: store T; 1: store float(out_scale * r); 2: float, out += out_scale * r
+  float out_scale;
   const float* coords;
   const int64_t* ii;
   const int64_t* jj;
@@ -280,6 +282,13 @@ struct CoordView {
   __device__ __forceinline__ int patch() const { return (int)reinterpret_cast<const long long*>(slot + kCoordFloats * 4)[off]; }
   __device__ __forceinline__ int frame() const { return (int)reinterpret_cast<const long long*>(slot + kCoordFloats * 4 + kCoordBatch * 8)[off]; }
 };
+
+// float output of a split-precision pass (mode 1: first pass writes, mode 2: later passes add; the same thread owns the
+// same element in every pass and the passes are separate launches)
+__device__ __forceinline__ void store_f32(float* dst, float v, int mode) {
+  if (mode == 2) v += *dst;
+  *dst = v;
+}
 
 // per-role item cursor: (e, l) advanced by `step` items without divisions
 struct ItemCursor {
@@ -562,6 +571,7 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
       CT_WAIT(3, asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"));   // the 4 warps of this group only
 
       T* orow = out + (size_t)e * prm.ld_out + l;
+      float* orow32 = reinterpret_cast<float*>(prm.out) + (size_t)e * prm.ld_out + l;     // split-precision passes
       if (pw >= 0) {
         const float* sp = vs + p * 128 + pw;
         const int bx = prm.box[l];        // accumulator row of box pixel (y, x) is y * bx + x
@@ -570,7 +580,8 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
           if (sxo[k] >= 0) {
             const float* s4 = sp + syo[k] * bx + sxo[k];
             const float r = w00 * s4[0] + w01 * s4[1] + w10 * s4[bx] + w11 * s4[bx + 1];
-            orow[ooff[k]] = from_f<T>(r);
+            if (prm.out_mode == 0) orow[ooff[k]] = from_f<T>(r);
+            else store_f32(orow32 + ooff[k], r * prm.out_scale, prm.out_mode);
           }
         }
       } else if (owner) {
@@ -589,7 +600,9 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
           const float v01 = direct_dot<T>(gp, lv, H, W, prm.C, fr, yy, xx + 1);
           const float v10 = direct_dot<T>(gp, lv, H, W, prm.C, fr, yy + 1, xx);
           const float v11 = direct_dot<T>(gp, lv, H, W, prm.C, fr, yy + 1, xx + 1);
-          orow[((xo * kOut + yo) * kPP + p) * L] = from_f<T>(w00 * v00 + w01 * v01 + w10 * v10 + w11 * v11);
+          const float r = w00 * v00 + w01 * v01 + w10 * v10 + w11 * v11;
+          if (prm.out_mode == 0) orow[((xo * kOut + yo) * kPP + p) * L] = from_f<T>(r);
+          else store_f32(orow32 + ((xo * kOut + yo) * kPP + p) * L, r * prm.out_scale, prm.out_mode);
         }
       }
       buf ^= 1;
@@ -693,6 +706,55 @@ __global__ void gmap_pack_kernel(const T* __restrict__ in, T* __restrict__ out, 
   }
 }
 
+// float -> (hi, lo) halves with a = hi + 2^-11 lo (see devo_corr_lookup_fused_split)
+__device__ __forceinline__ void split_half(float a, __half& hi, __half& lo) {
+  hi = __float2half_rn(a);
+  lo = __float2half_rn((a - __half2float(hi)) * 2048.0f);
+}
+
+__global__ void __launch_bounds__(256) pyramid_pack_split_kernel(const float* __restrict__ in, __half* __restrict__ out_hi,
+                                                                 __half* __restrict__ out_lo, int C, int H, int W, int Ho,
+                                                                 int Wo, int pool) {
+  extern __shared__ float tile[];   // [32][C+1]
+  const int n = blockIdx.z, yo = blockIdx.y, x0 = blockIdx.x * 32;
+  const int nx = min(32, Wo - x0);
+  const float div = (float)(pool * pool);
+  const float* src = in + (size_t)n * C * H * W;
+  for (int q = threadIdx.x; q < C * 32; q += blockDim.x) {
+    const int x = q & 31, c = q >> 5;
+    if (x < nx) {
+      float s = 0.f;
+      const float* p = src + ((size_t)c * H + (size_t)yo * pool) * W + (size_t)(x0 + x) * pool;
+      for (int a = 0; a < pool; a++)
+        for (int b = 0; b < pool; b++) s += p[(size_t)a * W + b];
+      tile[x * (C + 1) + c] = (pool == 1) ? s : s / div;
+    }
+  }
+  __syncthreads();
+  const size_t base = (((size_t)n * Ho + yo) * Wo + x0) * C;
+  for (int q = threadIdx.x; q < nx * C; q += blockDim.x) {
+    const int c = q % C, x = q / C;
+    __half hi, lo;
+    split_half(tile[x * (C + 1) + c], hi, lo);
+    out_hi[base + (size_t)x * C + c] = hi;
+    out_lo[base + (size_t)x * C + c] = lo;
+  }
+}
+
+__global__ void gmap_pack_split_kernel(const float* __restrict__ in, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                                       int Np, int C, int PP) {
+  const long long total = (long long)Np * C * PP;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(q % C);
+    const int p = (int)((q / C) % PP);
+    const long long n = q / ((long long)C * PP);
+    __half hi, lo;
+    split_half(in[(n * C + c) * PP + p], hi, lo);
+    out_hi[q] = hi;
+    out_lo[q] = lo;
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -790,9 +852,9 @@ int devo_corr_lookup_fused(const void* gmap_pm, const devo_pyramid_t* pyr, const
   return devo_corr_lookup_fused_ld(gmap_pm, pyr, coords, ii, jj, out, 0, dtype, Np, Nf, C, E, stream);
 }
 
-int devo_corr_lookup_fused_ld(const void* gmap_pm, const devo_pyramid_t* pyr, const float* coords,
-                              const int64_t* ii, const int64_t* jj, void* out, int ld_out, int dtype, int Np, int Nf,
-                              int C, int E, void* stream) {
+static int lookup_fused_impl(const void* gmap_pm, const devo_pyramid_t* pyr, const float* coords,
+                             const int64_t* ii, const int64_t* jj, void* out, int ld_out, int dtype, int Np, int Nf,
+                             int C, int E, void* stream, int out_mode, float out_scale) {
   DEVO_REQUIRE(pyr != nullptr && pyr->n_levels >= 1 && pyr->n_levels <= DEVO_MAX_LEVELS, DEVO_EINVAL,
                "corr_lookup_fused: bad pyramid");
   DEVO_REQUIRE(dtype == DEVO_F16 || dtype == DEVO_BF16, DEVO_EUNSUPPORTED, "corr_lookup_fused: dtype must be f16 or bf16");
@@ -804,6 +866,7 @@ int devo_corr_lookup_fused_ld(const void* gmap_pm, const devo_pyramid_t* pyr, co
   prm.E = E; prm.L = pyr->n_levels; prm.items = E * pyr->n_levels; prm.khalves = C / 64; prm.C = C;
   prm.coords = coords; prm.ii = ii; prm.jj = jj; prm.out = out; prm.gmap_pm = gmap_pm;
   prm.ld_out = ld_out > 0 ? ld_out : kOut * kOut * kPP * pyr->n_levels;
+  prm.out_mode = out_mode; prm.out_scale = out_scale;
   DEVO_REQUIRE(prm.ld_out >= kOut * kOut * kPP * pyr->n_levels, DEVO_EINVAL, "corr_lookup_fused: ld_out too small");
   {
     cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)kPP, (cuuint64_t)Np};
@@ -832,6 +895,53 @@ int devo_corr_lookup_fused_ld(const void* gmap_pm, const devo_pyramid_t* pyr, co
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == DEVO_F16) return launch_fast<__half>(maps, prm, s);
   return launch_fast<__nv_bfloat16>(maps, prm, s);
+}
+
+int devo_corr_lookup_fused_ld(const void* gmap_pm, const devo_pyramid_t* pyr, const float* coords,
+                              const int64_t* ii, const int64_t* jj, void* out, int ld_out, int dtype, int Np, int Nf,
+                              int C, int E, void* stream) {
+  return lookup_fused_impl(gmap_pm, pyr, coords, ii, jj, out, ld_out, dtype, Np, Nf, C, E, stream, 0, 1.0f);
+}
+
+// ---- float32 features on the tensor-core path: split precision ---------------------------------------------------------
+// a = hi + 2^-11 lo with hi = half(a), lo = half(2^11 (a - hi)): 22 significant bits.  <a, b> = <a_hi, b_hi> +
+// 2^-11 (<a_hi, b_lo> + <a_lo, b_hi>) + O(2^-22): three passes of the half kernel with float accumulation and a float
+// output (the bilinear blend is linear, so the passes simply add).  devo_pyramid_pack_split / devo_gmap_pack_split build
+// the pixel-major hi / lo buffers (average pooling in float, like F.avg_pool2d on the float features).
+int devo_corr_lookup_fused_split(const void* gmap_hi, const void* gmap_lo, const devo_pyramid_t* pyr_hi,
+                                 const devo_pyramid_t* pyr_lo, const float* coords, const int64_t* ii, const int64_t* jj,
+                                 float* out, int ld_out, int Np, int Nf, int C, int E, void* stream) {
+  DEVO_REQUIRE(pyr_hi && pyr_lo && pyr_hi->n_levels == pyr_lo->n_levels, DEVO_EINVAL, "corr_lookup_fused_split: bad pyramids");
+  const float k = 1.0f / 2048.0f;
+  int rc = lookup_fused_impl(gmap_hi, pyr_hi, coords, ii, jj, out, ld_out, DEVO_F16, Np, Nf, C, E, stream, 1, 1.0f);
+  if (rc != DEVO_OK) return rc;
+  rc = lookup_fused_impl(gmap_hi, pyr_lo, coords, ii, jj, out, ld_out, DEVO_F16, Np, Nf, C, E, stream, 2, k);
+  if (rc != DEVO_OK) return rc;
+  return lookup_fused_impl(gmap_lo, pyr_hi, coords, ii, jj, out, ld_out, DEVO_F16, Np, Nf, C, E, stream, 2, k);
+}
+
+int devo_pyramid_pack_split(const float* fmap_planar, void* out_hi, void* out_lo, int N, int C, int H, int W, int pool,
+                            void* stream) {
+  DEVO_REQUIRE(pool >= 1 && N >= 0 && C > 0 && H >= pool && W >= pool, DEVO_EINVAL, "pyramid_pack_split: bad sizes");
+  if (N == 0) return DEVO_OK;
+  const int Ho = H / pool, Wo = W / pool;
+  DEVO_REQUIRE(Ho <= 65535 && N <= 65535, DEVO_EINVAL, "pyramid_pack_split: dims too large");
+  const size_t smem = (size_t)32 * (C + 1) * sizeof(float);
+  DEVO_REQUIRE(smem <= 48 * 1024, DEVO_ECAPACITY, "pyramid_pack_split: C too large");
+  dim3 grid((Wo + 31) / 32, Ho, N);
+  pyramid_pack_split_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(fmap_planar, (__half*)out_hi, (__half*)out_lo, C, H, W, Ho, Wo, pool);
+  DEVO_LAUNCH_CHECK("pyramid_pack_split");
+  return DEVO_OK;
+}
+
+int devo_gmap_pack_split(const float* gmap_planar, void* out_hi, void* out_lo, int Np, int C, int PP, void* stream) {
+  const long long total = (long long)Np * C * PP;
+  if (total <= 0) return DEVO_OK;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  gmap_pack_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gmap_planar, (__half*)out_hi, (__half*)out_lo, Np, C, PP);
+  DEVO_LAUNCH_CHECK("gmap_pack_split");
+  return DEVO_OK;
 }
 
 #ifdef DEVO_CORR_TIMING

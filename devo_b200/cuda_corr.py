@@ -108,6 +108,70 @@ def lookup_fused(gmap_pm, levels_pm, scales, coords, ii, jj, out=None):
     return out
 
 
+def pack_pixel_major_split(fmap, pool=1):
+    """float planar [N,C,H,W] -> two pixel-major half buffers (hi, lo) with a = hi + 2^-11 lo (pooling in float)"""
+    _lib.require_cuda(fmap)
+    _lib.require_dtype(fmap, torch.float32, "fmap")
+    fmap = fmap.contiguous()
+    N, C, H, W = fmap.shape
+    hi = torch.empty(N, H // pool, W // pool, C, dtype=torch.float16, device=fmap.device)
+    lo = torch.empty_like(hi)
+    _lib.check(_lib.lib().devo_pyramid_pack_split(fmap.data_ptr(), hi.data_ptr(), lo.data_ptr(), N, C, H, W, pool,
+                                                  _lib.stream_ptr(fmap.device)), "pyramid_pack_split")
+    return hi, lo
+
+
+def pack_gmap_split(gmap):
+    """float planar [Np,C,P,P] -> (hi, lo) [Np,P*P,C] halves"""
+    _lib.require_cuda(gmap)
+    _lib.require_dtype(gmap, torch.float32, "gmap")
+    gmap = gmap.contiguous()
+    Np, C = gmap.shape[0], gmap.shape[1]
+    PP = gmap.shape[2] * gmap.shape[3]
+    hi = torch.empty(Np, PP, C, dtype=torch.float16, device=gmap.device)
+    lo = torch.empty_like(hi)
+    _lib.check(_lib.lib().devo_gmap_pack_split(gmap.data_ptr(), hi.data_ptr(), lo.data_ptr(), Np, C, PP,
+                                               _lib.stream_ptr(gmap.device)), "gmap_pack_split")
+    return hi, lo
+
+
+def _pyramid_struct(levels_pm, scales):
+    pyr = _lib.PyramidStruct()
+    pyr.n_levels = len(levels_pm)
+    for l, lv in enumerate(levels_pm):
+        pyr.level[l] = lv.data_ptr()
+        pyr.H[l] = lv.shape[1]
+        pyr.W[l] = lv.shape[2]
+        pyr.scale[l] = float(scales[l])
+    return pyr
+
+
+def lookup_fused_split(gmap_split, levels_split, scales, coords, ii, jj, out=None):
+    """`lookup_fused` for float32 features given as (hi, lo) half pairs (pack_gmap_split / pack_pixel_major_split):
+    three tensor-core passes with float accumulation; returns float32 [E, 49*9*L]"""
+    import ctypes
+    g_hi, g_lo = gmap_split
+    L = len(levels_split)
+    E = coords.shape[0]
+    Np, _, C = g_hi.shape
+    if out is None:
+        out = torch.empty(E, 49 * 9 * L, dtype=torch.float32, device=g_hi.device)
+    elif out.dim() != 2 or out.shape[0] != E or out.shape[1] < 49 * 9 * L or out.stride(1) != 1 or out.dtype != torch.float32:
+        raise RuntimeError("cuda_corr.lookup_fused_split: out must be float32 [E, >= 441*L] with unit inner stride")
+    p_hi = _pyramid_struct([lv[0] for lv in levels_split], scales)
+    p_lo = _pyramid_struct([lv[1] for lv in levels_split], scales)
+    _lib.check(_lib.lib().devo_corr_lookup_fused_split(g_hi.data_ptr(), g_lo.data_ptr(), ctypes.addressof(p_hi),
+                                                       ctypes.addressof(p_lo), coords.data_ptr(), ii.data_ptr(), jj.data_ptr(),
+                                                       out.data_ptr(), out.stride(0), Np, levels_split[0][0].shape[0], C, E,
+                                                       _lib.stream_ptr(g_hi.device)), "corr_lookup_fused_split")
+    return out
+
+
+def _split_eligible(fmap1, fmap2, coords, radius):
+    return (not _FORCE_GENERIC and fmap1.dtype == torch.float32 and fmap1.shape[0] == 1
+            and fmap1.shape[2] in (64, 128) and fmap1.shape[3] == 3 and fmap1.shape[4] == 3 and radius == 3)
+
+
 def _fast_eligible(fmap1, fmap2, coords, radius):
     return (not _FORCE_GENERIC and fmap1.dtype in (torch.float16, torch.bfloat16) and fmap1.shape[0] == 1
             and fmap1.shape[2] in (64, 128) and fmap1.shape[3] == 3 and fmap1.shape[4] == 3 and radius == 3)
@@ -129,6 +193,11 @@ def forward(fmap1, fmap2, coords, ii, jj, radius):
         lv = _cached(fmap2, lambda t: pack_pixel_major(t[0], 1))
         g = _cached(fmap1, lambda t: pack_gmap(t[0]))
         out = lookup_fused(g, [lv], [1.0], coords[0], ii, jj)
+        return [out.view(1, E, D1, D1, P, P)]
+    if E > 0 and _split_eligible(fmap1, fmap2, coords, radius):       # float32 features (training): split precision
+        lv = _cached(fmap2, lambda t: pack_pixel_major_split(t[0], 1))
+        g = _cached(fmap1, lambda t: pack_gmap_split(t[0]))
+        out = lookup_fused_split(g, [lv], [1.0], coords[0], ii, jj)
         return [out.view(1, E, D1, D1, P, P)]
     out = torch.empty(B, E, D1, D1, P, P, dtype=fmap1.dtype, device=fmap1.device)
     _lib.check(_lib.lib().devo_corr_forward(fmap1.data_ptr(), fmap2.data_ptr(), coords.data_ptr(), ii.data_ptr(),

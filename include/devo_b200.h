@@ -92,6 +92,19 @@ int devo_corr_lookup_fused_ld(const void* gmap_pm, const devo_pyramid_t* pyr, co
                               const int64_t* ii, const int64_t* jj, void* out, int ld_out, int dtype,
                               int Np, int Nf, int C, int E, void* stream);
 
+/* float32 features on the same tensor-core path (training runs altcorr in float32): split precision.  Every feature is
+ * stored as two halves, a = hi + 2^-11 lo (22 significant bits; devo_pyramid_pack_split / devo_gmap_pack_split, float
+ * planar in, two pixel-major half buffers out, pooling in float), and the lookup runs three passes of the half kernel
+ * (<hi,hi> + 2^-11 (<hi,lo> + <lo,hi>)) with float accumulation into a FLOAT output of the layout above.  Agrees with
+ * the float32 kernel (devo_corr_forward) to ~1e-6 relative; the reference kernel it replaces: correlation_kernel.cu:82-136
+ * instantiated for float. */
+int devo_pyramid_pack_split(const float* fmap_planar, void* out_hi, void* out_lo, int N, int C, int H, int W, int pool,
+                            void* stream);
+int devo_gmap_pack_split(const float* gmap_planar, void* out_hi, void* out_lo, int Np, int C, int PP, void* stream);
+int devo_corr_lookup_fused_split(const void* gmap_hi, const void* gmap_lo, const devo_pyramid_t* pyr_hi,
+                                 const devo_pyramid_t* pyr_lo, const float* coords, const int64_t* ii, const int64_t* jj,
+                                 float* out, int ld_out, int Np, int Nf, int C, int E, void* stream);
+
 /* ------------------------------------------------------------------ fastba (cuda_ba) */
 /* Edge-graph analysis shared by neighbors / BA / segment softmax: edges sorted by
  * (ka, kb, edge index).  All outputs are device arrays; any may be NULL.
