@@ -629,7 +629,11 @@ struct Epi {
 #pragma unroll
         for (int k = 0; k < 8; k++) v[k] = fmaxf((v[k] - mean) * rstd * gk[k] + bk[k], 0.f);
         *reinterpret_cast<uint4*>(An + a_off(r, c)) = pack8<T>(v);
+        // the K-blocks fed by N-tile 0 are complete after its kCPT chunks: the MMA warps start on them while this
+        // thread still normalises N-tile 1
+        if (kWritesA && i == kCPT - 1 && l + 1 < P.n_layers) signal_a(0);
       }
+      if (kWritesA && l + 1 < P.n_layers) signal_a(1);
       ln_used++;
     } else if constexpr (EPI == EPI_ADD3_LN || EPI == EPI_GATED_LN || EPI == EPI_RESID_LN_A) {
       tmem_wait_st();
@@ -657,6 +661,7 @@ struct Epi {
         *f4w(dst, 2 * c + 1) = make_float4(v[4], v[5], v[6], v[7]);
         if (EPI != EPI_ADD3_LN || out_img) *reinterpret_cast<uint4*>(An + a_off(r, c)) = pack8<T>(v);
         }
+        if (kWritesA && l + 1 < P.n_layers) signal_a(h);      // (as above: N-tile h of the next A operand is complete)
       }
       ln_used++;
     } else if constexpr (EPI == EPI_GATED_HEADS) {
@@ -674,9 +679,6 @@ struct Epi {
           *reinterpret_cast<float2*>(P.weight32 + (size_t)grow * 2) = wf;
         }
       }
-    }
-    if constexpr (kWritesA && kTwoPass) {
-      if (l + 1 < P.n_layers) { signal_a(0); signal_a(1); }
     }
     if (out_img) store_image((EPI == EPI_STORE_B) ? tm_ob : tm_oa);
     // this warp is done with the layer's accumulators (TMEM set l & 1 may be overwritten by layer l + 2)
