@@ -180,7 +180,7 @@ def per_op_times(op, wl, dev, stream, flush):
                 state=scratch, coords=coords)), stream, flush)
         target = (coords[:, :, :, 1, 1] + op.delta.float()).contiguous()
         weight = op.weight.float().contiguous()
-        p0, x0 = op._pristine
+        p0, x0 = op.pristine_geometry()
 
         def ba(iters):
             op.poses.copy_(p0)
@@ -235,7 +235,7 @@ def ref_cuda_times(op, wl, dev, stream, flush):
         out["fastba_neighbors"] = time_us(lambda: rb.neighbors(kk, jj), stream, flush, warm=20, n=100)
         target = (coords[:, :, :, 1, 1] + op.delta.float()).contiguous()
         weight = op.weight.float().contiguous()
-        p0, x0 = op._pristine
+        p0, x0 = op.pristine_geometry()
         poses, patches = p0.clone(), x0.clone()
 
         def ba(iters):

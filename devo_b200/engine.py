@@ -138,13 +138,22 @@ class UpdateOperator:
         return self.state.get() if self.state is not None else self.net
 
     def snapshot_geometry(self):
-        self._pristine = (self.poses.clone(), self.patches.clone())
+        # poses and patches are the first two blocks of the arena: one contiguous snapshot, restored by ONE copy
+        o, shape, dt = self.state_layout["patches"]
+        self._geom_bytes = o + self.patches.numel() * self.patches.element_size()
+        self._pristine = self.state_arena[:self._geom_bytes].clone()
+
+    def pristine_geometry(self):
+        """(poses, patches) views of the snapshot taken by snapshot_geometry()"""
+        po, ps, pd = self.state_layout["poses"]
+        xo, xs, xd = self.state_layout["patches"]
+        return (self._pristine[po:po + self.poses.numel() * 4].view(pd).view(ps),
+                self._pristine[xo:xo + self.patches.numel() * 4].view(xd).view(xs))
 
     # ---- one iteration -----------------------------------------------------------------------
     def _iteration(self, reset_geometry=False):
         if reset_geometry and self._pristine is not None:
-            self.poses.copy_(self._pristine[0])
-            self.patches.copy_(self._pristine[1])
+            self.state_arena[:self._geom_bytes].copy_(self._pristine)
         # (0) graph analysis on the device (neighbours, patch groups, frame-pair groups) on a side stream:
         #     it only depends on ii/jj/kk, so it overlaps the reprojection and the correlation lookup
         cur = torch.cuda.current_stream(self.device)
