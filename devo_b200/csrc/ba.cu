@@ -16,11 +16,17 @@
 //                                      partial of the *reduced* system  S = B - E Q E^T,
 //                                      y = v - E Q u  is accumulated in registers, one fixed
 //                                      set of matrix entries per thread, fixed summation order:
-//                                      no atomics at all, bitwise reproducible.
-//   solve  (same launch)               the last accumulate CTA to finish (atomic ticket): fixed-order
-//                                      reduction of the partials, damping, in-smem fp64 LDL^T elimination
-//                                      of [S|y] (one barrier per pivot), warp-shuffle back-substitution,
-//                                      SE3 retraction.
+//                                      no floating-point atomics, bitwise reproducible.  An entry
+//                                      only visits the edges listed for its pair of pose blocks
+//                                      (bitsets in shared memory); the terms every edge of a patch
+//                                      shares (its source frame's diagonal block / residual column)
+//                                      are pre-summed per patch by a warp.
+//   reduce (same launch)               clusters of 8 CTAs: partials parked in shared memory, slice r
+//                                      of the 8 added by CTA r through DSMEM in rank order; one ticket
+//                                      per CTA elects the last CTA of the grid.
+//   solve  (same launch)               that CTA: cluster partials added in index order, damping,
+//                                      block-6 LDL^T of [S|y] held in registers (2 barriers per pose
+//                                      block), back-substitution, SE3 retraction.
 //   depth update                       dZ_k = Q_k (u_k - E_k . dX); fused into the prologue of the
 //                                      next iteration's accum launch (same patch ownership).
 //
@@ -497,14 +503,14 @@ __device__ void ba_solve_device(unsigned char* smem_raw, float* poses, const dou
   }
 }
 
-// ---- hierarchical, order-preserving reduction of the per-CTA partials ----------------------------------
-// CTAs are grouped 8 by 8; the last CTA of a group to finish adds the group's partials in index order into a
-// group partial, and the last group to finish runs the solve on the group partials.  Which CTA does the work
-// depends on timing, what is summed in which order does not.
+// ---- order-preserving reduction of the per-CTA partials ---------------------------------------------------
+// The grid runs as thread-block clusters of kGroupCtas CTAs (see the end of ba_accumulate_kernel): which CTA does
+// the work depends on timing, what is summed in which order does not.
 constexpr int kGroupCtas = 8;
 
 // ---- accumulate kernel ----------------------------------------------------------------------
-// smem: X[R][LD] doubles, coef[R] doubles, zj[R] doubles (Jz per row), batch bookkeeping
+// smem: X[R][LD] doubles, coef[R] doubles, zj[R] doubles (Jz per row), per-patch pre-sums, block-pair bitsets, batch
+// bookkeeping (acc_shape() is the host-side mirror of the carve-up)
 template <int EPT>
 __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
     float* __restrict__ poses_rw, float* __restrict__ patches, const float* __restrict__ intrinsics,

@@ -47,6 +47,48 @@ def test_ba_vs_oracle(nf, m, t0, iters):
     assert torch.equal(patches[0, :, 2], patches[0, :, 2, :1, :1].expand(-1, 3, 3))
 
 
+@pytest.mark.parametrize("seed", [0, 1])
+def test_ba_arbitrary_edge_lists_vs_oracle(seed):
+    """The C ABI takes ANY (ii, jj, kk): edges of one patch leaving from different frames (no per-patch pre-sum: the
+    block-pair lists carry the diagonal terms), self edges i == j, duplicated edges, patches with 1 or 40 edges, a ragged
+    random subset of a patch graph -- all against the fp64 oracle.  (The DEVO graph, where every edge of a patch leaves
+    from the patch's frame, is the pre-summed fast case of the other tests.)"""
+    nf, m = 7, 24
+    P = ba_problem(n_frames=nf, patches_per_frame=m, seed=77 + seed, init="perturbed", noise=0.3)
+    g = torch.Generator().manual_seed(seed)
+    E0 = P["ii"].numel()
+    keep = torch.rand(E0, generator=g) < 0.6                             # ragged subset
+    keep[:3] = True
+    sel = torch.nonzero(keep).flatten()
+    ii, jj, kk = P["ii"][sel].clone(), P["jj"][sel].clone(), P["kk"][sel].clone()
+    tg, wt = P["targets"][:, sel].clone(), P["weights"][:, sel].clone()
+    # a third of the edges get a random source frame (the oracle and the kernel read poses[ii], whatever it is)
+    rnd = torch.rand(ii.numel(), generator=g) < 0.33
+    ii[rnd] = torch.randint(0, nf, (int(rnd.sum()),), generator=g)
+    # some self edges and some exact duplicates
+    selfe = torch.randperm(ii.numel(), generator=g)[:10]
+    jj[selfe] = ii[selfe]
+    dup = torch.randperm(ii.numel(), generator=g)[:25]
+    ii, jj, kk = torch.cat([ii, ii[dup]]), torch.cat([jj, jj[dup]]), torch.cat([kk, kk[dup]])
+    tg, wt = torch.cat([tg, tg[:, dup]], 1), torch.cat([wt, wt[:, dup]], 1)
+    # one patch with 40 edges
+    big = torch.randint(0, nf, (40,), generator=g)
+    ii = torch.cat([ii, torch.full((40,), 2)]); jj = torch.cat([jj, big]); kk = torch.cat([kk, torch.full((40,), 2 * m + 5)])
+    tg = torch.cat([tg, tg[:, :40]], 1); wt = torch.cat([wt, wt[:, :40] * 0.1], 1)
+    # targets consistent with the edited graph: reproject with the ground truth, add noise
+    cg = opops.transform(P["poses_gt"], P["patches_gt"], P["intrinsics"], ii, jj, kk)
+    tg = cg[..., 1, 1, :] + 0.3 * torch.randn(1, ii.numel(), 2, generator=g, dtype=torch.float64)
+    Q = dict(P, ii=ii, jj=jj, kk=kk, targets=tg, weights=wt)
+    for t0, iters in ((1, 2), (2, 3)):
+        poses, patches = _run_ba(Q, t0, nf, iters)
+        po, xo, st = _oracle_ba(Q, t0, nf, iters)
+        assert st == 0
+        dp = (poses[0].double().cpu() - po).abs().max().item()
+        dd = (patches[0, :, 2].double().cpu() - xo[:, 2]).abs().max().item()
+        assert dp <= 1e-5, dp
+        assert dd <= 1e-5, dd
+
+
 def test_ba_from_identity_converges_like_oracle():
     """config 3 of BASELINE.json (8 keyframes x 96 patches, 10 GN iterations from identity poses)"""
     P = ba_problem(n_frames=8, patches_per_frame=96, seed=1234)
