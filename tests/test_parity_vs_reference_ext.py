@@ -106,6 +106,26 @@ def test_reproject_vs_reference():
     assert (cuda_ba.reproject(*a) - ref.reproject(*a)).abs().max().item() <= 1e-4
 
 
+def test_lietorch_se3_ops_vs_reference_fastba_device_code():
+    """the reference's lietorch backend cannot be compiled here (Eigen absent), but its fastba extension
+    carries its own SE3 device code (relative pose, action on homogeneous points: ba_cuda.cu:18-156) and is compiled in
+    oracle/_ref.  The composed projective transform built from THIS library's lietorch kernels (Inv, Mul, Act4 of
+    csrc/lie_ops.cu through the group classes) must reproduce the reference's `reproject` kernel."""
+    ref = _ref("cuda_ba_ref")
+    from devo_b200 import projective_ops as pops
+    from devo_b200.lietorch import SE3
+    P = ba_problem(n_frames=6, patches_per_frame=24, seed=33, init="perturbed", motion=0.2)
+    poses, patches, intr = P["poses0"].float().cuda(), P["patches0"].float().cuda(), P["intrinsics"].float().cuda()
+    ii, jj, kk = P["ii"].cuda(), P["jj"].cuda(), P["kk"].cuda()
+    want = ref.reproject(poses, patches, intr, ii, jj, kk)                    # [1,E,2,3,3]
+    G = SE3(poses)
+    X0 = pops.iproj(patches[:, kk], intr[:, ii])
+    X1 = (G[:, jj] * G[:, ii].inv())[:, :, None, None] * X0                   # lietorch Mul, Inv, Act4 kernels
+    got = pops.proj(X1, intr[:, jj]).permute(0, 1, 4, 2, 3)
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() <= 1e-3, (got - want).abs().max().item()      # pixels, float32 both sides
+
+
 @pytest.mark.parametrize("nf,m,iters", [(4, 24, 2), (8, 96, 2), (8, 96, 10)])
 def test_fastba_vs_reference(nf, m, iters):
     ref = _ref("cuda_ba_ref")
