@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
   int* s_blk = reinterpret_cast<int*>(sel + (size_t)npairs * ((EB + 31) >> 5));   // [EB] (bi+1) | (bj+1) << 8 | active << 16
   int* s_gbi = s_blk + EB;                                           // [GB] the patch's free source block, or -1
   __shared__ int s_batch[3];   // gs, ge, bad
-  __shared__ float s_intr[4];
+  __shared__ __align__(16) float s_intr[4];   // (aligned: read with one LDS.128 that must not straddle s_batch)
   __shared__ int s_gstart[kMaxGroupsPerCta + 1];
 
   const int tid = threadIdx.x;
