@@ -39,6 +39,8 @@ SIGNATURES = {
     "devo_ba_workspace": (_sz, [_i, _i]),
     "devo_ba_forward": (_i, [_vp] * 9 + [_i] * 7 + [_vp, _sz, _vp, _vp]),
     "devo_ba_forward_planned": (_i, [_vp] * 9 + [_i] * 7 + [_vp] * 4 + [_vp, _sz, _vp, _vp]),
+    "devo_ba_prepare": (_i, [_vp, _sz, _i, _i, _vp, _vp]),
+    "devo_ba_forward_prepared": (_i, [_vp] * 9 + [_i] * 7 + [_vp] * 4 + [_vp, _sz, _vp, _vp, _vp]),
     "devo_ba_system_doubles": (_sz, [_i]),
     "devo_ba_sharded_accumulate": (_i, [_vp] * 9 + [_i] * 8 + [_vp, _vp, _sz, _vp, _vp]),
     "devo_ba_sharded_solve": (_i, [_vp, _vp] + [_i] * 5 + [_vp, _sz, _vp, _vp]),

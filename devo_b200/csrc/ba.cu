@@ -521,7 +521,8 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
     double* __restrict__ Qg, double* __restrict__ Ug, double* __restrict__ Ekg,
     double* __restrict__ partials, double* dX, int32_t* __restrict__ ticket,
     int32_t* __restrict__ status, int E, int PP, int centre, int t0, int nfree, int n_poses,
-    int EB, int GB, int apply_update, int do_accumulate, int itr, double* __restrict__ sys_out) {
+    int EB, int GB, int apply_update, int do_accumulate, int itr, double* __restrict__ sys_out,
+    int plan_is_older, int32_t* __restrict__ status_or) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const float* poses = poses_rw;
   const int n6 = 6 * nfree;
@@ -587,12 +588,13 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
   }
   // Launched with programmatic stream serialisation.  What the previous Gauss-Newton iteration writes (poses, depths, dX,
   // Q/u/E_k, partials, tickets, status) may only be touched after the wait; the edge list and its grouping are inputs of
-  // the whole call, so from the second iteration on (`itr > 0`: the predecessor is this kernel) the chain of dependent
-  // index loads perm -> ii/jj/kk is issued BEFORE the wait and overlaps the predecessor's solve.
+  // the whole call, so from the second iteration on (`itr > 0`: the predecessor is this kernel) -- or from the first when
+  // the caller vouches that the plan is older than the predecessor (`plan_is_older`, devo_ba_forward_prepared) -- the
+  // chain of dependent index loads perm -> ii/jj/kk is issued BEFORE the wait and overlaps the predecessor's tail.
   int pre_n = -1, pre_i = 0, pre_j = 0, pre_k = 0, pre_G = 0;
   long long pre_key = -1;                                // patch of the first group this warp updates
   bool pre = false;
-  if (itr > 0 && do_accumulate) {
+  if ((itr > 0 || plan_is_older) && do_accumulate) {
     pre = true;
     pre_G = *ngroups_p;
     const int gpc_ = (pre_G + gridDim.x - 1) / gridDim.x;
@@ -614,6 +616,8 @@ __global__ void __launch_bounds__(kAccThreads, 1) ba_accumulate_kernel(
   if (blockIdx.x == (gridDim.x >> 1) && tid == 0 && do_accumulate) g_ba_clk[16] = ba_now();
 #endif
   const int st = *(volatile int32_t*)status;               // (consumed below, after the loads of the depth update are out)
+  // the last launch of a call folds the call's status into the caller's sticky word (devo_ba_forward_prepared)
+  if (!do_accumulate && status_or != nullptr && blockIdx.x == 0 && tid == 0 && st != 0) atomicOr(status_or, st);
   if (!pre && tid < 4) s_intr[tid] = intrinsics[tid];   // only intrinsics[0] is used (:232-238)
   const int G = pre ? pre_G : *ngroups_p;
   const int gpc = (G + gridDim.x - 1) / gridDim.x;
@@ -1147,7 +1151,8 @@ static int launch_accumulate(const BaLayout& L, char* w, float* poses, float* pa
                              const int64_t* jj, const int64_t* kk, int32_t* status, int E, int PP, int centre,
                              int t0, int nfree, int n_poses, int EB, int GB, size_t smem, int apply_update,
                              int do_accumulate, int itr, cudaStream_t s, const int32_t* perm_p, const int32_t* gstart_p,
-                             const int64_t* gkey_p, const int32_t* ngroups_p, double* sys_out = nullptr) {
+                             const int64_t* gkey_p, const int32_t* ngroups_p, double* sys_out = nullptr,
+                             int plan_is_older = 0, int32_t* status_or = nullptr) {
   static devo::SmemConfig configured;
   if (configured.need(smem)) {
     DEVO_CUDA(cudaFuncSetAttribute(ba_accumulate_kernel<EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1155,7 +1160,8 @@ static int launch_accumulate(const BaLayout& L, char* w, float* poses, float* pa
   DEVO_CUDA(devo::launch_pdl_cluster(ba_accumulate_kernel<EPT>, dim3(L.grid), dim3(kAccThreads), kGroupCtas, smem, s,
       poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, perm_p, gstart_p, gkey_p, ngroups_p,
       (double*)(w + L.Q), (double*)(w + L.U), (double*)(w + L.Ek), (double*)(w + L.partials),
-      (double*)(w + L.dX), (int32_t*)(w + L.ticket), status, E, PP, centre, t0, nfree, n_poses, EB, GB, apply_update, do_accumulate, itr, sys_out));
+      (double*)(w + L.dX), (int32_t*)(w + L.ticket), status, E, PP, centre, t0, nfree, n_poses, EB, GB, apply_update, do_accumulate, itr, sys_out,
+      plan_is_older, status_or));
   DEVO_LAUNCH_CHECK("ba_accumulate");
   return DEVO_OK;
 }
@@ -1173,10 +1179,10 @@ static int ba_forward_impl(float* poses, float* patches, const float* intrinsics
                            const int64_t* kk, int E, int n_poses, int n_patches, int P, int t0, int t1,
                            int iterations, void* workspace, size_t workspace_bytes, int32_t* status, void* stream,
                            const int32_t* ext_perm, const int32_t* ext_gstart, const int64_t* ext_gkey,
-                           const int32_t* ext_ngroups) {
+                           const int32_t* ext_ngroups, bool prepared = false, int32_t* status_or = nullptr) {
   cudaStream_t s = (cudaStream_t)stream;
   DEVO_REQUIRE(status != nullptr, DEVO_EINVAL, "ba_forward: status pointer is NULL");
-  DEVO_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), s));
+  if (!prepared) DEVO_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), s));
   if (E <= 0 || iterations <= 0) return DEVO_OK;
   int nfree = t1 - t0;
   if (nfree < 0) nfree = 0;
@@ -1213,7 +1219,8 @@ static int ba_forward_impl(float* poses, float* patches, const float* intrinsics
 
 #define ACC(EPT_, APPLY, DOACC, ITR)                                                                         \
   launch_accumulate<EPT_>(L, w, poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, status, E, PP, \
-                          centre, t0, nfree, n_poses, EB, GB, smem_acc, APPLY, DOACC, ITR, s, perm_p, gstart_p, gkey_p, ngroups_p)
+                          centre, t0, nfree, n_poses, EB, GB, smem_acc, APPLY, DOACC, ITR, s, perm_p, gstart_p, gkey_p, ngroups_p, \
+                          nullptr, prepared ? 1 : 0, status_or)
 #define ACC_DISPATCH(APPLY, DOACC, ITR)                   \
   do {                                                    \
     if (ept <= 2) rc = ACC(2, APPLY, DOACC, ITR);         \
@@ -1227,7 +1234,7 @@ static int ba_forward_impl(float* poses, float* patches, const float* intrinsics
   DEVO_REQUIRE(ept <= 24, DEVO_ECAPACITY, "ba_forward: system too large (%d entries)", L.nent);
   const size_t smem_solve = ((size_t)n6 * (n6 + 1) / 2 + (n6 + 1) + 18 * (n6 + 1) + 8) * 8;   // A, y, 2 column blocks + W
   DEVO_REQUIRE(smem_solve <= smem_acc, DEVO_ECAPACITY, "ba_forward: solver does not fit the accumulate CTA's shared memory");
-  DEVO_CUDA(cudaMemsetAsync(w + L.ticket, 0, 4 * 32, s));
+  if (!prepared) DEVO_CUDA(cudaMemsetAsync(w + L.ticket, 0, 4 * 32, s));
   for (int itr = 0; itr < iterations; itr++) {
     ACC_DISPATCH(itr > 0 ? 1 : 0, 1, itr);   // accumulate + (last CTA) solve + retraction
   }
@@ -1384,6 +1391,37 @@ int devo_ba_forward_planned(float* poses, float* patches, const float* intrinsic
   DEVO_REQUIRE(perm && gstart && gkey && ngroups, DEVO_EINVAL, "ba_forward_planned: plan pointers must not be NULL");
   return ba_forward_impl(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, E, n_poses, n_patches, P, t0, t1,
                          iterations, workspace, workspace_bytes, status, stream, perm, gstart, gkey, ngroups);
+}
+
+// ---- the same call with its housekeeping moved off the critical path -------------------------------------------------
+// Between the update operator and the first Gauss-Newton launch devo_ba_forward_planned issues two memsets (status,
+// ticket) -- ~4 us of serialised DMA nodes that also break the programmatic launch chain -- and the engine followed the
+// call with a one-thread kernel that ORs the status into its sticky word.  devo_ba_prepare does the two memsets whenever
+// the caller likes (the engine: on the side stream that analyses the graph, while reprojection / lookup / update operator
+// run); devo_ba_forward_prepared then launches nothing but the iterations, reads the plan ahead of the programmatic wait
+// from the first iteration on (the caller vouches the plan is older than the preceding kernel of the stream) and folds
+// the status into `status_or` (may be NULL) in its last launch.
+int devo_ba_prepare(void* workspace, size_t workspace_bytes, int E, int n_free_poses, int32_t* status, void* stream) {
+  DEVO_REQUIRE(status != nullptr, DEVO_EINVAL, "ba_prepare: status pointer is NULL");
+  cudaStream_t s = (cudaStream_t)stream;
+  DEVO_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), s));
+  if (E <= 0) return DEVO_OK;
+  BaLayout L = ba_layout(E, n_free_poses > 0 ? n_free_poses : 0);
+  DEVO_REQUIRE(workspace && workspace_bytes >= L.total, DEVO_EWORKSPACE, "ba_prepare: workspace too small (%zu < %zu)",
+               workspace_bytes, L.total);
+  DEVO_CUDA(cudaMemsetAsync((char*)workspace + L.ticket, 0, 4 * 32, s));
+  return DEVO_OK;
+}
+
+int devo_ba_forward_prepared(float* poses, float* patches, const float* intrinsics, const float* target,
+                             const float* weight, const float* lmbda, const int64_t* ii, const int64_t* jj,
+                             const int64_t* kk, int E, int n_poses, int n_patches, int P, int t0, int t1,
+                             int iterations, const int32_t* perm, const int32_t* gstart, const int64_t* gkey,
+                             const int32_t* ngroups, void* workspace, size_t workspace_bytes, int32_t* status,
+                             int32_t* status_or, void* stream) {
+  DEVO_REQUIRE(perm && gstart && gkey && ngroups, DEVO_EINVAL, "ba_forward_prepared: plan pointers must not be NULL");
+  return ba_forward_impl(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, E, n_poses, n_patches, P, t0, t1,
+                         iterations, workspace, workspace_bytes, status, stream, perm, gstart, gkey, ngroups, true, status_or);
 }
 
 int devo_reproject(const float* poses, const float* patches, const float* intrinsics, const int64_t* ii,

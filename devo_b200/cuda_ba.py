@@ -30,10 +30,20 @@ def _idx(t, name):
     return t.contiguous()
 
 
+def prepare(E, n_free, status, workspace):
+    """housekeeping of the next `forward_async(..., prepared=True)` on this workspace / status word (two memsets), on the
+    CURRENT stream -- call it wherever it is off the critical path and make that stream precede the BA"""
+    _lib.check(_lib.lib().devo_ba_prepare(workspace.data_ptr(), workspace.numel(), int(E), int(n_free), status.data_ptr(),
+                                          _lib.stream_ptr(workspace.device)), "ba_prepare")
+
+
 def forward_async(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk, t0, t1, iterations, status=None,
-                  plan=None, workspace=None):
+                  plan=None, workspace=None, prepared=False, status_or=None):
     """enqueue the BA; returns the device status tensor (int32[1]) without synchronising.
-    plan: a GraphPlan(kk, jj) of the same edge list to reuse (skips the internal sort)."""
+    plan: a GraphPlan(kk, jj) of the same edge list to reuse (skips the internal sort).
+    prepared: `prepare()` ran for this workspace / status since the last call and the plan is older than the kernel that
+    precedes this call in the stream: the call launches nothing but its iterations; status_or: int32[1] the status is
+    OR-ed into by the last launch."""
     poses = _f32c(poses, "poses", True)
     patches = _f32c(patches, "patches", True)
     intrinsics = _f32c(intrinsics, "intrinsics")
@@ -55,6 +65,16 @@ def forward_async(poses, patches, intrinsics, target, weight, lmbda, ii, jj, kk,
     ws = workspace if workspace is not None else _lib.workspace(nbytes, dev, "ba")
     if ws.numel() < nbytes:
         raise RuntimeError("cuda_ba.forward: workspace too small")
+    if prepared:
+        if plan is None or workspace is None:
+            raise RuntimeError("cuda_ba.forward_async(prepared=True) needs the plan and the workspace prepare() was called with")
+        _lib.check(L.devo_ba_forward_prepared(poses.data_ptr(), patches.data_ptr(), intrinsics.data_ptr(), target.data_ptr(),
+                                              weight.data_ptr(), lmbda.data_ptr(), ii.data_ptr(), jj.data_ptr(), kk.data_ptr(),
+                                              E, n_poses, n_patches, P, int(t0), int(t1), int(iterations),
+                                              plan.perm.data_ptr(), plan.gstart.data_ptr(), plan.gkey.data_ptr(),
+                                              plan.ngroups.data_ptr(), ws.data_ptr(), ws.numel(), status.data_ptr(),
+                                              _lib.ptr(status_or), _lib.stream_ptr(dev)), "ba_forward_prepared")
+        return status
     if plan is not None:
         _lib.check(L.devo_ba_forward_planned(poses.data_ptr(), patches.data_ptr(), intrinsics.data_ptr(), target.data_ptr(),
                                              weight.data_ptr(), lmbda.data_ptr(), ii.data_ptr(), jj.data_ptr(), kk.data_ptr(),

@@ -151,7 +151,14 @@ class UpdateOperator:
                 self._pristine[xo:xo + self.patches.numel() * 4].view(xd).view(xs))
 
     # ---- one iteration -----------------------------------------------------------------------
-    def _iteration(self, reset_geometry=False):
+    def _iteration(self, reset_geometry=False, marks=None):
+        """`marks`: optional list of 5 CUDA events recorded on the current stream at the stage boundaries (start, after the
+        reprojection, after the lookup, after the update operator, after fastba) -- bench.py times the stages inside the
+        captured step with them (events created with external=True become event-record nodes of the graph)."""
+        def mark(i):
+            if marks is not None:
+                marks[i].record(torch.cuda.current_stream(self.device))
+        mark(0)
         if reset_geometry and self._pristine is not None:
             self.state_arena[:self._geom_bytes].copy_(self._pristine)
         # (0) graph analysis on the device (neighbours, patch groups, frame-pair groups) on a side stream:
@@ -161,16 +168,20 @@ class UpdateOperator:
         self._side2.wait_stream(cur)
         with torch.cuda.stream(self._side):
             self.plan_kk.update()
+            # the two memsets of the BA call, here instead of between the update operator and the first Gauss-Newton launch
+            cuda_ba.prepare(self.E, self.t1 - self.t0, self.status, self._ba_ws)
         with torch.cuda.stream(self._side2):
             self.plan_ij.update()
         # (1) reproject: [1,E,2,3,3]
         coords = pops.transform_fused(self.poses, self.patches, self.intrinsics, self.ii, self.jj, self.kk, layout=1)
+        mark(1)
         # (2) correlation lookup over all levels, output already in the GRU's [E, 882] layout
         if self._ingest_pending:                    # an overlapped frame ingest: the lookup is its first consumer
             cur.wait_stream(self._side3)
             self._ingest_pending = False
         cuda_corr.lookup_fused(self.gmap_pm, self.levels_pm, self.levels, coords[0], self.kk, self.jj, out=self.corr_buf)
         corr = self.corr_buf if self.fused_gru else self.corr_buf[:, :self.corr_k]
+        mark(2)
         cur.wait_stream(self._side)
         cur.wait_stream(self._side2)
         # (3) GRU: cached fp16 weights, autocast-identical dtype flow, no host sync
@@ -190,6 +201,7 @@ class UpdateOperator:
             net, (delta, weight, _) = self.update.forward_planned(
                 self.net, ctx, corr.reshape(1, self.E, -1), self.plan_kk, self.plan_ij, self.Np, self.Nf * self.Nf, self.fc)
             self.net.copy_(net)
+        mark(3)
         # (4) BA targets and in-place Gauss-Newton (reuses the kk/jj plan: one sort serves neighbours,
         #     SoftAgg and the Schur grouping)
         if target is None:
@@ -197,8 +209,9 @@ class UpdateOperator:
             weight = weight.float()
         cuda_ba.forward_async(self.poses, self.patches, self.intrinsics, target, weight, self.lmbda,
                               self.ii, self.jj, self.kk, self.t0, self.t1, self.ba_iterations, status=self.status,
-                              plan=self.plan_kk, workspace=self._ba_ws)
-        torch.bitwise_or(self.status_sticky, self.status, out=self.status_sticky)     # non-zero once any iteration failed (one launch)
+                              plan=self.plan_kk, workspace=self._ba_ws, prepared=True, status_or=self.status_sticky)
+        # (status_sticky: non-zero once any iteration failed; OR-ed in by the last launch of the BA)
+        mark(4)
         self.coords, self.delta, self.weight = coords, delta, weight
 
     @torch.no_grad()

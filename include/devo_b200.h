@@ -140,6 +140,20 @@ int devo_ba_forward_planned(float* poses, float* patches, const float* intrinsic
                             int E, int n_poses, int n_patches, int P, int t0, int t1, int iterations,
                             const int32_t* perm, const int32_t* gstart, const int64_t* gkey, const int32_t* ngroups,
                             void* workspace, size_t workspace_bytes, int32_t* status, void* stream);
+
+/* The same call with its housekeeping off the critical path (used by the engine; no reference counterpart).
+ * devo_ba_prepare: the two memsets of a call (status word, 128-byte ticket area of the workspace), on any stream that
+ * is made to precede the BA.  devo_ba_forward_prepared: after a prepare for this workspace / status, launches nothing
+ * but the iterations (+ the final depth update); the caller vouches that the plan arrays are older than the kernel
+ * preceding the call in `stream`, so they are read ahead of the programmatic dependent-launch wait from the first
+ * iteration on; `status_or` (may be NULL): device word the call's status is OR-ed into by the last launch. */
+int devo_ba_prepare(void* workspace, size_t workspace_bytes, int E, int n_free_poses, int32_t* status, void* stream);
+int devo_ba_forward_prepared(float* poses, float* patches, const float* intrinsics, const float* target,
+                             const float* weight, const float* lmbda, const int64_t* ii, const int64_t* jj,
+                             const int64_t* kk, int E, int n_poses, int n_patches, int P, int t0, int t1,
+                             int iterations, const int32_t* perm, const int32_t* gstart, const int64_t* gkey,
+                             const int32_t* ngroups, void* workspace, size_t workspace_bytes, int32_t* status,
+                             int32_t* status_or, void* stream);
 /* Edge-sharded form of cuda_ba.forward for ONE frame graph split over several GPUs by owning patch (the reference has
  * no such path: train.py:90-93 runs one sequence per DDP rank; BASELINE.json north_star / SURVEY 8e ask for it).
  * Per Gauss-Newton iteration, on every rank:
