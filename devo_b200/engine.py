@@ -84,6 +84,7 @@ class UpdateOperator:
         self._side = torch.cuda.Stream(device=dev)
         self._side2 = torch.cuda.Stream(device=dev)
         self._side3 = torch.cuda.Stream(device=dev)
+        self._side4 = torch.cuda.Stream(device=dev)
         self._ingest_pending = False
         self._ba_ws = torch.empty(_lib.lib().devo_ba_workspace(self.E, max(self.t1 - self.t0, 0)), dtype=torch.uint8, device=dev)
         self._graph = None
@@ -103,24 +104,32 @@ class UpdateOperator:
             self.plan_kk = cuda_ba.GraphPlan(self.kk, self.jj, self.Np, self.Nf)
             self.plan_ij = cuda_ba.GraphPlan(self.pair_key, self.zeros_e, -1, 1, want_neighbors=False)
 
-    def ingest_frame(self, idx, fmap, gmap_patches=None, imap_patches=None, overlap=False):
+    def ingest_frame(self, idx, fmap, gmap_patches=None, imap_patches=None, overlap=False, only_levels=None):
         """fmap [C,H,W] planar features of frame `idx` -> all pixel-major pyramid levels;
         gmap_patches [M,C,3,3], imap_patches [M,dim] -> patch feature buffers.
         overlap=True: the packing runs on a side stream; the next iteration joins it right before the correlation
         lookup (its first consumer), so it overlaps the graph analysis and the reprojection."""
         if overlap:
+            # two side streams: the full-resolution level on one, the pooled levels + patch features on the other.  The
+            # lookup is the first consumer of both, and 20 us of packing in a row on ONE stream were longer than the reset
+            # + reprojection they are meant to hide behind (12 us): the ingest sat on the critical path of the step.
             cur = torch.cuda.current_stream(self.device)
             self._side3.wait_stream(cur)
+            self._side4.wait_stream(cur)
             with torch.cuda.stream(self._side3):
-                self.ingest_frame(idx, fmap, gmap_patches, imap_patches, overlap=False)
+                self.ingest_frame(idx, fmap, None, None, overlap=False, only_levels=(0,))
+            with torch.cuda.stream(self._side4):
+                self.ingest_frame(idx, fmap, gmap_patches, imap_patches, overlap=False, only_levels=tuple(range(1, len(self.levels))))
             for t in (fmap, gmap_patches, imap_patches):
                 if t is not None and t.is_cuda:          # the caller may drop its inputs right away: the caching allocator must
                     t.record_stream(self._side3)         # not hand their memory out while the packing kernels still read it
+                    t.record_stream(self._side4)
             self._ingest_pending = True
             return
         f = fmap.reshape(1, self.C, self.H, self.W).to(self.feat_dtype)
         for l, s in enumerate(self.levels):        # packed straight into the ring-buffer slot (no staging copy)
-            cuda_corr.pack_pixel_major(f, s, out=self.levels_pm[l][idx:idx + 1])
+            if only_levels is None or l in only_levels:
+                cuda_corr.pack_pixel_major(f, s, out=self.levels_pm[l][idx:idx + 1])
         if gmap_patches is not None:
             cuda_corr.pack_gmap(gmap_patches.to(self.feat_dtype), out=self.gmap_pm[idx * self.M:(idx + 1) * self.M])
         if imap_patches is not None:
@@ -178,6 +187,7 @@ class UpdateOperator:
         # (2) correlation lookup over all levels, output already in the GRU's [E, 882] layout
         if self._ingest_pending:                    # an overlapped frame ingest: the lookup is its first consumer
             cur.wait_stream(self._side3)
+            cur.wait_stream(self._side4)
             self._ingest_pending = False
         cuda_corr.lookup_fused(self.gmap_pm, self.levels_pm, self.levels, coords[0], self.kk, self.jj, out=self.corr_buf)
         corr = self.corr_buf if self.fused_gru else self.corr_buf[:, :self.corr_k]
@@ -237,5 +247,6 @@ class UpdateOperator:
     def replay(self):
         if self._ingest_pending:                         # an overlapped ingest issued OUTSIDE the captured graph: join it here
             torch.cuda.current_stream(self.device).wait_stream(self._side3)
+            torch.cuda.current_stream(self.device).wait_stream(self._side4)
             self._ingest_pending = False
         self._graph.replay()
