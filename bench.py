@@ -600,7 +600,7 @@ def run_ours(args, rank, world, local_rank):
                     note="window gathers overlap ~6x: L2->SM bytes, not HBM bytes, bound this kernel (DESIGN.md)")
 
 
-    # ---- tensor roofline of the fused update operator (gru_mma_kernel x6: the largest share of a step), timed alone
+    # ---- tensor roofline of the fused update operator (gru_mma_kernel x5 + 2 segment reductions: the largest share of a step), timed alone
     roofline_gru = None
     if args.gru == "mma":
         with torch.no_grad():
