@@ -59,6 +59,30 @@ def frontend_from_reference_network(network, cfg):
     return patchify
 
 
+def frontend_from_encoders(fnet, inet, cfg, select=None):
+    """front end of PatchGraphVO on this library's fused patch gather (devo_b200/frontend.py): `fnet` / `inet` are the two
+    encoders (any callables image [1,1,B,H,W] -> [1,1,C,H/4,W/4]; the reference divides their outputs by 4, enet.py:125-126),
+    `select(image, n_patches)` -> centres [1,M,2] (default: the reference's RANDOM selection)."""
+    from .frontend import gather_patches
+
+    def patchify(image):
+        with torch.autocast("cuda", enabled=bool(cfg.MIXED_PRECISION)):
+            fmap = fnet(image[None, None]) / 4.0
+            imap = inet(image[None, None]) / 4.0
+        fmap, imap = fmap[0], imap[0].to(fmap.dtype)
+        h, w = fmap.shape[-2:]
+        M = cfg.PATCHES_PER_FRAME
+        if select is None:
+            x = torch.randint(1, w - 1, size=[1, M], device=fmap.device)
+            y = torch.randint(1, h - 1, size=[1, M], device=fmap.device)
+            coords = torch.stack([x, y], dim=-1).float()
+        else:
+            coords = select(image, M)
+        g, gpm, im, pt = gather_patches(fmap, imap, coords, None, 3, planar=False, pixel_major=True)
+        return dict(fmap=fmap[0], gmap=None, gmap_pm=gpm, imap=im, patches=pt, clr=None)
+    return patchify
+
+
 class PatchGraphVO:
     def __init__(self, cfg, update, patchify, ht=480, wd=640, dim_inet=384, dim_fnet=128, P=3, RES=4.0, mem=32,
                  levels=(1, 4), device="cuda", edge_capacity=65536):
@@ -265,7 +289,10 @@ class PatchGraphVO:
         # ---- ring-buffer ingest in the lookup's layouts (replaces devo.py:523-527 + avg_pool2d)
         slot = n % mem
         self.imap_[slot * M:(slot + 1) * M] = fe["imap"].reshape(M, self.dim).to(self.dt)
-        cuda_corr.pack_gmap(fe["gmap"].reshape(M, self.C, self.P, self.P).to(self.dt), out=self.gmap_pm[slot * M:(slot + 1) * M])
+        if fe.get("gmap_pm") is not None:             # a front end on devo_b200.frontend hands the pixel-major patches over directly
+            self.gmap_pm[slot * M:(slot + 1) * M] = fe["gmap_pm"].reshape(M, self.P * self.P, self.C).to(self.dt)
+        else:
+            cuda_corr.pack_gmap(fe["gmap"].reshape(M, self.C, self.P, self.P).to(self.dt), out=self.gmap_pm[slot * M:(slot + 1) * M])
         fmap = fe["fmap"].reshape(1, self.C, self.H4, self.W4).to(self.dt)
         for l, s in enumerate(self.levels):
             cuda_corr.pack_pixel_major(fmap, s, out=self.levels_pm[l][slot:slot + 1])

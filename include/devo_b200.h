@@ -62,6 +62,16 @@ int devo_patchify_forward(const void* net, const float* coords, void* patches, i
 int devo_patchify_backward(const void* patch_grad, const float* coords, void* net_grad, int dtype,
                            int B, int C, int H, int W, int M, int radius, void* stream);
 
+/* The tail of Patchifier.forward (devo/enet.py:179-191) as one launch: for patch centres coords [N,M,2] (x, y at feature
+ * resolution) the bilinear-mode altcorr.patchify of fmap [N,C,H,W] at radius P/2 (-> gmap_planar [N*M,C,P,P] and / or
+ * gmap_pm [N*M,P*P,C], the layout devo_corr_lookup_fused reads), of imap [N,D,H,W] at radius 0 (-> imap_out [N*M,D]) and of
+ * the (x, y, disps) grid of coords_grid_with_index at radius P/2 (-> patches [N*M,3,P,P] float; disps [N,H,W] or NULL =
+ * ones).  Blend in float32 like the reference (float32 offsets x half windows), outputs rounded to `dtype`.  Any of
+ * fmap / imap / patches may be NULL. */
+int devo_patch_gather(const void* fmap, const void* imap, const float* disps, const float* coords, void* gmap_planar,
+                      void* gmap_pm, void* imap_out, float* patches, int dtype, int N, int C, int D, int H, int W, int M,
+                      int P, void* stream);
+
 /* --- B200-native fast path of the lookup: pixel-major (channels-last) pyramid + fused
  * multi-level lookup.  Same arithmetic as devo_corr_forward over every level; replaces
  * pyramidify + 2x altcorr.corr + torch.stack (devo/devo.py:210-217, devo/enet.py:203-216,
