@@ -572,6 +572,24 @@ def run_ours(args, rank, world, local_rank):
         s = torch.tensor([status], device=dev)
         torch.distributed.all_reduce(s, op=torch.distributed.ReduceOp.MAX)
         status = int(s.item())
+        # BASELINE.json config 5: the one collective of the reference's multi-GPU path is DDP's gradient all-reduce
+        # (train.py:106-107); the update operator's parameters are 3.0 M floats = 12.0 MB.  Timed here at this world size
+        # (NCCL over NVLink, CUDA events, max over ranks), outside the timed steps.
+        nparam = sum(p.numel() for p in up.parameters())
+        gbuf = torch.zeros(nparam, dtype=torch.float32, device=dev)
+        for _ in range(5):
+            torch.distributed.all_reduce(gbuf)
+        torch.cuda.synchronize(dev)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(20):
+            torch.distributed.all_reduce(gbuf)
+        a1.record()
+        torch.cuda.synchronize(dev)
+        ar = torch.tensor([a0.elapsed_time(a1) / 20 * 1e3], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(ar, op=torch.distributed.ReduceOp.MAX)
+        ddp_allreduce = dict(us=round(float(ar.item()), 1), bytes=nparam * 4, world=world,
+                             bus_gbs=round(2 * (world - 1) / world * nparam * 4 / (float(ar.item()) * 1e-6) / 1e9, 1))
     if rank != 0:
         return None
     if args.profile:
@@ -657,6 +675,8 @@ def run_ours(args, rank, world, local_rank):
                             ba_status=status, value_l2_warm=round(world * args.steps / (warm_ms * 1e-3), 2),
                             value_l2_flushed_clean=(round(world / (clean_ms * 1e-3), 2) if clean_ms else None)),
                 roofline=(roofline_gru if roofline_gru is not None else roofline_corr), roofline_corr=roofline_corr, e2e=e2e, gpu_launches=int(launches_per_step * args.steps), clocks=clocks)
+    if world > 1:
+        line["extra"] = {"config5_ddp_gradient_allreduce": ddp_allreduce}
     if in_step is not None:
         line["in_step_us"] = in_step
     if per_op is not None:
