@@ -115,6 +115,7 @@ class PatchGraphVO:
         self.kk = torch.zeros(0, dtype=i64, device=dev)
         self.state = GruState(0, dev, dim_inet)
         self.first_update = True                   # the very first update sees a half zero-state (devo.py:84)
+        self._graph_epoch, self._plan_epoch = 0, -1  # bumped by append / remove_factors; the plans are rebuilt when they differ
         self.corr_ld = (441 * len(self.levels) + 63) // 64 * 64
         self.cap = int(edge_capacity)
         self.corr_buf = torch.zeros(self.cap, self.corr_ld, dtype=self.dt, device=dev)
@@ -158,11 +159,13 @@ class PatchGraphVO:
             raise RuntimeError("PatchGraphVO: edge capacity %d exceeded" % self.cap)
         idx = torch.cat([torch.arange(E0, device=self.device), torch.full((ii.numel(),), -1, dtype=torch.int64, device=self.device)])
         self.state = self.state.gather(idx)                    # new edges start from a zero hidden state
+        self._graph_epoch += 1
 
     def remove_factors(self, m):
         keep = torch.nonzero(~m).view(-1)
         self.ii, self.jj, self.kk = self.ii[keep], self.jj[keep], self.kk[keep]
         self.state = self.state.gather(keep)
+        self._graph_epoch += 1
 
     # ---- the unit of work (devo.py:210-223, 308-338)
     def _lookup(self, coords, kk, jj, E):
@@ -182,8 +185,10 @@ class PatchGraphVO:
     @torch.no_grad()
     def update(self):
         E = self.ii.numel()
-        self.plan_kk.rebind(self.kk, self.jj)
-        self.plan_ij.rebind(self.ii * 12345 + self.jj, torch.zeros_like(self.ii))
+        if self._plan_epoch != self._graph_epoch:              # the edge list only changes in append / remove_factors: the 12
+            self.plan_kk.rebind(self.kk, self.jj)              # updates of the initialisation (devo.py:536-538) share one analysis
+            self.plan_ij.rebind(self.ii * 12345 + self.jj, torch.zeros_like(self.ii))
+            self._plan_epoch = self._graph_epoch
         net16 = torch.zeros(1, E, self.dim, dtype=self.dt, device=self.device) if self.first_update else None
         self.first_update = False
         n_act = self.n
