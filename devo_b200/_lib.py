@@ -27,6 +27,7 @@ SIGNATURES = {
     "devo_patchify_forward": (_i, [_vp] * 3 + [_i] * 7 + [_vp]),
     "devo_patchify_backward": (_i, [_vp] * 3 + [_i] * 7 + [_vp]),
     "devo_pyramid_pack": (_i, [_vp, _vp] + [_i] * 6 + [_vp]),
+    "devo_pyramid_pack2": (_i, [_vp] * 3 + [_i] * 6 + [_vp]),
     "devo_gmap_pack": (_i, [_vp, _vp] + [_i] * 4 + [_vp]),
     "devo_patch_gather": (_i, [_vp] * 8 + [_i] * 8 + [_vp]),
     "devo_corr_lookup_fused": (_i, [_vp] * 6 + [_i] * 5 + [_vp]),

@@ -695,6 +695,59 @@ __global__ void __launch_bounds__(256) pyramid_pack_vec_kernel(const T* __restri
   }
 }
 
+// two pyramid levels from ONE read of the frame: the full-resolution level (a transpose) and the POOL x POOL average-pooled
+// level (same summation order and division as the kernels above, so the results are bit-identical to two separate calls).
+// CTA = POOL input rows x 8 input pixels (one 16-byte chunk per channel and row) x all channels, staged as raw T in shared
+// memory ([row][pixel][C + 8]); small tiles on purpose: 600 CTAs for a 160x120 frame keep every SM busy with several
+// (a 32-pixel tile gave 150 CTAs, one per SM, and no faster than the two separate kernels).
+template <typename T, int POOL>
+__global__ void __launch_bounds__(256) pyramid_pack2_kernel(const T* __restrict__ in, T* __restrict__ out1, T* __restrict__ outp,
+                                                            int C, int H, int W) {
+  extern __shared__ __align__(16) unsigned char tile_raw[];
+  T* tile = reinterpret_cast<T*>(tile_raw);           // [POOL][8][C + 8]
+  const int ld = C + 8;
+  const int n = blockIdx.z, yo = blockIdx.y, x0 = blockIdx.x * 8;
+  const T* src = in + (size_t)n * C * H * W;
+  for (int q = threadIdx.x; q < POOL * C; q += blockDim.x) {
+    const int c = q % C, a = q / C;
+    const uint4 raw = *reinterpret_cast<const uint4*>(src + ((size_t)c * H + (size_t)yo * POOL + a) * W + x0);
+    const T* v = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+    for (int k = 0; k < 8; k++) tile[((size_t)a * 8 + k) * ld + c] = v[k];
+  }
+  __syncthreads();
+  const int cv = C / 8;
+  // level 1: [y][x][C], 16-byte stores along C
+  for (int q = threadIdx.x; q < POOL * 8 * cv; q += blockDim.x) {
+    const int c8 = q % cv, x = (q / cv) & 7, a = q / (cv * 8);
+    const uint4 pk = *reinterpret_cast<const uint4*>(tile + ((size_t)a * 8 + x) * ld + c8 * 8);
+    *reinterpret_cast<uint4*>(out1 + (((size_t)n * H + (size_t)yo * POOL + a) * W + x0 + x) * C + c8 * 8) = pk;
+  }
+  // pooled level: rows outer, columns inner (the order of pyramid_pack_vec_kernel), then / POOL^2
+  const int Ho = H / POOL, Wo = W / POOL;
+  constexpr int NXO = 8 / POOL;
+  for (int q = threadIdx.x; q < NXO * cv; q += blockDim.x) {
+    const int c8 = q % cv, xo = q / cv;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = 0.f;
+#pragma unroll
+    for (int a = 0; a < POOL; a++)
+#pragma unroll
+      for (int b = 0; b < POOL; b++) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(tile + ((size_t)a * 8 + xo * POOL + b) * ld + c8 * 8);
+        const T* v = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] += devo::ElemTraits<T>::to_float(v[k]);
+      }
+    uint4 pk;
+    T* o = reinterpret_cast<T*>(&pk);
+#pragma unroll
+    for (int k = 0; k < 8; k++) o[k] = devo::ElemTraits<T>::from_float(acc[k] / (float)(POOL * POOL));
+    *reinterpret_cast<uint4*>(outp + (((size_t)n * Ho + yo) * Wo + x0 / POOL + xo) * C + c8 * 8) = pk;
+  }
+}
+
 template <typename T>
 __global__ void gmap_pack_kernel(const T* __restrict__ in, T* __restrict__ out, int Np, int C, int PP) {
   const long long total = (long long)Np * C * PP;
@@ -830,6 +883,30 @@ int devo_pyramid_pack(const void* fmap_planar, void* out_pixel_major, int dtype,
 #undef PACK_ANY
 #undef PACK_VEC
   DEVO_LAUNCH_CHECK("pyramid_pack");
+  return DEVO_OK;
+}
+
+int devo_pyramid_pack2(const void* fmap_planar, void* out_level1, void* out_pooled, int dtype, int N, int C, int H, int W,
+                       int pool, void* stream) {
+  DEVO_REQUIRE(dtype == DEVO_F16 || dtype == DEVO_BF16, DEVO_EINVAL, "pyramid_pack2: dtype must be f16 or bf16");
+  DEVO_REQUIRE(pool == 2 || pool == 4 || pool == 8, DEVO_EUNSUPPORTED, "pyramid_pack2: pool must be 2, 4 or 8");
+  DEVO_REQUIRE(N >= 0 && C > 0 && C % 8 == 0 && W % 8 == 0 && H % pool == 0 && W % pool == 0 && H >= pool, DEVO_EUNSUPPORTED,
+               "pyramid_pack2: needs C %% 8 == 0, W %% 8 == 0 and H, W multiples of the pool size");
+  DEVO_REQUIRE((((uintptr_t)fmap_planar | (uintptr_t)out_level1 | (uintptr_t)out_pooled) & 15) == 0, DEVO_EINVAL,
+               "pyramid_pack2: buffers must be 16-byte aligned");
+  if (N == 0) return DEVO_OK;
+  DEVO_REQUIRE(H / pool <= 65535 && N <= 65535, DEVO_EINVAL, "pyramid_pack2: dims too large");
+  const size_t smem = (size_t)pool * 8 * (C + 8) * 2;
+  DEVO_REQUIRE(smem <= 48 * 1024, DEVO_ECAPACITY, "pyramid_pack2: C too large for one tile");
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid(W / 8, H / pool, N);
+#define PACK2(T, POOL) pyramid_pack2_kernel<T, POOL><<<grid, 256, smem, s>>>((const T*)fmap_planar, (T*)out_level1, (T*)out_pooled, C, H, W)
+#define PACK2_ANY(T) do { if (pool == 2) PACK2(T, 2); else if (pool == 4) PACK2(T, 4); else PACK2(T, 8); } while (0)
+  if (dtype == DEVO_F16) PACK2_ANY(__half);
+  else PACK2_ANY(__nv_bfloat16);
+#undef PACK2_ANY
+#undef PACK2
+  DEVO_LAUNCH_CHECK("pyramid_pack2");
   return DEVO_OK;
 }
 

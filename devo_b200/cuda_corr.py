@@ -46,6 +46,22 @@ def pack_pixel_major(fmap, pool=1, out=None):
     return out
 
 
+def pack_pixel_major2(fmap, pool, out1, outp):
+    """the two levels of a [1, pool] pyramid from one read of the frames (bit-identical to two pack_pixel_major calls);
+    returns False -- nothing written -- when the shapes are outside what the fused kernel takes"""
+    _lib.require_cuda(fmap, out1, outp)
+    N, C, H, W = fmap.shape
+    if (pool not in (2, 4, 8) or C % 8 or W % 8 or H % pool or W % pool or pool * 8 * (C + 8) * 2 > 48 * 1024
+            or fmap.dtype not in (torch.float16, torch.bfloat16) or not fmap.is_contiguous()
+            or not out1.is_contiguous() or not outp.is_contiguous() or out1.dtype != fmap.dtype or outp.dtype != fmap.dtype
+            or out1.numel() != N * H * W * C or outp.numel() != N * (H // pool) * (W // pool) * C
+            or (fmap.data_ptr() | out1.data_ptr() | outp.data_ptr()) & 15):
+        return False
+    _lib.check(_lib.lib().devo_pyramid_pack2(fmap.data_ptr(), out1.data_ptr(), outp.data_ptr(), _lib.dtype_code(fmap),
+                                             N, C, H, W, pool, _lib.stream_ptr(fmap.device)), "pyramid_pack2")
+    return True
+
+
 def pack_gmap(gmap, out=None):
     """planar [Np,C,P,P] -> [Np,P*P,C]  (`out`: contiguous destination to pack into directly)"""
     _lib.require_cuda(gmap)

@@ -116,10 +116,12 @@ class UpdateOperator:
             cur = torch.cuda.current_stream(self.device)
             self._side3.wait_stream(cur)
             self._side4.wait_stream(cur)
+            fused2 = len(self.levels) == 2 and self.levels[0] == 1       # both levels from one read of the frame
             with torch.cuda.stream(self._side3):
-                self.ingest_frame(idx, fmap, None, None, overlap=False, only_levels=(0,))
+                self.ingest_frame(idx, fmap, None, None, overlap=False, only_levels=((0, 1) if fused2 else (0,)))
             with torch.cuda.stream(self._side4):
-                self.ingest_frame(idx, fmap, gmap_patches, imap_patches, overlap=False, only_levels=tuple(range(1, len(self.levels))))
+                self.ingest_frame(idx, fmap, gmap_patches, imap_patches, overlap=False,
+                                  only_levels=(() if fused2 else tuple(range(1, len(self.levels)))))
             for t in (fmap, gmap_patches, imap_patches):
                 if t is not None and t.is_cuda:          # the caller may drop its inputs right away: the caching allocator must
                     t.record_stream(self._side3)         # not hand their memory out while the packing kernels still read it
@@ -127,9 +129,12 @@ class UpdateOperator:
             self._ingest_pending = True
             return
         f = fmap.reshape(1, self.C, self.H, self.W).to(self.feat_dtype)
-        for l, s in enumerate(self.levels):        # packed straight into the ring-buffer slot (no staging copy)
-            if only_levels is None or l in only_levels:
-                cuda_corr.pack_pixel_major(f, s, out=self.levels_pm[l][idx:idx + 1])
+        want = [l for l in range(len(self.levels)) if only_levels is None or l in only_levels]
+        if want == [0, 1] and len(self.levels) == 2 and self.levels[0] == 1 and cuda_corr.pack_pixel_major2(
+                f, self.levels[1], self.levels_pm[0][idx:idx + 1], self.levels_pm[1][idx:idx + 1]):
+            want = []                              # the [1, s] pyramid of DEVO: one kernel, one read of the frame
+        for l in want:                             # packed straight into the ring-buffer slot (no staging copy)
+            cuda_corr.pack_pixel_major(f, self.levels[l], out=self.levels_pm[l][idx:idx + 1])
         if gmap_patches is not None:
             cuda_corr.pack_gmap(gmap_patches.to(self.feat_dtype), out=self.gmap_pm[idx * self.M:(idx + 1) * self.M])
         if imap_patches is not None:

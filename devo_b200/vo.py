@@ -299,8 +299,10 @@ class PatchGraphVO:
         else:
             cuda_corr.pack_gmap(fe["gmap"].reshape(M, self.C, self.P, self.P).to(self.dt), out=self.gmap_pm[slot * M:(slot + 1) * M])
         fmap = fe["fmap"].reshape(1, self.C, self.H4, self.W4).to(self.dt)
-        for l, s in enumerate(self.levels):
-            cuda_corr.pack_pixel_major(fmap, s, out=self.levels_pm[l][slot:slot + 1])
+        if not (len(self.levels) == 2 and self.levels[0] == 1 and cuda_corr.pack_pixel_major2(
+                fmap, self.levels[1], self.levels_pm[0][slot:slot + 1], self.levels_pm[1][slot:slot + 1])):
+            for l, s in enumerate(self.levels):
+                cuda_corr.pack_pixel_major(fmap, s, out=self.levels_pm[l][slot:slot + 1])
         self.counter += 1
         if self.n > 0 and not self.is_initialized:
             thres = 2.0 if scale == 1.0 else scale ** 2

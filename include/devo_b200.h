@@ -80,6 +80,10 @@ int devo_patch_gather(const void* fmap, const void* imap, const float* disps, co
  * pixel-major [N,H/pool,W/pool,C] (f16 or bf16). */
 int devo_pyramid_pack(const void* fmap_planar, void* out_pixel_major, int dtype,
                       int N, int C, int H, int W, int pool, void* stream);
+/* both levels of a [1, pool] pyramid from ONE read of the frames: out_level1 [N,H,W,C] and out_pooled [N,H/pool,W/pool,C];
+ * bit-identical to two devo_pyramid_pack calls.  pool in {2,4,8}; C % 8 == 0, W % 8 == 0, H and W multiples of pool. */
+int devo_pyramid_pack2(const void* fmap_planar, void* out_level1, void* out_pooled, int dtype, int N, int C, int H, int W,
+                       int pool, void* stream);
 /* repack gmap [Np,C,P,P] -> [Np,P*P,C] */
 int devo_gmap_pack(const void* gmap_planar, void* out, int dtype, int Np, int C, int PP, void* stream);
 #define DEVO_MAX_LEVELS 4

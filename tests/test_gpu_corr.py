@@ -120,6 +120,23 @@ def test_split_precision_multilevel_matches_per_level_float32():
     assert _rel(out, ref) <= 1e-5, _rel(out, ref)
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("pool,H,W,C", [(4, 120, 160, 128), (2, 30, 40, 64), (8, 32, 72, 128)])
+def test_pyramid_pack2_is_bit_identical_to_two_packs(dtype, pool, H, W, C):
+    """both levels of a [1, pool] pyramid from one read == pack(1) and pack(pool) == permute / F.avg_pool2d"""
+    import torch.nn.functional as F
+    from devo_b200 import cuda_corr
+    g = torch.Generator().manual_seed(3)
+    f = torch.randn(3, C, H, W, generator=g).to(dtype).cuda()
+    o1 = torch.empty(3, H, W, C, dtype=dtype, device="cuda")
+    op = torch.empty(3, H // pool, W // pool, C, dtype=dtype, device="cuda")
+    assert cuda_corr.pack_pixel_major2(f, pool, o1, op)
+    assert torch.equal(o1, cuda_corr.pack_pixel_major(f, 1)) and torch.equal(o1, f.permute(0, 2, 3, 1))
+    assert torch.equal(op, cuda_corr.pack_pixel_major(f, pool))
+    assert torch.equal(op, F.avg_pool2d(f, pool, pool).permute(0, 2, 3, 1))
+    assert not cuda_corr.pack_pixel_major2(f[:, :, :, :W - 4].contiguous(), pool, o1, op)       # W % 8 != 0: declined, caller falls back
+
+
 def test_fused_multilevel_layout_matches_stack():
     """lookup_fused over levels [1,4] == torch.stack([corr(l) for l], -1).view(1,E,-1) (devo.py:210-217)"""
     from devo_b200 import cuda_corr
