@@ -40,7 +40,8 @@ __global__ void __launch_bounds__(NT) plan_small_kernel(
     int32_t* __restrict__ perm, int32_t* __restrict__ gid, int32_t* __restrict__ gstart,
     int64_t* __restrict__ gkey, int32_t* __restrict__ ngroups, int64_t* __restrict__ ix,
     int64_t* __restrict__ jx, int64_t* __restrict__ sorted_a /* workspace i64[E] */,
-    int32_t* __restrict__ perm_ws /* workspace i32[E] (used when perm == NULL) */) {
+    int32_t* __restrict__ perm_ws /* workspace i32[E] (used when perm == NULL) */,
+    int hint_bits_a, int hint_bits_b /* significant bits of ka / kb when the caller gave both bounds, else -1 */) {
   using P = PlanSmall<NT, IPT>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typename P::Temp& temp = *reinterpret_cast<typename P::Temp*>(smem_raw);
@@ -62,13 +63,18 @@ __global__ void __launch_bounds__(NT) plan_small_kernel(
       a[k] = 0; b[k] = 0;
     }
   }
-  ma = typename P::Reduce(temp.reduce).Reduce(ma, cub::Max());
-  __syncthreads();
-  mb = typename P::Reduce(temp.reduce).Reduce(mb, cub::Max());
-  if (tid == 0) { s_max[0] = ma; s_max[1] = mb; }
-  __syncthreads();
-  const int bits_b = bits_needed(s_max[1]);
-  int bits_a = bits_needed(s_max[0]);
+  int bits_a, bits_b;
+  if (hint_bits_a > 0 && hint_bits_b > 0) {      // both exclusive bounds known on the host: no max-reductions
+    bits_a = hint_bits_a; bits_b = hint_bits_b;
+  } else {
+    ma = typename P::Reduce(temp.reduce).Reduce(ma, cub::Max());
+    __syncthreads();
+    mb = typename P::Reduce(temp.reduce).Reduce(mb, cub::Max());
+    if (tid == 0) { s_max[0] = ma; s_max[1] = mb; }
+    __syncthreads();
+    bits_b = bits_needed(s_max[1]);
+    bits_a = bits_needed(s_max[0]);
+  }
   if (bits_a + bits_b > 62) bits_a = 62 - bits_b;   // ids are tensor indices; cannot happen in practice
   const int bits = bits_a + bits_b;
 
@@ -208,7 +214,7 @@ static LargeLayout large_layout(int E) {
 template <int NT, int IPT>
 static int launch_small(const int64_t* ka, const int64_t* kb, int E, int32_t* perm, int32_t* gid,
                         int32_t* gstart, int64_t* gkey, int32_t* ngroups, int64_t* ix, int64_t* jx,
-                        void* ws, cudaStream_t s) {
+                        void* ws, cudaStream_t s, int hint_a, int hint_b) {
   using P = PlanSmall<NT, IPT>;
   static devo::SmemConfig configured;
   const int smem = (int)sizeof(typename P::Temp);
@@ -216,7 +222,7 @@ static int launch_small(const int64_t* ka, const int64_t* kb, int E, int32_t* pe
   int64_t* sorted_a = (int64_t*)ws;
   int32_t* perm_ws = (int32_t*)((char*)ws + align_up((size_t)E * 8));
   plan_small_kernel<NT, IPT><<<1, NT, smem, s>>>(ka, kb, E, perm, gid, gstart, gkey, ngroups, ix, jx,
-                                                 sorted_a, perm_ws);
+                                                 sorted_a, perm_ws, hint_a, hint_b);
   DEVO_LAUNCH_CHECK("graph_plan(small)");
   return DEVO_OK;
 }
@@ -243,10 +249,16 @@ int devo_graph_plan(const int64_t* ka, const int64_t* kb, int E, int64_t max_ka,
   }
   DEVO_REQUIRE(workspace && workspace_bytes >= devo_graph_plan_workspace(E), DEVO_EWORKSPACE,
                "graph_plan: workspace too small (%zu < %zu)", workspace_bytes, devo_graph_plan_workspace(E));
-  (void)max_kb;
-  if (E <= 2048) return launch_small<512, 4>(ka, kb, E, perm, gid, gstart, gkey, ngroups, ix, jx, workspace, s);
-  if (E <= 8192) return launch_small<1024, 8>(ka, kb, E, perm, gid, gstart, gkey, ngroups, ix, jx, workspace, s);
-  if (E <= kSmallMax) return launch_small<512, 32>(ka, kb, E, perm, gid, gstart, gkey, ngroups, ix, jx, workspace, s);
+  // both exclusive bounds given: the number of significant key bits is known here and the kernel skips its max-reductions
+  int hint_a = -1, hint_b = -1;
+  if (max_ka > 0 && max_kb > 0) {
+    auto nbits = [](int64_t bound) { int b = 1; while (b < 62 && ((int64_t)1 << b) < bound) b++; return b; };
+    hint_a = nbits(max_ka); hint_b = nbits(max_kb);
+    if (hint_a + hint_b > 62) hint_a = hint_b = -1;
+  }
+  if (E <= 2048) return launch_small<512, 4>(ka, kb, E, perm, gid, gstart, gkey, ngroups, ix, jx, workspace, s, hint_a, hint_b);
+  if (E <= 8192) return launch_small<1024, 8>(ka, kb, E, perm, gid, gstart, gkey, ngroups, ix, jx, workspace, s, hint_a, hint_b);
+  if (E <= kSmallMax) return launch_small<512, 32>(ka, kb, E, perm, gid, gstart, gkey, ngroups, ix, jx, workspace, s, hint_a, hint_b);
 
   // large path: ids are assumed < 2^32 (they index tensors)
   LargeLayout L = large_layout(E);
