@@ -738,7 +738,7 @@ def run_e2e(op, wl, dev, steps):
 
     def body(b):
         op.state_arena.copy_(stage[b][state_off:], non_blocking=True)      # the state the caller uploaded this step
-        torch.add(op.ii * 12345, op.jj, out=op.pair_key)
+        op.refresh_pair_key()
         op.ingest_frame(f, view(stage[b], "fmap"), view(stage[b], "gmap"), view(stage[b], "imap"), overlap=True)
         op._iteration(reset_geometry=False)
         out_dev[:Nf * 7].copy_(op.poses.view(-1))

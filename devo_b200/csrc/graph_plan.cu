@@ -64,7 +64,11 @@ __global__ void __launch_bounds__(NT) plan_small_kernel(
     }
   }
   int bits_a, bits_b;
-  if (hint_bits_a > 0 && hint_bits_b > 0) {      // both exclusive bounds known on the host: no max-reductions
+  // both exclusive bounds known on the host: no max-reductions -- unless a key breaks its bound (one block-wide OR), in which
+  // case the bounds are ignored: the hint can make the plan faster, never wrong
+  bool hinted = (hint_bits_a > 0 && hint_bits_b > 0);
+  if (hinted) hinted = !__syncthreads_or((int)(((ma >> hint_bits_a) | (mb >> hint_bits_b)) != 0ull));
+  if (hinted) {
     bits_a = hint_bits_a; bits_b = hint_bits_b;
   } else {
     ma = typename P::Reduce(temp.reduce).Reduce(ma, cub::Max());

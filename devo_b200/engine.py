@@ -99,13 +99,17 @@ class UpdateOperator:
         self.ii.copy_(ii)
         self.jj.copy_(jj)
         self.kk.copy_(kk)
-        # frame-pair key of SoftAgg's second grouping: the reference uses ii * 12345 + jj (blocks.py / enet.py:96); any key
-        # that orders the pairs the same way gives the same groups -- ii * Nf + jj needs 6 bits instead of 17, i.e. half the
-        # radix passes of the plan
-        torch.add(self.ii * self.Nf, self.jj, out=self.pair_key)
+        self.refresh_pair_key()
         if self.plan_kk is None:
             self.plan_kk = cuda_ba.GraphPlan(self.kk, self.jj, self.Np, self.Nf)
             self.plan_ij = cuda_ba.GraphPlan(self.pair_key, self.zeros_e, self.Nf * self.Nf, 1, want_neighbors=False)
+
+    def refresh_pair_key(self):
+        """(re)compute the frame-pair key of SoftAgg's second grouping from ii / jj -- after set_graph, or after the caller
+        refreshed `state_arena` with a new edge list.  The reference uses ii * 12345 + jj (enet.py:96); any key that orders
+        the pairs the same way gives the same groups, and ii * Nf + jj needs 6 bits instead of 17: half the radix passes of
+        the plan, whose width the engine fixes through the bound Nf * Nf it passes to GraphPlan."""
+        torch.add(self.ii * self.Nf, self.jj, out=self.pair_key)
 
     def ingest_frame(self, idx, fmap, gmap_patches=None, imap_patches=None, overlap=False, only_levels=None):
         """fmap [C,H,W] planar features of frame `idx` -> all pixel-major pyramid levels;

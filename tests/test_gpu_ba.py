@@ -166,6 +166,23 @@ def test_neighbors_bit_exact(E, nk, nj):
     assert torch.equal(ix.cpu(), rx) and torch.equal(jx.cpu(), ry)
 
 
+def test_graph_plan_key_bounds_are_only_a_hint():
+    """GraphPlan(ka, kb, max_ka, max_kb): correct bounds fix the radix width on the host; WRONG (too small) bounds must not
+    change the result -- the kernel notices and measures the keys itself"""
+    from devo_b200 import cuda_ba
+    g = torch.Generator().manual_seed(0)
+    ka = torch.randint(0, 700, (5000,), generator=g).cuda()
+    kb = torch.randint(0, 9, (5000,), generator=g).cuda()
+    ref = cuda_ba.GraphPlan(ka, kb, -1, -1)
+    for bounds in ((700, 9), (1024, 16), (8, 2), (1, 1)):
+        p = cuda_ba.GraphPlan(ka, kb, *bounds)
+        assert int(p.ngroups) == int(ref.ngroups)
+        n = int(ref.ngroups)
+        assert torch.equal(p.perm, ref.perm) and torch.equal(p.gid, ref.gid)
+        assert torch.equal(p.gstart[:n + 1], ref.gstart[:n + 1]) and torch.equal(p.gkey[:n], ref.gkey[:n])
+        assert torch.equal(p.ix, ref.ix) and torch.equal(p.jx, ref.jx)
+
+
 def test_graph_plan_equals_torch_unique():
     from devo_b200 import cuda_ba
     for E, nk in [(50, 7), (6144, 768), (20000, 1500)]:

@@ -80,3 +80,29 @@ def test_overlapped_ingest_equals_serial_ingest():
         res.append((op.poses.clone(), op.patches.clone(), op.get_net().clone(), op.levels_pm[0].clone()))
     for a, b in zip(*res):
         assert torch.equal(a, b)
+
+
+def test_state_arena_refresh_path_equals_set_graph_path():
+    """bench.py's end-to-end step refreshes the operator's whole state arena (poses, patches, intrinsics, edge list) from an
+    uploaded buffer and must then re-derive what set_graph derives (`refresh_pair_key`): same iteration, bit for bit, as
+    installing the same state through set_graph.  (A frame-pair key computed any other way than the engine's breaks the
+    radix width the engine promises to the plan.)"""
+    op, up, P, C, imap = _build()
+    net0 = op.get_net().clone()
+    arena0 = op.state_arena.clone()
+    op.snapshot_geometry()
+    with torch.no_grad():
+        op.step(reset_geometry=True)
+    a_poses, a_patches, a_net = op.poses.clone(), op.patches.clone(), op.get_net().clone()
+    # ---- the same state delivered as one buffer; the edge list arrives with it
+    op.set_net(net0)
+    op.ii.zero_(); op.jj.zero_(); op.kk.zero_(); op.pair_key.zero_()
+    with torch.no_grad():
+        op.state_arena.copy_(arena0)
+        op.refresh_pair_key()
+        op._iteration(reset_geometry=False)
+    torch.cuda.synchronize()
+    assert int(op.status.item()) == 0
+    assert torch.equal(op.poses, a_poses) and torch.equal(op.patches, a_patches) and torch.equal(op.get_net(), a_net)
+    nf = op.Nf
+    assert int(op.plan_ij.ngroups.item()) == torch.unique(op.ii * nf + op.jj).numel()
