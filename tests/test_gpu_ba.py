@@ -31,7 +31,8 @@ def _oracle_ba(P, t0, t1, iters):
                    torch.tensor([1e-4]).float().double(), P["ii"], P["jj"], P["kk"], t0, t1, iters)
 
 
-@pytest.mark.parametrize("nf,m,t0,iters", [(2, 32, 1, 2), (4, 24, 1, 2), (8, 96, 1, 2), (8, 96, 1, 10), (6, 16, 3, 3)])
+@pytest.mark.parametrize("nf,m,t0,iters", [(2, 32, 1, 2), (4, 24, 1, 2), (8, 96, 1, 2), (8, 96, 1, 10), (6, 16, 3, 3),
+                                            (13, 10, 1, 2), (21, 6, 1, 2), (26, 5, 1, 2)])   # 12 / 20 / 25 free poses: every entries-per-thread variant
 def test_ba_vs_oracle(nf, m, t0, iters):
     P = ba_problem(n_frames=nf, patches_per_frame=m, seed=1234 + nf, init="perturbed", noise=0.3)
     poses, patches = _run_ba(P, t0, nf, iters)
