@@ -155,6 +155,42 @@ def test_ba_masked_edges_and_failure_status():
     assert torch.isfinite(poses[0, :2]).all()
 
 
+def test_ba_prepared_form_equals_planned_form_and_folds_the_status():
+    """devo_ba_prepare + devo_ba_forward_prepared (the memsets of a call issued ahead, the status OR-ed into a sticky word
+    by the last launch): same poses / depths bit for bit as devo_ba_forward_planned; a failed call leaves its status in the
+    sticky word, a good one leaves it alone; the workspace can be reused call after call."""
+    from devo_b200 import _lib, cuda_ba
+    P = ba_problem(n_frames=5, patches_per_frame=16, seed=19, init="perturbed", noise=0.3)
+    ii, jj, kk = P["ii"].cuda(), P["jj"].cuda(), P["kk"].cuda()
+    plan = cuda_ba.GraphPlan(kk, jj, 5 * 16, 5)
+    args = (P["intrinsics"].float().cuda(), P["targets"].float().cuda(), P["weights"].float().cuda(), torch.tensor([1e-4], device="cuda"),
+            ii, jj, kk, 1, 5, 2)
+    p0, x0 = P["poses0"].float().cuda(), P["patches0"].float().cuda()
+    st0 = cuda_ba.forward_async(p0, x0, *args, plan=plan)
+    ws = torch.empty(_lib.lib().devo_ba_workspace(ii.numel(), 4), dtype=torch.uint8, device="cuda").fill_(0xAB)     # garbage on purpose
+    status = torch.full((1,), 77, dtype=torch.int32, device="cuda")
+    sticky = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for rep in range(3):
+        p1, x1 = P["poses0"].float().cuda(), P["patches0"].float().cuda()
+        cuda_ba.prepare(ii.numel(), 4, status, ws)
+        cuda_ba.forward_async(p1, x1, *args, status=status, plan=plan, workspace=ws, prepared=True, status_or=sticky)
+        assert int(status.item()) == 0 == int(st0.item()) and int(sticky.item()) == 0
+        assert torch.equal(p1, p0) and torch.equal(x1, x0)
+    badw = P["weights"].float().clone()
+    badw[0, 3, 0] = float("nan")
+    bargs = (args[0], args[1], badw.cuda()) + args[3:]
+    p2, x2 = P["poses0"].float().cuda(), P["patches0"].float().cuda()
+    cuda_ba.prepare(ii.numel(), 4, status, ws)
+    cuda_ba.forward_async(p2, x2, *bargs, status=status, plan=plan, workspace=ws, prepared=True, status_or=sticky)
+    assert int(status.item()) == 1 and int(sticky.item()) == 1
+    assert torch.equal(p2.cpu(), P["poses0"].float()) and torch.equal(x2.cpu(), P["patches0"].float())
+    # ... and the next good call on the same workspace works again, the sticky word keeps the failure
+    p3, x3 = P["poses0"].float().cuda(), P["patches0"].float().cuda()
+    cuda_ba.prepare(ii.numel(), 4, status, ws)
+    cuda_ba.forward_async(p3, x3, *args, status=status, plan=plan, workspace=ws, prepared=True, status_or=sticky)
+    assert int(status.item()) == 0 and int(sticky.item()) == 1 and torch.equal(p3, p0) and torch.equal(x3, x0)
+
+
 @pytest.mark.parametrize("E,nk,nj", [(1, 1, 1), (7, 2, 3), (300, 20, 6), (5000, 300, 8), (12000, 500, 12), (40000, 2000, 22)])
 def test_neighbors_bit_exact(E, nk, nj):
     from devo_b200 import fastba
