@@ -177,7 +177,7 @@ def per_op_times(op, wl, dev, stream, flush):
             scratch = GruState(op.E, dev).set(op.get_net())
             out["update_operator"] = time_us(graphed(lambda: op.update.forward_mma(
                 None, op.imap, op.kk, op.corr_buf, op.plan_kk, op.plan_ij, op.Np, op.Nf * op.Nf, op.packed, workspace=op._gru_ws,
-                state=scratch, coords=coords)), stream, flush)
+                state=scratch, coords=coords, tile_local=op.tile_local)), stream, flush)
         target = (coords[:, :, :, 1, 1] + op.delta.float()).contiguous()
         weight = op.weight.float().contiguous()
         p0, x0 = op.pristine_geometry()
@@ -627,7 +627,7 @@ def run_ours(args, rank, world, local_rank):
             scratch = GruState(op.E, dev).set(op.get_net())
             with torch.cuda.graph(gg):
                 op.update.forward_mma(None, op.imap, op.kk, op.corr_buf, op.plan_kk, op.plan_ij, op.Np, op.Nf * op.Nf,
-                                      op.packed, workspace=op._gru_ws, state=scratch)
+                                      op.packed, workspace=op._gru_ws, state=scratch, tile_local=op.tile_local)
             gt = []
             for _ in range(30):
                 flush.zero_()
@@ -646,13 +646,14 @@ def run_ours(args, rank, world, local_rank):
         except Exception:
             tpeak, tsrc = 1368.0, "fallback (B200_PROFILING.md)"
         in_ms = in_step["update_operator"] * 1e-3 if (in_step and "update_operator" in in_step) else None
-        roofline_gru = dict(bound="tensor", kernel="gru_mma_kernel x5 + segment_softmax_sum x2 (devo_gru_update)",
+        roofline_gru = dict(bound="tensor", kernel="gru_mma_kernel x%d + segment_softmax_sum x2 (devo_gru_update)" % (3 if op.tile_local else 5),
                             achieved=round(fl / (g_ms * 1e-3) / 1e12, 2), peak=tpeak, unit="TFLOP/s",
                             frac=round(fl / (g_ms * 1e-3) / 1e12 / tpeak, 4), traffic=ncu_traffic_bytes("gru"), flops=fl,
                             kernel_ms=round(g_ms, 5), kernel_ms_in_step_upper_bound=(round(in_ms, 5) if in_ms else None),
                             peak_source=tsrc,
                             note="the update operator is the largest share of a step; a chain of 19 dependent Linear layers "
-                                 "([6144,384]x[384,384], one with K=896) on 48 CTA pairs (cta_group::2 MMAs): per layer MMA -> epilogue "
+                                 "([6144,384]x[384,384], one with K=896) on 48 CTA pairs (cta_group::2 MMAs; the S8 edge list is patch-major, so the "
+                                 "first three programs run as one launch with in-tile neighbour exchange): per layer MMA -> epilogue "
                                  "-> next layer's MMA (DESIGN.md 2.6); timed alone as one graph replay, L2 flushed before each replay "
                                  "(kernel_ms_in_step_upper_bound: between event-record nodes inside the step, which break the "
                                  "programmatic launch chain)")
@@ -738,7 +739,7 @@ def run_e2e(op, wl, dev, steps):
 
     def body(b):
         op.state_arena.copy_(stage[b][state_off:], non_blocking=True)      # the state the caller uploaded this step
-        op.refresh_pair_key()
+        op.refresh_pair_key(same_graph=True)          # the arena carries the edge list set_graph installed, unchanged
         op.ingest_frame(f, view(stage[b], "fmap"), view(stage[b], "gmap"), view(stage[b], "imap"), overlap=True)
         op._iteration(reset_geometry=False)
         out_dev[:Nf * 7].copy_(op.poses.view(-1))

@@ -90,7 +90,7 @@ class GruIoStruct(ctypes.Structure):
                 ("ix", _vp), ("jx", _vp),
                 ("perm_kk", _vp), ("gstart_kk", _vp), ("ngroups_kk", _vp), ("gid_kk", _vp), ("max_groups_kk", _i),
                 ("perm_ij", _vp), ("gstart_ij", _vp), ("ngroups_ij", _vp), ("gid_ij", _vp), ("max_groups_ij", _i),
-                ("net16_out", _vp), ("delta", _vp), ("weight", _vp), ("coords", _vp), ("target32", _vp), ("weight32", _vp)]
+                ("net16_out", _vp), ("delta", _vp), ("weight", _vp), ("coords", _vp), ("target32", _vp), ("weight32", _vp), ("tile_local", _i)]
 
 
 _lib = None

@@ -73,7 +73,7 @@ constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kFirstEpiWarp = 2;           // warp 0: TMA producer, warp 1: MMA issuer of N-tile 0 (leader CTA) + TMEM allocation
 constexpr int kMma1Warp = kFirstEpiWarp + kEpiWarps;      // the last warp: MMA issuer of N-tile 1 (leader CTA)
 constexpr int kThreads = 32 * (kMma1Warp + 1);
-constexpr int kMaxLayers = 7;
+constexpr int kMaxLayers = 9;
 constexpr int kChunks = kD / 8;            // 16-byte chunks per row (48)
 constexpr int kCol4 = kD / 4;              // float4 groups per row (96)
 constexpr int kCPT = kNTc / kParts / 8;    // 16-byte chunks per thread per N-tile (3)
@@ -84,8 +84,8 @@ static_assert(kCPT * 8 * kParts == kNTc, "column split");
 constexpr int kOffW = 2 * kABuf;                               // weight ring
 constexpr int kOffBars = kOffW + kWStages * kWStage;           // 56 mbarrier slots
 constexpr int kOffTmem = kOffBars + 56 * 8;                    // TMEM base address (+ pad)
-constexpr int kOffIdx = kOffTmem + 16;                         // [64] gather sources of the tile
-constexpr int kOffStat = kOffIdx + kRows * 4;                  // [kSlots][64][4] row-reduction partials
+constexpr int kOffIdx = kOffTmem + 16;                         // [64] gather sources of the tile; merged program: [2][64] scatter rows
+constexpr int kOffStat = kOffIdx + 2 * kRows * 4;              // [kSlots][64][4] row-reduction partials
 constexpr int kOffLn = kOffStat + kSlots * kRows * 4 * 4;      // [2][2][384] f32: gamma, beta of the program's LayerNorms
 constexpr int kOffBias = kOffLn + 4 * kD * 4;                  // [kMaxLayers][384] biases as f32
 constexpr int kOffHead = kOffBias + kMaxLayers * kD * 4;       // [4][384] + [4] (+4 pad) head weights
@@ -98,9 +98,15 @@ static_assert(kBarProReady < 56, "barrier slots");
 
 enum { PRO_NONE = 0, PRO_GATHER = 1, PRO_CAST = 2 };
 enum { EPI_RELU_A = 0, EPI_LNRELU_A = 1, EPI_ADD3_LN = 2, EPI_RESID = 3, EPI_STORE_A = 4, EPI_STORE_B = 5,
-       EPI_GATE = 6, EPI_GATED_LN = 7, EPI_GATED_HEADS = 8, EPI_RESID_A = 9, EPI_RESID_LN_A = 10 };
+       EPI_GATE = 6, EPI_GATED_LN = 7, EPI_GATED_HEADS = 8, EPI_RESID_A = 9, EPI_RESID_LN_A = 10,
+       // the "tile-local" program (neighbour links of every edge stay inside the edge's 64-row tile): like ADD3_LN / RESID,
+       // but the half result becomes the next A operand with its rows PERMUTED through the neighbour links -- row r is
+       // written where the next layer's gather net[ix] / net[jx] would have fetched it from, rows without a neighbour
+       // are zero -- so the exchange that used to need a kernel boundary is a scatter inside the CTA's own A tile
+       EPI_ADD3_LN_SC = 11, EPI_RESID_SC = 12 };
 __host__ __device__ constexpr bool epi_writes_a(int e) {
-  return e == EPI_RELU_A || e == EPI_LNRELU_A || e == EPI_GATED_LN || e == EPI_RESID_A || e == EPI_RESID_LN_A;
+  return e == EPI_RELU_A || e == EPI_LNRELU_A || e == EPI_GATED_LN || e == EPI_RESID_A || e == EPI_RESID_LN_A ||
+         e == EPI_ADD3_LN_SC || e == EPI_RESID_SC;
 }
 
 template <typename T>
@@ -118,6 +124,8 @@ struct GruProg {
   const T* x16_in;                         // row-major [src_rows,384]: gather source / half hidden state in (ADD3)
   const int64_t* idx64;                    // PRO_GATHER: source row per row (-1 => zero row); null => identity
   const int32_t* idx32;                    // PRO_GATHER: ... or a 32-bit index (the group of each row) when idx64 is null
+  const int64_t* sc_ix;                    // tile-local program: previous / next edge of the same patch (graph plan), both in
+  const int64_t* sc_jx;                    //   the edge's own 64-row tile or -1
   const T* inp16;                          // ADD3: imap [n_patches,384]
   const int64_t* kk;                       // ADD3: patch of each row
   float* net32;                            // tile layout: the fp32 hidden state / running `net`
@@ -323,6 +331,22 @@ struct Epi {
   __device__ __forceinline__ const float* s_bias() const { return reinterpret_cast<const float*>(As + kOffBias); }
   __device__ __forceinline__ const T* s_head() const { return reinterpret_cast<const T*>(As + kOffHead); }
   __device__ __forceinline__ int* s_idx() const { return reinterpret_cast<int*>(As + kOffIdx); }
+  // tile-local program: s_sc(0)[r] = where the ADD3_LN_SC epilogue writes row r (as the c1 gather net[ix] would read it:
+  // row jx[r]), s_sc(1)[r] = the same for RESID_SC / the c2 gather net[jx] (row ix[r]).  Low 16 bits: tile row + 1
+  // (0: nobody reads this row); bit 16: row r itself has no source and must be zero in that operand.
+  __device__ __forceinline__ int* s_sc(int k) const { return reinterpret_cast<int*>(As + kOffIdx) + k * kRows; }
+  __device__ __forceinline__ void scatter_index() {
+    if (et < kRows) {
+      const int gr = row0 + et;
+      long long ixv = -1, jxv = -1;
+      if (gr < P.rows) { ixv = P.sc_ix[gr]; jxv = P.sc_jx[gr]; }
+      const int dj = jxv >= 0 ? (int)(jxv - row0) : -1, di = ixv >= 0 ? (int)(ixv - row0) : -1;
+      if ((jxv >= 0 && (dj < 0 || dj >= kRows)) || (ixv >= 0 && (di < 0 || di >= kRows))) __trap();   // the caller's promise is broken
+      s_sc(0)[et] = (dj + 1) | ((ixv < 0) ? (1 << 16) : 0);
+      s_sc(1)[et] = (di + 1) | ((jxv < 0) ? (1 << 16) : 0);
+    }
+    epi_bar_all();
+  }
   __device__ __forceinline__ uint64_t* acc_full() const { return reinterpret_cast<uint64_t*>(As + kOffBars) + kBarAccFull; }
   __device__ __forceinline__ unsigned char* next_a() const { return As + (cur ^ 1) * kABuf; }
 
@@ -445,10 +469,19 @@ struct Epi {
   template <int EPI>
   __device__ __forceinline__ void layer(int l) {
     constexpr bool kGated = (EPI == EPI_GATED_LN || EPI == EPI_GATED_HEADS);
-    constexpr bool kResid = (EPI == EPI_RESID || EPI == EPI_RESID_A || EPI == EPI_RESID_LN_A);
-    constexpr bool kTwoPass = (EPI == EPI_LNRELU_A || EPI == EPI_ADD3_LN || EPI == EPI_GATED_LN || EPI == EPI_RESID_LN_A);
+    constexpr bool kAdd3 = (EPI == EPI_ADD3_LN || EPI == EPI_ADD3_LN_SC);
+    constexpr bool kScatter = (EPI == EPI_ADD3_LN_SC || EPI == EPI_RESID_SC);
+    constexpr bool kResid = (EPI == EPI_RESID || EPI == EPI_RESID_SC || EPI == EPI_RESID_A || EPI == EPI_RESID_LN_A);
+    constexpr bool kTwoPass = (EPI == EPI_LNRELU_A || kAdd3 || EPI == EPI_GATED_LN || EPI == EPI_RESID_LN_A);
     constexpr bool kWritesA = epi_writes_a(EPI);
-    constexpr int kAux = (kResid || EPI == EPI_ADD3_LN) ? 2 : (kGated ? 3 : 1);
+    constexpr int kAux = (kResid || kAdd3) ? 2 : (kGated ? 3 : 1);
+    int drow = -1;                       // kScatter: tile row of the next A operand this thread's row goes to
+    bool zrow = false;                   // kScatter: this thread's own row of the next A operand is zero
+    if constexpr (kScatter) {
+      const int sc = s_sc(EPI == EPI_ADD3_LN_SC ? 0 : 1)[r];
+      drow = (sc & 0xffff) - 1;
+      zrow = (sc >> 16) != 0;
+    }
     constexpr int kIter = 2 * kCPT;
     const float* bias = s_bias() + l * kD;
     const int set = l & 1;
@@ -457,7 +490,7 @@ struct Epi {
     float hacc[4] = {0.f, 0.f, 0.f, 0.f};
     const T* netrow = nullptr;
     const T* inprow = nullptr;
-    if (EPI == EPI_ADD3_LN && live) {
+    if (kAdd3 && live) {
       netrow = P.x16_in + (size_t)grow * kD;
       inprow = P.inp16 + (size_t)P.kk[grow] * kD;
     }
@@ -477,7 +510,7 @@ struct Epi {
         q[0] = *f4(n32_r, 2 * c);
         q[1] = *f4(n32_r, 2 * c + 1);
         q[2] = *reinterpret_cast<const uint4*>(gate_r + (size_t)c * (kRows * 8));
-      } else if constexpr (EPI == EPI_ADD3_LN) {
+      } else if constexpr (kAdd3) {
         q[0] = make_uint4(0u, 0u, 0u, 0u);
         q[1] = q[0];
         if (P.state_half) { if (live) q[0] = *reinterpret_cast<const uint4*>(netrow + c * 8); }
@@ -495,7 +528,7 @@ struct Epi {
       for (int j = 0; j < kCPT; j++) {
         const int c = chunk_of(h, j);
         if constexpr (kAux > 1) load_aux(c, aux[j]);
-        if constexpr (EPI == EPI_ADD3_LN) {
+        if constexpr (kAdd3) {
           inp[j] = make_uint4(0u, 0u, 0u, 0u);
           if (live) inp[j] = __ldg(reinterpret_cast<const uint4*>(inprow + c * 8));
         }
@@ -532,7 +565,7 @@ struct Epi {
 #pragma unroll
           for (int k = 0; k < 8; k++) { s1 += o[k]; s2 += o[k] * o[k]; }
           *reinterpret_cast<uint4*>(An + a_off(r, c)) = oh;             // parked (half) until normalised
-        } else if constexpr (EPI == EPI_ADD3_LN) {
+        } else if constexpr (kAdd3) {
           float x[8], b[8];
           unpack8<T>(oh, o);
           unpack8<T>(inp[j], b);
@@ -554,13 +587,17 @@ struct Epi {
 #pragma unroll
           for (int k = 0; k < 8; k++) { s1 += x[k]; s2 += x[k] * x[k]; xs[k] = __float_as_uint(x[k]); }
           tmem_st8(tcol + h * kNTc + j * 8, xs);      // fp32 row parked in its own accumulator columns
-        } else if constexpr (EPI == EPI_RESID) {
+        } else if constexpr (EPI == EPI_RESID || EPI == EPI_RESID_SC) {
           unpack8<T>(oh, o);
           float4 a = as_f4(cur_[0]), b = as_f4(cur_[1]);
           a.x += o[0]; a.y += o[1]; a.z += o[2]; a.w += o[3]; b.x += o[4]; b.y += o[5]; b.z += o[6]; b.w += o[7];
           *f4w(net_r, 2 * c) = a;
           *f4w(net_r, 2 * c + 1) = b;
-          if (out_img) {
+          if constexpr (EPI == EPI_RESID_SC) {
+            const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            if (drow >= 0) *reinterpret_cast<uint4*>(An + a_off(drow, c)) = pack8<T>(v);
+            if (zrow) *reinterpret_cast<uint4*>(An + a_off(r, c)) = make_uint4(0u, 0u, 0u, 0u);
+          } else if (out_img) {
             const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
             *reinterpret_cast<uint4*>(An + a_off(r, c)) = pack8<T>(v);
           }
@@ -635,13 +672,13 @@ struct Epi {
       }
       if (kWritesA && l + 1 < P.n_layers) signal_a(1);
       ln_used++;
-    } else if constexpr (EPI == EPI_ADD3_LN || EPI == EPI_GATED_LN || EPI == EPI_RESID_LN_A) {
+    } else if constexpr (kAdd3 || EPI == EPI_GATED_LN || EPI == EPI_RESID_LN_A) {
       tmem_wait_st();
       float mean, rstd;
       ln_stats(s1, s2, mean, rstd);
       const float* gm = s_ln() + ln_used * 2 * kD;
       const float* bt = gm + kD;
-      float* dst = (EPI == EPI_ADD3_LN) ? net_r : n32_r;
+      float* dst = kAdd3 ? net_r : n32_r;
 #pragma unroll 1
       for (int h = 0; h < 2; h++) {
         uint32_t raw3[kCPT][8];
@@ -659,7 +696,12 @@ struct Epi {
         for (int k = 0; k < 8; k++) v[k] = (__uint_as_float(raw[k]) - mean) * rstd * gk[k] + bk[k];
         *f4w(dst, 2 * c) = make_float4(v[0], v[1], v[2], v[3]);
         *f4w(dst, 2 * c + 1) = make_float4(v[4], v[5], v[6], v[7]);
-        if (EPI != EPI_ADD3_LN || out_img) *reinterpret_cast<uint4*>(An + a_off(r, c)) = pack8<T>(v);
+        if constexpr (EPI == EPI_ADD3_LN_SC) {
+          if (drow >= 0) *reinterpret_cast<uint4*>(An + a_off(drow, c)) = pack8<T>(v);
+          if (zrow) *reinterpret_cast<uint4*>(An + a_off(r, c)) = make_uint4(0u, 0u, 0u, 0u);
+        } else if (EPI != EPI_ADD3_LN || out_img) {
+          *reinterpret_cast<uint4*>(An + a_off(r, c)) = pack8<T>(v);
+        }
         }
         if (kWritesA && l + 1 < P.n_layers) signal_a(h);      // (as above: N-tile h of the next A operand is complete)
       }
@@ -885,6 +927,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
     e.gate_r = P.gate16 + t16((int)blockIdx.x, 0, e.r);
     if (lane == 0 && P.out_a) prefetch_tensormap(&tm_oa);
     if (P.pro == PRO_GATHER) e.prologue_index();
+    if (P.sc_ix != nullptr) e.scatter_index();      // (graph-plan data: read ahead of the wait, like the gather indices)
     pdl_wait();                                     // first use of the previous kernels' results (and first global writes)
     switch (P.pro) {                                // warp-uniform
       case PRO_GATHER: e.template prologue<PRO_GATHER>(); break;
@@ -904,6 +947,8 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
         case EPI_GATED_LN: e.template layer<EPI_GATED_LN>(l); break;
         case EPI_RESID_A: e.template layer<EPI_RESID_A>(l); break;
         case EPI_RESID_LN_A: e.template layer<EPI_RESID_LN_A>(l); break;
+        case EPI_ADD3_LN_SC: e.template layer<EPI_ADD3_LN_SC>(l); break;
+        case EPI_RESID_SC: e.template layer<EPI_RESID_SC>(l); break;
         default: e.template layer<EPI_GATED_HEADS>(l); break;
       }
     }
@@ -1066,6 +1111,32 @@ static int gru_update_impl(const devo_gru_weights_t* Wt, const devo_gru_io_t* io
   base.kblocks0 = kKB;
   base.net32 = net32; base.n32 = n32; base.gate16 = gate16;
 
+  if (io->tile_local) {
+    // (1-3) as ONE program: corr MLP + norm | c1 | c2 | g, f of the patch-wise aggregation.  Every neighbour link stays
+    // inside the CTA's 64 rows (the caller's promise), so `mask * net[ix]` / `mask * net[jx]` are row permutations of the
+    // tile the CTA has just produced: the ADD3_LN / RESID epilogues write their half rows straight to where the next
+    // layer's A operand wants them.  Two kernel boundaries (~5 us each: bulk-store completion, skew, dependent gather)
+    // and the two [E,384] images that carried the rows across them are gone.
+    GruProg<T> P = base;
+    P.n_layers = 9; P.pro = PRO_NONE; P.kblocks0 = io->corr_ld / 64; P.stream_a0 = 1; P.use_w0 = 1;
+    P.w_row[0] = 0;      P.epi[0] = EPI_RELU_A;     P.bias[0] = bias;
+    P.w_row[1] = 0 * kD; P.epi[1] = EPI_LNRELU_A;   P.bias[1] = B(0);
+    P.w_row[2] = 1 * kD; P.epi[2] = EPI_ADD3_LN_SC; P.bias[2] = B(1);
+    P.w_row[3] = 2 * kD; P.epi[3] = EPI_RELU_A;     P.bias[3] = B(2);
+    P.w_row[4] = 3 * kD; P.epi[4] = EPI_RESID_SC;   P.bias[4] = B(3);
+    P.w_row[5] = 4 * kD; P.epi[5] = EPI_RELU_A;     P.bias[5] = B(4);
+    P.w_row[6] = 5 * kD; P.epi[6] = EPI_RESID_A;    P.bias[6] = B(5);
+    P.w_row[7] = 6 * kD; P.epi[7] = EPI_STORE_A;    P.bias[7] = B(6);
+    P.w_row[8] = 7 * kD; P.epi[8] = EPI_STORE_B;    P.bias[8] = B(7);
+    P.ln_g[0] = Wt->ln_gamma; P.ln_b[0] = Wt->ln_beta;
+    P.ln_g[1] = Wt->ln_gamma + kD; P.ln_b[1] = Wt->ln_beta + kD;
+    P.state_half = io->net16 != nullptr;
+    P.x16_in = (const T*)io->net16; P.inp16 = (const T*)io->imap16; P.kk = io->kk;
+    P.sc_ix = io->ix; P.sc_jx = io->jx;
+    P.out_a = 1; P.out_b = 1;
+    rc = launch_prog<T>(tw, tw0, ta, t_g16, t_f16, P, s);
+    if (rc != DEVO_OK) return rc;
+  } else {
   // (1) corr MLP + norm(net + inp + corr)  (enet.py:59-66,82-83)
   {
     GruProg<T> P = base;
@@ -1108,6 +1179,7 @@ static int gru_update_impl(const devo_gru_weights_t* Wt, const devo_gru_io_t* io
     rc = launch_prog<T>(tw, tw0, ta, t_g16, t_f16, P, s);
     if (rc != DEVO_OK) return rc;
   }
+  }   // !tile_local
   rc = devo::segment_softmax_sum(g16, f16, io->perm_kk, io->gstart_kk, io->ngroups_kk, io->max_groups_kk, y16, dtype, E, kD, (void*)s, 1);
   if (rc != DEVO_OK) return rc;
   {

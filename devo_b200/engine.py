@@ -89,6 +89,7 @@ class UpdateOperator:
         self._ba_ws = torch.empty(_lib.lib().devo_ba_workspace(self.E, max(self.t1 - self.t0, 0)), dtype=torch.uint8, device=dev)
         self._graph = None
         self._pristine = None
+        self.tile_local = False
         self.delta = None
         self.weight = None
         self.coords = None
@@ -103,13 +104,24 @@ class UpdateOperator:
         if self.plan_kk is None:
             self.plan_kk = cuda_ba.GraphPlan(self.kk, self.jj, self.Np, self.Nf)
             self.plan_ij = cuda_ba.GraphPlan(self.pair_key, self.zeros_e, self.Nf * self.Nf, 1, want_neighbors=False)
+        else:
+            self.plan_kk.update()
+        # does every neighbour link stay inside its 64-edge tile (a patch-major list, e.g. the all-pairs graph of
+        # enet.py:300-301)?  Then the update operator runs its first three programs as one launch.  Checked HERE, once per
+        # installed edge list (one host synchronisation), never per update.
+        from .update import tile_local_graph
+        self.tile_local = self.gru_mode == "mma" and tile_local_graph(self.plan_kk)
 
-    def refresh_pair_key(self):
+    def refresh_pair_key(self, same_graph=False):
         """(re)compute the frame-pair key of SoftAgg's second grouping from ii / jj -- after set_graph, or after the caller
-        refreshed `state_arena` with a new edge list.  The reference uses ii * 12345 + jj (enet.py:96); any key that orders
-        the pairs the same way gives the same groups, and ii * Nf + jj needs 6 bits instead of 17: half the radix passes of
-        the plan, whose width the engine fixes through the bound Nf * Nf it passes to GraphPlan."""
+        refreshed `state_arena` (which carries the edge list).  `same_graph`: the caller vouches that the refreshed edge
+        list is the one set_graph installed; otherwise what set_graph verified about it (`tile_local`) is dropped.
+        The reference uses ii * 12345 + jj (enet.py:96); any key that orders the pairs the same way gives the same groups,
+        and ii * Nf + jj needs 6 bits instead of 17: half the radix passes of the plan, whose width the engine fixes
+        through the bound Nf * Nf it passes to GraphPlan."""
         torch.add(self.ii * self.Nf, self.jj, out=self.pair_key)
+        if not same_graph:
+            self.tile_local = False
 
     def ingest_frame(self, idx, fmap, gmap_patches=None, imap_patches=None, overlap=False, only_levels=None):
         """fmap [C,H,W] planar features of frame `idx` -> all pixel-major pyramid levels;
@@ -211,7 +223,7 @@ class UpdateOperator:
         if self.gru_mode == "mma":      # target / weight for BA come out of the heads epilogue of the same launch
             _, (delta, weight16, (target, weight)) = self.update.forward_mma(
                 None, self.imap, self.kk, self.corr_buf, self.plan_kk, self.plan_ij, self.Np, self.Nf * self.Nf,
-                self.packed, workspace=self._gru_ws, coords=coords, state=self.state)
+                self.packed, workspace=self._gru_ws, coords=coords, state=self.state, tile_local=self.tile_local)
         elif self.fused_gru:
             ctx = self.imap[:, self.kk]
             net, (delta, weight, _) = self.update.forward_fused(

@@ -137,6 +137,16 @@ class PackedUpdateWeights:
         return self
 
 
+def tile_local_graph(plan_kk, tile=64):
+    """True when every neighbour link of the plan (previous / next edge of the same patch) stays inside the edge's own
+    `tile` consecutive edges -- e.g. the patch-major all-pairs graph of enet.py:300-301 when the edges per patch divide
+    the tile.  Synchronises with the host (one .item()): call it when the edge list is installed, not per update."""
+    E = plan_kk.ix.numel()
+    t = torch.arange(E, device=plan_kk.ix.device) // tile
+    ok = ((plan_kk.ix < 0) | (plan_kk.ix // tile == t)) & ((plan_kk.jx < 0) | (plan_kk.jx // tile == t))
+    return bool(ok.all().item())
+
+
 class GruState:
     """The recurrent hidden state of the fused update operator: float32, in the tile layout devo_gru_update reads and
     writes in place ([tiles of 64 rows][96 float4 groups][64][4], include/devo_b200.h).  `set` / `get` convert from / to the
@@ -269,8 +279,10 @@ class Update(nn.Module):
         return net, (run(self.d, net), run(self.w, net), None)
 
     def forward_mma(self, net, imap16, kk, corr16, plan_kk, plan_ij, max_patches, max_pairs, packed, net_out=None,
-                    workspace=None, coords=None, state=None):
+                    workspace=None, coords=None, state=None, tile_local=False):
         """The whole forward as fused tcgen05 kernels (csrc/gru_mma.cu, devo_gru_update).
+        tile_local: the caller's promise that every neighbour link (plan_kk.ix / jx) stays inside the edge's own 64-edge
+             tile (see `tile_local_graph`): corr MLP + norm, c1 and c2 + the kk-aggregation layers then run as ONE launch.
         net: the hidden state [1,E,384] -- float32 (every update but the first: enet.py GatedResidual returns float32 under
              autocast) or the autocast dtype (the half zero-state of the first update; follows the half dtype flow) --
              or None when `state` (a GruState, the engine's persistent tile-layout float32 buffer) already holds it.
@@ -315,7 +327,7 @@ class Update(nn.Module):
                               plan_kk.ix.data_ptr(), plan_kk.jx.data_ptr(),
                               plan_kk.perm.data_ptr(), plan_kk.gstart.data_ptr(), plan_kk.ngroups.data_ptr(), plan_kk.gid.data_ptr(), int(max_patches),
                               plan_ij.perm.data_ptr(), plan_ij.gstart.data_ptr(), plan_ij.ngroups.data_ptr(), plan_ij.gid.data_ptr(), int(max_pairs),
-                              0 if net_out is None else net_out.data_ptr(), delta.data_ptr(), weight.data_ptr(), 0, 0, 0)
+                              0 if net_out is None else net_out.data_ptr(), delta.data_ptr(), weight.data_ptr(), 0, 0, 0, int(bool(tile_local)))
         if net_out is not None:
             _lib.require_dtype(net_out, dt, "forward_mma net_out")
             _lib.require_contiguous(net_out=net_out)

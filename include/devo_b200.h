@@ -312,6 +312,11 @@ typedef struct {
   const float* coords;    /* [E, 2, 3, 3] reprojected patch coordinates, or NULL */
   float* target32;        /* [E, 2] or NULL */
   float* weight32;        /* [E, 2] or NULL */
+  int tile_local;         /* 1: the caller promises that ix[e] and jx[e] are -1 or lie in e's own 64-edge tile (e / 64) for every
+                             edge -- true for a patch-major edge list whose patches do not straddle a multiple of 64, e.g. the
+                             all-pairs graph of enet.py:300-301 with 8 frames.  The neighbour gathers of c1 / c2 then happen
+                             inside the CTA's shared memory and the first three programs run as one launch (the kernel
+                             traps if the promise is broken).  0: always correct. */
 } devo_gru_io_t;
 size_t devo_gru_workspace(int E, int max_groups);
 size_t devo_gru_state_floats(int E);

@@ -107,3 +107,41 @@ def test_gru_mma_is_deterministic():
     torch.cuda.synchronize()
     for o in outs[1:]:
         assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]) and torch.equal(o[2], outs[0][2])
+
+
+@pytest.mark.parametrize("nf,m,state_dtype", [(8, 96, torch.float32), (8, 96, torch.float16), (4, 40, torch.float32), (16, 12, torch.float32)])
+def test_gru_mma_tile_local_program_is_bit_identical(nf, m, state_dtype):
+    """devo_gru_io_t.tile_local: when every neighbour link stays inside its 64-edge tile (the patch-major all-pairs graph
+    with 8, 4 or 16 edges per patch) the first three programs run as one launch whose epilogues permute the rows inside
+    the CTA's own A tile instead of gathering them across a kernel boundary.  Same arithmetic, different data movement:
+    every output must match the three-launch form bit for bit."""
+    from devo_b200.update import GruState, PackedUpdateWeights, tile_local_graph
+    up, net, imap, corr, ii, jj, kk, plan_kk, plan_ij, Np, pairs = _problem(nf, m, 0)
+    assert tile_local_graph(plan_kk)
+    packed = PackedUpdateWeights(up, torch.float16, 896)
+    coords = torch.randn(1, ii.numel(), 2, 3, 3, device="cuda")
+    outs = []
+    with torch.no_grad():
+        for tl in (False, True):
+            n0 = net.to(state_dtype)
+            res = []
+            for it in range(2):                      # second update: the float32 state path even when the first was half
+                n_out, (d, w, (tg, wt)) = up.forward_mma(n0, imap, kk, corr, plan_kk, plan_ij, Np, pairs, packed, coords=coords, tile_local=tl)
+                res += [n_out.clone(), d.clone(), w.clone(), tg.clone(), wt.clone()]
+                n0 = n_out
+            outs.append(res)
+    torch.cuda.synchronize()
+    for a, b in zip(*outs):
+        assert torch.isfinite(a).all() and torch.equal(a, b)
+
+
+def test_tile_local_graph_detects_straddling_patches():
+    from devo_b200 import cuda_ba
+    from devo_b200.update import tile_local_graph
+    from problems import fully_connected_graph
+    for nf, ok in ((8, True), (4, True), (16, True), (5, False), (12, False), (22, False)):
+        ii, jj, kk = [t.cuda() for t in fully_connected_graph(nf, 16)]
+        assert tile_local_graph(cuda_ba.GraphPlan(kk, jj, nf * 16, nf)) == ok
+    ii, jj, kk = [t.cuda() for t in fully_connected_graph(8, 16)]
+    perm = torch.randperm(ii.numel(), device="cuda")                       # the DEVO loop's append order is not patch-major
+    assert not tile_local_graph(cuda_ba.GraphPlan(kk[perm], jj[perm], 8 * 16, 8))

@@ -18,7 +18,7 @@ scratch = GruState(op.E, dev).set(op.get_net())
 g = torch.cuda.CUDAGraph()
 with torch.cuda.graph(g), torch.no_grad():
     op.update.forward_mma(None, op.imap, op.kk, op.corr_buf, op.plan_kk, op.plan_ij, op.Np, op.Nf * op.Nf, op.packed,
-                          workspace=op._gru_ws, state=scratch)
+                          workspace=op._gru_ws, state=scratch, tile_local=op.tile_local)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 sets = {
     "nothing (cold)": [],

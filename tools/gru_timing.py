@@ -28,6 +28,7 @@ def main():
     plan_ij = cuda_ba.GraphPlan(ii * 12345 + jj, torch.zeros_like(ii), -1, 1, want_neighbors=False)
     fc = FrozenCast(torch.float16)
     packed = PackedUpdateWeights(up, torch.float16, 896)
+    TL = os.environ.get('GRU_TILE_LOCAL', '0') == '1'      # the merged first program (needs a tile-local graph: S8 is one)
     ctx = imap[:, kk].contiguous()
 
     def timeit(fn, n=50):
@@ -45,12 +46,12 @@ def main():
     with torch.no_grad():
         from devo_b200.update import GruState
         st = GruState(E, "cuda").set(net)
-        t_mma = timeit(lambda: up.forward_mma(None, imap, kk, corr, plan_kk, plan_ij, Np, nf * nf, packed, state=st))
+        t_mma = timeit(lambda: up.forward_mma(None, imap, kk, corr, plan_kk, plan_ij, Np, nf * nf, packed, state=st, tile_local=TL))
         net16 = net.half()
         t_cub = timeit(lambda: up.forward_fused(net16, ctx, corr.view(1, E, 896), plan_kk, plan_ij, Np, nf * nf, fc))
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            up.forward_mma(None, imap, kk, corr, plan_kk, plan_ij, Np, nf * nf, packed, state=st)
+            up.forward_mma(None, imap, kk, corr, plan_kk, plan_ij, Np, nf * nf, packed, state=st, tile_local=TL)
         t_graph = timeit(g.replay)
         g2 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g2):
@@ -61,7 +62,7 @@ def main():
         L.devo_gru_debug_timing.argtypes = [ctypes.c_void_p]
         L.devo_gru_debug_timing(None)
         for _ in range(int(os.environ.get("GRU_REPS", 32))):      # the stamps of the LAST update survive (16-launch ring): clocks are up by then
-            up.forward_mma(None, imap, kk, corr, plan_kk, plan_ij, Np, nf * nf, packed, state=st)
+            up.forward_mma(None, imap, kk, corr, plan_kk, plan_ij, Np, nf * nf, packed, state=st, tile_local=TL)
         torch.cuda.synchronize()
         buf = (ctypes.c_longlong * (2 * 16 * 48))()
         L.devo_gru_debug_timing(buf)
