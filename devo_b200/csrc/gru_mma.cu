@@ -73,7 +73,7 @@ constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kFirstEpiWarp = 2;           // warp 0: TMA producer, warp 1: MMA issuer of N-tile 0 (leader CTA) + TMEM allocation
 constexpr int kMma1Warp = kFirstEpiWarp + kEpiWarps;      // the last warp: MMA issuer of N-tile 1 (leader CTA)
 constexpr int kThreads = 32 * (kMma1Warp + 1);
-constexpr int kMaxLayers = 9;
+constexpr int kMaxLayers = 12;
 constexpr int kChunks = kD / 8;            // 16-byte chunks per row (48)
 constexpr int kCol4 = kD / 4;              // float4 groups per row (96)
 constexpr int kCPT = kNTc / kParts / 8;    // 16-byte chunks per thread per N-tile (3)
@@ -85,10 +85,10 @@ constexpr int kOffW = 2 * kABuf;                               // weight ring
 constexpr int kOffBars = kOffW + kWStages * kWStage;           // 56 mbarrier slots
 constexpr int kOffTmem = kOffBars + 56 * 8;                    // TMEM base address (+ pad)
 constexpr int kOffIdx = kOffTmem + 16;                         // [64] gather sources of the tile; merged program: [2][64] scatter rows
-constexpr int kOffStat = kOffIdx + 2 * kRows * 4;              // [kSlots][64][4] row-reduction partials
+constexpr int kOffStat = kOffIdx + 3 * kRows * 4 + 16;         // [kSlots][64][4] row-reduction partials
 constexpr int kOffLn = kOffStat + kSlots * kRows * 4 * 4;      // [2][2][384] f32: gamma, beta of the program's LayerNorms
-constexpr int kOffBias = kOffLn + 4 * kD * 4;                  // [kMaxLayers][384] biases as f32
-constexpr int kOffHead = kOffBias + kMaxLayers * kD * 4;       // [4][384] + [4] (+4 pad) head weights
+constexpr int kOffBias = kOffLn + 4 * kD * 4;                  // [kMaxLayers][384] biases (T: 12 layers of floats would not fit)
+constexpr int kOffHead = kOffBias + kMaxLayers * kD * 2;       // [4][384] + [4] (+4 pad) head weights
 constexpr int kOffEnd = kOffHead + (4 * kD + 8) * 2;
 // barrier slots
 constexpr int kBarWFull = 0, kBarWEmpty = kWStages, kBarAFull = 2 * kWStages, kBarAEmpty = 2 * kWStages + kASlots,
@@ -103,10 +103,15 @@ enum { EPI_RELU_A = 0, EPI_LNRELU_A = 1, EPI_ADD3_LN = 2, EPI_RESID = 3, EPI_STO
        // but the half result becomes the next A operand with its rows PERMUTED through the neighbour links -- row r is
        // written where the next layer's gather net[ix] / net[jx] would have fetched it from, rows without a neighbour
        // are zero -- so the exchange that used to need a kernel boundary is a scatter inside the CTA's own A tile
-       EPI_ADD3_LN_SC = 11, EPI_RESID_SC = 12 };
+       EPI_ADD3_LN_SC = 11, EPI_RESID_SC = 12,
+       // ... and the patch-wise SoftAgg inside the tile: STORE_G parks half(g) in the free A buffer, STORE_F_AGG parks
+       // half(f) in the buffer its own MMAs have finished reading, then the epilogue warps walk each patch's edge chain
+       // (the neighbour links), take the softmax-weighted sum per channel and write the group row to every member's row
+       // of the next A operand: segment_softmax_sum + the gather y[gid] without leaving shared memory
+       EPI_STORE_G = 13, EPI_STORE_F_AGG = 14 };
 __host__ __device__ constexpr bool epi_writes_a(int e) {
   return e == EPI_RELU_A || e == EPI_LNRELU_A || e == EPI_GATED_LN || e == EPI_RESID_A || e == EPI_RESID_LN_A ||
-         e == EPI_ADD3_LN_SC || e == EPI_RESID_SC;
+         e == EPI_ADD3_LN_SC || e == EPI_RESID_SC || e == EPI_STORE_F_AGG;
 }
 
 template <typename T>
@@ -328,7 +333,7 @@ struct Epi {
   __device__ __forceinline__ int chunk_of(int h, int j) const { return h * (kNT / 8) + cbase + j; }
   __device__ __forceinline__ float* s_stat() const { return reinterpret_cast<float*>(As + kOffStat); }
   __device__ __forceinline__ const float* s_ln() const { return reinterpret_cast<const float*>(As + kOffLn); }
-  __device__ __forceinline__ const float* s_bias() const { return reinterpret_cast<const float*>(As + kOffBias); }
+  __device__ __forceinline__ const T* s_bias() const { return reinterpret_cast<const T*>(As + kOffBias); }
   __device__ __forceinline__ const T* s_head() const { return reinterpret_cast<const T*>(As + kOffHead); }
   __device__ __forceinline__ int* s_idx() const { return reinterpret_cast<int*>(As + kOffIdx); }
   // tile-local program: s_sc(0)[r] = where the ADD3_LN_SC epilogue writes row r (as the c1 gather net[ix] would read it:
@@ -344,6 +349,14 @@ struct Epi {
       if ((jxv >= 0 && (dj < 0 || dj >= kRows)) || (ixv >= 0 && (di < 0 || di >= kRows))) __trap();   // the caller's promise is broken
       s_sc(0)[et] = (dj + 1) | ((ixv < 0) ? (1 << 16) : 0);
       s_sc(1)[et] = (di + 1) | ((jxv < 0) ? (1 << 16) : 0);
+    }
+    epi_bar_all();
+    if (et == 0) {        // the first edge of every patch chain, compacted: the work list of the in-tile aggregation
+      int* heads = s_sc(2);
+      int n = 0;
+      for (int q = 0; q < kRows; q++)
+        if (s_sc(0)[q] >> 16) heads[n++] = q;
+      heads[kRows] = n;
     }
     epi_bar_all();
   }
@@ -483,7 +496,7 @@ struct Epi {
       zrow = (sc >> 16) != 0;
     }
     constexpr int kIter = 2 * kCPT;
-    const float* bias = s_bias() + l * kD;
+    const T* bias = s_bias() + l * kD;
     const int set = l & 1;
     const uint32_t accph = (uint32_t)((l >> 1) & 1);
     float s1 = 0.f, s2 = 0.f;
@@ -497,8 +510,10 @@ struct Epi {
     const bool out_img = (EPI == EPI_STORE_A || EPI == EPI_ADD3_LN) ? (P.out_a != 0)
                        : (EPI == EPI_STORE_B) ? (P.out_b != 0)
                        : (EPI == EPI_RESID || EPI == EPI_GATED_HEADS) ? (P.out_a != 0 && l + 1 == P.n_layers) : false;
-    const bool writes_smem = kWritesA || out_img;
-    unsigned char* An = next_a();
+    const bool writes_smem = kWritesA || out_img || EPI == EPI_STORE_G;
+    // (STORE_F_AGG parks its tile in the buffer its OWN MMAs read -- free once both N-tiles are complete, see below --
+    //  because the other buffer holds g)
+    unsigned char* An = (EPI == EPI_STORE_F_AGG) ? (As + cur * kABuf) : next_a();
     const uint32_t tcol = trow + (uint32_t)(set * kNT);      // + h * kNTc + j * 8 (trow already points at this thread's 24 columns)
     // per-row operands of the element-wise tail, fetched one chunk ahead of their use
     // RESID: q[0..1] net32 ; GATED: q[0..1] n32, q[2] gate ; ADD3: q[0..1] state32 (or q[0] half state), q[... ] inp
@@ -534,7 +549,7 @@ struct Epi {
         }
       }
       // a streamed layer's epilogue overwrites A ring slots: BOTH tiles' MMAs must be done before the first store
-      if (l == 0 && P.stream_a0 && h == 0) mbar_wait(acc_full() + set * 2 + 1, accph);
+      if (((l == 0 && P.stream_a0) || EPI == EPI_STORE_F_AGG) && h == 0) mbar_wait(acc_full() + set * 2 + 1, accph);
       mbar_wait(acc_full() + set * 2 + h, accph);           // N-tile h of this layer is complete in TMEM (both CTAs)
       tc_fence_after();
       if (et == 0) stamp(P.dbg, 6 + 6 * l + h);
@@ -547,17 +562,16 @@ struct Epi {
         tmem_wait_ld();
         float o[8];
         {
-          const float4 b0 = *reinterpret_cast<const float4*>(bias + c * 8), b1 = *reinterpret_cast<const float4*>(bias + c * 8 + 4);
-          o[0] = __uint_as_float(raw[0]) + b0.x; o[1] = __uint_as_float(raw[1]) + b0.y;
-          o[2] = __uint_as_float(raw[2]) + b0.z; o[3] = __uint_as_float(raw[3]) + b0.w;
-          o[4] = __uint_as_float(raw[4]) + b1.x; o[5] = __uint_as_float(raw[5]) + b1.y;
-          o[6] = __uint_as_float(raw[6]) + b1.z; o[7] = __uint_as_float(raw[7]) + b1.w;
+          float bb[8];
+          unpack8<T>(*reinterpret_cast<const uint4*>(bias + c * 8), bb);
+#pragma unroll
+          for (int k = 0; k < 8; k++) o[k] = __uint_as_float(raw[k]) + bb[k];
         }
         const uint4 oh = pack8<T>(o);                 // the Linear output, rounded to half (autocast)
         if constexpr (EPI == EPI_RELU_A) {
           *reinterpret_cast<uint4*>(An + a_off(r, c)) = relu8<T>(oh);   // max(.,0) commutes with the rounding
-        } else if constexpr (EPI == EPI_STORE_A || EPI == EPI_STORE_B) {
-          *reinterpret_cast<uint4*>(An + a_off(r, c)) = oh;             // staging image, written out by TMA below
+        } else if constexpr (EPI == EPI_STORE_A || EPI == EPI_STORE_B || EPI == EPI_STORE_G || EPI == EPI_STORE_F_AGG) {
+          *reinterpret_cast<uint4*>(An + a_off(r, c)) = oh;             // staging image (written out by TMA below) / g, f tiles
         } else if constexpr (EPI == EPI_GATE) {
           *reinterpret_cast<uint4*>(gate_r + (size_t)c * (kRows * 8)) = oh;
         } else if constexpr (EPI == EPI_LNRELU_A) {
@@ -645,11 +659,52 @@ struct Epi {
           }
         }
       }
-      if constexpr (kWritesA && !kTwoPass) {
+      if constexpr (kWritesA && !kTwoPass && EPI != EPI_STORE_F_AGG) {
         if (l + 1 < P.n_layers) signal_a(h);     // the MMA warps may start on the K-blocks fed by this N-tile
       }
     }
     if (et == 0) stamp(P.dbg, 8 + 6 * l);
+    if constexpr (EPI == EPI_STORE_F_AGG) {
+      // ---------------- the patch-wise SoftAgg of this tile (blocks.py:40-43 on rows that all live here) ----------------
+      // g sits in the other A buffer, f in this layer's own; one (patch, 8-channel chunk) item per thread and round: walk
+      // the patch's edge chain (kb order, as the segment kernel's sort) with an online softmax, then write the group row
+      // to every member's row of the next A operand -- in place over g: an item owns its (rows, chunk) cells
+      epi_bar_all();                                         // every warp's g (previous layer) and f rows are in place
+      unsigned char* G = next_a();
+      const unsigned char* F = As + cur * kABuf;
+      const int* heads = s_sc(2);
+      const int* link = s_sc(0);
+      const int nitems = heads[kRows] * kChunks;
+#pragma unroll 1
+      for (int item = et; item < nitems; item += kEpiThreads) {
+        const int c = item % kChunks;
+        const int head = heads[item / kChunks];
+        float m[8], den[8], num[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { m[k] = -INFINITY; den[k] = 0.f; num[k] = 0.f; }
+        for (int rr = head; rr >= 0; rr = (link[rr] & 0xffff) - 1) {
+          float gv[8], fv[8];
+          unpack8<T>(*reinterpret_cast<const uint4*>(G + a_off(rr, c)), gv);
+          unpack8<T>(*reinterpret_cast<const uint4*>(F + a_off(rr, c)), fv);
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            if (gv[k] > m[k]) {
+              const float sc = __expf(m[k] - gv[k]);        // exp(-inf) = 0 on the first row
+              den[k] *= sc; num[k] *= sc; m[k] = gv[k];
+            }
+            const float e = __expf(gv[k] - m[k]);
+            den[k] += e;
+            num[k] += e * fv[k];
+          }
+        }
+        float y[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) y[k] = den[k] > 0.f ? num[k] / den[k] : 0.f;
+        const uint4 yh = pack8<T>(y);
+        for (int rr = head; rr >= 0; rr = (link[rr] & 0xffff) - 1) *reinterpret_cast<uint4*>(G + a_off(rr, c)) = yh;
+      }
+      if (l + 1 < P.n_layers) { signal_a(0); signal_a(1); }
+    }
     // ---------------- row-wise tails ----------------
     if constexpr (EPI == EPI_LNRELU_A) {
       float mean, rstd;
@@ -755,7 +810,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
   uint64_t* pro_ready = bars + kBarProReady;  // [1]        leader: prologue finished in both CTAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base + kOffTmem);
   float* s_ln = reinterpret_cast<float*>(base + kOffLn);
-  float* s_bias = reinterpret_cast<float*>(base + kOffBias);
+  T* s_bias = reinterpret_cast<T*>(base + kOffBias);
   T* s_head = reinterpret_cast<T*>(base + kOffHead);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -780,12 +835,8 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
     // stage the program's small parameters (biases, LayerNorm affine, heads) in shared memory once
     const int t = threadIdx.x - 32 * kFirstEpiWarp, nt = kEpiThreads;
     for (int l = 0; l < P.n_layers; l++)
-      for (int q = t; q < kD / 8; q += nt) {
-        float bv[8];
-        unpack8<T>(__ldg(reinterpret_cast<const uint4*>(P.bias[l]) + q), bv);
-        reinterpret_cast<float4*>(s_bias + l * kD)[2 * q] = make_float4(bv[0], bv[1], bv[2], bv[3]);
-        reinterpret_cast<float4*>(s_bias + l * kD)[2 * q + 1] = make_float4(bv[4], bv[5], bv[6], bv[7]);
-      }
+      for (int q = t; q < kD / 8; q += nt)
+        reinterpret_cast<uint4*>(s_bias + l * kD)[q] = __ldg(reinterpret_cast<const uint4*>(P.bias[l]) + q);
     for (int k = 0; k < 2; k++) {
       if (P.ln_g[k] == nullptr) continue;
       for (int q = t; q < kD / 4; q += nt) {
@@ -949,6 +1000,8 @@ __global__ void __launch_bounds__(kThreads, 1) gru_mma_kernel(const __grid_const
         case EPI_RESID_LN_A: e.template layer<EPI_RESID_LN_A>(l); break;
         case EPI_ADD3_LN_SC: e.template layer<EPI_ADD3_LN_SC>(l); break;
         case EPI_RESID_SC: e.template layer<EPI_RESID_SC>(l); break;
+        case EPI_STORE_G: e.template layer<EPI_STORE_G>(l); break;
+        case EPI_STORE_F_AGG: e.template layer<EPI_STORE_F_AGG>(l); break;
         default: e.template layer<EPI_GATED_HEADS>(l); break;
       }
     }
@@ -1117,8 +1170,12 @@ static int gru_update_impl(const devo_gru_weights_t* Wt, const devo_gru_io_t* io
     // tile the CTA has just produced: the ADD3_LN / RESID epilogues write their half rows straight to where the next
     // layer's A operand wants them.  Two kernel boundaries (~5 us each: bulk-store completion, skew, dependent gather)
     // and the two [E,384] images that carried the rows across them are gone.
+    // The patch-wise SoftAgg follows in the same launch: all edges of a patch are rows of this CTA, so the segment
+    // softmax + sum and the gather of the group row back to the edges (the A operand of `h`) are a walk along the
+    // patch's chain in shared memory (EPI_STORE_G / EPI_STORE_F_AGG) -- the segment-reduction kernel and its two
+    // boundaries are gone as well; `h`, then g / f of the frame-pair aggregation, close the program.
     GruProg<T> P = base;
-    P.n_layers = 9; P.pro = PRO_NONE; P.kblocks0 = io->corr_ld / 64; P.stream_a0 = 1; P.use_w0 = 1;
+    P.n_layers = 12; P.pro = PRO_NONE; P.kblocks0 = io->corr_ld / 64; P.stream_a0 = 1; P.use_w0 = 1;
     P.w_row[0] = 0;      P.epi[0] = EPI_RELU_A;     P.bias[0] = bias;
     P.w_row[1] = 0 * kD; P.epi[1] = EPI_LNRELU_A;   P.bias[1] = B(0);
     P.w_row[2] = 1 * kD; P.epi[2] = EPI_ADD3_LN_SC; P.bias[2] = B(1);
@@ -1126,8 +1183,11 @@ static int gru_update_impl(const devo_gru_weights_t* Wt, const devo_gru_io_t* io
     P.w_row[4] = 3 * kD; P.epi[4] = EPI_RESID_SC;   P.bias[4] = B(3);
     P.w_row[5] = 4 * kD; P.epi[5] = EPI_RELU_A;     P.bias[5] = B(4);
     P.w_row[6] = 5 * kD; P.epi[6] = EPI_RESID_A;    P.bias[6] = B(5);
-    P.w_row[7] = 6 * kD; P.epi[7] = EPI_STORE_A;    P.bias[7] = B(6);
-    P.w_row[8] = 7 * kD; P.epi[8] = EPI_STORE_B;    P.bias[8] = B(7);
+    P.w_row[7] = 6 * kD; P.epi[7] = EPI_STORE_G;     P.bias[7] = B(6);
+    P.w_row[8] = 7 * kD; P.epi[8] = EPI_STORE_F_AGG; P.bias[8] = B(7);
+    P.w_row[9] = 8 * kD;   P.epi[9] = EPI_RESID_A;  P.bias[9] = B(8);
+    P.w_row[10] = 9 * kD;  P.epi[10] = EPI_STORE_A; P.bias[10] = B(9);
+    P.w_row[11] = 10 * kD; P.epi[11] = EPI_STORE_B; P.bias[11] = B(10);
     P.ln_g[0] = Wt->ln_gamma; P.ln_b[0] = Wt->ln_beta;
     P.ln_g[1] = Wt->ln_gamma + kD; P.ln_b[1] = Wt->ln_beta + kD;
     P.state_half = io->net16 != nullptr;
@@ -1180,6 +1240,7 @@ static int gru_update_impl(const devo_gru_weights_t* Wt, const devo_gru_io_t* io
     if (rc != DEVO_OK) return rc;
   }
   }   // !tile_local
+  if (!io->tile_local) {
   rc = devo::segment_softmax_sum(g16, f16, io->perm_kk, io->gstart_kk, io->ngroups_kk, io->max_groups_kk, y16, dtype, E, kD, (void*)s, 1);
   if (rc != DEVO_OK) return rc;
   {
@@ -1192,6 +1253,7 @@ static int gru_update_impl(const devo_gru_weights_t* Wt, const devo_gru_io_t* io
     rc = launch_prog<T>(tw, tw0, ta, t_g16, t_f16, P, s);
     if (rc != DEVO_OK) return rc;
   }
+  }   // !tile_local
   rc = devo::segment_softmax_sum(g16, f16, io->perm_ij, io->gstart_ij, io->ngroups_ij, io->max_groups_ij, hy16, dtype, E, kD, (void*)s, 1);
   if (rc != DEVO_OK) return rc;
   {

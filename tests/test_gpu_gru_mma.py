@@ -110,12 +110,14 @@ def test_gru_mma_is_deterministic():
 
 
 @pytest.mark.parametrize("nf,m,state_dtype", [(8, 96, torch.float32), (8, 96, torch.float16), (4, 40, torch.float32), (16, 12, torch.float32)])
-def test_gru_mma_tile_local_program_is_bit_identical(nf, m, state_dtype):
+def test_gru_mma_tile_local_program_matches_the_classic_form(nf, m, state_dtype):
     """devo_gru_io_t.tile_local: when every neighbour link stays inside its 64-edge tile (the patch-major all-pairs graph
-    with 8, 4 or 16 edges per patch) the first three programs run as one launch whose epilogues permute the rows inside
-    the CTA's own A tile instead of gathering them across a kernel boundary.  Same arithmetic, different data movement:
-    every output must match the three-launch form bit for bit."""
-    from devo_b200.update import GruState, PackedUpdateWeights, tile_local_graph
+    with 8, 4 or 16 edges per patch) the first four programs and the patch-wise segment reduction run as one launch: the
+    epilogues permute rows inside the CTA's own A tile instead of gathering them across kernel boundaries, and the
+    SoftAgg over a patch's edges walks the patch's chain in shared memory.  The neighbour exchange is the same arithmetic
+    (bit-identical on its own); the in-tile softmax adds the rows of a patch in chain order where the segment kernel adds
+    two interleaved halves, so the group rows may differ in the last bit of a half: compared at half-precision noise."""
+    from devo_b200.update import PackedUpdateWeights, tile_local_graph
     up, net, imap, corr, ii, jj, kk, plan_kk, plan_ij, Np, pairs = _problem(nf, m, 0)
     assert tile_local_graph(plan_kk)
     packed = PackedUpdateWeights(up, torch.float16, 896)
@@ -131,8 +133,14 @@ def test_gru_mma_tile_local_program_is_bit_identical(nf, m, state_dtype):
                 n0 = n_out
             outs.append(res)
     torch.cuda.synchronize()
-    for a, b in zip(*outs):
-        assert torch.isfinite(a).all() and torch.equal(a, b)
+    names = ["net", "delta", "weight", "target", "weight32"] * 2
+    for nm, a, b in zip(names, *outs):
+        assert torch.isfinite(b).all()
+        err = (a.float() - b.float()).abs().max().item()
+        scale = max(a.float().abs().max().item(), 1.0)
+        print("tile-local vs classic %-8s max |diff| %.3e (scale %.2f)" % (nm, err, scale))
+        assert err <= 4e-3 * scale, (nm, err)
+        assert (a.float() - b.float()).abs().mean().item() <= 2e-4 * scale
 
 
 def test_tile_local_graph_detects_straddling_patches():
