@@ -232,12 +232,13 @@ __device__ __forceinline__ size_t t16(int tile, int c, int r) { return (((size_t
 __device__ __forceinline__ float4 as_f4(uint4 u) {
   return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
 }
+constexpr int kDbgSlots = 80;             // stamps per launch: 4 + 6 per layer, up to kMaxLayers = 12
 __device__ __forceinline__ void stamp(long long* dbg, int slot) {
   if (dbg != nullptr && blockIdx.x == 0) {
     long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     dbg[slot] = t;
-    dbg[16 * 48 + slot] = clock64();        // SM cycles next to wall time: separates clock ramps from pipeline stalls
+    dbg[16 * kDbgSlots + slot] = clock64(); // SM cycles next to wall time: separates clock ramps from pipeline stalls
   }
 }
 // sigmoid in 4 instructions (FMUL, MUFU.EX2, FADD, MUFU.RCP); the result is rounded to half right away
@@ -667,7 +668,7 @@ struct Epi {
     if constexpr (EPI == EPI_STORE_F_AGG) {
       // ---------------- the patch-wise SoftAgg of this tile (blocks.py:40-43 on rows that all live here) ----------------
       // g sits in the other A buffer, f in this layer's own; one (patch, 8-channel chunk) item per thread and round: walk
-      // the patch's edge chain (kb order, as the segment kernel's sort) with an online softmax, then write the group row
+      // the patch's edge chain (kb order, as the segment kernel's sort) for the softmax-weighted sum, then write the group row
       // to every member's row of the next A operand -- in place over g: an item owns its (rows, chunk) cells
       epi_bar_all();                                         // every warp's g (previous layer) and f rows are in place
       unsigned char* G = next_a();
@@ -679,19 +680,23 @@ struct Epi {
       for (int item = et; item < nitems; item += kEpiThreads) {
         const int c = item % kChunks;
         const int head = heads[item / kChunks];
+        // two passes over the chain (the rows sit in shared memory): the maximum first, then ONE exponential per element
+        // (the online form of the segment kernel costs two and a data-dependent branch: 5.9 us for this phase at S8)
         float m[8], den[8], num[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) { m[k] = -INFINITY; den[k] = 0.f; num[k] = 0.f; }
+        for (int rr = head; rr >= 0; rr = (link[rr] & 0xffff) - 1) {
+          float gv[8];
+          unpack8<T>(*reinterpret_cast<const uint4*>(G + a_off(rr, c)), gv);
+#pragma unroll
+          for (int k = 0; k < 8; k++) m[k] = fmaxf(m[k], gv[k]);
+        }
         for (int rr = head; rr >= 0; rr = (link[rr] & 0xffff) - 1) {
           float gv[8], fv[8];
           unpack8<T>(*reinterpret_cast<const uint4*>(G + a_off(rr, c)), gv);
           unpack8<T>(*reinterpret_cast<const uint4*>(F + a_off(rr, c)), fv);
 #pragma unroll
           for (int k = 0; k < 8; k++) {
-            if (gv[k] > m[k]) {
-              const float sc = __expf(m[k] - gv[k]);        // exp(-inf) = 0 on the first row
-              den[k] *= sc; num[k] *= sc; m[k] = gv[k];
-            }
             const float e = __expf(gv[k] - m[k]);
             den[k] += e;
             num[k] += e * fv[k];
@@ -1068,7 +1073,7 @@ static int make_map_2d(CUtensorMap* m, int dtype, const void* ptr, uint64_t rows
 constexpr size_t kSmemBytes = 1024 + (size_t)kOffEnd + 64;
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
-static long long* g_dbg = nullptr;     // 16 launches x 48 stamps (ns), then the same in SM cycles
+static long long* g_dbg = nullptr;     // 16 launches x kDbgSlots stamps (ns), then the same in SM cycles
 static int g_dbg_launch = 0;
 
 template <typename T>
@@ -1085,7 +1090,7 @@ static int launch_prog(const CUtensorMap& tw, const CUtensorMap& tw0, const CUte
   const int tiles = (P.rows + kRows - 1) / kRows;
   if (tiles <= 0) return DEVO_OK;
   GruProg<T> Pd = P;
-  Pd.dbg = g_dbg ? g_dbg + 48 * (g_dbg_launch++ % 16) : nullptr;
+  Pd.dbg = g_dbg ? g_dbg + kDbgSlots * (g_dbg_launch++ % 16) : nullptr;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)((tiles + 1) / 2 * 2), 1, 1);      // whole pairs; a CTA without live rows still plays its part
@@ -1294,11 +1299,11 @@ int devo_gru_state_gather(const float* src, int src_layout, int src_rows, const 
 // debug (tools/gru_timing.py): enable / read back the %globaltimer stamps of CTA 0 of the last 16 launches
 int devo_gru_debug_timing(long long* host_out) {
   if (!g_dbg) {
-    if (cudaMalloc(&g_dbg, 2 * 16 * 48 * sizeof(long long)) != cudaSuccess) return -1;
-    cudaMemset(g_dbg, 0, 2 * 16 * 48 * sizeof(long long));
+    if (cudaMalloc(&g_dbg, 2 * 16 * kDbgSlots * sizeof(long long)) != cudaSuccess) return -1;
+    cudaMemset(g_dbg, 0, 2 * 16 * kDbgSlots * sizeof(long long));
   }
   g_dbg_launch = 0;
-  if (host_out) return (int)cudaMemcpy(host_out, g_dbg, 2 * 16 * 48 * sizeof(long long), cudaMemcpyDeviceToHost);
+  if (host_out) return (int)cudaMemcpy(host_out, g_dbg, 2 * 16 * kDbgSlots * sizeof(long long), cudaMemcpyDeviceToHost);
   return 0;
 }
 

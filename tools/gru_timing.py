@@ -7,6 +7,8 @@ import sys
 
 import torch
 
+SL = 80            # debug stamps per launch (kDbgSlots in csrc/gru_mma.cu)
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 
@@ -64,10 +66,13 @@ def main():
         for _ in range(int(os.environ.get("GRU_REPS", 32))):      # the stamps of the LAST update survive (16-launch ring): clocks are up by then
             up.forward_mma(None, imap, kk, corr, plan_kk, plan_ij, Np, nf * nf, packed, state=st, tile_local=TL)
         torch.cuda.synchronize()
-        buf = (ctypes.c_longlong * (2 * 16 * 48))()
+        buf = (ctypes.c_longlong * (2 * 16 * SL))()
         L.devo_gru_debug_timing(buf)
     names = ["corr+norm", "c1", "c2+agg_kk g,f", "h_kk+agg_ij g,f", "h_ij+gru+heads"]
     nl = [3, 2, 4, 3, 7]
+    if TL:                     # tile-local graph: one program up to the frame-pair g / f, then the GRU program
+        names = ["corr+norm|c1|c2|agg_kk|h_kk|g,f_ij", "h_ij+gru+heads"]
+        nl = [12, 7]
     reps = int(os.environ.get("GRU_REPS", 32))
     # absolute view (ns clock shared by all SMs): when CTA 0 of each launch started, finished its prologue, issued its first
     # MMA, finished its last epilogue and exited -- the distance between "last epilogue of launch k" and "first MMA of
@@ -76,7 +81,7 @@ def main():
     rows = []
     for k, n in enumerate(nl):
         k16 = (len(names) * (reps - 1) + k) % 16
-        s_ = [buf[48 * k16 + q] for q in range(48)]
+        s_ = [buf[SL * k16 + q] for q in range(SL)]
         if base is None:
             base = s_[0]
         s0 = s_[0] if s_[0] else base                     # fused launch: only program 0 has the kernel-start stamp
@@ -87,8 +92,8 @@ def main():
         print("               %-16s %7.1f %9.1f %10.1f %9.1f %7.1f  | %s" % (r + (nxt,)))
     for k, (nm, n) in enumerate(zip(names, nl)):
         k16 = (len(names) * (reps - 1) + k) % 16
-        s = [buf[48 * k16 + q] for q in range(48)]
-        cyc = [buf[16 * 48 + 48 * k16 + q] for q in range(48)]
+        s = [buf[SL * k16 + q] for q in range(SL)]
+        cyc = [buf[16 * SL + SL * k16 + q] for q in range(SL)]
         mhz = (cyc[3] - cyc[0]) / max(s[3] - s[0], 1) * 1e3
         t0 = s[0] if s[0] else base
         rel = lambda q: (s[q] - t0) / 1e3 if s[q] else float("nan")
