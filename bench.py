@@ -646,14 +646,15 @@ def run_ours(args, rank, world, local_rank):
         except Exception:
             tpeak, tsrc = 1368.0, "fallback (B200_PROFILING.md)"
         in_ms = in_step["update_operator"] * 1e-3 if (in_step and "update_operator" in in_step) else None
-        roofline_gru = dict(bound="tensor", kernel="gru_mma_kernel x%d + segment_softmax_sum x2 (devo_gru_update)" % (3 if op.tile_local else 5),
+        roofline_gru = dict(bound="tensor", kernel=("gru_mma_kernel x2 + segment_softmax_sum x1 (devo_gru_update, tile-local edge list)" if op.tile_local
+                                    else "gru_mma_kernel x5 + segment_softmax_sum x2 (devo_gru_update)"),
                             achieved=round(fl / (g_ms * 1e-3) / 1e12, 2), peak=tpeak, unit="TFLOP/s",
                             frac=round(fl / (g_ms * 1e-3) / 1e12 / tpeak, 4), traffic=ncu_traffic_bytes("gru"), flops=fl,
                             kernel_ms=round(g_ms, 5), kernel_ms_in_step_upper_bound=(round(in_ms, 5) if in_ms else None),
                             peak_source=tsrc,
                             note="the update operator is the largest share of a step; a chain of 19 dependent Linear layers "
                                  "([6144,384]x[384,384], one with K=896) on 48 CTA pairs (cta_group::2 MMAs; the S8 edge list is patch-major, so the "
-                                 "first three programs run as one launch with in-tile neighbour exchange): per layer MMA -> epilogue "
+                                 "first four programs and the patch-wise aggregation run as one 12-layer launch with in-tile exchange): per layer MMA -> epilogue "
                                  "-> next layer's MMA (DESIGN.md 2.6); timed alone as one graph replay, L2 flushed before each replay "
                                  "(kernel_ms_in_step_upper_bound: between event-record nodes inside the step, which break the "
                                  "programmatic launch chain)")

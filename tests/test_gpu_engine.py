@@ -99,7 +99,7 @@ def test_state_arena_refresh_path_equals_set_graph_path():
     op.ii.zero_(); op.jj.zero_(); op.kk.zero_(); op.pair_key.zero_()
     with torch.no_grad():
         op.state_arena.copy_(arena0)
-        op.refresh_pair_key()
+        op.refresh_pair_key(same_graph=True)       # (keeps what set_graph verified about the list: the same program runs)
         op._iteration(reset_geometry=False)
     torch.cuda.synchronize()
     assert int(op.status.item()) == 0
