@@ -690,7 +690,7 @@ def run_ours(args, rank, world, local_rank):
     return line
 
 
-def run_e2e(op, wl, dev, steps):
+def run_e2e(op, wl, dev, steps, probe=False, h2d_frac=1.0, chunks=1, light_body=False):
     """The same step as `value` (ingest of the newly arrived frame + one update iteration), end to end from HOST buffers:
 
       copy stream     ONE H2D copy per step of a pinned host arena -- the new frame's features (fmap, gmap, imap: sensor data,
@@ -703,6 +703,7 @@ def run_e2e(op, wl, dev, steps):
       host            consumes step k-1's result while step k runs (at most two steps in flight)
 
     Every step's copies are inside the timed region (wall clock between two device synchronisations)."""
+    from devo_b200 import _lib
     M, Nf = wl["patches_per_frame"], wl["n_frames"]
     f = Nf - 1
     feats = dict(fmap=wl["fmap"][f].contiguous(), gmap=wl["gmap"][f * M:(f + 1) * M].contiguous(), imap=wl["imap"][f * M:(f + 1) * M].contiguous())
@@ -739,11 +740,15 @@ def run_e2e(op, wl, dev, steps):
     copy_s = torch.cuda.Stream(device=dev)
 
     def body(b):
-        op.state_arena.copy_(stage[b][state_off:], non_blocking=True)      # the state the caller uploaded this step
-        op.refresh_pair_key(same_graph=True)          # the arena carries the edge list set_graph installed, unchanged
+        if not light_body:
+            _lib.copy_(op.state_arena, stage[b][state_off:])      # the state the caller uploaded this step (a kernel: copy-
+                                                                  # engine nodes would queue behind the next step's H2D)
+            op.refresh_pair_key(same_graph=True)          # the arena carries the edge list set_graph installed, unchanged
         op.ingest_frame(f, view(stage[b], "fmap"), view(stage[b], "gmap"), view(stage[b], "imap"), overlap=True)
-        op._iteration(reset_geometry=False)
-        out_dev[:Nf * 7].copy_(op.poses.view(-1))
+        op._iteration(reset_geometry=light_body)
+        if light_body:
+            return
+        _lib.copy_(out_dev[:Nf * 7], op.poses.view(-1))
         out_dev[Nf * 7:].copy_(op.patches[0, :, 2, 1, 1])
         out_host[b].copy_(out_dev, non_blocking=True)                        # D2H of the result: a node of the step's graph
 
@@ -767,16 +772,28 @@ def run_e2e(op, wl, dev, steps):
         ev_done = [torch.cuda.Event() for _ in range(2)]
         results = []
 
-        def run(n):
+        def run(n, h2d_on=True, graph_on=True, trace=None):
             for k in range(n):
                 b = k & 1
                 with torch.cuda.stream(copy_s):
                     if k >= 2:
                         copy_s.wait_event(ev_done[b])              # staging buffer b was consumed by step k-2
-                    stage[b].copy_(host_in, non_blocking=True)     # H2D of this step's inputs
+                    if h2d_on and (h2d_frac != 1.0 or chunks != 1):   # probe variants only
+                        nb = int(total * h2d_frac) // chunks
+                        for c in range(chunks):
+                            stage[b][c * nb:(c + 1) * nb].copy_(host_in[c * nb:(c + 1) * nb], non_blocking=True)
+                    elif h2d_on:
+                        stage[b].copy_(host_in, non_blocking=True)     # H2D of this step's inputs
                     ev_in[b].record(copy_s)
                 cur.wait_event(ev_in[b])
-                graphs[b].replay()                                 # state refresh + ingest + update iteration + D2H of the result
+                if trace is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(cur)
+                if graph_on:
+                    graphs[b].replay()                             # state refresh + ingest + update iteration + D2H of the result
+                if trace is not None:
+                    e1.record(cur)
+                    trace.append((e0, e1))
                 ev_done[b].record(cur)
                 if k >= 1:
                     ev_done[b ^ 1].synchronize()                   # the host reads step k-1's result while step k runs
@@ -793,6 +810,26 @@ def run_e2e(op, wl, dev, steps):
             torch.cuda.synchronize(dev)
             dts.append(time.perf_counter() - t0)
         dt = sorted(dts)[1]
+        if probe:                                # tools/e2e_probe.py: which of the two legs bounds the pipeline
+            legs = {}
+            for name, kw in (("h2d_only", dict(graph_on=False)), ("graph_only", dict(h2d_on=False))):
+                run(4, **kw)
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                run(steps, **kw)
+                torch.cuda.synchronize(dev)
+                legs[name + "_us_per_step"] = round((time.perf_counter() - t0) / steps * 1e6, 2)
+            legs["e2e_us_per_step"] = round(dt / steps * 1e6, 2)
+            for name, kw in (("e2e", {}), ("graph_only", dict(h2d_on=False))):      # device-side view: replay duration and gaps
+                tr = []
+                run(steps, trace=tr, **kw)
+                torch.cuda.synchronize(dev)
+                dur = sorted(a.elapsed_time(b) * 1e3 for a, b in tr)
+                gap = sorted(tr[i][1].elapsed_time(tr[i + 1][0]) * 1e3 for i in range(len(tr) - 1))
+                legs[name + "_replay_us_median"] = round(dur[len(dur) // 2], 2)
+                legs[name + "_gap_us_median"] = round(gap[len(gap) // 2], 2)
+            legs["h2d_gbs"] = round(h2d / legs["h2d_only_us_per_step"] / 1e3, 2)
+            return legs
     return dict(value=round(steps / dt, 2), unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                 steps=steps, seconds=dt,
                 note="host pinned inputs every step: ONE H2D copy of the new frame's features + poses, patches, intrinsics and "

@@ -22,6 +22,7 @@ SIGNATURES = {
     "devo_abi_version": (_i, []),
     "devo_last_error": (_c.c_char_p, []),
     "devo_launch_count": (_c.c_uint64, []),
+    "devo_copy_bytes": (_i, [_vp, _vp, _sz, _vp]),
     "devo_corr_forward": (_i, [_vp] * 6 + [_i] * 10 + [_vp]),
     "devo_corr_backward": (_i, [_vp] * 8 + [_i] * 10 + [_vp]),
     "devo_patchify_forward": (_i, [_vp] * 3 + [_i] * 7 + [_vp]),
@@ -155,6 +156,17 @@ def require_dtype(t, dtype, name):
 
 def launch_count():
     return int(lib().devo_launch_count())
+
+
+def copy_(dst, src):
+    """dst.copy_(src) for two contiguous CUDA tensors of the same dtype and size, done by a kernel on the current stream
+    (devo_copy_bytes): inside a captured step a memcpy node would run on a copy engine and queue behind host uploads"""
+    require_cuda(dst, src)
+    if dst.dtype != src.dtype or dst.numel() != src.numel() or not (dst.is_contiguous() and src.is_contiguous()):
+        raise RuntimeError("devo_b200: copy_ needs two contiguous tensors of the same dtype and size")
+    check(lib().devo_copy_bytes(dst.data_ptr(), src.data_ptr(), dst.numel() * dst.element_size(), stream_ptr(dst.device)),
+          "copy_bytes")
+    return dst
 
 
 _ws_cache = {}

@@ -1401,15 +1401,27 @@ int devo_ba_forward_planned(float* poses, float* patches, const float* intrinsic
 // run); devo_ba_forward_prepared then launches nothing but the iterations, reads the plan ahead of the programmatic wait
 // from the first iteration on (the caller vouches the plan is older than the preceding kernel of the stream) and folds
 // the status into `status_or` (may be NULL) in its last launch.
+//
+// The two clears are ONE 32-thread kernel, not memset nodes: inside a captured step a memset node runs on a copy engine,
+// and when the caller uploads the next step's inputs meanwhile (one 5 MB H2D copy, ~100 us) the 4-byte memset queued
+// behind that copy and held the update operator back by 35-60 us per step (tools/e2e_probe.py).
+__global__ void ba_prepare_kernel(int32_t* __restrict__ status, int32_t* __restrict__ ticket) {
+  if (threadIdx.x == 0) *status = 0;
+  if (ticket != nullptr) ticket[threadIdx.x] = 0;
+}
+
 int devo_ba_prepare(void* workspace, size_t workspace_bytes, int E, int n_free_poses, int32_t* status, void* stream) {
   DEVO_REQUIRE(status != nullptr, DEVO_EINVAL, "ba_prepare: status pointer is NULL");
   cudaStream_t s = (cudaStream_t)stream;
-  DEVO_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), s));
-  if (E <= 0) return DEVO_OK;
-  BaLayout L = ba_layout(E, n_free_poses > 0 ? n_free_poses : 0);
-  DEVO_REQUIRE(workspace && workspace_bytes >= L.total, DEVO_EWORKSPACE, "ba_prepare: workspace too small (%zu < %zu)",
-               workspace_bytes, L.total);
-  DEVO_CUDA(cudaMemsetAsync((char*)workspace + L.ticket, 0, 4 * 32, s));
+  int32_t* ticket = nullptr;
+  if (E > 0) {
+    BaLayout L = ba_layout(E, n_free_poses > 0 ? n_free_poses : 0);
+    DEVO_REQUIRE(workspace && workspace_bytes >= L.total, DEVO_EWORKSPACE, "ba_prepare: workspace too small (%zu < %zu)",
+                 workspace_bytes, L.total);
+    ticket = (int32_t*)((char*)workspace + L.ticket);
+  }
+  ba_prepare_kernel<<<1, 32, 0, s>>>(status, ticket);
+  DEVO_LAUNCH_CHECK("ba_prepare");
   return DEVO_OK;
 }
 

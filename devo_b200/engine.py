@@ -157,7 +157,11 @@ class UpdateOperator:
         if gmap_patches is not None:
             cuda_corr.pack_gmap(gmap_patches.to(self.feat_dtype), out=self.gmap_pm[idx * self.M:(idx + 1) * self.M])
         if imap_patches is not None:
-            self.imap[0, idx * self.M:(idx + 1) * self.M].copy_(imap_patches.to(self.feat_dtype))
+            src, dst = imap_patches.to(self.feat_dtype), self.imap[0, idx * self.M:(idx + 1) * self.M]
+            if src.is_cuda and src.is_contiguous() and src.shape == dst.shape:
+                _lib.copy_(dst, src)               # a kernel: no copy-engine node inside a captured step
+            else:
+                dst.copy_(src)
 
     def set_net(self, net):
         """install the recurrent hidden state ([1,E,dim], any float dtype; kept as float32)"""
@@ -193,7 +197,7 @@ class UpdateOperator:
                 marks[i].record(torch.cuda.current_stream(self.device))
         mark(0)
         if reset_geometry and self._pristine is not None:
-            self.state_arena[:self._geom_bytes].copy_(self._pristine)
+            _lib.copy_(self.state_arena[:self._geom_bytes], self._pristine)
         # (0) graph analysis on the device (neighbours, patch groups, frame-pair groups) on a side stream:
         #     it only depends on ii/jj/kk, so it overlaps the reprojection and the correlation lookup
         cur = torch.cuda.current_stream(self.device)

@@ -35,6 +35,11 @@ int         devo_abi_version(void);
 const char* devo_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 uint64_t    devo_launch_count(void);
+/* device-to-device copy of nbytes done by a KERNEL on `stream` (16-byte vectors when dst, src and nbytes allow).  For the
+ * small state copies inside a captured step (what `tensor.copy_()` does in the reference's loop, devo/devo.py:232-239,
+ * 523-527): a cudaMemcpyAsync / cudaMemsetAsync there becomes a copy-engine node of the graph, which costs ~4 us of
+ * engine hand-over and queues behind whatever host upload is in flight on that engine (tools/e2e_probe.py). */
+int         devo_copy_bytes(void* dst, const void* src, size_t nbytes, void* stream);
 
 /* ------------------------------------------------------------------ altcorr (cuda_corr) */
 /* cuda_corr.forward  (devo/altcorr/correlation.cpp:57, correlation_kernel.cu:82-136,193-233)
