@@ -25,6 +25,7 @@ SIGNATURES = {
     "devo_copy_bytes": (_i, [_vp, _vp, _sz, _vp]),
     "devo_corr_forward": (_i, [_vp] * 6 + [_i] * 10 + [_vp]),
     "devo_corr_backward": (_i, [_vp] * 8 + [_i] * 10 + [_vp]),
+    "devo_corr_backward_pm": (_i, [_vp] * 8 + [_i] * 6 + [_vp]),
     "devo_patchify_forward": (_i, [_vp] * 3 + [_i] * 7 + [_vp]),
     "devo_patchify_backward": (_i, [_vp] * 3 + [_i] * 7 + [_vp]),
     "devo_pyramid_pack": (_i, [_vp, _vp] + [_i] * 6 + [_vp]),

@@ -77,13 +77,13 @@ def pack_gmap(gmap, out=None):
     return out
 
 
-def _cached(t, fn):
+def _cached(t, fn, tag=""):
     if not _USE_CACHE:
         return fn(t)
     # The entry keeps the SOURCE tensor alive: while it is cached its memory cannot be handed to another tensor, so an
     # equal (data_ptr, shape, dtype) can only be the same storage (views share the version counter).  Without that
     # reference a new tensor allocated at a recycled address with the same shape and version hit a stale entry.
-    key = (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t.dtype, t.device)
+    key = (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t.dtype, t.device, tag)
     hit = _pack_cache.get(key)
     if hit is not None and hit[0] == t._version:
         _pack_cache[key] = _pack_cache.pop(key)          # most recently used last
@@ -233,6 +233,16 @@ def backward(fmap1, fmap2, coords, ii, jj, corr_grad, radius):
     B, Np, C, P, _ = fmap1.shape
     _, Nf, _, H, W = fmap2.shape
     E = coords.shape[1]
+    if E > 0 and _split_eligible(fmap1, fmap2, coords, radius) and fmap2.dtype == torch.float32:
+        # training shape: pixel-major volumes, vector reductions (csrc/corr_bwd_pm.cu); the layout changes are plumbing
+        f2pm = _cached(fmap2, lambda t: t[0].permute(0, 2, 3, 1).contiguous(), tag="pm32")
+        g1pm = torch.zeros(Np, P * P, C, dtype=torch.float32, device=fmap1.device)
+        g2pm = torch.zeros(Nf, H, W, C, dtype=torch.float32, device=fmap1.device)
+        _lib.check(_lib.lib().devo_corr_backward_pm(fmap1.data_ptr(), f2pm.data_ptr(), coords.data_ptr(),
+                                                    ii.contiguous().data_ptr(), jj.contiguous().data_ptr(), grad.data_ptr(),
+                                                    g1pm.data_ptr(), g2pm.data_ptr(), Np, Nf, C, H, W, E,
+                                                    _lib.stream_ptr(fmap1.device)), "corr_backward_pm")
+        return [g1pm.permute(0, 2, 1).reshape(1, Np, C, P, P).contiguous(), g2pm.permute(0, 3, 1, 2).contiguous()[None]]
     g1 = torch.empty_like(fmap1)
     g2 = torch.empty_like(fmap2)
     _lib.check(_lib.lib().devo_corr_backward(fmap1.data_ptr(), fmap2.data_ptr(), coords.data_ptr(),

@@ -58,6 +58,13 @@ int devo_corr_backward(const void* fmap1, const void* fmap2, const float* coords
                        void* fmap1_grad, void* fmap2_grad, int dtype,
                        int B, int Np, int Nf, int C, int H, int W, int E, int P, int radius,
                        void* stream);
+/* The same backward on PIXEL-MAJOR float32 volumes (training shape: B = 1, P = 3, radius 3, C = 64 or 128): one warp per
+ * bounding-box pixel, one coalesced load and one 16-byte vector reduction per lane instead of C scalar atomics per pixel
+ * (csrc/corr_bwd_pm.cu).  fmap1 planar [Np,C,3,3]; fmap2_pm [Nf,H,W,C]; grad [E,7,7,3,3] as above; the two gradients are
+ * ACCUMULATED into fmap1_grad_pm [Np,9,C] and fmap2_grad_pm [Nf,H,W,C] (the caller zeroes them and converts the layouts). */
+int devo_corr_backward_pm(const float* fmap1, const float* fmap2_pm, const float* coords, const int64_t* ii,
+                          const int64_t* jj, const float* grad, float* fmap1_grad_pm, float* fmap2_grad_pm,
+                          int Np, int Nf, int C, int H, int W, int E, void* stream);
 /* cuda_corr.patchify_forward (correlation.cpp:60, correlation_kernel.cu:16-47,288-307)
  * net [B,C,H,W], coords [B,M,2] f32 -> patches [B,M,C,2r+2,2r+2] (fully written, OOB = 0). */
 int devo_patchify_forward(const void* net, const float* coords, void* patches, int dtype,

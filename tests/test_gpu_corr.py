@@ -165,6 +165,32 @@ def test_backward_vs_oracle(dtype, tol):
     assert _rel(g1, r1) <= tol and _rel(g2, r2) <= tol
 
 
+@pytest.mark.parametrize("C,spread", [(64, 4.0), (128, 4.0), (128, 1.0), (64, 40.0)])
+def test_backward_pixel_major_vs_oracle_and_generic(C, spread):
+    """float32 at the training shape takes csrc/corr_bwd_pm.cu (pixel-major volumes, vector reductions); spread 40 puts the
+    patch pixels so far apart that every pixel walks its own window (bounding box > 24 x 24)"""
+    from devo_b200 import cuda_corr
+    f1, f2, coords, ii, jj = _rand_problem(1, 12, 3, C, 20, 24, 60, 3, 11, torch.float32, spread=spread)
+    g = torch.randn(1, 60, 7, 7, 3, 3)
+    r1, r2 = ocorr.corr_backward(f1, f2, coords, ii, jj, g, 3)
+    a = (f1.cuda(), f2.cuda(), coords.cuda(), ii.cuda(), jj.cuda(), g.cuda())
+    assert cuda_corr._split_eligible(a[0], a[1], a[2], 3)
+    g1, g2 = cuda_corr.backward(*a, 3)
+    assert g1.shape == f1.shape and g2.shape == f2.shape and g1.is_contiguous() and g2.is_contiguous()
+    assert _rel(g1, r1) <= 2e-5 and _rel(g2, r2) <= 2e-5
+    cuda_corr._FORCE_GENERIC = True
+    try:
+        h1, h2 = cuda_corr.backward(*a, 3)
+    finally:
+        cuda_corr._FORCE_GENERIC = False
+    assert _rel(g1, h1) <= 2e-5 and _rel(g2, h2) <= 2e-5
+    # no edges, and an edge list that only reaches out-of-bounds windows
+    e1, e2 = cuda_corr.backward(a[0], a[1], a[2][:, :0], a[3][:0], a[4][:0], a[5][:, :0], 3)
+    assert float(e1.abs().max()) == 0 and float(e2.abs().max()) == 0
+    z1, z2 = cuda_corr.backward(a[0], a[1], a[2] + 1000.0, a[3], a[4], a[5], 3)
+    assert float(z1.abs().max()) == 0 and float(z2.abs().max()) == 0
+
+
 def test_autograd_wrappers():
     from devo_b200 import altcorr
     f1, f2, coords, ii, jj = _rand_problem(1, 6, 2, 8, 12, 14, 20, 3, 9, torch.float32)

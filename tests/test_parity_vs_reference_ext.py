@@ -72,6 +72,24 @@ def test_corr_backward_fp32_vs_reference():
     assert _rel(o1, r1) <= 1e-4 and _rel(o2, r2) <= 1e-4
 
 
+def test_corr_backward_pixel_major_fp32_vs_reference():
+    """C = 128 float32: the pixel-major backward (csrc/corr_bwd_pm.cu) against the reference's own kernel, both pyramid
+    levels, reprojected and out-of-bounds-stress coordinates"""
+    ref = _ref("cuda_corr_ref")
+    from devo_b200 import cuda_corr
+    Pm = corr_problem(n_frames=4, patches_per_frame=48, seed=2, dtype=torch.float32)
+    stress = corr_problem(n_frames=4, patches_per_frame=48, seed=2, dtype=torch.float32, oob_stress=True)["coords"]
+    g = torch.randn(1, Pm["kk"].numel(), 7, 7, 3, 3, device="cuda")
+    for lvl, s in enumerate((1, 4)):
+        for coords in (Pm["coords"], stress):
+            a = (Pm["gmap"].cuda(), Pm["pyramid"][lvl].cuda(), (coords / s).cuda(), Pm["kk"].cuda(), Pm["jj"].cuda())
+            assert cuda_corr._split_eligible(a[0], a[1], a[2], 3)
+            r1, r2 = ref.backward(*a, g, 3)
+            o1, o2 = cuda_corr.backward(*a, g, 3)
+            assert o1.shape == r1.shape and o2.shape == r2.shape
+            assert _rel(o1, r1) <= 1e-4 and _rel(o2, r2) <= 1e-4, (_rel(o1, r1), _rel(o2, r2))
+
+
 @pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
 def test_patchify_bit_exact_vs_reference(dtype):
     ref = _ref("cuda_corr_ref")
