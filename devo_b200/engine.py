@@ -112,14 +112,21 @@ class UpdateOperator:
         from .update import tile_local_graph
         self.tile_local = self.gru_mode == "mma" and tile_local_graph(self.plan_kk)
 
-    def refresh_pair_key(self, same_graph=False):
+    def refresh_pair_key(self, same_graph=False, overlap=False):
         """(re)compute the frame-pair key of SoftAgg's second grouping from ii / jj -- after set_graph, or after the caller
         refreshed `state_arena` (which carries the edge list).  `same_graph`: the caller vouches that the refreshed edge
         list is the one set_graph installed; otherwise what set_graph verified about it (`tile_local`) is dropped.
         The reference uses ii * 12345 + jj (enet.py:96); any key that orders the pairs the same way gives the same groups,
         and ii * Nf + jj needs 6 bits instead of 17: half the radix passes of the plan, whose width the engine fixes
         through the bound Nf * Nf it passes to GraphPlan."""
-        torch.add(self.ii * self.Nf, self.jj, out=self.pair_key)
+        if overlap:
+            # the key's only reader is the frame-pair plan, which the next iteration builds on `_side2`: computed there, the
+            # key is off the critical path (reprojection and lookup do not wait for it)
+            self._side2.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self._side2):
+                torch.add(self.jj, self.ii, alpha=self.Nf, out=self.pair_key)
+        else:
+            torch.add(self.jj, self.ii, alpha=self.Nf, out=self.pair_key)
         if not same_graph:
             self.tile_local = False
 
