@@ -26,6 +26,7 @@
 // Patch pixels whose window does not fit in the 11x11 box (reprojection scale > ~1.5x) take a
 // per-output direct path inside the same kernel.
 #include <cuda.h>
+#include <stdlib.h>
 #include <type_traits>
 #include "common.cuh"
 
@@ -102,6 +103,7 @@ struct FastParams {
   const void* gmap_pm;
   const void* level[DEVO_MAX_LEVELS];
   int C;
+  int l2_hint;                              // 1: pyramid boxes are loaded with an L2 evict-first hint
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -183,6 +185,21 @@ __device__ __forceinline__ void tma_load_4d_elect(uint32_t dst, const CUtensorMa
       "elect.sync _|q, 0xffffffff;\n\t"
       "@q cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t"
       "}" ::"r"(dst), "l"((uint64_t)map), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// the same load with an L2 eviction-priority hint (createpolicy)
+__device__ __forceinline__ void tma_load_4d_elect_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar_addr, int c0, int c1, int c2,
+                                                       int c3, uint64_t policy) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;\n\t"
+      "}" ::"r"(dst), "l"((uint64_t)map), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
 }
 __device__ __forceinline__ void tma_load_3d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar_addr, int c0, int c1, int c2) {
   asm volatile(
@@ -400,6 +417,7 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
     ItemCursor c;
     c.init(first, L, warp);
     CT_DECL
+    const uint64_t l2pol = l2_policy_evict_first();
     uint32_t stage = warp % kStages, phase = (warp / kStages) & 1;
     for (; c.it < nitems; c.advance(kProducers, L)) {
       if (warp == 0) {
@@ -434,12 +452,15 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
         const uint32_t fb = smem_u32(&full[stage]);
         CT_WAIT(1, mbar_wait(&empty[stage], phase ^ 1));
         mbar_arrive_expect_tx_elect(fb, bytes);
-        tma_load_4d_elect(st, tm, fb, 0, g.x0, g.y0, frame);
-        tma_load_3d_elect(st + 2 * kATileBytes, &tm_g, fb, 0, 0, patch);
-        if (khalves == 2) {
-          tma_load_4d_elect(st + kATileBytes, tm, fb, 64, g.x0, g.y0, frame);
-          tma_load_3d_elect(st + 2 * kATileBytes + kBTileBytes, &tm_g, fb, 64, 0, patch);
+        if (prm.l2_hint) {       // pyramid boxes marked evict-first: they displace each other, not the update operator's set
+          tma_load_4d_elect_hint(st, tm, fb, 0, g.x0, g.y0, frame, l2pol);
+          if (khalves == 2) tma_load_4d_elect_hint(st + kATileBytes, tm, fb, 64, g.x0, g.y0, frame, l2pol);
+        } else {
+          tma_load_4d_elect(st, tm, fb, 0, g.x0, g.y0, frame);
+          if (khalves == 2) tma_load_4d_elect(st + kATileBytes, tm, fb, 64, g.x0, g.y0, frame);
         }
+        tma_load_3d_elect(st + 2 * kATileBytes, &tm_g, fb, 0, 0, patch);
+        if (khalves == 2) tma_load_3d_elect(st + 2 * kATileBytes + kBTileBytes, &tm_g, fb, 64, 0, patch);
       }
       stage += kProducers;
       while (stage >= kStages) { stage -= kStages; phase ^= 1; }
@@ -944,6 +965,13 @@ static int lookup_fused_impl(const void* gmap_pm, const devo_pyramid_t* pyr, con
   prm.coords = coords; prm.ii = ii; prm.jj = jj; prm.out = out; prm.gmap_pm = gmap_pm;
   prm.ld_out = ld_out > 0 ? ld_out : kOut * kOut * kPP * pyr->n_levels;
   prm.out_mode = out_mode; prm.out_scale = out_scale;
+  // Pyramid boxes are read with an L2 evict-first hint (DEVO_CORR_L2_HINT=0 turns it off): the lookup streams ~50 MB per
+  // update, and as normal-priority lines these displaced the update operator's ~60 MB working set (weights, state,
+  // workspace) from L2 every iteration -- the operator then ran 15 us slower (tools/gru_cold_probe.py).  Marked evict-first
+  // the boxes replace each other instead.  Back-to-back steps: 213 -> 198 us; with the bench's L2 flush between steps the
+  // step time is unchanged (the lookup alone, after a flush, is 4 us slower: flush lines outrank the boxes).
+  static const int l2_hint_env = [] { const char* e = getenv("DEVO_CORR_L2_HINT"); return e ? atoi(e) : 1; }();
+  prm.l2_hint = l2_hint_env;
   DEVO_REQUIRE(prm.ld_out >= kOut * kOut * kPP * pyr->n_levels, DEVO_EINVAL, "corr_lookup_fused: ld_out too small");
   {
     cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)kPP, (cuuint64_t)Np};
