@@ -31,7 +31,8 @@ def _idx(t, name):
 
 
 def prepare(E, n_free, status, workspace):
-    """housekeeping of the next `forward_async(..., prepared=True)` on this workspace / status word (two memsets), on the
+    """housekeeping of the next `forward_async(..., prepared=True)` on this workspace / status word (status and ticket
+    area cleared by one small kernel -- no copy-engine node inside a captured step), on the
     CURRENT stream -- call it wherever it is off the critical path and make that stream precede the BA"""
     _lib.check(_lib.lib().devo_ba_prepare(workspace.data_ptr(), workspace.numel(), int(E), int(n_free), status.data_ptr(),
                                           _lib.stream_ptr(workspace.device)), "ba_prepare")

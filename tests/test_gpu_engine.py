@@ -106,3 +106,34 @@ def test_state_arena_refresh_path_equals_set_graph_path():
     assert torch.equal(op.poses, a_poses) and torch.equal(op.patches, a_patches) and torch.equal(op.get_net(), a_net)
     nf = op.Nf
     assert int(op.plan_ij.ngroups.item()) == torch.unique(op.ii * nf + op.jj).numel()
+
+
+def test_kernel_copy_and_ba_prepare_leave_no_copy_engine_work():
+    """`_lib.copy_` (devo_copy_bytes) copies any byte count -- 16-byte vectors when pointers and size allow, bytes otherwise --
+    and `cuda_ba.prepare` clears the status word and the ticket area of the workspace; both are kernels (counted by the
+    library's launch counter), so a captured step holds no memset / memcpy nodes that would queue behind host uploads"""
+    from devo_b200 import _lib, cuda_ba
+    g = torch.Generator(device="cuda").manual_seed(3)
+    src = torch.randint(0, 255, (1 << 20,), dtype=torch.uint8, device="cuda", generator=g)
+    for off_s, off_d, n in ((0, 0, 1 << 20), (0, 0, 4096 + 16), (1, 0, 1000), (0, 3, 77), (16, 32, 48), (5, 5, 1)):
+        dst = torch.zeros(1 << 20, dtype=torch.uint8, device="cuda")
+        l0 = _lib.launch_count()
+        _lib.copy_(dst[off_d:off_d + n], src[off_s:off_s + n])
+        assert _lib.launch_count() == l0 + 1
+        assert torch.equal(dst[off_d:off_d + n], src[off_s:off_s + n])
+        assert int(dst[:off_d].sum()) == 0 and int(dst[off_d + n:].sum()) == 0
+    _lib.copy_(dst[:0], src[:0])                                     # nothing to do
+    with pytest.raises(RuntimeError):
+        _lib.copy_(dst[:8], src[:9])
+    with pytest.raises(RuntimeError):
+        _lib.copy_(dst[:8].view(torch.float32), src[:8])
+    E, nfree = 6144, 7
+    ws = torch.full((int(_lib.lib().devo_ba_workspace(E, nfree)),), 255, dtype=torch.uint8, device="cuda")
+    status = torch.full((1,), 7, dtype=torch.int32, device="cuda")
+    before = ws.clone()
+    l0 = _lib.launch_count()
+    cuda_ba.prepare(E, nfree, status, ws)
+    assert _lib.launch_count() == l0 + 1
+    assert int(status) == 0
+    changed = (ws != before).nonzero().flatten()
+    assert changed.numel() == 128 and int(changed[-1] - changed[0]) == 127 and int(ws[changed].sum()) == 0
