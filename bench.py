@@ -690,7 +690,7 @@ def run_ours(args, rank, world, local_rank):
     return line
 
 
-def run_e2e(op, wl, dev, steps, probe=False, h2d_frac=1.0, chunks=1, light_body=False):
+def run_e2e(op, wl, dev, steps, probe=False, h2d_frac=1.0, chunks=1, light_body=False, d2h_kernel=True):
     """The same step as `value` (ingest of the newly arrived frame + one update iteration), end to end from HOST buffers:
 
       copy stream     ONE H2D copy per step of a pinned host arena -- the new frame's features (fmap, gmap, imap: sensor data,
@@ -753,7 +753,11 @@ def run_e2e(op, wl, dev, steps, probe=False, h2d_frac=1.0, chunks=1, light_body=
             return
         # D2H of the result, a node of the step's graph: the geometry block of the state arena (updated poses + patches,
         # contiguous), straight into pinned memory -- no packing kernels in front of it
-        out_host[b].copy_(op.state_arena[:geom_bytes], non_blocking=True)
+        if d2h_kernel:      # the same bytes written by a copy KERNEL into the (UVA-mapped) pinned buffer: no copy-engine node
+            _lib.check(_lib.lib().devo_copy_bytes(out_host[b].data_ptr(), op.state_arena.data_ptr(), geom_bytes,
+                                                  _lib.stream_ptr(dev)), "copy_bytes (D2H)")
+        else:
+            out_host[b].copy_(op.state_arena[:geom_bytes], non_blocking=True)
 
     with torch.no_grad():
         side = torch.cuda.Stream(device=dev)
@@ -843,7 +847,7 @@ def run_e2e(op, wl, dev, steps, probe=False, h2d_frac=1.0, chunks=1, light_body=
                 note="host pinned inputs every step: ONE H2D copy of the new frame's features + poses, patches, intrinsics and "
                      "edge list (copy stream, double-buffered staging; the recurrent hidden state stays on the device, as in the "
                      "reference); one CUDA-graph replay (state refresh, ingest, plans, update iteration, D2H of the updated "
-                     "poses + patches into pinned memory); wall clock between device synchronisations, <= 2 steps in flight; runs of "
+                     "poses + patches into pinned memory, written there by a copy kernel of the same graph); wall clock between device synchronisations, <= 2 steps in flight; runs of "
                      "`steps` steps until three in a row agree within 3 % (<= 12 runs), median of those three")
 
 
