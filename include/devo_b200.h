@@ -168,7 +168,7 @@ int devo_ba_forward_planned(float* poses, float* patches, const float* intrinsic
                             void* workspace, size_t workspace_bytes, int32_t* status, void* stream);
 
 /* The same call with its housekeeping off the critical path (used by the engine; no reference counterpart).
- * devo_ba_prepare: the two memsets of a call (status word, 128-byte ticket area of the workspace), on any stream that
+ * devo_ba_prepare: the two clears of a call (status word, 128-byte ticket area of the workspace; one small kernel), on any stream that
  * is made to precede the BA.  devo_ba_forward_prepared: after a prepare for this workspace / status, launches nothing
  * but the iterations (+ the final depth update); the caller vouches that the plan arrays are older than the kernel
  * preceding the call in `stream`, so they are read ahead of the programmatic dependent-launch wait from the first
