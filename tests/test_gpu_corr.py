@@ -260,6 +260,38 @@ def test_full_size_properties_s8():
     assert _rel(out[sel.cuda()], ref) <= 2e-3
 
 
+def test_backward_full_size_properties_s8_float32():
+    """the pixel-major backward at full size (E = 6144, 160x120 and 40x30, C = 128, float32), through size-independent
+    properties: the lookup is bilinear in (fmap1, fmap2), so <corr(f1, f2), g> = <f1, d/df1> = <f2, d/df2> (adjoint
+    identity, forward in float64-accumulated reference on a sample; here against this library's float32 forward);
+    linearity in the incoming gradient; exact zero for windows that lie outside the image"""
+    from devo_b200 import cuda_corr
+    Pm = corr_problem(seed=1234, dtype=torch.float32)
+    f1 = Pm["gmap"].cuda()
+    ii, jj = Pm["kk"].cuda(), Pm["jj"].cuda()
+    E = ii.numel()
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for lvl, s in enumerate((1, 4)):
+        f2 = Pm["pyramid"][lvl].cuda()
+        coords = (Pm["coords"] / s).cuda()
+        assert cuda_corr._split_eligible(f1, f2, coords, 3)
+        g = torch.randn(1, E, 7, 7, 3, 3, device="cuda", generator=gen)
+        h = torch.randn(1, E, 7, 7, 3, 3, device="cuda", generator=gen)
+        (out,) = cuda_corr.forward(f1, f2, coords, ii, jj, 3)
+        g1, g2 = cuda_corr.backward(f1, f2, coords, ii, jj, g, 3)
+        assert torch.isfinite(g1).all() and torch.isfinite(g2).all()
+        lhs = (out.double() * g.double()).sum().item()
+        a1 = (f1.double() * g1.double()).sum().item()
+        a2 = (f2.double() * g2.double()).sum().item()
+        scale = (out.double() * g.double()).abs().sum().item()
+        assert abs(lhs - a1) <= 1e-5 * scale and abs(lhs - a2) <= 1e-5 * scale, (lhs, a1, a2, scale)
+        h1, h2 = cuda_corr.backward(f1, f2, coords, ii, jj, h, 3)
+        c1, c2 = cuda_corr.backward(f1, f2, coords, ii, jj, 2.0 * g - 0.5 * h, 3)
+        assert _rel(c1, 2.0 * g1 - 0.5 * h1) <= 2e-5 and _rel(c2, 2.0 * g2 - 0.5 * h2) <= 2e-5
+        z1, z2 = cuda_corr.backward(f1, f2, coords + 5000.0, ii, jj, g, 3)
+        assert z1.abs().max().item() == 0.0 and z2.abs().max().item() == 0.0
+
+
 def test_pack_cache_is_not_fooled_by_recycled_addresses():
     """the drop-in cuda_corr.forward caches the pixel-major copy of its inputs; a NEW tensor that the caching allocator
     places at the address of a freed one (same shape, same version counter) must not hit the old entry"""
