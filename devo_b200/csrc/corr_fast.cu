@@ -103,7 +103,7 @@ struct FastParams {
   const void* gmap_pm;
   const void* level[DEVO_MAX_LEVELS];
   int C;
-  int l2_hint;                              // 1: pyramid boxes are loaded with an L2 evict-first hint
+  int l2_hint;                              // bit l: the boxes of level l are loaded with an L2 evict-first hint
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fast_kernel(
         const uint32_t fb = smem_u32(&full[stage]);
         CT_WAIT(1, mbar_wait(&empty[stage], phase ^ 1));
         mbar_arrive_expect_tx_elect(fb, bytes);
-        if (prm.l2_hint) {       // pyramid boxes marked evict-first: they displace each other, not the update operator's set
+        if ((prm.l2_hint >> c.l) & 1) {       // pyramid boxes marked evict-first: they displace each other, not the update operator's set
           tma_load_4d_elect_hint(st, tm, fb, 0, g.x0, g.y0, frame, l2pol);
           if (khalves == 2) tma_load_4d_elect_hint(st + kATileBytes, tm, fb, 64, g.x0, g.y0, frame, l2pol);
         } else {
@@ -971,7 +971,7 @@ static int lookup_fused_impl(const void* gmap_pm, const devo_pyramid_t* pyr, con
   // the boxes replace each other instead.  Back-to-back steps: 213 -> 198 us; with the bench's L2 flush between steps the
   // step time is unchanged (the lookup alone, after a flush, is 4 us slower: flush lines outrank the boxes).
   static const int l2_hint_env = [] { const char* e = getenv("DEVO_CORR_L2_HINT"); return e ? atoi(e) : 1; }();
-  prm.l2_hint = l2_hint_env;
+  prm.l2_hint = 0;     // (filled per level below: mode 1 = every level, mode 2 = only levels of >= 8 MB)
   DEVO_REQUIRE(prm.ld_out >= kOut * kOut * kPP * pyr->n_levels, DEVO_EINVAL, "corr_lookup_fused: ld_out too small");
   {
     cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)kPP, (cuuint64_t)Np};
@@ -985,6 +985,8 @@ static int lookup_fused_impl(const void* gmap_pm, const devo_pyramid_t* pyr, con
     DEVO_REQUIRE(((uintptr_t)pyr->level[ls] & 15) == 0, DEVO_EINVAL, "corr_lookup_fused: level %d not 16-byte aligned", ls);
     DEVO_REQUIRE(pyr->scale[ls] > 0.f, DEVO_EINVAL, "corr_lookup_fused: level %d scale must be > 0", ls);
     prm.H[l] = pyr->H[ls]; prm.W[l] = pyr->W[ls]; prm.scale[l] = pyr->scale[ls]; prm.level[l] = pyr->level[ls];
+    if (l < pyr->n_levels && (l2_hint_env == 1 || (l2_hint_env == 2 && (size_t)Nf * pyr->H[ls] * pyr->W[ls] * C * 2 >= ((size_t)8 << 20))))
+      prm.l2_hint |= 1 << l;
     {
       int ex = 0;
       const float m = frexpf(pyr->scale[ls], &ex);

@@ -1,4 +1,4 @@
-for h in 0 1 0 1; do
+for h in 0 1 2 0 1 2; do
 DEVO_CORR_L2_HINT=$h timeout 300 python bench.py 2>/dev/null > gpurun_out/ab_$h.json
 python - <<PY
 import json
