@@ -11,7 +11,8 @@
 //   * the frame pixel is ONE coalesced C*4-byte load, its gradient ONE vector reduction (red.global.add.v4.f32) per lane:
 //     C/4 16-byte reductions per box pixel instead of C scalar ones, each sector touched once;
 //   * the patch features live in registers (9 x C/32 per lane), so does the patch-feature gradient, which is summed over
-//     the box pixels in registers, over the CTA's warps in shared memory and leaves as 9*C/4 vector reductions per edge.
+//     the box pixels in registers, over the CTA's warps in shared memory and leaves as 9*C/4 vector reductions per edge;
+//   * which of the nine windows cover a box pixel, and with which weight, is tabulated once per edge in shared memory.
 // The transposed bilinear blend (grad of the 7x7 outputs -> grad of the 8x8 window values) is the same arithmetic as in
 // csrc/corr.cu.  Host side (cuda_corr.backward): pixel-major copies in / planar copies out are layout plumbing.
 #include "common.cuh"
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(kThreads) corr_backward_pm_kernel(
   constexpr int C = 32 * VEC;
   __shared__ float gV[PP * DD];            // [p][a (row)][b (col)]: gradient of the 8x8 window values
   __shared__ float f1s[C * PP];            // planar copy of the patch features, later reused as the g1 accumulator [p][C]
+  __shared__ __align__(16) float wtab[kMaxBoxArea * 12];   // per box pixel: nine window weights + a "covered" flag
   __shared__ int gx[PP], gy[PP];
   __shared__ float fdx[PP], fdy[PP];
   __shared__ int s_box[4];
@@ -104,44 +106,51 @@ __global__ void __launch_bounds__(kThreads) corr_backward_pm_kernel(
   const int x0 = s_box[0], y0 = s_box[1], bw = s_box[2], bh = s_box[3];
   if ((long long)bw * bh <= kMaxBoxArea) {
     const int npx = bw * bh;
-    // one box pixel per warp and round; the next round's pixel is requested before this round's arithmetic
-    float cur[VEC] = {}, nxt[VEC] = {};
-    int q = warp;
-    bool cur_in = false;
-    if (q < npx) {
+    // weight table of the box: wtab[q] = {w_0 .. w_8, covered, -, -} for box pixel q, w_p = gV[p][.][.] where pixel q lies in
+    // patch pixel p's 8x8 window, else 0; `covered` = 0 for a pixel outside the image or outside all nine windows.  Built
+    // once by the whole CTA: the per-pixel loop below is 3 shared-memory loads + 72 FMAs, no index arithmetic per window.
+    for (int idx = tid; idx < npx * 10; idx += kThreads) {
+      const int q = idx / 10, p = idx - q * 10;
       const int i1 = y0 + q / bw, j1 = x0 + q % bw;
-      cur_in = (i1 >= 0 && i1 < H && j1 >= 0 && j1 < W);
-      if (cur_in) load_vec(f2 + ((size_t)i1 * W + j1) * C, cur);
-    }
-    for (; q < npx; q += kWarps) {
-      const int i1 = y0 + q / bw, j1 = x0 + q % bw;
-      const int qn = q + kWarps;
-      bool nxt_in = false;
-      if (qn < npx) {
-        const int i2 = y0 + qn / bw, j2 = x0 + qn % bw;
-        nxt_in = (i2 >= 0 && i2 < H && j2 >= 0 && j2 < W);
-        if (nxt_in) load_vec(f2 + ((size_t)i2 * W + j2) * C, nxt);
+      const bool in_img = (i1 >= 0 && i1 < H && j1 >= 0 && j1 < W);
+      float w = 0.f;
+      if (p < PP) {
+        const int a = i1 - (gy[p] - R), bb = j1 - (gx[p] - R);
+        if (in_img && a >= 0 && a < D && bb >= 0 && bb < D) w = gV[p * DD + a * D + bb];
+      } else if (in_img) {
+#pragma unroll
+        for (int pp = 0; pp < PP; pp++) {
+          const int a = i1 - (gy[pp] - R), bb = j1 - (gx[pp] - R);
+          if (a >= 0 && a < D && bb >= 0 && bb < D) w = 1.f;
+        }
       }
-      if (cur_in) {
+      wtab[q * 12 + p] = w;
+    }
+    __syncthreads();
+    // one box pixel per warp and round; the pixels of the next two rounds are requested before this round's arithmetic
+    float cur[VEC] = {}, nx1[VEC] = {}, nx2[VEC] = {};
+    auto request = [&](int q, float (&dst)[VEC]) {
+      if (q < npx && wtab[q * 12 + 9] != 0.f) load_vec(f2 + ((size_t)(y0 + q / bw) * W + (x0 + q % bw)) * C, dst);
+    };
+    request(warp, cur);
+    request(warp + kWarps, nx1);
+    for (int q = warp; q < npx; q += kWarps) {
+      request(q + 2 * kWarps, nx2);
+      const float4* wt = reinterpret_cast<const float4*>(wtab + q * 12);
+      const float4 wa = wt[0], wb = wt[1], wc = wt[2];
+      if (wc.y != 0.f) {                                      // warp-uniform
+        const float w[PP] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x};
         float o[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; v++) o[v] = 0.f;
-        bool any = false;
 #pragma unroll
-        for (int p = 0; p < PP; p++) {
-          const int a = i1 - (gy[p] - R), bb = j1 - (gx[p] - R);
-          if (a >= 0 && a < D && bb >= 0 && bb < D) {          // warp-uniform
-            const float w = gV[p * DD + a * D + bb];
-            any = true;
+        for (int p = 0; p < PP; p++)
 #pragma unroll
-            for (int v = 0; v < VEC; v++) { o[v] = fmaf(w, f1r[p][v], o[v]); acc[p][v] = fmaf(w, cur[v], acc[p][v]); }
-          }
-        }
-        if (any) red_add(o2 + ((size_t)i1 * W + j1) * C, o);
+          for (int v = 0; v < VEC; v++) { o[v] = fmaf(w[p], f1r[p][v], o[v]); acc[p][v] = fmaf(w[p], cur[v], acc[p][v]); }
+        red_add(o2 + ((size_t)(y0 + q / bw) * W + (x0 + q % bw)) * C, o);
       }
-      cur_in = nxt_in;
 #pragma unroll
-      for (int v = 0; v < VEC; v++) cur[v] = nxt[v];
+      for (int v = 0; v < VEC; v++) { cur[v] = nx1[v]; nx1[v] = nx2[v]; }
     }
   } else {
     // degenerate geometry: each patch pixel walks its own 8x8 window
