@@ -15,13 +15,14 @@
 //   * which of the nine windows cover a box pixel, and with which weight, is tabulated once per edge in shared memory.
 // The transposed bilinear blend (grad of the 7x7 outputs -> grad of the 8x8 window values) is the same arithmetic as in
 // csrc/corr.cu.  Host side (cuda_corr.backward): pixel-major copies in / planar copies out are layout plumbing.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
 
 constexpr int kThreads = 256, kWarps = kThreads / 32;
 constexpr int R = 3, D = 2 * R + 2, Dm = D - 1, PP = 9, DD = D * D;
-constexpr int kMaxBoxArea = 24 * 24;      // beyond that (patch pixels far apart) every patch pixel walks its own window
+constexpr int kMaxBoxArea = 20 * 20;      // beyond that (patch pixels far apart) every patch pixel walks its own window
 
 template <int VEC> struct Vec;
 template <> struct Vec<4> { using type = float4; };
@@ -33,6 +34,18 @@ __device__ __forceinline__ void red_add(float* p, const float (&v)[4]) {
 __device__ __forceinline__ void red_add(float* p, const float (&v)[2]) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v[0]), "f"(v[1]) : "memory");
 }
+// bulk reduction shared -> global (TMA unit, `cp.reduce.async.bulk ... add.f32`): ONE instruction adds a pixel's C floats
+__device__ __forceinline__ void bulk_red_add(float* gdst, const float* ssrc, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+               ::"l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void store_vec(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+__device__ __forceinline__ void store_vec(float* p, const float (&v)[2]) { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+constexpr int kSlots = 4;                 // per-warp ring of staged pixels for the bulk reductions
+
 __device__ __forceinline__ void load_vec(const float* p, float (&v)[4]) {
   const float4 t = __ldg(reinterpret_cast<const float4*>(p));
   v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -43,7 +56,7 @@ __device__ __forceinline__ void load_vec(const float* p, float (&v)[2]) {
 }
 
 // grid = E.  f1: planar [Np][C][9]; f2pm: [Nf][H][W][C]; grad: [E][7 (x-off)][7 (y-off)][9]; g1pm: [Np][9][C]; g2pm like f2pm.
-template <int VEC>
+template <int VEC, bool BULK>
 __global__ void __launch_bounds__(kThreads) corr_backward_pm_kernel(
     const float* __restrict__ f1, const float* __restrict__ f2pm, const float* __restrict__ coords,
     const int64_t* __restrict__ ii, const int64_t* __restrict__ jj, const float* __restrict__ grad,
@@ -52,6 +65,7 @@ __global__ void __launch_bounds__(kThreads) corr_backward_pm_kernel(
   __shared__ float gV[PP * DD];            // [p][a (row)][b (col)]: gradient of the 8x8 window values
   __shared__ float f1s[C * PP];            // planar copy of the patch features, later reused as the g1 accumulator [p][C]
   __shared__ __align__(16) float wtab[kMaxBoxArea * 12];   // per box pixel: nine window weights + a "covered" flag
+  __shared__ __align__(16) float ring[BULK ? kWarps * kSlots * C : 4];   // BULK: staged pixel gradients (source of the bulk reductions)
   __shared__ int gx[PP], gy[PP];
   __shared__ float fdx[PP], fdy[PP];
   __shared__ int s_box[4];
@@ -134,6 +148,7 @@ __global__ void __launch_bounds__(kThreads) corr_backward_pm_kernel(
     };
     request(warp, cur);
     request(warp + kWarps, nx1);
+    int slot = 0;
     for (int q = warp; q < npx; q += kWarps) {
       request(q + 2 * kWarps, nx2);
       const float4* wt = reinterpret_cast<const float4*>(wtab + q * 12);
@@ -147,7 +162,21 @@ __global__ void __launch_bounds__(kThreads) corr_backward_pm_kernel(
         for (int p = 0; p < PP; p++)
 #pragma unroll
           for (int v = 0; v < VEC; v++) { o[v] = fmaf(w[p], f1r[p][v], o[v]); acc[p][v] = fmaf(w[p], cur[v], acc[p][v]); }
-        red_add(o2 + ((size_t)(y0 + q / bw) * W + (x0 + q % bw)) * C, o);
+        float* gdst = o2 + ((size_t)(y0 + q / bw) * W + (x0 + q % bw)) * C;
+        if constexpr (BULK) {
+          // stage the pixel in this warp's ring slot; lane 0 hands the 4*C bytes to the TMA unit as one reduction.  The slot
+          // was the source of the bulk group issued kSlots pixels ago: at most kSlots - 1 younger groups may still be reading.
+          float* sl = ring + (warp * kSlots + slot) * C;
+          if (lane == 0) bulk_wait_read<kSlots - 1>();
+          __syncwarp();
+          store_vec(sl + lane * VEC, o);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) { bulk_red_add(gdst - lane * VEC, sl, C * 4); bulk_commit(); }
+          slot = (slot + 1) % kSlots;
+        } else {
+          red_add(gdst, o);
+        }
       }
 #pragma unroll
       for (int v = 0; v < VEC; v++) { cur[v] = nx1[v]; nx1[v] = nx2[v]; }
@@ -177,6 +206,14 @@ __global__ void __launch_bounds__(kThreads) corr_backward_pm_kernel(
     for (int v = 0; v < VEC; v++) atomicAdd(&f1s[p * C + lane * VEC + v], acc[p][v]);
   __syncthreads();
   float* o1 = g1pm + (size_t)ix * PP * C;
+  if constexpr (BULK) {
+    // the CTA's [9][C] patch-feature gradient is contiguous in shared memory and in g1pm: one bulk reduction
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) { bulk_red_add(o1, f1s, PP * C * 4); bulk_commit(); }
+    if (lane == 0) bulk_wait_read<0>();       // every issuing lane: its sources must outlive the reads
+    return;
+  }
   for (int q = tid; q < PP * 32; q += kThreads) {
     float o[VEC];
 #pragma unroll
@@ -196,10 +233,11 @@ extern "C" int devo_corr_backward_pm(const float* fmap1, const float* fmap2_pm, 
                "corr_backward_pm: pixel-major buffers must be 16-byte aligned");
   if (E == 0) return DEVO_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  if (C == 128)
-    corr_backward_pm_kernel<4><<<E, kThreads, 0, s>>>(fmap1, fmap2_pm, coords, ii, jj, grad, fmap1_grad_pm, fmap2_grad_pm, Np, Nf, H, W);
-  else
-    corr_backward_pm_kernel<2><<<E, kThreads, 0, s>>>(fmap1, fmap2_pm, coords, ii, jj, grad, fmap1_grad_pm, fmap2_grad_pm, Np, Nf, H, W);
+  static const int bulk = [] { const char* e = getenv("DEVO_CORR_BWD_BULK"); return e ? atoi(e) : 0; }();
+#define BWD(VEC, BULK) corr_backward_pm_kernel<VEC, BULK><<<E, kThreads, 0, s>>>(fmap1, fmap2_pm, coords, ii, jj, grad, fmap1_grad_pm, fmap2_grad_pm, Np, Nf, H, W)
+  if (C == 128) { if (bulk) BWD(4, true); else BWD(4, false); }
+  else { if (bulk) BWD(2, true); else BWD(2, false); }
+#undef BWD
   DEVO_LAUNCH_CHECK("corr_backward_pm");
   return DEVO_OK;
 }

@@ -168,7 +168,7 @@ def test_backward_vs_oracle(dtype, tol):
 @pytest.mark.parametrize("C,spread", [(64, 4.0), (128, 4.0), (128, 1.0), (64, 40.0)])
 def test_backward_pixel_major_vs_oracle_and_generic(C, spread):
     """float32 at the training shape takes csrc/corr_bwd_pm.cu (pixel-major volumes, vector reductions); spread 40 puts the
-    patch pixels so far apart that every pixel walks its own window (bounding box > 24 x 24)"""
+    patch pixels so far apart that every pixel walks its own window (bounding box > 20 x 20)"""
     from devo_b200 import cuda_corr
     f1, f2, coords, ii, jj = _rand_problem(1, 12, 3, C, 20, 24, 60, 3, 11, torch.float32, spread=spread)
     g = torch.randn(1, 60, 7, 7, 3, 3)
