@@ -614,6 +614,7 @@ def run_ours(args, rank, world, local_rank):
     achieved = alg / (k_ms * 1e-3) / 1e9
     roofline_corr = dict(bound="hbm", kernel="corr_fast_kernel (devo_corr_lookup_fused)", achieved=round(achieved, 1),
                     peak=peak, unit="GB/s", frac=round(achieved / peak, 4), traffic=ncu_traffic_bytes(),
+                    traffic_source="profiles/corr_fast_traffic.json: dram bytes of one `ncu --set full` capture of this kernel (tools/ncu_traffic.py), not of this run",
                     algorithmic_bytes=alg, kernel_ms=round(k_ms, 5), peak_source=peak_src,
                     note="window gathers overlap ~6x: L2->SM bytes, not HBM bytes, bound this kernel (DESIGN.md)")
 
@@ -649,7 +650,9 @@ def run_ours(args, rank, world, local_rank):
         roofline_gru = dict(bound="tensor", kernel=("gru_mma_kernel x2 + segment_softmax_sum x1 (devo_gru_update, tile-local edge list)" if op.tile_local
                                     else "gru_mma_kernel x5 + segment_softmax_sum x2 (devo_gru_update)"),
                             achieved=round(fl / (g_ms * 1e-3) / 1e12, 2), peak=tpeak, unit="TFLOP/s",
-                            frac=round(fl / (g_ms * 1e-3) / 1e12 / tpeak, 4), traffic=ncu_traffic_bytes("gru"), flops=fl,
+                            frac=round(fl / (g_ms * 1e-3) / 1e12 / tpeak, 4), traffic=ncu_traffic_bytes("gru"),
+                            traffic_source="profiles/r02_gru_traffic.json: dram bytes of one `ncu --set full` capture of the update's launches (tools/ncu_traffic.py), not of this run",
+                            flops=fl,
                             kernel_ms=round(g_ms, 5), kernel_ms_in_step_upper_bound=(round(in_ms, 5) if in_ms else None),
                             peak_source=tsrc,
                             note="the update operator is the largest share of a step; a chain of 19 dependent Linear layers "

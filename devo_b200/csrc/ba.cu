@@ -1174,6 +1174,15 @@ int devo_ba_debug_clocks(long long* out) { return (int)cudaMemcpyFromSymbol(out,
 
 size_t devo_ba_workspace(int E, int n_free_poses) { return ba_layout(E, n_free_poses).total; }
 
+// The two clears are ONE 32-thread kernel, not memset nodes: inside a captured step a memset node runs on a copy engine,
+// and when the caller uploads the next step's inputs meanwhile (one 5 MB H2D copy, ~100 us) the 4-byte memset queued
+// behind that copy and held the update operator back by 35-60 us per step (tools/e2e_probe.py).
+__global__ void ba_prepare_kernel(int32_t* __restrict__ status, int32_t* __restrict__ ticket) {
+  if (threadIdx.x == 0) *status = 0;
+  if (ticket != nullptr) ticket[threadIdx.x] = 0;
+}
+
+
 static int ba_forward_impl(float* poses, float* patches, const float* intrinsics, const float* target,
                            const float* weight, const float* lmbda, const int64_t* ii, const int64_t* jj,
                            const int64_t* kk, int E, int n_poses, int n_patches, int P, int t0, int t1,
@@ -1182,8 +1191,10 @@ static int ba_forward_impl(float* poses, float* patches, const float* intrinsics
                            const int32_t* ext_ngroups, bool prepared = false, int32_t* status_or = nullptr) {
   cudaStream_t s = (cudaStream_t)stream;
   DEVO_REQUIRE(status != nullptr, DEVO_EINVAL, "ba_forward: status pointer is NULL");
-  if (!prepared) DEVO_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), s));
-  if (E <= 0 || iterations <= 0) return DEVO_OK;
+  if (E <= 0 || iterations <= 0) {
+    if (!prepared) { ba_prepare_kernel<<<1, 32, 0, s>>>(status, nullptr); DEVO_LAUNCH_CHECK("ba_prepare"); }
+    return DEVO_OK;
+  }
   int nfree = t1 - t0;
   if (nfree < 0) nfree = 0;
   DEVO_REQUIRE(P >= 1 && P <= 8, DEVO_EINVAL, "ba_forward: patch size %d unsupported", P);
@@ -1234,7 +1245,10 @@ static int ba_forward_impl(float* poses, float* patches, const float* intrinsics
   DEVO_REQUIRE(ept <= 24, DEVO_ECAPACITY, "ba_forward: system too large (%d entries)", L.nent);
   const size_t smem_solve = ((size_t)n6 * (n6 + 1) / 2 + (n6 + 1) + 18 * (n6 + 1) + 8) * 8;   // A, y, 2 column blocks + W
   DEVO_REQUIRE(smem_solve <= smem_acc, DEVO_ECAPACITY, "ba_forward: solver does not fit the accumulate CTA's shared memory");
-  if (!prepared) DEVO_CUDA(cudaMemsetAsync(w + L.ticket, 0, 4 * 32, s));
+  if (!prepared) {     // status word + ticket area: one small kernel (no copy-engine work, see devo_ba_prepare)
+    ba_prepare_kernel<<<1, 32, 0, s>>>(status, (int32_t*)(w + L.ticket));
+    DEVO_LAUNCH_CHECK("ba_prepare");
+  }
   for (int itr = 0; itr < iterations; itr++) {
     ACC_DISPATCH(itr > 0 ? 1 : 0, 1, itr);   // accumulate + (last CTA) solve + retraction
   }
@@ -1401,15 +1415,6 @@ int devo_ba_forward_planned(float* poses, float* patches, const float* intrinsic
 // run); devo_ba_forward_prepared then launches nothing but the iterations, reads the plan ahead of the programmatic wait
 // from the first iteration on (the caller vouches the plan is older than the preceding kernel of the stream) and folds
 // the status into `status_or` (may be NULL) in its last launch.
-//
-// The two clears are ONE 32-thread kernel, not memset nodes: inside a captured step a memset node runs on a copy engine,
-// and when the caller uploads the next step's inputs meanwhile (one 5 MB H2D copy, ~100 us) the 4-byte memset queued
-// behind that copy and held the update operator back by 35-60 us per step (tools/e2e_probe.py).
-__global__ void ba_prepare_kernel(int32_t* __restrict__ status, int32_t* __restrict__ ticket) {
-  if (threadIdx.x == 0) *status = 0;
-  if (ticket != nullptr) ticket[threadIdx.x] = 0;
-}
-
 int devo_ba_prepare(void* workspace, size_t workspace_bytes, int E, int n_free_poses, int32_t* status, void* stream) {
   DEVO_REQUIRE(status != nullptr, DEVO_EINVAL, "ba_prepare: status pointer is NULL");
   cudaStream_t s = (cudaStream_t)stream;
