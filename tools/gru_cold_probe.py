@@ -203,3 +203,22 @@ burst("20 x (flush + weights + state + corr + ctx + replay)", lambda: flush_then
 burst("20 x (flush + weights + state + corr + ctx + workspace + replay)", lambda: flush_then([op.packed.W, op.packed.W0, scratch.buf, op.corr_buf, op.imap, op._gru_ws]))
 print("sizes (MB): W %.1f W0 %.1f state %.1f corr %.1f imap %.1f workspace %.1f" % tuple(
     x.numel() * x.element_size() / 1e6 for x in (op.packed.W, op.packed.W0, scratch.buf, op.corr_buf, op.imap, op._gru_ws)))
+
+# ---- code vs data: a SECOND operator instance (own state / rows / workspace, the same packed weights and the same kernels)
+# replayed after the flush warms code + weights but none of the first instance's data
+op2, _, wl2 = build_engine(dev)
+load_state(op2, wl2, dev)
+op2.packed = op.packed
+op2.step()
+torch.cuda.synchronize()
+scratch2 = GruState(op2.E, dev).set(op2.get_net())
+g2 = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g2), torch.no_grad():
+    op2.update.forward_mma(None, op2.imap, op2.kk, op2.corr_buf, op2.plan_kk, op2.plan_ij, op2.Np, op2.Nf * op2.Nf, op2.packed,
+                           workspace=op2._gru_ws, state=scratch2, tile_local=op2.tile_local)
+mine = [scratch.buf, op.corr_buf, op.imap, op._gru_ws, op.plan_kk.perm, op.plan_kk.gid, op.plan_ij.perm, op.plan_ij.gid, op.plan_kk.ix, op.plan_kk.jx, op.kk]
+burst("20 x (flush + replay)                                       [all cold]", lambda: flush.zero_())
+burst("20 x (flush + other instance's replay + replay)    [code + weights warm]", lambda: (flush.zero_(), g2.replay()))
+burst("20 x (flush + ld.cg re-read of own data + replay)           [data warm]", lambda: flush_then(mine + [op.packed.W, op.packed.W0]))
+burst("20 x (flush + other instance + re-read of own data + replay) [all warm]", lambda: (flush.zero_(), g2.replay(), [dbg(1, 1024, 1184, x.view(torch.uint8).view(-1)) for x in mine]))
+burst("20 x (other instance's replay + replay), no flush", lambda: g2.replay())
