@@ -14,9 +14,10 @@ before update(), devo.py:523-527).  The whole step is one CUDA-graph replay.
             data-path collective: "weak" scaling); max over ranks.
   e2e       same step through the public API with HOST (pinned) inputs: H2D of the new frame's features
             (copy stream, double-buffered) and of the state the operator takes (poses, patches, intrinsics,
-            edge list), the step, D2H of the updated poses/depths; wall clock.
-  roofline  the dominant kernels of ours, the fused update operator (gru_mma_kernel x5 + 2 segment reductions: ~45 % of a
-            step): dense-layer FLOPs / measured duration vs the measured sustained bf16 tensor peak; `roofline_corr`:
+            edge list), the step, D2H of the updated poses + patches (written into the pinned buffer by a copy kernel of
+            the step's graph: no copy-engine node queues behind the next step's upload); wall clock.
+  roofline  the dominant kernels of ours, the fused update operator (gru_mma_kernel x2 + 1 segment reduction on the
+            patch-major S8 edge list: ~45 % of a step): dense-layer FLOPs / measured duration vs the measured sustained bf16 tensor peak; `roofline_corr`:
             the correlation lookup's algorithmic bytes / duration vs the measured HBM peak (MEASURED_PEAKS.json).
   per_op_us each stage of the step alone;  ref_cuda: the reference's own CUDA extensions (oracle/_ref, compiled from
             /root/reference) timed on the same GPU and inputs -- a baseline measurement, never on the product path;
